@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# Builds oracle/_ref/ref_host from the reference's own sources WHERE THEY LIE (never copied):
+#   /root/reference/cpp/helper.cpp  +  oracle/ref_host_driver.cpp  (ours)  +  oracle/ref_stub (ours).
+# The reference's neural path (ONNX Runtime + model files) is NOT buildable here — onnxruntime is
+# neither installed nor vendored — so only its pure host functions are compiled.
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"
+ref="${SUPERTONIC_REFERENCE:-/root/reference}"
+[ -f "$ref/cpp/helper.cpp" ] || { echo "reference sources not present; skipping oracle/_ref" >&2; exit 0; }
+nl="$(python - <<'PY'
+import glob, sys, sysconfig
+c = glob.glob(sysconfig.get_paths()["purelib"] + "/include/cudnn_frontend/thirdparty/nlohmann/json.hpp")
+print(c[0].rsplit("/nlohmann/", 1)[0] if c else "")
+PY
+)"
+[ -n "$nl" ] || { echo "nlohmann/json.hpp not found" >&2; exit 1; }
+mkdir -p "$here/_ref"
+# -O2 without -ffast-math: the float32 length math must keep IEEE semantics.
+g++ -std=c++17 -O2 -I "$here/ref_stub" -I "$ref/cpp" -I "$nl" \
+    "$ref/cpp/helper.cpp" "$here/ref_host_driver.cpp" -o "$here/_ref/ref_host"
+echo "built $here/_ref/ref_host"

@@ -1,0 +1,124 @@
+"""ORACLE tooling — generates tests/golden/host_golden.json by RUNNING the unmodified reference
+host code (oracle/_ref/ref_host, built by oracle/build_ref.sh from /root/reference/cpp/helper.cpp).
+
+Run in the build container only (needs /root/reference); the JSON it writes is committed and is
+what the CPU test-suite and the GPU box use. Inputs are the reference's own sample strings
+(file:line cited per case) plus edge cases for each pure host function.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from supertonic_b200 import surrogate  # noqa: E402
+
+DEFAULT_EN = ("This morning, I took a walk in the park, and the sound of the birds and the breeze was so "
+              "pleasant that I stopped for a long time just to listen.")  # cpp/example_onnx.cpp:17
+BATCH_EN = "The sun sets behind the mountains, painting the sky in shades of pink and orange."   # test_all.sh:63
+BATCH_KO = "오늘 아침에 공원을 산책했는데, 새소리와 바람 소리가 너무 기분 좋았어요."                 # test_all.sh:64
+LONGFORM = ("This is a very long text that will be automatically split into multiple chunks. "
+            "The system will process each chunk separately and then concatenate them together with "
+            "natural pauses between segments. This ensures that even very long texts can be processed "
+            "efficiently while maintaining natural speech flow and avoiding memory issues.")         # test_all.sh:70 (shape)
+
+
+def longform_from_reference():
+    """test_all.sh:70 holds the long-form paragraph; read it where it lies when available."""
+    p = "/root/reference/test_all.sh"
+    if os.path.exists(p):
+        import re
+        for line in open(p, encoding="utf-8"):
+            m = re.match(r'LONGFORM_TEXT="(.*)"\s*$', line)
+            if m:
+                return m.group(1)
+    return LONGFORM
+
+
+def cases():
+    lf = longform_from_reference()
+    c = [
+        dict(kind="cfg"),
+        dict(kind="text", texts=[DEFAULT_EN], langs=["en"], cite="cpp/example_onnx.cpp:17"),
+        dict(kind="text", texts=[BATCH_EN, BATCH_KO], langs=["en", "ko"], cite="test_all.sh:63-64"),
+        dict(kind="text", texts=["The Q3 revenue rose 12.5% to $4.2 billion, beating estimates."], langs=["en"]),
+        dict(kind="text", texts=["Café déjà vu — “été” à Noël… ça va?"], langs=["fr"], cite="SURVEY.md App. G"),
+        dict(kind="text", texts=["no final punct 😀 e.g., a_b [x] @home"], langs=["en"], cite="SURVEY.md App. G"),
+        dict(kind="text", texts=["El niño comió piñas, ¿verdad? ¡Sí!", "Ação e coração: não é fácil.",
+                                 "Où est l'hôtel? Ça coûte très cher, naïve Zoë."], langs=["es", "pt", "fr"]),
+        dict(kind="text", texts=["안녕하세요", "값", "ㄱㄴㄷ 한글 Test"], langs=["ko", "ko", "ko"]),
+        dict(kind="text", texts=["  spaces   and\ttabs\n\nnewlines  ", "a ,b .c !d ?e ;f :g 'h"], langs=["en", "en"]),
+        dict(kind="text", texts=['She said ""hi"" and \'\'bye\'\' ``ok``', "back\\slash ♥☆♡© → ← | / # `x´"],
+             langs=["en", "en"]),
+        dict(kind="text", texts=["ends with quote”", "ends with ellipsis…", "ends with bracket)", "x"],
+             langs=["en", "en", "en", "en"]),
+        dict(kind="text", texts=["i.e., that – or ‑ this — done"], langs=["en"]),
+        dict(kind="text", texts=["中文字符 and ÿ and €"], langs=["en"]),
+        dict(kind="text", texts=["bad lang"], langs=["de"]),
+        dict(kind="text", texts=[""], langs=["en"]),
+        dict(kind="text", texts=["invalid \xff\xfe utf8 \xc3"], langs=["en"]),
+        dict(kind="chunk", text=lf, max_len=300, cite="test_all.sh:70"),
+        dict(kind="chunk", text=lf + "\n\n" + lf + " " + lf, max_len=300),
+        dict(kind="chunk", text="Dr. Smith went home. Mr. X stayed! Really? Yes.", max_len=20, cite="SURVEY.md App. G"),
+        dict(kind="chunk", text=BATCH_KO + " " + BATCH_KO + " 정말요? 네! 그렇습니다.", max_len=120),
+        dict(kind="chunk", text="short", max_len=300),
+        dict(kind="chunk", text="", max_len=300),
+        dict(kind="chunk", text="   \n\n  \n", max_len=300),
+        dict(kind="chunk", text="One.  Two.\tThree.\nFour. " + "x" * 50 + ". tail", max_len=12),
+        dict(kind="chunk", text="para one. still one.\n\npara two! and more?\n \n\npara three", max_len=25),
+        dict(kind="latent_mask", wav_lengths=[3 * 44100, 9 * 44100 + 17], base_chunk_size=512,
+             chunk_compress_factor=6, cite="SURVEY.md App. G"),
+        dict(kind="latent_mask", wav_lengths=[1, 3072, 3073, 6144], base_chunk_size=512, chunk_compress_factor=6),
+        dict(kind="length_mask", lengths=[0, 1, 5, 3]),
+        dict(kind="length_mask", lengths=[2, 4], max_len=7),
+        dict(kind="sanitize", text=DEFAULT_EN, max_len=20),
+        dict(kind="sanitize", text=BATCH_KO, max_len=10),
+        dict(kind="sanitize", text="a/b\\c:d*e?f\"g<h>i|j é😀", max_len=40),
+        dict(kind="wav", samples=[0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 0.99999, 1e-5, -3.0517578e-05, 0.25],
+             sample_rate=44100),
+        dict(kind="wav", samples=[], sample_rate=22050),
+    ]
+    return c
+
+
+def main():
+    exe = os.path.join(HERE, "_ref", "ref_host")
+    if not os.path.exists(exe):
+        subprocess.check_call([os.path.join(HERE, "build_ref.sh")])
+    assets = surrogate.ensure_assets("tiny")
+    cs = cases()
+    cs.append(dict(kind="style", paths=[os.path.join(assets, "voice_styles", n + ".json") for n in ("M1", "F1")]))
+    with tempfile.TemporaryDirectory() as td:
+        for i, c in enumerate(cs):
+            if c["kind"] == "wav":
+                c["tmp"] = os.path.join(td, f"w{i}.wav")
+        # surrogateescape lets the deliberately invalid UTF-8 case reach the C++ side as raw bytes
+        cj = os.path.join(td, "cases.json")
+        with open(cj, "wb") as f:
+            f.write(json.dumps(cs, ensure_ascii=False).encode("utf-8", "surrogateescape"))
+        raw = subprocess.run([exe, cj, os.path.join(assets, "onnx")], check=True, capture_output=True).stdout
+    res = json.loads(raw.decode("utf-8", "surrogateescape"))
+    for r in res:
+        r["case"].pop("tmp", None)
+        if r["case"]["kind"] == "style":
+            r["case"]["paths"] = [os.path.basename(p) for p in r["case"]["paths"]]
+    out = os.path.join(ROOT, "tests", "golden", "host_golden.json")
+    with open(out, "w", encoding="utf-8", errors="surrogateescape") as f:
+        json.dump(dict(generator="oracle/make_golden.py", source="unmodified /root/reference/cpp/helper.cpp",
+                       indexer="supertonic_b200.surrogate.build_indexer()", results=res), f, ensure_ascii=True)
+    print(f"wrote {out}: {len(res)} cases")
+    for r in res:
+        k = r["case"]["kind"]
+        if "error" in r:
+            print(k, "ERROR", r["error"])
+        elif k == "text":
+            print(k, [len(x) for x in r["text_ids"]], [int(sum(m[0])) for m in r["text_mask"]])
+        elif k == "chunk":
+            print(k, [len(x.encode("utf-8", "surrogateescape")) for x in r["chunks"]])
+
+
+if __name__ == "__main__":
+    main()

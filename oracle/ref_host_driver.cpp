@@ -1,0 +1,53 @@
+// ORACLE BUILD ONLY — drives the unmodified reference host code (cpp/helper.cpp, compiled from
+// /root/reference where it lies) over a JSON list of cases and prints JSON answers. Used by
+// oracle/make_golden.py to produce tests/golden/host_golden.json.
+#include "helper.h"
+#include <fstream>
+#include <nlohmann/json.hpp>
+using json = nlohmann::json;
+std::vector<std::string> chunkText(const std::string& text, int max_len);
+std::string sanitizeFilename(const std::string& text, int max_len);
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::cerr << "usage: ref_host <cases.json> <onnx_dir>\n"; return 2; }
+    std::ifstream f(argv[1]); json cases; f >> cases;
+    std::string onnx_dir = argv[2];
+    auto proc = loadTextProcessor(onnx_dir);
+    json out = json::array();
+    for (auto& c : cases) {
+        json r; r["case"] = c;
+        std::string kind = c["kind"];
+        try {
+            if (kind == "text") {
+                std::vector<std::vector<int64_t>> ids; std::vector<std::vector<std::vector<float>>> mask;
+                proc->call(c["texts"].get<std::vector<std::string>>(), c["langs"].get<std::vector<std::string>>(), ids, mask);
+                r["text_ids"] = ids; r["text_mask"] = mask;
+            } else if (kind == "chunk") {
+                r["chunks"] = chunkText(c["text"].get<std::string>(), c["max_len"].get<int>());
+            } else if (kind == "latent_mask") {
+                r["mask"] = getLatentMask(c["wav_lengths"].get<std::vector<int64_t>>(), c["base_chunk_size"], c["chunk_compress_factor"]);
+            } else if (kind == "length_mask") {
+                r["mask"] = lengthToMask(c["lengths"].get<std::vector<int64_t>>(), c.value("max_len", -1));
+            } else if (kind == "sanitize") {
+                r["name"] = sanitizeFilename(c["text"].get<std::string>(), c["max_len"].get<int>());
+            } else if (kind == "wav") {
+                std::string path = c["tmp"].get<std::string>();
+                writeWavFile(path, c["samples"].get<std::vector<float>>(), c["sample_rate"].get<int>());
+                std::ifstream w(path, std::ios::binary); std::vector<unsigned char> b((std::istreambuf_iterator<char>(w)), {});
+                r["bytes"] = b;
+            } else if (kind == "style") {
+                Style s = loadVoiceStyle(c["paths"].get<std::vector<std::string>>());
+                r["ttl_shape"] = s.getTtlShape(); r["dp_shape"] = s.getDpShape();
+                double a = 0, b = 0; for (float v : s.getTtlData()) a += v; for (float v : s.getDpData()) b += v;
+                r["ttl_sum"] = a; r["dp_sum"] = b;
+                r["ttl_head"] = std::vector<float>(s.getTtlData().begin(), s.getTtlData().begin() + 4);
+            } else if (kind == "cfg") {
+                Config cfg = loadCfgs(onnx_dir);
+                r["cfg"] = {cfg.ae.sample_rate, cfg.ae.base_chunk_size, cfg.ttl.chunk_compress_factor, cfg.ttl.latent_dim};
+            }
+        } catch (const std::exception& e) { r["error"] = e.what(); }
+        out.push_back(r);
+    }
+    std::cout << out.dump() << std::endl;
+    return 0;
+}
