@@ -1,0 +1,155 @@
+/*
+ * libsupertonic_cuda — C ABI of the B200-native (sm_100a) Supertonic synthesis forward pass.
+ *
+ * Drop-in boundary for the reference's four ONNX Runtime sessions
+ * (zhoubin-me/supertonic cpp/helper.cpp: Ort::Session::Run at :519-523 duration_predictor,
+ * :552-556 text_encoder, :643-647 vector_estimator, :668-672 vocoder; sessions created at
+ * :784-795). Plain pointers and sizes only; every pointer is HOST memory owned and kept alive
+ * by the caller for the duration of the call (same ownership as the Ort::Value inputs the
+ * reference builds at cpp/helper.cpp:495-509, 574-580, 604-618); outputs are written into
+ * caller-provided host buffers. All tensors are dense row-major with the reference's layouts.
+ *
+ * Errors: every function returns STC_OK (0) or a negative status; the message is available via
+ * stc_last_error(). There is NO CPU fallback: without a CUDA device stc_create fails.
+ *
+ * Threading: one handle per GPU; calls on one handle are serialised by the caller (the reference
+ * is single-caller too: globals at cpp/helper.cpp:18-19, statics at :931-934). Distinct handles
+ * are fully concurrent.
+ */
+#ifndef SUPERTONIC_CUDA_H_
+#define SUPERTONIC_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct stc_handle stc_handle;
+
+enum {
+    STC_OK = 0,
+    STC_ERR_INVALID = -1,   /* bad argument / shape mismatch (reference: std::runtime_error) */
+    STC_ERR_IO = -2,        /* asset file missing or malformed (reference: cpp/helper.cpp:805, 1057) */
+    STC_ERR_CUDA = -3,      /* CUDA runtime failure or no usable device */
+    STC_ERR_UNSUPPORTED = -4,
+    STC_ERR_CAPACITY = -5   /* caller buffer too small */
+};
+
+/* GEMM arithmetic for the dense contractions. */
+enum {
+    STC_PREC_DEFAULT = 0,   /* = STC_PREC_BF16X3 unless env STC_PRECISION says otherwise */
+    STC_PREC_BF16X3 = 1,    /* tcgen05 kind::f16, 3-term split-bf16 products, fp32 accumulate in TMEM */
+    STC_PREC_FP32_SIMT = 2  /* CUDA-core fp32 FMA GEMM (debug cross-check; not the product path) */
+};
+
+/* Model geometry, read from onnx_dir/tts.json (reference loadCfgs, cpp/helper.cpp:801-818) and
+ * from the graphs' I/O signatures. */
+typedef struct stc_config {
+    int32_t sample_rate;            /* ae.sample_rate */
+    int32_t base_chunk_size;        /* ae.base_chunk_size */
+    int32_t chunk_compress_factor;  /* ttl.chunk_compress_factor */
+    int32_t latent_dim;             /* ttl.latent_dim */
+    int32_t latent_channels;        /* D = latent_dim * chunk_compress_factor (cpp/helper.cpp:439) */
+    int32_t chunk_size;             /* cs = base_chunk_size * chunk_compress_factor (:437) */
+    int32_t text_emb_channels;      /* C of text_emb[B,C,T] */
+    int32_t style_ttl_tokens, style_ttl_dim;   /* style_ttl[B,S,Cs] */
+    int32_t style_dp_tokens, style_dp_dim;     /* style_dp[B,e1,e2] */
+    int32_t vocab_size;
+} stc_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Replaces loadOnnxAll (cpp/helper.cpp:784-795) + the use_gpu branch of loadTextToSpeech
+ * (:903-937, which throws today): parses the four .onnx files in `onnx_dir`, uploads their
+ * initializers to `device`, builds the kernel plan. */
+int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out);
+void stc_destroy(stc_handle* h);
+/* Thread-local message of the last failing call (valid with h == NULL for stc_create failures). */
+const char* stc_last_error(const stc_handle* h);
+int stc_get_config(const stc_handle* h, stc_config* out);
+
+/* ---- parity layer: 1:1 with the four Session::Run calls, host pointers in/out ---------------- */
+
+/* duration_predictor.onnx — cpp/helper.cpp:512-526. text_ids[B,T] int64, style_dp[B,e1,e2],
+ * text_mask[B,1,T] -> duration[B] seconds (before the /speed of :529-531). */
+int stc_duration(stc_handle* h, const int64_t* text_ids, const float* style_dp, const float* text_mask,
+                 int B, int T, float* duration_out);
+
+/* text_encoder.onnx — cpp/helper.cpp:545-556, 583-587. -> text_emb[B,C,T]; shape_out = {B,C,T}. */
+int stc_text_encode(stc_handle* h, const int64_t* text_ids, const float* style_ttl, const float* text_mask,
+                    int B, int T, float* text_emb_out, int64_t shape_out[3]);
+
+/* vector_estimator.onnx — cpp/helper.cpp:620-658: ONE Euler step; the output is the updated latent.
+ * noisy_latent[B,D,L], text_emb[B,C,T], style_ttl[B,S,Cs], text_mask[B,1,T], latent_mask[B,1,L],
+ * total_step[B], current_step[B] (float32, as the reference passes them :573-618) -> denoised[B,D,L]. */
+int stc_vector_step(stc_handle* h, const float* noisy_latent, const float* text_emb, const float* style_ttl,
+                    const float* text_mask, const float* latent_mask, const float* total_step,
+                    const float* current_step, int B, int L, int T, float* denoised_out);
+
+/* vocoder.onnx — cpp/helper.cpp:662-682. latent[B,D,L] -> wav[B, L*cs]. */
+int stc_vocode(stc_handle* h, const float* latent, int B, int L, float* wav_out);
+
+/* ---- fast layer: the whole _infer body (cpp/helper.cpp:488-682) device-resident --------------- */
+
+/* DP -> /speed -> float32 length math of sampleNoisyLatent (:424-467) -> TE -> noise*mask ->
+ * total_step x VE -> vocoder, one device->host sync for the data-dependent latent length.
+ *
+ *   noise: NULL -> device Philox N(0,1) keyed by (seed, utterance index, channel, frame);
+ *          else host float32 [B][D][noise_ld] with noise_ld >= the L the call will compute
+ *          (the deterministic-noise hook the reference lacks: its RNG is unseedable, :442-443).
+ *   wav_out: [B][wav_ld] floats, wav_ld >= L*cs else STC_ERR_CAPACITY (L_out is still written, so
+ *          the caller can retry). Row b holds the full untrimmed L*cs samples like result.wav (:679).
+ *   duration_out[B]: seconds after /speed (:529-531). wav_lengths_out[B] (optional): (int64)(d*sr) (:434).
+ *   latent_out (optional): final latent [B][D][L] (for parity tests).
+ */
+int stc_synthesize(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                   const float* style_dp, int B, int T, int total_step, float speed,
+                   const float* noise, int64_t noise_ld, uint64_t seed,
+                   float* wav_out, int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out,
+                   int64_t* L_out, float* latent_out);
+
+/* Same work, but inputs already resident in device memory and outputs left there (bench `value`
+ * leg: no host<->device traffic in the timed region). Pointers are DEVICE pointers except L_out.
+ * wav_dev must hold B*wav_ld floats. */
+int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev,
+                          const float* style_ttl_dev, const float* style_dp_dev, int B, int T,
+                          int total_step, float speed, uint64_t seed, float* wav_dev, int64_t wav_ld,
+                          float* duration_dev, int64_t* L_out);
+
+/* ---- host front-end (kept on the host, semantics of the C++ reference) ----------------------- */
+
+/* UnicodeProcessor::call (cpp/helper.cpp:355-390) for n texts. Two-pass: call with text_ids == NULL to
+ * get T_out (max token count), then with buffers text_ids[n*T], text_mask[n*T]. langs: "en" ... */
+int stc_text_to_ids(stc_handle* h, const char* const* texts, const char* const* langs, int n,
+                    int64_t* text_ids, float* text_mask, int64_t T_cap, int64_t* T_out);
+
+/* The same front-end without a GPU handle (host-only: usable on machines with no CUDA device). */
+typedef struct stc_frontend stc_frontend;
+int stc_frontend_open(const char* unicode_indexer_json, stc_frontend** out);   /* loadTextProcessor, cpp/helper.cpp:820-823 */
+void stc_frontend_close(stc_frontend* fe);
+int stc_frontend_text_to_ids(const stc_frontend* fe, const char* const* texts, const char* const* langs, int n,
+                             int64_t* text_ids, float* text_mask, int64_t T_cap, int64_t* T_out);
+
+/* chunkText (cpp/helper.cpp:1117-1186). Writes chunk byte offsets/lengths into `text` order copies:
+ * out_buf receives the chunks back to back, NUL-separated; returns count in n_out. */
+int stc_chunk_text(const char* text, int max_len, char* out_buf, size_t out_cap, size_t* out_len, int* n_out);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+
+/* Kernels launched by this handle since creation (bench `gpu_launches`). */
+uint64_t stc_launch_count(const stc_handle* h);
+/* Use CUDA graphs for the fast layer (default 1). */
+int stc_set_graphs(stc_handle* h, int enabled);
+/* cudaStream_t the handle launches on (as void*), for callers that time with CUDA events. */
+void* stc_stream(stc_handle* h);
+/* Device-side timing of the most recent stc_synthesize* call: milliseconds per stage
+ * {dp, te, ve_total, vocoder, whole}. Requires stc_set_profile(h,1) (adds event records). */
+int stc_set_profile(stc_handle* h, int enabled);
+int stc_last_stage_ms(const stc_handle* h, float out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERTONIC_CUDA_H_ */

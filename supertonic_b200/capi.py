@@ -1,0 +1,248 @@
+"""ctypes binding of libsupertonic_cuda.so (include/supertonic_cuda.h).
+
+There is no fallback: if the shared library has not been built (``__graft_entry__.build()`` or
+``make -C supertonic_b200/csrc``) importing this module raises, and without a CUDA device
+``Engine(...)`` raises with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsupertonic_cuda.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing — build it first (python -c 'import __graft_entry__ as g; g.build()'); "
+                      "supertonic_b200 has no CPU fallback for the neural path")
+lib = C.CDLL(LIB_PATH)
+
+STC_OK = 0
+PREC_DEFAULT, PREC_BF16X3, PREC_FP32_SIMT = 0, 1, 2
+ERR_CAPACITY = -5
+
+
+class StcConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "sample_rate", "base_chunk_size", "chunk_compress_factor", "latent_dim", "latent_channels", "chunk_size",
+        "text_emb_channels", "style_ttl_tokens", "style_ttl_dim", "style_dp_tokens", "style_dp_dim", "vocab_size")]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_pf = C.POINTER(C.c_float)
+_pi64 = C.POINTER(C.c_int64)
+_SIGS = {
+    "stc_create": (_i, [C.c_char_p, _i, _i, C.POINTER(_vp)]),
+    "stc_destroy": (None, [_vp]),
+    "stc_last_error": (C.c_char_p, [_vp]),
+    "stc_get_config": (_i, [_vp, C.POINTER(StcConfig)]),
+    "stc_duration": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "stc_text_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "stc_vector_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "stc_vocode": (_i, [_vp, _vp, _i, _i, _vp]),
+    "stc_synthesize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
+    "stc_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
+    "stc_frontend_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "stc_frontend_close": (None, [_vp]),
+    "stc_frontend_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
+    "stc_chunk_text": (_i, [C.c_char_p, _i, _vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(_i)]),
+    "stc_launch_count": (C.c_uint64, [_vp]),
+    "stc_set_graphs": (_i, [_vp, _i]),
+    "stc_stream": (_vp, [_vp]),
+    "stc_set_profile": (_i, [_vp, _i]),
+    "stc_last_stage_ms": (_i, [_vp, _vp]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header and library out of sync
+    _fn.restype, _fn.argtypes = _res, _args
+
+EXPORTED = sorted(_SIGS)
+
+
+class StcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[stc {code}] {msg}")
+        self.code = code
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _cf(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _b(s) -> bytes:
+    return s if isinstance(s, bytes) else s.encode("utf-8", "surrogateescape")
+
+
+def _texts_to_ids(fn, handle, texts: Sequence, langs: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    n = len(texts)
+    ta = (C.c_char_p * n)(*[_b(t) for t in texts])
+    la = (C.c_char_p * n)(*[_b(l) for l in langs])
+    T = C.c_int64(0)
+    rc = fn(handle, ta, la, n, None, None, 0, C.byref(T))
+    if rc != STC_OK:
+        raise StcError(rc, lib.stc_last_error(None).decode())
+    ids = np.zeros((n, T.value), np.int64)
+    mask = np.zeros((n, 1, T.value), np.float32)
+    rc = fn(handle, ta, la, n, _ptr(ids), _ptr(mask), T.value, C.byref(T))
+    if rc != STC_OK:
+        raise StcError(rc, lib.stc_last_error(None).decode())
+    return ids, mask
+
+
+def chunk_text(text, max_len: int) -> List[bytes]:
+    """chunkText of the C++ reference (cpp/helper.cpp:1117-1186) → list of UTF-8 byte strings."""
+    raw = _b(text)
+    if b"\0" in raw:
+        raise ValueError("text contains NUL")
+    need, n = C.c_size_t(0), C.c_int(0)
+    cap = len(raw) + 64
+    while True:
+        buf = C.create_string_buffer(cap)
+        rc = lib.stc_chunk_text(raw, max_len, buf, cap, C.byref(need), C.byref(n))
+        if rc == STC_OK:
+            parts = buf.raw[:need.value].split(b"\0")[:-1]
+            return parts[:n.value] if n.value else [b""]
+        if rc != ERR_CAPACITY:
+            raise StcError(rc, lib.stc_last_error(None).decode())
+        cap = need.value + 16
+
+
+class Frontend:
+    """Host-only text front-end (no GPU needed): UnicodeProcessor::call of the C++ reference."""
+
+    def __init__(self, unicode_indexer_json: str):
+        self._h = _vp()
+        rc = lib.stc_frontend_open(_b(unicode_indexer_json), C.byref(self._h))
+        if rc != STC_OK:
+            raise StcError(rc, lib.stc_last_error(None).decode())
+
+    def __call__(self, texts, langs):
+        return _texts_to_ids(lib.stc_frontend_text_to_ids, self._h, texts, langs)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.stc_frontend_close(self._h)
+            self._h = None
+
+
+class Engine:
+    """One handle == one GPU replica of the four graphs (reference: loadOnnxAll, cpp/helper.cpp:784-795)."""
+
+    def __init__(self, onnx_dir: str, device: int = 0, precision: int = PREC_DEFAULT):
+        self._h = _vp()
+        rc = lib.stc_create(_b(onnx_dir), device, precision, C.byref(self._h))
+        if rc != STC_OK:
+            self._h = None
+            raise StcError(rc, lib.stc_last_error(None).decode())
+        self.cfg = StcConfig()
+        lib.stc_get_config(self._h, C.byref(self.cfg))
+        self.onnx_dir = onnx_dir
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.stc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != STC_OK:
+            raise StcError(rc, lib.stc_last_error(self._h).decode())
+
+    # ---- parity layer (1:1 with the reference's four Session::Run calls)
+    def duration(self, text_ids, style_dp, text_mask) -> np.ndarray:
+        ids, sty, m = _cf(text_ids, np.int64), _cf(style_dp, np.float32), _cf(text_mask, np.float32)
+        B, T = ids.shape
+        out = np.empty((B,), np.float32)
+        self._chk(lib.stc_duration(self._h, _ptr(ids), _ptr(sty), _ptr(m), B, T, _ptr(out)))
+        return out
+
+    def text_encode(self, text_ids, style_ttl, text_mask) -> np.ndarray:
+        ids, sty, m = _cf(text_ids, np.int64), _cf(style_ttl, np.float32), _cf(text_mask, np.float32)
+        B, T = ids.shape
+        out = np.empty((B, self.cfg.text_emb_channels, T), np.float32)
+        shp = np.zeros(3, np.int64)
+        self._chk(lib.stc_text_encode(self._h, _ptr(ids), _ptr(sty), _ptr(m), B, T, _ptr(out), _ptr(shp)))
+        assert tuple(shp) == out.shape
+        return out
+
+    def vector_step(self, noisy_latent, text_emb, style_ttl, text_mask, latent_mask, total_step, current_step) -> np.ndarray:
+        x, te, sty = _cf(noisy_latent, np.float32), _cf(text_emb, np.float32), _cf(style_ttl, np.float32)
+        tm, lm = _cf(text_mask, np.float32), _cf(latent_mask, np.float32)
+        tot, cur = _cf(total_step, np.float32), _cf(current_step, np.float32)
+        B, D, L = x.shape
+        T = te.shape[2]
+        out = np.empty_like(x)
+        self._chk(lib.stc_vector_step(self._h, _ptr(x), _ptr(te), _ptr(sty), _ptr(tm), _ptr(lm), _ptr(tot), _ptr(cur),
+                                      B, L, T, _ptr(out)))
+        return out
+
+    def vocode(self, latent) -> np.ndarray:
+        x = _cf(latent, np.float32)
+        B, D, L = x.shape
+        out = np.empty((B, L * self.cfg.chunk_size), np.float32)
+        self._chk(lib.stc_vocode(self._h, _ptr(x), B, L, _ptr(out)))
+        return out
+
+    # ---- fast layer
+    def synthesize(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
+                   noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, wav_cap: Optional[int] = None):
+        """Whole `_infer` body (cpp/helper.cpp:488-682). Returns dict(wav[B, L*cs], duration[B], wav_lengths[B], L, latent?)."""
+        ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
+        sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
+        B, T = ids.shape
+        cs = self.cfg.chunk_size
+        nz, nld = None, 0
+        if noise is not None:
+            nz = _cf(noise, np.float32)
+            nld = nz.shape[2]
+        # duration is data dependent; start from a per-token guess and retry once with the exact size on overflow
+        cap = wav_cap or max(int(T * 0.12 * self.cfg.sample_rate / cs) + 8, 16) * cs
+        dur = np.empty((B,), np.float32)
+        wl = np.empty((B,), np.int64)
+        L = C.c_int64(0)
+        for _ in range(2):
+            wav = np.empty((B, cap), np.float32)
+            lat = np.empty((B, self.cfg.latent_channels, cap // cs), np.float32) if want_latent else None
+            rc = lib.stc_synthesize(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
+                                    _ptr(nz), nld, seed, _ptr(wav), cap, _ptr(dur), _ptr(wl), C.byref(L), _ptr(lat))
+            if rc == ERR_CAPACITY and L.value * cs > cap:
+                cap = L.value * cs
+                continue
+            self._chk(rc)
+            break
+        Lv = L.value
+        res = dict(wav=wav[:, :Lv * cs], duration=dur, wav_lengths=wl, L=Lv)
+        if want_latent:
+            res["latent"] = lat.reshape(-1)[:B * self.cfg.latent_channels * Lv].reshape(B, self.cfg.latent_channels, Lv)
+        return res
+
+    def text_to_ids(self, texts, langs):
+        return _texts_to_ids(lib.stc_text_to_ids, self._h, texts, langs)
+
+    # ---- introspection
+    @property
+    def launches(self) -> int:
+        return int(lib.stc_launch_count(self._h))
+
+    def set_graphs(self, on: bool):
+        lib.stc_set_graphs(self._h, int(on))
+
+    def set_profile(self, on: bool):
+        lib.stc_set_profile(self._h, int(on))
+
+    def stage_ms(self):
+        out = np.zeros(5, np.float32)
+        lib.stc_last_stage_ms(self._h, _ptr(out))
+        return dict(zip(("dp", "te", "ve", "vocoder", "whole"), out.tolist()))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.stc_stream(self._h) or 0)

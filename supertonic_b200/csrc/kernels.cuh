@@ -1,0 +1,451 @@
+// Bandwidth / CUDA-core kernels of libsupertonic_cuda (sm_100a).
+//
+// Activation layout everywhere: channels-last rows, x[(b*N + n)*C + c]  (N = frames or tokens);
+// masks are flat float [B*N] (the reference's [B,1,N] tensors are exactly that in memory,
+// cpp/helper.cpp:740-757). Templated on T = float (TE / VE / vocoder) or double (duration
+// predictor, evaluated in fp64 so the integer frame counts derived from it are reproducible —
+// DESIGN.md "bit-exact durations").
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stc {
+
+#define STC_DEVINL __device__ __forceinline__
+
+template <typename T> STC_DEVINL T t_erf(T x);
+template <> STC_DEVINL float t_erf<float>(float x) { return erff(x); }
+template <> STC_DEVINL double t_erf<double>(double x) { return erf(x); }
+template <typename T> STC_DEVINL T t_sqrt(T x);
+template <> STC_DEVINL float t_sqrt<float>(float x) { return sqrtf(x); }
+template <> STC_DEVINL double t_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> STC_DEVINL T t_exp(T x);
+template <> STC_DEVINL float t_exp<float>(float x) { return expf(x); }
+template <> STC_DEVINL double t_exp<double>(double x) { return exp(x); }
+
+// exact (erf) GELU in the operation order the graphs use: (x * (erf(x / sqrt2) + 1)) * 0.5
+template <typename T> STC_DEVINL T gelu_erf(T x) {
+    const T rsq2 = (T)1.41421354f;   // float32(sqrt(2)) as stored in the graph
+    return (x * (t_erf<T>(x / rsq2) + (T)1)) * (T)0.5;
+}
+
+template <typename T> STC_DEVINL T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+STC_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- GEMM operand stores ---------------------------------------------------------------------
+// Operands of the tensor-core GEMMs are kept as split bf16 pairs: v ~= hi + lo, hi = bf16(v),
+// lo = bf16(v - hi) (16 mantissa bits). Plain mode keeps T.
+struct SplitPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+
+template <typename T> struct OutPlain {
+    T* p;
+    STC_DEVINL void store(size_t i, T v) const { p[i] = v; }
+};
+struct OutSplit {
+    __nv_bfloat16* hi; __nv_bfloat16* lo;
+    STC_DEVINL void store(size_t i, float v) const {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+};
+
+// ---- embedding: out[row,:] = emb[ids[row],:] * mask[row]  (Gather -> Transpose -> Mul) ---------
+template <typename T>
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
+                             const float* __restrict__ mask, T* __restrict__ out, int rows, int C, int V) {
+    int row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (row >= rows) return;
+    int64_t id = ids[row];
+    if (id < 0 || id >= V) id = 0;
+    T m = (T)mask[row];
+    for (int c = threadIdx.x; c < C; c += 32) out[(size_t)row * C + c] = (T)emb[(size_t)id * C + c] * m;
+}
+
+// ---- x[row,:] = (x[row,:] + v[b,:]) * mask[row]   (style add in DP, time conditioning in VE) -----
+template <typename T>
+__global__ void add_rowvec_mask_kernel(T* __restrict__ x, const T* __restrict__ v, const float* __restrict__ mask,
+                                       int rows, int N, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * C) return;
+    int row = (int)(i / C), c = (int)(i % C);
+    x[i] = (x[i] + v[(size_t)(row / N) * C + c]) * (T)mask[row];
+}
+
+// ---- depthwise conv1d (+bias) -> LayerNorm over C, one warp per row ------------------------------
+// y[c] = b[c] + sum_k w[c,k] * x[n + k*dil - pad_left, c] (zero outside [0,N) of the same utterance);
+// out = (y-mean)/sqrt(var+eps)*g + beta.   K == 0 selects plain LayerNorm (no conv).
+template <typename T, int CPL, typename Out>
+__global__ void __launch_bounds__(256)
+dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wb,
+                 const float* __restrict__ g, const float* __restrict__ beta, Out out,
+                 int rows, int N, int K, int dil, int pad_left, float eps) {
+    constexpr int C = CPL * 32;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    int b = row / N, n = row - b * N;
+    T y[CPL];
+    if (K == 0) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) y[i] = x[(size_t)row * C + lane + 32 * i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) y[i] = (T)wb[lane + 32 * i];
+        for (int k = 0; k < K; ++k) {
+            int nn = n + k * dil - pad_left;
+            if (nn < 0 || nn >= N) continue;
+            const T* xr = x + ((size_t)b * N + nn) * C;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                int c = lane + 32 * i;
+                y[i] += (T)w[c * K + k] * xr[c];
+            }
+        }
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) s += y[i];
+    T mean = warp_sum<T>(s) / (T)C;
+    T v = 0;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { y[i] -= mean; v += y[i] * y[i]; }
+    T var = warp_sum<T>(v) / (T)C;
+    T den = t_sqrt<T>(var + (T)eps);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        int c = lane + 32 * i;
+        out.store((size_t)row * C + c, y[i] / den * (T)g[c] + (T)beta[c]);
+    }
+}
+
+// ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
+template <typename Out>
+__global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out.store(i, x[i]);
+}
+
+// ---- fp32/fp64 CUDA-core GEMM with the fused epilogue --------------------------------------------
+// out[M,N] = epi( A[M,K] (T, row-major, lda) * W[K,N] (float, row-major) )
+//   v = acc + bias[col]; if gelu: v = gelu(v); if scale: v *= scale[col]; if resid: v += resid[row,col];
+//   if mask: v *= mask[row]
+struct Epilogue {
+    const float* bias = nullptr;    // [N]
+    const float* scale = nullptr;   // [N] layer-scale gamma, or dt for the Euler update
+    const void* resid = nullptr;    // [M,N] (T)
+    const float* mask = nullptr;    // [M]
+    int gelu = 0;
+};
+
+template <typename T, typename Out>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, Out out, int ldo,
+                 int M, int N, int K, Epilogue ep) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM + 1];
+    __shared__ T Ws[BK][BN + 1];
+    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, 4x4 micro-tile
+    int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    T acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = threadIdx.x; i < BM * BK; i += 256) {
+            int r = i / BK, c = i % BK;
+            int gm = m0 + r, gk = k0 + c;
+            As[c][r] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : (T)0;
+        }
+        for (int i = threadIdx.x; i < BK * BN; i += 256) {
+            int r = i / BN, c = i % BN;
+            int gk = k0 + r, gn = n0 + c;
+            Ws[r][c] = (gk < K && gn < N) ? (T)W[(size_t)gk * N + gn] : (T)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            T a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * w[j];
+        }
+        __syncthreads();
+    }
+    const T* resid = static_cast<const T*>(ep.resid);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+        T mk = ep.mask ? (T)ep.mask[gm] : (T)1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            T v = acc[i][j];
+            if (ep.bias) v += (T)ep.bias[gn];
+            if (ep.gelu) v = gelu_erf<T>(v);
+            if (ep.scale) v *= (T)ep.scale[gn];
+            if (resid) v += resid[(size_t)gm * ldo + gn];
+            if (ep.mask) v *= mk;
+            out.store((size_t)gm * ldo + gn, v);
+        }
+    }
+}
+
+// ---- sequence lengths from masks: len[b] = sum_n mask[b,n] ---------------------------------------
+__global__ void mask_len_kernel(const float* __restrict__ mask, float* __restrict__ len, int N) {
+    int b = blockIdx.x;
+    float s = 0.f;
+    for (int n = threadIdx.x; n < N; n += 32) s += mask[(size_t)b * N + n];
+    s = warp_sum<float>(s);
+    if (threadIdx.x == 0) len[b] = s;
+}
+
+// ---- rotary embedding in place on [rows, heads*DH]: rotate-half convention -----------------------
+// pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i]
+__global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
+                            int rows, int N, int heads, int DH, int normalise) {
+    int half = DH / 2;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)rows * heads * half;
+    if (i >= total) return;
+    int d = (int)(i % half);
+    int h = (int)((i / half) % heads);
+    int row = (int)(i / ((size_t)half * heads));
+    int b = row / N, n = row - b * N;
+    float pos = (float)n;
+    if (normalise) pos = pos / len[b];
+    float ang = pos * freqs[d];
+    float c = cosf(ang), s = sinf(ang);
+    float* p = x + (size_t)row * heads * DH + (size_t)h * DH;
+    float t1 = p[d], t2 = p[d + half];
+    p[d] = t1 * c - t2 * s;
+    p[d + half] = t1 * s + t2 * c;
+}
+
+// ---- multi-head attention core: O = softmax(Q K^T * scale + keymask) V ----------------------------
+// Q [B*Nq, H*DH], K/V [B*Nk, H*DH] (already rotated), kmask [B*Nk] or null. One warp = QPW queries,
+// keys streamed through shared memory in chunks of 32 with an online softmax (fp32).
+template <int DH, typename Out>
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ Vt,
+                 const float* __restrict__ kmask, Out out, int Nq, int Nk, int heads, float scale) {
+    constexpr int QPW = 4, WARPS = 4, QT = QPW * WARPS, KC = 32, DPL = DH / 32;
+    __shared__ float Ks[KC][DH + 1];
+    __shared__ float Vs[KC][DH + 1];
+    __shared__ float Qs[QT][DH];
+    __shared__ float Ms[KC];
+    int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int C = heads * DH;
+    for (int i = threadIdx.x; i < QT * DH; i += 128) {
+        int qi = i / DH, d = i % DH;
+        int q = q0 + qi;
+        Qs[qi][d] = (q < Nq) ? Q[((size_t)b * Nq + q) * C + h * DH + d] : 0.f;
+    }
+    float m[QPW], l[QPW], o[QPW][DPL];
+#pragma unroll
+    for (int i = 0; i < QPW; ++i) { m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) o[i][j] = 0.f; }
+    for (int k0 = 0; k0 < Nk; k0 += KC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KC * DH; i += 128) {
+            int kj = i / DH, d = i % DH;
+            int k = k0 + kj;
+            bool ok = k < Nk;
+            size_t g = ((size_t)b * Nk + (ok ? k : 0)) * C + h * DH + d;
+            Ks[kj][d] = ok ? Kt[g] : 0.f;
+            Vs[kj][d] = ok ? Vt[g] : 0.f;
+        }
+        if (threadIdx.x < KC) {
+            int k = k0 + threadIdx.x;
+            Ms[threadIdx.x] = (k < Nk) ? (kmask ? kmask[(size_t)b * Nk + k] : 1.f) : 0.f;
+        }
+        __syncthreads();
+        bool valid = Ms[lane] != 0.f;
+#pragma unroll
+        for (int qi = 0; qi < QPW; ++qi) {
+            const float* qv = Qs[warp * QPW + qi];
+            float s = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < DH; ++d) s += qv[d] * Ks[lane][d];
+            s = valid ? s * scale : -INFINITY;
+            float mx = fmaxf(m[qi], warp_max(s));
+            if (mx == -INFINITY) continue;              // nothing valid yet (warp-uniform)
+            float p = valid ? __expf(s - mx) : 0.f;
+            float corr = __expf(m[qi] - mx);            // m = -inf -> 0
+            l[qi] = l[qi] * corr + warp_sum<float>(p);
+            m[qi] = mx;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) o[qi][j] *= corr;
+            for (int kj = 0; kj < KC; ++kj) {
+                float pj = __shfl_sync(0xffffffffu, p, kj);
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) o[qi][j] += pj * Vs[kj][lane + 32 * j];
+            }
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+        int q = q0 + warp * QPW + qi;
+        if (q >= Nq) continue;
+        float inv = l[qi] > 0.f ? 1.f / l[qi] : 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            out.store(((size_t)b * Nq + q) * C + h * DH + lane + 32 * j, o[qi][j] * inv);
+    }
+}
+
+// ---- layout changes at the API boundary -----------------------------------------------------------
+// NCL [B,C,N] -> NLC [B,N,C] (and back), 32x32 shared-memory tile transpose
+template <typename TI, typename TO>
+__global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int Cc) {
+    // in: [batch][R][Cc] -> out: [batch][Cc][R]
+    __shared__ float tile[32][33];
+    int b = blockIdx.z;
+    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const TI* ip = in + (size_t)b * R * Cc;
+    TO* op = out + (size_t)b * R * Cc;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < Cc) ? (float)ip[(size_t)r * Cc + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < Cc && r < R) op[(size_t)c * R + r] = (TO)tile[threadIdx.x][i];
+    }
+}
+
+// ---- noise * mask into the channels-last loop state (sampleNoisyLatent, cpp/helper.cpp:446-466) ---
+// host-provided noise [B][D][ld] (reference draw order b,d,t) or Philox-keyed Gaussian.
+STC_DEVINL uint32_t mix32(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return (uint32_t)(z >> 16);
+}
+__global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, uint64_t seed,
+                                   const float* __restrict__ mask, float* __restrict__ x, int B, int D, int L) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * L * D) return;
+    int d = (int)(i % D);
+    int l = (int)((i / D) % L);
+    int b = (int)(i / ((size_t)D * L));
+    float v;
+    if (noise) v = noise[((size_t)b * D + d) * ld + l];
+    else {
+        uint64_t key = seed * 0x9E3779B97F4A7C15ull + ((uint64_t)b << 40) + ((uint64_t)d << 24) + (uint64_t)l;
+        float u1 = (mix32(key) + 1.0f) * (1.0f / 4294967808.0f);          // (0,1]
+        float u2 = mix32(key ^ 0xD1B54A32D192ED03ull) * (1.0f / 4294967296.0f);
+        v = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+    x[i] = v * mask[(size_t)b * L + l];
+}
+
+// latent mask from wav lengths: mask[b,l] = l < ceil(wav_len[b]/cs)  (getLatentMask, cpp/helper.cpp:759-770)
+__global__ void latent_mask_kernel(const int64_t* __restrict__ wav_len, float* __restrict__ mask, int B, int L, int cs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    int b = i / L, l = i % L;
+    int64_t ll = (wav_len[b] + cs - 1) / cs;
+    mask[i] = (l < ll) ? 1.f : 0.f;
+}
+
+// ---- vocoder front-end: de-normalise, un-compress [B,L,f*ld] -> frames [B,f*L,ld], im2col for conv_in
+// A[(b*fL + n), k*ld + c] = z[b, n - (K-1) + k, c] (causal, zero left pad);
+// z[b, f*l + j, c] = lat[b,l, j*ld + c] * std[j*ld+c] + mean[j*ld+c]
+template <typename Out>
+__global__ void voc_im2col_kernel(const float* __restrict__ lat, const float* __restrict__ sd,
+                                  const float* __restrict__ mean, Out out, int B, int L, int f, int ld, int K, int lda) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int KW = K * ld;
+    size_t total = (size_t)B * L * f * lda;
+    if (i >= total) return;
+    int col = (int)(i % lda);
+    size_t row = i / lda;
+    float v = 0.f;
+    if (col < KW) {
+        int k = col / ld, c = col % ld;
+        int fL = f * L;
+        int b = (int)(row / fL), n = (int)(row % fL);
+        int nn = n - (K - 1) + k;
+        if (nn >= 0) {
+            int l = nn / f, j = nn % f;
+            int ch = j * ld + c;
+            v = lat[((size_t)b * L + l) * (f * ld) + ch] * sd[ch] + mean[ch];
+        }
+    }
+    out.store(i, v);
+}
+
+// ---- duration head (fp64): dur[b] = sum_t mask * exp(clip(LN(x_t).w + b, -clip, clip)) * spt -------
+template <int CPL>
+__global__ void dp_head_kernel(const double* __restrict__ x, const float* __restrict__ g, const float* __restrict__ beta,
+                               const float* __restrict__ w, const float* __restrict__ wb, const float* __restrict__ mask,
+                               float* __restrict__ dur, int N, float eps, float clip, float spt) {
+    constexpr int C = CPL * 32;
+    __shared__ double part[32];
+    int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double acc = 0.0;
+    for (int n = warp; n < N; n += nw) {
+        const double* xr = x + ((size_t)b * N + n) * C;
+        double y[CPL], s = 0;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { y[i] = xr[lane + 32 * i]; s += y[i]; }
+        double mean = warp_sum<double>(s) / C, v = 0;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { y[i] -= mean; v += y[i] * y[i]; }
+        double den = sqrt(warp_sum<double>(v) / C + (double)eps), dot = 0;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { int c = lane + 32 * i; dot += (y[i] / den * (double)g[c] + (double)beta[c]) * (double)w[c]; }
+        dot = warp_sum<double>(dot) + (double)wb[0];
+        dot = fmin(fmax(dot, -(double)clip), (double)clip);
+        acc += exp(dot) * (double)spt * (double)mask[(size_t)b * N + n];
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < nw; ++i) t += part[i];
+        dur[b] = (float)t;
+    }
+}
+
+// duration /= speed; wav_len = (int64)(d*sr)   (cpp/helper.cpp:529-531, 434) — float32 IEEE, no fast-math
+__global__ void dur_post_kernel(float* __restrict__ dur, int64_t* __restrict__ wav_len, int B, float speed, int sr) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float d = __fdiv_rn(dur[b], speed);
+    dur[b] = d;
+    wav_len[b] = (int64_t)__fmul_rn(d, (float)sr);
+}
+
+// sinusoidal time embedding: t = cur/tot; out[b] = [sin(t*f), cos(t*f)]
+__global__ void time_embed_kernel(const float* __restrict__ cur, const float* __restrict__ tot,
+                                  const float* __restrict__ freqs, float* __restrict__ out, int B, int half) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    int b = i / half, j = i % half;
+    float t = __fdiv_rn(cur[b], tot[b]);
+    float a = t * freqs[j];
+    out[(size_t)b * 2 * half + j] = sinf(a);
+    out[(size_t)b * 2 * half + half + j] = cosf(a);
+}
+
+// copy rows [B][L*cs] out of a wider device matrix into a strided destination
+__global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace stc

@@ -1,0 +1,1121 @@
+// libsupertonic_cuda — weights, workspace, layer walkers and the C ABI (include/supertonic_cuda.h).
+//
+// What it replaces in the reference: the four Ort::Session objects (cpp/helper.cpp:784-795) and their
+// Run calls inside TextToSpeech::_infer (:512-523 DP, :545-556 TE, :620-647 VE step, :662-672 vocoder),
+// plus the host-side latent bookkeeping between them (:424-467, :590-659).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <nlohmann/json.hpp>
+
+#include "gemm_tc.cuh"
+#include "model.cuh"
+#include "text_frontend.h"
+
+using json = nlohmann::json;
+
+namespace stc {
+
+// ------------------------------------------------------------------------------------------ arena
+Arena::~Arena() { if (base_) cudaFree(base_); }
+void Arena::reserve(size_t bytes) {
+    if (bytes <= cap_) return;
+    if (base_) { cudaDeviceSynchronize(); cudaFree(base_); base_ = nullptr; }
+    size_t want = bytes + (bytes >> 3) + (1u << 20);
+    cudaError_t e = cudaMalloc((void**)&base_, want);
+    if (e != cudaSuccess) { cap_ = 0; throw StcError(STC_ERR_CUDA, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e)); }
+    cap_ = want;
+}
+void* Arena::alloc(size_t bytes) {
+    size_t a = (off_ + 1023) & ~size_t(1023);
+    off_ = a + bytes;
+    if (off_ > high_water) high_water = off_;
+    if (!base_ || off_ > cap_) return reinterpret_cast<void*>(uintptr_t(0x1000) + a);   // measuring pass: never dereferenced
+    return base_ + a;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct GraphKey {
+    int B, T, L, steps, mode;
+    bool operator<(const GraphKey& o) const { return std::tie(B, T, L, steps, mode) < std::tie(o.B, o.T, o.L, o.steps, o.mode); }
+};
+
+struct VeCtx {
+    int B = 0, L = 0, T = 0;
+    const float* lmask = nullptr; const float* tmask = nullptr;
+    float* llen = nullptr; float* tlen = nullptr;
+    std::vector<float*> Kc, Vc;       // per cross-attention layer, [B*Nk, C] fp32 (keys already rotated)
+};
+
+struct Handle {
+    int device = 0;
+    int precision = STC_PREC_BF16X3;
+    cudaStream_t stream = nullptr;
+    stc_config cfg{};
+    Net dp, te, ve, voc;
+    json dp_arch, te_arch, ve_arch, voc_arch;
+    std::vector<void*> owned;          // weight allocations
+    Arena arena;       // workspace: reset per stage
+    Arena persist;     // buffers that survive from stage 1 (DP/TE) into stage 2 (VE loop + vocoder)
+    bool dry = false;
+    uint64_t launches = 0;
+    EncodeTiledFn encode = nullptr;
+    std::map<std::tuple<const void*, int, int, int>, CUtensorMap> map_cache;
+    bool use_graphs = true;
+    bool profile = false;
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[7] = {};   // start, dp, te, ve, vocoder, end, duration-ready
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, size_t> ws_need;
+    TextFrontend frontend;
+    // persistent small device buffers for the fast layer
+    float* d_dtvec = nullptr; int dtvec_steps = -1;
+    // pinned staging
+    float* h_dur = nullptr; int64_t* h_wavlen = nullptr; int h_cap = 0;
+
+    ~Handle();
+    // ---- loading
+    void load(const std::string& onnx_dir);
+    float* upload_f32(const float* p, size_t n);
+    float* W(const OnnxFile& f, const std::string& name, size_t numel);
+    Linear make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, bool tc);
+    Linear make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, bool tc);
+    void load_net(const OnnxFile& f, const json& arch, Net& net, bool tc);
+    ConvNeXt load_convnext(const OnnxFile& f, const json& l, bool tc);
+    Attention load_attention(const OnnxFile& f, const json& l, bool tc);
+    CUtensorMap encode_map(const void* ptr, int rows, int K, int box_rows);
+    const CUtensorMap& act_map(const void* ptr, int rows, int K);
+
+    // ---- workspace helpers
+    template <typename T> T* ws(size_t n) { return static_cast<T*>(arena.alloc(n * sizeof(T))); }
+    bool tc_mode() const { return precision == STC_PREC_BF16X3; }
+    Act ws_act(size_t n) {
+        Act a;
+        if (tc_mode()) { a.hi = ws<__nv_bfloat16>(n); a.lo = ws<__nv_bfloat16>(n); } else a.f = ws<float>(n);
+        return a;
+    }
+    template <typename T> T* ps(size_t n) { return static_cast<T*>(persist.alloc(n * sizeof(T))); }
+    size_t mark() { return arena.used(); }
+    void release(size_t m) { arena.rewind(m); }
+
+    // ---- kernels
+    void to_act(const float* x, size_t n, const Act& out);
+    template <typename T> void dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C,
+                                         int rows, int N, float eps, T* out_plain, const Act* out_act);
+    void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
+    template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
+    template <typename T> void convnext(const ConvNeXt& c, T* x, int rows, int N, const float* mask);
+    void attention(const Attention& a, float* x, int B, int Nq, const float* qmask, const float* qlen,
+                   const Act* ctx, int Nk, const float* kmask, const float* klen, const float* Kpre, const float* Vpre);
+    void attn_core(const float* Q, const float* K, const float* V, const float* kmask, const Act& out, int B, int Nq, int Nk,
+                   int heads, int dh);
+    void rope(float* x, const float* freqs, const float* len, int rows, int N, int heads, int dh, int normalise);
+
+    // ---- graph walkers (device pointers)
+    void run_dp(const int64_t* ids, const float* style_dp, const float* mask, int B, int T, float* dur);
+    void run_te(const int64_t* ids, const float* style_ttl, const float* mask, int B, int T, float* text_emb_cl);
+    void prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_ttl);
+    void run_ve_step(const VeCtx& vc, float* x_lat, const float* cur, const float* tot, const float* dtvec);
+    void run_vocoder(const float* lat_cl, int B, int L, float* wav);
+
+    void check_launch(const char* what);
+    void ensure_ws(const std::function<void()>& fn);
+    void synth_tail(const float* d_text_emb, const float* d_tmask, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
+                    uint64_t seed, const int64_t* d_wavlen, int B, int T, int L, int steps, float* d_lmask, float* d_xlat, float* d_wav);
+};
+
+#define STC_LAUNCH(h, kernel, grid, block, smem, ...)                          \
+    do {                                                                       \
+        if (!(h)->dry) {                                                       \
+            auto _kfn = kernel;                                                \
+            _kfn<<<grid, block, smem, (h)->stream>>>(__VA_ARGS__);             \
+            ++(h)->launches;                                                   \
+        }                                                                      \
+    } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+Handle::~Handle() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (void* p : owned) cudaFree(p);
+    if (d_dtvec) cudaFree(d_dtvec);
+    if (h_dur) cudaFreeHost(h_dur);
+    if (h_wavlen) cudaFreeHost(h_wavlen);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Handle::check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------ loading
+float* Handle::upload_f32(const float* p, size_t n) {
+    float* d = nullptr;
+    STC_CUDA(cudaMalloc((void**)&d, std::max<size_t>(n, 1) * sizeof(float)));
+    owned.push_back(d);
+    STC_CUDA(cudaMemcpy(d, p, n * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static const OnnxTensor& get_tensor(const OnnxFile& f, const std::string& name, size_t numel) {
+    auto it = f.initializers.find(name);
+    if (it == f.initializers.end()) throw StcError(STC_ERR_IO, "initializer not found: " + name);
+    if (it->second.dtype != 1) throw StcError(STC_ERR_UNSUPPORTED, "initializer " + name + " is not float32");
+    if (numel && it->second.numel() != numel)
+        throw StcError(STC_ERR_IO, "initializer " + name + ": expected " + std::to_string(numel) + " elements, file has " +
+                                       std::to_string(it->second.numel()));
+    return it->second;
+}
+
+float* Handle::W(const OnnxFile& f, const std::string& name, size_t numel) {
+    const OnnxTensor& t = get_tensor(f, name, numel);
+    return upload_f32(t.f32(), t.numel());
+}
+
+CUtensorMap Handle::encode_map(const void* ptr, int rows, int K, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    if (K % 8) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs K % 8 == 0, got " + std::to_string(K));
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return m;
+}
+
+const CUtensorMap& Handle::act_map(const void* ptr, int rows, int K) {
+    auto key = std::make_tuple(ptr, rows, K, tc::BM);
+    auto it = map_cache.find(key);
+    if (it != map_cache.end()) return it->second;
+    if (map_cache.size() > 8192) map_cache.clear();
+    return map_cache.emplace(key, encode_map(ptr, rows, K, tc::BM)).first->second;
+}
+
+static inline uint16_t bf16_bits_rn(float v) {
+    uint32_t u; memcpy(&u, &v, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+
+Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, bool tc) {
+    Linear l; l.K = K; l.N = N;
+    l.w_kn = upload_f32(w_kn.data(), w_kn.size());
+    l.bias = upload_f32(bias.data(), bias.size());
+    if (tc) {
+        std::vector<uint16_t> hi((size_t)N * K), lo((size_t)N * K);
+        for (int k = 0; k < K; ++k)
+            for (int n = 0; n < N; ++n) {
+                float v = w_kn[(size_t)k * N + n];
+                uint16_t h = bf16_bits_rn(v);
+                hi[(size_t)n * K + k] = h;
+                lo[(size_t)n * K + k] = bf16_bits_rn(v - bf16_to_f(h));
+            }
+        STC_CUDA(cudaMalloc((void**)&l.w_hi, hi.size() * 2)); owned.push_back(l.w_hi);
+        STC_CUDA(cudaMalloc((void**)&l.w_lo, lo.size() * 2)); owned.push_back(l.w_lo);
+        STC_CUDA(cudaMemcpy(l.w_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+        STC_CUDA(cudaMemcpy(l.w_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+        l.map_hi = encode_map(l.w_hi, N, K, 128);
+        l.map_lo = encode_map(l.w_lo, N, K, 128);
+        l.has_maps = true;
+    }
+    return l;
+}
+
+Linear Handle::make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, bool tc) {
+    const OnnxTensor& w = get_tensor(f, prefix + ".weight", (size_t)K * N);
+    const OnnxTensor& b = get_tensor(f, prefix + ".bias", (size_t)N);
+    return make_linear_host(std::vector<float>(w.f32(), w.f32() + w.numel()), std::vector<float>(b.f32(), b.f32() + b.numel()), K, N, tc);
+}
+
+ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, bool tc) {
+    ConvNeXt c{};
+    std::string p = l.at("name");
+    c.C = l.at("C"); c.H = l.at("H"); c.K = l.at("K"); c.dil = l.at("dilation");
+    bool causal = l.at("causal");
+    c.masked = l.at("masked");
+    int span = c.dil * (c.K - 1);
+    c.pad_left = causal ? span : span / 2;
+    c.dw_w = W(f, p + ".dw.weight", (size_t)c.C * c.K);
+    c.dw_b = W(f, p + ".dw.bias", c.C);
+    c.ln_g = W(f, p + ".ln.weight", c.C);
+    c.ln_b = W(f, p + ".ln.bias", c.C);
+    c.gamma = W(f, p + ".gamma", c.C);
+    c.pw1 = make_linear(f, p + ".pw1", c.C, c.H, tc);
+    c.pw2 = make_linear(f, p + ".pw2", c.H, c.C, tc);
+    return c;
+}
+
+Attention Handle::load_attention(const OnnxFile& f, const json& l, bool tc) {
+    Attention a{};
+    std::string p = l.at("name");
+    a.C = l.at("C"); a.heads = l.at("heads"); a.ctx_dim = l.at("ctx_dim");
+    std::string ctx = l.at("ctx"), rope = l.at("rope");
+    a.ctx_kind = ctx == "self" ? CTX_SELF : ctx == "text_emb" ? CTX_TEXT : ctx == "style_ttl" ? CTX_STYLE : -1;
+    if (a.ctx_kind < 0) throw StcError(STC_ERR_UNSUPPORTED, "attention context " + ctx);
+    a.rope = rope == "none" ? ROPE_NONE : rope == "abs" ? ROPE_ABS : ROPE_NORM;
+    a.masked = l.at("masked"); a.key_masked = l.at("key_masked");
+    int dh = a.C / a.heads;
+    if (dh != 32 && dh != 64) throw StcError(STC_ERR_UNSUPPORTED, "attention head dim must be 32 or 64");
+    a.ln_g = W(f, p + ".ln.weight", a.C);
+    a.ln_b = W(f, p + ".ln.bias", a.C);
+    a.freqs = a.rope != ROPE_NONE ? W(f, p + ".rope_freqs", dh / 2) : nullptr;
+    a.q = make_linear(f, p + ".q", a.C, a.C, tc);
+    a.k = make_linear(f, p + ".k", a.ctx_dim, a.C, tc);
+    a.v = make_linear(f, p + ".v", a.ctx_dim, a.C, tc);
+    a.o = make_linear(f, p + ".o", a.C, a.C, tc);
+    return a;
+}
+
+void Handle::load_net(const OnnxFile& f, const json& arch, Net& net, bool tc) {
+    net.C = arch.value("C", 0); net.H = arch.value("H", 0); net.heads = arch.value("heads", 0);
+    int kv = 0;
+    for (const auto& l : arch.at("layers")) {
+        std::string type = l.at("type");
+        if (type == "convnext") { net.cn.push_back(load_convnext(f, l, tc)); net.layers.push_back({L_CONVNEXT, (int)net.cn.size() - 1}); }
+        else if (type == "attention") {
+            Attention a = load_attention(f, l, tc);
+            if (a.ctx_kind != CTX_SELF) a.kv_slot = kv++;
+            net.at.push_back(a); net.layers.push_back({L_ATTN, (int)net.at.size() - 1});
+        } else if (type == "time_cond") {
+            std::string p = l.at("name"); int C = l.at("C");
+            net.lin.push_back(make_linear(f, p, C, C, false)); net.layers.push_back({L_TIME_COND, (int)net.lin.size() - 1});
+        } else if (type == "proj_in" || type == "proj_out") {
+            std::string p = l.at("name"); int ci = l.at("cin"), co = l.at("cout");
+            net.lin.push_back(make_linear(f, p, ci, co, tc));
+            net.layers.push_back({type == "proj_in" ? L_PROJ_IN : L_PROJ_OUT, (int)net.lin.size() - 1});
+        } else if (type == "time_mlp") {
+            std::string p = l.at("name"); int td = l.at("time_dim"), C = l.at("C");
+            net.vec["time.freqs"] = W(f, p + ".freqs", td / 2);
+            net.lin.push_back(make_linear(f, p + ".fc1", td, C, false));
+            net.lin.push_back(make_linear(f, p + ".fc2", C, C, false));
+            net.layers.push_back({L_TIME_MLP, (int)net.lin.size() - 2});
+        } else if (type == "conv_in") {
+            // Conv1d(ld -> C, K, causal) followed by eval-mode BatchNorm: fold BN into the conv (in double) and
+            // express it as a [K*ld, C] linear over the im2col rows the front-end kernel writes.
+            std::string p = l.at("name"), bn = l.at("bn");
+            int ci = l.at("cin"), co = l.at("cout"), K = l.at("K");
+            const float* w = get_tensor(f, p + ".weight", (size_t)co * ci * K).f32();
+            const float* b = get_tensor(f, p + ".bias", co).f32();
+            const float* g = get_tensor(f, bn + ".weight", co).f32();
+            const float* be = get_tensor(f, bn + ".bias", co).f32();
+            const float* mu = get_tensor(f, bn + ".running_mean", co).f32();
+            const float* var = get_tensor(f, bn + ".running_var", co).f32();
+            std::vector<float> wk((size_t)K * ci * co), bb(co);
+            for (int o = 0; o < co; ++o) {
+                double s = (double)g[o] / std::sqrt((double)var[o] + 1e-5);
+                bb[o] = (float)(((double)b[o] - (double)mu[o]) * s + (double)be[o]);
+                for (int c = 0; c < ci; ++c)
+                    for (int k = 0; k < K; ++k) wk[(size_t)(k * ci + c) * co + o] = (float)((double)w[((size_t)o * ci + c) * K + k] * s);
+            }
+            net.lin.push_back(make_linear_host(wk, bb, K * ci, co, tc));
+            net.layers.push_back({L_CONV_IN, (int)net.lin.size() - 1});
+        } else if (type == "head") {
+            std::string p = l.at("name"); int ci = l.at("cin"), co = l.at("cout");
+            net.vec["head.ln_g"] = W(f, p + ".ln.weight", ci);
+            net.vec["head.ln_b"] = W(f, p + ".ln.bias", ci);
+            net.lin.push_back(make_linear(f, p + ".proj", ci, co, tc));
+            net.layers.push_back({L_HEAD, (int)net.lin.size() - 1});
+        } else throw StcError(STC_ERR_UNSUPPORTED, "layer type " + type);
+    }
+}
+
+static json arch_of(const OnnxFile& f, const std::string& path) {
+    auto it = f.metadata.find("stc_arch");
+    if (it == f.metadata.end())
+        throw StcError(STC_ERR_UNSUPPORTED, path + ": no 'stc_arch' metadata — only graphs whose layer plan is described are "
+                                                   "supported (topology matching of the released graphs is not implemented)");
+    return json::parse(it->second);
+}
+
+void Handle::load(const std::string& onnx_dir) {
+    {   // tts.json (reference loadCfgs, cpp/helper.cpp:801-818)
+        std::string p = onnx_dir + "/tts.json";
+        std::ifstream file(p);
+        if (!file.is_open()) throw StcError(STC_ERR_IO, "Failed to open config file: " + p);
+        json j; file >> j;
+        cfg.sample_rate = j["ae"]["sample_rate"]; cfg.base_chunk_size = j["ae"]["base_chunk_size"];
+        cfg.chunk_compress_factor = j["ttl"]["chunk_compress_factor"]; cfg.latent_dim = j["ttl"]["latent_dim"];
+        cfg.latent_channels = cfg.latent_dim * cfg.chunk_compress_factor;
+        cfg.chunk_size = cfg.base_chunk_size * cfg.chunk_compress_factor;
+    }
+    frontend.load_indexer(onnx_dir + "/unicode_indexer.json");
+    bool tc = tc_mode();
+    {
+        OnnxFile f = load_onnx(onnx_dir + "/duration_predictor.onnx");
+        dp_arch = arch_of(f, "duration_predictor.onnx");
+        load_net(f, dp_arch, dp, false);
+        cfg.vocab_size = dp_arch.at("vocab");
+        dp.vec["embed"] = W(f, "dp.embed.weight", (size_t)cfg.vocab_size * dp.C);
+        int si = dp_arch.at("style_in");
+        dp.lin.push_back(make_linear(f, "dp.style", si, dp.C, false));
+        dp.vec["head.ln_g"] = W(f, "dp.head.ln.weight", dp.C);
+        dp.vec["head.ln_b"] = W(f, "dp.head.ln.bias", dp.C);
+        dp.vec["head.w"] = W(f, "dp.head.proj.weight", dp.C);
+        dp.vec["head.b"] = W(f, "dp.head.proj.bias", 1);
+    }
+    {
+        OnnxFile f = load_onnx(onnx_dir + "/text_encoder.onnx");
+        te_arch = arch_of(f, "text_encoder.onnx");
+        load_net(f, te_arch, te, tc);
+        te.vec["embed"] = W(f, "te.embed.weight", (size_t)cfg.vocab_size * te.C);
+        cfg.text_emb_channels = te.C;
+        cfg.style_ttl_tokens = te_arch.at("n_style"); cfg.style_ttl_dim = te_arch.at("style_dim");
+    }
+    {
+        OnnxFile f = load_onnx(onnx_dir + "/vector_estimator.onnx");
+        ve_arch = arch_of(f, "vector_estimator.onnx");
+        load_net(f, ve_arch, ve, tc);
+        if ((int)ve_arch.at("latent_ch") != cfg.latent_channels) throw StcError(STC_ERR_IO, "vector_estimator latent_ch != tts.json");
+    }
+    {
+        OnnxFile f = load_onnx(onnx_dir + "/vocoder.onnx");
+        voc_arch = arch_of(f, "vocoder.onnx");
+        load_net(f, voc_arch, voc, tc);
+        voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
+        voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
+    }
+    // style_dp dims: e1*e2 = style_in; keep the reference's [B,e1,e2] split from the surrogate (8 x 16) when it matches
+    int si = dp_arch.at("style_in");
+    cfg.style_dp_tokens = 8; cfg.style_dp_dim = si / 8;
+}
+
+// ------------------------------------------------------------------------------------------ kernels (host side)
+void Handle::to_act(const float* x, size_t n, const Act& out) {
+    if (tc_mode()) STC_LAUNCH(this, (convert_kernel<OutSplit>), cdiv(n, 256), 256, 0, x, OutSplit{out.hi, out.lo}, n);
+    else STC_LAUNCH(this, (convert_kernel<OutPlain<float>>), cdiv(n, 256), 256, 0, x, OutPlain<float>{out.f}, n);
+}
+
+template <typename T, typename Out>
+static void launch_dwln(Handle* h, int C, const T* x, const float* w, const float* wb, const float* g, const float* b, Out out,
+                        int rows, int N, int K, int dil, int pad, float eps) {
+    dim3 grid(cdiv(rows, 8)), block(256);
+    switch (C / 32) {
+        case 1: STC_LAUNCH(h, (dwconv_ln_kernel<T, 1, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        case 2: STC_LAUNCH(h, (dwconv_ln_kernel<T, 2, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        case 4: STC_LAUNCH(h, (dwconv_ln_kernel<T, 4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        case 8: STC_LAUNCH(h, (dwconv_ln_kernel<T, 8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        case 16: STC_LAUNCH(h, (dwconv_ln_kernel<T, 16, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        default: throw StcError(STC_ERR_UNSUPPORTED, "channel count must be 32/64/128/256/512, got " + std::to_string(C));
+    }
+}
+
+template <typename T>
+void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C, int rows, int N, float eps,
+                       T* out_plain, const Act* out_act) {
+    const float* w = cn ? cn->dw_w : nullptr; const float* wb = cn ? cn->dw_b : nullptr;
+    int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0;
+    if constexpr (std::is_same<T, float>::value) {
+        if (out_act && out_act->hi) { launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, N, K, dil, pad, eps); return; }
+        if (out_act) out_plain = out_act->f;
+    }
+    launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_plain}, rows, N, K, dil, pad, eps);
+}
+
+template <typename T>
+void Handle::gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo) {
+    dim3 grid(cdiv(w.N, 64), cdiv(M, 64));
+    STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
+}
+
+void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, float* out_f32, const Act* out_act, int ldo) {
+    Epilogue ep = ep_in;
+    if (!ep.bias) ep.bias = w.bias;
+    if (!tc_mode()) {
+        float* o = out_f32 ? out_f32 : out_act->f;
+        gemm_simt<float>(a.f, w.K, M, w, ep, o, ldo);
+        return;
+    }
+    if (!w.has_maps) throw StcError(STC_ERR_INVALID, "linear has no tensor maps");
+    tc::Params p{};
+    p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
+    if (out_f32) { p.out_f32 = out_f32; p.split = 0; } else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
+    if (dry) return;
+    const CUtensorMap& ma_hi = act_map(a.hi, M, w.K);
+    CUtensorMap mh = ma_hi;
+    CUtensorMap ml = act_map(a.lo, M, w.K);
+    dim3 grid(cdiv(w.N, 128), cdiv(M, tc::BM));
+    STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<128>), grid, tc::NUM_THREADS, tc::Tile<128>::SMEM_BYTES, mh, ml, w.map_hi, w.map_lo, p);
+}
+
+template <typename T>
+void Handle::convnext(const ConvNeXt& c, T* x, int rows, int N, const float* mask) {
+    size_t mk = mark();
+    Epilogue e1; e1.gelu = 1;
+    Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? mask : nullptr;
+    if constexpr (std::is_same<T, float>::value) {
+        Act a = ws_act((size_t)rows * c.C), hid = ws_act((size_t)rows * c.H);
+        dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, rows, N, 1e-6f, nullptr, &a);
+        gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
+        gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
+    } else {
+        T* a = ws<T>((size_t)rows * c.C); T* hid = ws<T>((size_t)rows * c.H);
+        dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, rows, N, 1e-6f, a, nullptr);
+        e1.bias = c.pw1.bias; e2.bias = c.pw2.bias;
+        gemm_simt<T>(a, c.C, rows, c.pw1, e1, hid, c.H);
+        gemm_simt<T>(hid, c.H, rows, c.pw2, e2, x, c.C);
+    }
+    release(mk);
+}
+
+void Handle::rope(float* x, const float* freqs, const float* len, int rows, int N, int heads, int dh, int normalise) {
+    size_t n = (size_t)rows * heads * (dh / 2);
+    STC_LAUNCH(this, rope_kernel, cdiv(n, 256), 256, 0, x, freqs, len, rows, N, heads, dh, normalise);
+}
+
+void Handle::attn_core(const float* Q, const float* K, const float* V, const float* kmask, const Act& out, int B, int Nq, int Nk,
+                       int heads, int dh) {
+    dim3 grid(cdiv(Nq, 16), heads, B);
+    float scale = 1.0f / std::sqrt((float)dh);
+    if (out.hi) {
+        OutSplit o{out.hi, out.lo};
+        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+        else STC_LAUNCH(this, (attention_kernel<32, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+    } else {
+        OutPlain<float> o{out.f};
+        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+        else STC_LAUNCH(this, (attention_kernel<32, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+    }
+}
+
+void Handle::attention(const Attention& a, float* x, int B, int Nq, const float* qmask, const float* qlen, const Act* ctx, int Nk,
+                       const float* kmask, const float* klen, const float* Kpre, const float* Vpre) {
+    size_t mk = mark();
+    int rows = B * Nq, dh = a.C / a.heads;
+    Act xn = ws_act((size_t)rows * a.C);
+    dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, rows, Nq, 1e-6f, nullptr, &xn);
+    float* q = ws<float>((size_t)rows * a.C);
+    gemm(xn, rows, a.q, Epilogue{}, q, nullptr, a.C);
+    const float *Kp = Kpre, *Vp = Vpre;
+    if (a.ctx_kind == CTX_SELF) { ctx = &xn; Nk = Nq; kmask = a.key_masked ? qmask : nullptr; klen = qlen; }
+    if (!Kp) {
+        float* k = ws<float>((size_t)B * Nk * a.C); float* v = ws<float>((size_t)B * Nk * a.C);
+        gemm(*ctx, B * Nk, a.k, Epilogue{}, k, nullptr, a.C);
+        gemm(*ctx, B * Nk, a.v, Epilogue{}, v, nullptr, a.C);
+        if (a.rope != ROPE_NONE) rope(k, a.freqs, klen, B * Nk, Nk, a.heads, dh, a.rope == ROPE_NORM);
+        Kp = k; Vp = v;
+    }
+    if (a.rope != ROPE_NONE) rope(q, a.freqs, qlen, rows, Nq, a.heads, dh, a.rope == ROPE_NORM);
+    Act o = ws_act((size_t)rows * a.C);
+    attn_core(q, Kp, Vp, a.key_masked ? kmask : nullptr, o, B, Nq, Nk, a.heads, dh);
+    Epilogue eo; eo.resid = x; eo.mask = a.masked ? qmask : nullptr;
+    gemm(o, rows, a.o, eo, x, nullptr, a.C);
+    release(mk);
+}
+
+// ------------------------------------------------------------------------------------------ graph walkers
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (TO)in[i];
+}
+
+void Handle::run_dp(const int64_t* ids, const float* style_dp, const float* mask, int B, int T, float* dur) {
+    // duration_predictor.onnx evaluated in fp64 (reference call site cpp/helper.cpp:512-526)
+    size_t mk = mark();
+    int C = dp.C, rows = B * T, si = dp_arch.at("style_in");
+    double* x = ws<double>((size_t)rows * C);
+    STC_LAUNCH(this, embed_kernel<double>, cdiv(rows, 8), dim3(32, 8), 0, ids, dp.vec["embed"], mask, x, rows, C, cfg.vocab_size);
+    double* sd = ws<double>((size_t)B * si); double* s = ws<double>((size_t)B * C);
+    STC_LAUNCH(this, (cast_kernel<float, double>), cdiv((size_t)B * si, 256), 256, 0, style_dp, sd, (size_t)B * si);
+    const Linear& ls = dp.lin.back();
+    Epilogue es; es.bias = ls.bias;
+    gemm_simt<double>(sd, si, B, ls, es, s, C);
+    STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, T, C);
+    for (const Layer& l : dp.layers)
+        if (l.type == L_CONVNEXT) convnext<double>(dp.cn[l.idx], x, rows, T, mask);
+    float clip = dp_arch.at("clip"), spt = dp_arch.at("sec_per_token");
+    if (C == 64) STC_LAUNCH(this, dp_head_kernel<2>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
+    else if (C == 32) STC_LAUNCH(this, dp_head_kernel<1>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
+    else throw StcError(STC_ERR_UNSUPPORTED, "duration predictor width");
+    release(mk);
+}
+
+void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mask, int B, int T, float* text_emb_cl) {
+    // text_encoder.onnx (reference call site cpp/helper.cpp:545-556); output kept channels-last [B*T, C]
+    size_t mk = mark();
+    int C = te.C, rows = B * T, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim;
+    float* x = ws<float>((size_t)rows * C);
+    STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], mask, x, rows, C, cfg.vocab_size);
+    float* tlen = ws<float>(B);
+    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, mask, tlen, T);
+    Act sty = ws_act((size_t)B * S * Cs);
+    to_act(style_ttl, (size_t)B * S * Cs, sty);
+    for (const Layer& l : te.layers) {
+        if (l.type == L_CONVNEXT) convnext<float>(te.cn[l.idx], x, rows, T, mask);
+        else if (l.type == L_ATTN) {
+            const Attention& a = te.at[l.idx];
+            if (a.ctx_kind == CTX_SELF) attention(a, x, B, T, mask, tlen, nullptr, T, mask, tlen, nullptr, nullptr);
+            else attention(a, x, B, T, mask, tlen, &sty, S, nullptr, nullptr, nullptr, nullptr);
+        } else if (l.type == L_PROJ_OUT) {
+            Act xa = ws_act((size_t)rows * C);
+            to_act(x, (size_t)rows * C, xa);
+            Epilogue e; e.mask = mask;
+            gemm(xa, rows, te.lin[l.idx], e, text_emb_cl, nullptr, te.lin[l.idx].N);
+        }
+    }
+    release(mk);
+}
+
+void Handle::prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_ttl) {
+    // K/V of text_emb and style_ttl are step-invariant: hoisted out of the Euler loop (north_star).
+    int B = vc.B, T = vc.T, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim, Ct = cfg.text_emb_channels;
+    vc.llen = ws<float>(B); vc.tlen = ws<float>(B);
+    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, vc.lmask, vc.llen, vc.L);
+    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, vc.tmask, vc.tlen, T);
+    int nslots = 0;
+    for (const Attention& a : ve.at) if (a.kv_slot >= 0) nslots = std::max(nslots, a.kv_slot + 1);
+    vc.Kc.assign(nslots, nullptr); vc.Vc.assign(nslots, nullptr);
+    for (const Attention& a : ve.at) {
+        if (a.kv_slot < 0) continue;
+        int Nk = a.ctx_kind == CTX_TEXT ? T : S;
+        vc.Kc[a.kv_slot] = ws<float>((size_t)B * Nk * a.C);
+        vc.Vc[a.kv_slot] = ws<float>((size_t)B * Nk * a.C);
+    }
+    size_t mk = mark();
+    Act ta = ws_act((size_t)B * T * Ct), sa = ws_act((size_t)B * S * Cs);
+    to_act(text_emb_cl, (size_t)B * T * Ct, ta);
+    to_act(style_ttl, (size_t)B * S * Cs, sa);
+    for (const Attention& a : ve.at) {
+        if (a.kv_slot < 0) continue;
+        bool text = a.ctx_kind == CTX_TEXT;
+        int Nk = text ? T : S;
+        gemm(text ? ta : sa, B * Nk, a.k, Epilogue{}, vc.Kc[a.kv_slot], nullptr, a.C);
+        gemm(text ? ta : sa, B * Nk, a.v, Epilogue{}, vc.Vc[a.kv_slot], nullptr, a.C);
+        if (a.rope != ROPE_NONE) rope(vc.Kc[a.kv_slot], a.freqs, vc.tlen, B * Nk, Nk, a.heads, a.C / a.heads, a.rope == ROPE_NORM);
+    }
+    release(mk);
+}
+
+void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* cur, const float* tot, const float* dtvec) {
+    // vector_estimator.onnx: one Euler step, update in-graph (reference cpp/helper.cpp:620-658)
+    size_t mk = mark();
+    int B = vc.B, L = vc.L, rows = B * L, C = ve.C, D = cfg.latent_channels;
+    float* x = ws<float>((size_t)rows * C);
+    float* temb = nullptr;
+    for (const Layer& l : ve.layers) {
+        switch (l.type) {
+            case L_TIME_MLP: {
+                int td = ve_arch.at("time_dim");
+                float* e0 = ws<float>((size_t)B * td); float* e1 = ws<float>((size_t)B * C); temb = ws<float>((size_t)B * C);
+                STC_LAUNCH(this, time_embed_kernel, cdiv((size_t)B * td / 2, 128), 128, 0, cur, tot, ve.vec["time.freqs"], e0, B, td / 2);
+                Epilogue a; a.bias = ve.lin[l.idx].bias; a.gelu = 1;
+                gemm_simt<float>(e0, td, B, ve.lin[l.idx], a, e1, C);
+                Epilogue b; b.bias = ve.lin[l.idx + 1].bias;
+                gemm_simt<float>(e1, C, B, ve.lin[l.idx + 1], b, temb, C);
+                break;
+            }
+            case L_PROJ_IN: {
+                size_t m2 = mark();
+                Act xa = ws_act((size_t)rows * D);
+                to_act(x_lat, (size_t)rows * D, xa);
+                Epilogue e; e.mask = vc.lmask;
+                gemm(xa, rows, ve.lin[l.idx], e, x, nullptr, C);
+                release(m2);
+                break;
+            }
+            case L_CONVNEXT: convnext<float>(ve.cn[l.idx], x, rows, L, vc.lmask); break;
+            case L_TIME_COND: {
+                size_t m2 = mark();
+                float* tcv = ws<float>((size_t)B * C);
+                Epilogue e; e.bias = ve.lin[l.idx].bias;
+                gemm_simt<float>(temb, C, B, ve.lin[l.idx], e, tcv, C);
+                STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, tcv, vc.lmask, rows, L, C);
+                release(m2);
+                break;
+            }
+            case L_ATTN: {
+                const Attention& a = ve.at[l.idx];
+                bool text = a.ctx_kind == CTX_TEXT;
+                attention(a, x, B, L, vc.lmask, vc.llen, nullptr, text ? vc.T : cfg.style_ttl_tokens, text ? vc.tmask : nullptr,
+                          text ? vc.tlen : nullptr, vc.Kc[a.kv_slot], vc.Vc[a.kv_slot]);
+                break;
+            }
+            case L_PROJ_OUT: {
+                size_t m2 = mark();
+                Act xa = ws_act((size_t)rows * C);
+                to_act(x, (size_t)rows * C, xa);
+                Epilogue e; e.scale = dtvec; e.resid = x_lat; e.mask = vc.lmask;   // x <- (x + v*dt) * mask
+                gemm(xa, rows, ve.lin[l.idx], e, x_lat, nullptr, D);
+                release(m2);
+                break;
+            }
+            default: break;
+        }
+    }
+    release(mk);
+}
+
+void Handle::run_vocoder(const float* lat_cl, int B, int L, float* wav) {
+    // vocoder.onnx (reference call site cpp/helper.cpp:662-672); no mask: the whole padded rectangle is decoded
+    size_t mk = mark();
+    int f = cfg.chunk_compress_factor, ld = cfg.latent_dim, C = voc.C;
+    int rows = B * L * f;
+    float* x = ws<float>((size_t)rows * C);
+    for (const Layer& l : voc.layers) {
+        if (l.type == L_CONV_IN) {
+            size_t m2 = mark();
+            const Linear& w = voc.lin[l.idx];
+            int K = w.K / ld;
+            Act a = ws_act((size_t)rows * w.K);
+            size_t n = (size_t)rows * w.K;
+            if (a.hi) STC_LAUNCH(this, voc_im2col_kernel<OutSplit>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutSplit{a.hi, a.lo}, B, L, f, ld, K, w.K);
+            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f}, B, L, f, ld, K, w.K);
+            gemm(a, rows, w, Epilogue{}, x, nullptr, C);
+            release(m2);
+        } else if (l.type == L_CONVNEXT) convnext<float>(voc.cn[l.idx], x, rows, L * f, nullptr);
+        else if (l.type == L_HEAD) {
+            Act hn = ws_act((size_t)rows * C);
+            dwconv_ln<float>(x, nullptr, voc.vec["head.ln_g"], voc.vec["head.ln_b"], C, rows, L * f, 1e-6f, nullptr, &hn);
+            gemm(hn, rows, voc.lin[l.idx], Epilogue{}, wav, nullptr, voc.lin[l.idx].N);
+        }
+    }
+    release(mk);
+}
+
+// Run `fn` once in measuring mode to learn its workspace high-water marks; grow the arenas if needed.
+// (`fn` must start with arena.reset()/rewind so that both passes allocate identically.)
+void Handle::ensure_ws(const std::function<void()>& fn) {
+    bool was = dry;
+    size_t p_used = persist.used();
+    dry = true; arena.high_water = 0; persist.high_water = p_used;
+    try { fn(); } catch (...) { dry = was; throw; }
+    dry = was;
+    persist.rewind(p_used);
+    if (arena.high_water > arena.capacity() || persist.high_water > persist.capacity()) {
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second);     // captured pointers die with the old arena
+        graphs.clear(); map_cache.clear();
+        if (persist.high_water > persist.capacity()) {
+            if (p_used) throw StcError(STC_ERR_CUDA, "persistent arena cannot grow while in use");
+            persist.reserve(persist.high_water);
+        }
+        arena.reserve(arena.high_water);
+    }
+}
+
+}  // namespace stc
+
+// =============================================================================================== C ABI
+using namespace stc;
+
+static thread_local std::string g_last_error;
+
+static int fail(stc_handle* h, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (h) h->last_error = msg;
+    return code;
+}
+
+#define STC_TRY(h, ...)                                                                      \
+    try { __VA_ARGS__; return STC_OK; }                                                           \
+    catch (const StcError& e) { return fail(h, e.code, e.what()); }                          \
+    catch (const std::exception& e) { return fail(h, STC_ERR_INVALID, e.what()); }
+
+extern "C" {
+
+const char* stc_last_error(const stc_handle* h) { return h ? h->last_error.c_str() : g_last_error.c_str(); }
+
+int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out) {
+    if (!out || !onnx_dir) return fail(nullptr, STC_ERR_INVALID, "stc_create: null argument");
+    *out = nullptr;
+    auto sh = std::make_unique<stc_handle>();
+    try {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw StcError(STC_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                             "); libsupertonic_cuda has no CPU fallback");
+        if (device < 0 || device >= n) throw StcError(STC_ERR_INVALID, "device index out of range");
+        STC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop; STC_CUDA(cudaGetDeviceProperties(&prop, device));
+        auto hd = std::make_unique<Handle>();
+        hd->device = device;
+        if (precision == STC_PREC_DEFAULT) {
+            const char* env = getenv("STC_PRECISION");
+            precision = (env && std::string(env) == "fp32_simt") ? STC_PREC_FP32_SIMT : STC_PREC_BF16X3;
+        }
+        if (precision != STC_PREC_BF16X3 && precision != STC_PREC_FP32_SIMT) throw StcError(STC_ERR_INVALID, "unknown precision");
+        if (precision == STC_PREC_BF16X3 && prop.major != 10)
+            throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
+        hd->precision = precision;
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
+        for (auto& ev : hd->ev) STC_CUDA(cudaEventCreate(&ev));
+        if (precision == STC_PREC_BF16X3) {
+            void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+            STC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+            if (!fn || qr != cudaDriverEntryPointSuccess) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+            hd->encode = (EncodeTiledFn)fn;
+            STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
+        }
+        hd->load(onnx_dir);
+        sh->impl = std::move(hd);
+    } catch (const StcError& e) { return fail(nullptr, e.code, e.what()); }
+    catch (const std::exception& e) { return fail(nullptr, STC_ERR_IO, e.what()); }
+    *out = sh.release();
+    return STC_OK;
+}
+
+void stc_destroy(stc_handle* h) {
+    if (!h) return;
+    if (h->impl) { cudaSetDevice(h->impl->device); cudaStreamSynchronize(h->impl->stream); }
+    delete h;
+}
+
+int stc_get_config(const stc_handle* h, stc_config* out) {
+    if (!h || !out) return STC_ERR_INVALID;
+    *out = h->impl->cfg;
+    return STC_OK;
+}
+
+uint64_t stc_launch_count(const stc_handle* h) { return h ? h->impl->launches : 0; }
+int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID; h->impl->use_graphs = enabled != 0; return STC_OK; }
+void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
+int stc_set_profile(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID; h->impl->profile = enabled != 0; return STC_OK; }
+int stc_last_stage_ms(const stc_handle* h, float out[5]) {
+    if (!h || !out) return STC_ERR_INVALID;
+    memcpy(out, h->impl->stage_ms, sizeof(float) * 5);
+    return STC_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers shared by the entry points
+namespace {
+struct Scope {   // per-call: select device, reset arena
+    Handle* h;
+    explicit Scope(stc_handle* sh) : h(sh ? sh->impl.get() : nullptr) {
+        if (!h) throw StcError(STC_ERR_INVALID, "null handle");
+        STC_CUDA(cudaSetDevice(h->device));
+        h->arena.reset(); h->persist.reset();
+    }
+};
+template <typename T> T* upp(Handle* h, const T* host, size_t n) {   // into the persistent arena
+    T* d = h->ps<T>(n);
+    if (!h->dry) STC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return d;
+}
+template <typename T> T* up(Handle* h, const T* host, size_t n) {
+    T* d = h->ws<T>(n);
+    if (!h->dry) STC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return d;
+}
+void validate_ids(const int64_t* ids, size_t n, int V) {
+    for (size_t i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= V) throw StcError(STC_ERR_INVALID, "text_ids value out of the embedding table range");
+}
+void transpose(Handle* h, const float* in, float* out, int batch, int R, int Cc) {
+    dim3 grid(cdiv(Cc, 32), cdiv(R, 32), batch);
+    STC_LAUNCH(h, (transpose_kernel<float, float>), grid, dim3(32, 8), 0, in, out, R, Cc);
+}
+}  // namespace
+
+extern "C" {
+
+int stc_duration(stc_handle* sh, const int64_t* text_ids, const float* style_dp, const float* text_mask, int B, int T,
+                 float* duration_out) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (B <= 0 || T <= 0 || !text_ids || !style_dp || !text_mask || !duration_out) throw StcError(STC_ERR_INVALID, "stc_duration: bad argument");
+        validate_ids(text_ids, (size_t)B * T, h->cfg.vocab_size);
+        int si = h->cfg.style_dp_tokens * h->cfg.style_dp_dim;
+        auto body = [&]() {
+            h->arena.reset();
+            int64_t* d_ids = up(h, text_ids, (size_t)B * T);
+            float* d_sty = up(h, style_dp, (size_t)B * si);
+            float* d_mask = up(h, text_mask, (size_t)B * T);
+            float* d_dur = h->ws<float>(B);
+            h->run_dp(d_ids, d_sty, d_mask, B, T, d_dur);
+            if (!h->dry) STC_CUDA(cudaMemcpyAsync(duration_out, d_dur, B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        };
+        h->ensure_ws(body);
+        body();
+        STC_CUDA(cudaStreamSynchronize(h->stream));
+        h->check_launch("stc_duration");
+    })
+}
+
+int stc_text_encode(stc_handle* sh, const int64_t* text_ids, const float* style_ttl, const float* text_mask, int B, int T,
+                    float* text_emb_out, int64_t shape_out[3]) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (B <= 0 || T <= 0 || !text_ids || !style_ttl || !text_mask || !text_emb_out) throw StcError(STC_ERR_INVALID, "stc_text_encode: bad argument");
+        validate_ids(text_ids, (size_t)B * T, h->cfg.vocab_size);
+        int C = h->cfg.text_emb_channels, S = h->cfg.style_ttl_tokens, Cs = h->cfg.style_ttl_dim;
+        auto body = [&]() {
+            h->arena.reset();
+            int64_t* d_ids = up(h, text_ids, (size_t)B * T);
+            float* d_sty = up(h, style_ttl, (size_t)B * S * Cs);
+            float* d_mask = up(h, text_mask, (size_t)B * T);
+            float* d_cl = h->ws<float>((size_t)B * T * C);
+            float* d_ncl = h->ws<float>((size_t)B * T * C);
+            h->run_te(d_ids, d_sty, d_mask, B, T, d_cl);
+            transpose(h, d_cl, d_ncl, B, T, C);                       // [B,T,C] -> [B,C,T] (reference layout)
+            if (!h->dry) STC_CUDA(cudaMemcpyAsync(text_emb_out, d_ncl, (size_t)B * T * C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        };
+        h->ensure_ws(body);
+        body();
+        STC_CUDA(cudaStreamSynchronize(h->stream));
+        h->check_launch("stc_text_encode");
+        if (shape_out) { shape_out[0] = B; shape_out[1] = C; shape_out[2] = T; }
+    })
+}
+
+int stc_vector_step(stc_handle* sh, const float* noisy_latent, const float* text_emb, const float* style_ttl, const float* text_mask,
+                    const float* latent_mask, const float* total_step, const float* current_step, int B, int L, int T,
+                    float* denoised_out) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (B <= 0 || L <= 0 || T <= 0 || !noisy_latent || !text_emb || !style_ttl || !text_mask || !latent_mask || !total_step ||
+            !current_step || !denoised_out)
+            throw StcError(STC_ERR_INVALID, "stc_vector_step: bad argument");
+        for (int b = 1; b < B; ++b)
+            if (total_step[b] != total_step[0] || current_step[b] != current_step[0])
+                throw StcError(STC_ERR_UNSUPPORTED, "per-utterance step counters must be equal (the reference passes one value, cpp/helper.cpp:573,591)");
+        int C = h->cfg.text_emb_channels, S = h->cfg.style_ttl_tokens, Cs = h->cfg.style_ttl_dim, D = h->cfg.latent_channels;
+        float dt = 1.0f / total_step[0];
+        auto body = [&]() {
+            h->arena.reset();
+            float* d_x_ncl = up(h, noisy_latent, (size_t)B * D * L);
+            float* d_te_ncl = up(h, text_emb, (size_t)B * C * T);
+            float* d_sty = up(h, style_ttl, (size_t)B * S * Cs);
+            float* d_tm = up(h, text_mask, (size_t)B * T);
+            float* d_lm = up(h, latent_mask, (size_t)B * L);
+            float* d_tot = up(h, total_step, (size_t)B);
+            float* d_cur = up(h, current_step, (size_t)B);
+            float* d_x = h->ws<float>((size_t)B * L * D);
+            float* d_te = h->ws<float>((size_t)B * T * C);
+            float* d_dt = h->ws<float>(D);
+            transpose(h, d_x_ncl, d_x, B, D, L);
+            transpose(h, d_te_ncl, d_te, B, C, T);
+            STC_LAUNCH(h, fill_kernel, cdiv(D, 128), 128, 0, d_dt, dt, (size_t)D);
+            VeCtx vc; vc.B = B; vc.L = L; vc.T = T; vc.lmask = d_lm; vc.tmask = d_tm;
+            h->prepare_ve(vc, d_te, d_sty);
+            h->run_ve_step(vc, d_x, d_cur, d_tot, d_dt);
+            transpose(h, d_x, d_x_ncl, B, L, D);
+            if (!h->dry) STC_CUDA(cudaMemcpyAsync(denoised_out, d_x_ncl, (size_t)B * D * L * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        };
+        h->ensure_ws(body);
+        body();
+        STC_CUDA(cudaStreamSynchronize(h->stream));
+        h->check_launch("stc_vector_step");
+    })
+}
+
+int stc_vocode(stc_handle* sh, const float* latent, int B, int L, float* wav_out) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (B <= 0 || L <= 0 || !latent || !wav_out) throw StcError(STC_ERR_INVALID, "stc_vocode: bad argument");
+        int D = h->cfg.latent_channels; size_t nw = (size_t)B * L * h->cfg.chunk_size;
+        auto body = [&]() {
+            h->arena.reset();
+            float* d_ncl = up(h, latent, (size_t)B * D * L);
+            float* d_cl = h->ws<float>((size_t)B * D * L);
+            float* d_wav = h->ws<float>(nw);
+            transpose(h, d_ncl, d_cl, B, D, L);
+            h->run_vocoder(d_cl, B, L, d_wav);
+            if (!h->dry) STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, nw * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        };
+        h->ensure_ws(body);
+        body();
+        STC_CUDA(cudaStreamSynchronize(h->stream));
+        h->check_launch("stc_vocode");
+    })
+}
+
+}  // extern "C"
+
+// ---- fast layer ---------------------------------------------------------------------------------
+namespace stc {
+
+// float32 length math of sampleNoisyLatent (cpp/helper.cpp:430-438) — IEEE single precision, no contraction
+static int latent_len_f32(const float* dur, int B, int sr, int cs) {
+    volatile float mx = dur[0];
+    for (int b = 1; b < B; ++b) if (dur[b] > mx) mx = dur[b];
+    volatile float wav_len_max = mx * (float)sr;
+    volatile float t = wav_len_max + (float)cs;
+    t = t - 1.0f;
+    volatile float q = t / (float)cs;
+    return (int)q;
+}
+
+void Handle::synth_tail(const float* d_text_emb, const float* d_tmask, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
+                        uint64_t seed, const int64_t* d_wavlen, int B, int T, int L, int steps, float* d_lmask, float* d_xlat, float* d_wav) {
+    int D = cfg.latent_channels;
+    STC_LAUNCH(this, latent_mask_kernel, cdiv((size_t)B * L, 256), 256, 0, d_wavlen, d_lmask, B, L, cfg.chunk_size);
+    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)B * L * D, 256), 256, 0, d_noise, noise_ld, seed, d_lmask, d_xlat, B, D, L);
+    VeCtx vc; vc.B = B; vc.L = L; vc.T = T; vc.lmask = d_lmask; vc.tmask = d_tmask;
+    prepare_ve(vc, d_text_emb, d_style_ttl);
+    float* d_tot = ws<float>(B); float* d_cur = ws<float>((size_t)B * steps); float* d_dt = ws<float>(D);
+    STC_LAUNCH(this, fill_kernel, cdiv(B, 128), 128, 0, d_tot, (float)steps, (size_t)B);
+    STC_LAUNCH(this, fill_kernel, cdiv(D, 128), 128, 0, d_dt, 1.0f / (float)steps, (size_t)D);
+    for (int s = 0; s < steps; ++s) {
+        STC_LAUNCH(this, fill_kernel, cdiv(B, 128), 128, 0, d_cur + (size_t)s * B, (float)s, (size_t)B);
+        run_ve_step(vc, d_xlat, d_cur + (size_t)s * B, d_tot, d_dt);
+    }
+    if (profile && !dry) cudaEventRecord(ev[3], stream);
+    run_vocoder(d_xlat, B, L, d_wav);
+}
+
+}  // namespace stc
+
+extern "C" {
+
+static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                      const float* style_dp, int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld,
+                      uint64_t seed, float* wav_out, int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
+                      float* latent_out) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (B <= 0 || T <= 0 || total_step <= 0 || !(speed > 0.f) || !text_ids || !text_mask || !style_ttl || !style_dp || !wav_out)
+            throw StcError(STC_ERR_INVALID, "stc_synthesize: bad argument");
+        const stc_config& c = h->cfg;
+        int C = c.text_emb_channels, S = c.style_ttl_tokens, Cs = c.style_ttl_dim, D = c.latent_channels;
+        int si = c.style_dp_tokens * c.style_dp_dim;
+        if (host_io) validate_ids(text_ids, (size_t)B * T, c.vocab_size);
+        if (h->h_cap < B) {
+            if (h->h_dur) cudaFreeHost(h->h_dur);
+            if (h->h_wavlen) cudaFreeHost(h->h_wavlen);
+            STC_CUDA(cudaMallocHost((void**)&h->h_dur, sizeof(float) * B));
+            STC_CUDA(cudaMallocHost((void**)&h->h_wavlen, sizeof(int64_t) * B));
+            h->h_cap = B;
+        }
+        cudaStream_t st = h->stream;
+        // ---- stage 1: DP (+ /speed, wav lengths) and TE; sized independently of L
+        const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
+        float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
+        auto stage1 = [&]() {
+            h->arena.reset(); h->persist.reset();
+            if (host_io) {
+                d_ids = upp(h, text_ids, (size_t)B * T); d_tmask = upp(h, text_mask, (size_t)B * T);
+                d_sttl = upp(h, style_ttl, (size_t)B * S * Cs); d_sdp = upp(h, style_dp, (size_t)B * si);
+            } else { d_ids = text_ids; d_tmask = text_mask; d_sttl = style_ttl; d_sdp = style_dp; }
+            d_dur = h->ps<float>(B); d_wavlen = h->ps<int64_t>(B); d_temb = h->ps<float>((size_t)B * T * C);
+            if (h->profile && !h->dry) cudaEventRecord(h->ev[0], st);
+            h->run_dp(d_ids, d_sdp, d_tmask, B, T, d_dur);
+            STC_LAUNCH(h, dur_post_kernel, cdiv(B, 128), 128, 0, d_dur, d_wavlen, B, speed, c.sample_rate);
+            if (!h->dry) {
+                STC_CUDA(cudaMemcpyAsync(h->h_dur, d_dur, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+                STC_CUDA(cudaMemcpyAsync(h->h_wavlen, d_wavlen, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+                if (h->profile) cudaEventRecord(h->ev[1], st);
+                cudaEventRecord(h->ev[6], st);
+            }
+            h->run_te(d_ids, d_sttl, d_tmask, B, T, d_temb);      // overlaps the D2H of the durations
+            if (h->profile && !h->dry) cudaEventRecord(h->ev[2], st);
+        };
+        h->ensure_ws(stage1);
+        stage1();
+        STC_CUDA(cudaEventSynchronize(h->ev[6]));                 // the one data-dependent sync: duration -> L
+        int L = latent_len_f32(h->h_dur, B, c.sample_rate, c.chunk_size);
+        if (L_out) *L_out = L;
+        if (duration_out && host_io) memcpy(duration_out, h->h_dur, sizeof(float) * B);
+        if (wav_lengths_out) memcpy(wav_lengths_out, h->h_wavlen, sizeof(int64_t) * B);
+        if (L <= 0) throw StcError(STC_ERR_INVALID, "computed latent length is 0");
+        int64_t wav_row = (int64_t)L * c.chunk_size;
+        if (wav_ld < wav_row) throw StcError(STC_ERR_CAPACITY, "wav_out rows too short: need " + std::to_string(wav_row));
+        if (noise && noise_ld < L) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length " + std::to_string(L));
+        // ---- stage 2: everything that depends on L
+        float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
+        auto stage2 = [&]() {
+            h->arena.reset();
+            d_noise = nullptr;
+            if (noise) d_noise = up(h, noise, (size_t)B * D * noise_ld);
+            d_lmask = h->ws<float>((size_t)B * L); d_xlat = h->ws<float>((size_t)B * L * D);
+            d_wav = host_io ? h->ws<float>((size_t)B * wav_row) : wav_out;
+            if (latent_out) d_lat_ncl = h->ws<float>((size_t)B * L * D);
+            h->synth_tail(d_temb, d_tmask, d_sttl, d_noise, noise_ld, seed, d_wavlen, B, T, L, total_step, d_lmask, d_xlat, d_wav);
+        };
+        // NOTE: in device-I/O mode the wav rows are dense [B][L*cs] at the start of wav_dev when wav_ld == L*cs;
+        // otherwise rows are compacted by the caller via L_out.
+        h->ensure_ws(stage2);
+        stage2();
+        if (h->profile) cudaEventRecord(h->ev[4], st);
+        if (host_io) {
+            STC_CUDA(cudaMemcpy2DAsync(wav_out, (size_t)wav_ld * sizeof(float), d_wav, (size_t)wav_row * sizeof(float),
+                                       (size_t)wav_row * sizeof(float), B, cudaMemcpyDeviceToHost, st));
+            if (latent_out) {
+                transpose(h, d_xlat, d_lat_ncl, B, L, D);
+                STC_CUDA(cudaMemcpyAsync(latent_out, d_lat_ncl, (size_t)B * L * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
+        } else if (duration_out) {
+            STC_CUDA(cudaMemcpyAsync(duration_out, d_dur, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+        }
+        if (h->profile) cudaEventRecord(h->ev[5], st);
+        STC_CUDA(cudaStreamSynchronize(st));
+        h->check_launch("stc_synthesize");
+        if (h->profile) {
+            cudaEventElapsedTime(&h->stage_ms[0], h->ev[0], h->ev[1]);
+            cudaEventElapsedTime(&h->stage_ms[1], h->ev[1], h->ev[2]);
+            cudaEventElapsedTime(&h->stage_ms[2], h->ev[2], h->ev[3]);
+            cudaEventElapsedTime(&h->stage_ms[3], h->ev[3], h->ev[4]);
+            cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+        }
+    })
+}
+
+int stc_synthesize(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl, const float* style_dp,
+                   int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld, uint64_t seed, float* wav_out,
+                   int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out, float* latent_out) {
+    return synth_impl(h, true, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_ld,
+                      duration_out, wav_lengths_out, L_out, latent_out);
+}
+
+int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,
+                          const float* style_dp_dev, int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
+                          int64_t wav_ld, float* duration_dev, int64_t* L_out) {
+    return synth_impl(h, false, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
+                      wav_dev, wav_ld, duration_dev, nullptr, L_out, nullptr);
+}
+
+int stc_text_to_ids(stc_handle* sh, const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,
+                    int64_t T_cap, int64_t* T_out) {
+    STC_TRY(sh, {
+        if (!sh || !texts || !langs || n <= 0) throw StcError(STC_ERR_INVALID, "stc_text_to_ids: bad argument");
+        sh->impl->frontend.call(texts, langs, n, text_ids, text_mask, T_cap, T_out);
+    })
+}
+
+struct stc_frontend { stc::TextFrontend fe; };
+
+int stc_frontend_open(const char* unicode_indexer_json, stc_frontend** out) {
+    STC_TRY(nullptr, {
+        if (!unicode_indexer_json || !out) throw StcError(STC_ERR_INVALID, "stc_frontend_open: bad argument");
+        auto f = std::make_unique<stc_frontend>();
+        try { f->fe.load_indexer(unicode_indexer_json); } catch (const std::exception& e) { throw StcError(STC_ERR_IO, e.what()); }
+        *out = f.release();
+    })
+}
+void stc_frontend_close(stc_frontend* fe) { delete fe; }
+int stc_frontend_text_to_ids(const stc_frontend* fe, const char* const* texts, const char* const* langs, int n, int64_t* text_ids,
+                             float* text_mask, int64_t T_cap, int64_t* T_out) {
+    STC_TRY(nullptr, {
+        if (!fe || !texts || !langs || n <= 0) throw StcError(STC_ERR_INVALID, "stc_frontend_text_to_ids: bad argument");
+        fe->fe.call(texts, langs, n, text_ids, text_mask, T_cap, T_out);
+    })
+}
+
+int stc_chunk_text(const char* text, int max_len, char* out_buf, size_t out_cap, size_t* out_len, int* n_out) {
+    STC_TRY(nullptr, {
+        if (!text || !n_out || !out_len) throw StcError(STC_ERR_INVALID, "stc_chunk_text: bad argument");
+        std::vector<std::string> chunks = stc::chunk_text(text, max_len);
+        size_t need = 0;
+        for (auto& c : chunks) need += c.size() + 1;
+        *out_len = need; *n_out = (int)chunks.size();
+        if (!out_buf || out_cap < need) throw StcError(STC_ERR_CAPACITY, "stc_chunk_text: buffer too small");
+        size_t o = 0;
+        for (auto& c : chunks) { memcpy(out_buf + o, c.data(), c.size()); o += c.size(); out_buf[o++] = '\0'; }
+    })
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(include/supertonic_cuda.h via supertonic_b200.capi), against the CPU oracle on identical inputs —
+same injected Gaussian noise, same style vectors (north_star).
+
+Tolerances (written here, per north_star):
+  * integer quantities derived from duration_predictor — wav_lengths, latent_len, latent mask — BIT-EXACT;
+    the float32 durations themselves are compared bit-exact too (both sides evaluate DP in fp64 and round once);
+  * normalised latents: max-abs <= 1e-3 (north-star bound); we additionally assert the 2e-4 we actually expect
+    from split-bf16 (bf16x3) products with fp32 accumulation;
+  * waveform SNR >= 40 dB (north-star bound); expected >= 80 dB.
+"""
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+LAT_TOL_NORTH_STAR, LAT_TOL_EXPECTED = 1e-3, 2e-4
+SNR_NORTH_STAR, SNR_EXPECTED = 40.0, 80.0
+
+
+@pytest.fixture(scope="module", params=["tiny", "full"])
+def rig(request):
+    from oracle.pipeline import OraclePipeline
+    from supertonic_b200 import capi, surrogate
+    root = surrogate.ensure_assets(request.param)
+    eng = capi.Engine(root + "/onnx")
+    yield dict(name=request.param, root=root, eng=eng, ora=OraclePipeline(root), capi=capi)
+    eng.close()
+
+
+def _inputs(rig, seed, n, lo=20, hi=120, langs=None, texts=None):
+    from oracle import host_ref
+    if texts is None:
+        texts, langs = U.make_batch(seed, n, lo, hi)
+    ids, mask = host_ref.unicode_processor_call(rig["ora"].indexer, texts, langs)
+    names = [("M1", "F1", "M2", "F2")[i % 4] for i in range(len(texts))]
+    ttl, dp = U.styles(rig["root"], names)
+    return ids, mask, ttl, dp
+
+
+def test_duration_bit_exact(rig):
+    from oracle import host_ref
+    for seed, n in [(1, 1), (2, 4), (3, 7), (4, 16)]:
+        ids, mask, ttl, dp = _inputs(rig, seed, n)
+        want = rig["ora"].dp(dict(text_ids=ids, style_dp=dp, text_mask=mask)).reshape(-1)
+        got = rig["eng"].duration(ids, dp, mask)
+        assert got.dtype == np.float32 and got.shape == (n,)
+        np.testing.assert_array_equal(got, want)
+        g = host_ref.latent_geometry(got / np.float32(1.05), 44100, 512, 6)
+        w = host_ref.latent_geometry(want / np.float32(1.05), 44100, 512, 6)
+        np.testing.assert_array_equal(g[0], w[0]); assert g[1] == w[1]; np.testing.assert_array_equal(g[2], w[2])
+
+
+def test_text_encoder_parity(rig):
+    for seed, n in [(11, 1), (12, 5)]:
+        ids, mask, ttl, dp = _inputs(rig, seed, n)
+        want = rig["ora"].te(dict(text_ids=ids, style_ttl=ttl, text_mask=mask))
+        got = rig["eng"].text_encode(ids, ttl, mask)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= LAT_TOL_EXPECTED, np.abs(got - want).max()
+        # padded token positions are exactly zero on both sides
+        assert np.all(got * (1 - mask) == 0)
+
+
+def test_multilingual_text_encoder(rig):
+    texts = [U.KO, U.ES, U.PT, U.FR, "Plain English sentence here."]
+    ids, mask, ttl, dp = _inputs(rig, 0, 5, texts=texts, langs=["ko", "es", "pt", "fr", "en"])
+    want = rig["ora"].te(dict(text_ids=ids, style_ttl=ttl, text_mask=mask))
+    got = rig["eng"].text_encode(ids, ttl, mask)
+    assert np.abs(got - want).max() <= LAT_TOL_EXPECTED
+    np.testing.assert_array_equal(rig["eng"].duration(ids, dp, mask),
+                                  rig["ora"].dp(dict(text_ids=ids, style_dp=dp, text_mask=mask)).reshape(-1))
+
+
+def test_vector_estimator_step_parity(rig):
+    rng = np.random.default_rng(5)
+    for n, L, step, total in [(1, 37, 0, 5), (3, 70, 2, 5), (2, 129, 9, 10)]:
+        ids, mask, ttl, dp = _inputs(rig, 20 + n, n)
+        temb = rig["ora"].te(dict(text_ids=ids, style_ttl=ttl, text_mask=mask))
+        lens = rng.integers(L // 2, L + 1, size=n); lens[0] = L
+        lmask = (np.arange(L)[None, None, :] < lens[:, None, None]).astype(np.float32)
+        x = rng.standard_normal((n, 144, L)).astype(np.float32) * lmask
+        feeds = dict(noisy_latent=x, text_emb=temb, style_ttl=ttl, text_mask=mask, latent_mask=lmask,
+                     total_step=np.full(n, total, np.float32), current_step=np.full(n, step, np.float32))
+        want = rig["ora"].ve(feeds)
+        got = rig["eng"].vector_step(**feeds)
+        err = np.abs(got - want).max()
+        assert err <= LAT_TOL_NORTH_STAR and err <= LAT_TOL_EXPECTED, err
+        assert np.all(got * (1 - lmask) == 0)
+
+
+def test_vocoder_parity(rig):
+    rng = np.random.default_rng(6)
+    for n, L in [(1, 9), (2, 40)]:
+        lat = rng.standard_normal((n, 144, L)).astype(np.float32)
+        lat[-1, :, L // 2:] = 0            # a masked tail, as the loop leaves it; the vocoder still decodes it
+        want = rig["ora"].voc(dict(latent=lat))
+        got = rig["eng"].vocode(lat)
+        assert got.shape == (n, L * 3072)
+        assert U.snr_db(got, want) >= SNR_EXPECTED, U.snr_db(got, want)
+
+
+@pytest.mark.parametrize("steps", [2, 5])
+def test_synthesize_matches_oracle_infer(rig, steps):
+    """Whole `_infer` (cpp/helper.cpp:469-683) with injected noise: durations/frame counts bit-exact,
+    latents and waveform within tolerance."""
+    from oracle.pipeline import make_noise
+    ids, mask, ttl, dp = _inputs(rig, 30 + steps, 3, 30, 90)
+    tr = {}
+    wav_ref, dur_ref = rig["ora"].infer_ids(ids, mask, ttl, dp, steps, np.float32(1.05), make_noise(7), tr)
+    L = tr["latent_len"]
+    noise = make_noise(7)(3, 144, L)
+    out = rig["eng"].synthesize(ids, mask, ttl, dp, steps, 1.05, noise=noise, want_latent=True)
+    assert out["L"] == L
+    np.testing.assert_array_equal(out["duration"], dur_ref)
+    np.testing.assert_array_equal(out["wav_lengths"], tr["wav_lengths"])
+    err = np.abs(out["latent"] - tr["xs"][-1]).max()
+    assert err <= LAT_TOL_NORTH_STAR and err <= LAT_TOL_EXPECTED, err
+    snr = U.snr_db(out["wav"].reshape(-1), wav_ref)
+    assert snr >= SNR_NORTH_STAR and snr >= SNR_EXPECTED, snr
+
+
+def test_noise_stride_and_capacity_retry(rig):
+    from oracle.pipeline import make_noise
+    ids, mask, ttl, dp = _inputs(rig, 40, 2, 30, 60)
+    tr = {}
+    wav_ref, _ = rig["ora"].infer_ids(ids, mask, ttl, dp, 2, np.float32(1.05), make_noise(3), tr)
+    L = tr["latent_len"]
+    wide = np.zeros((2, 144, L + 13), np.float32)
+    wide[:, :, :L] = make_noise(3)(2, 144, L)                     # noise_ld > L
+    out = rig["eng"].synthesize(ids, mask, ttl, dp, 2, 1.05, noise=wide, wav_cap=3072)   # forces STC_ERR_CAPACITY + retry
+    assert out["L"] == L and U.snr_db(out["wav"].reshape(-1), wav_ref) >= SNR_EXPECTED
+
+
+def test_batch_composition_invariance(rig):
+    """An utterance synthesised alone equals the same utterance inside a ragged batch on its valid region
+    (what makes length-bucketing parity-neutral)."""
+    ids, mask, ttl, dp = _inputs(rig, 50, 4, 20, 110)
+    rng = np.random.default_rng(9)
+    full = rig["eng"].synthesize(ids, mask, ttl, dp, 3, 1.05, noise=rng.standard_normal((4, 144, 400)).astype(np.float32),
+                                 want_latent=True)
+    rng = np.random.default_rng(9)
+    nz = rng.standard_normal((4, 144, 400)).astype(np.float32)
+    for b in range(4):
+        t = int(mask[b].sum())
+        one = rig["eng"].synthesize(ids[b:b + 1, :t], mask[b:b + 1, :, :t], ttl[b:b + 1], dp[b:b + 1], 3, 1.05,
+                                    noise=nz[b:b + 1], want_latent=True)
+        np.testing.assert_array_equal(one["duration"], full["duration"][b:b + 1])
+        n = int(one["wav_lengths"][0])
+        Lb = one["L"]
+        assert np.abs(one["latent"][0] - full["latent"][b, :, :Lb]).max() <= 1e-5
+        assert U.snr_db(one["wav"][0, :n], full["wav"][b, :n]) >= 90.0
+
+
+def test_fp32_simt_cross_check(rig):
+    """The CUDA-core fp32 GEMM path and the tcgen05 split-bf16 path agree (guards the descriptor/swizzle plumbing)."""
+    capi = rig["capi"]
+    eng2 = capi.Engine(rig["root"] + "/onnx", precision=capi.PREC_FP32_SIMT)
+    try:
+        ids, mask, ttl, dp = _inputs(rig, 60, 2, 30, 70)
+        a = rig["eng"].text_encode(ids, ttl, mask)
+        b = eng2.text_encode(ids, ttl, mask)
+        assert np.abs(a - b).max() <= LAT_TOL_EXPECTED
+        np.testing.assert_array_equal(rig["eng"].duration(ids, dp, mask), eng2.duration(ids, dp, mask))
+    finally:
+        eng2.close()
+
+
+def test_error_paths(rig):
+    capi, eng = rig["capi"], rig["eng"]
+    ids, mask, ttl, dp = _inputs(rig, 70, 1)
+    bad = ids.copy(); bad[0, 0] = 10 ** 6
+    with pytest.raises(capi.StcError) as e:
+        eng.duration(bad, dp, mask)
+    assert e.value.code == -1
+    with pytest.raises(capi.StcError):
+        capi.Engine("/nonexistent/onnx")
+    assert eng.launches > 0
