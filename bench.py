@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds per wall-second of the Supertonic synthesis forward pass (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] — a batch of 32 mixed-length English utterances
+(character lengths uniform{20..300}, numpy default_rng(1234), README lengths 59/152/266 included),
+total_step=5, speed=1.05, voices cycling M1/F1/M2/F2, surrogate full-size graphs (the released weights are not
+mounted: SURVEY.md §0). One "step" = one pass of the hot path over that batch; with N GPUs every rank
+synthesises its own 32-utterance batch (weak scaling, replicas only, no collective on the data path).
+
+  value : device-resident leg — text_ids/masks/styles already in HBM, stc_synthesize_device per length bucket,
+          CUDA events on the library's stream, L2 flushed (untimed) between steps.
+  e2e   : same work through the public API (TextToSpeech.synthesize_many): host text front-end, H2D of the
+          inputs and D2H of every waveform inside the timed region.
+  --impl reference : the reference's CPU path restated (oracle/, torch-CPU ONNX interpreter on all host cores;
+          ONNX Runtime itself is not installable here — DESIGN.md) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+README_LENGTHS = (59, 152, 266)          # reference README.md:192
+WORDS = ("the quick brown fox jumps over a lazy dog while seven silver ships sail south toward quiet harbours and "
+         "nobody knows why morning light feels warmer after rain or how distant thunder rolls across open fields "
+         "yesterday we walked along the river talking about music science and old friends from school").split()
+
+
+def workload(n=32, seed=1234):
+    rng = np.random.default_rng(seed)
+    lens = [int(x) for x in rng.integers(20, 301, size=n)]
+    for i, v in enumerate(README_LENGTHS):
+        if i < n:
+            lens[i] = v
+    texts = []
+    for ln in lens:
+        out = []
+        while sum(len(w) + 1 for w in out) < ln:
+            out.append(WORDS[rng.integers(len(WORDS))])
+        s = " ".join(out)[:ln].strip()
+        texts.append(s[0].upper() + s[1:])
+    return texts, ["en"] * n, [("M1", "F1", "M2", "F2")[i % 4] for i in range(n)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], bf16=j["bf16_tflops"], bf16_sustained=j["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+def oracle_run(texts, langs, voices, total_step, reps):
+    """CPU arm: the oracle port of the reference `_infer` (one padded batch, like TextToSpeech::batch)."""
+    import torch
+    from oracle.pipeline import OraclePipeline, make_noise
+    from supertonic_b200 import surrogate
+    root = surrogate.ensure_assets("full")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ora = OraclePipeline(root)
+    ttl, dp = ora.style(voices)
+    times, audio = [], 0.0
+    for r in range(reps):
+        t0 = time.perf_counter()
+        wav, dur = ora.batch(texts, langs, ttl, dp, total_step, 1.05, make_noise(r))
+        times.append(time.perf_counter() - t0)
+        audio = float(dur.sum())
+    return audio, times, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--total-step", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lrank = int(os.environ.get("LOCAL_RANK", 0))
+    cfg = {"workload": f"configs[1]: batch {a.batch} mixed-length English utterances (chars uniform 20..300, seed 1234), "
+                       f"total_step={a.total_step}, speed=1.05, per GPU", "weights": "surrogate full-size graphs (random init, seed 0)",
+           "l2": "flushed (512 MiB write) between timed steps", "parallelism": f"replicas x{world}, utterance-sharded, no collective"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        texts, langs, voices = workload(a.batch)
+        k = min(a.cpu_sample, a.batch)
+        idx = list(np.linspace(0, a.batch - 1, k).astype(int))
+        st, sl, sv = [texts[i] for i in idx], [langs[i] for i in idx], [voices[i] for i in idx]
+        audio, times, cores = oracle_run(st, sl, sv, a.total_step, a.warmup + a.steps)
+        t = times[a.warmup:]
+        ms = 1000 * float(np.mean(t))
+        val = audio / (ms / 1000)
+        sample = f"{k} of the {a.batch} utterances (evenly spaced by index) as one padded batch per step"
+        print(json.dumps({"impl": "reference", "metric": "audio-sec/sec", "value": val, "unit": "audio-s/s", "n_gpus": a.gpus,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample,
+                                           "runtime": "oracle/ torch-CPU ONNX interpreter (not ONNX Runtime)"},
+                          "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from supertonic_b200 import capi, surrogate, tts as T
+    from supertonic_b200.scheduler import length_buckets
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    torch.cuda.set_device(lrank)
+    if lrank == 0:
+        root = surrogate.ensure_assets("full")
+    if world > 1:
+        dist.barrier()
+    root = surrogate.ensure_assets("full")
+    tt = T.load_text_to_speech(os.path.join(root, "onnx"), use_gpu=True, device=lrank)
+    eng = tt.engine
+    texts, langs, voices = workload(a.batch, 1234 + 1000 * rank)
+    style = T.load_voice_style([os.path.join(root, "voice_styles", v + ".json") for v in voices])
+    ext = torch.cuda.ExternalStream(eng.stream)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------------------
+    ids, mask = eng.text_to_ids(texts, langs)
+    lens = mask.reshape(a.batch, -1).sum(1).astype(np.int64)
+    cs = eng.cfg.chunk_size
+    buckets = []
+    for grp in length_buckets(lens, a.batch, 1.35):
+        g = np.asarray(grp); Tg = int(lens[g].max())
+        cap = (int(Tg * 0.12 * eng.cfg.sample_rate / cs) + 8) * cs
+        buckets.append(dict(B=len(g), T=Tg, cap=cap,
+                            ids=torch.from_numpy(np.ascontiguousarray(ids[g, :Tg])).cuda(),
+                            mask=torch.from_numpy(np.ascontiguousarray(mask[g, :, :Tg])).cuda(),
+                            ttl=torch.from_numpy(np.ascontiguousarray(style.ttl[g])).cuda(),
+                            dp=torch.from_numpy(np.ascontiguousarray(style.dp[g])).cuda(),
+                            wav=torch.empty(len(g) * cap, dtype=torch.float32, device="cuda"),
+                            dur=torch.empty(len(g), dtype=torch.float32, device="cuda")))
+
+    def device_step(seed):
+        for b in buckets:
+            b["L"] = eng.synthesize_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(),
+                                           b["B"], b["T"], a.total_step, 1.05, seed, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr())
+
+    for w in range(a.warmup):
+        device_step(w)
+    audio = float(sum(b["dur"].sum().item() for b in buckets))
+    barrier()
+    sampler = ClockSampler(lrank) if rank == 0 else None
+    l0 = eng.launches
+    step_ms = []
+    for k in range(a.steps):
+        flush.fill_(k & 0xFF)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+            device_step(100 + k)
+            e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    launches = eng.launches - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([float(np.sum(step_ms)), audio], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax[0:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
+    total_ms, audio_all = float(tmax[0].item()), float(t[1].item())
+    ms_per_step = total_ms / a.steps
+    value = audio_all / (ms_per_step / 1000)
+
+    # ---- end-to-end leg: public API, host buffers, front-end + H2D + D2H inside the timed region ---------
+    for w in range(max(1, a.warmup - 1)):
+        tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=a.batch)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for k in range(a.steps):
+        res = tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=a.batch, seed=k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_audio = float(sum(r[1] for r in res))
+    d2h = int(sum(b["B"] * b.get("L", 0) * cs * 4 + b["B"] * 12 for b in buckets))
+    h2d = int(sum(b["ids"].numel() * 8 + b["mask"].numel() * 4 + b["ttl"].numel() * 4 + b["dp"].numel() * 4 for b in buckets))
+    te = torch.tensor([e2e_s, e2e_audio], dtype=torch.float64, device="cuda")
+    temax = te.clone()
+    if world > 1:
+        dist.all_reduce(temax[0:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(te[1:2], op=dist.ReduceOp.SUM)
+    e2e_val = float(te[1].item()) / (float(temax[0].item()) / a.steps)
+
+    # ---- roofline leg (rank 0): per-launch CUDA events around the dominant kernel class -----------------
+    roof = None
+    stage = None
+    if rank == 0:
+        eng.set_profile(2)
+        prof = {"gemm_tc": dict(ms=0, flops=0, bytes=0, launches=0), "dwconv_ln": dict(ms=0, flops=0, bytes=0, launches=0),
+                "attention": dict(ms=0, flops=0, bytes=0, launches=0)}
+        stage = dict(dp=0.0, te=0.0, ve=0.0, vocoder=0.0, whole=0.0)
+        for b in buckets:
+            eng.synthesize_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(), b["B"], b["T"],
+                                  a.total_step, 1.05, 7, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr())
+            for k, v in eng.kernel_profile().items():
+                for kk in v:
+                    prof[k][kk] += v[kk]
+            for k, v in eng.stage_ms().items():
+                stage[k] += v
+        eng.set_profile(0)
+        pk = peaks()
+        g = prof["gemm_tc"]
+        ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"kernel": "tc::gemm_bf16x3_kernel<128> (tcgen05 kind::f16, 3 MMAs per K-slice)", "bound": "tensor",
+                "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)", "traffic": traffic,
+                "launches": g["launches"], "avg_launch_us": 1000 * g["ms"] / max(g["launches"], 1),
+                "algorithmic_flops_per_step": g["flops"], "executed_mma_flops_per_step": 3 * g["flops"],
+                "share_of_step": g["ms"] / max(stage["whole"], 1e-9),
+                "dwconv_ln": {"bound": "hbm", "achieved_gbs": prof["dwconv_ln"]["bytes"] / max(prof["dwconv_ln"]["ms"], 1e-9) / 1e6,
+                              "peak_gbs": pk["hbm"], "launches": prof["dwconv_ln"]["launches"],
+                              "share_of_step": prof["dwconv_ln"]["ms"] / max(stage["whole"], 1e-9)},
+                "attention": {"achieved_tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9,
+                              "launches": prof["attention"]["launches"],
+                              "share_of_step": prof["attention"]["ms"] / max(stage["whole"], 1e-9)}}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        k = min(a.cpu_sample, a.batch)
+        idx = list(np.linspace(0, a.batch - 1, k).astype(int))
+        audio_c, times, cores = oracle_run([texts[i] for i in idx], [langs[i] for i in idx], [voices[i] for i in idx], a.total_step, 3)
+        cpu = {"value": audio_c / float(np.mean(times[1:])), "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"{k} of the {a.batch} utterances as one padded batch, 2 timed repetitions after 1 warm-up",
+               "runtime": "oracle/ torch-CPU ONNX interpreter (not ONNX Runtime)"}
+    out = {"metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32",
+           "data": "synthetic", "config": dict(cfg, buckets=[[b["B"], b["T"], b.get("L")] for b in buckets],
+                                               audio_s_per_step_per_gpu=audio),
+           "clocks": clocks, "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                     "ms_per_step": 1000 * float(temax[0].item()) / a.steps},
+           "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
+           "p50_step_ms": float(np.median(step_ms))}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -145,8 +145,12 @@ int stc_set_graphs(stc_handle* h, int enabled);
 /* cudaStream_t the handle launches on (as void*), for callers that time with CUDA events. */
 void* stc_stream(stc_handle* h);
 /* Device-side timing of the most recent stc_synthesize* call: milliseconds per stage
- * {dp, te, ve_total, vocoder, whole}. Requires stc_set_profile(h,1) (adds event records). */
-int stc_set_profile(stc_handle* h, int enabled);
+ * {dp, te, ve_total, vocoder, whole}. Requires stc_set_profile(h, >=1) (adds event records). */
+int stc_set_profile(stc_handle* h, int level);   /* 0 off, 1 stage events, 2 + per-kernel events (bench roofline leg) */
+/* Per-kernel-class totals of the most recent stc_synthesize* call at profile level 2.
+ * cls: 0 = tcgen05 GEMM, 1 = depthwise-conv+LayerNorm, 2 = attention core.
+ * out = {milliseconds (CUDA events around each launch), algorithmic FLOPs, algorithmic bytes, launches}. */
+int stc_kernel_profile(const stc_handle* h, int cls, double out[4]);
 int stc_last_stage_ms(const stc_handle* h, float out[5]);
 
 #ifdef __cplusplus

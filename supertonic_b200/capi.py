@@ -54,6 +54,7 @@ _SIGS = {
     "stc_stream": (_vp, [_vp]),
     "stc_set_profile": (_i, [_vp, _i]),
     "stc_last_stage_ms": (_i, [_vp, _vp]),
+    "stc_kernel_profile": (_i, [_vp, _i, _vp]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here == header and library out of sync
@@ -224,6 +225,19 @@ class Engine:
             res["latent"] = lat.reshape(-1)[:B * self.cfg.latent_channels * Lv].reshape(B, self.cfg.latent_channels, Lv)
         return res
 
+    def synthesize_device(self, ids_ptr: int, mask_ptr: int, sttl_ptr: int, sdp_ptr: int, B: int, T: int, total_step: int,
+                          speed: float, seed: int, wav_ptr: int, wav_ld: int, dur_ptr: int) -> int:
+        """Device-resident variant (raw device pointers, e.g. torch `.data_ptr()`); returns L. Rows of wav are dense
+        [B][L*cs] from wav_ptr. Raises StcError(code=-5) when wav_ld < L*cs (retry with a larger buffer)."""
+        L = C.c_int64(0)
+        rc = lib.stc_synthesize_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, B, T, int(total_step), float(speed),
+                                       seed, wav_ptr, wav_ld, dur_ptr, C.byref(L))
+        if rc != STC_OK:
+            e = StcError(rc, lib.stc_last_error(self._h).decode())
+            e.L = L.value
+            raise e
+        return L.value
+
     def text_to_ids(self, texts, langs):
         return _texts_to_ids(lib.stc_text_to_ids, self._h, texts, langs)
 
@@ -235,8 +249,17 @@ class Engine:
     def set_graphs(self, on: bool):
         lib.stc_set_graphs(self._h, int(on))
 
-    def set_profile(self, on: bool):
-        lib.stc_set_profile(self._h, int(on))
+    def set_profile(self, level: int):
+        lib.stc_set_profile(self._h, int(level))
+
+    def kernel_profile(self):
+        """Per-kernel-class totals of the last synthesize call (profile level 2)."""
+        res = {}
+        for cls, name in enumerate(("gemm_tc", "dwconv_ln", "attention")):
+            out = np.zeros(4, np.float64)
+            lib.stc_kernel_profile(self._h, cls, _ptr(out))
+            res[name] = dict(ms=out[0], flops=out[1], bytes=out[2], launches=int(out[3]))
+        return res
 
     def stage_ms(self):
         out = np.zeros(5, np.float32)

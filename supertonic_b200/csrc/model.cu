@@ -68,7 +68,26 @@ struct Handle {
     EncodeTiledFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> map_cache;
     bool use_graphs = true;
-    bool profile = false;
+    int profile = 0;          // 0 off, 1 stage events, 2 + per-kernel events for the GEMM / dwconv+LN classes
+    struct KProf { double ms = 0, flops = 0, bytes = 0; uint64_t n = 0; };
+    KProf kprof[3];           // 0 = tcgen05 GEMM, 1 = dwconv+LayerNorm, 2 = attention core
+    struct Pending { int cls; cudaEvent_t a, b; double flops, bytes; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
+    cudaEvent_t pool_event() {
+        if (ev_next == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[ev_next++];
+    }
+    void kprof_begin(int cls, double flops, double bytes) {
+        if (profile < 2 || dry) return;
+        Pending p{cls, pool_event(), pool_event(), flops, bytes};
+        cudaEventRecord(p.a, stream); pending.push_back(p);
+    }
+    void kprof_end() { if (profile < 2 || dry) return; cudaEventRecord(pending.back().b, stream); }
+    void kprof_resolve() {
+        for (auto& p : pending) { float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b); auto& k = kprof[p.cls]; k.ms += ms; k.flops += p.flops; k.bytes += p.bytes; k.n++; }
+        pending.clear(); ev_next = 0;
+    }
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[7] = {};   // start, dp, te, ve, vocoder, end, duration-ready
     std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -148,6 +167,7 @@ Handle::~Handle() {
     if (h_dur) cudaFreeHost(h_dur);
     if (h_wavlen) cudaFreeHost(h_wavlen);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -418,7 +438,12 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
     const float* w = cn ? cn->dw_w : nullptr; const float* wb = cn ? cn->dw_b : nullptr;
     int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0;
     if constexpr (std::is_same<T, float>::value) {
-        if (out_act && out_act->hi) { launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, N, K, dil, pad, eps); return; }
+        if (out_act && out_act->hi) {
+            kprof_begin(1, (2.0 * K + 8.0) * rows * C, 8.0 * rows * C + 4.0 * C * (K + 3));
+            launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, N, K, dil, pad, eps);
+            kprof_end();
+            return;
+        }
         if (out_act) out_plain = out_act->f;
     }
     launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_plain}, rows, N, K, dil, pad, eps);
@@ -447,7 +472,9 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     CUtensorMap mh = ma_hi;
     CUtensorMap ml = act_map(a.lo, M, w.K);
     dim3 grid(cdiv(w.N, 128), cdiv(M, tc::BM));
+    kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<128>), grid, tc::NUM_THREADS, tc::Tile<128>::SMEM_BYTES, mh, ml, w.map_hi, w.map_lo, p);
+    kprof_end();
 }
 
 template <typename T>
@@ -479,6 +506,8 @@ void Handle::attn_core(const float* Q, const float* K, const float* V, const flo
                        int heads, int dh) {
     dim3 grid(cdiv(Nq, 16), heads, B);
     float scale = 1.0f / std::sqrt((float)dh);
+    kprof_begin(2, 4.0 * B * (double)Nq * Nk * heads * dh, 4.0 * B * heads * dh * (2.0 * Nq + 2.0 * Nk));
+    struct End { Handle* h; ~End() { h->kprof_end(); } } _end{this};
     if (out.hi) {
         OutSplit o{out.hi, out.lo};
         if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
@@ -782,7 +811,13 @@ int stc_get_config(const stc_handle* h, stc_config* out) {
 uint64_t stc_launch_count(const stc_handle* h) { return h ? h->impl->launches : 0; }
 int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID; h->impl->use_graphs = enabled != 0; return STC_OK; }
 void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
-int stc_set_profile(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID; h->impl->profile = enabled != 0; return STC_OK; }
+int stc_set_profile(stc_handle* h, int level) { if (!h) return STC_ERR_INVALID; h->impl->profile = level; return STC_OK; }
+int stc_kernel_profile(const stc_handle* h, int cls, double out[4]) {
+    if (!h || !out || cls < 0 || cls > 2) return STC_ERR_INVALID;
+    const auto& k = h->impl->kprof[cls];
+    out[0] = k.ms; out[1] = k.flops; out[2] = k.bytes; out[3] = (double)k.n;
+    return STC_OK;
+}
 int stc_last_stage_ms(const stc_handle* h, float out[5]) {
     if (!h || !out) return STC_ERR_INVALID;
     memcpy(out, h->impl->stage_ms, sizeof(float) * 5);
@@ -992,6 +1027,7 @@ static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, con
             h->h_cap = B;
         }
         cudaStream_t st = h->stream;
+        for (auto& k : h->kprof) k = Handle::KProf{};
         // ---- stage 1: DP (+ /speed, wav lengths) and TE; sized independently of L
         const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
         float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
@@ -1055,6 +1091,7 @@ static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, con
         STC_CUDA(cudaStreamSynchronize(st));
         h->check_launch("stc_synthesize");
         if (h->profile) {
+            h->kprof_resolve();
             cudaEventElapsedTime(&h->stage_ms[0], h->ev[0], h->ev[1]);
             cudaEventElapsedTime(&h->stage_ms[1], h->ev[1], h->ev[2]);
             cudaEventElapsedTime(&h->stage_ms[2], h->ev[2], h->ev[3]);
