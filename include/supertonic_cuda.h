@@ -118,6 +118,22 @@ int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const floa
                           int total_step, float speed, uint64_t seed, float* wav_dev, int64_t wav_ld,
                           float* duration_dev, int64_t* L_out);
 
+/* Throughput variant: the latent side runs on PACKED rows (utterance b owns ceil(wav_len_b/cs) frames, the integer
+ * formula of getLatentMask, cpp/helper.cpp:767) — no padded frames are computed. Results on every utterance's valid
+ * region equal the rectangle variant (utterances are independent; tests: batch-composition invariance).
+ *   wav_out: packed floats, utterance b at [wav_offsets_out[b], wav_offsets_out[b+1]) = frames_b*cs samples, of which the
+ *            first wav_lengths_out[b] are the utterance (what cpp/example_onnx.cpp:104-109 keeps); wav_cap in floats.
+ *   noise (optional) as in stc_synthesize, indexed [b][d][frame]; latent_out (optional): packed [sum frames][D] rows. */
+int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                          const float* style_dp, int B, int T, int total_step, float speed,
+                          const float* noise, int64_t noise_ld, uint64_t seed,
+                          float* wav_out, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out,
+                          int64_t* wav_lengths_out, float* latent_out);
+int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev,
+                                 const float* style_ttl_dev, const float* style_dp_dev, int B, int T,
+                                 int total_step, float speed, uint64_t seed, float* wav_dev, int64_t wav_cap,
+                                 int64_t* wav_offsets_out, float* duration_dev);
+
 /* ---- host front-end (kept on the host, semantics of the C++ reference) ----------------------- */
 
 /* UnicodeProcessor::call (cpp/helper.cpp:355-390) for n texts. Two-pass: call with text_ids == NULL to

@@ -44,6 +44,8 @@ _SIGS = {
     "stc_vocode": (_i, [_vp, _vp, _i, _i, _vp]),
     "stc_synthesize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
+    "stc_synthesize_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
     "stc_frontend_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "stc_frontend_close": (None, [_vp]),
@@ -224,6 +226,48 @@ class Engine:
         if want_latent:
             res["latent"] = lat.reshape(-1)[:B * self.cfg.latent_channels * Lv].reshape(B, self.cfg.latent_channels, Lv)
         return res
+
+    def synthesize_packed(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
+                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False):
+        """Throughput path: packed latent rows, no padded frames. Returns dict(wavs=[B trimmed arrays], duration[B],
+        wav_lengths[B], frames[B], latent? (list of [frames_b, D] arrays))."""
+        ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
+        sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
+        B, T = ids.shape
+        cs, D = self.cfg.chunk_size, self.cfg.latent_channels
+        nz, nld = None, 0
+        if noise is not None:
+            nz = _cf(noise, np.float32); nld = nz.shape[2]
+        cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs
+        dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
+        for _ in range(2):
+            wav = np.empty((cap,), np.float32)
+            lat = np.empty((cap // cs, D), np.float32) if want_latent else None
+            rc = lib.stc_synthesize_packed(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
+                                           _ptr(nz), nld, seed, _ptr(wav), cap, _ptr(off), _ptr(dur), _ptr(wl), _ptr(lat))
+            if rc == ERR_CAPACITY and off[B] > cap:
+                cap = int(off[B])
+                continue
+            self._chk(rc)
+            break
+        frames = ((off[1:] - off[:-1]) // cs).astype(np.int64)
+        res = dict(wavs=[wav[off[b]:off[b] + wl[b]] for b in range(B)], duration=dur, wav_lengths=wl, frames=frames)
+        if want_latent:
+            fo = np.concatenate([[0], np.cumsum(frames)])
+            res["latent"] = [lat[fo[b]:fo[b + 1]] for b in range(B)]
+        return res
+
+    def synthesize_packed_device(self, ids_ptr: int, mask_ptr: int, sttl_ptr: int, sdp_ptr: int, B: int, T: int, total_step: int,
+                                 speed: float, seed: int, wav_ptr: int, wav_cap: int, dur_ptr: int) -> np.ndarray:
+        """Device-resident packed variant; returns wav offsets [B+1] (floats). StcError(code=-5).need holds the size to retry with."""
+        off = np.zeros((B + 1,), np.int64)
+        rc = lib.stc_synthesize_packed_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, B, T, int(total_step), float(speed),
+                                              seed, wav_ptr, wav_cap, _ptr(off), dur_ptr)
+        if rc != STC_OK:
+            e = StcError(rc, lib.stc_last_error(self._h).decode())
+            e.need = int(off[B])
+            raise e
+        return off
 
     def synthesize_device(self, ids_ptr: int, mask_ptr: int, sttl_ptr: int, sdp_ptr: int, B: int, T: int, total_step: int,
                           speed: float, seed: int, wav_ptr: int, wav_ld: int, dur_ptr: int) -> int:

@@ -30,15 +30,16 @@ namespace tc {
 constexpr int BM = 128;        // UMMA_M (cta_group::1)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 template <int BN> struct Tile {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int W_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+    static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * BN;        // two accumulator buffers (BN in {64,128} -> power of two)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -49,6 +50,9 @@ STC_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
 }
 STC_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+STC_DEVINL void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 STC_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -137,6 +141,84 @@ struct Params {
     int split;
 };
 
+// Fused epilogue for 32 consecutive columns of one row held in registers.
+template <bool kFull>
+STC_DEVINL void epilogue_store(const Params& p, float (&v)[32], int row, int col0, float mk) {
+    const float* resid = static_cast<const float*>(p.ep.resid);
+    const size_t o = (size_t)row * p.ldo + col0;
+    if (kFull) {
+        if (p.ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+        }
+        if (p.ep.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        }
+        if (p.ep.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 s = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col0 + j));
+                v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
+            }
+        }
+        if (resid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 s = *reinterpret_cast<const float4*>(resid + o + j);
+                v[j] += s.x; v[j + 1] += s.y; v[j + 2] += s.z; v[j + 3] += s.w;
+            }
+        }
+        if (p.ep.mask) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= mk;
+        }
+        if (p.split) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * t]), h1 = __float2bfloat16_rn(v[j + 2 * t + 1]);
+                    __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * t] - __bfloat162float(h0));
+                    __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * t + 1] - __bfloat162float(h1));
+                    hi[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint4*>(p.out_hi + o + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(p.out_lo + o + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    } else {
+        // ragged N edge: scalar path (static indexing keeps v[] in registers)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+                float x = v[j];
+                if (p.ep.bias) x += p.ep.bias[col0 + j];
+                if (p.ep.gelu) x = gelu_erf_fast(x);
+                if (p.ep.scale) x *= p.ep.scale[col0 + j];
+                if (resid) x += resid[o + j];
+                if (p.ep.mask) x *= mk;
+                if (p.split) {
+                    __nv_bfloat16 h = __float2bfloat16_rn(x);
+                    p.out_hi[o + j] = h;
+                    p.out_lo[o + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+                } else p.out_f32[o + j] = x;
+            }
+        }
+    }
+}
+
+// Persistent over output tiles (tile = blockIdx.x + i*gridDim.x, n fastest). Two TMEM accumulator buffers:
+// the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -147,22 +229,24 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;
-    // barriers: full[STAGES], empty[STAGES], accum, then the TMEM base-address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (T::STAGES + s); };
-    const uint32_t accum_bar = bar_base + 8u * (2 * T::STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * T::STAGES + 1);
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T::STAGES * T::STAGE_BYTES + 8 * (2 * T::STAGES + 1));
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * T::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * T::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * T::STAGES + 4);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T::STAGES * T::STAGE_BYTES + 8 * (2 * T::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int num_kb = (p.K + BK - 1) / BK;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const int num_tiles = n_tiles * m_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
         for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, T::TMEM_COLS);
@@ -174,126 +258,84 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % T::STAGES;
-                const uint32_t ph = (kb / T::STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                const uint32_t st = smem_base + s * T::STAGE_BYTES;
-                mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
-                tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-                tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
-                tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
-                tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+            uint32_t kbc = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
+                    const int s = kbc % T::STAGES;
+                    const uint32_t ph = (kbc / T::STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    const uint32_t st = smem_base + s * T::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
+                    tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % T::STAGES;
-            const uint32_t ph = (kb / T::STAGES) & 1;
-            mbar_wait(full_bar(s), ph);
+        uint32_t kbc = 0, it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(tempty_bar(ab), aph ^ 1);                 // epilogue has drained this accumulator buffer
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t st = smem_base + s * T::STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + T::A_BYTES);
-                const uint64_t w_hi = make_smem_desc(st + 2 * T::A_BYTES), w_lo = make_smem_desc(st + 2 * T::A_BYTES + T::W_BYTES);
+            const uint32_t tmem_d = tmem_base + ab * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
+                const int s = kbc % T::STAGES;
+                const uint32_t ph = (kbc / T::STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_base + s * T::STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + T::A_BYTES);
+                    const uint64_t w_hi = make_smem_desc(st + 2 * T::A_BYTES), w_lo = make_smem_desc(st + 2 * T::A_BYTES + T::W_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);       // 32 B per K-slice inside the swizzle row
-                    umma_bf16(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
-                    umma_bf16(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
-                    umma_bf16(tmem_base, a_hi + adv, w_hi + adv, idesc, 1);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);       // 32 B per K-slice inside the swizzle row
+                        umma_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit(empty_bar(s));                          // frees the smem stage when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tfull_bar(ab));   // accumulator complete
                 }
-                umma_commit(empty_bar(s));                      // frees the smem stage when these MMAs retire
-                if (kb == num_kb - 1) umma_commit(accum_bar);   // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const bool row_ok = row < p.M;
-        const float mk = (p.ep.mask && row_ok) ? p.ep.mask[row] : 1.f;
-        const float* resid = static_cast<const float*>(p.ep.resid);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            const int col0 = n0 + c0;
-            if (!row_ok || col0 >= p.N) continue;
-            float v[32];
+        // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp-2)/4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BN / 2;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            const uint32_t ab = it & 1, aph = (it >> 1) & 1;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const float mk = (p.ep.mask && row_ok) ? __ldg(p.ep.mask + row) : 1.f;
+            mbar_wait(tfull_bar(ab), aph);
+            tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            const size_t o = (size_t)row * p.ldo + col0;
-            if (col0 + 32 <= p.N) {
+            for (int c = 0; c < COLS_PER_WARP; c += 32) {
+                const int c0 = half * COLS_PER_WARP + c;
+                uint32_t r[32];
+                __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), r);
+                const int col0 = n0 + c0;
+                if (row_ok && col0 < p.N) {
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b = p.ep.bias ? *reinterpret_cast<const float4*>(p.ep.bias + col0 + j) : make_float4(0, 0, 0, 0);
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-                if (p.ep.gelu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf<float>(v[j]);
-                }
-                if (p.ep.scale) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 s = *reinterpret_cast<const float4*>(p.ep.scale + col0 + j);
-                        v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
-                    }
-                }
-                if (resid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 s = *reinterpret_cast<const float4*>(resid + o + j);
-                        v[j] += s.x; v[j + 1] += s.y; v[j + 2] += s.z; v[j + 3] += s.w;
-                    }
-                }
-                if (p.ep.mask) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= mk;
-                }
-                if (p.split) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * t]), h1 = __float2bfloat16_rn(v[j + 2 * t + 1]);
-                            __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * t] - __bfloat162float(h0));
-                            __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * t + 1] - __bfloat162float(h1));
-                            hi[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-                        *reinterpret_cast<uint4*>(p.out_hi + o + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + o + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-            } else {
-                // ragged N edge: scalar path
-                for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-                    float x = v[j];
-                    if (p.ep.bias) x += p.ep.bias[col0 + j];
-                    if (p.ep.gelu) x = gelu_erf<float>(x);
-                    if (p.ep.scale) x *= p.ep.scale[col0 + j];
-                    if (resid) x += resid[o + j];
-                    if (p.ep.mask) x *= mk;
-                    if (p.split) {
-                        __nv_bfloat16 h = __float2bfloat16_rn(x);
-                        p.out_hi[o + j] = h;
-                        p.out_lo[o + j] = __float2bfloat16_rn(x - __bfloat162float(h));
-                    } else p.out_f32[o + j] = x;
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (col0 + 32 <= p.N) epilogue_store<true>(p, v, row, col0, mk);
+                    else epilogue_store<false>(p, v, row, col0, mk);
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(ab));
         }
     }
     tc_fence_before();

@@ -30,6 +30,10 @@ template <typename T> STC_DEVINL T gelu_erf(T x) {
     return (x * (t_erf<T>(x / rsq2) + (T)1)) * (T)0.5;
 }
 
+// float path used inside the tensor-core epilogue: multiply by 1/sqrt2 instead of the IEEE division (which
+// compiles to ~100 instructions); differs from the graph's Div by at most 1 ulp of the erf argument.
+STC_DEVINL float gelu_erf_fast(float x) { return (x * (erff(x * 0.70710678f) + 1.0f)) * 0.5f; }
+
 template <typename T> STC_DEVINL T warp_sum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -39,6 +43,20 @@ STC_DEVINL float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- packed sequences ------------------------------------------------------------------------
+// B variable-length sequences are stored back to back: rows of sequence b are [off[b], off[b+1]).
+// A padded rectangle [B,N] is the special case off[b] = b*N (plus a 0/1 row mask). Rows >= off[B]
+// (bucket padding of a captured CUDA graph) belong to no sequence.
+STC_DEVINL int find_seq(const int* __restrict__ off, int B, int row) {
+    if (row >= __ldg(off + B)) return -1;
+    int lo = 0, hi = B;                 // invariant: off[lo] <= row < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= row) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // ---- GEMM operand stores ---------------------------------------------------------------------
@@ -74,11 +92,13 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
 // ---- x[row,:] = (x[row,:] + v[b,:]) * mask[row]   (style add in DP, time conditioning in VE) -----
 template <typename T>
 __global__ void add_rowvec_mask_kernel(T* __restrict__ x, const T* __restrict__ v, const float* __restrict__ mask,
-                                       int rows, int N, int C) {
+                                       int rows, int N, int C, int vstride) {
+    // vstride = C: one vector per sequence of a [B,N] rectangle; vstride = 0: one vector for every row
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * C) return;
     int row = (int)(i / C), c = (int)(i % C);
-    x[i] = (x[i] + v[(size_t)(row / N) * C + c]) * (T)mask[row];
+    T m = mask ? (T)mask[row] : (T)1;
+    x[i] = (x[i] + v[(size_t)(vstride ? row / N : 0) * vstride + c]) * m;
 }
 
 // ---- depthwise conv1d (+bias) -> LayerNorm over C, one warp per row ------------------------------
@@ -88,12 +108,21 @@ template <typename T, int CPL, typename Out>
 __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wb,
                  const float* __restrict__ g, const float* __restrict__ beta, Out out,
-                 int rows, int N, int K, int dil, int pad_left, float eps) {
+                 int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
     constexpr int C = CPL * 32;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
-    int b = row / N, n = row - b * N;
+    int base = 0, n = 0, N = 0;
+    if (K != 0) {
+        int b = find_seq(off, B, row);
+        if (b < 0) {                                   // bucket padding row: keep it finite
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) out.store((size_t)row * C + lane + 32 * i, (T)0);
+            return;
+        }
+        base = __ldg(off + b); n = row - base; N = __ldg(off + b + 1) - base;
+    }
     T y[CPL];
     if (K == 0) {
 #pragma unroll
@@ -104,7 +133,7 @@ dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
         for (int k = 0; k < K; ++k) {
             int nn = n + k * dil - pad_left;
             if (nn < 0 || nn >= N) continue;
-            const T* xr = x + ((size_t)b * N + nn) * C;
+            const T* xr = x + ((size_t)base + nn) * C;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 int c = lane + 32 * i;
@@ -203,18 +232,21 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, 
 }
 
 // ---- sequence lengths from masks: len[b] = sum_n mask[b,n] ---------------------------------------
-__global__ void mask_len_kernel(const float* __restrict__ mask, float* __restrict__ len, int N) {
+__global__ void mask_len_kernel(const float* __restrict__ mask, float* __restrict__ len, int* __restrict__ cnt, int N) {
+    // len[b] = sum of the mask (what the graphs' ReduceSum sees); cnt[b] = 1 + index of the last non-zero entry
     int b = blockIdx.x;
-    float s = 0.f;
-    for (int n = threadIdx.x; n < N; n += 32) s += mask[(size_t)b * N + n];
+    float s = 0.f; int last = 0;
+    for (int n = threadIdx.x; n < N; n += 32) { float m = mask[(size_t)b * N + n]; s += m; if (m != 0.f) last = n + 1; }
     s = warp_sum<float>(s);
-    if (threadIdx.x == 0) len[b] = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    if (threadIdx.x == 0) { len[b] = s; cnt[b] = last; }
 }
 
 // ---- rotary embedding in place on [rows, heads*DH]: rotate-half convention -----------------------
 // pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i]
 __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
-                            int rows, int N, int heads, int DH, int normalise) {
+                            int rows, const int* __restrict__ off, int B, int heads, int DH, int normalise) {
     int half = DH / 2;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)rows * heads * half;
@@ -222,8 +254,9 @@ __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ fre
     int d = (int)(i % half);
     int h = (int)((i / half) % heads);
     int row = (int)(i / ((size_t)half * heads));
-    int b = row / N, n = row - b * N;
-    float pos = (float)n;
+    int b = find_seq(off, B, row);
+    if (b < 0) return;
+    float pos = (float)(row - __ldg(off + b));
     if (normalise) pos = pos / len[b];
     float ang = pos * freqs[d];
     float c = cosf(ang), s = sinf(ang);
@@ -239,19 +272,24 @@ __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ fre
 template <int DH, typename Out>
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ Vt,
-                 const float* __restrict__ kmask, Out out, int Nq, int Nk, int heads, float scale) {
+                 const float* __restrict__ kmask, Out out, const int* __restrict__ qoff, const int* __restrict__ koff,
+                 const int* __restrict__ kcnt, int heads, float scale) {
     constexpr int QPW = 4, WARPS = 4, QT = QPW * WARPS, KC = 32, DPL = DH / 32;
     __shared__ float Ks[KC][DH + 1];
     __shared__ float Vs[KC][DH + 1];
     __shared__ float Qs[QT][DH];
     __shared__ float Ms[KC];
     int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+    const int qbase = __ldg(qoff + b), Nq = __ldg(qoff + b + 1) - qbase;
+    const int kbase = __ldg(koff + b);
+    const int Nk = kcnt ? min(__ldg(koff + b + 1) - kbase, __ldg(kcnt + b)) : __ldg(koff + b + 1) - kbase;   // skip the masked tail
+    if (q0 >= Nq) return;                                   // block-uniform
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int C = heads * DH;
     for (int i = threadIdx.x; i < QT * DH; i += 128) {
         int qi = i / DH, d = i % DH;
         int q = q0 + qi;
-        Qs[qi][d] = (q < Nq) ? Q[((size_t)b * Nq + q) * C + h * DH + d] : 0.f;
+        Qs[qi][d] = (q < Nq) ? Q[((size_t)qbase + q) * C + h * DH + d] : 0.f;
     }
     float m[QPW], l[QPW], o[QPW][DPL];
 #pragma unroll
@@ -264,13 +302,13 @@ attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, cons
             int kj = i / DH, d = i % DH;
             int k = k0 + kj;
             bool ok = k < Nk;
-            size_t g = ((size_t)b * Nk + (ok ? k : 0)) * C + h * DH + d;
+            size_t g = ((size_t)kbase + (ok ? k : 0)) * C + h * DH + d;
             Ks[kj][d] = ok ? Kt[g] : 0.f;
             Vs[kj][d] = ok ? Vt[g] : 0.f;
         }
         if (threadIdx.x < KC) {
             int k = k0 + threadIdx.x;
-            Ms[threadIdx.x] = (k < Nk) ? (kmask ? kmask[(size_t)b * Nk + k] : 1.f) : 0.f;
+            Ms[threadIdx.x] = (k < Nk) ? (kmask ? kmask[(size_t)kbase + k] : 1.f) : 0.f;
         }
         __syncthreads();
         bool valid = Ms[lane] != 0.f;
@@ -283,8 +321,8 @@ attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, cons
             s = valid ? s * scale : -INFINITY;
             float mx = fmaxf(m[qi], warp_max(s));
             if (mx == -INFINITY) continue;              // nothing valid yet (warp-uniform)
-            float p = valid ? __expf(s - mx) : 0.f;
-            float corr = __expf(m[qi] - mx);            // m = -inf -> 0
+            float p = valid ? expf(s - mx) : 0.f;
+            float corr = expf(m[qi] - mx);              // m = -inf -> 0
             l[qi] = l[qi] * corr + warp_sum<float>(p);
             m[qi] = mx;
 #pragma unroll
@@ -303,7 +341,7 @@ attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, cons
         float inv = l[qi] > 0.f ? 1.f / l[qi] : 0.f;
 #pragma unroll
         for (int j = 0; j < DPL; ++j)
-            out.store(((size_t)b * Nq + q) * C + h * DH + lane + 32 * j, o[qi][j] * inv);
+            out.store(((size_t)qbase + q) * C + h * DH + lane + 32 * j, o[qi][j] * inv);
     }
 }
 
@@ -335,12 +373,15 @@ STC_DEVINL uint32_t mix32(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return (uint32_t)(z >> 16);
 }
 __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, uint64_t seed,
-                                   const float* __restrict__ mask, float* __restrict__ x, int B, int D, int L) {
+                                   const float* __restrict__ mask, float* __restrict__ x, int rows,
+                                   const int* __restrict__ off, int B, int D) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)B * L * D) return;
+    if (i >= (size_t)rows * D) return;
     int d = (int)(i % D);
-    int l = (int)((i / D) % L);
-    int b = (int)(i / ((size_t)D * L));
+    int row = (int)(i / D);
+    int b = find_seq(off, B, row);
+    if (b < 0) { x[i] = 0.f; return; }
+    int l = row - __ldg(off + b);
     float v;
     if (noise) v = noise[((size_t)b * D + d) * ld + l];
     else {
@@ -349,7 +390,7 @@ __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, 
         float u2 = mix32(key ^ 0xD1B54A32D192ED03ull) * (1.0f / 4294967296.0f);
         v = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     }
-    x[i] = v * mask[(size_t)b * L + l];
+    x[i] = mask ? v * mask[row] : v;
 }
 
 // latent mask from wav lengths: mask[b,l] = l < ceil(wav_len[b]/cs)  (getLatentMask, cpp/helper.cpp:759-770)
@@ -366,23 +407,27 @@ __global__ void latent_mask_kernel(const int64_t* __restrict__ wav_len, float* _
 // z[b, f*l + j, c] = lat[b,l, j*ld + c] * std[j*ld+c] + mean[j*ld+c]
 template <typename Out>
 __global__ void voc_im2col_kernel(const float* __restrict__ lat, const float* __restrict__ sd,
-                                  const float* __restrict__ mean, Out out, int B, int L, int f, int ld, int K, int lda) {
+                                  const float* __restrict__ mean, Out out, int rows6, const int* __restrict__ off,
+                                  int B, int f, int ld, int K, int lda) {
+    // off = LATENT-frame offsets; output rows run at f x the latent rate: row6 in [f*off[b], f*off[b+1])
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int KW = K * ld;
-    size_t total = (size_t)B * L * f * lda;
+    size_t total = (size_t)rows6 * lda;
     if (i >= total) return;
     int col = (int)(i % lda);
-    size_t row = i / lda;
+    int row6 = (int)(i / lda);
     float v = 0.f;
     if (col < KW) {
         int k = col / ld, c = col % ld;
-        int fL = f * L;
-        int b = (int)(row / fL), n = (int)(row % fL);
-        int nn = n - (K - 1) + k;
-        if (nn >= 0) {
-            int l = nn / f, j = nn % f;
-            int ch = j * ld + c;
-            v = lat[((size_t)b * L + l) * (f * ld) + ch] * sd[ch] + mean[ch];
+        int b = find_seq(off, B, row6 / f);
+        if (b >= 0) {
+            int base = __ldg(off + b);
+            int nn = row6 - f * base - (K - 1) + k;
+            if (nn >= 0) {
+                int l = nn / f, j = nn % f;
+                int ch = j * ld + c;
+                v = lat[((size_t)base + l) * (f * ld) + ch] * sd[ch] + mean[ch];
+            }
         }
     }
     out.store(i, v);

@@ -47,14 +47,13 @@ struct GraphKey {
 };
 
 struct VeCtx {
-    int B = 0, L = 0, T = 0;
-    const float* lmask = nullptr; const float* tmask = nullptr;
-    float* llen = nullptr; float* tlen = nullptr;
+    Seq lat, text, style;             // latent frames (packed or rectangle), text tokens [B,T], style tokens [B,S]
     std::vector<float*> Kc, Vc;       // per cross-attention layer, [B*Nk, C] fp32 (keys already rotated)
 };
 
 struct Handle {
     int device = 0;
+    int num_sms = 148;
     int precision = STC_PREC_BF16X3;
     cudaStream_t stream = nullptr;
     stc_config cfg{};
@@ -126,27 +125,34 @@ struct Handle {
     // ---- kernels
     void to_act(const float* x, size_t n, const Act& out);
     template <typename T> void dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C,
-                                         int rows, int N, float eps, T* out_plain, const Act* out_act);
+                                         const Seq& seq, float eps, T* out_plain, const Act* out_act);
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
-    template <typename T> void convnext(const ConvNeXt& c, T* x, int rows, int N, const float* mask);
-    void attention(const Attention& a, float* x, int B, int Nq, const float* qmask, const float* qlen,
-                   const Act* ctx, int Nk, const float* kmask, const float* klen, const float* Kpre, const float* Vpre);
-    void attn_core(const float* Q, const float* K, const float* V, const float* kmask, const Act& out, int B, int Nq, int Nk,
+    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
+    void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const float* Kpre, const float* Vpre);
+    void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
-    void rope(float* x, const float* freqs, const float* len, int rows, int N, int heads, int dh, int normalise);
+    void rope(float* x, const float* freqs, const Seq& seq, int heads, int dh, int normalise);
+    // sequence descriptors (offsets staged through pinned memory)
+    int* stage_ints(const std::vector<int>& v);
+    Seq rect_seq(int B, int N, const float* mask, bool want_len);
+    Seq packed_seq(const std::vector<int>& lens, int rows_launch, int maxlen_launch);
+    Seq scaled_seq(const Seq& s, int f);
+    const float* time_vectors(float cur, float tot);
 
     // ---- graph walkers (device pointers)
     void run_dp(const int64_t* ids, const float* style_dp, const float* mask, int B, int T, float* dur);
     void run_te(const int64_t* ids, const float* style_ttl, const float* mask, int B, int T, float* text_emb_cl);
     void prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_ttl);
-    void run_ve_step(const VeCtx& vc, float* x_lat, const float* cur, const float* tot, const float* dtvec);
-    void run_vocoder(const float* lat_cl, int B, int L, float* wav);
+    void run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const float* dtvec);
+    void run_vocoder(const float* lat_cl, const Seq& lat, float* wav);
 
     void check_launch(const char* what);
     void ensure_ws(const std::function<void()>& fn);
-    void synth_tail(const float* d_text_emb, const float* d_tmask, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                    uint64_t seed, const int64_t* d_wavlen, int B, int T, int L, int steps, float* d_lmask, float* d_xlat, float* d_wav);
+    void synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
+                    uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav);
+    std::map<std::pair<uint32_t, uint32_t>, float*> tvec_cache;
+    int* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging for offset arrays
 };
 
 #define STC_LAUNCH(h, kernel, grid, block, smem, ...)                          \
@@ -166,6 +172,7 @@ Handle::~Handle() {
     if (d_dtvec) cudaFree(d_dtvec);
     if (h_dur) cudaFreeHost(h_dur);
     if (h_wavlen) cudaFreeHost(h_wavlen);
+    if (h_stage) cudaFreeHost(h_stage);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : ev_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -249,6 +256,8 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
         STC_CUDA(cudaMemcpy(l.w_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
         l.map_hi = encode_map(l.w_hi, N, K, 128);
         l.map_lo = encode_map(l.w_lo, N, K, 128);
+        l.map64_hi = encode_map(l.w_hi, N, K, 64);
+        l.map64_lo = encode_map(l.w_lo, N, K, 64);
         l.has_maps = true;
     }
     return l;
@@ -420,33 +429,33 @@ void Handle::to_act(const float* x, size_t n, const Act& out) {
 
 template <typename T, typename Out>
 static void launch_dwln(Handle* h, int C, const T* x, const float* w, const float* wb, const float* g, const float* b, Out out,
-                        int rows, int N, int K, int dil, int pad, float eps) {
+                        int rows, const int* off, int B, int K, int dil, int pad, float eps) {
     dim3 grid(cdiv(rows, 8)), block(256);
     switch (C / 32) {
-        case 1: STC_LAUNCH(h, (dwconv_ln_kernel<T, 1, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
-        case 2: STC_LAUNCH(h, (dwconv_ln_kernel<T, 2, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
-        case 4: STC_LAUNCH(h, (dwconv_ln_kernel<T, 4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
-        case 8: STC_LAUNCH(h, (dwconv_ln_kernel<T, 8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
-        case 16: STC_LAUNCH(h, (dwconv_ln_kernel<T, 16, Out>), grid, block, 0, x, w, wb, g, b, out, rows, N, K, dil, pad, eps); break;
+        case 1: STC_LAUNCH(h, (dwconv_ln_kernel<T, 1, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
+        case 2: STC_LAUNCH(h, (dwconv_ln_kernel<T, 2, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
+        case 4: STC_LAUNCH(h, (dwconv_ln_kernel<T, 4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
+        case 8: STC_LAUNCH(h, (dwconv_ln_kernel<T, 8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
+        case 16: STC_LAUNCH(h, (dwconv_ln_kernel<T, 16, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
         default: throw StcError(STC_ERR_UNSUPPORTED, "channel count must be 32/64/128/256/512, got " + std::to_string(C));
     }
 }
 
 template <typename T>
-void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C, int rows, int N, float eps,
+void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C, const Seq& seq, float eps,
                        T* out_plain, const Act* out_act) {
     const float* w = cn ? cn->dw_w : nullptr; const float* wb = cn ? cn->dw_b : nullptr;
-    int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0;
+    int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0, rows = seq.rows;
     if constexpr (std::is_same<T, float>::value) {
         if (out_act && out_act->hi) {
             kprof_begin(1, (2.0 * K + 8.0) * rows * C, 8.0 * rows * C + 4.0 * C * (K + 3));
-            launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, N, K, dil, pad, eps);
+            launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, seq.off, seq.B, K, dil, pad, eps);
             kprof_end();
             return;
         }
         if (out_act) out_plain = out_act->f;
     }
-    launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_plain}, rows, N, K, dil, pad, eps);
+    launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_plain}, rows, seq.off, seq.B, K, dil, pad, eps);
 }
 
 template <typename T>
@@ -468,28 +477,33 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
     if (out_f32) { p.out_f32 = out_f32; p.split = 0; } else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
     if (dry) return;
-    const CUtensorMap& ma_hi = act_map(a.hi, M, w.K);
-    CUtensorMap mh = ma_hi;
+    CUtensorMap mh = act_map(a.hi, M, w.K);
     CUtensorMap ml = act_map(a.lo, M, w.K);
-    dim3 grid(cdiv(w.N, 128), cdiv(M, tc::BM));
+    // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
+    int tiles128 = cdiv(w.N, 128) * cdiv(M, tc::BM);
+    bool bn64 = tiles128 < num_sms && w.N > 64;
+    int tiles = bn64 ? cdiv(w.N, 64) * cdiv(M, tc::BM) : tiles128;
+    dim3 grid(std::min(tiles, num_sms));
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
-    STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<128>), grid, tc::NUM_THREADS, tc::Tile<128>::SMEM_BYTES, mh, ml, w.map_hi, w.map_lo, p);
+    if (bn64) STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<64>), grid, tc::NUM_THREADS, tc::Tile<64>::SMEM_BYTES, mh, ml, w.map64_hi, w.map64_lo, p);
+    else STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<128>), grid, tc::NUM_THREADS, tc::Tile<128>::SMEM_BYTES, mh, ml, w.map_hi, w.map_lo, p);
     kprof_end();
 }
 
 template <typename T>
-void Handle::convnext(const ConvNeXt& c, T* x, int rows, int N, const float* mask) {
+void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     size_t mk = mark();
+    int rows = seq.rows;
     Epilogue e1; e1.gelu = 1;
-    Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? mask : nullptr;
+    Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
         Act a = ws_act((size_t)rows * c.C), hid = ws_act((size_t)rows * c.H);
-        dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, rows, N, 1e-6f, nullptr, &a);
+        dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
         gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
         gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
     } else {
         T* a = ws<T>((size_t)rows * c.C); T* hid = ws<T>((size_t)rows * c.H);
-        dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, rows, N, 1e-6f, a, nullptr);
+        dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, a, nullptr);
         e1.bias = c.pw1.bias; e2.bias = c.pw2.bias;
         gemm_simt<T>(a, c.C, rows, c.pw1, e1, hid, c.H);
         gemm_simt<T>(hid, c.H, rows, c.pw2, e2, x, c.C);
@@ -497,51 +511,103 @@ void Handle::convnext(const ConvNeXt& c, T* x, int rows, int N, const float* mas
     release(mk);
 }
 
-void Handle::rope(float* x, const float* freqs, const float* len, int rows, int N, int heads, int dh, int normalise) {
-    size_t n = (size_t)rows * heads * (dh / 2);
-    STC_LAUNCH(this, rope_kernel, cdiv(n, 256), 256, 0, x, freqs, len, rows, N, heads, dh, normalise);
+void Handle::rope(float* x, const float* freqs, const Seq& seq, int heads, int dh, int normalise) {
+    size_t n = (size_t)seq.rows * heads * (dh / 2);
+    STC_LAUNCH(this, rope_kernel, cdiv(n, 256), 256, 0, x, freqs, seq.len, seq.rows, seq.off, seq.B, heads, dh, normalise);
 }
 
-void Handle::attn_core(const float* Q, const float* K, const float* V, const float* kmask, const Act& out, int B, int Nq, int Nk,
+void Handle::attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                        int heads, int dh) {
-    dim3 grid(cdiv(Nq, 16), heads, B);
+    dim3 grid(cdiv(q.maxlen, 16), heads, q.B);
     float scale = 1.0f / std::sqrt((float)dh);
-    kprof_begin(2, 4.0 * B * (double)Nq * Nk * heads * dh, 4.0 * B * heads * dh * (2.0 * Nq + 2.0 * Nk));
-    struct End { Handle* h; ~End() { h->kprof_end(); } } _end{this};
+    const float* kmask = key_masked ? k.mask : nullptr;
+    kprof_begin(2, 4.0 * (double)q.rows * k.maxlen * heads * dh, 4.0 * heads * dh * (2.0 * q.rows + 2.0 * k.rows));
     if (out.hi) {
         OutSplit o{out.hi, out.lo};
-        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
-        else STC_LAUNCH(this, (attention_kernel<32, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, q.off, k.off, kmask ? k.cnt : nullptr, heads, scale);
+        else STC_LAUNCH(this, (attention_kernel<32, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, q.off, k.off, kmask ? k.cnt : nullptr, heads, scale);
     } else {
         OutPlain<float> o{out.f};
-        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
-        else STC_LAUNCH(this, (attention_kernel<32, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, Nq, Nk, heads, scale);
+        if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, q.off, k.off, kmask ? k.cnt : nullptr, heads, scale);
+        else STC_LAUNCH(this, (attention_kernel<32, OutPlain<float>>), grid, 128, 0, Q, K, V, kmask, o, q.off, k.off, kmask ? k.cnt : nullptr, heads, scale);
     }
+    kprof_end();
 }
 
-void Handle::attention(const Attention& a, float* x, int B, int Nq, const float* qmask, const float* qlen, const Act* ctx, int Nk,
-                       const float* kmask, const float* klen, const float* Kpre, const float* Vpre) {
+// Pre-LN multi-head attention with residual. Self-attention: ctx == nullptr && Kpre == nullptr (keys from LN(x), kseq = qseq).
+void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* ctx, const Seq& ks_in, const float* Kpre, const float* Vpre) {
     size_t mk = mark();
-    int rows = B * Nq, dh = a.C / a.heads;
+    int rows = qs.rows, dh = a.C / a.heads;
     Act xn = ws_act((size_t)rows * a.C);
-    dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, rows, Nq, 1e-6f, nullptr, &xn);
+    dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, qs, 1e-6f, nullptr, &xn);
+    if (qs.rows > 0 && !dry && tc_mode()) {}   // (operand rows beyond off[B] are finite garbage: rows are independent)
     float* q = ws<float>((size_t)rows * a.C);
     gemm(xn, rows, a.q, Epilogue{}, q, nullptr, a.C);
     const float *Kp = Kpre, *Vp = Vpre;
-    if (a.ctx_kind == CTX_SELF) { ctx = &xn; Nk = Nq; kmask = a.key_masked ? qmask : nullptr; klen = qlen; }
+    const Seq& ks = a.ctx_kind == CTX_SELF ? qs : ks_in;
+    if (a.ctx_kind == CTX_SELF) ctx = &xn;
     if (!Kp) {
-        float* k = ws<float>((size_t)B * Nk * a.C); float* v = ws<float>((size_t)B * Nk * a.C);
-        gemm(*ctx, B * Nk, a.k, Epilogue{}, k, nullptr, a.C);
-        gemm(*ctx, B * Nk, a.v, Epilogue{}, v, nullptr, a.C);
-        if (a.rope != ROPE_NONE) rope(k, a.freqs, klen, B * Nk, Nk, a.heads, dh, a.rope == ROPE_NORM);
+        float* k = ws<float>((size_t)ks.rows * a.C); float* v = ws<float>((size_t)ks.rows * a.C);
+        gemm(*ctx, ks.rows, a.k, Epilogue{}, k, nullptr, a.C);
+        gemm(*ctx, ks.rows, a.v, Epilogue{}, v, nullptr, a.C);
+        if (a.rope != ROPE_NONE) rope(k, a.freqs, ks, a.heads, dh, a.rope == ROPE_NORM);
         Kp = k; Vp = v;
     }
-    if (a.rope != ROPE_NONE) rope(q, a.freqs, qlen, rows, Nq, a.heads, dh, a.rope == ROPE_NORM);
+    if (a.rope != ROPE_NONE) rope(q, a.freqs, qs, a.heads, dh, a.rope == ROPE_NORM);
     Act o = ws_act((size_t)rows * a.C);
-    attn_core(q, Kp, Vp, a.key_masked ? kmask : nullptr, o, B, Nq, Nk, a.heads, dh);
-    Epilogue eo; eo.resid = x; eo.mask = a.masked ? qmask : nullptr;
+    attn_core(q, Kp, Vp, o, qs, ks, a.key_masked, a.heads, dh);
+    Epilogue eo; eo.resid = x; eo.mask = a.masked ? qs.mask : nullptr;
     gemm(o, rows, a.o, eo, x, nullptr, a.C);
     release(mk);
+}
+
+// ------------------------------------------------------------------------------------------ sequence descriptors
+int* Handle::stage_ints(const std::vector<int>& v) {
+    int* d = ws<int>(v.size());
+    if (dry) return d;
+    if (h_stage_off + v.size() > h_stage_cap) throw StcError(STC_ERR_CAPACITY, "offset staging buffer exhausted (batch too large)");
+    int* hp = h_stage + h_stage_off;
+    h_stage_off += v.size();
+    memcpy(hp, v.data(), v.size() * sizeof(int));
+    STC_CUDA(cudaMemcpyAsync(d, hp, v.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    return d;
+}
+
+Seq Handle::rect_seq(int B, int N, const float* mask, bool want_len) {
+    std::vector<int> off(B + 1);
+    for (int b = 0; b <= B; ++b) off[b] = b * N;
+    Seq s; s.off = stage_ints(off); s.B = B; s.rows = B * N; s.maxlen = N; s.mask = mask;
+    if (want_len && mask) {
+        float* len = ws<float>(B); int* cnt = ws<int>(B);
+        STC_LAUNCH(this, mask_len_kernel, B, 32, 0, mask, len, cnt, N);
+        s.len = len; s.cnt = cnt;
+    }
+    return s;
+}
+
+Seq Handle::packed_seq(const std::vector<int>& lens, int rows_launch, int maxlen_launch) {
+    int B = (int)lens.size();
+    std::vector<int> off(B + 1, 0), lf(B);
+    for (int b = 0; b < B; ++b) off[b + 1] = off[b] + lens[b];
+    Seq s; s.off = stage_ints(off); s.B = B; s.rows = std::max(rows_launch, off[B]); s.maxlen = maxlen_launch; s.mask = nullptr;
+    // lengths as float via the same staging path (bit pattern copy)
+    std::vector<int> bits(B);
+    for (int b = 0; b < B; ++b) { float f = (float)lens[b]; memcpy(&bits[b], &f, 4); }
+    s.len = reinterpret_cast<const float*>(stage_ints(bits));
+    return s;
+}
+
+__global__ void scale_off_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int f) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] * f;
+}
+
+Seq Handle::scaled_seq(const Seq& s, int f) {
+    Seq r = s;
+    int* o = ws<int>(s.B + 1);
+    STC_LAUNCH(this, scale_off_kernel, cdiv(s.B + 1, 128), 128, 0, s.off, o, s.B + 1, f);
+    r.off = o; r.rows = s.rows * f; r.maxlen = s.maxlen * f; r.mask = nullptr; r.len = nullptr;
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------ graph walkers
@@ -555,6 +621,7 @@ void Handle::run_dp(const int64_t* ids, const float* style_dp, const float* mask
     // duration_predictor.onnx evaluated in fp64 (reference call site cpp/helper.cpp:512-526)
     size_t mk = mark();
     int C = dp.C, rows = B * T, si = dp_arch.at("style_in");
+    Seq seq = rect_seq(B, T, mask, false);
     double* x = ws<double>((size_t)rows * C);
     STC_LAUNCH(this, embed_kernel<double>, cdiv(rows, 8), dim3(32, 8), 0, ids, dp.vec["embed"], mask, x, rows, C, cfg.vocab_size);
     double* sd = ws<double>((size_t)B * si); double* s = ws<double>((size_t)B * C);
@@ -562,9 +629,9 @@ void Handle::run_dp(const int64_t* ids, const float* style_dp, const float* mask
     const Linear& ls = dp.lin.back();
     Epilogue es; es.bias = ls.bias;
     gemm_simt<double>(sd, si, B, ls, es, s, C);
-    STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, T, C);
+    STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, T, C, C);
     for (const Layer& l : dp.layers)
-        if (l.type == L_CONVNEXT) convnext<double>(dp.cn[l.idx], x, rows, T, mask);
+        if (l.type == L_CONVNEXT) convnext<double>(dp.cn[l.idx], x, seq);
     float clip = dp_arch.at("clip"), spt = dp_arch.at("sec_per_token");
     if (C == 64) STC_LAUNCH(this, dp_head_kernel<2>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
     else if (C == 32) STC_LAUNCH(this, dp_head_kernel<1>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
@@ -576,18 +643,17 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mas
     // text_encoder.onnx (reference call site cpp/helper.cpp:545-556); output kept channels-last [B*T, C]
     size_t mk = mark();
     int C = te.C, rows = B * T, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim;
+    Seq tseq = rect_seq(B, T, mask, true), sseq = rect_seq(B, S, nullptr, false);
     float* x = ws<float>((size_t)rows * C);
     STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], mask, x, rows, C, cfg.vocab_size);
-    float* tlen = ws<float>(B);
-    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, mask, tlen, T);
     Act sty = ws_act((size_t)B * S * Cs);
     to_act(style_ttl, (size_t)B * S * Cs, sty);
     for (const Layer& l : te.layers) {
-        if (l.type == L_CONVNEXT) convnext<float>(te.cn[l.idx], x, rows, T, mask);
+        if (l.type == L_CONVNEXT) convnext<float>(te.cn[l.idx], x, tseq);
         else if (l.type == L_ATTN) {
             const Attention& a = te.at[l.idx];
-            if (a.ctx_kind == CTX_SELF) attention(a, x, B, T, mask, tlen, nullptr, T, mask, tlen, nullptr, nullptr);
-            else attention(a, x, B, T, mask, tlen, &sty, S, nullptr, nullptr, nullptr, nullptr);
+            if (a.ctx_kind == CTX_SELF) attention(a, x, tseq, nullptr, tseq, nullptr, nullptr);
+            else attention(a, x, tseq, &sty, sseq, nullptr, nullptr);
         } else if (l.type == L_PROJ_OUT) {
             Act xa = ws_act((size_t)rows * C);
             to_act(x, (size_t)rows * C, xa);
@@ -600,83 +666,99 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mas
 
 void Handle::prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_ttl) {
     // K/V of text_emb and style_ttl are step-invariant: hoisted out of the Euler loop (north_star).
-    int B = vc.B, T = vc.T, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim, Ct = cfg.text_emb_channels;
-    vc.llen = ws<float>(B); vc.tlen = ws<float>(B);
-    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, vc.lmask, vc.llen, vc.L);
-    STC_LAUNCH(this, mask_len_kernel, B, 32, 0, vc.tmask, vc.tlen, T);
+    int Cs = cfg.style_ttl_dim, Ct = cfg.text_emb_channels;
     int nslots = 0;
     for (const Attention& a : ve.at) if (a.kv_slot >= 0) nslots = std::max(nslots, a.kv_slot + 1);
     vc.Kc.assign(nslots, nullptr); vc.Vc.assign(nslots, nullptr);
     for (const Attention& a : ve.at) {
         if (a.kv_slot < 0) continue;
-        int Nk = a.ctx_kind == CTX_TEXT ? T : S;
-        vc.Kc[a.kv_slot] = ws<float>((size_t)B * Nk * a.C);
-        vc.Vc[a.kv_slot] = ws<float>((size_t)B * Nk * a.C);
+        int kr = a.ctx_kind == CTX_TEXT ? vc.text.rows : vc.style.rows;
+        vc.Kc[a.kv_slot] = ws<float>((size_t)kr * a.C);
+        vc.Vc[a.kv_slot] = ws<float>((size_t)kr * a.C);
     }
     size_t mk = mark();
-    Act ta = ws_act((size_t)B * T * Ct), sa = ws_act((size_t)B * S * Cs);
-    to_act(text_emb_cl, (size_t)B * T * Ct, ta);
-    to_act(style_ttl, (size_t)B * S * Cs, sa);
+    Act ta = ws_act((size_t)vc.text.rows * Ct), sa = ws_act((size_t)vc.style.rows * Cs);
+    to_act(text_emb_cl, (size_t)vc.text.rows * Ct, ta);
+    to_act(style_ttl, (size_t)vc.style.rows * Cs, sa);
     for (const Attention& a : ve.at) {
         if (a.kv_slot < 0) continue;
         bool text = a.ctx_kind == CTX_TEXT;
-        int Nk = text ? T : S;
-        gemm(text ? ta : sa, B * Nk, a.k, Epilogue{}, vc.Kc[a.kv_slot], nullptr, a.C);
-        gemm(text ? ta : sa, B * Nk, a.v, Epilogue{}, vc.Vc[a.kv_slot], nullptr, a.C);
-        if (a.rope != ROPE_NONE) rope(vc.Kc[a.kv_slot], a.freqs, vc.tlen, B * Nk, Nk, a.heads, a.C / a.heads, a.rope == ROPE_NORM);
+        const Seq& ks = text ? vc.text : vc.style;
+        gemm(text ? ta : sa, ks.rows, a.k, Epilogue{}, vc.Kc[a.kv_slot], nullptr, a.C);
+        gemm(text ? ta : sa, ks.rows, a.v, Epilogue{}, vc.Vc[a.kv_slot], nullptr, a.C);
+        if (a.rope != ROPE_NONE) rope(vc.Kc[a.kv_slot], a.freqs, ks, a.heads, a.C / a.heads, a.rope == ROPE_NORM);
     }
     release(mk);
 }
 
-void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* cur, const float* tot, const float* dtvec) {
+// Time conditioning depends only on (current_step, total_step): the sinusoid -> MLP -> per-super-block linears are
+// evaluated once per distinct pair and cached for the lifetime of the handle: [n_time_cond][C] fp32.
+const float* Handle::time_vectors(float cur, float tot) {
+    uint32_t kc, kt; memcpy(&kc, &cur, 4); memcpy(&kt, &tot, 4);
+    auto key = std::make_pair(kc, kt);
+    auto it = tvec_cache.find(key);
+    if (it != tvec_cache.end()) return it->second;
+    int C = ve.C, td = ve_arch.at("time_dim"), ntc = 0;
+    for (const Layer& l : ve.layers) if (l.type == L_TIME_COND) ++ntc;
+    if (dry) return reinterpret_cast<const float*>(uintptr_t(0x1000));
+    float* out = nullptr;
+    STC_CUDA(cudaMalloc((void**)&out, sizeof(float) * std::max(1, ntc) * C)); owned.push_back(out);
+    float* tmp = nullptr;
+    STC_CUDA(cudaMalloc((void**)&tmp, sizeof(float) * (td + 2 * C + 2)));
+    float* d_cur = tmp; float* d_tot = tmp + 1; float* e0 = tmp + 2; float* e1 = e0 + td; float* temb = e1 + C;
+    STC_LAUNCH(this, fill_kernel, 1, 32, 0, d_cur, cur, (size_t)1);
+    STC_LAUNCH(this, fill_kernel, 1, 32, 0, d_tot, tot, (size_t)1);
+    int i = 0;
+    for (const Layer& l : ve.layers) {
+        if (l.type == L_TIME_MLP) {
+            STC_LAUNCH(this, time_embed_kernel, cdiv((size_t)td / 2, 128), 128, 0, d_cur, d_tot, ve.vec["time.freqs"], e0, 1, td / 2);
+            Epilogue a; a.bias = ve.lin[l.idx].bias; a.gelu = 1;
+            gemm_simt<float>(e0, td, 1, ve.lin[l.idx], a, e1, C);
+            Epilogue b; b.bias = ve.lin[l.idx + 1].bias;
+            gemm_simt<float>(e1, C, 1, ve.lin[l.idx + 1], b, temb, C);
+        } else if (l.type == L_TIME_COND) {
+            Epilogue e; e.bias = ve.lin[l.idx].bias;
+            gemm_simt<float>(temb, C, 1, ve.lin[l.idx], e, out + (size_t)(i++) * C, C);
+        }
+    }
+    STC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(tmp);
+    tvec_cache[key] = out;
+    return out;
+}
+
+void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const float* dtvec) {
     // vector_estimator.onnx: one Euler step, update in-graph (reference cpp/helper.cpp:620-658)
     size_t mk = mark();
-    int B = vc.B, L = vc.L, rows = B * L, C = ve.C, D = cfg.latent_channels;
+    const Seq& ls = vc.lat;
+    int rows = ls.rows, C = ve.C, D = cfg.latent_channels, itc = 0;
     float* x = ws<float>((size_t)rows * C);
-    float* temb = nullptr;
     for (const Layer& l : ve.layers) {
         switch (l.type) {
-            case L_TIME_MLP: {
-                int td = ve_arch.at("time_dim");
-                float* e0 = ws<float>((size_t)B * td); float* e1 = ws<float>((size_t)B * C); temb = ws<float>((size_t)B * C);
-                STC_LAUNCH(this, time_embed_kernel, cdiv((size_t)B * td / 2, 128), 128, 0, cur, tot, ve.vec["time.freqs"], e0, B, td / 2);
-                Epilogue a; a.bias = ve.lin[l.idx].bias; a.gelu = 1;
-                gemm_simt<float>(e0, td, B, ve.lin[l.idx], a, e1, C);
-                Epilogue b; b.bias = ve.lin[l.idx + 1].bias;
-                gemm_simt<float>(e1, C, B, ve.lin[l.idx + 1], b, temb, C);
-                break;
-            }
             case L_PROJ_IN: {
                 size_t m2 = mark();
                 Act xa = ws_act((size_t)rows * D);
                 to_act(x_lat, (size_t)rows * D, xa);
-                Epilogue e; e.mask = vc.lmask;
+                Epilogue e; e.mask = ls.mask;
                 gemm(xa, rows, ve.lin[l.idx], e, x, nullptr, C);
                 release(m2);
                 break;
             }
-            case L_CONVNEXT: convnext<float>(ve.cn[l.idx], x, rows, L, vc.lmask); break;
-            case L_TIME_COND: {
-                size_t m2 = mark();
-                float* tcv = ws<float>((size_t)B * C);
-                Epilogue e; e.bias = ve.lin[l.idx].bias;
-                gemm_simt<float>(temb, C, B, ve.lin[l.idx], e, tcv, C);
-                STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, tcv, vc.lmask, rows, L, C);
-                release(m2);
+            case L_CONVNEXT: convnext<float>(ve.cn[l.idx], x, ls); break;
+            case L_TIME_COND:
+                STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, tvec + (size_t)(itc++) * C, ls.mask,
+                           rows, 1, C, 0);
                 break;
-            }
             case L_ATTN: {
                 const Attention& a = ve.at[l.idx];
-                bool text = a.ctx_kind == CTX_TEXT;
-                attention(a, x, B, L, vc.lmask, vc.llen, nullptr, text ? vc.T : cfg.style_ttl_tokens, text ? vc.tmask : nullptr,
-                          text ? vc.tlen : nullptr, vc.Kc[a.kv_slot], vc.Vc[a.kv_slot]);
+                attention(a, x, ls, nullptr, a.ctx_kind == CTX_TEXT ? vc.text : vc.style, vc.Kc[a.kv_slot], vc.Vc[a.kv_slot]);
                 break;
             }
             case L_PROJ_OUT: {
                 size_t m2 = mark();
                 Act xa = ws_act((size_t)rows * C);
                 to_act(x, (size_t)rows * C, xa);
-                Epilogue e; e.scale = dtvec; e.resid = x_lat; e.mask = vc.lmask;   // x <- (x + v*dt) * mask
+                Epilogue e; e.scale = dtvec; e.resid = x_lat; e.mask = ls.mask;   // x <- (x + v*dt) * mask
                 gemm(xa, rows, ve.lin[l.idx], e, x_lat, nullptr, D);
                 release(m2);
                 break;
@@ -687,11 +769,12 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* cur, const 
     release(mk);
 }
 
-void Handle::run_vocoder(const float* lat_cl, int B, int L, float* wav) {
-    // vocoder.onnx (reference call site cpp/helper.cpp:662-672); no mask: the whole padded rectangle is decoded
+void Handle::run_vocoder(const float* lat_cl, const Seq& lat, float* wav) {
+    // vocoder.onnx (reference call site cpp/helper.cpp:662-672); no mask: every launched frame is decoded
     size_t mk = mark();
     int f = cfg.chunk_compress_factor, ld = cfg.latent_dim, C = voc.C;
-    int rows = B * L * f;
+    Seq s6 = scaled_seq(lat, f);
+    int rows = s6.rows;
     float* x = ws<float>((size_t)rows * C);
     for (const Layer& l : voc.layers) {
         if (l.type == L_CONV_IN) {
@@ -700,14 +783,14 @@ void Handle::run_vocoder(const float* lat_cl, int B, int L, float* wav) {
             int K = w.K / ld;
             Act a = ws_act((size_t)rows * w.K);
             size_t n = (size_t)rows * w.K;
-            if (a.hi) STC_LAUNCH(this, voc_im2col_kernel<OutSplit>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutSplit{a.hi, a.lo}, B, L, f, ld, K, w.K);
-            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f}, B, L, f, ld, K, w.K);
+            if (a.hi) STC_LAUNCH(this, voc_im2col_kernel<OutSplit>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutSplit{a.hi, a.lo}, rows, lat.off, lat.B, f, ld, K, w.K);
+            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f}, rows, lat.off, lat.B, f, ld, K, w.K);
             gemm(a, rows, w, Epilogue{}, x, nullptr, C);
             release(m2);
-        } else if (l.type == L_CONVNEXT) convnext<float>(voc.cn[l.idx], x, rows, L * f, nullptr);
+        } else if (l.type == L_CONVNEXT) convnext<float>(voc.cn[l.idx], x, s6);
         else if (l.type == L_HEAD) {
             Act hn = ws_act((size_t)rows * C);
-            dwconv_ln<float>(x, nullptr, voc.vec["head.ln_g"], voc.vec["head.ln_b"], C, rows, L * f, 1e-6f, nullptr, &hn);
+            dwconv_ln<float>(x, nullptr, voc.vec["head.ln_g"], voc.vec["head.ln_b"], C, s6, 1e-6f, nullptr, &hn);
             gemm(hn, rows, voc.lin[l.idx], Epilogue{}, wav, nullptr, voc.lin[l.idx].N);
         }
     }
@@ -771,6 +854,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         cudaDeviceProp prop; STC_CUDA(cudaGetDeviceProperties(&prop, device));
         auto hd = std::make_unique<Handle>();
         hd->device = device;
+        hd->num_sms = prop.multiProcessorCount;
         if (precision == STC_PREC_DEFAULT) {
             const char* env = getenv("STC_PRECISION");
             precision = (env && std::string(env) == "fp32_simt") ? STC_PREC_FP32_SIMT : STC_PREC_BF16X3;
@@ -787,6 +871,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             if (!fn || qr != cudaDriverEntryPointSuccess) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
             hd->encode = (EncodeTiledFn)fn;
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
         }
         hd->load(onnx_dir);
         sh->impl = std::move(hd);
@@ -834,6 +919,8 @@ struct Scope {   // per-call: select device, reset arena
         if (!h) throw StcError(STC_ERR_INVALID, "null handle");
         STC_CUDA(cudaSetDevice(h->device));
         h->arena.reset(); h->persist.reset();
+        if (!h->h_stage) { h->h_stage_cap = 1 << 18; STC_CUDA(cudaMallocHost((void**)&h->h_stage, h->h_stage_cap * sizeof(int))); }
+        h->h_stage_off = 0;
     }
 };
 template <typename T> T* upp(Handle* h, const T* host, size_t n) {   // into the persistent arena
@@ -866,7 +953,7 @@ int stc_duration(stc_handle* sh, const int64_t* text_ids, const float* style_dp,
         validate_ids(text_ids, (size_t)B * T, h->cfg.vocab_size);
         int si = h->cfg.style_dp_tokens * h->cfg.style_dp_dim;
         auto body = [&]() {
-            h->arena.reset();
+            h->arena.reset(); h->h_stage_off = 0;
             int64_t* d_ids = up(h, text_ids, (size_t)B * T);
             float* d_sty = up(h, style_dp, (size_t)B * si);
             float* d_mask = up(h, text_mask, (size_t)B * T);
@@ -889,7 +976,7 @@ int stc_text_encode(stc_handle* sh, const int64_t* text_ids, const float* style_
         validate_ids(text_ids, (size_t)B * T, h->cfg.vocab_size);
         int C = h->cfg.text_emb_channels, S = h->cfg.style_ttl_tokens, Cs = h->cfg.style_ttl_dim;
         auto body = [&]() {
-            h->arena.reset();
+            h->arena.reset(); h->h_stage_off = 0;
             int64_t* d_ids = up(h, text_ids, (size_t)B * T);
             float* d_sty = up(h, style_ttl, (size_t)B * S * Cs);
             float* d_mask = up(h, text_mask, (size_t)B * T);
@@ -920,24 +1007,24 @@ int stc_vector_step(stc_handle* sh, const float* noisy_latent, const float* text
                 throw StcError(STC_ERR_UNSUPPORTED, "per-utterance step counters must be equal (the reference passes one value, cpp/helper.cpp:573,591)");
         int C = h->cfg.text_emb_channels, S = h->cfg.style_ttl_tokens, Cs = h->cfg.style_ttl_dim, D = h->cfg.latent_channels;
         float dt = 1.0f / total_step[0];
+        const float* tvec = h->time_vectors(current_step[0], total_step[0]);
         auto body = [&]() {
-            h->arena.reset();
+            h->arena.reset(); h->h_stage_off = 0;
             float* d_x_ncl = up(h, noisy_latent, (size_t)B * D * L);
             float* d_te_ncl = up(h, text_emb, (size_t)B * C * T);
             float* d_sty = up(h, style_ttl, (size_t)B * S * Cs);
             float* d_tm = up(h, text_mask, (size_t)B * T);
             float* d_lm = up(h, latent_mask, (size_t)B * L);
-            float* d_tot = up(h, total_step, (size_t)B);
-            float* d_cur = up(h, current_step, (size_t)B);
             float* d_x = h->ws<float>((size_t)B * L * D);
             float* d_te = h->ws<float>((size_t)B * T * C);
             float* d_dt = h->ws<float>(D);
             transpose(h, d_x_ncl, d_x, B, D, L);
             transpose(h, d_te_ncl, d_te, B, C, T);
             STC_LAUNCH(h, fill_kernel, cdiv(D, 128), 128, 0, d_dt, dt, (size_t)D);
-            VeCtx vc; vc.B = B; vc.L = L; vc.T = T; vc.lmask = d_lm; vc.tmask = d_tm;
+            VeCtx vc;
+            vc.lat = h->rect_seq(B, L, d_lm, true); vc.text = h->rect_seq(B, T, d_tm, true); vc.style = h->rect_seq(B, S, nullptr, false);
             h->prepare_ve(vc, d_te, d_sty);
-            h->run_ve_step(vc, d_x, d_cur, d_tot, d_dt);
+            h->run_ve_step(vc, d_x, tvec, d_dt);
             transpose(h, d_x, d_x_ncl, B, L, D);
             if (!h->dry) STC_CUDA(cudaMemcpyAsync(denoised_out, d_x_ncl, (size_t)B * D * L * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         };
@@ -954,12 +1041,12 @@ int stc_vocode(stc_handle* sh, const float* latent, int B, int L, float* wav_out
         if (B <= 0 || L <= 0 || !latent || !wav_out) throw StcError(STC_ERR_INVALID, "stc_vocode: bad argument");
         int D = h->cfg.latent_channels; size_t nw = (size_t)B * L * h->cfg.chunk_size;
         auto body = [&]() {
-            h->arena.reset();
+            h->arena.reset(); h->h_stage_off = 0;
             float* d_ncl = up(h, latent, (size_t)B * D * L);
             float* d_cl = h->ws<float>((size_t)B * D * L);
             float* d_wav = h->ws<float>(nw);
             transpose(h, d_ncl, d_cl, B, D, L);
-            h->run_vocoder(d_cl, B, L, d_wav);
+            h->run_vocoder(d_cl, h->rect_seq(B, L, nullptr, false), d_wav);
             if (!h->dry) STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, nw * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         };
         h->ensure_ws(body);
@@ -985,33 +1072,32 @@ static int latent_len_f32(const float* dur, int B, int sr, int cs) {
     return (int)q;
 }
 
-void Handle::synth_tail(const float* d_text_emb, const float* d_tmask, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                        uint64_t seed, const int64_t* d_wavlen, int B, int T, int L, int steps, float* d_lmask, float* d_xlat, float* d_wav) {
+void Handle::synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
+                        uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav) {
     int D = cfg.latent_channels;
-    STC_LAUNCH(this, latent_mask_kernel, cdiv((size_t)B * L, 256), 256, 0, d_wavlen, d_lmask, B, L, cfg.chunk_size);
-    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)B * L * D, 256), 256, 0, d_noise, noise_ld, seed, d_lmask, d_xlat, B, D, L);
-    VeCtx vc; vc.B = B; vc.L = L; vc.T = T; vc.lmask = d_lmask; vc.tmask = d_tmask;
+    std::vector<const float*> tv(steps);
+    for (int s = 0; s < steps; ++s) tv[s] = time_vectors((float)s, (float)steps);
+    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)lat.rows * D, 256), 256, 0, d_noise, noise_ld, seed, lat.mask, d_xlat, lat.rows, lat.off, lat.B, D);
+    VeCtx vc; vc.lat = lat; vc.text = text; vc.style = rect_seq(text.B, cfg.style_ttl_tokens, nullptr, false);
     prepare_ve(vc, d_text_emb, d_style_ttl);
-    float* d_tot = ws<float>(B); float* d_cur = ws<float>((size_t)B * steps); float* d_dt = ws<float>(D);
-    STC_LAUNCH(this, fill_kernel, cdiv(B, 128), 128, 0, d_tot, (float)steps, (size_t)B);
+    float* d_dt = ws<float>(D);
     STC_LAUNCH(this, fill_kernel, cdiv(D, 128), 128, 0, d_dt, 1.0f / (float)steps, (size_t)D);
-    for (int s = 0; s < steps; ++s) {
-        STC_LAUNCH(this, fill_kernel, cdiv(B, 128), 128, 0, d_cur + (size_t)s * B, (float)s, (size_t)B);
-        run_ve_step(vc, d_xlat, d_cur + (size_t)s * B, d_tot, d_dt);
-    }
+    for (int s = 0; s < steps; ++s) run_ve_step(vc, d_xlat, tv[s], d_dt);
     if (profile && !dry) cudaEventRecord(ev[3], stream);
-    run_vocoder(d_xlat, B, L, d_wav);
+    run_vocoder(d_xlat, lat, d_wav);
 }
 
 }  // namespace stc
 
 extern "C" {
 
-static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+// mode bits: 1 = host I/O (else device pointers), 2 = packed latent rows (else the reference's padded rectangle)
+static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
                       const float* style_dp, int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld,
-                      uint64_t seed, float* wav_out, int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
-                      float* latent_out) {
+                      uint64_t seed, float* wav_out, int64_t wav_cap, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
+                      float* latent_out, int64_t* wav_offsets_out) {
     STC_TRY(sh, {
+        const bool host_io = mode & 1, packed = mode & 2;
         Scope sc(sh); Handle* h = sc.h;
         if (B <= 0 || T <= 0 || total_step <= 0 || !(speed > 0.f) || !text_ids || !text_mask || !style_ttl || !style_dp || !wav_out)
             throw StcError(STC_ERR_INVALID, "stc_synthesize: bad argument");
@@ -1028,11 +1114,12 @@ static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, con
         }
         cudaStream_t st = h->stream;
         for (auto& k : h->kprof) k = Handle::KProf{};
-        // ---- stage 1: DP (+ /speed, wav lengths) and TE; sized independently of L
+        for (int s = 0; s < total_step; ++s) h->time_vectors((float)s, (float)total_step);     // cached after the first call
+        // ---- stage 1: DP (+ /speed, wav lengths) and TE; independent of L
         const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
         float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
         auto stage1 = [&]() {
-            h->arena.reset(); h->persist.reset();
+            h->arena.reset(); h->persist.reset(); h->h_stage_off = 0;
             if (host_io) {
                 d_ids = upp(h, text_ids, (size_t)B * T); d_tmask = upp(h, text_mask, (size_t)B * T);
                 d_sttl = upp(h, style_ttl, (size_t)B * S * Cs); d_sdp = upp(h, style_dp, (size_t)B * si);
@@ -1058,31 +1145,51 @@ static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, con
         if (duration_out && host_io) memcpy(duration_out, h->h_dur, sizeof(float) * B);
         if (wav_lengths_out) memcpy(wav_lengths_out, h->h_wavlen, sizeof(int64_t) * B);
         if (L <= 0) throw StcError(STC_ERR_INVALID, "computed latent length is 0");
-        int64_t wav_row = (int64_t)L * c.chunk_size;
-        if (wav_ld < wav_row) throw StcError(STC_ERR_CAPACITY, "wav_out rows too short: need " + std::to_string(wav_row));
-        if (noise && noise_ld < L) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length " + std::to_string(L));
+        // latent frames per utterance: integer formula of getLatentMask (cpp/helper.cpp:767)
+        std::vector<int> lens(B);
+        int64_t R = 0; int maxlen = 0;
+        for (int b = 0; b < B; ++b) {
+            lens[b] = (int)((h->h_wavlen[b] + c.chunk_size - 1) / c.chunk_size);
+            R += lens[b]; maxlen = std::max(maxlen, lens[b]);
+        }
+        if (wav_offsets_out) { wav_offsets_out[0] = 0; for (int b = 0; b < B; ++b) wav_offsets_out[b + 1] = wav_offsets_out[b] + (int64_t)lens[b] * c.chunk_size; }
+        const int64_t rows = packed ? R : (int64_t)B * L;
+        const int64_t wav_need = packed ? R * c.chunk_size : (int64_t)L * c.chunk_size;   // total floats (packed) / per row (rectangle)
+        if (wav_cap < wav_need) throw StcError(STC_ERR_CAPACITY, "wav_out too small: need " + std::to_string(wav_need));
+        if (noise && noise_ld < (packed ? maxlen : L)) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length");
         // ---- stage 2: everything that depends on L
         float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
         auto stage2 = [&]() {
-            h->arena.reset();
+            h->arena.reset();          // (the pinned offset staging keeps growing: stage-1 copies may still be in flight)
             d_noise = nullptr;
             if (noise) d_noise = up(h, noise, (size_t)B * D * noise_ld);
-            d_lmask = h->ws<float>((size_t)B * L); d_xlat = h->ws<float>((size_t)B * L * D);
-            d_wav = host_io ? h->ws<float>((size_t)B * wav_row) : wav_out;
-            if (latent_out) d_lat_ncl = h->ws<float>((size_t)B * L * D);
-            h->synth_tail(d_temb, d_tmask, d_sttl, d_noise, noise_ld, seed, d_wavlen, B, T, L, total_step, d_lmask, d_xlat, d_wav);
+            d_xlat = h->ws<float>((size_t)rows * D);
+            d_wav = host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
+            Seq text = h->rect_seq(B, T, d_tmask, true), lat;
+            if (packed) lat = h->packed_seq(lens, (int)R, maxlen);
+            else {
+                d_lmask = h->ws<float>((size_t)B * L);
+                STC_LAUNCH(h, latent_mask_kernel, cdiv((size_t)B * L, 256), 256, 0, d_wavlen, d_lmask, B, L, c.chunk_size);
+                lat = h->rect_seq(B, L, d_lmask, true);
+                if (latent_out) d_lat_ncl = h->ws<float>((size_t)B * L * D);
+            }
+            h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav);
         };
-        // NOTE: in device-I/O mode the wav rows are dense [B][L*cs] at the start of wav_dev when wav_ld == L*cs;
-        // otherwise rows are compacted by the caller via L_out.
         h->ensure_ws(stage2);
         stage2();
         if (h->profile) cudaEventRecord(h->ev[4], st);
         if (host_io) {
-            STC_CUDA(cudaMemcpy2DAsync(wav_out, (size_t)wav_ld * sizeof(float), d_wav, (size_t)wav_row * sizeof(float),
-                                       (size_t)wav_row * sizeof(float), B, cudaMemcpyDeviceToHost, st));
-            if (latent_out) {
-                transpose(h, d_xlat, d_lat_ncl, B, L, D);
-                STC_CUDA(cudaMemcpyAsync(latent_out, d_lat_ncl, (size_t)B * L * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (packed) {
+                STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)R * c.chunk_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (latent_out) STC_CUDA(cudaMemcpyAsync(latent_out, d_xlat, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            } else {
+                int64_t wav_row = (int64_t)L * c.chunk_size;
+                STC_CUDA(cudaMemcpy2DAsync(wav_out, (size_t)wav_cap * sizeof(float), d_wav, (size_t)wav_row * sizeof(float),
+                                           (size_t)wav_row * sizeof(float), B, cudaMemcpyDeviceToHost, st));
+                if (latent_out) {
+                    transpose(h, d_xlat, d_lat_ncl, B, L, D);
+                    STC_CUDA(cudaMemcpyAsync(latent_out, d_lat_ncl, (size_t)B * L * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+                }
             }
         } else if (duration_out) {
             STC_CUDA(cudaMemcpyAsync(duration_out, d_dur, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
@@ -1104,15 +1211,30 @@ static int synth_impl(stc_handle* sh, bool host_io, const int64_t* text_ids, con
 int stc_synthesize(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl, const float* style_dp,
                    int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld, uint64_t seed, float* wav_out,
                    int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out, float* latent_out) {
-    return synth_impl(h, true, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_ld,
-                      duration_out, wav_lengths_out, L_out, latent_out);
+    return synth_impl(h, 1, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_ld,
+                      duration_out, wav_lengths_out, L_out, latent_out, nullptr);
 }
 
 int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,
                           const float* style_dp_dev, int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
                           int64_t wav_ld, float* duration_dev, int64_t* L_out) {
-    return synth_impl(h, false, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
-                      wav_dev, wav_ld, duration_dev, nullptr, L_out, nullptr);
+    return synth_impl(h, 0, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
+                      wav_dev, wav_ld, duration_dev, nullptr, L_out, nullptr, nullptr);
+}
+
+int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl, const float* style_dp,
+                          int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld, uint64_t seed,
+                          float* wav_out, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out, int64_t* wav_lengths_out,
+                          float* latent_out) {
+    return synth_impl(h, 3, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_cap,
+                      duration_out, wav_lengths_out, nullptr, latent_out, wav_offsets_out);
+}
+
+int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,
+                                 const float* style_dp_dev, int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
+                                 int64_t wav_cap, int64_t* wav_offsets_out, float* duration_dev) {
+    return synth_impl(h, 2, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
+                      wav_dev, wav_cap, duration_dev, nullptr, nullptr, nullptr, wav_offsets_out);
 }
 
 int stc_text_to_ids(stc_handle* sh, const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,

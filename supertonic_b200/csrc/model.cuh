@@ -45,7 +45,8 @@ struct Linear {
     float* bias = nullptr;            // [N]
     __nv_bfloat16* w_hi = nullptr;    // [N,K] K-major split pair (tensor-core B operand)
     __nv_bfloat16* w_lo = nullptr;
-    CUtensorMap map_hi{}, map_lo{};
+    CUtensorMap map_hi{}, map_lo{};        // box rows 128
+    CUtensorMap map64_hi{}, map64_lo{};    // box rows 64
     bool has_maps = false;
 };
 
@@ -94,7 +95,16 @@ private:
     size_t cap_ = 0, off_ = 0;
 };
 
-struct NeedGrow { size_t bytes; };
+// B variable-length sequences stored back to back (kernels.cuh "packed sequences").
+struct Seq {
+    const int* off = nullptr;    // device [B+1] row offsets
+    int B = 0;
+    int rows = 0;                // rows launched (>= off[B] when a graph bucket pads)
+    int maxlen = 0;              // upper bound of any sequence length (attention grid)
+    const float* len = nullptr;  // device [B] float lengths (length-aware RoPE); sum of the mask in rectangle mode
+    const int* cnt = nullptr;    // device [B]: 1 + last unmasked index (lets attention skip a masked tail); null = all
+    const float* mask = nullptr; // device per-row 0/1 mask; null when every row is valid (packed mode)
+};
 
 struct Handle;
 }  // namespace stc

@@ -150,22 +150,23 @@ class TextToSpeech:
 
     # -- throughput path (north_star: "a request batch is length-bucketed")
     def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05,
-                        max_batch: int = 64, max_pad: float = 1.35, seed: int = 0):
-        """Independent utterances → list of (trimmed wav, duration) in input order. Utterances are sorted by
-        token count and cut into sub-batches whose longest/shortest token ratio stays below `max_pad`, so padded
-        work stays bounded; results do not depend on the grouping (tests: batch-composition invariance)."""
+                        max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None):
+        """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
+        rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
+        utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
+        (tests: batch-composition invariance)."""
         from .scheduler import length_buckets
         n = len(texts)
         ids, mask = self.engine.text_to_ids(texts, langs)
         lens = mask.reshape(n, -1).sum(1).astype(np.int64)
         out: List[Optional[Tuple[np.ndarray, float]]] = [None] * n
-        for grp in length_buckets(lens, max_batch, max_pad):
+        for grp in length_buckets(lens, max_batch, 1e9):
             g = np.asarray(grp)
             T = int(lens[g].max())
-            r = self.engine.synthesize(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed, seed=seed)
+            r = self.engine.synthesize_packed(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed,
+                                              seed=seed, noise=None if noise is None else noise[g])
             for k, i in enumerate(grp):
-                m = int(r["wav_lengths"][k])
-                out[i] = (r["wav"][k, :m].copy(), float(r["duration"][k]))
+                out[i] = (r["wavs"][k], float(r["duration"][k]))
         return out
 
 

@@ -154,6 +154,28 @@ def test_batch_composition_invariance(rig):
         assert U.snr_db(one["wav"][0, :n], full["wav"][b, :n]) >= 90.0
 
 
+def test_packed_synthesis_matches_oracle_per_utterance(rig):
+    """Throughput path (packed latent rows, stc_synthesize_packed): every utterance's trimmed waveform, duration,
+    sample count and latent equal the oracle's `_infer` of that utterance alone with the same noise."""
+    ids, mask, ttl, dp = _inputs(rig, 80, 5, 20, 120)
+    rng = np.random.default_rng(11)
+    nz = rng.standard_normal((5, 144, 300)).astype(np.float32)
+    out = rig["eng"].synthesize_packed(ids, mask, ttl, dp, 3, 1.05, noise=nz, want_latent=True)
+    for b in range(5):
+        t = int(mask[b].sum())
+        tr = {}
+        wav_ref, dur_ref = rig["ora"].infer_ids(ids[b:b + 1, :t], mask[b:b + 1, :, :t], ttl[b:b + 1], dp[b:b + 1], 3, np.float32(1.05),
+                                                lambda B, D, L, b=b: nz[b:b + 1, :, :L], tr)
+        np.testing.assert_array_equal(out["duration"][b:b + 1], dur_ref)
+        np.testing.assert_array_equal(out["wav_lengths"][b:b + 1], tr["wav_lengths"])
+        assert out["frames"][b] == tr["latent_len"]
+        err = np.abs(out["latent"][b].T - tr["xs"][-1][0]).max()
+        assert err <= LAT_TOL_EXPECTED, err
+        n = int(tr["wav_lengths"][0])
+        assert len(out["wavs"][b]) == n
+        assert U.snr_db(out["wavs"][b], wav_ref[:n]) >= SNR_EXPECTED
+
+
 def test_fp32_simt_cross_check(rig):
     """The CUDA-core fp32 GEMM path and the tcgen05 split-bf16 path agree (guards the descriptor/swizzle plumbing)."""
     capi = rig["capi"]
