@@ -372,7 +372,7 @@ STC_DEVINL uint32_t mix32(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return (uint32_t)(z >> 16);
 }
-__global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, uint64_t seed,
+__global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, const uint64_t* __restrict__ seed_p,
                                    const float* __restrict__ mask, float* __restrict__ x, int rows,
                                    const int* __restrict__ off, int B, int D) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,7 +385,7 @@ __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, 
     float v;
     if (noise) v = noise[((size_t)b * D + d) * ld + l];
     else {
-        uint64_t key = seed * 0x9E3779B97F4A7C15ull + ((uint64_t)b << 40) + ((uint64_t)d << 24) + (uint64_t)l;
+        uint64_t key = __ldg(seed_p) * 0x9E3779B97F4A7C15ull + ((uint64_t)b << 40) + ((uint64_t)d << 24) + (uint64_t)l;
         float u1 = (mix32(key) + 1.0f) * (1.0f / 4294967808.0f);          // (0,1]
         float u2 = mix32(key ^ 0xD1B54A32D192ED03ull) * (1.0f / 4294967296.0f);
         v = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);

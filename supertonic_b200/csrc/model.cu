@@ -42,8 +42,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct GraphKey {
-    int B, T, L, steps, mode;
-    bool operator<(const GraphKey& o) const { return std::tie(B, T, L, steps, mode) < std::tie(o.B, o.T, o.L, o.steps, o.mode); }
+    int stage, mode, B, T, rows, maxlen, steps; int64_t noise_ld; uintptr_t p0, p1;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1) <
+               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1);
+    }
 };
 
 struct VeCtx {
@@ -62,7 +65,13 @@ struct Handle {
     std::vector<void*> owned;          // weight allocations
     Arena arena;       // workspace: reset per stage
     Arena persist;     // buffers that survive from stage 1 (DP/TE) into stage 2 (VE loop + vocoder)
-    bool dry = false;
+    bool dry = false;          // no launches / copies (workspace measuring pass, or re-staging before a graph replay)
+    bool restage = false;      // dry, but offset arrays are still written into their pinned staging slots
+    bool capturing = false;    // launches go into a stream capture; host->device copies of caller memory are deferred
+    struct PreCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<PreCopy> pre_copies;
+    void run_graphed(const GraphKey& key, const std::function<void()>& body);
+    uint64_t graph_replays = 0, graph_captures = 0;
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> map_cache;
@@ -89,7 +98,8 @@ struct Handle {
     }
     float stage_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[7] = {};   // start, dp, te, ve, vocoder, end, duration-ready
-    std::map<GraphKey, cudaGraphExec_t> graphs;
+    struct GraphEntry { cudaGraphExec_t exec; uint64_t kernels; };
+    std::map<GraphKey, GraphEntry> graphs;
     std::map<GraphKey, size_t> ws_need;
     TextFrontend frontend;
     // persistent small device buffers for the fast layer
@@ -167,7 +177,7 @@ struct Handle {
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 Handle::~Handle() {
-    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
     for (void* p : owned) cudaFree(p);
     if (d_dtvec) cudaFree(d_dtvec);
     if (h_dur) cudaFreeHost(h_dur);
@@ -564,12 +574,12 @@ void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* c
 // ------------------------------------------------------------------------------------------ sequence descriptors
 int* Handle::stage_ints(const std::vector<int>& v) {
     int* d = ws<int>(v.size());
-    if (dry) return d;
+    if (dry && !restage) return d;
     if (h_stage_off + v.size() > h_stage_cap) throw StcError(STC_ERR_CAPACITY, "offset staging buffer exhausted (batch too large)");
     int* hp = h_stage + h_stage_off;
     h_stage_off += v.size();
     memcpy(hp, v.data(), v.size() * sizeof(int));
-    STC_CUDA(cudaMemcpyAsync(d, hp, v.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (!restage) STC_CUDA(cudaMemcpyAsync(d, hp, v.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     return d;
 }
 
@@ -807,7 +817,7 @@ void Handle::ensure_ws(const std::function<void()>& fn) {
     dry = was;
     persist.rewind(p_used);
     if (arena.high_water > arena.capacity() || persist.high_water > persist.capacity()) {
-        for (auto& g : graphs) cudaGraphExecDestroy(g.second);     // captured pointers die with the old arena
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);     // captured pointers die with the old arena
         graphs.clear(); map_cache.clear();
         if (persist.high_water > persist.capacity()) {
             if (p_used) throw StcError(STC_ERR_CUDA, "persistent arena cannot grow while in use");
@@ -815,6 +825,43 @@ void Handle::ensure_ws(const std::function<void()>& fn) {
         }
         arena.reserve(arena.high_water);
     }
+}
+
+// Run `body` (which must allocate deterministically from the arenas) either eagerly or as a cached CUDA graph.
+// Replay: `body` is re-run with launches suppressed, only to refresh the pinned staging slots (sequence offsets, seed)
+// and to collect the caller-memory uploads, then the instantiated graph is launched.
+void Handle::run_graphed(const GraphKey& key, const std::function<void()>& body) {
+    if (!use_graphs || profile) { ensure_ws(body); body(); return; }
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+        ensure_ws(body);                       // may grow the arenas (and then drops every cached graph)
+        if (graphs.size() >= 48) { for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec); graphs.clear(); }
+        pre_copies.clear();
+        uint64_t l0 = launches;
+        cudaGraph_t graph = nullptr;
+        STC_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+        try { body(); } catch (...) { capturing = false; cudaStreamEndCapture(stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        capturing = false;
+        STC_CUDA(cudaStreamEndCapture(stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        it = graphs.emplace(key, GraphEntry{exec, launches - l0}).first;
+        launches = l0;                         // captured, not launched yet
+        ++graph_captures;
+    } else {
+        pre_copies.clear();
+        dry = true; restage = true;
+        try { body(); } catch (...) { dry = false; restage = false; throw; }
+        dry = false; restage = false;
+        ++graph_replays;
+    }
+    for (const PreCopy& c : pre_copies) STC_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, stream));
+    pre_copies.clear();
+    STC_CUDA(cudaGraphLaunch(it->second.exec, stream));
+    launches += it->second.kernels;            // kernels executed by this replay
 }
 
 }  // namespace stc
@@ -923,16 +970,12 @@ struct Scope {   // per-call: select device, reset arena
         h->h_stage_off = 0;
     }
 };
-template <typename T> T* upp(Handle* h, const T* host, size_t n) {   // into the persistent arena
-    T* d = h->ps<T>(n);
-    if (!h->dry) STC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    return d;
+template <typename T> void h2d(Handle* h, T* d, const T* host, size_t n) {
+    if (h->capturing || h->restage) h->pre_copies.push_back({d, host, n * sizeof(T)});     // issued before the graph launch
+    else if (!h->dry) STC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
 }
-template <typename T> T* up(Handle* h, const T* host, size_t n) {
-    T* d = h->ws<T>(n);
-    if (!h->dry) STC_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    return d;
-}
+template <typename T> T* upp(Handle* h, const T* host, size_t n) { T* d = h->ps<T>(n); h2d(h, d, host, n); return d; }   // persistent arena
+template <typename T> T* up(Handle* h, const T* host, size_t n) { T* d = h->ws<T>(n); h2d(h, d, host, n); return d; }
 void validate_ids(const int64_t* ids, size_t n, int V) {
     for (size_t i = 0; i < n; ++i)
         if (ids[i] < 0 || ids[i] >= V) throw StcError(STC_ERR_INVALID, "text_ids value out of the embedding table range");
@@ -1077,7 +1120,9 @@ void Handle::synth_tail(const float* d_text_emb, const Seq& text, const float* d
     int D = cfg.latent_channels;
     std::vector<const float*> tv(steps);
     for (int s = 0; s < steps; ++s) tv[s] = time_vectors((float)s, (float)steps);
-    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)lat.rows * D, 256), 256, 0, d_noise, noise_ld, seed, lat.mask, d_xlat, lat.rows, lat.off, lat.B, D);
+    std::vector<int> sbits = {(int)(uint32_t)(seed & 0xffffffffu), (int)(uint32_t)(seed >> 32)};
+    const uint64_t* d_seed = reinterpret_cast<const uint64_t*>(stage_ints(sbits));     // per call, outside the graph's baked arguments
+    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)lat.rows * D, 256), 256, 0, d_noise, noise_ld, d_seed, lat.mask, d_xlat, lat.rows, lat.off, lat.B, D);
     VeCtx vc; vc.lat = lat; vc.text = text; vc.style = rect_seq(text.B, cfg.style_ttl_tokens, nullptr, false);
     prepare_ve(vc, d_text_emb, d_style_ttl);
     float* d_dt = ws<float>(D);
@@ -1111,34 +1156,42 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             STC_CUDA(cudaMallocHost((void**)&h->h_dur, sizeof(float) * B));
             STC_CUDA(cudaMallocHost((void**)&h->h_wavlen, sizeof(int64_t) * B));
             h->h_cap = B;
+            for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);     // graphs captured the old pinned addresses
+            h->graphs.clear();
         }
         cudaStream_t st = h->stream;
         for (auto& k : h->kprof) k = Handle::KProf{};
         for (int s = 0; s < total_step; ++s) h->time_vectors((float)s, (float)total_step);     // cached after the first call
-        // ---- stage 1: DP (+ /speed, wav lengths) and TE; independent of L
+        // ---- stage 1: DP (+ /speed, wav lengths) and TE; independent of L. Two graphs so that the host can start waiting
+        //      for the durations while the text encoder is still running.
         const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
         float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
-        auto stage1 = [&]() {
+        const uintptr_t pin = host_io ? 0 : (uintptr_t)text_ids ^ ((uintptr_t)text_mask << 1) ^ ((uintptr_t)style_ttl << 2) ^ ((uintptr_t)style_dp << 3);
+        auto stage1a = [&]() {
             h->arena.reset(); h->persist.reset(); h->h_stage_off = 0;
             if (host_io) {
                 d_ids = upp(h, text_ids, (size_t)B * T); d_tmask = upp(h, text_mask, (size_t)B * T);
                 d_sttl = upp(h, style_ttl, (size_t)B * S * Cs); d_sdp = upp(h, style_dp, (size_t)B * si);
             } else { d_ids = text_ids; d_tmask = text_mask; d_sttl = style_ttl; d_sdp = style_dp; }
             d_dur = h->ps<float>(B); d_wavlen = h->ps<int64_t>(B); d_temb = h->ps<float>((size_t)B * T * C);
-            if (h->profile && !h->dry) cudaEventRecord(h->ev[0], st);
             h->run_dp(d_ids, d_sdp, d_tmask, B, T, d_dur);
             STC_LAUNCH(h, dur_post_kernel, cdiv(B, 128), 128, 0, d_dur, d_wavlen, B, speed, c.sample_rate);
             if (!h->dry) {
                 STC_CUDA(cudaMemcpyAsync(h->h_dur, d_dur, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
                 STC_CUDA(cudaMemcpyAsync(h->h_wavlen, d_wavlen, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
-                if (h->profile) cudaEventRecord(h->ev[1], st);
-                cudaEventRecord(h->ev[6], st);
             }
-            h->run_te(d_ids, d_sttl, d_tmask, B, T, d_temb);      // overlaps the D2H of the durations
-            if (h->profile && !h->dry) cudaEventRecord(h->ev[2], st);
         };
-        h->ensure_ws(stage1);
-        stage1();
+        auto stage1b = [&]() {
+            h->arena.reset();
+            h->run_te(d_ids, d_sttl, d_tmask, B, T, d_temb);      // overlaps the D2H of the durations
+        };
+        uint32_t speed_bits; memcpy(&speed_bits, &speed, 4);
+        if (h->profile) cudaEventRecord(h->ev[0], st);
+        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0}, stage1a);
+        if (h->profile) cudaEventRecord(h->ev[1], st);
+        cudaEventRecord(h->ev[6], st);
+        h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0}, stage1b);
+        if (h->profile) cudaEventRecord(h->ev[2], st);
         STC_CUDA(cudaEventSynchronize(h->ev[6]));                 // the one data-dependent sync: duration -> L
         int L = latent_len_f32(h->h_dur, B, c.sample_rate, c.chunk_size);
         if (L_out) *L_out = L;
@@ -1153,9 +1206,15 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             R += lens[b]; maxlen = std::max(maxlen, lens[b]);
         }
         if (wav_offsets_out) { wav_offsets_out[0] = 0; for (int b = 0; b < B; ++b) wav_offsets_out[b + 1] = wav_offsets_out[b] + (int64_t)lens[b] * c.chunk_size; }
-        const int64_t rows = packed ? R : (int64_t)B * L;
-        const int64_t wav_need = packed ? R * c.chunk_size : (int64_t)L * c.chunk_size;   // total floats (packed) / per row (rectangle)
-        if (wav_cap < wav_need) throw StcError(STC_ERR_CAPACITY, "wav_out too small: need " + std::to_string(wav_need));
+        // graph buckets: packed rows are rounded up to a multiple of 128 (extra rows belong to no sequence), the
+        // longest-utterance bound (attention grid) to a multiple of 16
+        const int64_t rows = packed ? (h->use_graphs && !h->profile ? (R + 127) / 128 * 128 : R) : (int64_t)B * L;
+        const int maxlen_launch = packed ? (maxlen + 15) / 16 * 16 : L;
+        const int64_t wav_need = packed ? rows * c.chunk_size : (int64_t)L * c.chunk_size;   // total floats (packed) / per row (rectangle)
+        if (wav_cap < wav_need) {
+            if (wav_offsets_out) wav_offsets_out[B] = std::max<int64_t>(wav_offsets_out[B], wav_need);
+            throw StcError(STC_ERR_CAPACITY, "wav_out too small: need " + std::to_string(wav_need));
+        }
         if (noise && noise_ld < (packed ? maxlen : L)) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length");
         // ---- stage 2: everything that depends on L
         float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
@@ -1166,7 +1225,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             d_xlat = h->ws<float>((size_t)rows * D);
             d_wav = host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
             Seq text = h->rect_seq(B, T, d_tmask, true), lat;
-            if (packed) lat = h->packed_seq(lens, (int)R, maxlen);
+            if (packed) lat = h->packed_seq(lens, (int)rows, maxlen_launch);
             else {
                 d_lmask = h->ws<float>((size_t)B * L);
                 STC_LAUNCH(h, latent_mask_kernel, cdiv((size_t)B * L, 256), 256, 0, d_wavlen, d_lmask, B, L, c.chunk_size);
@@ -1175,8 +1234,8 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             }
             h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav);
         };
-        h->ensure_ws(stage2);
-        stage2();
+        h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
+                                pin, host_io ? 0 : (uintptr_t)wav_out}, stage2);
         if (h->profile) cudaEventRecord(h->ev[4], st);
         if (host_io) {
             if (packed) {

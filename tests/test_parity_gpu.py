@@ -176,6 +176,40 @@ def test_packed_synthesis_matches_oracle_per_utterance(rig):
         assert U.snr_db(out["wavs"][b], wav_ref[:n]) >= SNR_EXPECTED
 
 
+def test_cuda_graph_replay_is_bit_identical(rig):
+    """Capture (1st call), replay (2nd call, different utterances of the same bucket) and eager execution agree bit for bit."""
+    eng = rig["eng"]
+    rng = np.random.default_rng(12)
+    nz = rng.standard_normal((4, 144, 300)).astype(np.float32)
+    ids, mask, ttl, dp = _inputs(rig, 90, 4, 40, 80)
+    ids2, mask2, ttl2, dp2 = _inputs(rig, 91, 4, 40, 80)
+    T = max(ids.shape[1], ids2.shape[1])
+
+    def pad(i, m):
+        io = np.zeros((4, T), np.int64); mo = np.zeros((4, 1, T), np.float32)
+        io[:, :i.shape[1]] = i; mo[:, :, :m.shape[2]] = m
+        return io, mo
+    (ids, mask), (ids2, mask2) = pad(ids, mask), pad(ids2, mask2)
+    eng.set_graphs(True)
+    a1 = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    b1 = eng.synthesize_packed(ids2, mask2, ttl2, dp2, 2, 1.05, noise=nz, want_latent=True)
+    a2 = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    r1 = eng.synthesize(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    r2 = eng.synthesize(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    eng.set_graphs(False)
+    a0 = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    b0 = eng.synthesize_packed(ids2, mask2, ttl2, dp2, 2, 1.05, noise=nz, want_latent=True)
+    r0 = eng.synthesize(ids, mask, ttl, dp, 2, 1.05, noise=nz, want_latent=True)
+    eng.set_graphs(True)
+    for x, y in ((a1, a0), (a2, a0), (b1, b0)):
+        np.testing.assert_array_equal(x["duration"], y["duration"])
+        for k in range(4):
+            np.testing.assert_array_equal(x["wavs"][k], y["wavs"][k])
+            np.testing.assert_array_equal(x["latent"][k], y["latent"][k])
+    for x in (r1, r2):
+        np.testing.assert_array_equal(x["wav"], r0["wav"]); np.testing.assert_array_equal(x["latent"], r0["latent"])
+
+
 def test_fp32_simt_cross_check(rig):
     """The CUDA-core fp32 GEMM path and the tcgen05 split-bf16 path agree (guards the descriptor/swizzle plumbing)."""
     capi = rig["capi"]
