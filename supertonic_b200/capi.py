@@ -129,10 +129,14 @@ class Frontend:
     def __call__(self, texts, langs):
         return _texts_to_ids(lib.stc_frontend_text_to_ids, self._h, texts, langs)
 
-    def __del__(self):
+    text_to_ids = __call__
+
+    def close(self):
         if getattr(self, "_h", None):
             lib.stc_frontend_close(self._h)
             self._h = None
+
+    __del__ = close
 
 
 class Engine:

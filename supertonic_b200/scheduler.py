@@ -44,3 +44,27 @@ def synth_cost(n_tokens: int, total_step: int) -> float:
     """Relative cost of one utterance: frames ∝ tokens; VE runs `total_step` times at 1x frame rate, the vocoder once
     at 6x with 2x the width (4x the FLOPs per frame)."""
     return float(n_tokens) * (total_step * 1.0 + 6 * 4.0 * 0.35)
+
+
+def shard_for_rank(n_tokens: Sequence[int], total_step: int, rank: int, world_size: int) -> List[int]:
+    """Indices of the utterances rank `rank` synthesises: LPT over `synth_cost`, identical on every rank (pure function of
+    the token counts), so no rank needs to talk to another to know its share."""
+    return shard_lpt([synth_cost(int(t), total_step) for t in n_tokens], world_size)[rank]
+
+
+def reduce_throughput(audio_seconds: float, elapsed_ms: float, world_size: int = 1):
+    """Whole-job audio-sec/sec from per-rank (audio, device time): sum of the audio over ranks / MAX of the time over ranks.
+    Uses torch.distributed when a process group is up (NCCL on the GPU box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(elapsed_ms), float(audio_seconds)], dtype=torch.float64)
+    if world_size > 1 and dist.is_initialized():
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, audio = float(tmax[0]), float(tsum[1])
+    else:
+        ms, audio = float(t[0]), float(t[1])
+    return audio / (ms / 1000.0), ms, audio
