@@ -19,3 +19,14 @@ mkdir -p "$here/_ref"
 g++ -std=c++17 -O2 -I "$here/ref_stub" -I "$ref/cpp" -I "$nl" \
     "$ref/cpp/helper.cpp" "$here/ref_host_driver.cpp" -o "$here/_ref/ref_host"
 echo "built $here/_ref/ref_host"
+
+# The drop-in proof: the UNMODIFIED reference CLI (cpp/example_onnx.cpp + cpp/helper.cpp, compiled where they lie)
+# against include/ort_shim/onnxruntime_cxx_api.h, linked to libsupertonic_cuda.so instead of libonnxruntime.
+# Run by tests/test_dropin_gpu.py on the B200 box. (-O2, no -ffast-math: see above.)
+lib="$here/../supertonic_b200/libsupertonic_cuda.so"
+if [ -f "$lib" ]; then
+    g++ -std=c++17 -O2 -I "$here/../include/ort_shim" -I "$ref/cpp" -I "$nl" \
+        "$ref/cpp/helper.cpp" "$ref/cpp/example_onnx.cpp" -o "$here/_ref/example_onnx_stc" \
+        -L "$here/../supertonic_b200" -lsupertonic_cuda -Wl,-rpath,'$ORIGIN/../../supertonic_b200'
+    echo "built $here/_ref/example_onnx_stc"
+fi
