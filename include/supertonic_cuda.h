@@ -169,6 +169,13 @@ int stc_set_profile(stc_handle* h, int level);   /* 0 off, 1 stage events, 2 + p
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]);
 int stc_last_stage_ms(const stc_handle* h, float out[5]);
 
+/* Tuning / self-check of the tcgen05 GEMM: out[M,N] = epi(A[M,K] W[K,N]) on seeded random data with a forced tile width
+ * `bn` (64/128/256; 0 = the library's own choice) and cluster shape cm x cn; epilogue 0 = bias, 1 = bias+GELU -> split
+ * bf16 operand, 2 = bias, layer-scale, residual (in place), row mask. Returns the mean device time of `iters` back-to-back
+ * launches (L2-warm) and the max-abs difference to the CUDA-core fp32 GEMM of the same operands. */
+int stc_debug_gemm(stc_handle* h, int M, int N, int K, int bn, int cm, int cn, int epilogue, int iters,
+                   float* ms_per_iter, float* max_abs_err);
+
 #ifdef __cplusplus
 }
 #endif

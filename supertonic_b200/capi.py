@@ -57,6 +57,7 @@ _SIGS = {
     "stc_set_profile": (_i, [_vp, _i]),
     "stc_last_stage_ms": (_i, [_vp, _vp]),
     "stc_kernel_profile": (_i, [_vp, _i, _vp]),
+    "stc_debug_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _pf, _pf]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here == header and library out of sync
@@ -308,6 +309,12 @@ class Engine:
             lib.stc_kernel_profile(self._h, cls, _ptr(out))
             res[name] = dict(ms=out[0], flops=out[1], bytes=out[2], launches=int(out[3]))
         return res
+
+    def debug_gemm(self, M, N, K, bn=0, cm=1, cn=1, epilogue=0, iters=20):
+        """One tcgen05 GEMM with a forced launch configuration -> (microseconds per launch, max-abs error vs fp32 CUDA cores)."""
+        ms, err = C.c_float(0), C.c_float(0)
+        self._chk(lib.stc_debug_gemm(self._h, M, N, K, bn, cm, cn, epilogue, iters, C.byref(ms), C.byref(err)))
+        return ms.value * 1000.0, err.value
 
     def stage_ms(self):
         out = np.zeros(5, np.float32)

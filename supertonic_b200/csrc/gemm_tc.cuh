@@ -9,13 +9,22 @@
 // full surrogate at 20 Euler steps: max-abs latent error 1e-5 vs 9e-4 for single-pass TF32 and 7e-3 for plain
 // bf16 (DESIGN.md "precision"); the north-star bound is 1e-3.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (persistent over 128 x BN output tiles, 320 threads, one CTA per SM):
 //   warp 0   : TMA producer   — cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles, STAGES-deep mbarrier ring
 //   warp 1   : MMA issuer     — one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16);
 //                               tcgen05.commit releases smem stages and finally signals the accumulator barrier
-//   warps 2-5: epilogue       — tcgen05.ld 32x32b.x32 (lane = row, 32 columns per load), fused
-//                               bias / GELU(erf) / layer-scale / residual / mask / Euler update, then
-//                               fp32 or split-bf16 stores.
+//   warps 2-9: epilogue       — tcgen05.ld 32x32b.x16 (lane = row) -> per-warp smem staging -> re-read with
+//                               lanes along the row, so that residual reads and output stores are coalesced;
+//                               fused bias / GELU(erf) / layer-scale / residual / mask / Euler update;
+//                               fp32 or split-bf16 stores. Two TMEM accumulator buffers: the epilogue of tile i
+//                               overlaps the MMAs of tile i+1.
+//
+// Operand traffic: the kernel is bound by L2 -> shared-memory operand bytes, not by the tensor pipe (measured:
+// profiles/r1b_*): a 128 x BN tile re-reads its A rows for every N tile and its W rows for every M tile. CTAs are
+// therefore launched as thread-block clusters of CM x CN tiles: the A tile of a cluster row is loaded once and
+// TMA-multicast to the CN CTAs that share it (each issues 1/CN of the rows), the W tile of a cluster column once for
+// its CM CTAs. A stage is released to the producers of every CTA that multicasts into it by a multicast
+// tcgen05.commit.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,14 +41,19 @@ constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_CHUNK = 16;                  // accumulator columns moved TMEM -> smem -> global per step
+constexpr int EPI_PITCH = EPI_CHUNK + 4;       // floats per staged row: 16-byte aligned, conflict-free for v4 accesses
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
 
 template <int BN> struct Tile {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int W_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;        // two accumulator buffers (BN in {64,128} -> power of two)
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                       // mbarriers + TMEM slot
+    static constexpr int EPI_OFF = BAR_OFF + 256;                              // epilogue staging
+    static constexpr int SMEM_BYTES = EPI_OFF + EPI_BYTES + 1024 /*align slack*/;
+    static constexpr int TMEM_COLS = 2 * BN;        // two accumulator buffers (BN in {64,128,256} -> power of two)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -139,86 +153,63 @@ struct Params {
     __nv_bfloat16* out_lo;
     int ldo;
     int split;
+    int cm, cn;                     // cluster shape in tiles (cm * cn CTAs per cluster)
 };
 
-// Fused epilogue for 32 consecutive columns of one row held in registers.
-template <bool kFull>
-STC_DEVINL void epilogue_store(const Params& p, float (&v)[32], int row, int col0, float mk) {
-    const float* resid = static_cast<const float*>(p.ep.resid);
-    const size_t o = (size_t)row * p.ldo + col0;
-    if (kFull) {
-        if (p.ep.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-        }
-        if (p.ep.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-        }
-        if (p.ep.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 s = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col0 + j));
-                v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
-            }
-        }
-        if (resid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 s = *reinterpret_cast<const float4*>(resid + o + j);
-                v[j] += s.x; v[j + 1] += s.y; v[j + 2] += s.z; v[j + 3] += s.w;
-            }
-        }
-        if (p.ep.mask) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= mk;
-        }
-        if (p.split) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * t]), h1 = __float2bfloat16_rn(v[j + 2 * t + 1]);
-                    __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * t] - __bfloat162float(h0));
-                    __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * t + 1] - __bfloat162float(h1));
-                    hi[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                *reinterpret_cast<uint4*>(p.out_hi + o + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(p.out_lo + o + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(p.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-    } else {
-        // ragged N edge: scalar path (static indexing keeps v[] in registers)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-                float x = v[j];
-                if (p.ep.bias) x += p.ep.bias[col0 + j];
-                if (p.ep.gelu) x = gelu_erf_fast(x);
-                if (p.ep.scale) x *= p.ep.scale[col0 + j];
-                if (resid) x += resid[o + j];
-                if (p.ep.mask) x *= mk;
-                if (p.split) {
-                    __nv_bfloat16 h = __float2bfloat16_rn(x);
-                    p.out_hi[o + j] = h;
-                    p.out_lo[o + j] = __float2bfloat16_rn(x - __bfloat162float(h));
-                } else p.out_f32[o + j] = x;
-            }
-        }
-    }
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with MUFU reciprocal / exp2: ~14 instructions against ~40 for
+// erff() + IEEE division. The GELU is then (x * (erf(x/sqrt2) + 1)) * 0.5 as in the graphs.
+STC_DEVINL float gelu_erf_mufu(float x) {
+    const float z = fabsf(x) * 0.70710678f;
+    float t; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    return (x * (copysignf(erf_abs, x) + 1.0f)) * 0.5f;
 }
 
-// Persistent over output tiles (tile = blockIdx.x + i*gridDim.x, n fastest). Two TMEM accumulator buffers:
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// v (fp32 x2) -> packed bf16x2 hi and lo with v ~= hi + lo
+STC_DEVINL void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));            // upper half <- first source
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+STC_DEVINL void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+STC_DEVINL void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+STC_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+STC_DEVINL uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+STC_DEVINL uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+STC_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+STC_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Tile coordinates of this CTA for cluster-tile `ct` (n fastest, so that concurrently running clusters share A rows in L2).
+struct TileIter {
+    int ctn, cm, cn, im, in;
+    STC_DEVINL void coords(int ct, int& mt, int& nt) const { mt = (ct / ctn) * cm + im; nt = (ct % ctn) * cn + in; }
+};
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -227,58 +218,82 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     using T = Tile<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + T::STAGES * T::STAGE_BYTES;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));           // (same offset in every CTA of the cluster)
+    const uint32_t bar_base = smem_base + T::BAR_OFF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (T::STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * T::STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * T::STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * T::STAGES + 4);
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T::STAGES * T::STAGE_BYTES + 8 * (2 * T::STAGES + 4));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T::BAR_OFF + 8 * (2 * T::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cm = p.cm, cn = p.cn, csize = cm * cn;
+    const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
     const int num_kb = (p.K + BK - 1) / BK;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.M + BM - 1) / BM;
-    const int num_tiles = n_tiles * m_tiles;
+    TileIter ti{(n_tiles + cn - 1) / cn, cm, cn, crank / cn, crank % cn};
+    const int num_ct = ((m_tiles + cm - 1) / cm) * ti.ctn;
+    const int ct0 = csize > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int ct_step = csize > 1 ? (int)cluster_count_x() : (int)gridDim.x;
+    // CTAs this one exchanges operand slices with: its cluster row (same A tile) and column (same W tile)
+    uint16_t row_mask = 0, col_mask = 0;
+    for (int j = 0; j < cn; ++j) row_mask |= (uint16_t)(1u << (ti.im * cn + j));
+    for (int j = 0; j < cm; ++j) col_mask |= (uint16_t)(1u << (j * cn + ti.in));
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
-        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)(cm + cn - 1)); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, T::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
+            const int a_rows = BM / cn, w_rows = BN / cm;                    // rows of the slice this CTA fetches
+            const uint32_t a_off = (uint32_t)(ti.in * a_rows * BK * 2), w_off = (uint32_t)(ti.im * w_rows * BK * 2);
             uint32_t kbc = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            for (int ct = ct0; ct < num_ct; ct += ct_step) {
+                int mt, nt; ti.coords(ct, mt, nt);
+                const int m0 = mt * BM + ti.in * a_rows, n0 = nt * BN + ti.im * w_rows;
                 for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
                     const int s = kbc % T::STAGES;
                     const uint32_t ph = (kbc / T::STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_wait(empty_bar(s), ph ^ 1);                         // freed by every CTA that receives these slices
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
-                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
-                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
-                    tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);             // own slices + the peers' multicasts
+                    if (cn > 1) {
+                        tma_load_2d_mc(st + a_off, &map_a_hi, full_bar(s), kb * BK, m0, row_mask);
+                        tma_load_2d_mc(st + T::A_BYTES + a_off, &map_a_lo, full_bar(s), kb * BK, m0, row_mask);
+                    } else {
+                        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                        tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
+                    }
+                    if (cm > 1) {
+                        tma_load_2d_mc(st + 2 * T::A_BYTES + w_off, &map_w_hi, full_bar(s), kb * BK, n0, col_mask);
+                        tma_load_2d_mc(st + 2 * T::A_BYTES + T::W_BYTES + w_off, &map_w_lo, full_bar(s), kb * BK, n0, col_mask);
+                    } else {
+                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
+                        tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        const uint16_t free_mask = row_mask | col_mask;
         uint32_t kbc = 0, it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
             const uint32_t ab = it & 1, aph = (it >> 1) & 1;
             mbar_wait(tempty_bar(ab), aph ^ 1);                 // epilogue has drained this accumulator buffer
             tc_fence_after();
@@ -299,7 +314,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
                         umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
                     }
-                    umma_commit(empty_bar(s));                          // frees the smem stage when these MMAs retire
+                    if (csize > 1) umma_commit_mc(empty_bar(s), free_mask);          // frees the stage in every sender
+                    else umma_commit(empty_bar(s));
                     if (kb == num_kb - 1) umma_commit(tfull_bar(ab));   // accumulator complete
                 }
                 __syncwarp();
@@ -309,28 +325,59 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp-2)/4 =====
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr int COLS_PER_WARP = BN / 2;
+        float* stg = reinterpret_cast<float*>(smem_gen + T::EPI_OFF) + (warp - 2) * 32 * EPI_PITCH;
+        const int sub = lane >> 2, cq = (lane & 3) * 4;         // phase 2: 8 rows x 4 float4 per warp instruction
+        const float* resid = static_cast<const float*>(p.ep.resid);
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
+            int mt, nt; ti.coords(ct, mt, nt);
+            const int m0 = mt * BM + q * 32, n0 = nt * BN + half * COLS_PER_WARP;
             const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < p.M;
-            const float mk = (p.ep.mask && row_ok) ? __ldg(p.ep.mask + row) : 1.f;
+            float mk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = m0 + i * 8 + sub;
+                mk[i] = (p.ep.mask && row < p.M) ? __ldg(p.ep.mask + row) : 1.f;
+            }
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WARP; c += EPI_CHUNK) {
+                uint32_t r[16];
+                __syncwarp();                                   // tcgen05.ld is .sync.aligned; staging of the previous chunk is consumed
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + half * COLS_PER_WARP + c), r);
 #pragma unroll
-            for (int c = 0; c < COLS_PER_WARP; c += 32) {
-                const int c0 = half * COLS_PER_WARP + c;
-                uint32_t r[32];
-                __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), r);
-                const int col0 = n0 + c0;
-                if (row_ok && col0 < p.N) {
-                    float v[32];
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                __syncwarp();
+                const int col = n0 + c + cq;
+                if (col < p.N) {                                // N % 4 == 0 is checked on the host
+                    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), scale = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (p.ep.bias) bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
+                    if (p.ep.scale) scale = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (col0 + 32 <= p.N) epilogue_store<true>(p, v, row, col0, mk);
-                    else epilogue_store<false>(p, v, row, col0, mk);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = i * 8 + sub, row = m0 + rl;
+                        if (row >= p.M) continue;
+                        float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq);
+                        v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                        if (p.ep.gelu) { v.x = gelu_erf_mufu(v.x); v.y = gelu_erf_mufu(v.y); v.z = gelu_erf_mufu(v.z); v.w = gelu_erf_mufu(v.w); }
+                        if (p.ep.scale) { v.x *= scale.x; v.y *= scale.y; v.z *= scale.z; v.w *= scale.w; }
+                        const size_t o = (size_t)row * p.ldo + col;
+                        if (resid) {
+                            const float4 s = *reinterpret_cast<const float4*>(resid + o);
+                            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+                        }
+                        if (p.ep.mask) { v.x *= mk[i]; v.y *= mk[i]; v.z *= mk[i]; v.w *= mk[i]; }
+                        if (p.split) {
+                            uint2 hi, lo;
+                            split_pair(v.x, v.y, hi.x, lo.x); split_pair(v.z, v.w, hi.y, lo.y);
+                            *reinterpret_cast<uint2*>(p.out_hi + o) = hi;
+                            *reinterpret_cast<uint2*>(p.out_lo + o) = lo;
+                        } else {
+                            *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -340,6 +387,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, T::TMEM_COLS);
 }

@@ -118,7 +118,10 @@ struct Handle {
     ConvNeXt load_convnext(const OnnxFile& f, const json& l, bool tc);
     Attention load_attention(const OnnxFile& f, const json& l, bool tc);
     CUtensorMap encode_map(const void* ptr, int rows, int K, int box_rows);
-    const CUtensorMap& act_map(const void* ptr, int rows, int K);
+    const CUtensorMap& tmap(const void* ptr, int rows, int K, int box_rows);
+    struct GemmCfg { int bn, cm, cn; };
+    GemmCfg pick_gemm(int M, int N, int K) const;
+    GemmCfg force_cfg{0, 0, 0};      // debug / sweep override (bn == 0: heuristic)
 
     // ---- workspace helpers
     template <typename T> T* ws(size_t n) { return static_cast<T*>(arena.alloc(n * sizeof(T))); }
@@ -231,12 +234,12 @@ CUtensorMap Handle::encode_map(const void* ptr, int rows, int K, int box_rows) {
     return m;
 }
 
-const CUtensorMap& Handle::act_map(const void* ptr, int rows, int K) {
-    auto key = std::make_tuple(ptr, rows, K, tc::BM);
+const CUtensorMap& Handle::tmap(const void* ptr, int rows, int K, int box_rows) {
+    auto key = std::make_tuple(ptr, rows, K, box_rows);
     auto it = map_cache.find(key);
     if (it != map_cache.end()) return it->second;
-    if (map_cache.size() > 8192) map_cache.clear();
-    return map_cache.emplace(key, encode_map(ptr, rows, K, tc::BM)).first->second;
+    if (map_cache.size() > 16384) map_cache.clear();
+    return map_cache.emplace(key, encode_map(ptr, rows, K, box_rows)).first->second;
 }
 
 static inline uint16_t bf16_bits_rn(float v) {
@@ -264,10 +267,8 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
         STC_CUDA(cudaMalloc((void**)&l.w_lo, lo.size() * 2)); owned.push_back(l.w_lo);
         STC_CUDA(cudaMemcpy(l.w_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
         STC_CUDA(cudaMemcpy(l.w_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
-        l.map_hi = encode_map(l.w_hi, N, K, 128);
-        l.map_lo = encode_map(l.w_lo, N, K, 128);
-        l.map64_hi = encode_map(l.w_hi, N, K, 64);
-        l.map64_lo = encode_map(l.w_lo, N, K, 64);
+        if (K % 8) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs K % 8 == 0, got " + std::to_string(K));
+        if (N % 4) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs N % 4 == 0, got " + std::to_string(N));
         l.has_maps = true;
     }
     return l;
@@ -487,17 +488,45 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
     if (out_f32) { p.out_f32 = out_f32; p.split = 0; } else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
     if (dry) return;
-    CUtensorMap mh = act_map(a.hi, M, w.K);
-    CUtensorMap ml = act_map(a.lo, M, w.K);
-    // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
-    int tiles128 = cdiv(w.N, 128) * cdiv(M, tc::BM);
-    bool bn64 = tiles128 < num_sms && w.N > 64;
-    int tiles = bn64 ? cdiv(w.N, 64) * cdiv(M, tc::BM) : tiles128;
-    dim3 grid(std::min(tiles, num_sms));
+    const GemmCfg c = force_cfg.bn ? force_cfg : pick_gemm(M, w.N, w.K);
+    p.cm = c.cm; p.cn = c.cn;
+    const int csize = c.cm * c.cn;
+    const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM / c.cn), mal = tmap(a.lo, M, w.K, tc::BM / c.cn);
+    const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, c.bn / c.cm), mwl = tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
+    const int m_tiles = cdiv(M, tc::BM), n_tiles = cdiv(w.N, c.bn);
+    const int cluster_tiles = cdiv(m_tiles, c.cm) * cdiv(n_tiles, c.cn);
+    const int clusters = std::max(1, std::min(cluster_tiles, num_sms / csize));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * csize); cfg.blockDim = dim3(tc::NUM_THREADS); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = csize > 1 ? 1 : 0;
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
-    if (bn64) STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<64>), grid, tc::NUM_THREADS, tc::Tile<64>::SMEM_BYTES, mh, ml, w.map64_hi, w.map64_lo, p);
-    else STC_LAUNCH(this, (tc::gemm_bf16x3_kernel<128>), grid, tc::NUM_THREADS, tc::Tile<128>::SMEM_BYTES, mh, ml, w.map_hi, w.map_lo, p);
+    cudaError_t e;
+    switch (c.bn) {
+        case 64: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64>, mah, mal, mwh, mwl, p); break;
+        case 128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128>, mah, mal, mwh, mwl, p); break;
+        case 256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256>, mah, mal, mwh, mwl, p); break;
+        default: throw StcError(STC_ERR_INVALID, "bad GEMM tile width");
+    }
+    if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(e));
+    ++launches;
     kprof_end();
+}
+
+// Tile width and cluster shape per problem (tuned with stc_debug_gemm sweeps on B200, profiles/): the kernel is bound by
+// L2 -> smem operand bytes, so prefer the shape that minimises (A bytes / cn + W bytes / cm) per tile while still giving
+// every SM a tile.
+Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
+    // Measured (tools/gemm_sweep.py, profiles/r1c_gemm_sweep.txt): TMA multicast inside a cluster does not shorten any of
+    // the hot shapes — the limit is bytes delivered INTO each SM, which multicast does not reduce — so clusters stay off.
+    // Wide tiles win once every SM has many tiles (fewer operand bytes per flop); narrow ones when tiles are scarce.
+    const int tiles128 = cdiv(M, tc::BM) * cdiv(N, 128);
+    int bn = 64;
+    if (tiles128 >= 16 * num_sms && N % 256 == 0) bn = 256;
+    else if (tiles128 >= num_sms && K >= 512 && N > 64) bn = 128;
+    return GemmCfg{bn, 1, 1};
 }
 
 template <typename T>
@@ -917,6 +946,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
             if (!fn || qr != cudaDriverEntryPointSuccess) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
             hd->encode = (EncodeTiledFn)fn;
+            STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
         }
@@ -1294,6 +1324,100 @@ int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, con
                                  int64_t wav_cap, int64_t* wav_offsets_out, float* duration_dev) {
     return synth_impl(h, 2, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
                       wav_dev, wav_cap, duration_dev, nullptr, nullptr, nullptr, wav_offsets_out);
+}
+
+// ---- debug / tuning: one tcgen05 GEMM of a given shape and launch configuration, timed and checked -----------------
+__global__ void debug_fill_kernel(float* __restrict__ p, size_t n, uint64_t seed, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float u1 = (stc::mix32(seed + 2 * i) + 1.0f) * (1.0f / 4294967808.0f), u2 = stc::mix32(seed + 2 * i + 1) * (1.0f / 4294967296.0f);
+    p[i] = scale * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__global__ void debug_maxdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i] - b[i]));
+    m = stc::warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));     // non-negative floats order like ints
+}
+__global__ void debug_join_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
+int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, int epilogue, int iters, float* ms_per_iter,
+                   float* max_abs_err) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (!h->tc_mode()) throw StcError(STC_ERR_UNSUPPORTED, "stc_debug_gemm needs the tcgen05 precision mode");
+        if (M <= 0 || N <= 0 || K <= 0 || iters <= 0 || epilogue < 0 || epilogue > 2) throw StcError(STC_ERR_INVALID, "stc_debug_gemm: bad argument");
+        if (bn && (bn != 64 && bn != 128 && bn != 256)) throw StcError(STC_ERR_INVALID, "bn must be 0, 64, 128 or 256");
+        if (bn && (cm < 1 || cn < 1 || cm * cn > 8 || (tc::BM / cn) % 8 || (bn / cm) % 8)) throw StcError(STC_ERR_INVALID, "bad cluster shape");
+        std::vector<float> wk((size_t)K * N), bias(N);
+        uint64_t z = 12345;
+        auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
+        for (auto& v : wk) v = rnd() / std::sqrt((float)K) * 1.7f;
+        for (auto& v : bias) v = rnd() * 0.1f;
+        Linear lin = h->make_linear_host(wk, bias, K, N, true);
+        auto body = [&]() {
+            h->arena.reset(); h->h_stage_off = 0;
+            float* A = h->ws<float>((size_t)M * K); float* X = h->ws<float>((size_t)M * N); float* Xr = h->ws<float>((size_t)M * N);
+            float* gamma = h->ws<float>(N); float* mask = h->ws<float>(M);
+            float* out = h->ws<float>((size_t)M * N); float* ref = h->ws<float>((size_t)M * N); float* err = h->ws<float>(1);
+            Act a = h->ws_act((size_t)M * K), o = h->ws_act((size_t)M * N);
+            if (h->dry) return;
+            debug_fill_kernel<<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, (size_t)M * K, 1, 1.0f);
+            debug_fill_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(X, (size_t)M * N, 2, 1.0f);
+            debug_fill_kernel<<<cdiv(N, 256), 256, 0, h->stream>>>(gamma, N, 3, 0.1f);
+            fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
+            fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 2, 0.0f, (size_t)std::min(M - M / 2, 3));
+            fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
+            h->to_act(A, (size_t)M * K, a);
+            Epilogue ep;
+            if (epilogue == 1) ep.gelu = 1;
+            if (epilogue == 2) { ep.scale = gamma; ep.mask = mask; }
+            // reference: CUDA-core fp32 GEMM, same epilogue
+            Epilogue er = ep; er.bias = lin.bias;
+            STC_CUDA(cudaMemcpyAsync(Xr, X, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
+            if (epilogue == 2) er.resid = Xr;
+            h->gemm_simt<float>(A, K, M, lin, er, epilogue == 2 ? Xr : ref, N);
+            const float* refp = epilogue == 2 ? Xr : ref;
+            h->force_cfg = Handle::GemmCfg{bn, cm, cn};
+            cudaEvent_t e0 = h->pool_event(), e1 = h->pool_event();
+            auto one = [&](bool checked) {
+                if (epilogue == 2) {
+                    if (checked) STC_CUDA(cudaMemcpyAsync(out, X, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
+                    Epilogue e2 = ep; e2.resid = out;
+                    h->gemm(a, M, lin, e2, out, nullptr, N);
+                } else if (epilogue == 1) h->gemm(a, M, lin, ep, nullptr, &o, N);
+                else h->gemm(a, M, lin, ep, out, nullptr, N);
+            };
+            one(true);
+            if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
+            debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(out, refp, (size_t)M * N, err);
+            // timed: `iters` launches replayed from a CUDA graph (as in production), so the host is not in the loop
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            STC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            for (int it = 0; it < iters; ++it) one(false);
+            STC_CUDA(cudaStreamEndCapture(h->stream, &graph));
+            STC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            STC_CUDA(cudaGraphLaunch(exec, h->stream));        // warm
+            cudaEventRecord(e0, h->stream);
+            STC_CUDA(cudaGraphLaunch(exec, h->stream));
+            cudaEventRecord(e1, h->stream);
+            h->force_cfg = Handle::GemmCfg{0, 0, 0};
+            STC_CUDA(cudaStreamSynchronize(h->stream));
+            h->check_launch("stc_debug_gemm");
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+            if (ms_per_iter) *ms_per_iter = ms / iters;
+            if (max_abs_err) STC_CUDA(cudaMemcpy(max_abs_err, err, 4, cudaMemcpyDeviceToHost));
+            h->ev_next = 0;
+        };
+        h->force_cfg = Handle::GemmCfg{0, 0, 0};
+        h->ensure_ws(body);
+        body();
+        // the temporary weights stay owned by the handle until it is destroyed (debug entry point: acceptable)
+    })
 }
 
 int stc_text_to_ids(stc_handle* sh, const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,

@@ -45,9 +45,7 @@ struct Linear {
     float* bias = nullptr;            // [N]
     __nv_bfloat16* w_hi = nullptr;    // [N,K] K-major split pair (tensor-core B operand)
     __nv_bfloat16* w_lo = nullptr;
-    CUtensorMap map_hi{}, map_lo{};        // box rows 128
-    CUtensorMap map64_hi{}, map64_lo{};    // box rows 64
-    bool has_maps = false;
+    bool has_maps = false;            // w_hi / w_lo present (tensor maps are cached per box shape in the handle)
 };
 
 struct ConvNeXt {
