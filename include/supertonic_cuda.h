@@ -134,6 +134,14 @@ int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, con
                                  int total_step, float speed, uint64_t seed, float* wav_dev, int64_t wav_cap,
                                  int64_t* wav_offsets_out, float* duration_dev);
 
+/* ---- page-locked host buffers (optional) ------------------------------------------------------ */
+
+/* Any host pointer is accepted by the entry points above; buffers obtained here are page-locked, so the device->host copy
+ * of the waveform (the bulk of the traffic: 4 bytes x 44100 per audio-second) runs at PCIe speed instead of being staged
+ * through the driver's bounce buffers. Needs a CUDA device. */
+int stc_pinned_alloc(size_t bytes, void** out);
+void stc_pinned_free(void* p);
+
 /* ---- host front-end (kept on the host, semantics of the C++ reference) ----------------------- */
 
 /* UnicodeProcessor::call (cpp/helper.cpp:355-390) for n texts. Two-pass: call with text_ids == NULL to

@@ -46,6 +46,8 @@ _SIGS = {
     "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_synthesize_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
+    "stc_pinned_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "stc_pinned_free": (None, [_vp]),
     "stc_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
     "stc_frontend_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "stc_frontend_close": (None, [_vp]),
@@ -155,10 +157,33 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for arr, ptr in getattr(self, "_pinned", {}).values():
+                lib.stc_pinned_free(ptr)
+            self._pinned = {}
             lib.stc_destroy(self._h)
             self._h = None
 
     __del__ = close
+
+    def pinned(self, name: str, count: int, dtype) -> np.ndarray:
+        """A page-locked host array of at least `count` elements, owned by the engine and reused between calls
+        (contents are overwritten by the next call that asks for the same `name`)."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        dt = np.dtype(dtype)
+        cur = self._pinned.get(name)
+        if cur is None or cur[0].size < count or cur[0].dtype != dt:
+            if cur is not None:
+                lib.stc_pinned_free(cur[1])
+            n = int(count * 1.25) + 1024
+            ptr = _vp()
+            rc = lib.stc_pinned_alloc(n * dt.itemsize, C.byref(ptr))
+            if rc != STC_OK:
+                raise StcError(rc, lib.stc_last_error(None).decode())
+            buf = (C.c_char * (n * dt.itemsize)).from_address(ptr.value)
+            cur = (np.frombuffer(buf, dtype=dt, count=n), ptr)
+            self._pinned[name] = cur
+        return cur[0][:count]
 
     def _chk(self, rc):
         if rc != STC_OK:
@@ -233,9 +258,11 @@ class Engine:
         return res
 
     def synthesize_packed(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
-                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False):
+                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, pinned: bool = False):
         """Throughput path: packed latent rows, no padded frames. Returns dict(wavs=[B trimmed arrays], duration[B],
-        wav_lengths[B], frames[B], latent? (list of [frames_b, D] arrays))."""
+        wav_lengths[B], frames[B], latent? (list of [frames_b, D] arrays)).
+        pinned=True: the waveforms are VIEWS into an engine-owned page-locked buffer (D2H at PCIe speed, no copy);
+        they stay valid until the next pinned call on this engine."""
         ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
         sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
         B, T = ids.shape
@@ -246,7 +273,7 @@ class Engine:
         cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs
         dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
         for _ in range(2):
-            wav = np.empty((cap,), np.float32)
+            wav = self.pinned("wav_packed", cap, np.float32) if pinned else np.empty((cap,), np.float32)
             lat = np.empty((cap // cs, D), np.float32) if want_latent else None
             rc = lib.stc_synthesize_packed(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
                                            _ptr(nz), nld, seed, _ptr(wav), cap, _ptr(off), _ptr(dur), _ptr(wl), _ptr(lat))

@@ -157,6 +157,94 @@ dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
     }
 }
 
+// Vectorised float variant for C in {128, 256, 512}: lane owns CPL CONSECUTIVE channels (float4 loads of x and of the
+// tap-major weights wT[K][C], 8/16-byte operand stores), one warp per row, 8 rows per block.
+STC_DEVINL void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+template <int CPL> STC_DEVINL void store_row_vec(const OutSplit& o, size_t i, const float (&y)[CPL]) {
+    uint32_t hi[CPL / 2], lo[CPL / 2];
+#pragma unroll
+    for (int j = 0; j < CPL / 2; ++j) split2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+    if constexpr (CPL == 4) {
+        *reinterpret_cast<uint2*>(o.hi + i) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(o.lo + i) = make_uint2(lo[0], lo[1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPL / 8; ++j) {
+            *reinterpret_cast<uint4*>(o.hi + i + 8 * j) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(o.lo + i + 8 * j) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+    }
+}
+template <int CPL> STC_DEVINL void store_row_vec(const OutPlain<float>& o, size_t i, const float (&y)[CPL]) {
+#pragma unroll
+    for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(o.p + i + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+}
+
+template <int CPL, typename Out>
+__global__ void __launch_bounds__(256)
+dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
+                     const float* __restrict__ g, const float* __restrict__ beta, Out out,
+                     int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
+    constexpr int C = CPL * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const int c0 = lane * CPL;
+    float y[CPL];
+    if (K == 0) {
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * C + c0 + j);
+            y[j] = v.x; y[j + 1] = v.y; y[j + 2] = v.z; y[j + 3] = v.w;
+        }
+    } else {
+        const int b = find_seq(off, B, row);
+        if (b < 0) {                                   // bucket padding row: keep it finite
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) y[j] = 0.f;
+            store_row_vec<CPL>(out, (size_t)row * C + c0, y);
+            return;
+        }
+        const int base = __ldg(off + b), n = row - base, N = __ldg(off + b + 1) - base;
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(wb + c0 + j));
+            y[j] = v.x; y[j + 1] = v.y; y[j + 2] = v.z; y[j + 3] = v.w;
+        }
+        for (int k = 0; k < K; ++k) {
+            const int nn = n + k * dil - pad_left;
+            if (nn < 0 || nn >= N) continue;
+            const float* xr = x + ((size_t)base + nn) * C + c0;
+            const float* wr = wT + (size_t)k * C + c0;
+#pragma unroll
+            for (int j = 0; j < CPL; j += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + j);
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+                y[j] += wv.x * xv.x; y[j + 1] += wv.y * xv.y; y[j + 2] += wv.z * xv.z; y[j + 3] += wv.w * xv.w;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) s += y[j];
+    const float mean = warp_sum<float>(s) / (float)C;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { y[j] -= mean; v += y[j] * y[j]; }
+    const float den = sqrtf(warp_sum<float>(v) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < CPL; j += 4) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c0 + j)), bv = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
+        y[j] = y[j] / den * gv.x + bv.x; y[j + 1] = y[j + 1] / den * gv.y + bv.y;
+        y[j + 2] = y[j + 2] / den * gv.z + bv.z; y[j + 3] = y[j + 3] / den * gv.w + bv.w;
+    }
+    store_row_vec<CPL>(out, (size_t)row * C + c0, y);
+}
+
 // ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
 template <typename Out>
 __global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {

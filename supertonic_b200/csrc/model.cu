@@ -289,6 +289,12 @@ ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, bool tc) {
     int span = c.dil * (c.K - 1);
     c.pad_left = causal ? span : span / 2;
     c.dw_w = W(f, p + ".dw.weight", (size_t)c.C * c.K);
+    {   // tap-major copy for the vectorised kernel
+        const float* w = get_tensor(f, p + ".dw.weight", (size_t)c.C * c.K).f32();
+        std::vector<float> wt((size_t)c.C * c.K);
+        for (int ch = 0; ch < c.C; ++ch) for (int k = 0; k < c.K; ++k) wt[(size_t)k * c.C + ch] = w[(size_t)ch * c.K + k];
+        c.dw_wt = upload_f32(wt.data(), wt.size());
+    }
     c.dw_b = W(f, p + ".dw.bias", c.C);
     c.ln_g = W(f, p + ".ln.weight", c.C);
     c.ln_b = W(f, p + ".ln.bias", c.C);
@@ -442,6 +448,15 @@ template <typename T, typename Out>
 static void launch_dwln(Handle* h, int C, const T* x, const float* w, const float* wb, const float* g, const float* b, Out out,
                         int rows, const int* off, int B, int K, int dil, int pad, float eps) {
     dim3 grid(cdiv(rows, 8)), block(256);
+    if constexpr (std::is_same<T, float>::value) {
+        // w is the tap-major transpose wT[K][C] for these widths (ConvNeXt::dw_wt)
+        switch (C / 32) {
+            case 4: STC_LAUNCH(h, (dwconv_ln_vec_kernel<4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
+            case 8: STC_LAUNCH(h, (dwconv_ln_vec_kernel<8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
+            case 16: STC_LAUNCH(h, (dwconv_ln_vec_kernel<16, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
+            default: break;
+        }
+    }
     switch (C / 32) {
         case 1: STC_LAUNCH(h, (dwconv_ln_kernel<T, 1, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
         case 2: STC_LAUNCH(h, (dwconv_ln_kernel<T, 2, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
@@ -455,7 +470,8 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
 template <typename T>
 void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const float* b, int C, const Seq& seq, float eps,
                        T* out_plain, const Act* out_act) {
-    const float* w = cn ? cn->dw_w : nullptr; const float* wb = cn ? cn->dw_b : nullptr;
+    const bool vec = std::is_same<T, float>::value && (C == 128 || C == 256 || C == 512);
+    const float* w = cn ? (vec ? cn->dw_wt : cn->dw_w) : nullptr; const float* wb = cn ? cn->dw_b : nullptr;
     int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0, rows = seq.rows;
     if constexpr (std::is_same<T, float>::value) {
         if (out_act && out_act->hi) {
@@ -1419,6 +1435,15 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         // the temporary weights stay owned by the handle until it is destroyed (debug entry point: acceptable)
     })
 }
+
+int stc_pinned_alloc(size_t bytes, void** out) {
+    STC_TRY(nullptr, {
+        if (!out || !bytes) throw StcError(STC_ERR_INVALID, "stc_pinned_alloc: bad argument");
+        *out = nullptr;
+        STC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    })
+}
+void stc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int stc_text_to_ids(stc_handle* sh, const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,
                     int64_t T_cap, int64_t* T_out) {

@@ -51,7 +51,7 @@ struct Linear {
 struct ConvNeXt {
     int C, H, K, dil, pad_left;
     bool masked;
-    float *dw_w, *dw_b, *ln_g, *ln_b, *gamma;
+    float *dw_w, *dw_wt, *dw_b, *ln_g, *ln_b, *gamma;     // dw_w [C][K] as in the graph, dw_wt [K][C]
     Linear pw1, pw2;
 };
 

@@ -150,23 +150,26 @@ class TextToSpeech:
 
     # -- throughput path (north_star: "a request batch is length-bucketed")
     def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05,
-                        max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None):
+                        max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None, copy: bool = False):
         """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
         rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
         utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
-        (tests: batch-composition invariance)."""
+        (tests: batch-composition invariance). With a single group (n <= max_batch) and copy=False the waveforms are
+        views into the engine's page-locked result buffer, valid until the next call."""
         from .scheduler import length_buckets
         n = len(texts)
         ids, mask = self.engine.text_to_ids(texts, langs)
         lens = mask.reshape(n, -1).sum(1).astype(np.int64)
         out: List[Optional[Tuple[np.ndarray, float]]] = [None] * n
-        for grp in length_buckets(lens, max_batch, 1e9):
+        groups = length_buckets(lens, max_batch, 1e9)
+        views_ok = len(groups) == 1 and not copy
+        for grp in groups:
             g = np.asarray(grp)
             T = int(lens[g].max())
             r = self.engine.synthesize_packed(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed,
-                                              seed=seed, noise=None if noise is None else noise[g])
+                                              seed=seed, noise=None if noise is None else noise[g], pinned=True)
             for k, i in enumerate(grp):
-                out[i] = (r["wavs"][k], float(r["duration"][k]))
+                out[i] = (r["wavs"][k] if views_ok else r["wavs"][k].copy(), float(r["duration"][k]))
         return out
 
 
