@@ -245,6 +245,76 @@ dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, 
     store_row_vec<CPL>(out, (size_t)row * C + c0, y);
 }
 
+// Shared-memory tiled variant: a block owns R consecutive packed rows and stages the R + (K-1)*dil input rows its taps
+// touch ONCE (coalesced float4), instead of re-reading every tap row through L2 (7 x 57 MB per vocoder block before).
+// Lane owns the float4 chunks {lane + 32 j}: every shared/global access of a warp is one contiguous 512-byte run.
+template <int CPL, typename Out>
+__global__ void __launch_bounds__(256)
+dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
+                      const float* __restrict__ g, const float* __restrict__ beta, Out out,
+                      int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps, int R) {
+    constexpr int C = CPL * 32, V = CPL / 4;
+    extern __shared__ float4 tile4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * R;
+    const int span = (K - 1) * dil;
+    const int w0 = r0 - pad_left, wrows = R + span;               // staged window of packed rows [w0, w0 + wrows)
+    for (int i = threadIdx.x; i < wrows * (C / 4); i += blockDim.x) {
+        const int wr = i / (C / 4), gr = w0 + wr;
+        tile4[i] = (gr >= 0 && gr < rows) ? *reinterpret_cast<const float4*>(x + (size_t)gr * C + (i % (C / 4)) * 4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int rl = warp; rl < R; rl += (blockDim.x >> 5)) {
+        const int row = r0 + rl;
+        if (row >= rows) break;
+        float4 y[V];
+        const int b = find_seq(off, B, row);
+        if (b < 0) {                                   // bucket padding row: keep it finite
+#pragma unroll
+            for (int j = 0; j < V; ++j) y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int base = __ldg(off + b), n = row - base, N = __ldg(off + b + 1) - base;
+#pragma unroll
+            for (int j = 0; j < V; ++j) y[j] = __ldg(reinterpret_cast<const float4*>(wb) + lane + 32 * j);
+            for (int k = 0; k < K; ++k) {
+                const int nn = n + k * dil - pad_left;
+                if (nn < 0 || nn >= N) continue;
+                const float4* xr = tile4 + (size_t)(rl + k * dil) * (C / 4);
+                const float4* wr = reinterpret_cast<const float4*>(wT + (size_t)k * C);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float4 xv = xr[lane + 32 * j], wv = __ldg(wr + lane + 32 * j);
+                    y[j].x += wv.x * xv.x; y[j].y += wv.y * xv.y; y[j].z += wv.z * xv.z; y[j].w += wv.w * xv.w;
+                }
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) s += (y[j].x + y[j].y) + (y[j].z + y[j].w);
+            const float mean = warp_sum<float>(s) / (float)C;
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                y[j].x -= mean; y[j].y -= mean; y[j].z -= mean; y[j].w -= mean;
+                v += (y[j].x * y[j].x + y[j].y * y[j].y) + (y[j].z * y[j].z + y[j].w * y[j].w);
+            }
+            const float den = sqrtf(warp_sum<float>(v) / (float)C + eps);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * j);
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+                y[j].x = y[j].x / den * gv.x + bv.x; y[j].y = y[j].y / den * gv.y + bv.y;
+                y[j].z = y[j].z / den * gv.z + bv.z; y[j].w = y[j].w / den * gv.w + bv.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float t[4] = {y[j].x, y[j].y, y[j].z, y[j].w};
+            store_row_vec<4>(out, (size_t)row * C + 4 * (lane + 32 * j), t);
+        }
+    }
+}
+
 // ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
 template <typename Out>
 __global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {
@@ -264,16 +334,16 @@ struct Epilogue {
     int gelu = 0;
 };
 
-template <typename T, typename Out>
+template <typename T, typename Out, int BM = 64>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, Out out, int ldo,
                  int M, int N, int K, Epilogue ep) {
-    constexpr int BM = 64, BN = 64, BK = 16;
+    constexpr int BN = 64, BK = 16, TM = BM / 16;
     __shared__ T As[BK][BM + 1];
     __shared__ T Ws[BK][BN + 1];
-    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, 4x4 micro-tile
+    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, TM x 4 micro-tile
     int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    T acc[4][4] = {};
+    T acc[TM][4] = {};
     for (int k0 = 0; k0 < K; k0 += BK) {
         for (int i = threadIdx.x; i < BM * BK; i += 256) {
             int r = i / BK, c = i % BK;
@@ -288,11 +358,13 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, 
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            T a[4], w[4];
+            T a[TM], w[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) w[i] = Ws[k][tx * 4 + i];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * w[j];
         }
@@ -300,8 +372,8 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, 
     }
     const T* resid = static_cast<const T*>(ep.resid);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        int gm = m0 + ty * TM + i;
         if (gm >= M) continue;
         T mk = ep.mask ? (T)ep.mask[gm] : (T)1;
 #pragma unroll

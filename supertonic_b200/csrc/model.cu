@@ -12,6 +12,7 @@
 #include <nlohmann/json.hpp>
 
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 #include "model.cuh"
 #include "text_frontend.h"
 
@@ -49,9 +50,18 @@ struct GraphKey {
     }
 };
 
+// Keys / values of one attention layer, ready for the core: either fp32 [rows, C] (K already rotated; CUDA-core path) or the
+// tensor-core operands — K as split-bf16 [rows, C], V transposed per (sequence, head) to [B*heads*64, ldk] split-bf16.
+struct KV {
+    const float* K = nullptr; const float* V = nullptr;
+    __nv_bfloat16 *k_hi = nullptr, *k_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;
+    int ldk = 0;
+    bool tc = false;
+};
+
 struct VeCtx {
     Seq lat, text, style;             // latent frames (packed or rectangle), text tokens [B,T], style tokens [B,S]
-    std::vector<float*> Kc, Vc;       // per cross-attention layer, [B*Nk, C] fp32 (keys already rotated)
+    std::vector<KV> kv;               // per cross-attention layer: step-invariant, hoisted out of the Euler loop
 };
 
 struct Handle {
@@ -76,6 +86,7 @@ struct Handle {
     EncodeTiledFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> map_cache;
     bool use_graphs = true;
+    bool force_simt_attn = false;     // env STC_ATTN=simt: keep the CUDA-core attention core (cross-check)
     int profile = 0;          // 0 off, 1 stage events, 2 + per-kernel events for the GEMM / dwconv+LN classes
     struct KProf { double ms = 0, flops = 0, bytes = 0; uint64_t n = 0; };
     KProf kprof[3];           // 0 = tcgen05 GEMM, 1 = dwconv+LayerNorm, 2 = attention core
@@ -142,9 +153,12 @@ struct Handle {
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
-    void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const float* Kpre, const float* Vpre);
+    void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
+    bool attn_on_tc(const Attention& a, const Seq& ks) const;
+    KV make_kv(const Attention& a, const Act& ctx, const Seq& ks);      // result lives in the arena above the caller's mark
+    void attn_core_tc(const float* Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k);
     void rope(float* x, const float* freqs, const Seq& seq, int heads, int dh, int normalise);
     // sequence descriptors (offsets staged through pinned memory)
     int* stage_ints(const std::vector<int>& v);
@@ -450,6 +464,20 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
     dim3 grid(cdiv(rows, 8)), block(256);
     if constexpr (std::is_same<T, float>::value) {
         // w is the tap-major transpose wT[K][C] for these widths (ConvNeXt::dw_wt)
+        if (K > 0 && (C == 128 || C == 256 || C == 512)) {
+            // rows per block: as many as keep >= 2 blocks per SM in flight (shared-memory tile = (R + span) rows)
+            int R = 32;
+            while (R > 8 && (int)cdiv(rows, R) < 2 * h->num_sms) R >>= 1;
+            const size_t smem = (size_t)(R + (K - 1) * dil) * C * sizeof(float);
+            if (smem <= 200 * 1024) {
+                dim3 tg(cdiv(rows, R));
+                switch (C / 32) {
+                    case 4: STC_LAUNCH(h, (dwconv_ln_tile_kernel<4, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
+                    case 8: STC_LAUNCH(h, (dwconv_ln_tile_kernel<8, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
+                    case 16: STC_LAUNCH(h, (dwconv_ln_tile_kernel<16, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
+                }
+            }
+        }
         switch (C / 32) {
             case 4: STC_LAUNCH(h, (dwconv_ln_vec_kernel<4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
             case 8: STC_LAUNCH(h, (dwconv_ln_vec_kernel<8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
@@ -487,6 +515,12 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
 
 template <typename T>
 void Handle::gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo) {
+    // small row tiles when 64-row tiles would not give every SM a block (the fp64 duration predictor: 150 blocks before)
+    if (cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && M > 16) {
+        dim3 grid(cdiv(w.N, 64), cdiv(M, 16));
+        STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>, 16>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
+        return;
+    }
     dim3 grid(cdiv(w.N, 64), cdiv(M, 64));
     STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
 }
@@ -589,28 +623,81 @@ void Handle::attn_core(const float* Q, const float* K, const float* V, const Act
     kprof_end();
 }
 
-// Pre-LN multi-head attention with residual. Self-attention: ctx == nullptr && Kpre == nullptr (keys from LN(x), kseq = qseq).
-void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* ctx, const Seq& ks_in, const float* Kpre, const float* Vpre) {
+bool Handle::attn_on_tc(const Attention& a, const Seq& ks) const {
+    return tc_mode() && a.C / a.heads == attn::DH && ks.maxlen <= attn::MAX_BLOCKS * attn::KB && !force_simt_attn;
+}
+
+// K and V projections of `ctx` for one layer (+ rotary embedding on K), in the form the chosen attention core reads.
+KV Handle::make_kv(const Attention& a, const Act& ctx, const Seq& ks) {
+    KV kv;
+    const int dh = a.C / a.heads;
+    const size_t n = (size_t)ks.rows * a.C;
+    kv.tc = attn_on_tc(a, ks);
+    float *k = nullptr, *v = nullptr;
+    if (kv.tc) {
+        kv.ldk = (ks.maxlen + attn::KB - 1) / attn::KB * attn::KB;
+        const size_t nv = (size_t)ks.B * a.heads * attn::DH * kv.ldk;
+        kv.k_hi = ws<__nv_bfloat16>(n); kv.k_lo = ws<__nv_bfloat16>(n);
+        kv.vt_hi = ws<__nv_bfloat16>(nv); kv.vt_lo = ws<__nv_bfloat16>(nv);
+    } else { k = ws<float>(n); v = ws<float>(n); }
+    const size_t mk = mark();
+    if (kv.tc) { k = ws<float>(n); v = ws<float>(n); }
+    gemm(ctx, ks.rows, a.k, Epilogue{}, k, nullptr, a.C);
+    gemm(ctx, ks.rows, a.v, Epilogue{}, v, nullptr, a.C);
+    if (kv.tc) {
+        STC_LAUNCH(this, attn::qk_prep_kernel, cdiv((size_t)ks.rows * a.heads * 8, 256), 256, 0, k, a.rope != ROPE_NONE ? a.freqs : nullptr,
+                   ks.len, kv.k_hi, kv.k_lo, ks.rows, ks.off, ks.B, a.heads, a.rope == ROPE_NORM);
+        STC_LAUNCH(this, attn::v_prep_kernel, dim3(kv.ldk / attn::KB, a.heads, ks.B), 256, 0, v, kv.vt_hi, kv.vt_lo, ks.off, a.heads, kv.ldk);
+        release(mk);
+    } else {
+        if (a.rope != ROPE_NONE) rope(k, a.freqs, ks, a.heads, dh, a.rope == ROPE_NORM);
+        kv.K = k; kv.V = v;
+    }
+    return kv;
+}
+
+void Handle::attn_core_tc(const float* Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k) {
+    const size_t mk = mark();
+    const size_t n = (size_t)q.rows * a.C;
+    __nv_bfloat16* q_hi = ws<__nv_bfloat16>(n); __nv_bfloat16* q_lo = ws<__nv_bfloat16>(n);
+    STC_LAUNCH(this, attn::qk_prep_kernel, cdiv((size_t)q.rows * a.heads * 8, 256), 256, 0, Q, a.rope != ROPE_NONE ? a.freqs : nullptr, q.len,
+               q_hi, q_lo, q.rows, q.off, q.B, a.heads, a.rope == ROPE_NORM);
+    attn::Params p{};
+    p.qoff = q.off; p.koff = k.off; p.kcnt = (a.key_masked && k.mask) ? k.cnt : nullptr;
+    p.heads = a.heads; p.scale_log2e = (1.0f / std::sqrt((float)attn::DH)) * 1.4426950408889634f;
+    if (out.hi) { p.out_hi = out.hi; p.out_lo = out.lo; p.split = 1; } else { p.out_f32 = out.f; p.split = 0; }
+    kprof_begin(2, 4.0 * (double)q.rows * k.maxlen * a.C, 4.0 * a.C * (2.0 * q.rows + 2.0 * k.rows));
+    if (!dry) {
+        const int vrows = k.B * a.heads * attn::DH;
+        const CUtensorMap mqh = tmap(q_hi, q.rows, a.C, attn::BQ), mql = tmap(q_lo, q.rows, a.C, attn::BQ);
+        const CUtensorMap mkh = tmap(kv.k_hi, k.rows, a.C, attn::KB), mkl = tmap(kv.k_lo, k.rows, a.C, attn::KB);
+        const CUtensorMap mvh = tmap(kv.vt_hi, vrows, kv.ldk, attn::DH), mvl = tmap(kv.vt_lo, vrows, kv.ldk, attn::DH);
+        dim3 grid(cdiv(q.maxlen, attn::BQ), a.heads, q.B);
+        attn::attention_tc_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
+        ++launches;
+    }
+    kprof_end();
+    release(mk);
+}
+
+// Pre-LN multi-head attention with residual. Self-attention: ctx == nullptr && pre == nullptr (keys from LN(x), kseq = qseq).
+void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* ctx, const Seq& ks_in, const KV* pre) {
     size_t mk = mark();
     int rows = qs.rows, dh = a.C / a.heads;
     Act xn = ws_act((size_t)rows * a.C);
     dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, qs, 1e-6f, nullptr, &xn);
-    if (qs.rows > 0 && !dry && tc_mode()) {}   // (operand rows beyond off[B] are finite garbage: rows are independent)
     float* q = ws<float>((size_t)rows * a.C);
     gemm(xn, rows, a.q, Epilogue{}, q, nullptr, a.C);
-    const float *Kp = Kpre, *Vp = Vpre;
     const Seq& ks = a.ctx_kind == CTX_SELF ? qs : ks_in;
     if (a.ctx_kind == CTX_SELF) ctx = &xn;
-    if (!Kp) {
-        float* k = ws<float>((size_t)ks.rows * a.C); float* v = ws<float>((size_t)ks.rows * a.C);
-        gemm(*ctx, ks.rows, a.k, Epilogue{}, k, nullptr, a.C);
-        gemm(*ctx, ks.rows, a.v, Epilogue{}, v, nullptr, a.C);
-        if (a.rope != ROPE_NONE) rope(k, a.freqs, ks, a.heads, dh, a.rope == ROPE_NORM);
-        Kp = k; Vp = v;
-    }
-    if (a.rope != ROPE_NONE) rope(q, a.freqs, qs, a.heads, dh, a.rope == ROPE_NORM);
+    KV local;
+    if (!pre) { local = make_kv(a, *ctx, ks); pre = &local; }
     Act o = ws_act((size_t)rows * a.C);
-    attn_core(q, Kp, Vp, o, qs, ks, a.key_masked, a.heads, dh);
+    if (pre->tc) attn_core_tc(q, a, *pre, o, qs, ks);
+    else {
+        if (a.rope != ROPE_NONE) rope(q, a.freqs, qs, a.heads, dh, a.rope == ROPE_NORM);
+        attn_core(q, pre->K, pre->V, o, qs, ks, a.key_masked, a.heads, dh);
+    }
     Epilogue eo; eo.resid = x; eo.mask = a.masked ? qs.mask : nullptr;
     gemm(o, rows, a.o, eo, x, nullptr, a.C);
     release(mk);
@@ -707,8 +794,8 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mas
         if (l.type == L_CONVNEXT) convnext<float>(te.cn[l.idx], x, tseq);
         else if (l.type == L_ATTN) {
             const Attention& a = te.at[l.idx];
-            if (a.ctx_kind == CTX_SELF) attention(a, x, tseq, nullptr, tseq, nullptr, nullptr);
-            else attention(a, x, tseq, &sty, sseq, nullptr, nullptr);
+            if (a.ctx_kind == CTX_SELF) attention(a, x, tseq, nullptr, tseq, nullptr);
+            else attention(a, x, tseq, &sty, sseq, nullptr);
         } else if (l.type == L_PROJ_OUT) {
             Act xa = ws_act((size_t)rows * C);
             to_act(x, (size_t)rows * C, xa);
@@ -724,26 +811,16 @@ void Handle::prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_
     int Cs = cfg.style_ttl_dim, Ct = cfg.text_emb_channels;
     int nslots = 0;
     for (const Attention& a : ve.at) if (a.kv_slot >= 0) nslots = std::max(nslots, a.kv_slot + 1);
-    vc.Kc.assign(nslots, nullptr); vc.Vc.assign(nslots, nullptr);
-    for (const Attention& a : ve.at) {
-        if (a.kv_slot < 0) continue;
-        int kr = a.ctx_kind == CTX_TEXT ? vc.text.rows : vc.style.rows;
-        vc.Kc[a.kv_slot] = ws<float>((size_t)kr * a.C);
-        vc.Vc[a.kv_slot] = ws<float>((size_t)kr * a.C);
-    }
-    size_t mk = mark();
+    vc.kv.assign(nslots, KV{});
+    // the split-bf16 copies of the two contexts stay allocated next to the K/V they feed (arena space, a few MB)
     Act ta = ws_act((size_t)vc.text.rows * Ct), sa = ws_act((size_t)vc.style.rows * Cs);
     to_act(text_emb_cl, (size_t)vc.text.rows * Ct, ta);
     to_act(style_ttl, (size_t)vc.style.rows * Cs, sa);
     for (const Attention& a : ve.at) {
         if (a.kv_slot < 0) continue;
-        bool text = a.ctx_kind == CTX_TEXT;
-        const Seq& ks = text ? vc.text : vc.style;
-        gemm(text ? ta : sa, ks.rows, a.k, Epilogue{}, vc.Kc[a.kv_slot], nullptr, a.C);
-        gemm(text ? ta : sa, ks.rows, a.v, Epilogue{}, vc.Vc[a.kv_slot], nullptr, a.C);
-        if (a.rope != ROPE_NONE) rope(vc.Kc[a.kv_slot], a.freqs, ks, a.heads, a.C / a.heads, a.rope == ROPE_NORM);
+        const bool text = a.ctx_kind == CTX_TEXT;
+        vc.kv[a.kv_slot] = make_kv(a, text ? ta : sa, text ? vc.text : vc.style);
     }
-    release(mk);
 }
 
 // Time conditioning depends only on (current_step, total_step): the sinusoid -> MLP -> per-super-block linears are
@@ -806,7 +883,7 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
                 break;
             case L_ATTN: {
                 const Attention& a = ve.at[l.idx];
-                attention(a, x, ls, nullptr, a.ctx_kind == CTX_TEXT ? vc.text : vc.style, vc.Kc[a.kv_slot], vc.Vc[a.kv_slot]);
+                attention(a, x, ls, nullptr, a.ctx_kind == CTX_TEXT ? vc.text : vc.style, &vc.kv[a.kv_slot]);
                 break;
             }
             case L_PROJ_OUT: {
@@ -955,6 +1032,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         if (precision == STC_PREC_BF16X3 && prop.major != 10)
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
+        { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         for (auto& ev : hd->ev) STC_CUDA(cudaEventCreate(&ev));
         if (precision == STC_PREC_BF16X3) {
@@ -965,6 +1043,16 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+        }
+        {
+            const int big = 200 * 1024;
+            STC_CUDA(cudaFuncSetAttribute(dwconv_ln_tile_kernel<4, OutSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            STC_CUDA(cudaFuncSetAttribute(dwconv_ln_tile_kernel<8, OutSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            STC_CUDA(cudaFuncSetAttribute(dwconv_ln_tile_kernel<16, OutSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            STC_CUDA(cudaFuncSetAttribute((dwconv_ln_tile_kernel<4, OutPlain<float>>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            STC_CUDA(cudaFuncSetAttribute((dwconv_ln_tile_kernel<8, OutPlain<float>>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            STC_CUDA(cudaFuncSetAttribute((dwconv_ln_tile_kernel<16, OutPlain<float>>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         }
         hd->load(onnx_dir);
         sh->impl = std::move(hd);

@@ -234,3 +234,34 @@ def test_error_paths(rig):
     with pytest.raises(capi.StcError):
         capi.Engine("/nonexistent/onnx")
     assert eng.launches > 0
+
+
+def test_tensor_core_attention_matches_cuda_core_attention(rig):
+    """tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core fp32 core
+    (env STC_ATTN=simt) on the same engine weights: text encoder (self + style attention, rotary) and one vector-estimator
+    step (length-aware rotary cross-attention with a masked key tail, 50-key style attention)."""
+    import os
+    if rig["name"] != "full":
+        pytest.skip("head dim 32: the tiny config always uses the CUDA-core attention")
+    capi = rig["capi"]
+    os.environ["STC_ATTN"] = "simt"
+    try:
+        eng2 = capi.Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_ATTN"]
+    try:
+        rng = np.random.default_rng(77)
+        ids, mask, ttl, dp = _inputs(rig, 61, 5, 20, 300)
+        a = rig["eng"].text_encode(ids, ttl, mask)
+        b = eng2.text_encode(ids, ttl, mask)
+        assert np.abs(a - b).max() <= 5e-5, np.abs(a - b).max()
+        n, L = 5, 300
+        lens = rng.integers(40, L + 1, size=n); lens[0] = L; lens[1] = 129
+        lmask = (np.arange(L)[None, None, :] < lens[:, None, None]).astype(np.float32)
+        x = rng.standard_normal((n, 144, L)).astype(np.float32) * lmask
+        feeds = dict(noisy_latent=x, text_emb=a, style_ttl=ttl, text_mask=mask, latent_mask=lmask,
+                     total_step=np.full(n, 5, np.float32), current_step=np.full(n, 3, np.float32))
+        ya, yb = rig["eng"].vector_step(**feeds), eng2.vector_step(**feeds)
+        assert np.abs(ya - yb).max() <= 5e-5, np.abs(ya - yb).max()
+    finally:
+        eng2.close()
