@@ -54,6 +54,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
                     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
                     const Params p) {
+    pdl_trigger(); pdl_wait();
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(256)
 qk_prep_kernel(const float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, const int* __restrict__ off, int B,
                int heads, int normalise) {
+    pdl_trigger(); pdl_wait();
     // one thread: 4 consecutive dims d..d+3 (d < 32) of the first half and their partners d+32..d+35
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)rows * heads * 8;
@@ -280,6 +282,7 @@ qk_prep_kernel(const float* __restrict__ x, const float* __restrict__ freqs, con
 __global__ void __launch_bounds__(256)
 v_prep_kernel(const float* __restrict__ v, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
               const int* __restrict__ koff, int heads, int ldk) {
+    pdl_trigger(); pdl_wait();
     __shared__ float tile[KB][DH + 1];
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * KB;
     const int kbase = __ldg(koff + b), Nk = __ldg(koff + b + 1) - kbase;

@@ -14,6 +14,11 @@ namespace stc {
 
 #define STC_DEVINL __device__ __forceinline__
 
+// Programmatic dependent launch: every kernel is launched with programmatic stream serialization, lets its successor start
+// (launch latency, prologue) right away, and waits for its predecessor's writes itself before touching global memory.
+STC_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+STC_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> STC_DEVINL T t_erf(T x);
 template <> STC_DEVINL float t_erf<float>(float x) { return erff(x); }
 template <> STC_DEVINL double t_erf<double>(double x) { return erf(x); }
@@ -81,6 +86,7 @@ struct OutSplit {
 template <typename T>
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
                              const float* __restrict__ mask, T* __restrict__ out, int rows, int C, int V) {
+    pdl_trigger(); pdl_wait();
     int row = blockIdx.x * blockDim.y + threadIdx.y;
     if (row >= rows) return;
     int64_t id = ids[row];
@@ -93,6 +99,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
 template <typename T>
 __global__ void add_rowvec_mask_kernel(T* __restrict__ x, const T* __restrict__ v, const float* __restrict__ mask,
                                        int rows, int N, int C, int vstride) {
+    pdl_trigger(); pdl_wait();
     // vstride = C: one vector per sequence of a [B,N] rectangle; vstride = 0: one vector for every row
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * C) return;
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wb,
                  const float* __restrict__ g, const float* __restrict__ beta, Out out,
                  int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = CPL * 32;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -189,6 +197,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                      const float* __restrict__ g, const float* __restrict__ beta, Out out,
                      int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = CPL * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -253,23 +262,33 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                       const float* __restrict__ g, const float* __restrict__ beta, Out out,
                       int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps, int R) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = CPL * 32, V = CPL / 4;
     extern __shared__ float4 tile4[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * R;
     const int span = (K - 1) * dil;
     const int w0 = r0 - pad_left, wrows = R + span;               // staged window of packed rows [w0, w0 + wrows)
-    for (int i = threadIdx.x; i < wrows * (C / 4); i += blockDim.x) {
-        const int wr = i / (C / 4), gr = w0 + wr;
-        tile4[i] = (gr >= 0 && gr < rows) ? *reinterpret_cast<const float4*>(x + (size_t)gr * C + (i % (C / 4)) * 4)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    {   // cp.async fill: every 16-byte piece of the window is in flight at once (no register staging); rows outside
+        // [0, rows) are zero-filled by a zero source size
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tile4);
+        for (int i = threadIdx.x; i < wrows * (C / 4); i += blockDim.x) {
+            const int gr = w0 + i / (C / 4);
+            const bool ok = gr >= 0 && gr < rows;
+            const float* src = ok ? x + (size_t)gr * C + (i % (C / 4)) * 4 : x;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)i * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    int b = -2;                                        // sequence of the previous row handled by this warp (-2: none yet)
     for (int rl = warp; rl < R; rl += (blockDim.x >> 5)) {
         const int row = r0 + rl;
         if (row >= rows) break;
         float4 y[V];
-        const int b = find_seq(off, B, row);
+        if (b == -2) b = find_seq(off, B, row);
+        else if (b >= 0) { while (b < B && row >= __ldg(off + b + 1)) ++b; if (b >= B) b = -1; }
         if (b < 0) {                                   // bucket padding row: keep it finite
 #pragma unroll
             for (int j = 0; j < V; ++j) y[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -318,6 +337,7 @@ dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT,
 // ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
 template <typename Out>
 __global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out.store(i, x[i]);
 }
@@ -338,6 +358,7 @@ template <typename T, typename Out, int BM = 64>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, Out out, int ldo,
                  int M, int N, int K, Epilogue ep) {
+    pdl_trigger(); pdl_wait();
     constexpr int BN = 64, BK = 16, TM = BM / 16;
     __shared__ T As[BK][BM + 1];
     __shared__ T Ws[BK][BN + 1];
@@ -393,6 +414,7 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, 
 
 // ---- sequence lengths from masks: len[b] = sum_n mask[b,n] ---------------------------------------
 __global__ void mask_len_kernel(const float* __restrict__ mask, float* __restrict__ len, int* __restrict__ cnt, int N) {
+    pdl_trigger(); pdl_wait();
     // len[b] = sum of the mask (what the graphs' ReduceSum sees); cnt[b] = 1 + index of the last non-zero entry
     int b = blockIdx.x;
     float s = 0.f; int last = 0;
@@ -407,6 +429,7 @@ __global__ void mask_len_kernel(const float* __restrict__ mask, float* __restric
 // pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i]
 __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
                             int rows, const int* __restrict__ off, int B, int heads, int DH, int normalise) {
+    pdl_trigger(); pdl_wait();
     int half = DH / 2;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)rows * heads * half;
@@ -434,6 +457,7 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ Vt,
                  const float* __restrict__ kmask, Out out, const int* __restrict__ qoff, const int* __restrict__ koff,
                  const int* __restrict__ kcnt, int heads, float scale) {
+    pdl_trigger(); pdl_wait();
     constexpr int QPW = 4, WARPS = 4, QT = QPW * WARPS, KC = 32, DPL = DH / 32;
     __shared__ float Ks[KC][DH + 1];
     __shared__ float Vs[KC][DH + 1];
@@ -509,6 +533,7 @@ attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, cons
 // NCL [B,C,N] -> NLC [B,N,C] (and back), 32x32 shared-memory tile transpose
 template <typename TI, typename TO>
 __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int Cc) {
+    pdl_trigger(); pdl_wait();
     // in: [batch][R][Cc] -> out: [batch][Cc][R]
     __shared__ float tile[32][33];
     int b = blockIdx.z;
@@ -535,6 +560,7 @@ STC_DEVINL uint32_t mix32(uint64_t z) {
 __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, const uint64_t* __restrict__ seed_p,
                                    const float* __restrict__ mask, float* __restrict__ x, int rows,
                                    const int* __restrict__ off, int B, int D) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * D) return;
     int d = (int)(i % D);
@@ -555,6 +581,7 @@ __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, 
 
 // latent mask from wav lengths: mask[b,l] = l < ceil(wav_len[b]/cs)  (getLatentMask, cpp/helper.cpp:759-770)
 __global__ void latent_mask_kernel(const int64_t* __restrict__ wav_len, float* __restrict__ mask, int B, int L, int cs) {
+    pdl_trigger(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     int b = i / L, l = i % L;
@@ -569,6 +596,7 @@ template <typename Out>
 __global__ void voc_im2col_kernel(const float* __restrict__ lat, const float* __restrict__ sd,
                                   const float* __restrict__ mean, Out out, int rows6, const int* __restrict__ off,
                                   int B, int f, int ld, int K, int lda) {
+    pdl_trigger(); pdl_wait();
     // off = LATENT-frame offsets; output rows run at f x the latent rate: row6 in [f*off[b], f*off[b+1])
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int KW = K * ld;
@@ -598,6 +626,7 @@ template <int CPL>
 __global__ void dp_head_kernel(const double* __restrict__ x, const float* __restrict__ g, const float* __restrict__ beta,
                                const float* __restrict__ w, const float* __restrict__ wb, const float* __restrict__ mask,
                                float* __restrict__ dur, int N, float eps, float clip, float spt) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = CPL * 32;
     __shared__ double part[32];
     int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -628,6 +657,7 @@ __global__ void dp_head_kernel(const double* __restrict__ x, const float* __rest
 
 // duration /= speed; wav_len = (int64)(d*sr)   (cpp/helper.cpp:529-531, 434) — float32 IEEE, no fast-math
 __global__ void dur_post_kernel(float* __restrict__ dur, int64_t* __restrict__ wav_len, int B, float speed, int sr) {
+    pdl_trigger(); pdl_wait();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float d = __fdiv_rn(dur[b], speed);
@@ -638,6 +668,7 @@ __global__ void dur_post_kernel(float* __restrict__ dur, int64_t* __restrict__ w
 // sinusoidal time embedding: t = cur/tot; out[b] = [sin(t*f), cos(t*f)]
 __global__ void time_embed_kernel(const float* __restrict__ cur, const float* __restrict__ tot,
                                   const float* __restrict__ freqs, float* __restrict__ out, int B, int half) {
+    pdl_trigger(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     int b = i / half, j = i % half;
@@ -649,6 +680,7 @@ __global__ void time_embed_kernel(const float* __restrict__ cur, const float* __
 
 // copy rows [B][L*cs] out of a wider device matrix into a strided destination
 __global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }

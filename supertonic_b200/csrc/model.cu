@@ -69,18 +69,21 @@ struct Handle {
     int num_sms = 148;
     int precision = STC_PREC_BF16X3;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;    // the text encoder runs here, concurrently with the duration predictor on `stream`
+    cudaEvent_t ev_in = nullptr, ev_te = nullptr;
     stc_config cfg{};
     Net dp, te, ve, voc;
     json dp_arch, te_arch, ve_arch, voc_arch;
     std::vector<void*> owned;          // weight allocations
     Arena arena;       // workspace: reset per stage
+    Arena arena2;      // workspace of whatever runs on stream2 (swapped in for the duration of that stage)
     Arena persist;     // buffers that survive from stage 1 (DP/TE) into stage 2 (VE loop + vocoder)
     bool dry = false;          // no launches / copies (workspace measuring pass, or re-staging before a graph replay)
     bool restage = false;      // dry, but offset arrays are still written into their pinned staging slots
     bool capturing = false;    // launches go into a stream capture; host->device copies of caller memory are deferred
     struct PreCopy { void* dst; const void* src; size_t bytes; };
     std::vector<PreCopy> pre_copies;
-    void run_graphed(const GraphKey& key, const std::function<void()>& body);
+    void run_graphed(const GraphKey& key, const std::function<void()>& body, cudaEvent_t after_uploads = nullptr);
     uint64_t graph_replays = 0, graph_captures = 0;
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
@@ -182,13 +185,30 @@ struct Handle {
     int* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging for offset arrays
 };
 
-#define STC_LAUNCH(h, kernel, grid, block, smem, ...)                          \
-    do {                                                                       \
-        if (!(h)->dry) {                                                       \
-            auto _kfn = kernel;                                                \
-            _kfn<<<grid, block, smem, (h)->stream>>>(__VA_ARGS__);             \
-            ++(h)->launches;                                                   \
-        }                                                                      \
+// Optional (env STC_PDL=1) programmatic dependent launch: every kernel goes out with programmatic stream serialization, may
+// start while its predecessor drains, and waits for the predecessor's memory itself (pdl_wait() at the top of every kernel;
+// a no-op without the attribute). Measured on B200 (profiles/r1g_bench.json vs r1f): 15.2 ms/step with PDL against 14.3
+// without — the ~860 programmatic graph edges cost more than the overlapped prologues save — so it is OFF by default.
+static bool g_use_pdl = [] { const char* e = getenv("STC_PDL"); return e && e[0] == '1'; }();
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+}
+
+#define STC_LAUNCH(h, kernel, grid, block, smem, ...)                                       \
+    do {                                                                                    \
+        if (!(h)->dry) {                                                                    \
+            launch_pdl((h), kernel, dim3(grid), dim3(block), (size_t)(smem), (h)->stream, __VA_ARGS__); \
+            ++(h)->launches;                                                                \
+        }                                                                                   \
     } while (0)
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -203,6 +223,9 @@ Handle::~Handle() {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : ev_pool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_te) cudaEventDestroy(ev_te);
 }
 
 void Handle::check_launch(const char* what) {
@@ -466,10 +489,11 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
         // w is the tap-major transpose wT[K][C] for these widths (ConvNeXt::dw_wt)
         if (K > 0 && (C == 128 || C == 256 || C == 512)) {
             // rows per block: as many as keep >= 2 blocks per SM in flight (shared-memory tile = (R + span) rows)
-            int R = 32;
-            while (R > 8 && (int)cdiv(rows, R) < 2 * h->num_sms) R >>= 1;
-            const size_t smem = (size_t)(R + (K - 1) * dil) * C * sizeof(float);
-            if (smem <= 200 * 1024) {
+            const int span = (K - 1) * dil;
+            int R = std::min(32, (int)(100 * 1024 / (C * sizeof(float))) - span) / 8 * 8;       // <= 100 KB: two blocks per SM
+            while (R > 8 && (int)cdiv(rows, R) < 2 * h->num_sms) R -= 8;
+            const size_t smem = (size_t)(std::max(R, 8) + span) * C * sizeof(float);
+            if (R >= 8 && smem <= 200 * 1024) {
                 dim3 tg(cdiv(rows, R));
                 switch (C / 32) {
                     case 4: STC_LAUNCH(h, (dwconv_ln_tile_kernel<4, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
@@ -548,10 +572,11 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     const int clusters = std::max(1, std::min(cluster_tiles, num_sms / csize));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * csize); cfg.blockDim = dim3(tc::NUM_THREADS); cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = csize > 1 ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    if (csize > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = csize; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
+    cfg.attrs = attr; cfg.numAttrs = na;
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
     switch (c.bn) {
@@ -673,7 +698,7 @@ void Handle::attn_core_tc(const float* Q, const Attention& a, const KV& kv, cons
         const CUtensorMap mkh = tmap(kv.k_hi, k.rows, a.C, attn::KB), mkl = tmap(kv.k_lo, k.rows, a.C, attn::KB);
         const CUtensorMap mvh = tmap(kv.vt_hi, vrows, kv.ldk, attn::DH), mvl = tmap(kv.vt_lo, vrows, kv.ldk, attn::DH);
         dim3 grid(cdiv(q.maxlen, attn::BQ), a.heads, q.B);
-        attn::attention_tc_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
+        launch_pdl(this, attn::attention_tc_kernel, grid, dim3(attn::NUM_THREADS), (size_t)attn::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
         ++launches;
     }
     kprof_end();
@@ -740,6 +765,7 @@ Seq Handle::packed_seq(const std::vector<int>& lens, int rows_launch, int maxlen
 }
 
 __global__ void scale_off_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int f) {
+    pdl_trigger(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] * f;
 }
@@ -755,6 +781,7 @@ Seq Handle::scaled_seq(const Seq& s, int f) {
 // ------------------------------------------------------------------------------------------ graph walkers
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (TO)in[i];
 }
@@ -952,8 +979,12 @@ void Handle::ensure_ws(const std::function<void()>& fn) {
 // Run `body` (which must allocate deterministically from the arenas) either eagerly or as a cached CUDA graph.
 // Replay: `body` is re-run with launches suppressed, only to refresh the pinned staging slots (sequence offsets, seed)
 // and to collect the caller-memory uploads, then the instantiated graph is launched.
-void Handle::run_graphed(const GraphKey& key, const std::function<void()>& body) {
-    if (!use_graphs || profile) { ensure_ws(body); body(); return; }
+void Handle::run_graphed(const GraphKey& key, const std::function<void()>& body, cudaEvent_t after_uploads) {
+    if (!use_graphs || profile) {            // eager (profiling / debugging): no overlap — the event fires after the whole body
+        ensure_ws(body); body();
+        if (after_uploads) STC_CUDA(cudaEventRecord(after_uploads, stream));
+        return;
+    }
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         ensure_ws(body);                       // may grow the arenas (and then drops every cached graph)
@@ -982,6 +1013,7 @@ void Handle::run_graphed(const GraphKey& key, const std::function<void()>& body)
     }
     for (const PreCopy& c : pre_copies) STC_CUDA(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, stream));
     pre_copies.clear();
+    if (after_uploads) STC_CUDA(cudaEventRecord(after_uploads, stream));
     STC_CUDA(cudaGraphLaunch(it->second.exec, stream));
     launches += it->second.kernels;            // kernels executed by this replay
 }
@@ -1034,6 +1066,9 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
+        STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
+        STC_CUDA(cudaEventCreateWithFlags(&hd->ev_te, cudaEventDisableTiming));
         for (auto& ev : hd->ev) STC_CUDA(cudaEventCreate(&ev));
         if (precision == STC_PREC_BF16X3) {
             void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
@@ -1321,10 +1356,20 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         };
         uint32_t speed_bits; memcpy(&speed_bits, &speed, 4);
         if (h->profile) cudaEventRecord(h->ev[0], st);
-        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0}, stage1a);
+        // duration predictor on the main stream (behind the input uploads), text encoder concurrently on stream2 with its own
+        // workspace: the two are independent (cpp/helper.cpp:512-556 runs them back to back) and DP alone leaves the GPU idle
+        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0}, stage1a, h->ev_in);
         if (h->profile) cudaEventRecord(h->ev[1], st);
         cudaEventRecord(h->ev[6], st);
-        h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0}, stage1b);
+        {
+            STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
+            std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
+            try { h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0}, stage1b); }
+            catch (...) { std::swap(h->stream, h->stream2); h->arena.swap(h->arena2); throw; }
+            cudaEventRecord(h->ev_te, h->stream);
+            std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
+            STC_CUDA(cudaStreamWaitEvent(st, h->ev_te, 0));            // everything after this point on the main stream sees text_emb
+        }
         if (h->profile) cudaEventRecord(h->ev[2], st);
         STC_CUDA(cudaEventSynchronize(h->ev[6]));                 // the one data-dependent sync: duration -> L
         int L = latent_len_f32(h->h_dur, B, c.sample_rate, c.chunk_size);
@@ -1432,18 +1477,21 @@ int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, con
 
 // ---- debug / tuning: one tcgen05 GEMM of a given shape and launch configuration, timed and checked -----------------
 __global__ void debug_fill_kernel(float* __restrict__ p, size_t n, uint64_t seed, float scale) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float u1 = (stc::mix32(seed + 2 * i) + 1.0f) * (1.0f / 4294967808.0f), u2 = stc::mix32(seed + 2 * i + 1) * (1.0f / 4294967296.0f);
     p[i] = scale * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 __global__ void debug_maxdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+    pdl_trigger(); pdl_wait();
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i] - b[i]));
     m = stc::warp_max(m);
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));     // non-negative floats order like ints
 }
 __global__ void debug_join_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, size_t n) {
+    pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }

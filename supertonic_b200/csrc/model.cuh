@@ -87,6 +87,10 @@ public:
     size_t used() const { return off_; }
     size_t capacity() const { return cap_; }
     size_t high_water = 0;
+    Arena() = default;
+    Arena(const Arena&) = delete;
+    Arena& operator=(const Arena&) = delete;
+    void swap(Arena& o) { std::swap(base_, o.base_); std::swap(cap_, o.cap_); std::swap(off_, o.off_); std::swap(high_water, o.high_water); }
     ~Arena();
 private:
     char* base_ = nullptr;
