@@ -1,0 +1,258 @@
+// Fused ConvNeXt MLP on tcgen05 for the C = 256, H = 1024 blocks of the vector estimator and the text encoder (sm_100a):
+//
+//     x[rows, C]  <-  ( x + gamma * ( GELU( a W1 + b1 ) W2 + b2 ) ) * mask          a = LayerNorm(dwconv(x)) as split-bf16
+//
+// Why: as two GEMMs the block is bound by operand ingest into the SMs — the 19 MB hidden tensor is written,
+// then re-read once per N tile, and every tile re-reads its share of W. Here the hidden activations never leave the SM.
+//
+// One thread-block CLUSTER of 4 CTAs owns a 128-row tile; CTA c owns hidden units [256c, 256c+256):
+//   phase 1  S_c[128 x 256]  = a[128 x 256] . W1[256c.., :]^T            (TMEM columns 0..255)
+//   epi 1    P_c = split-bf16( GELU(S_c + b1) ) written as a K-major swizzled A operand into the smem the a-tile occupied
+//   phase 2  O_c[128 x 256] = P_c[128 x 256] . W2[:, 256c..]^T           (TMEM columns 256..511)  — a partial sum over hidden units
+//   reduce   CTA p owns output columns [64p, 64p+64): every CTA ships its partial for those columns into p's shared memory
+//            over DSMEM (st.shared::cluster), p adds the four partials in rank order (deterministic) and applies
+//            bias / layer-scale / residual / mask with coalesced global accesses.
+// Per SM ingest: a-tile 128 KB + a quarter of W1 and of W2 (2 x 256 KB), against ~1.3 MB for the same rows as two GEMMs.
+//
+// Warps: 0 = TMA producer (a tile once, then 16 weight units of 128 rows x 64 K through a 3-slot ring), 1 = MMA issuer,
+// 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4). Arithmetic: split-bf16, 3 MMAs per K slice.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace stc {
+namespace mlp {
+
+constexpr int C = 256, H = 1024, CS = 4, HC = H / CS;     // channels, hidden units, cluster size, hidden units per CTA
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int NUM_THREADS = 320;
+constexpr int KBLK = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16, one half (hi or lo)
+constexpr int X_BYTES = 2 * (C / BK) * KBLK;      // 128 KB: a-tile (hi k-blocks 0..3, lo k-blocks 0..3); later P, later staging
+constexpr int UNIT = 2 * KBLK;                    // 32 KB: 128 weight rows x 64 K, hi + lo
+constexpr int SLOTS = 3;
+constexpr int OFF_X = 0, OFF_RING = X_BYTES, OFF_BAR = OFF_RING + SLOTS * UNIT;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int UNITS_PER_PHASE = (C / BK) * (HC / 128);     // 8
+constexpr int RECV_BYTES = BM * 64 * 4;           // 32 KB: one sender's partial for my 64 columns
+static_assert(3 * RECV_BYTES <= SLOTS * UNIT, "receive slots alias the weight ring");
+static_assert(HC == C, "phase 1 and phase 2 share the unit schedule");
+
+struct Params {
+    int M;
+    const float* b1; const float* b2; const float* gamma; const float* mask;
+    float* x;                       // [M, C] residual stream, updated in place
+};
+
+STC_DEVINL uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
+}
+STC_DEVINL void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                    const Params p) {
+    using namespace tc;
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar = smem_base + OFF_BAR;
+    const uint32_t bar_a = bar, bar_s1 = bar + 8, bar_o = bar + 16;
+    auto full_bar = [&](int s) { return bar + 24 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar + 48 + 8u * s; };
+    auto bar_p = [&](int j) { return bar + 72 + 8u * j; };
+    const uint32_t tmem_slot = bar + 104;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();
+    const int m0 = (int)cluster_id_x() * BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
+        tma_prefetch_desc(&map_w1_lo); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo);
+        mbar_init(bar_a, 1); mbar_init(bar_s1, 1); mbar_init(bar_o, 1);
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int j = 0; j < HC / BK; ++j) mbar_init(bar_p(j), 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_a, X_BYTES);
+            for (int kb = 0; kb < C / BK; ++kb) {
+                tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_a, kb * BK, m0);
+                tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
+            }
+            for (int u = 0; u < 2 * UNITS_PER_PHASE; ++u) {
+                const int s = u % SLOTS;
+                mbar_wait(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
+                const uint32_t dst = smem_base + OFF_RING + s * UNIT;
+                mbar_expect_tx(full_bar(s), UNIT);
+                const int v = u % UNITS_PER_PHASE, kb = v >> 1, nh = v & 1;
+                if (u < UNITS_PER_PHASE) {          // W1[hidden rows, C]: rows crank*HC + nh*128, K block kb of C
+                    tma_load_2d(dst, &map_w1_hi, full_bar(s), kb * BK, crank * HC + nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w1_lo, full_bar(s), kb * BK, crank * HC + nh * 128);
+                } else {                            // W2[C rows, hidden]: rows nh*128, K block kb of this CTA's hidden slice
+                    tma_load_2d(dst, &map_w2_hi, full_bar(s), crank * HC + kb * BK, nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w2_lo, full_bar(s), crank * HC + kb * BK, nh * 128);
+                }
+            }
+        }
+        __syncwarp();                      // reconverge before the (warp-aligned) cluster barriers below
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
+        mbar_wait(bar_a, 0);
+        for (int u = 0; u < 2 * UNITS_PER_PHASE; ++u) {
+            const int s = u % SLOTS, v = u % UNITS_PER_PHASE, kb = v >> 1, nh = v & 1;
+            const bool second = u >= UNITS_PER_PHASE;
+            if (second && nh == 0) mbar_wait(bar_p(kb), 0);             // P k-block kb written by the epilogue warps
+            mbar_wait(full_bar(s), (u / SLOTS) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t xk = smem_base + OFF_X + kb * KBLK, st = smem_base + OFF_RING + s * UNIT;
+                const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
+                const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
+                const uint32_t d = tmem_base + (second ? 256 : 0) + nh * 128;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                    umma_bf16(d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+                    umma_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
+                    umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
+                }
+                umma_commit(empty_bar(s));
+                if (u == UNITS_PER_PHASE - 1) umma_commit(bar_s1);      // S complete; the a-tile is dead
+                if (u == 2 * UNITS_PER_PHASE - 1) umma_commit(bar_o);   // partial O complete; ring and P are dead
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue 1: P = split(GELU(S + b1)) =====
+        const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t prow_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        mbar_wait(bar_s1, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < HC / BK; ++j) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(trow + j * BK + half * 32, v);
+            const float* b1 = p.b1 + crank * HC + j * BK + half * 32;
+            uint8_t* p_hi = smem_gen + OFF_X + j * KBLK + prow_off;
+            uint8_t* p_lo = p_hi + (C / BK) * KBLK;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float e0 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t]) + __ldg(b1 + c8 * 8 + 2 * t));
+                    const float e1 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t + 1]) + __ldg(b1 + c8 * 8 + 2 * t + 1));
+                    split_pair(e0, e1, hi[t], lo[t]);
+                }
+                const int chunk = (half * 4 + c8) ^ (r & 7);
+                *reinterpret_cast<uint4*>(p_hi + chunk * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(p_lo + chunk * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p(j));
+        }
+        mbar_wait(bar_o, 0);               // all MMAs of this CTA retired: ring, P and (for reads) the O accumulator are ours
+        tc_fence_after();
+    }
+
+    // ===== cross-CTA reduction of the partial outputs (all threads take part in the cluster barriers) =====
+    cluster_sync_all();                    // every CTA's weight ring is dead: it becomes the receive area
+    if (warp >= 2) {
+        const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+        for (int d = 1; d < CS; ++d) {
+            const int peer = (crank + d) % CS;                       // stagger the targets
+            const int slot = crank < peer ? crank : crank - 1;       // my slot among the peer's three senders
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(trow + peer * 64 + half * 32, v);
+            const uint32_t local = smem_base + OFF_RING + slot * RECV_BYTES + r * 256;
+            const uint32_t remote = mapa_u32(local, (uint32_t)peer);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int chunk = (half * 8 + i) ^ (r & 15);
+                st_cluster_v4(remote + chunk * 16, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                              __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+        }
+    }
+    cluster_sync_all();                    // partials have landed (release / acquire at cluster scope)
+    if (warp >= 2) {
+        const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+        float* stg = reinterpret_cast<float*>(smem_gen + OFF_X) + (warp - 2) * 32 * EPI_PITCH;
+        const int sub = lane >> 2, cq = (lane & 3) * 4;
+        float acc[32];
+        {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(trow + crank * 64 + half * 32, v);
+            // sum the four partials in source-rank order (own one at position crank): the same order in every CTA
+#pragma unroll
+            for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+            for (int src = 0; src < CS; ++src) {
+                if (src == crank) {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) acc[t] += __uint_as_float(v[t]);
+                } else {
+                    const int slot = src < crank ? src : src - 1;
+                    const uint8_t* row = smem_gen + OFF_RING + slot * RECV_BYTES + r * 256;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int chunk = (half * 8 + i) ^ (r & 15);
+                        const float4 w = *reinterpret_cast<const float4*>(row + chunk * 16);
+                        acc[4 * i] += w.x; acc[4 * i + 1] += w.y; acc[4 * i + 2] += w.z; acc[4 * i + 3] += w.w;
+                    }
+                }
+            }
+        }
+        // epilogue 2 through per-warp staging: lanes along the row, coalesced residual reads and stores
+        const int mrow0 = m0 + q * 32, col0 = crank * 64 + half * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += EPI_CHUNK) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < EPI_CHUNK; j += 4)
+                *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + j) = make_float4(acc[c + j], acc[c + j + 1], acc[c + j + 2], acc[c + j + 3]);
+            __syncwarp();
+            const int col = col0 + c + cq;
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = i * 8 + sub, row = mrow0 + rl;
+                if (row >= p.M) continue;
+                float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq);
+                float* xp = p.x + (size_t)row * C + col;
+                const float4 res = *reinterpret_cast<const float4*>(xp);
+                const float mk = p.mask ? __ldg(p.mask + row) : 1.f;
+                v.x = ((v.x + b2.x) * g.x + res.x) * mk; v.y = ((v.y + b2.y) * g.y + res.y) * mk;
+                v.z = ((v.z + b2.z) * g.z + res.z) * mk; v.w = ((v.w + b2.w) * g.w + res.w) * mk;
+                *reinterpret_cast<float4*>(xp) = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mlp
+}  // namespace stc

@@ -13,6 +13,7 @@
 
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "mlp_tc.cuh"
 #include "model.cuh"
 #include "text_frontend.h"
 
@@ -156,6 +157,9 @@ struct Handle {
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
+    bool mlp_fusable(const ConvNeXt& c) const;
+    void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask);
+    bool force_unfused_mlp = false;   // env STC_MLP=unfused: pw1 / pw2 as two GEMMs (cross-check)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
@@ -604,6 +608,26 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
     return GemmCfg{bn, 1, 1};
 }
 
+bool Handle::mlp_fusable(const ConvNeXt& c) const {
+    return tc_mode() && !force_unfused_mlp && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps;
+}
+
+// pw1 -> GELU -> pw2 -> layer-scale, residual, mask in ONE kernel (mlp_tc.cuh): a 4-CTA cluster per 128-row tile.
+void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask) {
+    mlp::Params p{};
+    p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
+    kprof_begin(0, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
+    if (!dry) {
+        const CUtensorMap mah = tmap(a.hi, rows, c.C, mlp::BM), mal = tmap(a.lo, rows, c.C, mlp::BM);
+        const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
+        const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
+        launch_pdl(this, mlp::convnext_mlp_kernel, dim3(cdiv(rows, mlp::BM) * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                   mah, mal, w1h, w1l, w2h, w2l, p);
+        ++launches;
+    }
+    kprof_end();
+}
+
 template <typename T>
 void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     size_t mk = mark();
@@ -611,10 +635,14 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     Epilogue e1; e1.gelu = 1;
     Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
-        Act a = ws_act((size_t)rows * c.C), hid = ws_act((size_t)rows * c.H);
+        Act a = ws_act((size_t)rows * c.C);
         dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-        gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
-        gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
+        if (mlp_fusable(c)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr);
+        else {
+            Act hid = ws_act((size_t)rows * c.H);
+            gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
+            gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
+        }
     } else {
         T* a = ws<T>((size_t)rows * c.C); T* hid = ws<T>((size_t)rows * c.H);
         dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, a, nullptr);
@@ -1065,6 +1093,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
+        { const char* e = getenv("STC_MLP"); hd->force_unfused_mlp = e && std::string(e) == "unfused"; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
@@ -1079,6 +1108,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
         }
         {
             const int big = 200 * 1024;

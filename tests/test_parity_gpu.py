@@ -236,19 +236,21 @@ def test_error_paths(rig):
     assert eng.launches > 0
 
 
-def test_tensor_core_attention_matches_cuda_core_attention(rig):
-    """tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core fp32 core
-    (env STC_ATTN=simt) on the same engine weights: text encoder (self + style attention, rotary) and one vector-estimator
-    step (length-aware rotary cross-attention with a masked key tail, 50-key style attention)."""
+@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused")])
+def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
+    """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
+    fp32 core. STC_MLP=unfused: the 4-CTA-cluster fused ConvNeXt MLP (mlp_tc.cuh, DSMEM reduction) against pw1 / pw2 as two
+    GEMMs. Same weights, text encoder (self + style attention, rotary) and one vector-estimator step (length-aware rotary
+    cross-attention with a masked key tail, 50-key style attention, ragged rows incl. a partial last tile)."""
     import os
     if rig["name"] != "full":
-        pytest.skip("head dim 32: the tiny config always uses the CUDA-core attention")
+        pytest.skip("the tiny config (head dim 32, C=64) always takes the simple kernels")
     capi = rig["capi"]
-    os.environ["STC_ATTN"] = "simt"
+    os.environ[env[0]] = env[1]
     try:
         eng2 = capi.Engine(rig["root"] + "/onnx")
     finally:
-        del os.environ["STC_ATTN"]
+        del os.environ[env[0]]
     try:
         rng = np.random.default_rng(77)
         ids, mask, ttl, dp = _inputs(rig, 61, 5, 20, 300)
