@@ -184,6 +184,10 @@ int stc_last_stage_ms(const stc_handle* h, float out[5]);
 int stc_debug_gemm(stc_handle* h, int M, int N, int K, int bn, int cm, int cn, int epilogue, int iters,
                    float* ms_per_iter, float* max_abs_err);
 
+/* Same for the fused ConvNeXt MLP (C = 256, H = 1024) against the two-GEMM form on M rows of seeded data: mean device time of
+ * each (CUDA-graph replay of `iters` launches) and the max-abs difference of the updated residual stream. */
+int stc_debug_mlp(stc_handle* h, int M, int iters, float* ms_fused, float* ms_unfused, float* max_abs_err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,7 @@ _SIGS = {
     "stc_set_profile": (_i, [_vp, _i]),
     "stc_last_stage_ms": (_i, [_vp, _vp]),
     "stc_kernel_profile": (_i, [_vp, _i, _vp]),
+    "stc_debug_mlp": (_i, [_vp, _i, _i, _pf, _pf, _pf]),
     "stc_debug_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _pf, _pf]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -342,6 +343,12 @@ class Engine:
         ms, err = C.c_float(0), C.c_float(0)
         self._chk(lib.stc_debug_gemm(self._h, M, N, K, bn, cm, cn, epilogue, iters, C.byref(ms), C.byref(err)))
         return ms.value * 1000.0, err.value
+
+    def debug_mlp(self, M, iters=20):
+        """Fused ConvNeXt MLP vs two GEMMs on M rows -> (us fused, us unfused, max-abs difference)."""
+        a, b, e = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._chk(lib.stc_debug_mlp(self._h, M, iters, C.byref(a), C.byref(b), C.byref(e)))
+        return a.value * 1000.0, b.value * 1000.0, e.value
 
     def stage_ms(self):
         out = np.zeros(5, np.float32)

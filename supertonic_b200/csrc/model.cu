@@ -157,9 +157,9 @@ struct Handle {
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
-    bool mlp_fusable(const ConvNeXt& c) const;
+    bool mlp_fusable(const ConvNeXt& c, int rows) const;
     void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask);
-    bool force_unfused_mlp = false;   // env STC_MLP=unfused: pw1 / pw2 as two GEMMs (cross-check)
+    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" always, 2 "unfused" always (cross-checks)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
@@ -608,8 +608,15 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
     return GemmCfg{bn, 1, 1};
 }
 
-bool Handle::mlp_fusable(const ConvNeXt& c) const {
-    return tc_mode() && !force_unfused_mlp && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps;
+// The fused kernel needs its 4-CTA clusters resident in ONE wave: B200 places 33 of them (GPCs of 16/18/20 SMs strand 16 SMs),
+// so at 34+ row tiles a second wave doubles its time. Measured (tools/mlp_sweep.py, profiles/r1i_mlp_sweep.txt): 2048 rows
+// 21.9 us fused vs 23.2 us as two GEMMs, 4224 rows 23.7 vs 29.1, 4736 rows (37 tiles) 42.6 vs 29.3 -> fused for 16..33 tiles.
+bool Handle::mlp_fusable(const ConvNeXt& c, int rows) const {
+    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps)) return false;
+    if (mlp_mode == 1) return true;
+    if (mlp_mode == 2) return false;
+    const int tiles = cdiv(rows, mlp::BM);
+    return tiles >= 16 && tiles <= 33;
 }
 
 // pw1 -> GELU -> pw2 -> layer-scale, residual, mask in ONE kernel (mlp_tc.cuh): a 4-CTA cluster per 128-row tile.
@@ -637,7 +644,7 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     if constexpr (std::is_same<T, float>::value) {
         Act a = ws_act((size_t)rows * c.C);
         dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-        if (mlp_fusable(c)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr);
+        if (mlp_fusable(c, rows)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr);
         else {
             Act hid = ws_act((size_t)rows * c.H);
             gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
@@ -1093,7 +1100,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
-        { const char* e = getenv("STC_MLP"); hd->force_unfused_mlp = e && std::string(e) == "unfused"; }
+        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : 0; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
@@ -1599,6 +1606,73 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         h->ensure_ws(body);
         body();
         // the temporary weights stay owned by the handle until it is destroyed (debug entry point: acceptable)
+    })
+}
+
+int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_unfused, float* max_abs_err) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (!h->tc_mode() || M <= 0 || iters <= 0) throw StcError(STC_ERR_INVALID, "stc_debug_mlp: bad argument");
+        const int C = mlp::C, H = mlp::H;
+        uint64_t z = 777;
+        auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
+        std::vector<float> w1((size_t)C * H), b1(H), w2((size_t)H * C), b2(C), gm(C);
+        for (auto& v : w1) v = rnd() / 16.f * 1.7f;
+        for (auto& v : w2) v = rnd() / 32.f * 1.7f;
+        for (auto& v : b1) v = rnd() * 0.1f;
+        for (auto& v : b2) v = rnd() * 0.1f;
+        for (auto& v : gm) v = 0.1f + rnd() * 0.02f;
+        ConvNeXt cn{};
+        cn.C = C; cn.H = H; cn.pw1 = h->make_linear_host(w1, b1, C, H, true); cn.pw2 = h->make_linear_host(w2, b2, H, C, true);
+        cn.gamma = h->upload_f32(gm.data(), gm.size());
+        auto body = [&]() {
+            h->arena.reset(); h->h_stage_off = 0;
+            float* A = h->ws<float>((size_t)M * C); float* X0 = h->ws<float>((size_t)M * C);
+            float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
+            float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
+            Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
+            if (h->dry) return;
+            debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
+            debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
+            fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
+            fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
+            fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
+            h->to_act(A, (size_t)M * C, a);
+            auto fused = [&](float* x) { h->fused_mlp(a, M, cn, x, mask); };
+            auto unfused = [&](float* x) {
+                Epilogue e1; e1.gelu = 1;
+                Epilogue e2; e2.scale = cn.gamma; e2.resid = x; e2.mask = mask;
+                h->gemm(a, M, cn.pw1, e1, nullptr, &hid, H);
+                h->gemm(hid, M, cn.pw2, e2, x, nullptr, C);
+            };
+            STC_CUDA(cudaMemcpyAsync(Xa, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
+            STC_CUDA(cudaMemcpyAsync(Xb, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
+            fused(Xa); unfused(Xb);
+            debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(Xa, Xb, (size_t)M * C, err);
+            float out_ms[2] = {0, 0};
+            for (int which = 0; which < 2; ++which) {
+                cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+                cudaEvent_t e0 = h->pool_event(), e1 = h->pool_event();
+                STC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                for (int it = 0; it < iters; ++it) { if (which == 0) fused(Xa); else unfused(Xb); }
+                STC_CUDA(cudaStreamEndCapture(h->stream, &graph));
+                STC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+                STC_CUDA(cudaGraphLaunch(exec, h->stream));
+                cudaEventRecord(e0, h->stream);
+                STC_CUDA(cudaGraphLaunch(exec, h->stream));
+                cudaEventRecord(e1, h->stream);
+                STC_CUDA(cudaStreamSynchronize(h->stream));
+                cudaEventElapsedTime(&out_ms[which], e0, e1);
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+            }
+            h->check_launch("stc_debug_mlp");
+            if (ms_fused) *ms_fused = out_ms[0] / iters;
+            if (ms_unfused) *ms_unfused = out_ms[1] / iters;
+            if (max_abs_err) STC_CUDA(cudaMemcpy(max_abs_err, err, 4, cudaMemcpyDeviceToHost));
+            h->ev_next = 0;
+        };
+        h->ensure_ws(body);
+        body();
     })
 }
 

@@ -236,11 +236,11 @@ def test_error_paths(rig):
     assert eng.launches > 0
 
 
-@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused")])
+@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP", "fused")])
 def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
     """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
-    fp32 core. STC_MLP=unfused: the 4-CTA-cluster fused ConvNeXt MLP (mlp_tc.cuh, DSMEM reduction) against pw1 / pw2 as two
-    GEMMs. Same weights, text encoder (self + style attention, rotary) and one vector-estimator step (length-aware rotary
+    fp32 core. STC_MLP=fused / unfused: the 4-CTA-cluster fused ConvNeXt MLP (mlp_tc.cuh, DSMEM reduction) forced on or off
+    against the library's own choice (fused only where its clusters fit one wave). Same weights, text encoder (self + style attention, rotary) and one vector-estimator step (length-aware rotary
     cross-attention with a masked key tail, 50-key style attention, ragged rows incl. a partial last tile)."""
     import os
     if rig["name"] != "full":
