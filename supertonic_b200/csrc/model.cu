@@ -3,6 +3,7 @@
 // What it replaces in the reference: the four Ort::Session objects (cpp/helper.cpp:784-795) and their
 // Run calls inside TextToSpeech::_infer (:512-523 DP, :545-556 TE, :620-647 VE step, :662-672 vocoder),
 // plus the host-side latent bookkeeping between them (:424-467, :590-659).
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1408,7 +1409,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             STC_CUDA(cudaStreamWaitEvent(st, h->ev_te, 0));            // everything after this point on the main stream sees text_emb
         }
         if (h->profile) cudaEventRecord(h->ev[2], st);
+        const auto t_host0 = std::chrono::steady_clock::now();
         STC_CUDA(cudaEventSynchronize(h->ev[6]));                 // the one data-dependent sync: duration -> L
+        const auto t_host1 = std::chrono::steady_clock::now();
         int L = latent_len_f32(h->h_dur, B, c.sample_rate, c.chunk_size);
         if (L_out) *L_out = L;
         if (duration_out && host_io) memcpy(duration_out, h->h_dur, sizeof(float) * B);
@@ -1452,6 +1455,12 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         };
         h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
                                 pin, host_io ? 0 : (uintptr_t)wav_out}, stage2);
+        if (getenv("STC_TIMING")) {
+            const auto t_host2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[stc timing] wait for durations %.1f us, host work until stage-2 launch returned %.1f us\n",
+                    std::chrono::duration<double, std::micro>(t_host1 - t_host0).count(),
+                    std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
+        }
         if (h->profile) cudaEventRecord(h->ev[4], st);
         if (host_io) {
             if (packed) {
