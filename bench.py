@@ -128,7 +128,7 @@ def main():
     cfg = {"workload": f"configs[1]: batch {a.batch} mixed-length English utterances (chars uniform 20..300, seed 1234), "
                        f"total_step={a.total_step}, speed=1.05, per GPU", "weights": "surrogate full-size graphs (random init, seed 0)",
            "l2": "flushed (512 MiB write) between timed steps", "parallelism": f"replicas x{world}, utterance-sharded, no collective",
-           "layout": "latent side packed (no padded frames); text side one [B,T_max] rectangle"}
+           "layout": "latent frames and text tokens both as packed rows (no padded frames or tokens are computed)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -186,6 +186,7 @@ def main():
         buckets.append(dict(B=len(g), T=Tg, cap=cap,
                             ids=torch.from_numpy(np.ascontiguousarray(ids[g, :Tg])).cuda(),
                             mask=torch.from_numpy(np.ascontiguousarray(mask[g, :, :Tg])).cuda(),
+                            lens=np.ascontiguousarray(lens[g], dtype=np.int32),
                             ttl=torch.from_numpy(np.ascontiguousarray(style.ttl[g])).cuda(),
                             dp=torch.from_numpy(np.ascontiguousarray(style.dp[g])).cuda(),
                             wav=torch.empty(cap, dtype=torch.float32, device="cuda"),
@@ -194,7 +195,8 @@ def main():
     def device_step(seed):
         for b in buckets:
             off = eng.synthesize_packed_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(),
-                                               b["B"], b["T"], a.total_step, 1.05, seed, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr())
+                                               b["B"], b["T"], a.total_step, 1.05, seed, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr(),
+                                               text_lens=b["lens"])
             b["L"] = int(off[-1] // cs)
 
     for w in range(a.warmup):
@@ -256,7 +258,7 @@ def main():
         stage = dict(dp=0.0, te=0.0, ve=0.0, vocoder=0.0, whole=0.0)
         for b in buckets:
             eng.synthesize_packed_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(), b["B"], b["T"],
-                                         a.total_step, 1.05, 7, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr())
+                                         a.total_step, 1.05, 7, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr(), text_lens=b["lens"])
             for k, v in eng.kernel_profile().items():
                 for kk in v:
                     prof[k][kk] += v[kk]

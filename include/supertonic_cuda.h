@@ -119,7 +119,8 @@ int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const floa
                           float* duration_dev, int64_t* L_out);
 
 /* Throughput variant: the latent side runs on PACKED rows (utterance b owns ceil(wav_len_b/cs) frames, the integer
- * formula of getLatentMask, cpp/helper.cpp:767) — no padded frames are computed. Results on every utterance's valid
+ * formula of getLatentMask, cpp/helper.cpp:767) and the text side on packed tokens (the mask rows must be the prefix masks
+ * of lengthToMask, cpp/helper.cpp:740-757) — no padded frames or tokens are computed. Results on every utterance's valid
  * region equal the rectangle variant (utterances are independent; tests: batch-composition invariance).
  *   wav_out: packed floats, utterance b at [wav_offsets_out[b], wav_offsets_out[b+1]) = frames_b*cs samples, of which the
  *            first wav_lengths_out[b] are the utterance (what cpp/example_onnx.cpp:104-109 keeps); wav_cap in floats.
@@ -129,10 +130,12 @@ int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* t
                           const float* noise, int64_t noise_ld, uint64_t seed,
                           float* wav_out, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out,
                           int64_t* wav_lengths_out, float* latent_out);
+/* text_lens (HOST int32[B], optional): token count of every utterance (= sum of its mask row); lets the text side run on
+ * packed rows too. NULL -> the text side is computed on the padded [B,T] rectangle. */
 int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev,
-                                 const float* style_ttl_dev, const float* style_dp_dev, int B, int T,
-                                 int total_step, float speed, uint64_t seed, float* wav_dev, int64_t wav_cap,
-                                 int64_t* wav_offsets_out, float* duration_dev);
+                                 const float* style_ttl_dev, const float* style_dp_dev, const int32_t* text_lens,
+                                 int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
+                                 int64_t wav_cap, int64_t* wav_offsets_out, float* duration_dev);
 
 /* ---- page-locked host buffers (optional) ------------------------------------------------------ */
 

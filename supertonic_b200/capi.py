@@ -45,7 +45,7 @@ _SIGS = {
     "stc_synthesize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_synthesize_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
-    "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
+    "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_pinned_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "stc_pinned_free": (None, [_vp]),
     "stc_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
@@ -291,10 +291,13 @@ class Engine:
         return res
 
     def synthesize_packed_device(self, ids_ptr: int, mask_ptr: int, sttl_ptr: int, sdp_ptr: int, B: int, T: int, total_step: int,
-                                 speed: float, seed: int, wav_ptr: int, wav_cap: int, dur_ptr: int) -> np.ndarray:
-        """Device-resident packed variant; returns wav offsets [B+1] (floats). StcError(code=-5).need holds the size to retry with."""
+                                 speed: float, seed: int, wav_ptr: int, wav_cap: int, dur_ptr: int,
+                                 text_lens: Optional[np.ndarray] = None) -> np.ndarray:
+        """Device-resident packed variant; returns wav offsets [B+1] (floats). StcError(code=-5).need holds the size to retry with.
+        text_lens: host int32[B] token counts (packs the text side too)."""
         off = np.zeros((B + 1,), np.int64)
-        rc = lib.stc_synthesize_packed_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, B, T, int(total_step), float(speed),
+        tl = None if text_lens is None else _cf(text_lens, np.int32)
+        rc = lib.stc_synthesize_packed_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, _ptr(tl), B, T, int(total_step), float(speed),
                                               seed, wav_ptr, wav_cap, _ptr(off), dur_ptr)
         if rc != STC_OK:
             e = StcError(rc, lib.stc_last_error(self._h).decode())

@@ -82,30 +82,39 @@ struct OutSplit {
     }
 };
 
-// ---- embedding: out[row,:] = emb[ids[row],:] * mask[row]  (Gather -> Transpose -> Mul) ---------
+// ---- embedding: out[row,:] = emb[ids[b, t],:] * mask[row]  (Gather -> Transpose -> Mul) ---------
+// rows are packed sequences (row = off[b] + t) over the caller's [B, T] id rectangle; mask (per row) may be null.
 template <typename T>
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
-                             const float* __restrict__ mask, T* __restrict__ out, int rows, int C, int V) {
+                             const float* __restrict__ mask, T* __restrict__ out, int rows, int C, int V,
+                             const int* __restrict__ off, int B, int Tn) {
     pdl_trigger(); pdl_wait();
     int row = blockIdx.x * blockDim.y + threadIdx.y;
     if (row >= rows) return;
-    int64_t id = ids[row];
+    const int b = find_seq(off, B, row);
+    if (b < 0) {                                       // bucket padding row
+        for (int c = threadIdx.x; c < C; c += 32) out[(size_t)row * C + c] = (T)0;
+        return;
+    }
+    int64_t id = ids[(size_t)b * Tn + (row - __ldg(off + b))];
     if (id < 0 || id >= V) id = 0;
-    T m = (T)mask[row];
+    T m = mask ? (T)mask[row] : (T)1;
     for (int c = threadIdx.x; c < C; c += 32) out[(size_t)row * C + c] = (T)emb[(size_t)id * C + c] * m;
 }
 
 // ---- x[row,:] = (x[row,:] + v[b,:]) * mask[row]   (style add in DP, time conditioning in VE) -----
 template <typename T>
 __global__ void add_rowvec_mask_kernel(T* __restrict__ x, const T* __restrict__ v, const float* __restrict__ mask,
-                                       int rows, int N, int C, int vstride) {
+                                       int rows, int C, int vstride, const int* __restrict__ off, int B) {
     pdl_trigger(); pdl_wait();
-    // vstride = C: one vector per sequence of a [B,N] rectangle; vstride = 0: one vector for every row
+    // vstride = C: one vector per sequence (row -> b through the packed offsets); vstride = 0: one vector for every row
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * C) return;
     int row = (int)(i / C), c = (int)(i % C);
+    int b = 0;
+    if (vstride) { b = find_seq(off, B, row); if (b < 0) return; }
     T m = mask ? (T)mask[row] : (T)1;
-    x[i] = (x[i] + v[(size_t)(vstride ? row / N : 0) * vstride + c]) * m;
+    x[i] = (x[i] + v[(size_t)b * vstride + c]) * m;
 }
 
 // ---- depthwise conv1d (+bias) -> LayerNorm over C, one warp per row ------------------------------
@@ -625,14 +634,15 @@ __global__ void voc_im2col_kernel(const float* __restrict__ lat, const float* __
 template <int CPL>
 __global__ void dp_head_kernel(const double* __restrict__ x, const float* __restrict__ g, const float* __restrict__ beta,
                                const float* __restrict__ w, const float* __restrict__ wb, const float* __restrict__ mask,
-                               float* __restrict__ dur, int N, float eps, float clip, float spt) {
+                               float* __restrict__ dur, const int* __restrict__ off, float eps, float clip, float spt) {
     pdl_trigger(); pdl_wait();
     constexpr int C = CPL * 32;
     __shared__ double part[32];
     int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int base = __ldg(off + b), N = __ldg(off + b + 1) - base;
     double acc = 0.0;
     for (int n = warp; n < N; n += nw) {
-        const double* xr = x + ((size_t)b * N + n) * C;
+        const double* xr = x + ((size_t)base + n) * C;
         double y[CPL], s = 0;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) { y[i] = xr[lane + 32 * i]; s += y[i]; }
@@ -644,7 +654,7 @@ __global__ void dp_head_kernel(const double* __restrict__ x, const float* __rest
         for (int i = 0; i < CPL; ++i) { int c = lane + 32 * i; dot += (y[i] / den * (double)g[c] + (double)beta[c]) * (double)w[c]; }
         dot = warp_sum<double>(dot) + (double)wb[0];
         dot = fmin(fmax(dot, -(double)clip), (double)clip);
-        acc += exp(dot) * (double)spt * (double)mask[(size_t)b * N + n];
+        acc += exp(dot) * (double)spt * (mask ? (double)mask[(size_t)base + n] : 1.0);
     }
     if (lane == 0) part[warp] = acc;
     __syncthreads();

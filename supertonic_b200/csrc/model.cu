@@ -46,9 +46,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct GraphKey {
     int stage, mode, B, T, rows, maxlen, steps; int64_t noise_ld; uintptr_t p0, p1;
+    int trows = 0, tmaxlen = 0;         // packed text side: launched rows / longest-sequence bound (0: rectangle)
     bool operator<(const GraphKey& o) const {
-        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1) <
-               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1);
+        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1, trows, tmaxlen) <
+               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1, o.trows, o.tmaxlen);
     }
 };
 
@@ -176,8 +177,9 @@ struct Handle {
     const float* time_vectors(float cur, float tot);
 
     // ---- graph walkers (device pointers)
-    void run_dp(const int64_t* ids, const float* style_dp, const float* mask, int B, int T, float* dur);
-    void run_te(const int64_t* ids, const float* style_ttl, const float* mask, int B, int T, float* text_emb_cl);
+    // `seq`: the text tokens as packed rows (fast layer: only real tokens) or as the reference's [B,T] rectangle + row mask
+    void run_dp(const int64_t* ids, const float* style_dp, const Seq& seq, int T, float* dur);
+    void run_te(const int64_t* ids, const float* style_ttl, const Seq& seq, int T, float* text_emb_cl);
     void prepare_ve(VeCtx& vc, const float* text_emb_cl, const float* style_ttl);
     void run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const float* dtvec);
     void run_vocoder(const float* lat_cl, const Seq& lat, float* wav);
@@ -496,7 +498,7 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             // rows per block: as many as keep >= 2 blocks per SM in flight (shared-memory tile = (R + span) rows)
             const int span = (K - 1) * dil;
             int R = std::min(32, (int)(100 * 1024 / (C * sizeof(float))) - span) / 8 * 8;       // <= 100 KB: two blocks per SM
-            while (R > 8 && (int)cdiv(rows, R) < 2 * h->num_sms) R -= 8;
+            while (R > 8 && (int)cdiv(rows, R) < 4 * h->num_sms) R -= 8;
             const size_t smem = (size_t)(std::max(R, 8) + span) * C * sizeof(float);
             if (R >= 8 && smem <= 200 * 1024) {
                 dim3 tg(cdiv(rows, R));
@@ -822,35 +824,35 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, siz
     if (i < n) out[i] = (TO)in[i];
 }
 
-void Handle::run_dp(const int64_t* ids, const float* style_dp, const float* mask, int B, int T, float* dur) {
+void Handle::run_dp(const int64_t* ids, const float* style_dp, const Seq& seq, int T, float* dur) {
     // duration_predictor.onnx evaluated in fp64 (reference call site cpp/helper.cpp:512-526)
     size_t mk = mark();
-    int C = dp.C, rows = B * T, si = dp_arch.at("style_in");
-    Seq seq = rect_seq(B, T, mask, false);
+    const int C = dp.C, rows = seq.rows, B = seq.B, si = dp_arch.at("style_in");
+    const float* mask = seq.mask;
     double* x = ws<double>((size_t)rows * C);
-    STC_LAUNCH(this, embed_kernel<double>, cdiv(rows, 8), dim3(32, 8), 0, ids, dp.vec["embed"], mask, x, rows, C, cfg.vocab_size);
+    STC_LAUNCH(this, embed_kernel<double>, cdiv(rows, 8), dim3(32, 8), 0, ids, dp.vec["embed"], mask, x, rows, C, cfg.vocab_size, seq.off, B, T);
     double* sd = ws<double>((size_t)B * si); double* s = ws<double>((size_t)B * C);
     STC_LAUNCH(this, (cast_kernel<float, double>), cdiv((size_t)B * si, 256), 256, 0, style_dp, sd, (size_t)B * si);
     const Linear& ls = dp.lin.back();
     Epilogue es; es.bias = ls.bias;
     gemm_simt<double>(sd, si, B, ls, es, s, C);
-    STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, T, C, C);
+    STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, C, C, seq.off, B);
     for (const Layer& l : dp.layers)
         if (l.type == L_CONVNEXT) convnext<double>(dp.cn[l.idx], x, seq);
     float clip = dp_arch.at("clip"), spt = dp_arch.at("sec_per_token");
-    if (C == 64) STC_LAUNCH(this, dp_head_kernel<2>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
-    else if (C == 32) STC_LAUNCH(this, dp_head_kernel<1>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, T, 1e-6f, clip, spt);
+    if (C == 64) STC_LAUNCH(this, dp_head_kernel<2>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, seq.off, 1e-6f, clip, spt);
+    else if (C == 32) STC_LAUNCH(this, dp_head_kernel<1>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, seq.off, 1e-6f, clip, spt);
     else throw StcError(STC_ERR_UNSUPPORTED, "duration predictor width");
     release(mk);
 }
 
-void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mask, int B, int T, float* text_emb_cl) {
-    // text_encoder.onnx (reference call site cpp/helper.cpp:545-556); output kept channels-last [B*T, C]
+void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq, int T, float* text_emb_cl) {
+    // text_encoder.onnx (reference call site cpp/helper.cpp:545-556); output kept channels-last [rows, C]
     size_t mk = mark();
-    int C = te.C, rows = B * T, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim;
-    Seq tseq = rect_seq(B, T, mask, true), sseq = rect_seq(B, S, nullptr, false);
+    const int C = te.C, rows = tseq.rows, B = tseq.B, S = cfg.style_ttl_tokens, Cs = cfg.style_ttl_dim;
+    Seq sseq = rect_seq(B, S, nullptr, false);
     float* x = ws<float>((size_t)rows * C);
-    STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], mask, x, rows, C, cfg.vocab_size);
+    STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], tseq.mask, x, rows, C, cfg.vocab_size, tseq.off, B, T);
     Act sty = ws_act((size_t)B * S * Cs);
     to_act(style_ttl, (size_t)B * S * Cs, sty);
     for (const Layer& l : te.layers) {
@@ -862,7 +864,7 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const float* mas
         } else if (l.type == L_PROJ_OUT) {
             Act xa = ws_act((size_t)rows * C);
             to_act(x, (size_t)rows * C, xa);
-            Epilogue e; e.mask = mask;
+            Epilogue e; e.mask = tseq.mask;
             gemm(xa, rows, te.lin[l.idx], e, text_emb_cl, nullptr, te.lin[l.idx].N);
         }
     }
@@ -942,7 +944,7 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
             case L_CONVNEXT: convnext<float>(ve.cn[l.idx], x, ls); break;
             case L_TIME_COND:
                 STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, tvec + (size_t)(itc++) * C, ls.mask,
-                           rows, 1, C, 0);
+                           rows, C, 0, ls.off, ls.B);
                 break;
             case L_ATTN: {
                 const Attention& a = ve.at[l.idx];
@@ -1208,7 +1210,7 @@ int stc_duration(stc_handle* sh, const int64_t* text_ids, const float* style_dp,
             float* d_sty = up(h, style_dp, (size_t)B * si);
             float* d_mask = up(h, text_mask, (size_t)B * T);
             float* d_dur = h->ws<float>(B);
-            h->run_dp(d_ids, d_sty, d_mask, B, T, d_dur);
+            h->run_dp(d_ids, d_sty, h->rect_seq(B, T, d_mask, false), T, d_dur);
             if (!h->dry) STC_CUDA(cudaMemcpyAsync(duration_out, d_dur, B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         };
         h->ensure_ws(body);
@@ -1232,7 +1234,7 @@ int stc_text_encode(stc_handle* sh, const int64_t* text_ids, const float* style_
             float* d_mask = up(h, text_mask, (size_t)B * T);
             float* d_cl = h->ws<float>((size_t)B * T * C);
             float* d_ncl = h->ws<float>((size_t)B * T * C);
-            h->run_te(d_ids, d_sty, d_mask, B, T, d_cl);
+            h->run_te(d_ids, d_sty, h->rect_seq(B, T, d_mask, true), T, d_cl);
             transpose(h, d_cl, d_ncl, B, T, C);                       // [B,T,C] -> [B,C,T] (reference layout)
             if (!h->dry) STC_CUDA(cudaMemcpyAsync(text_emb_out, d_ncl, (size_t)B * T * C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         };
@@ -1347,7 +1349,7 @@ extern "C" {
 static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
                       const float* style_dp, int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld,
                       uint64_t seed, float* wav_out, int64_t wav_cap, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
-                      float* latent_out, int64_t* wav_offsets_out) {
+                      float* latent_out, int64_t* wav_offsets_out, const int32_t* text_lens) {
     STC_TRY(sh, {
         const bool host_io = mode & 1, packed = mode & 2;
         Scope sc(sh); Handle* h = sc.h;
@@ -1366,6 +1368,34 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.exec);     // graphs captured the old pinned addresses
             h->graphs.clear();
         }
+        // Text side: only the real tokens are computed (packed rows) when the token counts are known on the host — from the
+        // mask itself (host I/O; it must be the prefix mask the reference builds, cpp/helper.cpp:740-757) or from `text_lens`
+        // (device-resident inputs). Otherwise the reference's padded [B,T] rectangle + row mask.
+        std::vector<int> tlens;
+        if (packed) {
+            tlens.resize(B);
+            bool ok = true;
+            for (int b = 0; b < B && ok; ++b) {
+                if (host_io) {
+                    int cnt = 0, last = 0;
+                    for (int t = 0; t < T; ++t) if (text_mask[(size_t)b * T + t] != 0.f) { ++cnt; last = t + 1; }
+                    tlens[b] = cnt; ok = cnt == last && cnt > 0;
+                } else { ok = text_lens && text_lens[b] > 0 && text_lens[b] <= T; if (ok) tlens[b] = text_lens[b]; }
+            }
+            if (!ok) tlens.clear();
+        }
+        const bool tpacked = !tlens.empty();
+        int trows = 0, tmaxlen = 0;
+        if (tpacked) {
+            int sum = 0, mx = 0;
+            for (int v : tlens) { sum += v; mx = std::max(mx, v); }
+            trows = h->use_graphs && !h->profile ? (sum + 127) / 128 * 128 : sum;
+            tmaxlen = (mx + 15) / 16 * 16;
+        }
+        auto text_seq = [&](const float* d_mask, bool want_len) {
+            return tpacked ? h->packed_seq(tlens, trows, tmaxlen) : h->rect_seq(B, T, d_mask, want_len);
+        };
+        const size_t text_rows = tpacked ? (size_t)trows : (size_t)B * T;
         cudaStream_t st = h->stream;
         for (auto& k : h->kprof) k = Handle::KProf{};
         for (int s = 0; s < total_step; ++s) h->time_vectors((float)s, (float)total_step);     // cached after the first call
@@ -1380,8 +1410,8 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
                 d_ids = upp(h, text_ids, (size_t)B * T); d_tmask = upp(h, text_mask, (size_t)B * T);
                 d_sttl = upp(h, style_ttl, (size_t)B * S * Cs); d_sdp = upp(h, style_dp, (size_t)B * si);
             } else { d_ids = text_ids; d_tmask = text_mask; d_sttl = style_ttl; d_sdp = style_dp; }
-            d_dur = h->ps<float>(B); d_wavlen = h->ps<int64_t>(B); d_temb = h->ps<float>((size_t)B * T * C);
-            h->run_dp(d_ids, d_sdp, d_tmask, B, T, d_dur);
+            d_dur = h->ps<float>(B); d_wavlen = h->ps<int64_t>(B); d_temb = h->ps<float>(text_rows * C);
+            h->run_dp(d_ids, d_sdp, text_seq(d_tmask, false), T, d_dur);
             STC_LAUNCH(h, dur_post_kernel, cdiv(B, 128), 128, 0, d_dur, d_wavlen, B, speed, c.sample_rate);
             if (!h->dry) {
                 STC_CUDA(cudaMemcpyAsync(h->h_dur, d_dur, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
@@ -1390,19 +1420,19 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         };
         auto stage1b = [&]() {
             h->arena.reset();
-            h->run_te(d_ids, d_sttl, d_tmask, B, T, d_temb);      // overlaps the D2H of the durations
+            h->run_te(d_ids, d_sttl, text_seq(d_tmask, true), T, d_temb);      // overlaps the D2H of the durations
         };
         uint32_t speed_bits; memcpy(&speed_bits, &speed, 4);
         if (h->profile) cudaEventRecord(h->ev[0], st);
         // duration predictor on the main stream (behind the input uploads), text encoder concurrently on stream2 with its own
         // workspace: the two are independent (cpp/helper.cpp:512-556 runs them back to back) and DP alone leaves the GPU idle
-        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0}, stage1a, h->ev_in);
+        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in);
         if (h->profile) cudaEventRecord(h->ev[1], st);
         cudaEventRecord(h->ev[6], st);
         {
             STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
-            try { h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0}, stage1b); }
+            try { h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0, trows, tmaxlen}, stage1b); }
             catch (...) { std::swap(h->stream, h->stream2); h->arena.swap(h->arena2); throw; }
             cudaEventRecord(h->ev_te, h->stream);
             std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
@@ -1443,7 +1473,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             if (noise) d_noise = up(h, noise, (size_t)B * D * noise_ld);
             d_xlat = h->ws<float>((size_t)rows * D);
             d_wav = host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
-            Seq text = h->rect_seq(B, T, d_tmask, true), lat;
+            Seq text = text_seq(d_tmask, true), lat;
             if (packed) lat = h->packed_seq(lens, (int)rows, maxlen_launch);
             else {
                 d_lmask = h->ws<float>((size_t)B * L);
@@ -1454,7 +1484,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav);
         };
         h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
-                                pin, host_io ? 0 : (uintptr_t)wav_out}, stage2);
+                                pin, host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}, stage2);
         if (getenv("STC_TIMING")) {
             const auto t_host2 = std::chrono::steady_clock::now();
             fprintf(stderr, "[stc timing] wait for durations %.1f us, host work until stage-2 launch returned %.1f us\n",
@@ -1496,14 +1526,14 @@ int stc_synthesize(stc_handle* h, const int64_t* text_ids, const float* text_mas
                    int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld, uint64_t seed, float* wav_out,
                    int64_t wav_ld, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out, float* latent_out) {
     return synth_impl(h, 1, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_ld,
-                      duration_out, wav_lengths_out, L_out, latent_out, nullptr);
+                      duration_out, wav_lengths_out, L_out, latent_out, nullptr, nullptr);
 }
 
 int stc_synthesize_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,
                           const float* style_dp_dev, int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
                           int64_t wav_ld, float* duration_dev, int64_t* L_out) {
     return synth_impl(h, 0, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
-                      wav_dev, wav_ld, duration_dev, nullptr, L_out, nullptr, nullptr);
+                      wav_dev, wav_ld, duration_dev, nullptr, L_out, nullptr, nullptr, nullptr);
 }
 
 int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl, const float* style_dp,
@@ -1511,14 +1541,14 @@ int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* t
                           float* wav_out, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out, int64_t* wav_lengths_out,
                           float* latent_out) {
     return synth_impl(h, 3, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_cap,
-                      duration_out, wav_lengths_out, nullptr, latent_out, wav_offsets_out);
+                      duration_out, wav_lengths_out, nullptr, latent_out, wav_offsets_out, nullptr);
 }
 
 int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,
-                                 const float* style_dp_dev, int B, int T, int total_step, float speed, uint64_t seed, float* wav_dev,
-                                 int64_t wav_cap, int64_t* wav_offsets_out, float* duration_dev) {
+                                 const float* style_dp_dev, const int32_t* text_lens, int B, int T, int total_step, float speed,
+                                 uint64_t seed, float* wav_dev, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_dev) {
     return synth_impl(h, 2, text_ids_dev, text_mask_dev, style_ttl_dev, style_dp_dev, B, T, total_step, speed, nullptr, 0, seed,
-                      wav_dev, wav_cap, duration_dev, nullptr, nullptr, nullptr, wav_offsets_out);
+                      wav_dev, wav_cap, duration_dev, nullptr, nullptr, nullptr, wav_offsets_out, text_lens);
 }
 
 // ---- debug / tuning: one tcgen05 GEMM of a given shape and launch configuration, timed and checked -----------------
