@@ -233,16 +233,29 @@ dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, 
             const float4 v = __ldg(reinterpret_cast<const float4*>(wb + c0 + j));
             y[j] = v.x; y[j + 1] = v.y; y[j + 2] = v.z; y[j + 3] = v.w;
         }
-        for (int k = 0; k < K; ++k) {
-            const int nn = n + k * dil - pad_left;
-            if (nn < 0 || nn >= N) continue;
-            const float* xr = x + ((size_t)base + nn) * C + c0;
-            const float* wr = wT + (size_t)k * C + c0;
+        // taps in groups of up to 4: all loads of a group are issued before the first FMA (independent 16-byte requests in
+        // flight per lane: the input is L2-resident, so the kernel is bound by load latency, not bandwidth)
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            float4 xv[4][CPL / 4];
+            bool ok[4];
 #pragma unroll
-            for (int j = 0; j < CPL; j += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xr + j);
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
-                y[j] += wv.x * xv.x; y[j + 1] += wv.y * xv.y; y[j + 2] += wv.z * xv.z; y[j + 3] += wv.w * xv.w;
+            for (int t = 0; t < 4; ++t) {
+                const int nn = n + (k0 + t) * dil - pad_left;
+                ok[t] = (k0 + t < K) && nn >= 0 && nn < N;
+                const float* xr = x + ((size_t)base + (ok[t] ? nn : n)) * C + c0;
+#pragma unroll
+                for (int j = 0; j < CPL / 4; ++j) xv[t][j] = *reinterpret_cast<const float4*>(xr + 4 * j);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (!ok[t]) continue;
+                const float* wr = wT + (size_t)(k0 + t) * C + c0;
+#pragma unroll
+                for (int j = 0; j < CPL / 4; ++j) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + 4 * j));
+                    y[4 * j] += wv.x * xv[t][j].x; y[4 * j + 1] += wv.y * xv[t][j].y;
+                    y[4 * j + 2] += wv.z * xv[t][j].z; y[4 * j + 3] += wv.w * xv[t][j].w;
+                }
             }
         }
     }

@@ -494,6 +494,8 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
     dim3 grid(cdiv(rows, 8)), block(256);
     if constexpr (std::is_same<T, float>::value) {
         // w is the tap-major transpose wT[K][C] for these widths (ConvNeXt::dw_wt)
+        // (measured: the shared-memory tiles also beat the direct warp-per-row kernel on the L2-resident VE / TE tensors:
+        //  12.97 vs 13.27 ms/step)
         if (K > 0 && (C == 128 || C == 256 || C == 512)) {
             // rows per block: as many as keep >= 2 blocks per SM in flight (shared-memory tile = (R + span) rows)
             const int span = (K - 1) * dil;
