@@ -161,6 +161,7 @@ struct Handle {
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
     bool mlp_fusable(const ConvNeXt& c, int rows) const;
     void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask);
+    int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
     int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" always, 2 "unfused" always (cross-checks)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
@@ -187,7 +188,8 @@ struct Handle {
     void check_launch(const char* what);
     void ensure_ws(const std::function<void()>& fn);
     void synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                    uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav);
+                    uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, bool with_vocoder);
+    cudaEvent_t ev_voc[4] = {};       // vocoder group g finished (its waveform may be copied out while group g+1 runs)
     std::map<std::pair<uint32_t, uint32_t>, float*> tvec_cache;
     int* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging for offset arrays
 };
@@ -233,6 +235,7 @@ Handle::~Handle() {
     if (stream2) cudaStreamDestroy(stream2);
     if (ev_in) cudaEventDestroy(ev_in);
     if (ev_te) cudaEventDestroy(ev_te);
+    for (auto& e : ev_voc) if (e) cudaEventDestroy(e);
 }
 
 void Handle::check_launch(const char* what) {
@@ -1105,11 +1108,13 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
+        { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : 0; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_te, cudaEventDisableTiming));
+        for (auto& e : hd->ev_voc) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& ev : hd->ev) STC_CUDA(cudaEventCreate(&ev));
         if (precision == STC_PREC_BF16X3) {
             void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
@@ -1327,7 +1332,7 @@ static int latent_len_f32(const float* dur, int B, int sr, int cs) {
 }
 
 void Handle::synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                        uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav) {
+                        uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, bool with_vocoder) {
     int D = cfg.latent_channels;
     std::vector<const float*> tv(steps);
     for (int s = 0; s < steps; ++s) tv[s] = time_vectors((float)s, (float)steps);
@@ -1340,7 +1345,10 @@ void Handle::synth_tail(const float* d_text_emb, const Seq& text, const float* d
     STC_LAUNCH(this, fill_kernel, cdiv(D, 128), 128, 0, d_dt, 1.0f / (float)steps, (size_t)D);
     for (int s = 0; s < steps; ++s) run_ve_step(vc, d_xlat, tv[s], d_dt);
     if (profile && !dry) cudaEventRecord(ev[3], stream);
-    run_vocoder(d_xlat, lat, d_wav);
+    if (with_vocoder) run_vocoder(d_xlat, lat, d_wav);
+    else if (dry && !restage) {         // measuring pass: reserve the workspace the (later, eager) vocoder passes will need
+        size_t m = mark(); run_vocoder(d_xlat, lat, d_wav); release(m);
+    }
 }
 
 }  // namespace stc
@@ -1468,6 +1476,23 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         }
         if (noise && noise_ld < (packed ? maxlen : L)) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length");
         // ---- stage 2: everything that depends on L
+        // Optional (env STC_VOC_GROUPS=2..4) for the host-I/O throughput path: the vocoder runs in utterance groups (eager launches
+        // behind the VE graph) and every group's waveform is copied out on the second stream while the next group is decoded.
+        // Measured on configs[1] (57 MB of waveform per step): e2e 15.8 ms/step with 4 groups against 14.7 ms with one pass —
+        // the four smaller passes lose more tensor-pipe efficiency than the hidden copy (1.1 ms) gains — so it is OFF by default.
+        std::vector<int> grp_end;      // utterance index where each vocoder group ends
+        if (h->voc_groups > 1 && host_io && packed && !h->profile && h->use_graphs && B >= 2 &&
+            R * c.chunk_size * (int64_t)sizeof(float) >= (int64_t(8) << 20)) {
+            const int G = std::min(h->voc_groups, B);
+            int64_t acc = 0; int g = 1;
+            for (int b = 0; b < B; ++b) {
+                acc += lens[b];
+                if (acc * G >= R * g && (int)grp_end.size() < G - 1 && b + 1 < B) { grp_end.push_back(b + 1); while (acc * G >= R * g) ++g; }
+            }
+            grp_end.push_back(B);
+            if (grp_end.size() < 2) grp_end.clear();
+        }
+        const bool chunked = !grp_end.empty();
         float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
         auto stage2 = [&]() {
             h->arena.reset();          // (the pinned offset staging keeps growing: stage-1 copies may still be in flight)
@@ -1483,9 +1508,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
                 lat = h->rect_seq(B, L, d_lmask, true);
                 if (latent_out) d_lat_ncl = h->ws<float>((size_t)B * L * D);
             }
-            h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav);
+            h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav, !chunked);
         };
-        h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
+        h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0) | (chunked ? 8 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
                                 pin, host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}, stage2);
         if (getenv("STC_TIMING")) {
             const auto t_host2 = std::chrono::steady_clock::now();
@@ -1494,7 +1519,27 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
                     std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
         }
         if (h->profile) cudaEventRecord(h->ev[4], st);
-        if (host_io) {
+        if (chunked) {
+            int b0 = 0; int64_t r0 = 0;
+            for (size_t g = 0; g < grp_end.size(); ++g) {
+                const int b1 = grp_end[g];
+                std::vector<int> gl(lens.begin() + b0, lens.begin() + b1);
+                int64_t rg = 0; int mg = 0;
+                for (int v : gl) { rg += v; mg = std::max(mg, v); }
+                const size_t m = h->mark();
+                Seq lg = h->packed_seq(gl, (int)rg, (mg + 15) / 16 * 16);
+                h->run_vocoder(d_xlat + r0 * D, lg, d_wav + r0 * c.chunk_size);
+                h->release(m);
+                STC_CUDA(cudaEventRecord(h->ev_voc[g], st));
+                STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_voc[g], 0));
+                STC_CUDA(cudaMemcpyAsync(wav_out + r0 * c.chunk_size, d_wav + r0 * c.chunk_size, (size_t)rg * c.chunk_size * sizeof(float),
+                                         cudaMemcpyDeviceToHost, h->stream2));
+                b0 = b1; r0 += rg;
+            }
+            STC_CUDA(cudaEventRecord(h->ev_te, h->stream2));
+            STC_CUDA(cudaStreamWaitEvent(st, h->ev_te, 0));
+            if (latent_out) STC_CUDA(cudaMemcpyAsync(latent_out, d_xlat, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        } else if (host_io) {
             if (packed) {
                 STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)R * c.chunk_size * sizeof(float), cudaMemcpyDeviceToHost, st));
                 if (latent_out) STC_CUDA(cudaMemcpyAsync(latent_out, d_xlat, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -302,3 +302,29 @@ def test_speed_and_long_form_chunks(rig):
         n = int(one["wav_lengths"][0])
         assert len(packed["wavs"][k]) == n
         assert U.snr_db(packed["wavs"][k], one["wav"][0, :n]) >= 90.0
+
+
+def test_chunked_vocoder_with_overlapped_copies_is_bit_identical(rig):
+    """STC_VOC_GROUPS=4: large host-I/O batches decode the vocoder in utterance groups and copy each group out while the next
+    one runs (stc_synthesize_packed, graphs on); the result must equal the single-pass eager path bit for bit."""
+    import os
+    os.environ["STC_VOC_GROUPS"] = "4"
+    try:
+        eng = rig["capi"].Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_VOC_GROUPS"]
+    ids, mask, ttl, dp = _inputs(rig, 120, 9, 200, 300)
+    nz = np.random.default_rng(13).standard_normal((9, 144, 420)).astype(np.float32)
+    eng.set_graphs(True)
+    a = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz, pinned=True)
+    wa = [w.copy() for w in a["wavs"]]
+    a2 = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz)          # replay, pageable destination
+    eng.set_graphs(False)
+    b = eng.synthesize_packed(ids, mask, ttl, dp, 2, 1.05, noise=nz)
+    eng.set_graphs(True)
+    assert sum(len(w) for w in wa) * 4 >= 8 << 20, "batch too small to trigger the chunked path"
+    np.testing.assert_array_equal(a["duration"], b["duration"])
+    for k in range(9):
+        np.testing.assert_array_equal(wa[k], b["wavs"][k])
+        np.testing.assert_array_equal(a2["wavs"][k], b["wavs"][k])
+    eng.close()
