@@ -40,6 +40,7 @@ struct Params {
     int M;
     const float* b1; const float* b2; const float* gamma; const float* mask;
     float* x;                       // [M, C] residual stream, updated in place
+    float* partial;                 // split variant: [CS][M rounded up to 128][C] fp32 partial outputs (reduced by mlp_reduce_kernel)
 };
 
 STC_DEVINL uint32_t mapa_u32(uint32_t local, uint32_t rank) {
@@ -49,11 +50,13 @@ STC_DEVINL void st_cluster_v4(uint32_t addr, float a, float b, float c, float d)
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                    const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
-                    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
-                    const Params p) {
+// kCluster: the four CTAs of a row tile form a cluster and reduce over DSMEM (needs all clusters resident in one wave: 33 fit
+// on a B200). !kCluster: four independent CTAs (blockIdx.x % 4 = hidden slice) write their partial outputs to global scratch
+// and mlp_reduce_kernel finishes the block — no placement constraint, 37 row tiles fill the 148 SMs.
+template <bool kCluster>
+STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo, const CUtensorMap& map_w1_hi,
+                                  const CUtensorMap& map_w1_lo, const CUtensorMap& map_w2_hi, const CUtensorMap& map_w2_lo,
+                                  const Params& p) {
     using namespace tc;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -67,8 +70,8 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const uint32_t tmem_slot = bar + 104;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int crank = (int)cluster_ctarank();
-    const int m0 = (int)cluster_id_x() * BM;
+    const int crank = kCluster ? (int)cluster_ctarank() : (int)(blockIdx.x % CS);
+    const int m0 = (kCluster ? (int)cluster_id_x() : (int)(blockIdx.x / CS)) * BM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
@@ -171,6 +174,37 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         tc_fence_after();
     }
 
+    if constexpr (!kCluster) {
+        // ===== split variant: partial O (all 256 columns) -> global scratch, coalesced through the per-warp staging =====
+        if (warp >= 2) {
+            const int q = warp & 3, half = (warp - 2) >> 2;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+            float* stg = reinterpret_cast<float*>(smem_gen + OFF_X) + (warp - 2) * 32 * EPI_PITCH;
+            const int sub = lane >> 2, cq = (lane & 3) * 4;
+            const size_t mpad = (size_t)((p.M + BM - 1) / BM) * BM;
+            float* dst = p.partial + ((size_t)crank * mpad + m0 + q * 32) * C + half * 128;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += EPI_CHUNK) {
+                uint32_t r16[16];
+                __syncwarp();
+                tmem_ld16(trow + half * 128 + c, r16);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j) = make_uint4(r16[j], r16[j + 1], r16[j + 2], r16[j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = i * 8 + sub;
+                    *reinterpret_cast<float4*>(dst + (size_t)rl * C + c + cq) = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp == 1) tmem_dealloc(tmem_base, 512);
+        return;
+    }
     // ===== cross-CTA reduction of the partial outputs (all threads take part in the cluster barriers) =====
     cluster_sync_all();                    // every CTA's weight ring is dead: it becomes the receive area
     if (warp >= 2) {
@@ -252,6 +286,44 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     __syncthreads();
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                    const Params p) {
+    convnext_mlp_body<true>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                          const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                          const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                          const Params p) {
+    convnext_mlp_body<false>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+// x <- ((p0 + p1 + p2 + p3 + b2) * gamma + x) * mask : the four hidden-slice partials in rank order (deterministic)
+__global__ void __launch_bounds__(256)
+mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
+                  const float* __restrict__ mask, float* __restrict__ x, int M) {
+    pdl_trigger(); pdl_wait();
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= (size_t)M * C) return;
+    const int row = (int)(i / C), col = (int)(i % C);
+    float4 acc = *reinterpret_cast<const float4*>(partial + i);
+#pragma unroll
+    for (int s = 1; s < CS; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + s * slice + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + col)), g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 r = *reinterpret_cast<const float4*>(x + i);
+    const float mk = mask ? __ldg(mask + row) : 1.f;
+    acc.x = ((acc.x + b.x) * g.x + r.x) * mk; acc.y = ((acc.y + b.y) * g.y + r.y) * mk;
+    acc.z = ((acc.z + b.z) * g.z + r.z) * mk; acc.w = ((acc.w + b.w) * g.w + r.w) * mk;
+    *reinterpret_cast<float4*>(x + i) = acc;
 }
 
 }  // namespace mlp

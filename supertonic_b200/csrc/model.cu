@@ -159,10 +159,10 @@ struct Handle {
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
-    bool mlp_fusable(const ConvNeXt& c, int rows) const;
-    void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask);
+    int mlp_form(const ConvNeXt& c, int rows) const;
+    void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, int form);
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
-    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" always, 2 "unfused" always (cross-checks)
+    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
@@ -616,31 +616,48 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
     return GemmCfg{bn, 1, 1};
 }
 
-// The fused kernel needs its 4-CTA clusters resident in ONE wave: B200 places 33 of them (GPCs of 16/18/20 SMs strand 16 SMs),
-// so at 34+ row tiles a second wave doubles its time. Measured (tools/mlp_sweep.py, profiles/r1i_mlp_sweep.txt): 2048 rows
-// 21.9 us fused vs 23.2 us as two GEMMs, 4224 rows 23.7 vs 29.1, 4736 rows (37 tiles) 42.6 vs 29.3 -> fused for 16..33 tiles.
-bool Handle::mlp_fusable(const ConvNeXt& c, int rows) const {
-    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps)) return false;
-    if (mlp_mode == 1) return true;
-    if (mlp_mode == 2) return false;
-    const int tiles = cdiv(rows, mlp::BM);
-    return tiles >= 16 && tiles <= 33;
+// Fused forms of the ConvNeXt MLP (mlp_tc.cuh) and where each pays (tools/mlp_sweep.py, profiles/r1o_mlp_sweep.txt):
+//   1 cluster : 4-CTA clusters + DSMEM reduction. All clusters must be resident in ONE wave and a B200 places only 33 of them
+//               (GPCs of 16/18/20 SMs strand 16 SMs): 34+ row tiles double its time.
+//   2 split   : four independent CTAs per row tile write partial outputs, a small kernel reduces them. Measured faster than the
+//               two GEMMs at every row count tried (128 rows 18.0 vs 20.3 us, 4736 rows 20.9 vs 30.1, 9600 rows 53.3 vs 56.0) and
+//               than the cluster form (4224 rows: 20.8 vs 23.7) -> the default.
+//   0 unfused : pw1 and pw2 as two GEMMs (other widths: vocoder C=512/H=2048, tiny config).
+int Handle::mlp_form(const ConvNeXt& c, int rows) const {
+    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps)) return 0;
+    if (mlp_mode == 1) return 1;
+    if (mlp_mode == 2) return 0;
+    if (mlp_mode == 3) return 2;
+    (void)rows;
+    return 2;
 }
 
-// pw1 -> GELU -> pw2 -> layer-scale, residual, mask in ONE kernel (mlp_tc.cuh): a 4-CTA cluster per 128-row tile.
-void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask) {
+void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, int form) {
     mlp::Params p{};
     p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
+    const int tiles = cdiv(rows, mlp::BM);
+    const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
+    const size_t mk = mark();
+    if (form == 2) p.partial = ws<float>(slice * mlp::CS);
     kprof_begin(0, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
         const CUtensorMap mah = tmap(a.hi, rows, c.C, mlp::BM), mal = tmap(a.lo, rows, c.C, mlp::BM);
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
         const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
-        launch_pdl(this, mlp::convnext_mlp_kernel, dim3(cdiv(rows, mlp::BM) * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                   mah, mal, w1h, w1l, w2h, w2l, p);
+        if (form == 1)
+            launch_pdl(this, mlp::convnext_mlp_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                       mah, mal, w1h, w1l, w2h, w2l, p);
+        else {
+            launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                       mah, mal, w1h, w1l, w2h, w2l, p);
+            launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
+                       (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows);
+            ++launches;
+        }
         ++launches;
     }
     kprof_end();
+    release(mk);
 }
 
 template <typename T>
@@ -652,7 +669,7 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     if constexpr (std::is_same<T, float>::value) {
         Act a = ws_act((size_t)rows * c.C);
         dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-        if (mlp_fusable(c, rows)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr);
+        if (const int form = mlp_form(c, rows)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr, form);
         else {
             Act hid = ws_act((size_t)rows * c.H);
             gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
@@ -1109,7 +1126,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
-        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : 0; }
+        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : 0; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
@@ -1126,6 +1143,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
         }
         {
             const int big = 200 * 1024;
@@ -1717,14 +1735,15 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
             float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
             Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
-            if (h->dry) return;
+            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS); return; }     // split form's scratch
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
-            auto fused = [&](float* x) { h->fused_mlp(a, M, cn, x, mask); };
+            const int form = h->mlp_mode == 3 ? 2 : 1;
+            auto fused = [&](float* x) { h->fused_mlp(a, M, cn, x, mask, form); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;
                 Epilogue e2; e2.scale = cn.gamma; e2.resid = x; e2.mask = mask;
