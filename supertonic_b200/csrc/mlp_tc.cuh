@@ -41,7 +41,13 @@ struct Params {
     const float* b1; const float* b2; const float* gamma; const float* mask;
     float* x;                       // [M, C] residual stream, updated in place
     float* partial;                 // split variant: [CS][M rounded up to 128][C] fp32 partial outputs (reduced by mlp_reduce_kernel)
+    // Producer mode (dw_wT != null; opt-in, measured slower — see Handle::mlp_producer): the a-tile is not loaded but COMPUTED
+    // here — depthwise conv (+bias) -> LayerNorm of the residual stream x, straight into the swizzled operand layout.
+    const float* dw_wT; const float* dw_b; const float* ln_g; const float* ln_b;     // taps [K][C], bias, LayerNorm scale / shift
+    const int* off; int B; int K, dil, pad_left; float eps;                          // packed sequences of x, conv geometry
 };
+
+constexpr int KMAX = 5;             // depthwise taps supported by the producer mode
 
 STC_DEVINL uint32_t mapa_u32(uint32_t local, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
@@ -76,7 +82,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
         tma_prefetch_desc(&map_w1_lo); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo);
-        mbar_init(bar_a, 1); mbar_init(bar_s1, 1); mbar_init(bar_o, 1);
+        mbar_init(bar_a, p.dw_wT ? 8 : 1); mbar_init(bar_s1, 1); mbar_init(bar_o, 1);
         for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int j = 0; j < HC / BK; ++j) mbar_init(bar_p(j), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,10 +96,12 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_expect_tx(bar_a, X_BYTES);
-            for (int kb = 0; kb < C / BK; ++kb) {
-                tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_a, kb * BK, m0);
-                tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
+            if (!p.dw_wT) {
+                mbar_expect_tx(bar_a, X_BYTES);
+                for (int kb = 0; kb < C / BK; ++kb) {
+                    tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_a, kb * BK, m0);
+                    tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
+                }
             }
             for (int u = 0; u < 2 * UNITS_PER_PHASE; ++u) {
                 const int s = u % SLOTS;
@@ -139,6 +147,79 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
             __syncwarp();
         }
     } else {
+        if (p.dw_wT) {
+            // ===== a-tile producer: warp w takes rows w-2, w+6, ... two at a time (both rows' taps in flight together);
+            //       lane owns channels [8 lane, 8 lane + 8) = one 16-byte chunk of k-block lane / 8 =====
+            const int c0 = lane * 8;
+            uint8_t* xa = smem_gen + OFF_X + (lane >> 3) * KBLK;
+            int bseq = -2;
+#pragma unroll 1
+            for (int rl = warp - 2; rl < BM; rl += 16) {
+                float4 xv[2][KMAX][2];
+                bool ok[2][KMAX];
+                int seq_ok[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int row = m0 + rl + 8 * u;
+                    int b = -1;
+                    if (row < p.M) {
+                        if (bseq == -2 || bseq < 0) b = find_seq(p.off, p.B, row);
+                        else { b = bseq; while (b < p.B && row >= __ldg(p.off + b + 1)) ++b; if (b >= p.B) b = -1; }
+                        bseq = b;
+                    }
+                    seq_ok[u] = b;
+                    const int base = b >= 0 ? __ldg(p.off + b) : 0, n = row - base, N = b >= 0 ? __ldg(p.off + b + 1) - base : 0;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        const int nn = n + k * p.dil - p.pad_left;
+                        ok[u][k] = b >= 0 && k < p.K && nn >= 0 && nn < N;
+                        const float* xr = p.x + ((size_t)base + (ok[u][k] ? nn : 0)) * C + c0;
+                        if (ok[u][k]) { xv[u][k][0] = *reinterpret_cast<const float4*>(xr); xv[u][k][1] = *reinterpret_cast<const float4*>(xr + 4); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = rl + 8 * u;
+                    float y[8];
+                    if (seq_ok[u] < 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] = 0.f;                      // rows past M / bucket padding: finite operand
+                    } else {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.dw_b + c0)), b1v = __ldg(reinterpret_cast<const float4*>(p.dw_b + c0 + 4));
+                        y[0] = b0.x; y[1] = b0.y; y[2] = b0.z; y[3] = b0.w; y[4] = b1v.x; y[5] = b1v.y; y[6] = b1v.z; y[7] = b1v.w;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            if (!ok[u][k]) continue;
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw_wT + (size_t)k * C + c0));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw_wT + (size_t)k * C + c0 + 4));
+                            y[0] += w0.x * xv[u][k][0].x; y[1] += w0.y * xv[u][k][0].y; y[2] += w0.z * xv[u][k][0].z; y[3] += w0.w * xv[u][k][0].w;
+                            y[4] += w1.x * xv[u][k][1].x; y[5] += w1.y * xv[u][k][1].y; y[6] += w1.z * xv[u][k][1].z; y[7] += w1.w * xv[u][k][1].w;
+                        }
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s += y[j];
+                        const float mean = warp_sum<float>(s) / (float)C;
+                        float v = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { y[j] -= mean; v += y[j] * y[j]; }
+                        const float den = sqrtf(warp_sum<float>(v) / (float)C + p.eps);
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0 + 4));
+                        const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0 + 4));
+                        y[0] = y[0] / den * g0.x + h0.x; y[1] = y[1] / den * g0.y + h0.y; y[2] = y[2] / den * g0.z + h0.z; y[3] = y[3] / den * g0.w + h0.w;
+                        y[4] = y[4] / den * g1.x + h1.x; y[5] = y[5] / den * g1.y + h1.y; y[6] = y[6] / den * g1.z + h1.z; y[7] = y[7] / den * g1.w + h1.w;
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) split_pair(y[2 * t], y[2 * t + 1], hi[t], lo[t]);
+                    uint8_t* dst = xa + (r >> 3) * 1024 + (r & 7) * 128 + (((lane & 7) ^ (r & 7)) * 16);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(dst + (C / BK) * KBLK) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a);
+        }
         // ===== epilogue 1: P = split(GELU(S + b1)) =====
         const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);

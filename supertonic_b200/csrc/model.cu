@@ -160,7 +160,11 @@ struct Handle {
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
     int mlp_form(const ConvNeXt& c, int rows) const;
-    void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, int form);
+    void fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form);
+    // env STC_MLP_PRODUCER=1: compute LayerNorm(dwconv(x)) inside the fused MLP kernel instead of a separate launch. Measured
+    // SLOWER (15.3 vs 11.5 ms/step): with 226 KB of shared memory in use the SM has no L1 left, so every tap row and every
+    // per-channel weight is re-fetched from L2 (~1.6 MB per CTA on top of the 0.5 MB of GEMM weights). OFF by default.
+    bool mlp_producer = false;
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
     int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
@@ -632,18 +636,23 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
     return 2;
 }
 
-void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, int form) {
+// a == nullptr: producer mode — the kernel computes LayerNorm(dwconv(x)) itself (needs seq, c.K <= mlp::KMAX).
+void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form) {
     mlp::Params p{};
     p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
+    if (!a) {
+        p.dw_wT = c.dw_wt; p.dw_b = c.dw_b; p.ln_g = c.ln_g; p.ln_b = c.ln_b; p.off = seq->off; p.B = seq->B;
+        p.K = c.K; p.dil = c.dil; p.pad_left = c.pad_left; p.eps = 1e-6f;
+    }
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
     if (form == 2) p.partial = ws<float>(slice * mlp::CS);
     kprof_begin(0, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
-        const CUtensorMap mah = tmap(a.hi, rows, c.C, mlp::BM), mal = tmap(a.lo, rows, c.C, mlp::BM);
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
         const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
+        const CUtensorMap mah = a ? tmap(a->hi, rows, c.C, mlp::BM) : w1h, mal = a ? tmap(a->lo, rows, c.C, mlp::BM) : w1l;   // unused in producer mode
         if (form == 1)
             launch_pdl(this, mlp::convnext_mlp_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                        mah, mal, w1h, w1l, w2h, w2l, p);
@@ -667,9 +676,15 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
     Epilogue e1; e1.gelu = 1;
     Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
+        const int form = mlp_form(c, rows);
+        if (form && mlp_producer && c.K <= mlp::KMAX) {
+            fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form);
+            release(mk);
+            return;
+        }
         Act a = ws_act((size_t)rows * c.C);
         dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-        if (const int form = mlp_form(c, rows)) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr, form);
+        if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form);
         else {
             Act hid = ws_act((size_t)rows * c.H);
             gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
@@ -1125,6 +1140,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
+        { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : 0; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
@@ -1743,7 +1759,7 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
             const int form = h->mlp_mode == 3 ? 2 : 1;
-            auto fused = [&](float* x) { h->fused_mlp(a, M, cn, x, mask, form); };
+            auto fused = [&](float* x) { h->fused_mlp(&a, M, cn, x, nullptr, mask, form); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;
                 Epilogue e2; e2.scale = cn.gamma; e2.resid = x; e2.mask = mask;
