@@ -15,8 +15,8 @@
 //                      O += P_j V_j (A = P_j [128 x 64 keys], B = V^T_j [64 d x 64 keys])
 //   warps 2-5: softmax — lane = query row: TMEM -> registers, max, exp2, sum, split to bf16 pairs, swizzled st.shared of P_j;
 //                      finally O / sum -> split-bf16 (or fp32) rows of the output.
-// Operands are prepared by attn_prep kernels (kernels below): Q/K as [rows, H*64] bf16 pairs (rotary embedding fused),
-// V transposed per (b, h) to [64, keys padded to 64] so that the PV product sees a K-major B operand.
+// Operands: Q/K as [rows, H*64] bf16 pairs written by the projection GEMMs (rotary embedding fused into their epilogue),
+// V transposed per (b, h) to [64, keys padded to 64] by v_prep_kernel so that the PV product sees a K-major B operand.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -237,46 +237,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 }
 
 // ---- operand preparation -----------------------------------------------------------------------------------------
-// Q / K: fp32 [rows, heads*64] -> rotary embedding (rotate-half; position n, or n / len[b] for the length-aware variant)
-// -> bf16 (hi, lo) pairs in the same layout. Thread = (row, head, pair of dims d, d+32 ... handled as 4 consecutive d).
-__global__ void __launch_bounds__(256)
-qk_prep_kernel(const float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
-               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, const int* __restrict__ off, int B,
-               int heads, int normalise) {
-    pdl_trigger(); pdl_wait();
-    // one thread: 4 consecutive dims d..d+3 (d < 32) of the first half and their partners d+32..d+35
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)rows * heads * 8;
-    if (i >= total) return;
-    const int d = (int)(i % 8) * 4;
-    const int hh = (int)((i / 8) % heads);
-    const int row = (int)(i / ((size_t)8 * heads));
-    const size_t base = (size_t)row * heads * DH + (size_t)hh * DH;
-    float4 a = *reinterpret_cast<const float4*>(x + base + d), c = *reinterpret_cast<const float4*>(x + base + d + 32);
-    if (freqs) {
-        const int b = find_seq(off, B, row);
-        if (b >= 0) {
-            float pos = (float)(row - __ldg(off + b));
-            if (normalise) pos = pos / len[b];
-            float a4[4] = {a.x, a.y, a.z, a.w}, c4[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float ang = pos * freqs[d + t];
-                const float cs = cosf(ang), sn = sinf(ang);
-                const float t1 = a4[t], t2 = c4[t];
-                a4[t] = t1 * cs - t2 * sn;
-                c4[t] = t1 * sn + t2 * cs;
-            }
-            a = make_float4(a4[0], a4[1], a4[2], a4[3]); c = make_float4(c4[0], c4[1], c4[2], c4[3]);
-        }
-    }
-    uint2 h1, l1, h2, l2;
-    tc::split_pair(a.x, a.y, h1.x, l1.x); tc::split_pair(a.z, a.w, h1.y, l1.y);
-    tc::split_pair(c.x, c.y, h2.x, l2.x); tc::split_pair(c.z, c.w, h2.y, l2.y);
-    *reinterpret_cast<uint2*>(hi + base + d) = h1; *reinterpret_cast<uint2*>(lo + base + d) = l1;
-    *reinterpret_cast<uint2*>(hi + base + d + 32) = h2; *reinterpret_cast<uint2*>(lo + base + d + 32) = l2;
-}
-
+// Q and K arrive as split-bf16 [rows, heads*64] straight from their projection GEMMs (rotary embedding fused into the
+// GEMM epilogue, gemm_tc.cuh); only V needs a pass of its own:
 // V: fp32 [Rk, heads*64] packed rows -> V^T (hi, lo) [(b*heads + h)*64 + d][ldk], keys >= Nk_b zero-filled up to ldk.
 // Block = (64-key tile, head, sequence): coalesced reads along d, transposed through shared memory, coalesced writes along keys.
 __global__ void __launch_bounds__(256)

@@ -335,11 +335,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             int mt, nt; ti.coords(ct, mt, nt);
             const int m0 = mt * BM + q * 32, n0 = nt * BN + half * COLS_PER_WARP;
             const uint32_t ab = it & 1, aph = (it >> 1) & 1;
-            float mk[4];
+            float mk[4], pos[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = m0 + i * 8 + sub;
                 mk[i] = (p.ep.mask && row < p.M) ? __ldg(p.ep.mask + row) : 1.f;
+                pos[i] = 0.f;
+                if (p.ep.rope_freqs && row < p.M) {            // rotary position of this output row
+                    const int b = find_seq(p.ep.rope_off, p.ep.rope_B, row);
+                    if (b >= 0) {
+                        pos[i] = (float)(row - __ldg(p.ep.rope_off + b));
+                        if (p.ep.rope_len) pos[i] = pos[i] / __ldg(p.ep.rope_len + b);
+                    }
+                }
             }
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
@@ -357,12 +365,22 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), scale = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (p.ep.bias) bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
                     if (p.ep.scale) scale = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col));
+                    float f0 = 0.f, f1 = 0.f;
+                    if (p.ep.rope_freqs) {                      // this float4 = rotary pairs i, i+1 of its head
+                        const int i2 = (col % p.ep.rope_dh) >> 1;
+                        f0 = __ldg(p.ep.rope_freqs + i2); f1 = __ldg(p.ep.rope_freqs + i2 + 1);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rl = i * 8 + sub, row = m0 + rl;
                         if (row >= p.M) continue;
                         float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq);
                         v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                        if (p.ep.rope_freqs) {
+                            float s0, c0, s1, c1;
+                            sincosf(pos[i] * f0, &s0, &c0); sincosf(pos[i] * f1, &s1, &c1);
+                            v = make_float4(v.x * c0 - v.y * s0, v.x * s0 + v.y * c0, v.z * c1 - v.w * s1, v.z * s1 + v.w * c1);
+                        }
                         if (p.ep.gelu) { v.x = gelu_erf_mufu(v.x); v.y = gelu_erf_mufu(v.y); v.z = gelu_erf_mufu(v.z); v.w = gelu_erf_mufu(v.w); }
                         if (p.ep.scale) { v.x *= scale.x; v.y *= scale.y; v.z *= scale.z; v.w *= scale.w; }
                         const size_t o = (size_t)row * p.ldo + col;

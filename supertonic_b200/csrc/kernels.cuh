@@ -374,6 +374,11 @@ struct Epilogue {
     const void* resid = nullptr;    // [M,N] (T)
     const float* mask = nullptr;    // [M]
     int gelu = 0;
+    // rotary embedding on the (bias-added) output, pairs in adjacent columns (tensor-core GEMM only; see rope_kernel)
+    const float* rope_freqs = nullptr;   // [DH/2]; null = no rotation
+    const int* rope_off = nullptr;       // packed row offsets [B+1] of the output rows
+    const float* rope_len = nullptr;     // [B] sequence lengths (length-aware variant) or null
+    int rope_B = 0, rope_dh = 64;
 };
 
 template <typename T, typename Out, int BM = 64>
@@ -447,8 +452,11 @@ __global__ void mask_len_kernel(const float* __restrict__ mask, float* __restric
     if (threadIdx.x == 0) { len[b] = s; cnt[b] = last; }
 }
 
-// ---- rotary embedding in place on [rows, heads*DH]: rotate-half convention -----------------------
-// pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i]
+// ---- rotary embedding in place on [rows, heads*DH] ------------------------------------------------
+// The graphs rotate the pairs (d, d + DH/2) ("rotate-half"). The library permutes the output columns of every rotary Q / K
+// projection at load time so that such a pair sits in ADJACENT columns (2i, 2i+1) — Q.K^T is invariant under a common
+// permutation of the head dimension — which lets the tensor-core GEMM epilogue rotate inside one float4. This kernel is the
+// CUDA-core path's form of the same thing. pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i].
 __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
                             int rows, const int* __restrict__ off, int B, int heads, int DH, int normalise) {
     pdl_trigger(); pdl_wait();
@@ -465,10 +473,9 @@ __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ fre
     if (normalise) pos = pos / len[b];
     float ang = pos * freqs[d];
     float c = cosf(ang), s = sinf(ang);
-    float* p = x + (size_t)row * heads * DH + (size_t)h * DH;
-    float t1 = p[d], t2 = p[d + half];
-    p[d] = t1 * c - t2 * s;
-    p[d + half] = t1 * s + t2 * c;
+    float2* p = reinterpret_cast<float2*>(x + (size_t)row * heads * DH + (size_t)h * DH) + d;
+    const float2 t = *p;
+    *p = make_float2(t.x * c - t.y * s, t.x * s + t.y * c);
 }
 
 // ---- multi-head attention core: O = softmax(Q K^T * scale + keymask) V ----------------------------

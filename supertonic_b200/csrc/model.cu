@@ -172,7 +172,8 @@ struct Handle {
                    int heads, int dh);
     bool attn_on_tc(const Attention& a, const Seq& ks) const;
     KV make_kv(const Attention& a, const Act& ctx, const Seq& ks);      // result lives in the arena above the caller's mark
-    void attn_core_tc(const float* Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k);
+    void attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k);
+    Epilogue rope_epilogue(const Attention& a, const Seq& seq) const;
     void rope(float* x, const float* freqs, const Seq& seq, int heads, int dh, int normalise);
     // sequence descriptors (offsets staged through pinned memory)
     int* stage_ints(const std::vector<int>& v);
@@ -369,8 +370,26 @@ Attention Handle::load_attention(const OnnxFile& f, const json& l, bool tc) {
     a.ln_g = W(f, p + ".ln.weight", a.C);
     a.ln_b = W(f, p + ".ln.bias", a.C);
     a.freqs = a.rope != ROPE_NONE ? W(f, p + ".rope_freqs", dh / 2) : nullptr;
-    a.q = make_linear(f, p + ".q", a.C, a.C, tc);
-    a.k = make_linear(f, p + ".k", a.ctx_dim, a.C, tc);
+    if (a.rope != ROPE_NONE) {
+        // rotary pairs (d, d + dh/2) of every head move to adjacent output columns (2i, 2i+1) of the Q and K projections
+        // (kernels.cuh rope_kernel): Q.K^T does not change, and the GEMM epilogue can rotate inside one float4
+        auto permuted = [&](const std::string& name, int K) {
+            const float* w = get_tensor(f, name + ".weight", (size_t)K * a.C).f32();
+            const float* b = get_tensor(f, name + ".bias", (size_t)a.C).f32();
+            std::vector<float> wp((size_t)K * a.C), bp(a.C);
+            for (int n = 0; n < a.C; ++n) {
+                const int h = n / dh, j = n % dh, src = h * dh + ((j & 1) ? dh / 2 + j / 2 : j / 2);
+                bp[n] = b[src];
+                for (int k = 0; k < K; ++k) wp[(size_t)k * a.C + n] = w[(size_t)k * a.C + src];
+            }
+            return make_linear_host(wp, bp, K, a.C, tc);
+        };
+        a.q = permuted(p + ".q", a.C);
+        a.k = permuted(p + ".k", a.ctx_dim);
+    } else {
+        a.q = make_linear(f, p + ".q", a.C, a.C, tc);
+        a.k = make_linear(f, p + ".k", a.ctx_dim, a.C, tc);
+    }
     a.v = make_linear(f, p + ".v", a.ctx_dim, a.C, tc);
     a.o = make_linear(f, p + ".o", a.C, a.C, tc);
     return a;
@@ -741,12 +760,13 @@ KV Handle::make_kv(const Attention& a, const Act& ctx, const Seq& ks) {
         kv.vt_hi = ws<__nv_bfloat16>(nv); kv.vt_lo = ws<__nv_bfloat16>(nv);
     } else { k = ws<float>(n); v = ws<float>(n); }
     const size_t mk = mark();
-    if (kv.tc) { k = ws<float>(n); v = ws<float>(n); }
-    gemm(ctx, ks.rows, a.k, Epilogue{}, k, nullptr, a.C);
+    if (kv.tc) {
+        v = ws<float>(n);
+        Act kact; kact.hi = kv.k_hi; kact.lo = kv.k_lo;
+        gemm(ctx, ks.rows, a.k, rope_epilogue(a, ks), nullptr, &kact, a.C);        // K: rotary + split-bf16 in the epilogue
+    } else gemm(ctx, ks.rows, a.k, Epilogue{}, k, nullptr, a.C);
     gemm(ctx, ks.rows, a.v, Epilogue{}, v, nullptr, a.C);
     if (kv.tc) {
-        STC_LAUNCH(this, attn::qk_prep_kernel, cdiv((size_t)ks.rows * a.heads * 8, 256), 256, 0, k, a.rope != ROPE_NONE ? a.freqs : nullptr,
-                   ks.len, kv.k_hi, kv.k_lo, ks.rows, ks.off, ks.B, a.heads, a.rope == ROPE_NORM);
         STC_LAUNCH(this, attn::v_prep_kernel, dim3(kv.ldk / attn::KB, a.heads, ks.B), 256, 0, v, kv.vt_hi, kv.vt_lo, ks.off, a.heads, kv.ldk);
         release(mk);
     } else {
@@ -756,12 +776,18 @@ KV Handle::make_kv(const Attention& a, const Act& ctx, const Seq& ks) {
     return kv;
 }
 
-void Handle::attn_core_tc(const float* Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k) {
+Epilogue Handle::rope_epilogue(const Attention& a, const Seq& seq) const {
+    Epilogue e;
+    if (a.rope != ROPE_NONE) {
+        e.rope_freqs = a.freqs; e.rope_off = seq.off; e.rope_B = seq.B; e.rope_dh = a.C / a.heads;
+        e.rope_len = a.rope == ROPE_NORM ? seq.len : nullptr;
+    }
+    return e;
+}
+
+void Handle::attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const Act& out, const Seq& q, const Seq& k) {
     const size_t mk = mark();
-    const size_t n = (size_t)q.rows * a.C;
-    __nv_bfloat16* q_hi = ws<__nv_bfloat16>(n); __nv_bfloat16* q_lo = ws<__nv_bfloat16>(n);
-    STC_LAUNCH(this, attn::qk_prep_kernel, cdiv((size_t)q.rows * a.heads * 8, 256), 256, 0, Q, a.rope != ROPE_NONE ? a.freqs : nullptr, q.len,
-               q_hi, q_lo, q.rows, q.off, q.B, a.heads, a.rope == ROPE_NORM);
+    __nv_bfloat16 *q_hi = Q.hi, *q_lo = Q.lo;
     attn::Params p{};
     p.qoff = q.off; p.koff = k.off; p.kcnt = (a.key_masked && k.mask) ? k.cnt : nullptr;
     p.heads = a.heads; p.scale_log2e = (1.0f / std::sqrt((float)attn::DH)) * 1.4426950408889634f;
@@ -786,15 +812,18 @@ void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* c
     int rows = qs.rows, dh = a.C / a.heads;
     Act xn = ws_act((size_t)rows * a.C);
     dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, qs, 1e-6f, nullptr, &xn);
-    float* q = ws<float>((size_t)rows * a.C);
-    gemm(xn, rows, a.q, Epilogue{}, q, nullptr, a.C);
     const Seq& ks = a.ctx_kind == CTX_SELF ? qs : ks_in;
     if (a.ctx_kind == CTX_SELF) ctx = &xn;
     KV local;
     if (!pre) { local = make_kv(a, *ctx, ks); pre = &local; }
     Act o = ws_act((size_t)rows * a.C);
-    if (pre->tc) attn_core_tc(q, a, *pre, o, qs, ks);
-    else {
+    if (pre->tc) {
+        Act q = ws_act((size_t)rows * a.C);
+        gemm(xn, rows, a.q, rope_epilogue(a, qs), nullptr, &q, a.C);               // Q: rotary + split-bf16 in the epilogue
+        attn_core_tc(q, a, *pre, o, qs, ks);
+    } else {
+        float* q = ws<float>((size_t)rows * a.C);
+        gemm(xn, rows, a.q, Epilogue{}, q, nullptr, a.C);
         if (a.rope != ROPE_NONE) rope(q, a.freqs, qs, a.heads, dh, a.rope == ROPE_NORM);
         attn_core(q, pre->K, pre->V, o, qs, ks, a.key_masked, a.heads, dh);
     }
