@@ -210,7 +210,9 @@ struct TileIter {
     STC_DEVINL void coords(int ct, int& mt, int& nt) const { mt = (ct / ctn) * cm + im; nt = (ct % ctn) * cn + in; }
 };
 
-template <int BN>
+// kRope: the rotary-embedding epilogue (Q / K projections) lives in its own instantiation — its sincosf slow path costs
+// registers, a stack frame and unrolling in every epilogue it is compiled into (the vocoder GEMMs lost 10 % to it).
+template <int BN, bool kRope = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -341,7 +343,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const int row = m0 + i * 8 + sub;
                 mk[i] = (p.ep.mask && row < p.M) ? __ldg(p.ep.mask + row) : 1.f;
                 pos[i] = 0.f;
-                if (p.ep.rope_freqs && row < p.M) {            // rotary position of this output row
+                if (kRope && p.ep.rope_freqs && row < p.M) {   // rotary position of this output row
                     const int b = find_seq(p.ep.rope_off, p.ep.rope_B, row);
                     if (b >= 0) {
                         pos[i] = (float)(row - __ldg(p.ep.rope_off + b));
@@ -366,7 +368,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     if (p.ep.bias) bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
                     if (p.ep.scale) scale = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col));
                     float f0 = 0.f, f1 = 0.f;
-                    if (p.ep.rope_freqs) {                      // this float4 = rotary pairs i, i+1 of its head
+                    if (kRope && p.ep.rope_freqs) {             // this float4 = rotary pairs i, i+1 of its head
                         const int i2 = (col % p.ep.rope_dh) >> 1;
                         f0 = __ldg(p.ep.rope_freqs + i2); f1 = __ldg(p.ep.rope_freqs + i2 + 1);
                     }
@@ -376,7 +378,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         if (row >= p.M) continue;
                         float4 v = *reinterpret_cast<const float4*>(stg + rl * EPI_PITCH + cq);
                         v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                        if (p.ep.rope_freqs) {
+                        if (kRope && p.ep.rope_freqs) {
                             float s0, c0, s1, c1;
                             sincosf(pos[i] * f0, &s0, &c0); sincosf(pos[i] * f1, &s1, &c1);
                             v = make_float4(v.x * c0 - v.y * s0, v.x * s0 + v.y * c0, v.z * c1 - v.w * s1, v.z * s1 + v.w * c1);

@@ -597,7 +597,8 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
     if (out_f32) { p.out_f32 = out_f32; p.split = 0; } else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
     if (dry) return;
-    const GemmCfg c = force_cfg.bn ? force_cfg : pick_gemm(M, w.N, w.K);
+    GemmCfg c = force_cfg.bn ? force_cfg : pick_gemm(M, w.N, w.K);
+    if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
     p.cm = c.cm; p.cn = c.cn;
     const int csize = c.cm * c.cn;
     const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM / c.cn), mal = tmap(a.lo, M, w.K, tc::BM / c.cn);
@@ -614,7 +615,8 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     cfg.attrs = attr; cfg.numAttrs = na;
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
-    switch (c.bn) {
+    switch (ep.rope_freqs ? 1 : c.bn) {
+        case 1: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, true>, mah, mal, mwh, mwl, p); break;
         case 64: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64>, mah, mal, mwh, mwl, p); break;
         case 128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128>, mah, mal, mwh, mwl, p); break;
         case 256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256>, mah, mal, mwh, mwl, p); break;
@@ -1186,6 +1188,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
