@@ -95,7 +95,7 @@ struct Handle {
     bool force_simt_attn = false;     // env STC_ATTN=simt: keep the CUDA-core attention core (cross-check)
     int profile = 0;          // 0 off, 1 stage events, 2 + per-kernel events for the GEMM / dwconv+LN classes
     struct KProf { double ms = 0, flops = 0, bytes = 0; uint64_t n = 0; };
-    KProf kprof[3];           // 0 = tcgen05 GEMM, 1 = dwconv+LayerNorm, 2 = attention core
+    KProf kprof[4];           // 0 = tcgen05 GEMM, 1 = dwconv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (+ its reduce)
     struct Pending { int cls; cudaEvent_t a, b; double flops, bytes; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
@@ -669,7 +669,7 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
     if (form == 2) p.partial = ws<float>(slice * mlp::CS);
-    kprof_begin(0, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
+    kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
         const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
@@ -1227,7 +1227,7 @@ int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID;
 void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
 int stc_set_profile(stc_handle* h, int level) { if (!h) return STC_ERR_INVALID; h->impl->profile = level; return STC_OK; }
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]) {
-    if (!h || !out || cls < 0 || cls > 2) return STC_ERR_INVALID;
+    if (!h || !out || cls < 0 || cls > 3) return STC_ERR_INVALID;
     const auto& k = h->impl->kprof[cls];
     out[0] = k.ms; out[1] = k.flops; out[2] = k.bytes; out[3] = (double)k.n;
     return STC_OK;
