@@ -194,9 +194,17 @@ def main():
 
     def device_step(seed):
         for b in buckets:
-            off = eng.synthesize_packed_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(),
-                                               b["B"], b["T"], a.total_step, 1.05, seed, b["wav"].data_ptr(), b["cap"], b["dur"].data_ptr(),
-                                               text_lens=b["lens"])
+            for attempt in range(2):
+                try:
+                    off = eng.synthesize_packed_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(),
+                                                       b["B"], b["T"], a.total_step, 1.05, seed, b["wav"].data_ptr(), b["cap"],
+                                                       b["dur"].data_ptr(), text_lens=b["lens"])
+                    break
+                except capi.StcError as e:          # result buffer too small for the (128-row bucketed) frame count: grow once
+                    if e.code != capi.ERR_CAPACITY or attempt:
+                        raise
+                    b["cap"] = int(e.need)
+                    b["wav"] = torch.empty(b["cap"], dtype=torch.float32, device="cuda")
             b["L"] = int(off[-1] // cs)
 
     for w in range(a.warmup):
