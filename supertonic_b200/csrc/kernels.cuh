@@ -266,12 +266,12 @@ dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, 
     float v = 0.f;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) { y[j] -= mean; v += y[j] * y[j]; }
-    const float den = sqrtf(warp_sum<float>(v) / (float)C + eps);
+    const float inv = 1.0f / sqrtf(warp_sum<float>(v) / (float)C + eps);      // see dwconv_ln_tile_kernel
 #pragma unroll
     for (int j = 0; j < CPL; j += 4) {
         const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c0 + j)), bv = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
-        y[j] = y[j] / den * gv.x + bv.x; y[j + 1] = y[j + 1] / den * gv.y + bv.y;
-        y[j + 2] = y[j + 2] / den * gv.z + bv.z; y[j + 3] = y[j + 3] / den * gv.w + bv.w;
+        y[j] = y[j] * inv * gv.x + bv.x; y[j + 1] = y[j + 1] * inv * gv.y + bv.y;
+        y[j + 2] = y[j + 2] * inv * gv.z + bv.z; y[j + 3] = y[j + 3] * inv * gv.w + bv.w;
     }
     store_row_vec<CPL>(out, (size_t)row * C + c0, y);
 }
@@ -339,13 +339,15 @@ dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT,
                 y[j].x -= mean; y[j].y -= mean; y[j].z -= mean; y[j].w -= mean;
                 v += (y[j].x * y[j].x + y[j].y * y[j].y) + (y[j].z * y[j].z + y[j].w * y[j].w);
             }
-            const float den = sqrtf(warp_sum<float>(v) / (float)C + eps);
+            // one reciprocal per row instead of C IEEE divisions (~10 instructions each in a kernel that is issue bound):
+            // (y * (1/den)) * g + b differs from the graph's (y / den) * g + b by <= 1 ulp of the quotient
+            const float inv = 1.0f / sqrtf(warp_sum<float>(v) / (float)C + eps);
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * j);
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
-                y[j].x = y[j].x / den * gv.x + bv.x; y[j].y = y[j].y / den * gv.y + bv.y;
-                y[j].z = y[j].z / den * gv.z + bv.z; y[j].w = y[j].w / den * gv.w + bv.w;
+                y[j].x = y[j].x * inv * gv.x + bv.x; y[j].y = y[j].y * inv * gv.y + bv.y;
+                y[j].z = y[j].z * inv * gv.z + bv.z; y[j].w = y[j].w * inv * gv.w + bv.w;
             }
         }
 #pragma unroll
