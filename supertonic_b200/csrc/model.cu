@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <nlohmann/json.hpp>
 
 #include "gemm_tc.cuh"
@@ -22,10 +23,16 @@ using json = nlohmann::json;
 
 namespace stc {
 
+// Stream captures and the "potentially unsafe" runtime calls (cudaMalloc / cudaFree / cudaMallocHost / device-wide syncs) of
+// different handles must not overlap: a capture in one thread is invalidated ("operation not permitted when stream is
+// capturing") by such a call in another. One process-wide lock around both; graph REPLAYS do not take it.
+static std::recursive_mutex g_capture_mu;
+
 // ------------------------------------------------------------------------------------------ arena
 Arena::~Arena() { if (base_) cudaFree(base_); }
 void Arena::reserve(size_t bytes) {
     if (bytes <= cap_) return;
+    std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
     if (base_) { cudaDeviceSynchronize(); cudaFree(base_); base_ = nullptr; }
     size_t want = bytes + (bytes >> 3) + (1u << 20);
     cudaError_t e = cudaMalloc((void**)&base_, want);
@@ -966,6 +973,7 @@ const float* Handle::time_vectors(float cur, float tot) {
     int C = ve.C, td = ve_arch.at("time_dim"), ntc = 0;
     for (const Layer& l : ve.layers) if (l.type == L_TIME_COND) ++ntc;
     if (dry) return reinterpret_cast<const float*>(uintptr_t(0x1000));
+    std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
     float* out = nullptr;
     STC_CUDA(cudaMalloc((void**)&out, sizeof(float) * std::max(1, ntc) * C)); owned.push_back(out);
     float* tmp = nullptr;
@@ -1093,6 +1101,7 @@ void Handle::run_graphed(const GraphKey& key, const std::function<void()>& body,
     }
     auto it = graphs.find(key);
     if (it == graphs.end()) {
+        std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
         ensure_ws(body);                       // may grow the arenas (and then drops every cached graph)
         if (graphs.size() >= 48) { for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec); graphs.clear(); }
         pre_copies.clear();
@@ -1150,6 +1159,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
     if (!out || !onnx_dir) return fail(nullptr, STC_ERR_INVALID, "stc_create: null argument");
     *out = nullptr;
     auto sh = std::make_unique<stc_handle>();
+    std::lock_guard<std::recursive_mutex> lk(stc::g_capture_mu);
     try {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
@@ -1212,6 +1222,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
 
 void stc_destroy(stc_handle* h) {
     if (!h) return;
+    std::lock_guard<std::recursive_mutex> lk(stc::g_capture_mu);
     if (h->impl) { cudaSetDevice(h->impl->device); cudaStreamSynchronize(h->impl->stream); }
     delete h;
 }
@@ -1248,7 +1259,10 @@ struct Scope {   // per-call: select device, reset arena
         if (!h) throw StcError(STC_ERR_INVALID, "null handle");
         STC_CUDA(cudaSetDevice(h->device));
         h->arena.reset(); h->persist.reset();
-        if (!h->h_stage) { h->h_stage_cap = 1 << 18; STC_CUDA(cudaMallocHost((void**)&h->h_stage, h->h_stage_cap * sizeof(int))); }
+        if (!h->h_stage) {
+            std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
+            h->h_stage_cap = 1 << 18; STC_CUDA(cudaMallocHost((void**)&h->h_stage, h->h_stage_cap * sizeof(int)));
+        }
         h->h_stage_off = 0;
     }
 };
@@ -1436,6 +1450,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         int si = c.style_dp_tokens * c.style_dp_dim;
         if (host_io) validate_ids(text_ids, (size_t)B * T, c.vocab_size);
         if (h->h_cap < B) {
+            std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
             if (h->h_dur) cudaFreeHost(h->h_dur);
             if (h->h_wavlen) cudaFreeHost(h->h_wavlen);
             STC_CUDA(cudaMallocHost((void**)&h->h_dur, sizeof(float) * B));
@@ -1833,10 +1848,15 @@ int stc_pinned_alloc(size_t bytes, void** out) {
     STC_TRY(nullptr, {
         if (!out || !bytes) throw StcError(STC_ERR_INVALID, "stc_pinned_alloc: bad argument");
         *out = nullptr;
+        std::lock_guard<std::recursive_mutex> lk(stc::g_capture_mu);
         STC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
     })
 }
-void stc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+void stc_pinned_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::recursive_mutex> lk(stc::g_capture_mu);
+    cudaFreeHost(p);
+}
 
 int stc_text_to_ids(stc_handle* sh, const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,
                     int64_t T_cap, int64_t* T_out) {

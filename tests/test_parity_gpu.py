@@ -328,3 +328,39 @@ def test_chunked_vocoder_with_overlapped_copies_is_bit_identical(rig):
         np.testing.assert_array_equal(wa[k], b["wavs"][k])
         np.testing.assert_array_equal(a2["wavs"][k], b["wavs"][k])
     eng.close()
+
+
+def test_two_handles_in_two_threads(rig):
+    """Distinct handles are fully concurrent (include/supertonic_cuda.h "Threading"): two engines capture their CUDA graphs and
+    synthesise at the same time from two threads; each result equals what the module's engine computes alone."""
+    import threading
+    capi = rig["capi"]
+    engs = [capi.Engine(rig["root"] + "/onnx") for _ in range(2)]
+    try:
+        jobs = []
+        for k in range(2):
+            ids, mask, ttl, dp = _inputs(rig, 200 + k, 3 + k, 30, 100)
+            nz = np.random.default_rng(50 + k).standard_normal((ids.shape[0], 144, 300)).astype(np.float32)
+            jobs.append((ids, mask, ttl, dp, nz))
+        out, err = [None, None], []
+
+        def work(k):
+            try:
+                for _ in range(3):          # first call captures, later calls replay
+                    out[k] = engs[k].synthesize_packed(*jobs[k][:4], 2, 1.05, noise=jobs[k][4])
+            except Exception as e:          # noqa: BLE001
+                err.append(e)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not err, err
+        for k in range(2):
+            ref = rig["eng"].synthesize_packed(*jobs[k][:4], 2, 1.05, noise=jobs[k][4])
+            np.testing.assert_array_equal(out[k]["duration"], ref["duration"])
+            for a, b in zip(out[k]["wavs"], ref["wavs"]):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        for e in engs:
+            e.close()
