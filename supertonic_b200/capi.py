@@ -259,11 +259,11 @@ class Engine:
         return res
 
     def synthesize_packed(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
-                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, pinned: bool = False):
+                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, pinned=False):
         """Throughput path: packed latent rows, no padded frames. Returns dict(wavs=[B trimmed arrays], duration[B],
         wav_lengths[B], frames[B], latent? (list of [frames_b, D] arrays)).
-        pinned=True: the waveforms are VIEWS into an engine-owned page-locked buffer (D2H at PCIe speed, no copy);
-        they stay valid until the next pinned call on this engine."""
+        pinned=True (or a buffer name): the waveforms are VIEWS into an engine-owned page-locked buffer (D2H at PCIe speed, no
+        copy); they stay valid until the next call that uses the same buffer name on this engine."""
         ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
         sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
         B, T = ids.shape
@@ -274,7 +274,8 @@ class Engine:
         cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs
         dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
         for _ in range(2):
-            wav = self.pinned("wav_packed", cap, np.float32) if pinned else np.empty((cap,), np.float32)
+            wav = (self.pinned(pinned if isinstance(pinned, str) else "wav_packed", cap, np.float32) if pinned
+                   else np.empty((cap,), np.float32))
             lat = np.empty((cap // cs, D), np.float32) if want_latent else None
             rc = lib.stc_synthesize_packed(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
                                            _ptr(nz), nld, seed, _ptr(wav), cap, _ptr(off), _ptr(dur), _ptr(wl), _ptr(lat))

@@ -154,22 +154,20 @@ class TextToSpeech:
         """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
         rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
         utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
-        (tests: batch-composition invariance). With a single group (n <= max_batch) and copy=False the waveforms are
-        views into the engine's page-locked result buffer, valid until the next call."""
+        (tests: batch-composition invariance). With copy=False the waveforms are views into the engine's page-locked result
+        buffers (one per group), valid until the next call."""
         from .scheduler import length_buckets
         n = len(texts)
         ids, mask = self.engine.text_to_ids(texts, langs)
         lens = mask.reshape(n, -1).sum(1).astype(np.int64)
         out: List[Optional[Tuple[np.ndarray, float]]] = [None] * n
-        groups = length_buckets(lens, max_batch, 1e9)
-        views_ok = len(groups) == 1 and not copy
-        for grp in groups:
+        for gi, grp in enumerate(length_buckets(lens, max_batch, 1e9)):
             g = np.asarray(grp)
             T = int(lens[g].max())
             r = self.engine.synthesize_packed(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed,
-                                              seed=seed, noise=None if noise is None else noise[g], pinned=True)
+                                              seed=seed, noise=None if noise is None else noise[g], pinned=f"wav_packed{gi}")
             for k, i in enumerate(grp):
-                out[i] = (r["wavs"][k] if views_ok else r["wavs"][k].copy(), float(r["duration"][k]))
+                out[i] = (r["wavs"][k].copy() if copy else r["wavs"][k], float(r["duration"][k]))
         return out
 
 
