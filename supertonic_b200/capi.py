@@ -89,18 +89,24 @@ def _b(s) -> bytes:
 
 def _texts_to_ids(fn, handle, texts: Sequence, langs: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
     n = len(texts)
-    ta = (C.c_char_p * n)(*[_b(t) for t in texts])
+    raw = [_b(t) for t in texts]
+    ta = (C.c_char_p * n)(*raw)
     la = (C.c_char_p * n)(*[_b(l) for l in langs])
+    # one pass with a guessed width (bytes + tags + slack; the rare expanding rules — '@' -> ' at ', 'e.g.,' -> 'for example, ' —
+    # can exceed it: the library then reports the exact token count and the call is repeated once)
+    cap = max((len(r) for r in raw), default=0) + 40
     T = C.c_int64(0)
-    rc = fn(handle, ta, la, n, None, None, 0, C.byref(T))
+    for _ in range(2):
+        ids = np.empty((n, cap), np.int64)
+        mask = np.empty((n, 1, cap), np.float32)
+        rc = fn(handle, ta, la, n, _ptr(ids), _ptr(mask), cap, C.byref(T))
+        if rc != STC_OK and T.value > cap:
+            cap = T.value
+            continue
+        break
     if rc != STC_OK:
         raise StcError(rc, lib.stc_last_error(None).decode())
-    ids = np.zeros((n, T.value), np.int64)
-    mask = np.zeros((n, 1, T.value), np.float32)
-    rc = fn(handle, ta, la, n, _ptr(ids), _ptr(mask), T.value, C.byref(T))
-    if rc != STC_OK:
-        raise StcError(rc, lib.stc_last_error(None).decode())
-    return ids, mask
+    return np.ascontiguousarray(ids[:, :T.value]), np.ascontiguousarray(mask[:, :, :T.value])
 
 
 def chunk_text(text, max_len: int) -> List[bytes]:

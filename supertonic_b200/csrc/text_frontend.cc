@@ -1,5 +1,8 @@
 #include "text_frontend.h"
 
+#include <exception>
+#include <thread>
+
 #include <algorithm>
 #include <cstring>
 #include <fstream>
@@ -144,11 +147,24 @@ void TextFrontend::load_indexer(const std::string& path) {
 void TextFrontend::call(const char* const* texts, const char* const* langs, int n, int64_t* text_ids, float* text_mask,
                         int64_t T_cap, int64_t* T_out) const {
     std::vector<std::vector<uint16_t>> units((size_t)n);
-    int64_t T = 0;
-    for (int i = 0; i < n; ++i) {
-        text_to_units(preprocess_text(texts[i], langs[i]), units[i]);
-        T = std::max<int64_t>(T, (int64_t)units[i].size());
+    // texts are independent: large requests are normalised on a few host threads (semantics unchanged — the reference does
+    // them one by one, cpp/helper.cpp:362-368); an exception in a worker (unknown language) is rethrown here
+    const int workers = n >= 64 ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (workers > 1) {
+        std::vector<std::thread> pool;
+        std::vector<std::exception_ptr> errs((size_t)workers);
+        for (int w = 0; w < workers; ++w)
+            pool.emplace_back([&, w]() {
+                try { for (int i = w; i < n; i += workers) text_to_units(preprocess_text(texts[i], langs[i]), units[i]); }
+                catch (...) { errs[(size_t)w] = std::current_exception(); }
+            });
+        for (auto& t : pool) t.join();
+        for (auto& e : errs) if (e) std::rethrow_exception(e);
+    } else {
+        for (int i = 0; i < n; ++i) text_to_units(preprocess_text(texts[i], langs[i]), units[i]);
     }
+    int64_t T = 0;
+    for (int i = 0; i < n; ++i) T = std::max<int64_t>(T, (int64_t)units[i].size());
     if (T_out) *T_out = T;
     if (!text_ids) return;
     if (T_cap < T) throw std::runtime_error("stc_text_to_ids: T_cap smaller than the token count");
