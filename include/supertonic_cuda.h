@@ -130,6 +130,19 @@ int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* t
                           const float* noise, int64_t noise_ld, uint64_t seed,
                           float* wav_out, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out,
                           int64_t* wav_lengths_out, float* latent_out);
+/* Asynchronous flavour of stc_synthesize_packed for request streams: returns as soon as the result SIZES are known
+ * (duration_out / wav_lengths_out / wav_offsets_out are valid on return) and all device work including the device->host copy of
+ * the waveform has been enqueued. wav_out_pinned must be page-locked (stc_pinned_alloc) and is valid after stc_wait(h). The next
+ * stc_synthesize_packed_async on the same handle may be issued BEFORE stc_wait: its computation overlaps this call's copy (two
+ * alternating device result buffers), so at most two calls may be outstanding per wait. Any synchronous entry point drains
+ * outstanding asynchronous calls first. Noise: device Philox keyed by `seed`. */
+int stc_synthesize_packed_async(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                                const float* style_dp, int B, int T, int total_step, float speed, uint64_t seed,
+                                float* wav_out_pinned, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out,
+                                int64_t* wav_lengths_out);
+/* Waits for every outstanding asynchronous call of the handle; reports their errors. */
+int stc_wait(stc_handle* h);
+
 /* text_lens (HOST int32[B], optional): token count of every utterance (= sum of its mask row); lets the text side run on
  * packed rows too. NULL -> the text side is computed on the padded [B,T] rectangle. */
 int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev,

@@ -45,6 +45,8 @@ _SIGS = {
     "stc_synthesize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_synthesize_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "stc_synthesize_packed_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp, _vp]),
+    "stc_wait": (_i, [_vp]),
     "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_pinned_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "stc_pinned_free": (None, [_vp]),
@@ -181,6 +183,8 @@ class Engine:
         cur = self._pinned.get(name)
         if cur is None or cur[0].size < count or cur[0].dtype != dt:
             if cur is not None:
+                if getattr(self, "_pending", None):
+                    self.wait()                            # an outstanding copy may still target the buffer being replaced
                 lib.stc_pinned_free(cur[1])
             n = int(count * 1.25) + 1024
             ptr = _vp()
@@ -265,11 +269,15 @@ class Engine:
         return res
 
     def synthesize_packed(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
-                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, pinned=False):
+                          noise: Optional[np.ndarray] = None, seed: int = 0, want_latent: bool = False, pinned=False,
+                          wait: bool = True):
         """Throughput path: packed latent rows, no padded frames. Returns dict(wavs=[B trimmed arrays], duration[B],
         wav_lengths[B], frames[B], latent? (list of [frames_b, D] arrays)).
         pinned=True (or a buffer name): the waveforms are VIEWS into an engine-owned page-locked buffer (D2H at PCIe speed, no
-        copy); they stay valid until the next call that uses the same buffer name on this engine."""
+        copy); they stay valid until the next call that uses the same buffer name on this engine.
+        wait=False (needs a pinned buffer, no injected noise): returns once the sizes are known and the work is enqueued; the
+        waveform views hold data only after `Engine.wait()`. The next call may be issued before that (its compute overlaps this
+        call's copy) as long as it uses a different pinned buffer name."""
         ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
         sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
         B, T = ids.shape
@@ -279,10 +287,22 @@ class Engine:
             nz = _cf(noise, np.float32); nld = nz.shape[2]
         cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs
         dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
+        use_async = (not wait) and bool(pinned) and noise is None and not want_latent
+        pname = pinned if isinstance(pinned, str) else "wav_packed"
+        # (re-using a buffer whose earlier copy is still in flight is ordered by the library — copies run in issue order on one
+        #  stream — the caller just must have consumed the older result by then)
         for _ in range(2):
-            wav = (self.pinned(pinned if isinstance(pinned, str) else "wav_packed", cap, np.float32) if pinned
-                   else np.empty((cap,), np.float32))
+            wav = self.pinned(pname, cap, np.float32) if pinned else np.empty((cap,), np.float32)
             lat = np.empty((cap // cs, D), np.float32) if want_latent else None
+            if use_async:
+                rc = lib.stc_synthesize_packed_async(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
+                                                     seed, _ptr(wav), cap, _ptr(off), _ptr(dur), _ptr(wl))
+                if rc == ERR_CAPACITY and off[B] > cap:
+                    cap = int(off[B])
+                    continue
+                self._chk(rc)
+                self._pending = getattr(self, "_pending", set()) | {pname}
+                break
             rc = lib.stc_synthesize_packed(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
                                            _ptr(nz), nld, seed, _ptr(wav), cap, _ptr(off), _ptr(dur), _ptr(wl), _ptr(lat))
             if rc == ERR_CAPACITY and off[B] > cap:
@@ -296,6 +316,11 @@ class Engine:
             fo = np.concatenate([[0], np.cumsum(frames)])
             res["latent"] = [lat[fo[b]:fo[b + 1]] for b in range(B)]
         return res
+
+    def wait(self):
+        """Deliver every outstanding wait=False call (their waveform views hold data afterwards)."""
+        self._pending = set()
+        self._chk(lib.stc_wait(self._h))
 
     def synthesize_packed_device(self, ids_ptr: int, mask_ptr: int, sttl_ptr: int, sdp_ptr: int, B: int, T: int, total_step: int,
                                  speed: float, seed: int, wav_ptr: int, wav_cap: int, dur_ptr: int,

@@ -81,6 +81,14 @@ struct Handle {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;    // the text encoder runs here, concurrently with the duration predictor on `stream`
     cudaEvent_t ev_in = nullptr, ev_te = nullptr;
+    // asynchronous result copies (stc_synthesize_packed_async): a third stream carries the device->host copy of the waveform
+    // while the main stream already runs the next call; two alternating device result buffers and staging halves
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t ev_out = nullptr, copy_done[2] = {nullptr, nullptr};
+    float* outbuf[2] = {nullptr, nullptr}; size_t outcap[2] = {0, 0};
+    int slot = 0; bool async_pending = false;
+    size_t h_stage_lim = 0;
+    void wait_async();
     stc_config cfg{};
     Net dp, te, ve, voc;
     json dp_arch, te_arch, ve_arch, voc_arch;
@@ -246,8 +254,20 @@ Handle::~Handle() {
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
     if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
+    for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+    for (auto& p : outbuf) if (p) cudaFree(p);
+    if (stream_copy) cudaStreamDestroy(stream_copy);
     if (ev_te) cudaEventDestroy(ev_te);
     for (auto& e : ev_voc) if (e) cudaEventDestroy(e);
+}
+
+void Handle::wait_async() {
+    if (!async_pending) return;
+    STC_CUDA(cudaStreamSynchronize(stream_copy));
+    STC_CUDA(cudaStreamSynchronize(stream));
+    async_pending = false;
+    check_launch("asynchronous synthesis");
 }
 
 void Handle::check_launch(const char* what) {
@@ -845,7 +865,7 @@ void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* c
 int* Handle::stage_ints(const std::vector<int>& v) {
     int* d = ws<int>(v.size());
     if (dry && !restage) return d;
-    if (h_stage_off + v.size() > h_stage_cap) throw StcError(STC_ERR_CAPACITY, "offset staging buffer exhausted (batch too large)");
+    if (h_stage_off + v.size() > (h_stage_lim ? h_stage_lim : h_stage_cap)) throw StcError(STC_ERR_CAPACITY, "offset staging buffer exhausted (batch too large)");
     int* hp = h_stage + h_stage_off;
     h_stage_off += v.size();
     memcpy(hp, v.data(), v.size() * sizeof(int));
@@ -1186,6 +1206,9 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : 0; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
+        STC_CUDA(cudaEventCreateWithFlags(&hd->ev_out, cudaEventDisableTiming));
+        for (auto& e : hd->copy_done) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_te, cudaEventDisableTiming));
         for (auto& e : hd->ev_voc) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1255,15 +1278,16 @@ int stc_last_stage_ms(const stc_handle* h, float out[5]) {
 namespace {
 struct Scope {   // per-call: select device, reset arena
     Handle* h;
-    explicit Scope(stc_handle* sh) : h(sh ? sh->impl.get() : nullptr) {
+    explicit Scope(stc_handle* sh, bool keep_async = false) : h(sh ? sh->impl.get() : nullptr) {
         if (!h) throw StcError(STC_ERR_INVALID, "null handle");
         STC_CUDA(cudaSetDevice(h->device));
+        if (!keep_async) h->wait_async();              // every synchronous entry point drains outstanding asynchronous calls first
         h->arena.reset(); h->persist.reset();
         if (!h->h_stage) {
             std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
             h->h_stage_cap = 1 << 18; STC_CUDA(cudaMallocHost((void**)&h->h_stage, h->h_stage_cap * sizeof(int)));
         }
-        h->h_stage_off = 0;
+        h->h_stage_off = 0; h->h_stage_lim = 0;
     }
 };
 template <typename T> void h2d(Handle* h, T* d, const T* host, size_t n) {
@@ -1439,10 +1463,18 @@ extern "C" {
 static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
                       const float* style_dp, int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld,
                       uint64_t seed, float* wav_out, int64_t wav_cap, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
-                      float* latent_out, int64_t* wav_offsets_out, const int32_t* text_lens) {
+                      float* latent_out, int64_t* wav_offsets_out, const int32_t* text_lens, bool async_copy = false) {
     STC_TRY(sh, {
         const bool host_io = mode & 1, packed = mode & 2;
-        Scope sc(sh); Handle* h = sc.h;
+        Scope sc(sh, async_copy); Handle* h = sc.h;
+        if (async_copy && !(host_io && packed && !latent_out && !h->profile && h->use_graphs)) async_copy = false;
+        int slot = 0;
+        if (async_copy) {                              // this call's half of the pinned offset staging + its device result buffer
+            slot = h->slot; h->slot ^= 1;
+            h->h_stage_off = slot ? h->h_stage_cap / 2 : 0;
+            h->h_stage_lim = slot ? h->h_stage_cap : h->h_stage_cap / 2;
+            mode |= 16 | (slot << 5);                  // graphs bake the staging / result addresses: one set per slot
+        }
         if (B <= 0 || T <= 0 || total_step <= 0 || !(speed > 0.f) || !text_ids || !text_mask || !style_ttl || !style_dp || !wav_out)
             throw StcError(STC_ERR_INVALID, "stc_synthesize: bad argument");
         const stc_config& c = h->cfg;
@@ -1495,8 +1527,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
         float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
         const uintptr_t pin = host_io ? 0 : (uintptr_t)text_ids ^ ((uintptr_t)text_mask << 1) ^ ((uintptr_t)style_ttl << 2) ^ ((uintptr_t)style_dp << 3);
+        const size_t stage_base = h->h_stage_off;
         auto stage1a = [&]() {
-            h->arena.reset(); h->persist.reset(); h->h_stage_off = 0;
+            h->arena.reset(); h->persist.reset(); h->h_stage_off = stage_base;
             if (host_io) {
                 d_ids = upp(h, text_ids, (size_t)B * T); d_tmask = upp(h, text_mask, (size_t)B * T);
                 d_sttl = upp(h, style_ttl, (size_t)B * S * Cs); d_sdp = upp(h, style_dp, (size_t)B * si);
@@ -1562,7 +1595,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         // Measured on configs[1] (57 MB of waveform per step): e2e 15.8 ms/step with 4 groups against 14.7 ms with one pass —
         // the four smaller passes lose more tensor-pipe efficiency than the hidden copy (1.1 ms) gains — so it is OFF by default.
         std::vector<int> grp_end;      // utterance index where each vocoder group ends
-        if (h->voc_groups > 1 && host_io && packed && !h->profile && h->use_graphs && B >= 2 &&
+        if (h->voc_groups > 1 && !async_copy && host_io && packed && !h->profile && h->use_graphs && B >= 2 &&
             R * c.chunk_size * (int64_t)sizeof(float) >= (int64_t(8) << 20)) {
             const int G = std::min(h->voc_groups, B);
             int64_t acc = 0; int g = 1;
@@ -1575,12 +1608,24 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         }
         const bool chunked = !grp_end.empty();
         float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
+        if (async_copy) {
+            const size_t need = (size_t)rows * c.chunk_size;
+            if (h->outcap[slot] < need) {
+                std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
+                STC_CUDA(cudaEventSynchronize(h->copy_done[slot]));                  // the copy that last read this buffer
+                if (h->outbuf[slot]) cudaFree(h->outbuf[slot]);
+                h->outbuf[slot] = nullptr; h->outcap[slot] = 0;
+                STC_CUDA(cudaMalloc((void**)&h->outbuf[slot], (need + need / 4) * sizeof(float)));
+                h->outcap[slot] = need + need / 4;
+            }
+            STC_CUDA(cudaStreamWaitEvent(st, h->copy_done[slot], 0));                // device-side: do not overwrite before it is copied out
+        }
         auto stage2 = [&]() {
             h->arena.reset();          // (the pinned offset staging keeps growing: stage-1 copies may still be in flight)
             d_noise = nullptr;
             if (noise) d_noise = up(h, noise, (size_t)B * D * noise_ld);
             d_xlat = h->ws<float>((size_t)rows * D);
-            d_wav = host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
+            d_wav = async_copy ? h->outbuf[slot] : host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
             Seq text = text_seq(d_tmask, true), lat;
             if (packed) lat = h->packed_seq(lens, (int)rows, maxlen_launch);
             else {
@@ -1592,7 +1637,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav, !chunked);
         };
         h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0) | (chunked ? 8 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
-                                pin, host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}, stage2);
+                                pin, async_copy ? (uintptr_t)h->outbuf[slot] : host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}, stage2);
         if (getenv("STC_TIMING")) {
             const auto t_host2 = std::chrono::steady_clock::now();
             fprintf(stderr, "[stc timing] wait for durations %.1f us, host work until stage-2 launch returned %.1f us\n",
@@ -1600,6 +1645,15 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
                     std::chrono::duration<double, std::micro>(t_host2 - t_host1).count());
         }
         if (h->profile) cudaEventRecord(h->ev[4], st);
+        if (async_copy) {
+            // the copy rides its own stream; this call returns as soon as it is enqueued (stc_wait delivers it)
+            STC_CUDA(cudaEventRecord(h->ev_out, st));
+            STC_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_out, 0));
+            STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)R * c.chunk_size * sizeof(float), cudaMemcpyDeviceToHost, h->stream_copy));
+            STC_CUDA(cudaEventRecord(h->copy_done[slot], h->stream_copy));
+            h->async_pending = true;
+            return STC_OK;
+        }
         if (chunked) {
             int b0 = 0; int64_t r0 = 0;
             for (size_t g = 0; g < grp_end.size(); ++g) {
@@ -1670,6 +1724,21 @@ int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* t
                           float* latent_out) {
     return synth_impl(h, 3, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, wav_out, wav_cap,
                       duration_out, wav_lengths_out, nullptr, latent_out, wav_offsets_out, nullptr);
+}
+
+int stc_synthesize_packed_async(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                                const float* style_dp, int B, int T, int total_step, float speed, uint64_t seed, float* wav_out_pinned,
+                                int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out, int64_t* wav_lengths_out) {
+    return synth_impl(h, 3, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, nullptr, 0, seed, wav_out_pinned, wav_cap,
+                      duration_out, wav_lengths_out, nullptr, nullptr, wav_offsets_out, nullptr, true);
+}
+
+int stc_wait(stc_handle* sh) {
+    STC_TRY(sh, {
+        if (!sh || !sh->impl) throw StcError(STC_ERR_INVALID, "null handle");
+        STC_CUDA(cudaSetDevice(sh->impl->device));
+        sh->impl->wait_async();
+    })
 }
 
 int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, const float* text_mask_dev, const float* style_ttl_dev,

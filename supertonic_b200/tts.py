@@ -150,24 +150,34 @@ class TextToSpeech:
 
     # -- throughput path (north_star: "a request batch is length-bucketed")
     def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05,
-                        max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None, copy: bool = False):
+                        max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None, copy: bool = False,
+                        wait: bool = True):
         """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
         rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
         utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
         (tests: batch-composition invariance). With copy=False the waveforms are views into the engine's page-locked result
-        buffers (one per group), valid until the next call."""
+        buffers (one per group, two alternating sets), valid until the call after the next one. Groups are issued
+        asynchronously: the device->host copy of one group overlaps the computation of the next. wait=False returns before the
+        last copies have landed — call `engine.wait()` before reading the waveforms; issuing the next synthesize_many first
+        overlaps its computation with these copies (request streams)."""
         from .scheduler import length_buckets
         n = len(texts)
         ids, mask = self.engine.text_to_ids(texts, langs)
         lens = mask.reshape(n, -1).sum(1).astype(np.int64)
         out: List[Optional[Tuple[np.ndarray, float]]] = [None] * n
+        self._parity = 1 - getattr(self, "_parity", 1)
         for gi, grp in enumerate(length_buckets(lens, max_batch, 1e9)):
             g = np.asarray(grp)
             T = int(lens[g].max())
             r = self.engine.synthesize_packed(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed,
-                                              seed=seed, noise=None if noise is None else noise[g], pinned=f"wav_packed{gi}")
+                                              seed=seed, noise=None if noise is None else noise[g],
+                                              pinned=f"wav_packed{gi}_{self._parity}", wait=False)
             for k, i in enumerate(grp):
-                out[i] = (r["wavs"][k].copy() if copy else r["wavs"][k], float(r["duration"][k]))
+                out[i] = (r["wavs"][k], float(r["duration"][k]))
+        if wait or copy:
+            self.engine.wait()
+            if copy:
+                out = [(w.copy(), d) for w, d in out]
         return out
 
 

@@ -364,3 +364,25 @@ def test_two_handles_in_two_threads(rig):
     finally:
         for e in engs:
             e.close()
+
+
+def test_asynchronous_request_stream_equals_synchronous_calls(rig):
+    """stc_synthesize_packed_async / stc_wait: three calls issued back to back (the copy of call k overlapping call k+1,
+    alternating device result buffers and staging halves) deliver exactly what the synchronous entry point computes."""
+    eng = rig["eng"]
+    jobs = [_inputs(rig, 300 + k, 3 + k, 30, 110) for k in range(3)]
+    want = [eng.synthesize_packed(*j, 2, 1.05, seed=40 + k) for k, j in enumerate(jobs)]
+    got = [eng.synthesize_packed(*j, 2, 1.05, seed=40 + k, pinned=f"t{k}", wait=False) for k, j in enumerate(jobs)]
+    eng.wait()
+    for w, g in zip(want, got):
+        np.testing.assert_array_equal(w["duration"], g["duration"])
+        np.testing.assert_array_equal(w["wav_lengths"], g["wav_lengths"])
+        for a, b in zip(w["wavs"], g["wavs"]):
+            np.testing.assert_array_equal(a, b)
+    # a synchronous call after asynchronous ones drains them first
+    g2 = eng.synthesize_packed(*jobs[0], 2, 1.05, seed=40, pinned="t0", wait=False)
+    s2 = eng.synthesize_packed(*jobs[1], 2, 1.05, seed=41)
+    for a, b in zip(g2["wavs"], want[0]["wavs"]):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(s2["wavs"], want[1]["wavs"]):
+        np.testing.assert_array_equal(a, b)
