@@ -134,7 +134,7 @@ int stc_synthesize_packed(stc_handle* h, const int64_t* text_ids, const float* t
  * (duration_out / wav_lengths_out / wav_offsets_out are valid on return) and all device work including the device->host copy of
  * the waveform has been enqueued. wav_out_pinned must be page-locked (stc_pinned_alloc) and is valid after stc_wait(h). The next
  * stc_synthesize_packed_async on the same handle may be issued BEFORE stc_wait: its computation overlaps this call's copy (two
- * alternating device result buffers), so at most two calls may be outstanding per wait. Any synchronous entry point drains
+ * alternating device result buffers; a third call blocks until the first has landed). Any synchronous entry point drains
  * outstanding asynchronous calls first. Noise: device Philox keyed by `seed`. */
 int stc_synthesize_packed_async(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
                                 const float* style_dp, int B, int T, int total_step, float speed, uint64_t seed,

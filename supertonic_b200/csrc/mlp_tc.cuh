@@ -385,26 +385,69 @@ convnext_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
     convnext_mlp_body<false>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
 }
 
-// x <- ((p0 + p1 + p2 + p3 + b2) * gamma + x) * mask : the four hidden-slice partials in rank order (deterministic)
+// x <- ((p0 + p1 + p2 + p3 + b2) * gamma + x) * mask : the four hidden-slice partials in rank order (deterministic).
+// One warp per row (lane owns 8 consecutive channels), so what FOLLOWS the block in the graphs can ride along instead of
+// costing a launch of its own:
+//   add_vec : x <- (x + add_vec) * mask           (time conditioning after a ConvNeXt block, cpp-side: vector_estimator graph)
+//   out     : the next layer's tensor-core operand — LayerNorm(x) (pre-LN of an attention layer; ln_g / ln_b) or x itself
+//             (ln_g == null; input of an output projection) as split-bf16
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
-                  const float* __restrict__ mask, float* __restrict__ x, int M) {
+                  const float* __restrict__ mask, float* __restrict__ x, int M, const float* __restrict__ add_vec,
+                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
     pdl_trigger(); pdl_wait();
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= (size_t)M * C) return;
-    const int row = (int)(i / C), col = (int)(i % C);
-    float4 acc = *reinterpret_cast<const float4*>(partial + i);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= M) return;
+    const int c0 = lane * 8;
+    const size_t i = (size_t)row * C + c0;
+    float y[8];
+    {
+        const float4 a0 = *reinterpret_cast<const float4*>(partial + i), a1 = *reinterpret_cast<const float4*>(partial + i + 4);
+        y[0] = a0.x; y[1] = a0.y; y[2] = a0.z; y[3] = a0.w; y[4] = a1.x; y[5] = a1.y; y[6] = a1.z; y[7] = a1.w;
+    }
 #pragma unroll
     for (int s = 1; s < CS; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(partial + s * slice + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const float4 v0 = *reinterpret_cast<const float4*>(partial + s * slice + i), v1 = *reinterpret_cast<const float4*>(partial + s * slice + i + 4);
+        y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x; y[5] += v1.y; y[6] += v1.z; y[7] += v1.w;
     }
-    const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + col)), g = __ldg(reinterpret_cast<const float4*>(gamma + col));
-    const float4 r = *reinterpret_cast<const float4*>(x + i);
     const float mk = mask ? __ldg(mask + row) : 1.f;
-    acc.x = ((acc.x + b.x) * g.x + r.x) * mk; acc.y = ((acc.y + b.y) * g.y + r.y) * mk;
-    acc.z = ((acc.z + b.z) * g.z + r.z) * mk; acc.w = ((acc.w + b.w) * g.w + r.w) * mk;
-    *reinterpret_cast<float4*>(x + i) = acc;
+    float bb[8], gg[8], rr[8];
+    *reinterpret_cast<float4*>(bb) = __ldg(reinterpret_cast<const float4*>(b2 + c0)); *reinterpret_cast<float4*>(bb + 4) = __ldg(reinterpret_cast<const float4*>(b2 + c0 + 4));
+    *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(gamma + c0)); *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    *reinterpret_cast<float4*>(rr) = *reinterpret_cast<const float4*>(x + i); *reinterpret_cast<float4*>(rr + 4) = *reinterpret_cast<const float4*>(x + i + 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = ((y[j] + bb[j]) * gg[j] + rr[j]) * mk;
+    if (add_vec) {
+        float tt[8];
+        *reinterpret_cast<float4*>(tt) = __ldg(reinterpret_cast<const float4*>(add_vec + c0)); *reinterpret_cast<float4*>(tt + 4) = __ldg(reinterpret_cast<const float4*>(add_vec + c0 + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (y[j] + tt[j]) * mk;
+    }
+    *reinterpret_cast<float4*>(x + i) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(x + i + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    if (!out_hi) return;
+    if (ln_g) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += y[j];
+        const float mean = warp_sum<float>(s) / (float)C;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { y[j] -= mean; v += y[j] * y[j]; }
+        const float inv = 1.0f / sqrtf(warp_sum<float>(v) / (float)C + eps);
+        float g8[8], h8[8];
+        *reinterpret_cast<float4*>(g8) = __ldg(reinterpret_cast<const float4*>(ln_g + c0)); *reinterpret_cast<float4*>(g8 + 4) = __ldg(reinterpret_cast<const float4*>(ln_g + c0 + 4));
+        *reinterpret_cast<float4*>(h8) = __ldg(reinterpret_cast<const float4*>(ln_b + c0)); *reinterpret_cast<float4*>(h8 + 4) = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = y[j] * inv * g8[j] + h8[j];
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) tc::split_pair(y[2 * t], y[2 * t + 1], hi[t], lo[t]);
+    *reinterpret_cast<uint4*>(out_hi + i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out_lo + i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 }  // namespace mlp

@@ -69,6 +69,13 @@ struct KV {
     bool tc = false;
 };
 
+// What follows a ConvNeXt block in the graph and can ride in its final (reduce) kernel instead of a launch of its own.
+struct PostOps {
+    const float* add_vec = nullptr;                      // x <- (x + add_vec) * mask   (time conditioning)
+    const float* ln_g = nullptr; const float* ln_b = nullptr;   // with `out`: LayerNorm(x); without ln_g: x itself
+    const Act* out = nullptr;                            // split-bf16 operand of the next layer
+};
+
 struct VeCtx {
     Seq lat, text, style;             // latent frames (packed or rectangle), text tokens [B,T], style tokens [B,S]
     std::vector<KV> kv;               // per cross-attention layer: step-invariant, hoisted out of the Euler loop
@@ -173,16 +180,18 @@ struct Handle {
                                          const Seq& seq, float eps, T* out_plain, const Act* out_act);
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
-    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq);
+    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr);
+    void apply_post(const PostOps& post, float* x, const Seq& seq, int C);      // the same post-ops as separate launches
     int mlp_form(const ConvNeXt& c, int rows) const;
-    void fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form);
+    void fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
+                   const PostOps* post = nullptr);
     // env STC_MLP_PRODUCER=1: compute LayerNorm(dwconv(x)) inside the fused MLP kernel instead of a separate launch. Measured
     // SLOWER (15.3 vs 11.5 ms/step): with 226 KB of shared memory in use the SM has no L1 left, so every tap row and every
     // per-channel weight is re-fetched from L2 (~1.6 MB per CTA on top of the 0.5 MB of GEMM weights). OFF by default.
     bool mlp_producer = false;
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
     int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks)
-    void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre);
+    void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre, const Act* xn_pre = nullptr);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
     bool attn_on_tc(const Attention& a, const Seq& ks) const;
@@ -685,7 +694,8 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
 }
 
 // a == nullptr: producer mode — the kernel computes LayerNorm(dwconv(x)) itself (needs seq, c.K <= mlp::KMAX).
-void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form) {
+void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
+                       const PostOps* post) {
     mlp::Params p{};
     p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
     if (!a) {
@@ -707,8 +717,11 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
         else {
             launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                        mah, mal, w1h, w1l, w2h, w2l, p);
-            launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
-                       (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows);
+            const bool po = post && form == 2;
+            launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
+                       (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, po ? post->add_vec : (const float*)nullptr,
+                       po ? post->ln_g : (const float*)nullptr, po ? post->ln_b : (const float*)nullptr, 1e-6f,
+                       po && post->out ? post->out->hi : (__nv_bfloat16*)nullptr, po && post->out ? post->out->lo : (__nv_bfloat16*)nullptr);
             ++launches;
         }
         ++launches;
@@ -717,27 +730,38 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
     release(mk);
 }
 
+void Handle::apply_post(const PostOps& post, float* x, const Seq& seq, int C) {
+    const int rows = seq.rows;
+    if (post.add_vec)
+        STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, post.add_vec, seq.mask, rows, C, 0, seq.off, seq.B);
+    if (post.out) {
+        if (post.ln_g) dwconv_ln<float>(x, nullptr, post.ln_g, post.ln_b, C, seq, 1e-6f, nullptr, post.out);
+        else to_act(x, (size_t)rows * C, *post.out);
+    }
+}
+
 template <typename T>
-void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq) {
+void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post) {
     size_t mk = mark();
     int rows = seq.rows;
     Epilogue e1; e1.gelu = 1;
     Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
         const int form = mlp_form(c, rows);
+        const bool post_fused = post && form == 2;          // the split form's reduce kernel carries the post-ops
         if (form && mlp_producer && c.K <= mlp::KMAX) {
-            fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form);
-            release(mk);
-            return;
+            fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
+        } else {
+            Act a = ws_act((size_t)rows * c.C);
+            dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
+            if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
+            else {
+                Act hid = ws_act((size_t)rows * c.H);
+                gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
+                gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
+            }
         }
-        Act a = ws_act((size_t)rows * c.C);
-        dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-        if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form);
-        else {
-            Act hid = ws_act((size_t)rows * c.H);
-            gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
-            gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
-        }
+        if (post && !post_fused) apply_post(*post, x, seq, c.C);
     } else {
         T* a = ws<T>((size_t)rows * c.C); T* hid = ws<T>((size_t)rows * c.H);
         dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, a, nullptr);
@@ -836,11 +860,12 @@ void Handle::attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const 
 }
 
 // Pre-LN multi-head attention with residual. Self-attention: ctx == nullptr && pre == nullptr (keys from LN(x), kseq = qseq).
-void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* ctx, const Seq& ks_in, const KV* pre) {
+void Handle::attention(const Attention& a, float* x, const Seq& qs, const Act* ctx, const Seq& ks_in, const KV* pre, const Act* xn_pre) {
     size_t mk = mark();
     int rows = qs.rows, dh = a.C / a.heads;
-    Act xn = ws_act((size_t)rows * a.C);
-    dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, qs, 1e-6f, nullptr, &xn);
+    Act xn;
+    if (xn_pre) xn = *xn_pre;                                  // LayerNorm(x) already produced by the preceding block's reduce kernel
+    else { xn = ws_act((size_t)rows * a.C); dwconv_ln<float>(x, nullptr, a.ln_g, a.ln_b, a.C, qs, 1e-6f, nullptr, &xn); }
     const Seq& ks = a.ctx_kind == CTX_SELF ? qs : ks_in;
     if (a.ctx_kind == CTX_SELF) ctx = &xn;
     KV local;
@@ -950,15 +975,29 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq,
     STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], tseq.mask, x, rows, C, cfg.vocab_size, tseq.off, B, T);
     Act sty = ws_act((size_t)B * S * Cs);
     to_act(style_ttl, (size_t)B * S * Cs, sty);
-    for (const Layer& l : te.layers) {
-        if (l.type == L_CONVNEXT) convnext<float>(te.cn[l.idx], x, tseq);
-        else if (l.type == L_ATTN) {
+    Act nxt = ws_act((size_t)rows * C);
+    bool nxt_ready = false;
+    for (size_t li = 0; li < te.layers.size(); ++li) {
+        const Layer& l = te.layers[li];
+        if (l.type == L_CONVNEXT) {
+            PostOps post; bool any = false;
+            if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_ATTN) {
+                const Attention& a = te.at[te.layers[li + 1].idx];
+                post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = nxt_ready = true;
+            } else if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_PROJ_OUT) {
+                post.out = &nxt; any = nxt_ready = true;
+            }
+            convnext<float>(te.cn[l.idx], x, tseq, any ? &post : nullptr);
+        } else if (l.type == L_ATTN) {
             const Attention& a = te.at[l.idx];
-            if (a.ctx_kind == CTX_SELF) attention(a, x, tseq, nullptr, tseq, nullptr);
-            else attention(a, x, tseq, &sty, sseq, nullptr);
+            const Act* pre_ln = nxt_ready ? &nxt : nullptr;
+            nxt_ready = false;
+            if (a.ctx_kind == CTX_SELF) attention(a, x, tseq, nullptr, tseq, nullptr, pre_ln);
+            else attention(a, x, tseq, &sty, sseq, nullptr, pre_ln);
         } else if (l.type == L_PROJ_OUT) {
-            Act xa = ws_act((size_t)rows * C);
-            to_act(x, (size_t)rows * C, xa);
+            Act xa = nxt;
+            if (!nxt_ready) { xa = ws_act((size_t)rows * C); to_act(x, (size_t)rows * C, xa); }
+            nxt_ready = false;
             Epilogue e; e.mask = tseq.mask;
             gemm(xa, rows, te.lin[l.idx], e, text_emb_cl, nullptr, te.lin[l.idx].N);
         }
@@ -1026,7 +1065,10 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
     const Seq& ls = vc.lat;
     int rows = ls.rows, C = ve.C, D = cfg.latent_channels, itc = 0;
     float* x = ws<float>((size_t)rows * C);
-    for (const Layer& l : ve.layers) {
+    Act nxt = ws_act((size_t)rows * C);           // operand a ConvNeXt block's reduce kernel prepares for the layer after it
+    bool nxt_ready = false;
+    for (size_t li = 0; li < ve.layers.size(); ++li) {
+        const Layer& l = ve.layers[li];
         switch (l.type) {
             case L_PROJ_IN: {
                 size_t m2 = mark();
@@ -1037,20 +1079,38 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
                 release(m2);
                 break;
             }
-            case L_CONVNEXT: convnext<float>(ve.cn[l.idx], x, ls); break;
+            case L_CONVNEXT: {
+                // fold what follows into the block's last kernel: time conditioning, the pre-LayerNorm of an attention layer,
+                // or the operand conversion for the output projection
+                PostOps post; bool any = false;
+                size_t nx = li + 1;
+                if (nx < ve.layers.size() && ve.layers[nx].type == L_TIME_COND) {
+                    post.add_vec = tvec + (size_t)(itc++) * C; any = true; ++li; ++nx;          // the time_cond layer is consumed here
+                }
+                if (nx < ve.layers.size() && ve.layers[nx].type == L_ATTN) {
+                    const Attention& a = ve.at[ve.layers[nx].idx];
+                    post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = true; nxt_ready = true;
+                } else if (nx < ve.layers.size() && ve.layers[nx].type == L_PROJ_OUT) {
+                    post.out = &nxt; any = true; nxt_ready = true;
+                }
+                convnext<float>(ve.cn[l.idx], x, ls, any ? &post : nullptr);
+                break;
+            }
             case L_TIME_COND:
                 STC_LAUNCH(this, add_rowvec_mask_kernel<float>, cdiv((size_t)rows * C, 256), 256, 0, x, tvec + (size_t)(itc++) * C, ls.mask,
                            rows, C, 0, ls.off, ls.B);
                 break;
             case L_ATTN: {
                 const Attention& a = ve.at[l.idx];
-                attention(a, x, ls, nullptr, a.ctx_kind == CTX_TEXT ? vc.text : vc.style, &vc.kv[a.kv_slot]);
+                attention(a, x, ls, nullptr, a.ctx_kind == CTX_TEXT ? vc.text : vc.style, &vc.kv[a.kv_slot], nxt_ready ? &nxt : nullptr);
+                nxt_ready = false;
                 break;
             }
             case L_PROJ_OUT: {
                 size_t m2 = mark();
-                Act xa = ws_act((size_t)rows * C);
-                to_act(x, (size_t)rows * C, xa);
+                Act xa = nxt;
+                if (!nxt_ready) { xa = ws_act((size_t)rows * C); to_act(x, (size_t)rows * C, xa); }
+                nxt_ready = false;
                 Epilogue e; e.scale = dtvec; e.resid = x_lat; e.mask = ls.mask;   // x <- (x + v*dt) * mask
                 gemm(xa, rows, ve.lin[l.idx], e, x_lat, nullptr, D);
                 release(m2);
@@ -1471,6 +1531,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         int slot = 0;
         if (async_copy) {                              // this call's half of the pinned offset staging + its device result buffer
             slot = h->slot; h->slot ^= 1;
+            // the call that last used this slot (two calls ago) must have run to the end of its copy before its staging half
+            // is rewritten: at most two asynchronous calls are in flight, the library throttles the caller here
+            STC_CUDA(cudaEventSynchronize(h->copy_done[slot]));
             h->h_stage_off = slot ? h->h_stage_cap / 2 : 0;
             h->h_stage_lim = slot ? h->h_stage_cap : h->h_stage_cap / 2;
             mode |= 16 | (slot << 5);                  // graphs bake the staging / result addresses: one set per slot

@@ -172,34 +172,47 @@ std::vector<TextToSpeech::Utterance> TextToSpeech::many(const std::vector<std::s
     std::vector<Utterance> out(n);
     const int cs = geo_.chunk_size;
     ++calls_;
-    for (int g0 = 0; g0 < n; g0 += max_batch) {
-        std::vector<int> grp(order.begin() + g0, order.begin() + std::min(n, g0 + max_batch));
-        const int B = (int)grp.size(), Tg = tok[grp.back()];
-        std::vector<int64_t> gi((size_t)B * Tg); std::vector<float> gm((size_t)B * Tg);
-        int64_t toks = 0;
-        for (int k = 0; k < B; ++k) {
-            std::copy_n(ids.begin() + (size_t)grp[k] * T, Tg, gi.begin() + (size_t)k * Tg);
-            std::copy_n(mask.begin() + (size_t)grp[k] * T, Tg, gm.begin() + (size_t)k * Tg);
-            toks += tok[grp[k]];
+    // Groups go out as an asynchronous request stream (stc_synthesize_packed_async): the device->host copy of group g runs
+    // while group g+1 is computed. Each group gets its own page-locked result buffer; everything lands at stc_wait.
+    struct Pending { std::vector<int> grp; float* wav = nullptr; std::vector<int64_t> off, wl; std::vector<float> dur; };
+    std::vector<Pending> pend;
+    auto free_all = [&]() { for (auto& p : pend) stc_pinned_free(p.wav); };
+    try {
+        for (int g0 = 0; g0 < n; g0 += max_batch) {
+            Pending p;
+            p.grp.assign(order.begin() + g0, order.begin() + std::min(n, g0 + max_batch));
+            const int B = (int)p.grp.size(), Tg = tok[p.grp.back()];
+            std::vector<int64_t> gi((size_t)B * Tg); std::vector<float> gm((size_t)B * Tg);
+            int64_t toks = 0;
+            for (int k = 0; k < B; ++k) {
+                std::copy_n(ids.begin() + (size_t)p.grp[k] * T, Tg, gi.begin() + (size_t)k * Tg);
+                std::copy_n(mask.begin() + (size_t)p.grp[k] * T, Tg, gm.begin() + (size_t)k * Tg);
+                toks += tok[p.grp[k]];
+            }
+            Style st = style.slice(p.grp);
+            int64_t cap = (int64_t)((double)toks * 0.12 * sample_rate_) + (int64_t)(B + 8) * cs;
+            p.off.assign(B + 1, 0); p.wl.assign(B, 0); p.dur.assign(B, 0.f);
+            for (int attempt = 0;; ++attempt) {
+                void* mem = nullptr;
+                if (stc_pinned_alloc((size_t)cap * sizeof(float), &mem) != STC_OK) raise(nullptr, "stc_pinned_alloc");
+                p.wav = static_cast<float*>(mem);
+                int rc = stc_synthesize_packed_async(engine_, gi.data(), gm.data(), st.getTtlData().data(), st.getDpData().data(), B, Tg,
+                                                     total_step, speed, seed_ + calls_, p.wav, cap, p.off.data(), p.dur.data(), p.wl.data());
+                if (rc == STC_ERR_CAPACITY && attempt == 0 && p.off[B] > cap) { stc_pinned_free(p.wav); p.wav = nullptr; cap = p.off[B]; continue; }
+                if (rc != STC_OK) { stc_pinned_free(p.wav); p.wav = nullptr; raise(engine_, "stc_synthesize_packed_async"); }
+                break;
+            }
+            pend.push_back(std::move(p));          // (the library keeps at most two calls in flight)
         }
-        Style st = style.slice(grp);
-        int64_t cap = (int64_t)((double)toks * 0.12 * sample_rate_) + (int64_t)(B + 8) * cs;
-        std::vector<int64_t> off(B + 1), wl(B);
-        std::vector<float> dur(B), wav;
-        for (int attempt = 0;; ++attempt) {
-            wav.resize((size_t)cap);
-            int rc = stc_synthesize_packed(engine_, gi.data(), gm.data(), st.getTtlData().data(), st.getDpData().data(), B, Tg, total_step,
-                                           speed, nullptr, 0, seed_ + calls_, wav.data(), cap, off.data(), dur.data(), wl.data(), nullptr);
-            if (rc == STC_ERR_CAPACITY && attempt == 0 && off[B] > cap) { cap = off[B]; continue; }
-            if (rc != STC_OK) raise(engine_, "stc_synthesize_packed");
-            break;
+        if (stc_wait(engine_) != STC_OK) raise(engine_, "stc_wait");
+    } catch (...) { stc_wait(engine_); free_all(); throw; }
+    for (auto& p : pend)
+        for (size_t k = 0; k < p.grp.size(); ++k) {
+            Utterance& u = out[p.grp[k]];
+            u.duration = p.dur[k];
+            u.wav.assign(p.wav + p.off[k], p.wav + p.off[k] + p.wl[k]);
         }
-        for (int k = 0; k < B; ++k) {
-            Utterance& u = out[grp[k]];
-            u.duration = dur[k];
-            u.wav.assign(wav.begin() + off[k], wav.begin() + off[k] + wl[k]);
-        }
-    }
+    free_all();
     return out;
 }
 
