@@ -717,11 +717,13 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
         else {
             launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                        mah, mal, w1h, w1l, w2h, w2l, p);
-            const bool po = post && form == 2;
-            launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
-                       (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, po ? post->add_vec : (const float*)nullptr,
-                       po ? post->ln_g : (const float*)nullptr, po ? post->ln_b : (const float*)nullptr, 1e-6f,
-                       po && post->out ? post->out->hi : (__nv_bfloat16*)nullptr, po && post->out ? post->out->lo : (__nv_bfloat16*)nullptr);
+            if (post)
+                launch_pdl(this, mlp::mlp_reduce_post_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
+                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
+                           post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr);
+            else
+                launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
+                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows);
             ++launches;
         }
         ++launches;
