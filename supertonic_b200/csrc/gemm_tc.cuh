@@ -111,6 +111,15 @@ STC_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::tf32: fp32 operands straight from shared memory (the tensor core reads the upper 19 bits), K = 8 per instruction
+// (32 bytes of a 128-byte swizzled row, like K = 16 of bf16), half the bf16 rate per element.
+STC_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 STC_DEVINL void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -144,6 +153,9 @@ STC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {          // a = b = TF32 (format 2)
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 struct Params {
     int M, N, K;
@@ -153,6 +165,7 @@ struct Params {
     __nv_bfloat16* out_lo;
     int ldo;
     int split;
+    int round_tf32;                 // fp32 output is the tf32 operand of the next GEMM: round it to nearest here
     int cm, cn;                     // cluster shape in tiles (cm * cn CTAs per cluster)
 };
 
@@ -212,7 +225,10 @@ struct TileIter {
 
 // kRope: the rotary-embedding epilogue (Q / K projections) lives in its own instantiation — its sincosf slow path costs
 // registers, a stack frame and unrolling in every epilogue it is compiled into (the vocoder GEMMs lost 10 % to it).
-template <int BN, bool kRope = false>
+// kTf32: single-pass TF32 arithmetic for the vocoder (DESIGN.md "precision"): map_a_hi / map_w_hi describe fp32 [rows, K]
+// operands (box 32 elements = one 128-byte swizzled row); a stage still holds 64 K-elements — K sub-block 0 where the bf16
+// hi halves go, sub-block 1 where the lo halves go — and issues 8 MMAs (2 sub-blocks x 4 K-slices of 8) instead of 12.
+template <int BN, bool kRope = false, bool kTf32 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -275,6 +291,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     mbar_wait(empty_bar(s), ph ^ 1);                         // freed by every CTA that receives these slices
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
                     mbar_expect_tx(full_bar(s), T::STAGE_BYTES);             // own slices + the peers' multicasts
+                    if constexpr (kTf32) {
+                        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                        tma_load_2d(st + T::A_BYTES, &map_a_hi, full_bar(s), kb * BK + BK / 2, m0);
+                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
+                        tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_hi, full_bar(s), kb * BK + BK / 2, n0);
+                        continue;
+                    }
                     if (cn > 1) {
                         tma_load_2d_mc(st + a_off, &map_a_hi, full_bar(s), kb * BK, m0, row_mask);
                         tma_load_2d_mc(st + T::A_BYTES + a_off, &map_a_lo, full_bar(s), kb * BK, m0, row_mask);
@@ -294,7 +317,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = kTf32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
         const uint16_t free_mask = row_mask | col_mask;
         uint32_t kbc = 0, it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
@@ -311,12 +334,25 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
                     const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + T::A_BYTES);
                     const uint64_t w_hi = make_smem_desc(st + 2 * T::A_BYTES), w_lo = make_smem_desc(st + 2 * T::A_BYTES + T::W_BYTES);
+                    if constexpr (kTf32) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B = 8 fp32 per K-slice
+                            umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            umma_tf32(tmem_d, a_lo + adv, w_lo + adv, idesc, 1);       // K sub-block 1 (the "lo" slots)
+                        }
+                    } else {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);       // 32 B per K-slice inside the swizzle row
                         umma_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
                         umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
                         umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
                     }
                     if (csize > 1) umma_commit_mc(empty_bar(s), free_mask);          // frees the stage in every sender
                     else umma_commit(empty_bar(s));
@@ -397,6 +433,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             *reinterpret_cast<uint2*>(p.out_hi + o) = hi;
                             *reinterpret_cast<uint2*>(p.out_lo + o) = lo;
                         } else {
+                            if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                             *reinterpret_cast<float4*>(p.out_f32 + o) = v;
                         }
                     }

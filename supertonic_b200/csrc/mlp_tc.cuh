@@ -45,7 +45,9 @@ struct Params {
     // here — depthwise conv (+bias) -> LayerNorm of the residual stream x, straight into the swizzled operand layout.
     const float* dw_wT; const float* dw_b; const float* ln_g; const float* ln_b;     // taps [K][C], bias, LayerNorm scale / shift
     const int* off; int B; int K, dil, pad_left; float eps;                          // packed sequences of x, conv geometry
+    long long* trace;               // debug (stc_debug_mlp with STC_MLP_TRACE=1): clock64() stamps of CTA 0's pipeline events
 };
+#define STC_TRACE(idx) do { if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[idx] = clock64(); } while (0)
 
 constexpr int KMAX = 5;             // depthwise taps supported by the producer mode
 
@@ -383,6 +385,236 @@ convnext_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                           const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                           const Params p) {
     convnext_mlp_body<false>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+// ===== "TS" form of the split kernel: P = GELU(S) never touches shared memory =================================================
+// The split kernel above is serial per CTA — phase 1 (all of S) -> GELU -> phase 2 — because P overwrites the a-tile: its tensor
+// pipe is busy 43 % of the kernel (ncu, profiles/r1w_mlp_ncu_full_summary.txt). Here the epilogue warps write P back INTO the
+// TMEM columns S came from (fp32 S block of 64 columns -> 32 columns of packed bf16 hi + 32 of lo) and phase 2 reads its A
+// operand from TMEM (tcgen05.mma with [a_tmem], the form flash-attention kernels use for P.V). Nothing aliases the a-tile, so
+//   * phase 1 runs hidden-half-major (nh outer): S[:, 0:128] is complete after 4 of its 8 weight units and its GELU overlaps
+//     the MMAs of S[:, 128:256];
+//   * phase 2 is K-block-major: its first half consumes P blocks 0,1 while the epilogue warps still produce blocks 2,3.
+// TMEM A layout (M = 128, K-major bf16): lane = row, 32-bit column c of a K=16 slice holds elements (2c, 2c+1), 8 columns per
+// slice. Per 16 hidden units g of block j: hi at column 64 j + 16 g, lo at + 8 — each warp only overwrites columns it has
+// already read, so any number of warps per lane quarter can share a block.
+STC_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+STC_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+STC_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+STC_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+STC_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> STC_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// Weight units u = 0..15 (32 KB each: 128 weight rows x 64 K, hi + lo). Phase 1 (u < 8) streams W1 through the 3-slot ring;
+// phase 2 streams W2 through the ring AND through the dead a-tile (4 more slots, units 11..14), so that 7 of its 8 units are in
+// flight as soon as S is complete (a unit takes ~2000 cycles to land when three share the SM's ~52 B/clk ingest).
+struct UnitSlot { int ring; int idx; uint32_t par; };      // ring slot (idx, use parity) or a-region slot (idx, parity 0)
+STC_DEVINL UnitSlot unit_slot(int u) {
+    if (u >= 11 && u <= 14) return UnitSlot{0, u - 11, 0u};
+    if (u == 15) return UnitSlot{1, 2, 1u};                 // fourth use of ring slot 2 (after u = 2, 5, 8)
+    return UnitSlot{1, u % SLOTS, (uint32_t)((u / SLOTS) & 1)};
+}
+
+template <int NEPI>             // epilogue warps: 8 or 16 (NEPI / 4 per TMEM lane quarter)
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1)
+convnext_mlp_ts_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                       const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                       const __grid_constant__ CUtensorMap map_part, const Params p) {
+    using namespace tc;
+    static_assert(NEPI == 8 || NEPI == 16, "two or four epilogue warps per TMEM lane quarter");
+    constexpr int NP = NEPI / 4;              // warps sharing a lane quarter
+    constexpr int CW = BK / NP;               // S columns of a 64-column block per warp (32 or 16)
+    constexpr int OW = C / NP;                // output columns per warp in the final epilogue
+    constexpr int NU = 2 * UNITS_PER_PHASE;
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 64) p.trace[3] = clock64();
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar = smem_base + OFF_BAR;
+    const uint32_t bar_a = bar, bar_o = bar + 16;
+    auto bar_s = [&](int h) { return bar + 8 + 104u * h; };            // +8, +112
+    auto full_bar = [&](int s) { return bar + 24 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar + 48 + 8u * s; };
+    auto bar_p = [&](int j) { return bar + 72 + 8u * j; };
+    auto afull_bar = [&](int i) { return bar + 128 + 8u * i; };
+    const uint32_t tmem_slot = bar + 104;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)(blockIdx.x % CS);
+    const int m0 = (int)(blockIdx.x / CS) * BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
+        tma_prefetch_desc(&map_w1_lo); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo); tma_prefetch_desc(&map_part);
+        mbar_init(bar_a, 1); mbar_init(bar_s(0), 1); mbar_init(bar_s(1), 1); mbar_init(bar_o, 1);
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(afull_bar(i), 1);
+        for (int j = 0; j < HC / BK; ++j) mbar_init(bar_p(j), NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        STC_TRACE(4);
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); STC_TRACE(5); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    if (warp == 2) STC_TRACE(0);
+    pdl_wait();
+    if (warp == 2) STC_TRACE(1);
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_a, X_BYTES);
+            for (int kb = 0; kb < C / BK; ++kb) {
+                tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_a, kb * BK, m0);
+                tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
+            }
+            for (int u = 0; u < NU; ++u) {
+                const UnitSlot us = unit_slot(u);
+                uint32_t dst, fb;
+                if (us.ring) {
+                    mbar_wait(empty_bar(us.idx), us.par ^ 1);
+                    dst = smem_base + OFF_RING + us.idx * UNIT; fb = full_bar(us.idx);
+                } else {
+                    if (us.idx == 0) mbar_wait(bar_s(1), 0);          // every phase-1 MMA has retired: the a-tile is dead
+                    dst = smem_base + OFF_X + us.idx * UNIT; fb = afull_bar(us.idx);
+                }
+                if (p.trace && blockIdx.x == 0) p.trace[40 + u] = clock64();
+                mbar_expect_tx(fb, UNIT);
+                const int v = u % UNITS_PER_PHASE;
+                if (u < UNITS_PER_PHASE) {          // W1[hidden rows, C]: hidden half nh = v / 4 (outer), K block kb = v % 4 of C
+                    const int nh = v >> 2, kb = v & 3;
+                    tma_load_2d(dst, &map_w1_hi, fb, kb * BK, crank * HC + nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w1_lo, fb, kb * BK, crank * HC + nh * 128);
+                } else {                            // W2[C rows, hidden]: K block kb = v / 2 (outer) of this CTA's hidden slice, rows nh*128
+                    const int kb = v >> 1, nh = v & 1;
+                    tma_load_2d(dst, &map_w2_hi, fb, crank * HC + kb * BK, nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w2_lo, fb, crank * HC + kb * BK, nh * 128);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
+        mbar_wait(bar_a, 0);
+        STC_TRACE(2);
+        for (int u = 0; u < NU; ++u) {
+            const UnitSlot us = unit_slot(u);
+            const int v = u % UNITS_PER_PHASE;
+            const bool second = u >= UNITS_PER_PHASE;
+            const int kb = second ? (v >> 1) : (v & 3), nh = second ? (v & 1) : (v >> 2);
+            if (second && nh == 0) mbar_wait(bar_p(kb), 0);             // P block kb is in TMEM
+            mbar_wait(us.ring ? full_bar(us.idx) : afull_bar(us.idx), us.par);
+            tc_fence_after();
+            STC_TRACE(8 + u);
+            if (elect_one()) {
+                const uint32_t st = us.ring ? smem_base + OFF_RING + us.idx * UNIT : smem_base + OFF_X + us.idx * UNIT;
+                const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
+                if (!second) {
+                    const uint32_t xk = smem_base + OFF_X + kb * KBLK;
+                    const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
+                    const uint32_t d = tmem_base + nh * 128;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16(d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        umma_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                } else {
+                    const uint32_t d = tmem_base + 256 + nh * 128;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        const uint32_t p_hi = tmem_base + kb * BK + k * UMMA_K, p_lo = p_hi + UMMA_K / 2;
+                        umma_bf16_ts(d, p_lo, w_hi + adv, idesc, (kb | k) != 0);
+                        umma_bf16_ts(d, p_hi, w_lo + adv, idesc, 1);
+                        umma_bf16_ts(d, p_hi, w_hi + adv, idesc, 1);
+                    }
+                }
+                if (us.ring) umma_commit(empty_bar(us.idx));
+                if (!second && kb == C / BK - 1) umma_commit(bar_s(nh));          // S[:, 128 nh .. +128) complete
+                if (u == NU - 1) umma_commit(bar_o);                               // partial O complete; every smem operand is dead
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue 1: P = split(GELU(S + b1)), in place in TMEM =====
+        const int q = warp & 3, part = (warp - 2) >> 2;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int j = 0; j < HC / BK; ++j) {
+            if ((j & 1) == 0) { mbar_wait(bar_s(j >> 1), 0); tc_fence_after(); if (warp == 2) STC_TRACE(24 + (j >> 1)); }
+#pragma unroll
+            for (int g = 0; g < CW / 16; ++g) {
+                const int col = j * BK + part * CW + g * 16;
+                uint32_t v[16], o[16];
+                __syncwarp();
+                tmem_ld16(trow + col, v);
+                const float* b1 = p.b1 + crank * HC + col;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float e0 = gelu_erf_mufu(__uint_as_float(v[2 * t]) + __ldg(b1 + 2 * t));
+                    const float e1 = gelu_erf_mufu(__uint_as_float(v[2 * t + 1]) + __ldg(b1 + 2 * t + 1));
+                    split_pair(e0, e1, o[t], o[8 + t]);
+                }
+                tmem_st16(trow + col, o);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p(j));
+            if (warp == 2) STC_TRACE(26 + j);
+        }
+        mbar_wait(bar_o, 0);               // all MMAs of this CTA retired: the a-tile region (staging below) and the O accumulator are ours
+        tc_fence_after();
+        if (warp == 2) STC_TRACE(30);
+        // ===== partial O (256 columns) -> global scratch by TMA: 32 rows x 32 columns (one 128-byte swizzled row per lane) per
+        //       store, two staging buffers per warp so that the copy of one box overlaps the TMEM read of the next =====
+        const uint32_t orow = trow + 256 + part * OW;
+        const uint32_t stg = smem_base + OFF_X + (uint32_t)(warp - 2) * 8192u;
+        const int mpad = ((p.M + BM - 1) / BM) * BM;
+        const int grow = crank * mpad + m0 + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < OW; c += 32) {
+            const uint32_t buf = stg + (uint32_t)((c >> 5) & 1) * 4096u;
+            if (c >= 64) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }        // the store that last read this buffer has drained
+            uint32_t v[32];
+            tmem_ld32(orow + c, v);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((ch ^ (lane & 7)) * 16)),
+                             "r"(v[4 * ch]), "r"(v[4 * ch + 1]), "r"(v[4 * ch + 2]), "r"(v[4 * ch + 3]) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_part, buf, part * OW + c, grow); bulk_commit(); }
+        }
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) STC_TRACE(31);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // x <- ((p0 + p1 + p2 + p3 + b2) * gamma + x) * mask : the four hidden-slice partials in rank order (deterministic).

@@ -151,13 +151,15 @@ struct Handle {
     void load(const std::string& onnx_dir);
     float* upload_f32(const float* p, size_t n);
     float* W(const OnnxFile& f, const std::string& name, size_t numel);
-    Linear make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, bool tc);
-    Linear make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, bool tc);
-    void load_net(const OnnxFile& f, const json& arch, Net& net, bool tc);
-    ConvNeXt load_convnext(const OnnxFile& f, const json& l, bool tc);
-    Attention load_attention(const OnnxFile& f, const json& l, bool tc);
+    Linear make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, int tc);
+    Linear make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, int tc);
+    void load_net(const OnnxFile& f, const json& arch, Net& net, int tc);
+    ConvNeXt load_convnext(const OnnxFile& f, const json& l, int tc);
+    Attention load_attention(const OnnxFile& f, const json& l, int tc);
     CUtensorMap encode_map(const void* ptr, int rows, int K, int box_rows);
     const CUtensorMap& tmap(const void* ptr, int rows, int K, int box_rows);
+    const CUtensorMap& tmap_f32(const void* ptr, int rows, int cols);
+    const CUtensorMap& tmap_tf32(const void* ptr, int rows, int K, int box_rows);
     struct GemmCfg { int bn, cm, cn; };
     GemmCfg pick_gemm(int M, int N, int K) const;
     GemmCfg force_cfg{0, 0, 0};      // debug / sweep override (bn == 0: heuristic)
@@ -165,6 +167,8 @@ struct Handle {
     // ---- workspace helpers
     template <typename T> T* ws(size_t n) { return static_cast<T*>(arena.alloc(n * sizeof(T))); }
     bool tc_mode() const { return precision == STC_PREC_BF16X3; }
+    Act ws_act_f32(size_t n) { Act a; a.f = ws<float>(n); return a; }       // operand of a kind::tf32 GEMM (or of the CUDA-core path)
+    Act ws_act_for(const Linear& w, size_t n) { return w.w_nk ? ws_act_f32(n) : ws_act(n); }
     Act ws_act(size_t n) {
         Act a;
         if (tc_mode()) { a.hi = ws<__nv_bfloat16>(n); a.lo = ws<__nv_bfloat16>(n); } else a.f = ws<float>(n);
@@ -190,7 +194,12 @@ struct Handle {
     // per-channel weight is re-fetched from L2 (~1.6 MB per CTA on top of the 0.5 MB of GEMM weights). OFF by default.
     bool mlp_producer = false;
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
-    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks)
+    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks), 4 "ts"
+    long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
+    bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
+                                      // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
+                                      // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
+    int mlp_epi = 8;                  // env STC_MLP_EPI: epilogue warps of the TS form (8 or 16)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre, const Act* xn_pre = nullptr);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
@@ -322,6 +331,42 @@ CUtensorMap Handle::encode_map(const void* ptr, int rows, int K, int box_rows) {
     return m;
 }
 
+// fp32 [rows, cols] row-major, box 32 x 32 (128-byte swizzled rows): destination of the fused MLP's TMA stores
+const CUtensorMap& Handle::tmap_f32(const void* ptr, int rows, int cols) {
+    auto key = std::make_tuple(ptr, rows, cols, -32);
+    auto it = map_cache.find(key);
+    if (it != map_cache.end()) return it->second;
+    if (map_cache.size() > 16384) map_cache.clear();
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed: " + std::to_string((int)r));
+    return map_cache.emplace(key, m).first->second;
+}
+
+// fp32 [rows, K] K-major GEMM operand for kind::tf32: box = 32 elements (one 128-byte swizzled row) x box_rows
+const CUtensorMap& Handle::tmap_tf32(const void* ptr, int rows, int K, int box_rows) {
+    auto key = std::make_tuple(ptr, rows, K, 100000 + box_rows);
+    auto it = map_cache.find(key);
+    if (it != map_cache.end()) return it->second;
+    if (map_cache.size() > 16384) map_cache.clear();
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK / 2, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled (tf32 operand) failed: " + std::to_string((int)r));
+    return map_cache.emplace(key, m).first->second;
+}
+
 const CUtensorMap& Handle::tmap(const void* ptr, int rows, int K, int box_rows) {
     auto key = std::make_tuple(ptr, rows, K, box_rows);
     auto it = map_cache.find(key);
@@ -338,11 +383,23 @@ static inline uint16_t bf16_bits_rn(float v) {
 }
 static inline float bf16_to_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
 
-Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, bool tc) {
+Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, int tc) {
     Linear l; l.K = K; l.N = N;
     l.w_kn = upload_f32(w_kn.data(), w_kn.size());
     l.bias = upload_f32(bias.data(), bias.size());
-    if (tc) {
+    if (tc == 2) {          // kind::tf32 operand: [N,K] K-major fp32, rounded to nearest TF32
+        std::vector<float> nk((size_t)N * K);
+        for (int k = 0; k < K; ++k)
+            for (int n = 0; n < N; ++n) {
+                uint32_t u; memcpy(&u, &w_kn[(size_t)k * N + n], 4);
+                if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+                memcpy(&nk[(size_t)n * K + k], &u, 4);
+            }
+        l.w_nk = upload_f32(nk.data(), nk.size());
+        if (K % 4) throw StcError(STC_ERR_UNSUPPORTED, "tf32 GEMM needs K % 4 == 0, got " + std::to_string(K));
+        if (N % 4) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs N % 4 == 0, got " + std::to_string(N));
+        l.has_maps = true;
+    } else if (tc) {
         std::vector<uint16_t> hi((size_t)N * K), lo((size_t)N * K);
         for (int k = 0; k < K; ++k)
             for (int n = 0; n < N; ++n) {
@@ -362,13 +419,13 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
     return l;
 }
 
-Linear Handle::make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, bool tc) {
+Linear Handle::make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, int tc) {
     const OnnxTensor& w = get_tensor(f, prefix + ".weight", (size_t)K * N);
     const OnnxTensor& b = get_tensor(f, prefix + ".bias", (size_t)N);
     return make_linear_host(std::vector<float>(w.f32(), w.f32() + w.numel()), std::vector<float>(b.f32(), b.f32() + b.numel()), K, N, tc);
 }
 
-ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, bool tc) {
+ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, int tc) {
     ConvNeXt c{};
     std::string p = l.at("name");
     c.C = l.at("C"); c.H = l.at("H"); c.K = l.at("K"); c.dil = l.at("dilation");
@@ -392,7 +449,7 @@ ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, bool tc) {
     return c;
 }
 
-Attention Handle::load_attention(const OnnxFile& f, const json& l, bool tc) {
+Attention Handle::load_attention(const OnnxFile& f, const json& l, int tc) {
     Attention a{};
     std::string p = l.at("name");
     a.C = l.at("C"); a.heads = l.at("heads"); a.ctx_dim = l.at("ctx_dim");
@@ -431,7 +488,7 @@ Attention Handle::load_attention(const OnnxFile& f, const json& l, bool tc) {
     return a;
 }
 
-void Handle::load_net(const OnnxFile& f, const json& arch, Net& net, bool tc) {
+void Handle::load_net(const OnnxFile& f, const json& arch, Net& net, int tc) {
     net.C = arch.value("C", 0); net.H = arch.value("H", 0); net.heads = arch.value("heads", 0);
     int kv = 0;
     for (const auto& l : arch.at("layers")) {
@@ -535,7 +592,7 @@ void Handle::load(const std::string& onnx_dir) {
     {
         OnnxFile f = load_onnx(onnx_dir + "/vocoder.onnx");
         voc_arch = arch_of(f, "vocoder.onnx");
-        load_net(f, voc_arch, voc, tc);
+        load_net(f, voc_arch, voc, tc ? (voc_tf32 ? 2 : 1) : 0);
         voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
         voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
     }
@@ -603,7 +660,12 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
             kprof_end();
             return;
         }
-        if (out_act) out_plain = out_act->f;
+        if (out_act) {          // fp32 operand: of the CUDA-core GEMMs (fp32_simt mode), or of a kind::tf32 GEMM (rounded here)
+            kprof_begin(1, (2.0 * K + 8.0) * rows * C, 8.0 * rows * C + 4.0 * C * (K + 3));
+            launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_act->f, tc_mode() ? 1 : 0}, rows, seq.off, seq.B, K, dil, pad, eps);
+            kprof_end();
+            return;
+        }
     }
     launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_plain}, rows, seq.off, seq.B, K, dil, pad, eps);
 }
@@ -631,14 +693,21 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (!w.has_maps) throw StcError(STC_ERR_INVALID, "linear has no tensor maps");
     tc::Params p{};
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
-    if (out_f32) { p.out_f32 = out_f32; p.split = 0; } else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
+    const bool tf32 = w.w_nk != nullptr;          // vocoder in tf32 mode: fp32 operands (a.f, w.w_nk), single-pass kind::tf32
+    if (tf32 && (!a.f || ep.rope_freqs)) throw StcError(STC_ERR_INVALID, "tf32 linear needs an fp32 activation operand");
+    if (out_f32) { p.out_f32 = out_f32; p.split = 0; }
+    else if (!out_act->hi) { p.out_f32 = out_act->f; p.split = 0; p.round_tf32 = 1; }     // fp32 operand of the next tf32 GEMM
+    else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
     if (dry) return;
     GemmCfg c = force_cfg.bn ? force_cfg : pick_gemm(M, w.N, w.K);
     if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
     p.cm = c.cm; p.cn = c.cn;
     const int csize = c.cm * c.cn;
-    const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM / c.cn), mal = tmap(a.lo, M, w.K, tc::BM / c.cn);
-    const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, c.bn / c.cm), mwl = tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
+    if (tf32) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
+    const CUtensorMap mah = tf32 ? tmap_tf32(a.f, M, w.K, tc::BM) : tmap(a.hi, M, w.K, tc::BM / c.cn);
+    const CUtensorMap mal = tf32 ? mah : tmap(a.lo, M, w.K, tc::BM / c.cn);
+    const CUtensorMap mwh = tf32 ? tmap_tf32(w.w_nk, w.N, w.K, c.bn) : tmap(w.w_hi, w.N, w.K, c.bn / c.cm);
+    const CUtensorMap mwl = tf32 ? mwh : tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
     const int m_tiles = cdiv(M, tc::BM), n_tiles = cdiv(w.N, c.bn);
     const int cluster_tiles = cdiv(m_tiles, c.cm) * cdiv(n_tiles, c.cn);
     const int clusters = std::max(1, std::min(cluster_tiles, num_sms / csize));
@@ -651,7 +720,10 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     cfg.attrs = attr; cfg.numAttrs = na;
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
-    switch (ep.rope_freqs ? 1 : c.bn) {
+    switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : c.bn) {
+        case 1064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, true>, mah, mal, mwh, mwl, p); break;
+        case 1128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, true>, mah, mal, mwh, mwl, p); break;
+        case 1256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256, false, true>, mah, mal, mwh, mwl, p); break;
         case 1: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, true>, mah, mal, mwh, mwl, p); break;
         case 64: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64>, mah, mal, mwh, mwl, p); break;
         case 128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128>, mah, mal, mwh, mwl, p); break;
@@ -685,10 +757,11 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
 //               than the cluster form (4224 rows: 20.8 vs 23.7) -> the default.
 //   0 unfused : pw1 and pw2 as two GEMMs (other widths: vocoder C=512/H=2048, tiny config).
 int Handle::mlp_form(const ConvNeXt& c, int rows) const {
-    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.has_maps && c.pw2.has_maps)) return 0;
+    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi)) return 0;
     if (mlp_mode == 1) return 1;
     if (mlp_mode == 2) return 0;
     if (mlp_mode == 3) return 2;
+    if (mlp_mode == 4) return 3;
     (void)rows;
     return 2;
 }
@@ -697,6 +770,7 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
 void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
                        const PostOps* post) {
     mlp::Params p{};
+    p.trace = mlp_trace;
     p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
     if (!a) {
         p.dw_wT = c.dw_wt; p.dw_b = c.dw_b; p.ln_g = c.ln_g; p.ln_b = c.ln_b; p.off = seq->off; p.B = seq->B;
@@ -705,7 +779,7 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
-    if (form == 2) p.partial = ws<float>(slice * mlp::CS);
+    if (form >= 2) p.partial = ws<float>(slice * mlp::CS);
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
@@ -715,8 +789,18 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
             launch_pdl(this, mlp::convnext_mlp_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                        mah, mal, w1h, w1l, w2h, w2l, p);
         else {
-            launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                       mah, mal, w1h, w1l, w2h, w2l, p);
+            if (form == 3) {
+                const CUtensorMap mpart = tmap_f32(p.partial, tiles * mlp::BM * mlp::CS, mlp::C);
+                if (mlp_epi == 16)
+                    launch_pdl(this, mlp::convnext_mlp_ts_kernel<16>, dim3(tiles * mlp::CS), dim3(64 + 32 * 16), (size_t)mlp::SMEM_BYTES, stream,
+                               mah, mal, w1h, w1l, w2h, w2l, mpart, p);
+                else
+                    launch_pdl(this, mlp::convnext_mlp_ts_kernel<8>, dim3(tiles * mlp::CS), dim3(64 + 32 * 8), (size_t)mlp::SMEM_BYTES, stream,
+                               mah, mal, w1h, w1l, w2h, w2l, mpart, p);
+            }
+            else
+                launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                           mah, mal, w1h, w1l, w2h, w2l, p);
             if (post)
                 launch_pdl(this, mlp::mlp_reduce_post_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
                            (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
@@ -750,15 +834,15 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* po
     Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
         const int form = mlp_form(c, rows);
-        const bool post_fused = post && form == 2;          // the split form's reduce kernel carries the post-ops
+        const bool post_fused = post && form >= 2;          // the split forms' reduce kernel carries the post-ops
         if (form && mlp_producer && c.K <= mlp::KMAX) {
             fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
         } else {
-            Act a = ws_act((size_t)rows * c.C);
+            Act a = ws_act_for(c.pw1, (size_t)rows * c.C);
             dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
             if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
             else {
-                Act hid = ws_act((size_t)rows * c.H);
+                Act hid = ws_act_for(c.pw2, (size_t)rows * c.H);
                 gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
                 gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
             }
@@ -1136,15 +1220,15 @@ void Handle::run_vocoder(const float* lat_cl, const Seq& lat, float* wav) {
             size_t m2 = mark();
             const Linear& w = voc.lin[l.idx];
             int K = w.K / ld;
-            Act a = ws_act((size_t)rows * w.K);
+            Act a = ws_act_for(w, (size_t)rows * w.K);
             size_t n = (size_t)rows * w.K;
             if (a.hi) STC_LAUNCH(this, voc_im2col_kernel<OutSplit>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutSplit{a.hi, a.lo}, rows, lat.off, lat.B, f, ld, K, w.K);
-            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f}, rows, lat.off, lat.B, f, ld, K, w.K);
+            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f, tc_mode() ? 1 : 0}, rows, lat.off, lat.B, f, ld, K, w.K);
             gemm(a, rows, w, Epilogue{}, x, nullptr, C);
             release(m2);
         } else if (l.type == L_CONVNEXT) convnext<float>(voc.cn[l.idx], x, s6);
         else if (l.type == L_HEAD) {
-            Act hn = ws_act((size_t)rows * C);
+            Act hn = ws_act_for(voc.lin[l.idx], (size_t)rows * C);
             dwconv_ln<float>(x, nullptr, voc.vec["head.ln_g"], voc.vec["head.ln_b"], C, s6, 1e-6f, nullptr, &hn);
             gemm(hn, rows, voc.lin[l.idx], Epilogue{}, wav, nullptr, voc.lin[l.idx].N);
         }
@@ -1265,7 +1349,9 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
-        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : 0; }
+        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : 0; }
+        { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
+        { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
@@ -1284,9 +1370,14 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
         }
         {
             const int big = 200 * 1024;
@@ -1847,13 +1938,14 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
         for (auto& v : wk) v = rnd() / std::sqrt((float)K) * 1.7f;
         for (auto& v : bias) v = rnd() * 0.1f;
-        Linear lin = h->make_linear_host(wk, bias, K, N, true);
+        const bool tf32 = getenv("STC_DEBUG_TF32") != nullptr;          // time / check the kind::tf32 instantiation instead
+        Linear lin = h->make_linear_host(wk, bias, K, N, tf32 ? 2 : 1);
         auto body = [&]() {
             h->arena.reset(); h->h_stage_off = 0;
             float* A = h->ws<float>((size_t)M * K); float* X = h->ws<float>((size_t)M * N); float* Xr = h->ws<float>((size_t)M * N);
             float* gamma = h->ws<float>(N); float* mask = h->ws<float>(M);
             float* out = h->ws<float>((size_t)M * N); float* ref = h->ws<float>((size_t)M * N); float* err = h->ws<float>(1);
-            Act a = h->ws_act((size_t)M * K), o = h->ws_act((size_t)M * N);
+            Act a = tf32 ? h->ws_act_f32((size_t)M * K) : h->ws_act((size_t)M * K), o = tf32 ? h->ws_act_f32((size_t)M * N) : h->ws_act((size_t)M * N);
             if (h->dry) return;
             debug_fill_kernel<<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, (size_t)M * K, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(X, (size_t)M * N, 2, 1.0f);
@@ -1861,7 +1953,8 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 2, 0.0f, (size_t)std::min(M - M / 2, 3));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
-            h->to_act(A, (size_t)M * K, a);
+            if (tf32) convert_kernel<OutPlain<float>><<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, OutPlain<float>{a.f, 1}, (size_t)M * K);
+            else h->to_act(A, (size_t)M * K, a);
             Epilogue ep;
             if (epilogue == 1) ep.gelu = 1;
             if (epilogue == 2) { ep.scale = gamma; ep.mask = mask; }
@@ -1882,7 +1975,8 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
                 else h->gemm(a, M, lin, ep, out, nullptr, N);
             };
             one(true);
-            if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
+            if (epilogue == 1 && tf32) STC_CUDA(cudaMemcpyAsync(out, o.f, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
+            else if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
             debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(out, refp, (size_t)M * N, err);
             // timed: `iters` launches replayed from a CUDA graph (as in production), so the host is not in the loop
             cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
@@ -1932,14 +2026,14 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
             float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
             Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
-            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS); return; }     // split form's scratch
+            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS); h->ws<long long>(64); return; }     // split form's scratch
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
-            const int form = h->mlp_mode == 3 ? 2 : 1;
+            const int form = h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
             auto fused = [&](float* x) { h->fused_mlp(&a, M, cn, x, nullptr, mask, form); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;
@@ -1949,6 +2043,19 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             };
             STC_CUDA(cudaMemcpyAsync(Xa, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
             STC_CUDA(cudaMemcpyAsync(Xb, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
+            if (getenv("STC_MLP_TRACE")) {
+                long long* tr = h->ws<long long>(64);
+                STC_CUDA(cudaMemsetAsync(tr, 0, 64 * 8, h->stream));
+                fused(Xa);                                   // warm (descriptors, L2)
+                h->mlp_trace = tr; fused(Xa); h->mlp_trace = nullptr;
+                long long ht[64];
+                STC_CUDA(cudaMemcpyAsync(ht, tr, 64 * 8, cudaMemcpyDeviceToHost, h->stream));
+                STC_CUDA(cudaStreamSynchronize(h->stream));
+                fprintf(stderr, "mlp trace M=%d (cycles since prologue end):", M);
+                for (int i = 0; i < 64; ++i) fprintf(stderr, "%s%lld", i % 8 == 0 ? "\n  " : " ", ht[i] ? ht[i] - ht[0] : -99999);
+                fprintf(stderr, "\n");
+                STC_CUDA(cudaMemcpyAsync(Xa, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
+            }
             fused(Xa); unfused(Xb);
             debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(Xa, Xb, (size_t)M * C, err);
             float out_ms[2] = {0, 0};

@@ -122,6 +122,27 @@ def test_synthesize_matches_oracle_infer(rig, steps):
     assert snr >= SNR_NORTH_STAR and snr >= SNR_EXPECTED, snr
 
 
+def test_tf32_vocoder_mode_stays_inside_the_waveform_bound(rig):
+    """STC_VOC=tf32 (opt-in): the vocoder's GEMMs run single-pass kind::tf32 on operands rounded to nearest. The waveform must stay
+    inside the north-star bound (>= 40 dB) with margin (>= 60 dB asserted; ~70 dB measured); the default mode keeps >= 80 dB."""
+    import os
+    os.environ["STC_VOC"] = "tf32"
+    try:
+        eng = rig["capi"].Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_VOC"]
+    try:
+        rng = np.random.default_rng(5)
+        lat = rng.standard_normal((2, 144, 70)).astype(np.float32)
+        want = rig["ora"].voc(dict(latent=lat))
+        got, exact = eng.vocode(lat), rig["eng"].vocode(lat)
+        snr_tf32, snr_exact = U.snr_db(got.reshape(-1), want.reshape(-1)), U.snr_db(exact.reshape(-1), want.reshape(-1))
+        assert snr_tf32 >= 60.0, snr_tf32
+        assert snr_exact >= SNR_EXPECTED and snr_exact > snr_tf32, (snr_exact, snr_tf32)
+    finally:
+        eng.close()
+
+
 def test_noise_stride_and_capacity_retry(rig):
     from oracle.pipeline import make_noise
     ids, mask, ttl, dp = _inputs(rig, 40, 2, 30, 60)
