@@ -167,6 +167,7 @@ struct Params {
     int split;
     int round_tf32;                 // fp32 output is the tf32 operand of the next GEMM: round it to nearest here
     int cm, cn;                     // cluster shape in tiles (cm * cn CTAs per cluster)
+    long long* trace;               // debug (stc_debug_gemm, STC_GEMM_TRACE=1): clock64() stamps of block 0's producer / MMA warps
 };
 
 // erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with MUFU reciprocal / exp2: ~14 instructions against ~40 for

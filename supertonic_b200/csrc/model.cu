@@ -16,6 +16,7 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "mlp_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "model.cuh"
 #include "text_frontend.h"
 
@@ -195,7 +196,9 @@ struct Handle {
     bool mlp_producer = false;
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
     int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks), 4 "ts"
+    long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
+    bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
     bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
                                       // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
@@ -692,6 +695,7 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     }
     if (!w.has_maps) throw StcError(STC_ERR_INVALID, "linear has no tensor maps");
     tc::Params p{};
+    p.trace = gemm_trace;
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
     const bool tf32 = w.w_nk != nullptr;          // vocoder in tf32 mode: fp32 operands (a.f, w.w_nk), single-pass kind::tf32
     if (tf32 && (!a.f || ep.rope_freqs)) throw StcError(STC_ERR_INVALID, "tf32 linear needs an fp32 activation operand");
@@ -703,6 +707,28 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
     p.cm = c.cm; p.cn = c.cn;
     const int csize = c.cm * c.cn;
+    if (c.bn == 512 && (tf32 || ep.rope_freqs)) c = GemmCfg{256, 1, 1};       // variants the two-SM kernel does not carry
+    if (c.bn == 512) {          // two-SM form (gemm2_tc.cuh): 256 x 256 tiles computed by CTA pairs
+        if (w.N % 4) throw StcError(STC_ERR_INVALID, "two-SM GEMM: N % 4 != 0");
+        p.cm = 2; p.cn = 1;
+        const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM), mal = tmap(a.lo, M, w.K, tc::BM);
+        const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, tc2::HALF), mwl = tmap(w.w_lo, w.N, w.K, tc2::HALF);
+        const int num_ct = cdiv(cdiv(M, tc::BM), 2) * cdiv(w.N, tc2::BN);
+        const int clusters = std::max(1, std::min(num_ct, num_sms / 2));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(tc2::THREADS); cfg.stream = stream;
+        cfg.dynamicSmemBytes = tc2::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        int na = 0;
+        if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+        cfg.attrs = attr; cfg.numAttrs = na;
+        kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel, mah, mal, mwh, mwl, p);
+        if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("two-SM tcgen05 GEMM launch: ") + cudaGetErrorString(e));
+        ++launches;
+        kprof_end();
+        return;
+    }
     if (tf32) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
     const CUtensorMap mah = tf32 ? tmap_tf32(a.f, M, w.K, tc::BM) : tmap(a.hi, M, w.K, tc::BM / c.cn);
     const CUtensorMap mal = tf32 ? mah : tmap(a.lo, M, w.K, tc::BM / c.cn);
@@ -742,6 +768,9 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
     // Measured (tools/gemm_sweep.py, profiles/r1c_gemm_sweep.txt): TMA multicast inside a cluster does not shorten any of
     // the hot shapes — the limit is bytes delivered INTO each SM, which multicast does not reduce — so clusters stay off.
     // Wide tiles win once every SM has many tiles (fewer operand bytes per flop); narrow ones when tiles are scarce.
+    // Two-SM 256 x 256 tiles (gemm2_tc.cuh) once there are at least two waves of them: the vocoder projections. Measured
+    // (tools/gemm_epi.py, profiles/r1z_gemm_epi.txt): pw1 158.8 -> 142.3 us, pw2 145.3 -> 127.6 us.
+    if (gemm2 && N % 256 == 0 && K >= 512 && cdiv(M, 2 * tc::BM) * (N / 256) >= num_sms) return GemmCfg{512, 2, 1};
     const int tiles128 = cdiv(M, tc::BM) * cdiv(N, 128);
     int bn = 64;
     if (tiles128 >= 16 * num_sms && N % 256 == 0) bn = 256;
@@ -1350,6 +1379,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : 0; }
+        { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
@@ -1370,6 +1400,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
@@ -1931,8 +1962,8 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         Scope sc(sh); Handle* h = sc.h;
         if (!h->tc_mode()) throw StcError(STC_ERR_UNSUPPORTED, "stc_debug_gemm needs the tcgen05 precision mode");
         if (M <= 0 || N <= 0 || K <= 0 || iters <= 0 || epilogue < 0 || epilogue > 2) throw StcError(STC_ERR_INVALID, "stc_debug_gemm: bad argument");
-        if (bn && (bn != 64 && bn != 128 && bn != 256)) throw StcError(STC_ERR_INVALID, "bn must be 0, 64, 128 or 256");
-        if (bn && (cm < 1 || cn < 1 || cm * cn > 8 || (tc::BM / cn) % 8 || (bn / cm) % 8)) throw StcError(STC_ERR_INVALID, "bad cluster shape");
+        if (bn && (bn != 64 && bn != 128 && bn != 256 && bn != 512)) throw StcError(STC_ERR_INVALID, "bn must be 0, 64, 128, 256 or 512 (two-SM 256 x 256)");
+        if (bn && bn != 512 && (cm < 1 || cn < 1 || cm * cn > 8 || (tc::BM / cn) % 8 || (bn / cm) % 8)) throw StcError(STC_ERR_INVALID, "bad cluster shape");
         std::vector<float> wk((size_t)K * N), bias(N);
         uint64_t z = 12345;
         auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
@@ -1946,7 +1977,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             float* gamma = h->ws<float>(N); float* mask = h->ws<float>(M);
             float* out = h->ws<float>((size_t)M * N); float* ref = h->ws<float>((size_t)M * N); float* err = h->ws<float>(1);
             Act a = tf32 ? h->ws_act_f32((size_t)M * K) : h->ws_act((size_t)M * K), o = tf32 ? h->ws_act_f32((size_t)M * N) : h->ws_act((size_t)M * N);
-            if (h->dry) return;
+            if (h->dry) { h->ws<long long>(128); return; }
             debug_fill_kernel<<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, (size_t)M * K, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(X, (size_t)M * N, 2, 1.0f);
             debug_fill_kernel<<<cdiv(N, 256), 256, 0, h->stream>>>(gamma, N, 3, 0.1f);
@@ -1974,6 +2005,18 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
                 } else if (epilogue == 1) h->gemm(a, M, lin, ep, nullptr, &o, N);
                 else h->gemm(a, M, lin, ep, out, nullptr, N);
             };
+            if (getenv("STC_GEMM_TRACE")) {
+                long long* tr = h->ws<long long>(128);
+                STC_CUDA(cudaMemsetAsync(tr, 0, 128 * 8, h->stream));
+                one(true);
+                h->gemm_trace = tr; one(true); h->gemm_trace = nullptr;
+                long long ht[128];
+                STC_CUDA(cudaMemcpyAsync(ht, tr, 128 * 8, cudaMemcpyDeviceToHost, h->stream));
+                STC_CUDA(cudaStreamSynchronize(h->stream));
+                fprintf(stderr, "gemm trace (cycles; MMA warp after full-wait [0..47], producer after empty-wait [64..111], tile starts [120..]):");
+                for (int i = 0; i < 128; ++i) fprintf(stderr, "%s%lld", i % 8 == 0 ? "\n  " : " ", ht[i] ? ht[i] - ht[64] : -99999);
+                fprintf(stderr, "\n");
+            }
             one(true);
             if (epilogue == 1 && tf32) STC_CUDA(cudaMemcpyAsync(out, o.f, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
             else if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
