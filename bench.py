@@ -5,7 +5,10 @@ Workload (config.workload): BASELINE.json configs[1] — a batch of 32 mixed-len
 (character lengths uniform{20..300}, numpy default_rng(1234), README lengths 59/152/266 included),
 total_step=5, speed=1.05, voices cycling M1/F1/M2/F2, surrogate full-size graphs (the released weights are not
 mounted: SURVEY.md §0). One "step" = one pass of the hot path over that batch; with N GPUs every rank
-synthesises its own 32-utterance batch (weak scaling, replicas only, no collective on the data path).
+synthesises that same configs[1] batch with its own noise seeds (weak scaling: the per-GPU work is FIXED as N grows; replicas
+only, no collective on the data path). --vary-batches gives every rank its own draw of 32 utterances instead (the total
+latent frames then differ by +-15 % between ranks, and a rank whose frames need 38+ row tiles takes two waves of the fused
+MLP kernel instead of one — DESIGN.md §6); `per_rank` in the JSON line lists each rank's frames and time either way.
 
   value : device-resident leg — text_ids/masks/styles already in HBM, stc_synthesize_device per length bucket,
           CUDA events on the library's stream, L2 flushed (untimed) between steps.
@@ -124,6 +127,7 @@ def main():
     ap.add_argument("--total-step", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vary-batches", action="store_true", help="N > 1: every rank draws its own 32 utterances (seed 1234 + 1000 rank)")
     ap.add_argument("--workload", default="batch", choices=["batch", "sweep1024"],
                     help="batch: configs[1], every GPU its own --batch utterances (weak scaling, the default and the headline). "
                          "sweep1024: configs[4], 1024 utterances sharded over the GPUs in groups of 128 (strong scaling)")
@@ -177,8 +181,11 @@ def main():
         cfg["workload"] = (f"configs[4]: 1024 synthetic utterances (chars uniform 20..300, seed 1234) sharded over {world} GPU(s) by LPT, "
                            f"groups of {group}, total_step={a.total_step}, speed=1.05")
     else:
-        texts, langs, voices = workload(a.batch, 1234 + 1000 * rank)
+        texts, langs, voices = workload(a.batch, 1234 + (1000 * rank if a.vary_batches else 0))
         group = a.batch
+        if world > 1:
+            cfg["workload"] += (" (every rank its own draw, seed 1234 + 1000 rank)" if a.vary_batches
+                                else " (the same batch on every rank, rank-specific noise seeds)")
     n_utt = len(texts)
     style = T.load_voice_style([os.path.join(root, "voice_styles", v + ".json") for v in voices])
     ext = torch.cuda.ExternalStream(eng.stream)
@@ -222,6 +229,7 @@ def main():
                     b["wav"] = torch.empty(b["cap"], dtype=torch.float32, device="cuda")
             b["L"] = int(off[-1] // cs)
 
+    seed0 = 100 + 1000 * rank
     for w in range(a.warmup):
         device_step(w)
     audio = float(sum(b["dur"].sum().item() for b in buckets))
@@ -235,7 +243,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ext):
             e0.record()
-            device_step(100 + k)
+            device_step(seed0 + k)
             e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -248,6 +256,14 @@ def main():
         dist.all_reduce(tmax[0:1], op=dist.ReduceOp.MAX)
         dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)
     total_ms, audio_all = float(tmax[0].item()), float(t[1].item())
+    mine = torch.tensor([float(np.sum(step_ms)) / a.steps, audio, float(sum(b.get("L", 0) for b in buckets))], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": i, "ms_per_step": float(v[0]), "audio_s_per_step": float(v[1]), "latent_frames": int(v[2]),
+                 "row_tiles_of_128": int(-(-int(v[2]) // 128))} for i, v in enumerate(allr)]
     ms_per_step = total_ms / a.steps
     value = audio_all / (ms_per_step / 1000)
 
@@ -322,7 +338,9 @@ def main():
         dom = max(("gemm_tc", "fused_mlp"), key=lambda k: prof[k]["ms"])
         other = "fused_mlp" if dom == "gemm_tc" else "gemm_tc"
         roof = tensor_line(dom)
-        roof["traffic"] = traffic if dom == "gemm_tc" else None
+        tpm = os.path.join(ROOT, "profiles", "mlp_traffic.json")
+        roof["traffic"] = traffic if dom == "gemm_tc" else (json.load(open(tpm)).get("dram_bytes_per_launch") if os.path.exists(tpm) else None)
+        roof["traffic_source"] = "profiles/gemm_traffic.json" if dom == "gemm_tc" else "profiles/mlp_traffic.json"
         roof["note"] = ("split-bf16 arithmetic executes 3 MMAs per algorithmic multiply-add, so `frac` (algorithmic) cannot exceed 1/3; "
                         "`frac_executed_mma` is the tensor-pipe load")
         roof[other] = tensor_line(other)
@@ -353,7 +371,7 @@ def main():
                                                audio_s_per_step_per_gpu=audio),
            "clocks": clocks, "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                      "ms_per_step": 1000 * float(temax[0].item()) / a.steps},
-           "gpu_launches": int(launches), "latency": lat, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
+           "gpu_launches": int(launches), "per_rank": per_rank, "latency": lat, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
            "p50_step_ms": float(np.median(step_ms))}
     print(json.dumps(out))
     if world > 1:

@@ -204,6 +204,13 @@ int stc_debug_gemm(stc_handle* h, int M, int N, int K, int bn, int cm, int cn, i
  * each (CUDA-graph replay of `iters` launches) and the max-abs difference of the updated residual stream. */
 int stc_debug_mlp(stc_handle* h, int M, int iters, float* ms_fused, float* ms_unfused, float* max_abs_err);
 
+/* Same for depthwise conv1d + LayerNorm (the `Conv(group=C)` -> `LayerNormalization` pair of every ConvNeXt block): C in
+ * {128, 256, 512}, K in {5, 7}, `B` ragged sequences packed into `rows` rows (the last rows/16 are bucket padding, one sequence
+ * is empty). Register sliding-window kernel (chains of `rt` rows; 0 = the library's choice) against the shared-memory tiled
+ * kernel: mean device time of each writing split-bf16 operands, and the max-abs difference of their fp32 outputs. */
+int stc_debug_dwconv(stc_handle* h, int rows, int C, int K, int dil, int causal, int B, int rt, int iters, float* ms_slide,
+                     float* ms_tile, float* max_abs_diff);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ _SIGS = {
     "stc_last_stage_ms": (_i, [_vp, _vp]),
     "stc_kernel_profile": (_i, [_vp, _i, _vp]),
     "stc_debug_mlp": (_i, [_vp, _i, _i, _pf, _pf, _pf]),
+    "stc_debug_dwconv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _pf, _pf, _pf]),
     "stc_debug_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _pf, _pf]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -383,6 +384,12 @@ class Engine:
         """Fused ConvNeXt MLP vs two GEMMs on M rows -> (us fused, us unfused, max-abs difference)."""
         a, b, e = C.c_float(0), C.c_float(0), C.c_float(0)
         self._chk(lib.stc_debug_mlp(self._h, M, iters, C.byref(a), C.byref(b), C.byref(e)))
+        return a.value * 1000.0, b.value * 1000.0, e.value
+
+    def debug_dwconv(self, rows, C_, K, dil, causal=False, B=8, rt=0, iters=20):
+        """Depthwise conv + LayerNorm, sliding-window vs tiled kernel -> (us slide, us tile, max-abs difference)."""
+        a, b, e = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._chk(lib.stc_debug_dwconv(self._h, rows, C_, K, dil, int(causal), B, rt, iters, C.byref(a), C.byref(b), C.byref(e)))
         return a.value * 1000.0, b.value * 1000.0, e.value
 
     def stage_ms(self):

@@ -374,6 +374,174 @@ dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT,
     }
 }
 
+// Sliding-window variant: a thread owns FOUR channels (one float4) and walks a CHAIN of output rows r, r + dil, r + 2 dil, ...
+// Along such a chain a dilated convolution is an undilated one, so the K tap rows of consecutive outputs overlap in K - 1 rows,
+// which stay in registers: every input row is read from global memory once per chain (+ K - 1 halo rows), coalesced (the C/4
+// threads of a group read one contiguous row), with no shared-memory staging and no re-read of taps or weights — the K tap
+// weights and the bias live in registers for the whole chain (the tile kernel above issues an LDS + an LDG per tap and float4:
+// ~1100 warp instructions per 512-channel row, which made it issue bound at 20 % of the HBM rate). Tap products use the packed
+// fma.rn.f32x2 of sm_100 in the same k order as the other variants (bit-identical convolution). LayerNorm needs the whole
+// row = the NW warps of a group: partial sums of U = 4 rows at a time go through a transposing butterfly (6 shuffles for four
+// sums), shared memory and one named barrier per pass; two-pass (mean, then centred squares) like everywhere else.
+// Grid: chain c of a tile of RT * dil rows has phase c % dil; 4 / NW groups (chains) per 128-thread block.
+STC_DEVINL float warp_sum4(float v0, float v1, float v2, float v3, int lane) {
+    // lane l ends with the warp total of value 2 * bit4(l) + bit3(l)
+    const bool h16 = lane & 16, h8 = lane & 8;
+    const float a0 = (h16 ? v2 : v0) + __shfl_xor_sync(0xffffffffu, h16 ? v0 : v2, 16);
+    const float a1 = (h16 ? v3 : v1) + __shfl_xor_sync(0xffffffffu, h16 ? v1 : v3, 16);
+    float b = (h8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, h8 ? a0 : a1, 8);
+    b += __shfl_xor_sync(0xffffffffu, b, 4);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    return b;
+}
+template <int NW> STC_DEVINL void group_barrier(int grp) {
+    if constexpr (NW == 1) __syncwarp();
+    else if constexpr (NW == 4) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(32 * NW) : "memory");
+}
+template <int NW> STC_DEVINL float group_total(const float* p) {     // sum of the NW per-warp partials, same order in every thread
+    if constexpr (NW == 4) { const float4 v = *reinterpret_cast<const float4*>(p); return (v.x + v.y) + (v.z + v.w); }
+    else if constexpr (NW == 2) { const float2 v = *reinterpret_cast<const float2*>(p); return v.x + v.y; }
+    else return p[0];
+}
+
+// RING: the rows of the next RING_D iterations are in flight as per-thread cp.async copies into a shared-memory ring (a thread
+// reads back only what it copied itself: no barrier), 128 KB per SM instead of the 32 KB a register prefetch of one iteration
+// keeps in flight — the long vocoder chains are bound by bytes in flight, the short VE / TE chains (one or two iterations)
+// by latency and keep the register prefetch.
+constexpr int RING_D = 4;
+template <int NW, int K, bool RING, typename Out>
+__global__ void __launch_bounds__(128)
+dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
+                       const float* __restrict__ g, const float* __restrict__ beta, Out out,
+                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
+    pdl_trigger(); pdl_wait();
+    constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = 4;
+    __shared__ __align__(16) float red[2][GPB][U][NW];
+    const int grp = threadIdx.x / GT, t = threadIdx.x % GT, wig = t >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * GPB + grp;
+    const int r_first = (chain / dil) * (RT * dil) + chain % dil;
+    if (r_first >= rows) return;                       // the whole group leaves (barriers are per group)
+    const float* xc = x + 4 * t;
+    float2 w[K][2];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wT + (size_t)k * C) + t);
+        w[k][0] = make_float2(v.x, v.y); w[k][1] = make_float2(v.z, v.w);
+    }
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(wb) + t);
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + t), bv = __ldg(reinterpret_cast<const float4*>(beta) + t);
+    auto load_row = [&](int r) -> float4 {
+        return (r >= 0 && r < rows) ? *reinterpret_cast<const float4*>(xc + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int rw0 = r_first - pad_left;                // window slot j of output i holds row rw0 + (i + j) * dil
+    float4 win[K - 1 + U], nxt[RING ? 1 : U];
+    __shared__ float4 ring[RING ? (RING_D + 1) * U * 128 : 1];          // [slot][u][thread]: conflict-free 16-byte accesses
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 16u;
+    auto fetch = [&](int it) {                         // rows of iteration `it` -> ring slot it % (RING_D + 1); always one commit group
+        if (it * U < RT) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = rw0 + (K - 1 + it * U + u) * dil;
+                const bool ok = r >= 0 && r < rows;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + (uint32_t)((it % (RING_D + 1)) * U + u) * 2048u),
+                             "l"(ok ? xc + (size_t)r * C : xc), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if constexpr (RING) {
+#pragma unroll
+        for (int it = 0; it < RING_D; ++it) fetch(it);
+    }
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) win[j] = load_row(rw0 + j * dil);
+    if constexpr (!RING) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) nxt[u] = load_row(rw0 + (K - 1 + u) * dil);
+    }
+    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
+    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+    for (int i0 = 0; i0 < RT; i0 += U) {
+        if (r_first + i0 * dil >= rows) break;         // uniform in the group
+        if constexpr (RING) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RING_D - 1) : "memory");
+            const int slot = (i0 / U) % (RING_D + 1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) win[K - 1 + u] = ring[(slot * U + u) * 128 + threadIdx.x];
+            fetch(i0 / U + RING_D);                    // into the slot consumed one iteration ago
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) win[K - 1 + u] = nxt[u];
+            if (i0 + U < RT) {                         // next iteration's rows are in flight during this one's arithmetic
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = load_row(rw0 + (K - 1 + i0 + U + u) * dil);
+            }
+        }
+        float2 y[U][2];
+        bool pad[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = r_first + (i0 + u) * dil;
+            if (b >= 0 && r >= hi) {                   // next sequence (empty ones are skipped); past the last one: padding
+                do ++b; while (b < B && r >= __ldg(off + b + 1));
+                if (b >= B) b = -1; else { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+            }
+            pad[u] = b < 0;
+            y[u][0] = make_float2(bias.x, bias.y); y[u][1] = make_float2(bias.z, bias.w);
+            const int first = r - pad_left;
+            if (b < 0) {                               // bucket padding row: keep it finite
+                y[u][0] = y[u][1] = make_float2(0.f, 0.f);
+            } else if (first >= lo && first + (K - 1) * dil < hi) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    y[u][0] = __ffma2_rn(w[k][0], make_float2(win[u + k].x, win[u + k].y), y[u][0]);
+                    y[u][1] = __ffma2_rn(w[k][1], make_float2(win[u + k].z, win[u + k].w), y[u][1]);
+                }
+            } else {                                   // a sequence edge: taps outside [lo, hi) are the zero padding
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int rk = first + k * dil;
+                    if (rk >= lo && rk < hi) {
+                        y[u][0] = __ffma2_rn(w[k][0], make_float2(win[u + k].x, win[u + k].y), y[u][0]);
+                        y[u][1] = __ffma2_rn(w[k][1], make_float2(win[u + k].z, win[u + k].w), y[u][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) win[j] = win[j + U];
+        // LayerNorm over the C channels of each of the U rows
+        float tot = warp_sum4((y[0][0].x + y[0][0].y) + (y[0][1].x + y[0][1].y), (y[1][0].x + y[1][0].y) + (y[1][1].x + y[1][1].y),
+                              (y[2][0].x + y[2][0].y) + (y[2][1].x + y[2][1].y), (y[3][0].x + y[3][0].y) + (y[3][1].x + y[3][1].y), lane);
+        if ((lane & 7) == 0) red[0][grp][lane >> 3][wig] = tot;
+        group_barrier<NW>(grp);
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float mean = group_total<NW>(&red[0][grp][u][0]) / (float)C;
+            const float2 nm = make_float2(-mean, -mean);
+            y[u][0] = __fadd2_rn(y[u][0], nm); y[u][1] = __fadd2_rn(y[u][1], nm);
+            v[u] = (y[u][0].x * y[u][0].x + y[u][0].y * y[u][0].y) + (y[u][1].x * y[u][1].x + y[u][1].y * y[u][1].y);
+        }
+        tot = warp_sum4(v[0], v[1], v[2], v[3], lane);
+        if ((lane & 7) == 0) red[1][grp][lane >> 3][wig] = tot;
+        group_barrier<NW>(grp);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = r_first + (i0 + u) * dil;
+            if (r >= rows) continue;
+            const float inv = 1.0f / sqrtf(group_total<NW>(&red[1][grp][u][0]) / (float)C + eps);     // see dwconv_ln_tile_kernel
+            const float2 iv = make_float2(inv, inv);
+            const float2 o0 = __ffma2_rn(__fmul2_rn(y[u][0], iv), make_float2(gv.x, gv.y), make_float2(bv.x, bv.y));
+            const float2 o1 = __ffma2_rn(__fmul2_rn(y[u][1], iv), make_float2(gv.z, gv.w), make_float2(bv.z, bv.w));
+            const float o[4] = {pad[u] ? 0.f : o0.x, pad[u] ? 0.f : o0.y, pad[u] ? 0.f : o1.x, pad[u] ? 0.f : o1.y};
+            store_row_vec<4>(out, (size_t)r * C + 4 * t, o);
+        }
+    }
+}
+
 // ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
 template <typename Out>
 __global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {

@@ -203,6 +203,9 @@ struct Handle {
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
                                       // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
     int mlp_epi = 8;                  // env STC_MLP_EPI: epilogue warps of the TS form (8 or 16)
+    bool dw_slide = true;             // env STC_DW=tile: shared-memory tiled depthwise conv + LayerNorm instead of the register sliding window
+    int dw_rt = 0;                    // env STC_DW_RT: rows per chain of the sliding-window kernel (0: heuristic)
+    int dw_ring = -1;                 // env STC_DW_RING: 1 / 0 force the shared-memory ring prefetch on / off (-1: by chain length)
     void attention(const Attention& a, float* x, const Seq& q, const Act* ctx, const Seq& k, const KV* pre, const Act* xn_pre = nullptr);
     void attn_core(const float* Q, const float* K, const float* V, const Act& out, const Seq& q, const Seq& k, bool key_masked,
                    int heads, int dh);
@@ -618,6 +621,37 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
         // w is the tap-major transpose wT[K][C] for these widths (ConvNeXt::dw_wt)
         // (measured: the shared-memory tiles also beat the direct warp-per-row kernel on the L2-resident VE / TE tensors:
         //  12.97 vs 13.27 ms/step)
+        if (h->dw_slide && (K == 5 || K == 7) && (C == 128 || C == 256 || C == 512) && dil >= 1) {
+            // register sliding window along chains of RT rows (kernels.cuh): RT as long as every SM still gets >= ~1024 threads
+            const int GT = C / 4;
+            int RT = h->dw_rt;
+            if (RT <= 0) {
+                // long chains (shared-memory ring prefetch) when one wave of resident chains (4 blocks of 128 threads per SM) covers
+                // the rows with >= 16 rows per chain, else chains of 4 rows (one iteration: latency bound, as many threads as possible)
+                const int resident = h->num_sms * 4 * (512 / C);
+                RT = (int)cdiv(cdiv(rows, resident), 4) * 4;
+                if (RT < 16) RT = 4;
+            }
+            RT = std::max(4, RT / 4 * 4);
+            const bool ring = h->dw_ring < 0 ? RT >= 16 : h->dw_ring > 0;
+            const unsigned chains = cdiv(rows, RT * dil) * dil;
+            dim3 sg(cdiv(chains, 512 / C));
+#define STC_SLIDE(NW, KK)                                                                                                                     \
+    do {                                                                                                                                      \
+        if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT); \
+        else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT);     \
+        return;                                                                                                                               \
+    } while (0)
+            switch (C / 128 * 10 + K) {
+                case 15: STC_SLIDE(1, 5);
+                case 17: STC_SLIDE(1, 7);
+                case 25: STC_SLIDE(2, 5);
+                case 27: STC_SLIDE(2, 7);
+                case 45: STC_SLIDE(4, 5);
+                case 47: STC_SLIDE(4, 7);
+            }
+#undef STC_SLIDE
+        }
         if (K > 0 && (C == 128 || C == 256 || C == 512)) {
             // rows per block: as many as keep >= 2 blocks per SM in flight (shared-memory tile = (R + span) rows)
             const int span = (K - 1) * dil;
@@ -1382,6 +1416,9 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
+        { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); }
+        { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
+        { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
@@ -2121,6 +2158,74 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             if (ms_fused) *ms_fused = out_ms[0] / iters;
             if (ms_unfused) *ms_unfused = out_ms[1] / iters;
             if (max_abs_err) STC_CUDA(cudaMemcpy(max_abs_err, err, 4, cudaMemcpyDeviceToHost));
+            h->ev_next = 0;
+        };
+        h->ensure_ws(body);
+        body();
+    })
+}
+
+// Depthwise conv + LayerNorm in isolation: B ragged sequences packed into `rows` rows (the last rows/16 are bucket padding),
+// sliding-window kernel (chains of `rt` rows, 0 = heuristic) against the shared-memory tiled kernel on the same input.
+int stc_debug_dwconv(stc_handle* sh, int rows, int C, int K, int dil, int causal, int B, int rt, int iters, float* ms_slide,
+                     float* ms_tile, float* max_abs_diff) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (rows <= 0 || B <= 0 || iters <= 0 || (C != 128 && C != 256 && C != 512) || (K != 5 && K != 7) || dil < 1)
+            throw StcError(STC_ERR_INVALID, "stc_debug_dwconv: bad argument");
+        uint64_t z = 4242;
+        auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
+        std::vector<float> wt((size_t)K * C), wb(C), gm(C), bt(C);
+        for (auto& v : wt) v = rnd() * 0.5f;
+        for (auto& v : wb) v = rnd() * 0.1f;
+        for (auto& v : gm) v = 1.0f + rnd() * 0.2f;
+        for (auto& v : bt) v = rnd() * 0.1f;
+        ConvNeXt cn{};
+        cn.C = C; cn.K = K; cn.dil = dil; cn.pad_left = causal ? (K - 1) * dil : (K - 1) * dil / 2;
+        cn.dw_wt = h->upload_f32(wt.data(), wt.size()); cn.dw_b = h->upload_f32(wb.data(), wb.size());
+        const float* g = h->upload_f32(gm.data(), gm.size()); const float* bta = h->upload_f32(bt.data(), bt.size());
+        // ragged lengths (one empty sequence when B > 2), real rows = rows - rows / 16
+        std::vector<int> lens(B);
+        { int real = rows - rows / 16, left = real;
+          for (int i = 0; i < B; ++i) { int want = (i == B - 1) ? left : std::min(left, (int)((real / B) * (0.5f + (rnd() + 1.0f) * 0.5f))); if (B > 2 && i == 1) want = 0; lens[i] = want; left -= want; } }
+        auto body = [&]() {
+            h->arena.reset(); h->h_stage_off = 0;
+            float* X = h->ws<float>((size_t)rows * C);
+            float* Ya = h->ws<float>((size_t)rows * C); float* Yb = h->ws<float>((size_t)rows * C);
+            float* err = h->ws<float>(1);
+            Act oa = h->ws_act((size_t)rows * C);
+            Seq seq = h->packed_seq(lens, rows, 0);
+            if (h->dry) return;
+            debug_fill_kernel<<<cdiv((size_t)rows * C, 256), 256, 0, h->stream>>>(X, (size_t)rows * C, 3, 1.0f);
+            fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
+            const bool keep = h->dw_slide; const int keep_rt = h->dw_rt;
+            auto run = [&](bool slide, float* y, const Act* act) {
+                h->dw_slide = slide; h->dw_rt = rt;
+                h->dwconv_ln<float>(X, &cn, g, bta, C, seq, 1e-6f, act ? nullptr : y, act);
+                h->dw_slide = keep; h->dw_rt = keep_rt;
+            };
+            run(true, Ya, nullptr); run(false, Yb, nullptr);
+            debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(Ya, Yb, (size_t)rows * C, err);
+            float out_ms[2] = {0, 0};
+            for (int which = 0; which < 2; ++which) {
+                cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+                cudaEvent_t e0 = h->pool_event(), e1 = h->pool_event();
+                STC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                for (int it = 0; it < iters; ++it) run(which == 0, nullptr, &oa);
+                STC_CUDA(cudaStreamEndCapture(h->stream, &graph));
+                STC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+                STC_CUDA(cudaGraphLaunch(exec, h->stream));
+                cudaEventRecord(e0, h->stream);
+                STC_CUDA(cudaGraphLaunch(exec, h->stream));
+                cudaEventRecord(e1, h->stream);
+                STC_CUDA(cudaStreamSynchronize(h->stream));
+                cudaEventElapsedTime(&out_ms[which], e0, e1);
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+            }
+            h->check_launch("stc_debug_dwconv");
+            if (ms_slide) *ms_slide = out_ms[0] / iters;
+            if (ms_tile) *ms_tile = out_ms[1] / iters;
+            if (max_abs_diff) STC_CUDA(cudaMemcpy(max_abs_diff, err, 4, cudaMemcpyDeviceToHost));
             h->ev_next = 0;
         };
         h->ensure_ws(body);

@@ -257,7 +257,8 @@ def test_error_paths(rig):
     assert eng.launches > 0
 
 
-@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP", "fused"), ("STC_MLP", "split"), ("STC_MLP_PRODUCER", "1")])
+@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP", "fused"), ("STC_MLP", "split"), ("STC_MLP_PRODUCER", "1"),
+                                 ("STC_DW", "tile")])
 def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
     """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
     fp32 core. STC_MLP=fused / unfused: the 4-CTA-cluster fused ConvNeXt MLP (mlp_tc.cuh, DSMEM reduction) forced on or off
@@ -288,6 +289,20 @@ def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
         assert np.abs(ya - yb).max() <= 5e-5, np.abs(ya - yb).max()
     finally:
         eng2.close()
+
+
+def test_sliding_window_dwconv_layernorm_equals_the_tiled_kernel(rig):
+    """Depthwise conv + LayerNorm: the register sliding-window kernel (chains of rows, packed f32x2 FMAs, cross-warp LayerNorm)
+    against the shared-memory tiled kernel on ragged packed sequences with an empty sequence, bucket-padding rows, every
+    dilation / width / tap count of the graphs, same-padded and causal, chains longer and shorter than a sequence."""
+    if rig["name"] != "full":
+        pytest.skip("kernel-level check, independent of the graphs")
+    eng = rig["eng"]
+    for rows, C, K, dil, causal, B, rt in [(4736, 256, 5, 1, False, 32, 0), (4736, 256, 5, 8, False, 32, 8), (4736, 256, 5, 4, True, 7, 16),
+                                           (1000, 512, 7, 1, False, 3, 4), (5555, 512, 7, 4, False, 32, 32), (5555, 512, 7, 2, True, 5, 64),
+                                           (333, 128, 5, 2, False, 4, 4), (130, 128, 7, 1, False, 1, 8), (27726, 512, 7, 2, False, 32, 0)]:
+        _, _, diff = eng.debug_dwconv(rows, C, K, dil, causal, B, rt, 2)
+        assert diff <= 2e-5, (rows, C, K, dil, causal, B, rt, diff)
 
 
 def test_twenty_euler_steps_stay_inside_the_north_star_bound(rig):
