@@ -35,6 +35,7 @@ constexpr int UNITS_PER_PHASE = (C / BK) * (HC / 128);     // 8
 constexpr int RECV_BYTES = BM * 64 * 4;           // 32 KB: one sender's partial for my 64 columns
 static_assert(3 * RECV_BYTES <= SLOTS * UNIT, "receive slots alias the weight ring");
 static_assert(HC == C, "phase 1 and phase 2 share the unit schedule");
+constexpr int HC_THIN = 128, CS_THIN = H / HC_THIN;        // "thin" split form: eight hidden slices of 128 per row tile (small batches)
 
 struct Params {
     int M;
@@ -61,7 +62,10 @@ STC_DEVINL void st_cluster_v4(uint32_t addr, float a, float b, float c, float d)
 // kCluster: the four CTAs of a row tile form a cluster and reduce over DSMEM (needs all clusters resident in one wave: 33 fit
 // on a B200). !kCluster: four independent CTAs (blockIdx.x % 4 = hidden slice) write their partial outputs to global scratch
 // and mlp_reduce_kernel finishes the block — no placement constraint, 37 row tiles fill the 148 SMs.
-template <bool kCluster>
+// HCt: hidden units per CTA. 256 (CS = 4 CTAs per row tile) everywhere the SMs are full; 128 (the "thin" form, eight CTAs per row
+// tile, !kCluster only) when 8 x row tiles still fit one wave: a CTA's serial chain a-tile -> S -> GELU -> O halves (18 -> ~12 us
+// for a single row tile — the batch-1 latency path runs 172 of these per utterance).
+template <bool kCluster, int HCt = HC>
 STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo, const CUtensorMap& map_w1_hi,
                                   const CUtensorMap& map_w1_lo, const CUtensorMap& map_w2_hi, const CUtensorMap& map_w2_lo,
                                   const Params& p) {
@@ -78,15 +82,18 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     const uint32_t tmem_slot = bar + 104;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int crank = kCluster ? (int)cluster_ctarank() : (int)(blockIdx.x % CS);
-    const int m0 = (kCluster ? (int)cluster_id_x() : (int)(blockIdx.x / CS)) * BM;
+    static_assert(HCt == HC || (HCt == HC_THIN && !kCluster), "hidden slice per CTA");
+    constexpr int CSt = H / HCt;
+    constexpr int U1 = (C / BK) * (HCt / 128), U2 = (HCt / BK) * (C / 128);      // weight units of phase 1 / phase 2
+    const int crank = kCluster ? (int)cluster_ctarank() : (int)(blockIdx.x % CSt);
+    const int m0 = (kCluster ? (int)cluster_id_x() : (int)(blockIdx.x / CSt)) * BM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
         tma_prefetch_desc(&map_w1_lo); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo);
         mbar_init(bar_a, p.dw_wT ? 8 : 1); mbar_init(bar_s1, 1); mbar_init(bar_o, 1);
         for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int j = 0; j < HC / BK; ++j) mbar_init(bar_p(j), 8);
+        for (int j = 0; j < HCt / BK; ++j) mbar_init(bar_p(j), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -105,18 +112,20 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                     tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
                 }
             }
-            for (int u = 0; u < 2 * UNITS_PER_PHASE; ++u) {
+            for (int u = 0; u < U1 + U2; ++u) {
                 const int s = u % SLOTS;
                 mbar_wait(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
                 const uint32_t dst = smem_base + OFF_RING + s * UNIT;
                 mbar_expect_tx(full_bar(s), UNIT);
-                const int v = u % UNITS_PER_PHASE, kb = v >> 1, nh = v & 1;
-                if (u < UNITS_PER_PHASE) {          // W1[hidden rows, C]: rows crank*HC + nh*128, K block kb of C
-                    tma_load_2d(dst, &map_w1_hi, full_bar(s), kb * BK, crank * HC + nh * 128);
-                    tma_load_2d(dst + KBLK, &map_w1_lo, full_bar(s), kb * BK, crank * HC + nh * 128);
+                const bool second = u >= U1;
+                const int v = second ? u - U1 : u;
+                const int kb = (second || HCt == HC) ? v >> 1 : v, nh = (second || HCt == HC) ? v & 1 : 0;
+                if (!second) {                      // W1[hidden rows, C]: rows crank*HCt + nh*128, K block kb of C
+                    tma_load_2d(dst, &map_w1_hi, full_bar(s), kb * BK, crank * HCt + nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w1_lo, full_bar(s), kb * BK, crank * HCt + nh * 128);
                 } else {                            // W2[C rows, hidden]: rows nh*128, K block kb of this CTA's hidden slice
-                    tma_load_2d(dst, &map_w2_hi, full_bar(s), crank * HC + kb * BK, nh * 128);
-                    tma_load_2d(dst + KBLK, &map_w2_lo, full_bar(s), crank * HC + kb * BK, nh * 128);
+                    tma_load_2d(dst, &map_w2_hi, full_bar(s), crank * HCt + kb * BK, nh * 128);
+                    tma_load_2d(dst + KBLK, &map_w2_lo, full_bar(s), crank * HCt + kb * BK, nh * 128);
                 }
             }
         }
@@ -124,9 +133,10 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
         mbar_wait(bar_a, 0);
-        for (int u = 0; u < 2 * UNITS_PER_PHASE; ++u) {
-            const int s = u % SLOTS, v = u % UNITS_PER_PHASE, kb = v >> 1, nh = v & 1;
-            const bool second = u >= UNITS_PER_PHASE;
+        for (int u = 0; u < U1 + U2; ++u) {
+            const bool second = u >= U1;
+            const int s = u % SLOTS, v = second ? u - U1 : u;
+            const int kb = (second || HCt == HC) ? v >> 1 : v, nh = (second || HCt == HC) ? v & 1 : 0;
             if (second && nh == 0) mbar_wait(bar_p(kb), 0);             // P k-block kb written by the epilogue warps
             mbar_wait(full_bar(s), (u / SLOTS) & 1);
             tc_fence_after();
@@ -143,8 +153,8 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                     umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
                 }
                 umma_commit(empty_bar(s));
-                if (u == UNITS_PER_PHASE - 1) umma_commit(bar_s1);      // S complete; the a-tile is dead
-                if (u == 2 * UNITS_PER_PHASE - 1) umma_commit(bar_o);   // partial O complete; ring and P are dead
+                if (u == U1 - 1) umma_commit(bar_s1);                   // S complete; the a-tile is dead
+                if (u == U1 + U2 - 1) umma_commit(bar_o);               // partial O complete; ring and P are dead
             }
             __syncwarp();
         }
@@ -229,11 +239,11 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
         mbar_wait(bar_s1, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 0; j < HC / BK; ++j) {
+        for (int j = 0; j < HCt / BK; ++j) {
             uint32_t v[32];
             __syncwarp();
             tmem_ld32(trow + j * BK + half * 32, v);
-            const float* b1 = p.b1 + crank * HC + j * BK + half * 32;
+            const float* b1 = p.b1 + crank * HCt + j * BK + half * 32;
             uint8_t* p_hi = smem_gen + OFF_X + j * KBLK + prow_off;
             uint8_t* p_lo = p_hi + (C / BK) * KBLK;
 #pragma unroll
@@ -377,6 +387,14 @@ convnext_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                     const Params p) {
     convnext_mlp_body<true>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_thin_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                         const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                         const Params p) {
+    convnext_mlp_body<false, HC_THIN>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -627,7 +645,7 @@ __global__ void __launch_bounds__(256)
 mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
                   const float* __restrict__ mask, float* __restrict__ x, int M, const float* __restrict__ add_vec,
                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int nslice) {
     pdl_trigger(); pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -639,8 +657,8 @@ mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const fl
         const float4 a0 = *reinterpret_cast<const float4*>(partial + i), a1 = *reinterpret_cast<const float4*>(partial + i + 4);
         y[0] = a0.x; y[1] = a0.y; y[2] = a0.z; y[3] = a0.w; y[4] = a1.x; y[5] = a1.y; y[6] = a1.z; y[7] = a1.w;
     }
-#pragma unroll
-    for (int s = 1; s < CS; ++s) {
+#pragma unroll 4
+    for (int s = 1; s < nslice; ++s) {
         const float4 v0 = *reinterpret_cast<const float4*>(partial + s * slice + i), v1 = *reinterpret_cast<const float4*>(partial + s * slice + i + 4);
         y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x; y[5] += v1.y; y[6] += v1.z; y[7] += v1.w;
     }
@@ -686,14 +704,14 @@ mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const fl
 // (4.2 vs 7.0 us at 4 736 rows, profiles/r1w_mlp_ncu_full_summary.txt), so blocks with nothing folded in keep this form.
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
-                  const float* __restrict__ mask, float* __restrict__ x, int M) {
+                  const float* __restrict__ mask, float* __restrict__ x, int M, int nslice) {
     pdl_trigger(); pdl_wait();
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= (size_t)M * C) return;
     const int row = (int)(i / C), col = (int)(i % C);
     float4 acc = *reinterpret_cast<const float4*>(partial + i);
-#pragma unroll
-    for (int s = 1; s < CS; ++s) {
+#pragma unroll 4
+    for (int s = 1; s < nslice; ++s) {
         const float4 v = *reinterpret_cast<const float4*>(partial + s * slice + i);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -195,7 +195,7 @@ struct Handle {
     // per-channel weight is re-fetched from L2 (~1.6 MB per CTA on top of the 0.5 MB of GEMM weights). OFF by default.
     bool mlp_producer = false;
     int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
-    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks), 4 "ts"
+    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks), 4 "ts", 5 "thin" always
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
     bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
@@ -203,6 +203,7 @@ struct Handle {
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
                                       // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
     int mlp_epi = 8;                  // env STC_MLP_EPI: epilogue warps of the TS form (8 or 16)
+    bool mlp_thin = true;             // env STC_MLP_THIN=0: never use the thin split form (eight 128-unit hidden slices per row tile)
     bool dw_slide = true;             // env STC_DW=tile: shared-memory tiled depthwise conv + LayerNorm instead of the register sliding window
     int dw_rt = 0;                    // env STC_DW_RT: rows per chain of the sliding-window kernel (0: heuristic)
     int dw_ring = -1;                 // env STC_DW_RING: 1 / 0 force the shared-memory ring prefetch on / off (-1: by chain length)
@@ -825,7 +826,9 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
     if (mlp_mode == 2) return 0;
     if (mlp_mode == 3) return 2;
     if (mlp_mode == 4) return 3;
-    (void)rows;
+    if (mlp_mode == 5) return 4;
+    // "thin" split form (eight hidden slices of 128 per row tile) while its CTAs still fit one wave: small batches / batch-1 latency
+    if (mlp_thin && (int)cdiv(rows, mlp::BM) * mlp::CS_THIN <= num_sms) return 4;
     return 2;
 }
 
@@ -842,7 +845,8 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
-    if (form >= 2) p.partial = ws<float>(slice * mlp::CS);
+    const int nslice = form == 4 ? mlp::CS_THIN : mlp::CS;
+    if (form >= 2) p.partial = ws<float>(slice * nslice);
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
@@ -861,16 +865,19 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
                     launch_pdl(this, mlp::convnext_mlp_ts_kernel<8>, dim3(tiles * mlp::CS), dim3(64 + 32 * 8), (size_t)mlp::SMEM_BYTES, stream,
                                mah, mal, w1h, w1l, w2h, w2l, mpart, p);
             }
+            else if (form == 4)
+                launch_pdl(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                           mah, mal, w1h, w1l, w2h, w2l, p);
             else
                 launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                            mah, mal, w1h, w1l, w2h, w2l, p);
             if (post)
                 launch_pdl(this, mlp::mlp_reduce_post_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
                            (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
-                           post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr);
+                           post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr, nslice);
             else
                 launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
-                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows);
+                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, nslice);
             ++launches;
         }
         ++launches;
@@ -1412,10 +1419,11 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
-        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : 0; }
+        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : 0; }
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
+        { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); }
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
         { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
@@ -1444,6 +1452,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
         }
@@ -2106,14 +2115,14 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
             float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
             Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
-            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS); h->ws<long long>(64); return; }     // split form's scratch
+            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS_THIN); h->ws<long long>(64); return; }     // split form's scratch
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
-            const int form = h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
+            const int form = h->mlp_mode == 5 ? 4 : h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
             auto fused = [&](float* x) { h->fused_mlp(&a, M, cn, x, nullptr, mask, form); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;
