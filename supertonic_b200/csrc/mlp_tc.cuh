@@ -79,6 +79,9 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     auto full_bar = [&](int s) { return bar + 24 + 8u * s; };
     auto empty_bar = [&](int s) { return bar + 48 + 8u * s; };
     auto bar_p = [&](int j) { return bar + 72 + 8u * j; };
+    // a-tile K block kb (hi + lo, 32 KB) has landed: the first MMAs start after 32 KB of `a` + one weight unit instead of after the
+    // whole 128 KB tile (producer mode keeps the single bar_a)
+    auto bar_ak = [&](int kb) { return kb == 0 ? bar_a : bar + 160 + 8u * kb; };
     const uint32_t tmem_slot = bar + 104;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,6 +95,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi);
         tma_prefetch_desc(&map_w1_lo); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo);
         mbar_init(bar_a, p.dw_wT ? 8 : 1); mbar_init(bar_s1, 1); mbar_init(bar_o, 1);
+        for (int kb = 1; kb < C / BK; ++kb) mbar_init(bar_ak(kb), 1);
         for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int j = 0; j < HCt / BK; ++j) mbar_init(bar_p(j), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -105,13 +109,12 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
 
     if (warp == 0) {
         if (elect_one()) {
-            if (!p.dw_wT) {
-                mbar_expect_tx(bar_a, X_BYTES);
-                for (int kb = 0; kb < C / BK; ++kb) {
-                    tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_a, kb * BK, m0);
-                    tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_a, kb * BK, m0);
-                }
-            }
+            auto load_a = [&](int kb) {
+                mbar_expect_tx(bar_ak(kb), 2 * KBLK);
+                tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_ak(kb), kb * BK, m0);
+                tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_ak(kb), kb * BK, m0);
+            };
+            if (!p.dw_wT) load_a(0);
             for (int u = 0; u < U1 + U2; ++u) {
                 const int s = u % SLOTS;
                 mbar_wait(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
@@ -127,16 +130,20 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                     tma_load_2d(dst, &map_w2_hi, full_bar(s), crank * HCt + kb * BK, nh * 128);
                     tma_load_2d(dst + KBLK, &map_w2_lo, full_bar(s), crank * HCt + kb * BK, nh * 128);
                 }
+                if (u == 0 && !p.dw_wT) {           // the rest of the a-tile queues behind the first weight unit
+                    for (int k2 = 1; k2 < C / BK; ++k2) load_a(k2);
+                }
             }
         }
         __syncwarp();                      // reconverge before the (warp-aligned) cluster barriers below
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
-        mbar_wait(bar_a, 0);
+        if (p.dw_wT) mbar_wait(bar_a, 0);
         for (int u = 0; u < U1 + U2; ++u) {
             const bool second = u >= U1;
             const int s = u % SLOTS, v = second ? u - U1 : u;
             const int kb = (second || HCt == HC) ? v >> 1 : v, nh = (second || HCt == HC) ? v & 1 : 0;
+            if (!second && nh == 0 && !p.dw_wT) mbar_wait(bar_ak(kb), 0);       // a-tile K block kb has landed
             if (second && nh == 0) mbar_wait(bar_p(kb), 0);             // P k-block kb written by the epilogue warps
             mbar_wait(full_bar(s), (u / SLOTS) & 1);
             tc_fence_after();
