@@ -411,11 +411,23 @@ template <int NW> STC_DEVINL float group_total(const float* p) {     // sum of t
 // keeps in flight — the long vocoder chains are bound by bytes in flight, the short VE / TE chains (one or two iterations)
 // by latency and keep the register prefetch.
 constexpr int RING_D = 4;
-template <int NW, int K, bool RING, typename Out>
+// RED: the kernel also FINISHES the previous ConvNeXt block (what mlp_reduce_kernel / mlp_reduce_post_kernel do): the row it
+// "loads" is  x_new = ((sum_s partial_s + b2) * gamma + x) * mask  [then (x_new + add_vec) * mask], computed from the fused MLP's
+// hidden-slice partials in the same order and with the same expressions as those kernels (bit-identical); halo rows are
+// recomputed by the neighbouring chains, the chain that owns a row writes it to x_out — a buffer OTHER than x, because the
+// neighbours still read the old x of their halo rows. One launch instead of two per ConvNeXt -> ConvNeXt transition.
+struct SlideRed {
+    const float* partial = nullptr; size_t slice = 0; int nslice = 0;
+    const float* b2 = nullptr; const float* gamma = nullptr; const float* mask = nullptr; const float* add_vec = nullptr;
+    float* x_out = nullptr;
+    int jc = 0;                 // window slot of an output row's own input row: pad_left / dil
+};
+template <int NW, int K, bool RING, typename Out, bool RED = false>
 __global__ void __launch_bounds__(128)
 dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                        const float* __restrict__ g, const float* __restrict__ beta, Out out,
-                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
+                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT, const SlideRed rd) {
+    static_assert(!(RED && RING), "the reducing form uses the register prefetch");
     pdl_trigger(); pdl_wait();
     constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = 4;
     __shared__ __align__(16) float red[2][GPB][U][NW];
@@ -432,8 +444,31 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
     }
     const float4 bias = __ldg(reinterpret_cast<const float4*>(wb) + t);
     const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + t), bv = __ldg(reinterpret_cast<const float4*>(beta) + t);
+    float4 rb2, rgm, rav;
+    if constexpr (RED) {
+        rb2 = __ldg(reinterpret_cast<const float4*>(rd.b2) + t); rgm = __ldg(reinterpret_cast<const float4*>(rd.gamma) + t);
+        rav = rd.add_vec ? __ldg(reinterpret_cast<const float4*>(rd.add_vec) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     auto load_row = [&](int r) -> float4 {
-        return (r >= 0 && r < rows) ? *reinterpret_cast<const float4*>(xc + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(r >= 0 && r < rows)) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (!RED) return *reinterpret_cast<const float4*>(xc + (size_t)r * C);
+        else {
+            const size_t i = (size_t)r * C + 4 * t;
+            float4 acc = *reinterpret_cast<const float4*>(rd.partial + i);
+#pragma unroll 4
+            for (int sl = 1; sl < rd.nslice; ++sl) {
+                const float4 v = *reinterpret_cast<const float4*>(rd.partial + sl * rd.slice + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float4 res = *reinterpret_cast<const float4*>(x + i);
+            const float mk = rd.mask ? __ldg(rd.mask + r) : 1.f;
+            acc.x = ((acc.x + rb2.x) * rgm.x + res.x) * mk; acc.y = ((acc.y + rb2.y) * rgm.y + res.y) * mk;
+            acc.z = ((acc.z + rb2.z) * rgm.z + res.z) * mk; acc.w = ((acc.w + rb2.w) * rgm.w + res.w) * mk;
+            if (rd.add_vec) {
+                acc.x = (acc.x + rav.x) * mk; acc.y = (acc.y + rav.y) * mk; acc.z = (acc.z + rav.z) * mk; acc.w = (acc.w + rav.w) * mk;
+            }
+            return acc;
+        }
     };
     const int rw0 = r_first - pad_left;                // window slot j of output i holds row rw0 + (i + j) * dil
     float4 win[K - 1 + U], nxt[RING ? 1 : U];
@@ -489,6 +524,10 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
                 if (b >= B) b = -1; else { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
             }
             pad[u] = b < 0;
+            if constexpr (RED) {                       // this chain owns row r of the residual stream
+                // same-padded (jc = (K-1)/2) or causal (jc = K-1) convolutions only: static register indices
+                if (r < rows) *reinterpret_cast<float4*>(rd.x_out + (size_t)r * C + 4 * t) = rd.jc == K - 1 ? win[u + K - 1] : win[u + (K - 1) / 2];
+            }
             y[u][0] = make_float2(bias.x, bias.y); y[u][1] = make_float2(bias.z, bias.w);
             const int first = r - pad_left;
             if (b < 0) {                               // bucket padding row: keep it finite

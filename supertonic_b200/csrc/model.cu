@@ -75,6 +75,10 @@ struct PostOps {
     const float* add_vec = nullptr;                      // x <- (x + add_vec) * mask   (time conditioning)
     const float* ln_g = nullptr; const float* ln_b = nullptr;   // with `out`: LayerNorm(x); without ln_g: x itself
     const Act* out = nullptr;                            // split-bf16 operand of the next layer
+    // the next layer is another ConvNeXt block: the reduce kernel also runs ITS depthwise conv + LayerNorm (dwconv_ln_slide_kernel
+    // <.., RED>): `out` receives LayerNorm(dwconv(x_new)), the residual stream continues in x_out (not in place, see SlideRed)
+    const ConvNeXt* next_dw = nullptr;
+    float* x_out = nullptr;
 };
 
 struct VeCtx {
@@ -185,9 +189,15 @@ struct Handle {
                                          const Seq& seq, float eps, T* out_plain, const Act* out_act);
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
-    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr);
+    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr, const Act* a_pre = nullptr);
     void apply_post(const PostOps& post, float* x, const Seq& seq, int C);      // the same post-ops as separate launches
     int mlp_form(const ConvNeXt& c, int rows) const;
+    bool can_chain_dw(const ConvNeXt& c, const ConvNeXt& n, int rows) const;
+    // env STC_DW_CHAIN=1: fold the next ConvNeXt block's depthwise conv + LayerNorm into the reduce kernel of the block before it
+    // (dwconv_ln_slide_kernel<.., RED>). Bit-identical, 120 launches fewer per step, and measured SLOWER on B200 (11.02 vs 10.46
+    // ms/step, batch-1 latency 6.46 vs 5.58 ms): a chain reduces its K-1 halo rows again (8 x 5..9 loads per thread against one row's
+    // 5 in the plain reduce kernel's 300k threads), which costs more than the launch it saves. OFF by default.
+    bool dw_chain = false;
     void fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
                    const PostOps* post = nullptr);
     // env STC_MLP_PRODUCER=1: compute LayerNorm(dwconv(x)) inside the fused MLP kernel instead of a separate launch. Measured
@@ -639,8 +649,8 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             dim3 sg(cdiv(chains, 512 / C));
 #define STC_SLIDE(NW, KK)                                                                                                                     \
     do {                                                                                                                                      \
-        if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT); \
-        else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT);     \
+        if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{}); \
+        else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{});     \
         return;                                                                                                                               \
     } while (0)
             switch (C / 128 * 10 + K) {
@@ -832,6 +842,15 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
     return 2;
 }
 
+// The reduce kernel of block `c` can also run the depthwise conv + LayerNorm of the following block `n` (PostOps::next_dw)
+bool Handle::can_chain_dw(const ConvNeXt& c, const ConvNeXt& n, int rows) const {
+    if (!dw_chain || !dw_slide || mlp_producer || mlp_form(c, rows) < 2 || mlp_form(n, rows) < 2) return false;
+    if (n.C != 256 || n.K != 5 || n.dil < 1 || n.pad_left % n.dil) return false;
+    const int jc = n.pad_left / n.dil;
+    if (jc != n.K - 1 && jc != (n.K - 1) / 2) return false;
+    return rows <= num_sms * 8 * 12;                 // chains of 4 rows (register prefetch), as launch_dwln would choose
+}
+
 // a == nullptr: producer mode — the kernel computes LayerNorm(dwconv(x)) itself (needs seq, c.K <= mlp::KMAX).
 void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
                        const PostOps* post) {
@@ -871,7 +890,17 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
             else
                 launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                            mah, mal, w1h, w1l, w2h, w2l, p);
-            if (post)
+            if (post && post->next_dw) {
+                // reduce + the next block's depthwise conv + LayerNorm in one launch (eligibility: Handle::can_chain_dw)
+                const ConvNeXt& nd = *post->next_dw;
+                SlideRed rd; rd.partial = p.partial; rd.slice = slice; rd.nslice = nslice; rd.b2 = p.b2; rd.gamma = p.gamma; rd.mask = p.mask;
+                rd.add_vec = post->add_vec; rd.x_out = post->x_out; rd.jc = nd.pad_left / nd.dil;
+                const int RT = 4;
+                const unsigned chains = cdiv(rows, RT * nd.dil) * nd.dil;
+                launch_pdl(this, (dwconv_ln_slide_kernel<2, 5, false, OutSplit, true>), dim3(cdiv(chains, 2)), dim3(128), (size_t)0, stream,
+                           (const float*)p.x, (const float*)nd.dw_wt, (const float*)nd.dw_b, (const float*)nd.ln_g, (const float*)nd.ln_b,
+                           OutSplit{post->out->hi, post->out->lo}, rows, seq->off, seq->B, nd.dil, nd.pad_left, 1e-6f, RT, rd);
+            } else if (post)
                 launch_pdl(this, mlp::mlp_reduce_post_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
                            (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
                            post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr, nslice);
@@ -897,7 +926,7 @@ void Handle::apply_post(const PostOps& post, float* x, const Seq& seq, int C) {
 }
 
 template <typename T>
-void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post) {
+void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post, const Act* a_pre) {
     size_t mk = mark();
     int rows = seq.rows;
     Epilogue e1; e1.gelu = 1;
@@ -908,8 +937,12 @@ void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* po
         if (form && mlp_producer && c.K <= mlp::KMAX) {
             fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
         } else {
-            Act a = ws_act_for(c.pw1, (size_t)rows * c.C);
-            dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
+            Act a;
+            if (a_pre) a = *a_pre;                 // LayerNorm(dwconv(x)) came out of the previous block's reduce kernel
+            else {
+                a = ws_act_for(c.pw1, (size_t)rows * c.C);
+                dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
+            }
             if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
             else {
                 Act hid = ws_act_for(c.pw2, (size_t)rows * c.H);
@@ -1132,7 +1165,8 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq,
     Act sty = ws_act((size_t)B * S * Cs);
     to_act(style_ttl, (size_t)B * S * Cs, sty);
     Act nxt = ws_act((size_t)rows * C);
-    bool nxt_ready = false;
+    float* x_alt = ws<float>((size_t)rows * C);   // see run_ve_step
+    bool nxt_ready = false, a_ready = false;
     for (size_t li = 0; li < te.layers.size(); ++li) {
         const Layer& l = te.layers[li];
         if (l.type == L_CONVNEXT) {
@@ -1142,8 +1176,14 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq,
                 post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = nxt_ready = true;
             } else if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_PROJ_OUT) {
                 post.out = &nxt; any = nxt_ready = true;
+            } else if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_CONVNEXT &&
+                       can_chain_dw(te.cn[l.idx], te.cn[te.layers[li + 1].idx], rows)) {
+                post.next_dw = &te.cn[te.layers[li + 1].idx]; post.out = &nxt; post.x_out = x_alt; any = true;
             }
-            convnext<float>(te.cn[l.idx], x, tseq, any ? &post : nullptr);
+            const bool had_a = a_ready;
+            convnext<float>(te.cn[l.idx], x, tseq, any ? &post : nullptr, had_a ? &nxt : nullptr);
+            a_ready = post.next_dw != nullptr;
+            if (a_ready) std::swap(x, x_alt);
         } else if (l.type == L_ATTN) {
             const Attention& a = te.at[l.idx];
             const Act* pre_ln = nxt_ready ? &nxt : nullptr;
@@ -1221,8 +1261,9 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
     const Seq& ls = vc.lat;
     int rows = ls.rows, C = ve.C, D = cfg.latent_channels, itc = 0;
     float* x = ws<float>((size_t)rows * C);
+    float* x_alt = ws<float>((size_t)rows * C);   // the residual stream alternates between x and x_alt across chained ConvNeXt blocks
     Act nxt = ws_act((size_t)rows * C);           // operand a ConvNeXt block's reduce kernel prepares for the layer after it
-    bool nxt_ready = false;
+    bool nxt_ready = false, a_ready = false;      // a_ready: nxt holds LayerNorm(dwconv(x)) of the ConvNeXt block that comes next
     for (size_t li = 0; li < ve.layers.size(); ++li) {
         const Layer& l = ve.layers[li];
         switch (l.type) {
@@ -1248,8 +1289,13 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
                     post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = true; nxt_ready = true;
                 } else if (nx < ve.layers.size() && ve.layers[nx].type == L_PROJ_OUT) {
                     post.out = &nxt; any = true; nxt_ready = true;
+                } else if (nx < ve.layers.size() && ve.layers[nx].type == L_CONVNEXT && can_chain_dw(ve.cn[l.idx], ve.cn[ve.layers[nx].idx], rows)) {
+                    post.next_dw = &ve.cn[ve.layers[nx].idx]; post.out = &nxt; post.x_out = x_alt; any = true;
                 }
-                convnext<float>(ve.cn[l.idx], x, ls, any ? &post : nullptr);
+                const bool had_a = a_ready;
+                convnext<float>(ve.cn[l.idx], x, ls, any ? &post : nullptr, had_a ? &nxt : nullptr);
+                a_ready = post.next_dw != nullptr;
+                if (a_ready) std::swap(x, x_alt);
                 break;
             }
             case L_TIME_COND:
@@ -1426,6 +1472,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); }
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
+        { const char* e = getenv("STC_DW_CHAIN"); hd->dw_chain = e && e[0] == '1'; }
         { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
