@@ -154,7 +154,31 @@ def create_app(tts, style_loader: Optional[Callable] = None, max_batch: int = 32
     from fastapi.responses import JSONResponse, Response
     from . import tts as T
 
-    style_loader = style_loader or T.load_voice_style
+    if style_loader is None:
+        # voice-style JSON (50 x 256 + 8 x 16 floats as text) takes longer to parse than a short utterance takes to synthesise:
+        # keep the parsed tensors per (path, mtime, size)
+        cache, cache_mu = {}, threading.Lock()
+
+        def style_loader(paths):
+            ttl, dp = [], []
+            for p in paths:
+                try:
+                    st = os.stat(p)
+                except OSError:
+                    raise RuntimeError(f"Failed to open voice style file: {p}")
+                key = (p, st.st_mtime_ns, st.st_size)
+                with cache_mu:
+                    one = cache.get(key)
+                if one is None:
+                    one = T.load_voice_style([p])
+                    with cache_mu:
+                        if len(cache) >= 256:
+                            cache.clear()
+                        cache[key] = one
+                ttl.append(one.ttl); dp.append(one.dp)
+            if any(t.shape[1:] != ttl[0].shape[1:] for t in ttl) or any(d.shape[1:] != dp[0].shape[1:] for d in dp):
+                raise RuntimeError("voice styles of different dimensions in one request")
+            return T.Style(np.concatenate(ttl, 0), np.concatenate(dp, 0))
     batcher = DynamicBatcher(tts, max_batch, max_wait_ms)
     app = FastAPI(title="Supertonic TTS Service (libsupertonic_cuda)")
     app.state.batcher = batcher
