@@ -36,6 +36,7 @@ constexpr int RECV_BYTES = BM * 64 * 4;           // 32 KB: one sender's partial
 static_assert(3 * RECV_BYTES <= SLOTS * UNIT, "receive slots alias the weight ring");
 static_assert(HC == C, "phase 1 and phase 2 share the unit schedule");
 constexpr int HC_THIN = 128, CS_THIN = H / HC_THIN;        // "thin" split form: eight hidden slices of 128 per row tile (small batches)
+constexpr int HC_THIN64 = 64, CS_THIN64 = H / HC_THIN64;   // sixteen slices of 64 (<= 9 row tiles: the batch-1 latency path)
 
 struct Params {
     int M;
@@ -47,6 +48,12 @@ struct Params {
     const float* dw_wT; const float* dw_b; const float* ln_g; const float* ln_b;     // taps [K][C], bias, LayerNorm scale / shift
     const int* off; int B; int K, dil, pad_left; float eps;                          // packed sequences of x, conv geometry
     long long* trace;               // debug (stc_debug_mlp with STC_MLP_TRACE=1): clock64() stamps of CTA 0's pipeline events
+    // In-kernel reduce (split forms, cooperative launch with grid <= SM count so that every CTA is resident): cnt != null. After its
+    // partial is in global memory a CTA arrives on its row tile's counter, waits for the tile's other hidden-slice CTAs and then
+    // finishes BM / CSt rows of the tile itself — what mlp_reduce_kernel / mlp_reduce_post_kernel would do in a launch of their own.
+    int* cnt;                       // [row tiles][2]: arrivals, departures (self-resetting)
+    const float* add_vec; const float* post_ln_g; const float* post_ln_b;       // post-ops, see mlp_reduce_post_kernel
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
 };
 #define STC_TRACE(idx) do { if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[idx] = clock64(); } while (0)
 
@@ -85,9 +92,10 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     const uint32_t tmem_slot = bar + 104;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    static_assert(HCt == HC || (HCt == HC_THIN && !kCluster), "hidden slice per CTA");
+    static_assert(HCt == HC || ((HCt == HC_THIN || HCt == HC_THIN64) && !kCluster), "hidden slice per CTA");
     constexpr int CSt = H / HCt;
-    constexpr int U1 = (C / BK) * (HCt / 128), U2 = (HCt / BK) * (C / 128);      // weight units of phase 1 / phase 2
+    constexpr int WR1 = HCt < 128 ? HCt : 128;                                    // weight rows of a phase-1 unit (= its MMA N)
+    constexpr int U1 = (C / BK) * (HCt / WR1), U2 = (HCt / BK) * (C / 128);       // weight units of phase 1 / phase 2
     const int crank = kCluster ? (int)cluster_ctarank() : (int)(blockIdx.x % CSt);
     const int m0 = (kCluster ? (int)cluster_id_x() : (int)(blockIdx.x / CSt)) * BM;
 
@@ -119,8 +127,8 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                 const int s = u % SLOTS;
                 mbar_wait(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
                 const uint32_t dst = smem_base + OFF_RING + s * UNIT;
-                mbar_expect_tx(full_bar(s), UNIT);
                 const bool second = u >= U1;
+                mbar_expect_tx(full_bar(s), second ? UNIT : 2 * WR1 * BK * 2);
                 const int v = second ? u - U1 : u;
                 const int kb = (second || HCt == HC) ? v >> 1 : v, nh = (second || HCt == HC) ? v & 1 : 0;
                 if (!second) {                      // W1[hidden rows, C]: rows crank*HCt + nh*128, K block kb of C
@@ -137,7 +145,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
         }
         __syncwarp();                      // reconverge before the (warp-aligned) cluster barriers below
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
+        constexpr uint32_t idesc2 = make_idesc_bf16(BM, 128), idesc1 = make_idesc_bf16(BM, WR1);
         if (p.dw_wT) mbar_wait(bar_a, 0);
         for (int u = 0; u < U1 + U2; ++u) {
             const bool second = u >= U1;
@@ -152,6 +160,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                 const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
                 const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
                 const uint32_t d = tmem_base + (second ? 256 : 0) + nh * 128;
+                const uint32_t idesc = second ? idesc2 : idesc1;
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -299,6 +308,87 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                 }
             }
         }
+        if (p.cnt) {
+            // ===== in-kernel reduce: x <- ((sum_s partial_s + b2) * gamma + x) * mask (+ post-ops) for this CTA's share of the tile's rows,
+            //       partials summed in slice order with the expressions of mlp_reduce_post_kernel (bit-identical to the two-launch form)
+            int* cnt = p.cnt + 2 * (m0 / BM);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();           // cumulative: the CTA's partial stores (ordered before the barrier) precede the arrival
+                atomicAdd(cnt, 1);
+                int seen;
+                do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory"); } while (seen < CSt);
+                if (atomicAdd(cnt + 1, 1) == CSt - 1) { cnt[0] = 0; cnt[1] = 0; }      // every CTA of the tile has seen the full count
+                __threadfence();
+            }
+            __syncthreads();
+            if (warp >= 2) {
+                constexpr int RPC = BM / CSt, RPW = RPC / 8;           // rows per CTA / per epilogue warp
+                static_assert(RPW >= 1, "eight epilogue warps share a CTA's rows");
+                const size_t slice = (size_t)((p.M + BM - 1) / BM) * BM * C;
+                const int c0 = lane * 8, row0 = m0 + crank * RPC + (warp - 2) * RPW;
+                float y[RPW][8];
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const size_t o = (size_t)(row0 + i) * C + c0;
+                    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p.partial + o)), a1 = __ldcg(reinterpret_cast<const float4*>(p.partial + o + 4));
+                    y[i][0] = a0.x; y[i][1] = a0.y; y[i][2] = a0.z; y[i][3] = a0.w; y[i][4] = a1.x; y[i][5] = a1.y; y[i][6] = a1.z; y[i][7] = a1.w;
+                }
+#pragma unroll 4
+                for (int sl = 1; sl < CSt; ++sl) {
+#pragma unroll
+                    for (int i = 0; i < RPW; ++i) {
+                        const size_t o = sl * slice + (size_t)(row0 + i) * C + c0;
+                        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(p.partial + o)), v1 = __ldcg(reinterpret_cast<const float4*>(p.partial + o + 4));
+                        y[i][0] += v0.x; y[i][1] += v0.y; y[i][2] += v0.z; y[i][3] += v0.w; y[i][4] += v1.x; y[i][5] += v1.y; y[i][6] += v1.z; y[i][7] += v1.w;
+                    }
+                }
+                float bb[8], gg[8];
+                *reinterpret_cast<float4*>(bb) = __ldg(reinterpret_cast<const float4*>(p.b2 + c0)); *reinterpret_cast<float4*>(bb + 4) = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 4));
+                *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(p.gamma + c0)); *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4));
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const int row = row0 + i;
+                    if (row >= p.M) continue;
+                    const size_t o = (size_t)row * C + c0;
+                    const float mk = p.mask ? __ldg(p.mask + row) : 1.f;
+                    float rr[8];
+                    *reinterpret_cast<float4*>(rr) = *reinterpret_cast<const float4*>(p.x + o); *reinterpret_cast<float4*>(rr + 4) = *reinterpret_cast<const float4*>(p.x + o + 4);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[i][j] = ((y[i][j] + bb[j]) * gg[j] + rr[j]) * mk;
+                    if (p.add_vec) {
+                        float tt[8];
+                        *reinterpret_cast<float4*>(tt) = __ldg(reinterpret_cast<const float4*>(p.add_vec + c0)); *reinterpret_cast<float4*>(tt + 4) = __ldg(reinterpret_cast<const float4*>(p.add_vec + c0 + 4));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[i][j] = (y[i][j] + tt[j]) * mk;
+                    }
+                    *reinterpret_cast<float4*>(p.x + o) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+                    *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(y[i][4], y[i][5], y[i][6], y[i][7]);
+                    if (!p.out_hi) continue;
+                    if (p.post_ln_g) {
+                        float sm = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sm += y[i][j];
+                        const float mean = warp_sum<float>(sm) / (float)C;
+                        float vv = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { y[i][j] -= mean; vv += y[i][j] * y[i][j]; }
+                        const float inv = 1.0f / sqrtf(warp_sum<float>(vv) / (float)C + 1e-6f);
+                        float g8[8], h8[8];
+                        *reinterpret_cast<float4*>(g8) = __ldg(reinterpret_cast<const float4*>(p.post_ln_g + c0)); *reinterpret_cast<float4*>(g8 + 4) = __ldg(reinterpret_cast<const float4*>(p.post_ln_g + c0 + 4));
+                        *reinterpret_cast<float4*>(h8) = __ldg(reinterpret_cast<const float4*>(p.post_ln_b + c0)); *reinterpret_cast<float4*>(h8 + 4) = __ldg(reinterpret_cast<const float4*>(p.post_ln_b + c0 + 4));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[i][j] = y[i][j] * inv * g8[j] + h8[j];
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) split_pair(y[i][2 * t], y[i][2 * t + 1], hi[t], lo[t]);
+                    *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -402,6 +492,15 @@ convnext_mlp_thin_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                          const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                          const Params p) {
     convnext_mlp_body<false, HC_THIN>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+// map_w1_*: boxes of 64 weight rows here (128 in the other forms)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_thin64_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                           const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                           const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                           const Params p) {
+    convnext_mlp_body<false, HC_THIN64>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)

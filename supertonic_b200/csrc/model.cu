@@ -213,6 +213,13 @@ struct Handle {
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
                                       // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
     int mlp_epi = 8;                  // env STC_MLP_EPI: epilogue warps of the TS form (8 or 16)
+    // env STC_MLP_INREDUCE=1: finish a split-form block inside the MLP kernel (cooperative launch; a CTA waits for its row tile's
+    // sibling CTAs and reduces BM / CS rows itself) instead of launching the reduce kernel. Bit-identical and measured SLOWER on
+    // B200: 23.9 vs 20.0 us per block at 37 row tiles, 16.0 vs 14.3 us at one tile, 10.86 vs 10.40 ms per configs[1] step — the wait
+    // for the slowest sibling plus a 256-thread reduce sit on every CTA's critical path, where the separate kernel spreads the
+    // same 24 MB over 300k threads in 4 us. OFF by default.
+    bool mlp_inreduce = false;
+    int* mlp_cnt = nullptr;           // [64 row tiles][2] arrival / departure counters of the in-kernel reduce (zeroed once, self-resetting)
     bool mlp_thin = true;             // env STC_MLP_THIN=0: never use the thin split form (eight 128-unit hidden slices per row tile)
     bool dw_slide = true;             // env STC_DW=tile: shared-memory tiled depthwise conv + LayerNorm instead of the register sliding window
     int dw_rt = 0;                    // env STC_DW_RT: rows per chain of the sliding-window kernel (0: heuristic)
@@ -265,6 +272,21 @@ static inline void launch_pdl(stc::Handle* h, void (*kernel)(KArgs...), dim3 gri
     cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+}
+
+// Cooperative launch (every CTA of the grid resident at once; the launch fails instead of deadlocking if that is impossible): the
+// fused MLP's in-kernel reduce waits on sibling CTAs.
+template <typename... KArgs, typename... Args>
+static inline void launch_coop(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("cooperative kernel launch: ") + cudaGetErrorString(e));
 }
 
 #define STC_LAUNCH(h, kernel, grid, block, smem, ...)                                       \
@@ -837,7 +859,9 @@ int Handle::mlp_form(const ConvNeXt& c, int rows) const {
     if (mlp_mode == 3) return 2;
     if (mlp_mode == 4) return 3;
     if (mlp_mode == 5) return 4;
+    if (mlp_mode == 6) return 5;
     // "thin" split form (eight hidden slices of 128 per row tile) while its CTAs still fit one wave: small batches / batch-1 latency
+    if (mlp_thin && (int)cdiv(rows, mlp::BM) * mlp::CS_THIN64 <= num_sms) return 5;       // sixteen slices of 64 (<= 9 row tiles)
     if (mlp_thin && (int)cdiv(rows, mlp::BM) * mlp::CS_THIN <= num_sms) return 4;
     return 2;
 }
@@ -864,8 +888,18 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
-    const int nslice = form == 4 ? mlp::CS_THIN : mlp::CS;
+    const int nslice = form == 5 ? mlp::CS_THIN64 : form == 4 ? mlp::CS_THIN : mlp::CS;
     if (form >= 2) p.partial = ws<float>(slice * nslice);
+    // in-kernel reduce: split forms whose grid fits the SMs (cooperative launch), nothing chained behind the reduce
+    const bool inred = mlp_inreduce && mlp_cnt && (form == 2 || form == 4 || form == 5) && a && tiles * nslice <= num_sms && tiles <= 64 &&
+                       !g_use_pdl && !(post && post->next_dw);
+    if (inred) {
+        p.cnt = mlp_cnt;
+        if (post) {
+            p.add_vec = post->add_vec; p.post_ln_g = post->ln_g; p.post_ln_b = post->ln_b;
+            p.out_hi = post->out ? post->out->hi : nullptr; p.out_lo = post->out ? post->out->lo : nullptr;
+        }
+    }
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
@@ -884,13 +918,26 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
                     launch_pdl(this, mlp::convnext_mlp_ts_kernel<8>, dim3(tiles * mlp::CS), dim3(64 + 32 * 8), (size_t)mlp::SMEM_BYTES, stream,
                                mah, mal, w1h, w1l, w2h, w2l, mpart, p);
             }
-            else if (form == 4)
-                launch_pdl(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                           mah, mal, w1h, w1l, w2h, w2l, p);
-            else
-                launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                           mah, mal, w1h, w1l, w2h, w2l, p);
-            if (post && post->next_dw) {
+            else if (form == 5) {
+                const CUtensorMap w1h64 = tmap(c.pw1.w_hi, c.H, c.C, 64), w1l64 = tmap(c.pw1.w_lo, c.H, c.C, 64);
+                if (inred) launch_coop(this, mlp::convnext_mlp_thin64_kernel, dim3(tiles * mlp::CS_THIN64), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                       mah, mal, w1h64, w1l64, w2h, w2l, p);
+                else launch_pdl(this, mlp::convnext_mlp_thin64_kernel, dim3(tiles * mlp::CS_THIN64), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                mah, mal, w1h64, w1l64, w2h, w2l, p);
+            } else if (form == 4) {
+                if (inred) launch_coop(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                       mah, mal, w1h, w1l, w2h, w2l, p);
+                else launch_pdl(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                mah, mal, w1h, w1l, w2h, w2l, p);
+            } else {
+                if (inred) launch_coop(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                       mah, mal, w1h, w1l, w2h, w2l, p);
+                else launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                                mah, mal, w1h, w1l, w2h, w2l, p);
+            }
+            if (inred) {
+                --launches;                 // no reduce launch follows (the common `++launches` below counts one)
+            } else if (post && post->next_dw) {
                 // reduce + the next block's depthwise conv + LayerNorm in one launch (eligibility: Handle::can_chain_dw)
                 const ConvNeXt& nd = *post->next_dw;
                 SlideRed rd; rd.partial = p.partial; rd.slice = slice; rd.nslice = nslice; rd.b2 = p.b2; rd.gamma = p.gamma; rd.mask = p.mask;
@@ -1465,11 +1512,12 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
-        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : 0; }
+        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : std::string(e) == "thin64" ? 6 : 0; }
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
+        { const char* e = getenv("STC_MLP_INREDUCE"); hd->mlp_inreduce = e && e[0] == '1'; }
         { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); }
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
         { const char* e = getenv("STC_DW_CHAIN"); hd->dw_chain = e && e[0] == '1'; }
@@ -1500,8 +1548,11 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaMalloc((void**)&hd->mlp_cnt, 128 * sizeof(int))); hd->owned.push_back(hd->mlp_cnt);
+            STC_CUDA(cudaMemset(hd->mlp_cnt, 0, 128 * sizeof(int)));
         }
         {
             const int big = 200 * 1024;
@@ -2162,14 +2213,14 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
             float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
             Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
-            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS_THIN); h->ws<long long>(64); return; }     // split form's scratch
+            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS_THIN64); h->ws<long long>(64); return; }     // split form's scratch
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
-            const int form = h->mlp_mode == 5 ? 4 : h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
+            const int form = h->mlp_mode == 6 ? 5 : h->mlp_mode == 5 ? 4 : h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
             auto fused = [&](float* x) { h->fused_mlp(&a, M, cn, x, nullptr, mask, form); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;

@@ -258,7 +258,7 @@ def test_error_paths(rig):
 
 
 @pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP", "fused"), ("STC_MLP", "split"), ("STC_MLP_PRODUCER", "1"),
-                                 ("STC_DW", "tile"), ("STC_MLP", "thin"), ("STC_DW_CHAIN", "1")])
+                                 ("STC_DW", "tile"), ("STC_MLP", "thin"), ("STC_MLP", "thin64"), ("STC_DW_CHAIN", "1"), ("STC_MLP_INREDUCE", "1")])
 def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
     """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
     fp32 core. STC_MLP=fused / unfused: the 4-CTA-cluster fused ConvNeXt MLP (mlp_tc.cuh, DSMEM reduction) forced on or off

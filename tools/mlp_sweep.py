@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from supertonic_b200 import capi, surrogate
-forms = sys.argv[1].split(",") if len(sys.argv) > 1 else ["fused", "split", "thin", "ts", "ts16"]
+forms = sys.argv[1].split(",") if len(sys.argv) > 1 else ["fused", "split", "thin", "thin64", "ts", "ts16"]
 rows = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [128, 1024, 1536, 2048, 4096, 4224, 4352, 4736, 4864, 8448, 9600]
 for form in forms:
     os.environ["STC_MLP"] = "ts" if form.startswith("ts") else form
