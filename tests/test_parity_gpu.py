@@ -122,6 +122,37 @@ def test_synthesize_matches_oracle_infer(rig, steps):
     assert snr >= SNR_NORTH_STAR and snr >= SNR_EXPECTED, snr
 
 
+def test_unchunked_text_longer_than_the_tensor_core_attention_limit(rig):
+    """`batch()` does not chunk (cpp/helper.cpp:725-734): a 600-character text is ~610 tokens, past the 320 keys the tcgen05
+    attention core keeps in TMEM, next to a short one (ragged batch). The library must fall back to its CUDA-core attention for
+    that launch and still match the oracle: frame counts bit-exact, latents / waveform within tolerance."""
+    from oracle import host_ref
+    from oracle.pipeline import make_noise
+    rng = np.random.default_rng(5)
+    texts = [U.make_text(rng, 600), U.make_text(rng, 40)]
+    ids, mask = host_ref.unicode_processor_call(rig["ora"].indexer, texts, ["en", "en"])
+    assert ids.shape[1] > 320
+    ttl, dp = U.styles(rig["root"], ["F2", "M1"])
+    tr = {}
+    wav_ref, dur_ref = rig["ora"].infer_ids(ids, mask, ttl, dp, 3, np.float32(1.05), make_noise(11), tr)
+    L = tr["latent_len"]
+    out = rig["eng"].synthesize(ids, mask, ttl, dp, 3, 1.05, noise=make_noise(11)(2, 144, L), want_latent=True)
+    assert out["L"] == L
+    np.testing.assert_array_equal(out["duration"], dur_ref)
+    np.testing.assert_array_equal(out["wav_lengths"], tr["wav_lengths"])
+    err = np.abs(out["latent"] - tr["xs"][-1]).max()
+    assert err <= LAT_TOL_NORTH_STAR and err <= LAT_TOL_EXPECTED, err
+    snr = U.snr_db(out["wav"].reshape(-1), wav_ref)
+    assert snr >= SNR_NORTH_STAR and snr >= SNR_EXPECTED, snr
+    # the same two utterances through the packed throughput path
+    lens = mask.reshape(2, -1).sum(1).astype(np.int32)
+    pk = rig["eng"].synthesize_packed(ids, mask, ttl, dp, 3, 1.05, noise=make_noise(11)(2, 144, L))
+    for b in range(2):
+        n = int(tr["wav_lengths"][b])
+        assert U.snr_db(pk["wavs"][b][:n], wav_ref.reshape(2, -1)[b, :n]) >= SNR_EXPECTED
+    assert lens[0] > 320
+
+
 def test_tf32_vocoder_mode_stays_inside_the_waveform_bound(rig):
     """STC_VOC=tf32 (opt-in): the vocoder's GEMMs run single-pass kind::tf32 on operands rounded to nearest. The waveform must stay
     inside the north-star bound (>= 40 dB) with margin (>= 60 dB asserted; ~70 dB measured); the default mode keeps >= 80 dB."""
