@@ -96,6 +96,12 @@ struct Handle {
     // asynchronous result copies (stc_synthesize_packed_async): a third stream carries the device->host copy of the waveform
     // while the main stream already runs the next call; two alternating device result buffers and staging halves
     cudaStream_t stream_copy = nullptr;
+    // Request streams (stc_synthesize_packed_async), env STC_OVERLAP: uploads + duration predictor of call k+1 run on stream_f
+    // with their own workspace (arena_f) and the text encoder on stream2 WHILE the Euler loop / vocoder of call k still occupy the
+    // main stream; the stage-1 buffers (inputs, durations, text_emb) of odd calls live in persist_alt, so that call k's stage 2 and
+    // call k+1's stage 1 never share memory. The host's wait for the durations of call k+1 then ends while call k is still running.
+    cudaStream_t stream_f = nullptr;
+    bool overlap = true;
     cudaEvent_t ev_out = nullptr, copy_done[2] = {nullptr, nullptr};
     float* outbuf[2] = {nullptr, nullptr}; size_t outcap[2] = {0, 0};
     int slot = 0; bool async_pending = false;
@@ -108,6 +114,7 @@ struct Handle {
     Arena arena;       // workspace: reset per stage
     Arena arena2;      // workspace of whatever runs on stream2 (swapped in for the duration of that stage)
     Arena persist;     // buffers that survive from stage 1 (DP/TE) into stage 2 (VE loop + vocoder)
+    Arena arena_f, persist_alt;        // see stream_f
     bool dry = false;          // no launches / copies (workspace measuring pass, or re-staging before a graph replay)
     bool restage = false;      // dry, but offset arrays are still written into their pinned staging slots
     bool capturing = false;    // launches go into a stream capture; host->device copies of caller memory are deferred
@@ -315,6 +322,7 @@ Handle::~Handle() {
     for (auto& e : copy_done) if (e) cudaEventDestroy(e);
     for (auto& p : outbuf) if (p) cudaFree(p);
     if (stream_copy) cudaStreamDestroy(stream_copy);
+    if (stream_f) cudaStreamDestroy(stream_f);
     if (ev_te) cudaEventDestroy(ev_te);
     for (auto& e : ev_voc) if (e) cudaEventDestroy(e);
 }
@@ -323,6 +331,8 @@ void Handle::wait_async() {
     if (!async_pending) return;
     STC_CUDA(cudaStreamSynchronize(stream_copy));
     STC_CUDA(cudaStreamSynchronize(stream));
+    if (stream_f) STC_CUDA(cudaStreamSynchronize(stream_f));
+    if (stream2) STC_CUDA(cudaStreamSynchronize(stream2));
     async_pending = false;
     check_launch("asynchronous synthesis");
 }
@@ -1522,9 +1532,19 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
         { const char* e = getenv("STC_DW_CHAIN"); hd->dw_chain = e && e[0] == '1'; }
         { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
-        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
-        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
-        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
+        {
+            // env STC_PRIO=1: the main stream (Euler loop + vocoder) gets the highest priority, the stage-1 streams the lowest, so that
+            // in a request stream the next call's duration predictor / text encoder only fill what the current call leaves free
+            int lo = 0, hi = 0;
+            STC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const char* e = getenv("STC_PRIO");
+            const bool prio = e && e[0] == '1';
+            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream, cudaStreamNonBlocking, prio ? hi : 0));
+            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream2, cudaStreamNonBlocking, prio ? lo : 0));
+            STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
+            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream_f, cudaStreamNonBlocking, prio ? lo : 0));
+        }
+        { const char* e = getenv("STC_OVERLAP"); hd->overlap = !(e && e[0] == '0'); }
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_out, cudaEventDisableTiming));
         for (auto& e : hd->copy_done) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
@@ -1806,6 +1826,14 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             h->h_stage_lim = slot ? h->h_stage_cap : h->h_stage_cap / 2;
             mode |= 16 | (slot << 5);                  // graphs bake the staging / result addresses: one set per slot
         }
+        const bool ovl = async_copy && h->overlap && h->stream_f;
+        // odd calls of a request stream keep their stage-1 buffers in the second persistent arena (swapped back when the call returns)
+        struct PersistSwap {
+            Handle* h; bool on;
+            PersistSwap(Handle* hh, bool o) : h(hh), on(o) { if (on) { h->persist.swap(h->persist_alt); h->persist.reset(); } }
+            ~PersistSwap() { if (on) h->persist.swap(h->persist_alt); }
+        } persist_swap(h, ovl && slot == 1);
+        if (ovl) mode |= 128;                          // graphs of the overlapped form bake other addresses than the serial form's
         if (B <= 0 || T <= 0 || total_step <= 0 || !(speed > 0.f) || !text_ids || !text_mask || !style_ttl || !style_dp || !wav_out)
             throw StcError(STC_ERR_INVALID, "stc_synthesize: bad argument");
         const stc_config& c = h->cfg;
@@ -1869,8 +1897,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             h->run_dp(d_ids, d_sdp, text_seq(d_tmask, false), T, d_dur);
             STC_LAUNCH(h, dur_post_kernel, cdiv(B, 128), 128, 0, d_dur, d_wavlen, B, speed, c.sample_rate);
             if (!h->dry) {
-                STC_CUDA(cudaMemcpyAsync(h->h_dur, d_dur, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
-                STC_CUDA(cudaMemcpyAsync(h->h_wavlen, d_wavlen, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+                // (h->stream: the main stream, or stream_f when this stage runs ahead of the previous call's stage 2)
+                STC_CUDA(cudaMemcpyAsync(h->h_dur, d_dur, sizeof(float) * B, cudaMemcpyDeviceToHost, h->stream));
+                STC_CUDA(cudaMemcpyAsync(h->h_wavlen, d_wavlen, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, h->stream));
             }
         };
         auto stage1b = [&]() {
@@ -1881,9 +1910,18 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         if (h->profile) cudaEventRecord(h->ev[0], st);
         // duration predictor on the main stream (behind the input uploads), text encoder concurrently on stream2 with its own
         // workspace: the two are independent (cpp/helper.cpp:512-556 runs them back to back) and DP alone leaves the GPU idle
-        h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in);
-        if (h->profile) cudaEventRecord(h->ev[1], st);
-        cudaEventRecord(h->ev[6], st);
+        if (ovl) {
+            std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f);
+            try { h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in); }
+            catch (...) { std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f); throw; }
+            cudaEventRecord(h->ev[6], h->stream);
+            std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f);
+            STC_CUDA(cudaStreamWaitEvent(st, h->ev[6], 0));           // stage 2 reads the durations / wav lengths on the device
+        } else {
+            h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in);
+            if (h->profile) cudaEventRecord(h->ev[1], st);
+            cudaEventRecord(h->ev[6], st);
+        }
         {
             STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);

@@ -446,6 +446,15 @@ def test_asynchronous_request_stream_equals_synchronous_calls(rig):
         np.testing.assert_array_equal(w["wav_lengths"], g["wav_lengths"])
         for a, b in zip(w["wavs"], g["wavs"]):
             np.testing.assert_array_equal(a, b)
+    # a longer stream of graph REPLAYS: stage 1 (duration predictor, text encoder) of call k+1 runs under stage 2 of call k on
+    # its own streams and arenas (STC_OVERLAP) — every call must still equal its synchronous result
+    for rep in range(2):
+        got = [eng.synthesize_packed(*jobs[k % 3], 2, 1.05, seed=40 + k % 3, pinned=f"s{k}", wait=False) for k in range(9)]
+        eng.wait()
+        for k, g in enumerate(got):
+            np.testing.assert_array_equal(want[k % 3]["duration"], g["duration"])
+            for a, b in zip(want[k % 3]["wavs"], g["wavs"]):
+                np.testing.assert_array_equal(a, b)
     # a synchronous call after asynchronous ones drains them first
     g2 = eng.synthesize_packed(*jobs[0], 2, 1.05, seed=40, pinned="t0", wait=False)
     s2 = eng.synthesize_packed(*jobs[1], 2, 1.05, seed=41)
