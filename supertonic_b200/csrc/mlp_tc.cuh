@@ -747,6 +747,10 @@ convnext_mlp_ts_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
 //   add_vec : x <- (x + add_vec) * mask           (time conditioning after a ConvNeXt block, cpp-side: vector_estimator graph)
 //   out     : the next layer's tensor-core operand — LayerNorm(x) (pre-LN of an attention layer; ln_g / ln_b) or x itself
 //             (ln_g == null; input of an output projection) as split-bf16
+// WIDE (the thin forms: 8 or 16 hidden slices, small batches): the partial loads of up to eight slices are in flight together —
+// those launches wait for L2 round trips, not for bandwidth (batch-1 latency 5.22 -> 4.96 ms); with four slices and 4 736 rows the
+// extra registers cost occupancy instead (10.40 -> 10.86 ms/step), so the two-deep loop stays there.
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
                   const float* __restrict__ mask, float* __restrict__ x, int M, const float* __restrict__ add_vec,
@@ -763,10 +767,26 @@ mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const fl
         const float4 a0 = *reinterpret_cast<const float4*>(partial + i), a1 = *reinterpret_cast<const float4*>(partial + i + 4);
         y[0] = a0.x; y[1] = a0.y; y[2] = a0.z; y[3] = a0.w; y[4] = a1.x; y[5] = a1.y; y[6] = a1.z; y[7] = a1.w;
     }
+    if constexpr (!WIDE) {
 #pragma unroll 4
-    for (int s = 1; s < nslice; ++s) {
-        const float4 v0 = *reinterpret_cast<const float4*>(partial + s * slice + i), v1 = *reinterpret_cast<const float4*>(partial + s * slice + i + 4);
-        y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x; y[5] += v1.y; y[6] += v1.z; y[7] += v1.w;
+        for (int s = 1; s < nslice; ++s) {
+            const float4 v0 = *reinterpret_cast<const float4*>(partial + s * slice + i), v1 = *reinterpret_cast<const float4*>(partial + s * slice + i + 4);
+            y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x; y[5] += v1.y; y[6] += v1.z; y[7] += v1.w;
+        }
+    } else
+    for (int s0 = 1; s0 < nslice; s0 += 8) {           // eight slices' loads in flight at a time, summed in slice order
+        float4 q0[8], q1[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s0 + s < nslice) {
+                q0[s] = *reinterpret_cast<const float4*>(partial + (s0 + s) * slice + i);
+                q1[s] = *reinterpret_cast<const float4*>(partial + (s0 + s) * slice + i + 4);
+            }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s0 + s < nslice) {
+                y[0] += q0[s].x; y[1] += q0[s].y; y[2] += q0[s].z; y[3] += q0[s].w; y[4] += q1[s].x; y[5] += q1[s].y; y[6] += q1[s].z; y[7] += q1[s].w;
+            }
     }
     const float mk = mask ? __ldg(mask + row) : 1.f;
     float bb[8], gg[8], rr[8];
@@ -808,6 +828,7 @@ mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const fl
 
 // The plain reduce (no post-ops): one float4 per thread — twice the threads of the row-wise kernel above and ~3 us faster
 // (4.2 vs 7.0 us at 4 736 rows, profiles/r1w_mlp_ncu_full_summary.txt), so blocks with nothing folded in keep this form.
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
                   const float* __restrict__ mask, float* __restrict__ x, int M, int nslice) {
@@ -815,11 +836,22 @@ mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* 
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= (size_t)M * C) return;
     const int row = (int)(i / C), col = (int)(i % C);
-    float4 acc = *reinterpret_cast<const float4*>(partial + i);
+    float4 acc;
+    if constexpr (WIDE) {
+        // every partial's load is in flight before the first add (one L2 round trip for up to 16 hidden slices), summed in slice order
+        float4 pv[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) if (s < nslice) pv[s] = *reinterpret_cast<const float4*>(partial + s * slice + i);
+        acc = pv[0];
+#pragma unroll
+        for (int s = 1; s < 16; ++s) if (s < nslice) { acc.x += pv[s].x; acc.y += pv[s].y; acc.z += pv[s].z; acc.w += pv[s].w; }
+    } else {
+        acc = *reinterpret_cast<const float4*>(partial + i);
 #pragma unroll 4
-    for (int s = 1; s < nslice; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(partial + s * slice + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int s = 1; s < nslice; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(partial + s * slice + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
     const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + col)), g = __ldg(reinterpret_cast<const float4*>(gamma + col));
     const float4 r = *reinterpret_cast<const float4*>(x + i);

@@ -958,11 +958,11 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
                            (const float*)p.x, (const float*)nd.dw_wt, (const float*)nd.dw_b, (const float*)nd.ln_g, (const float*)nd.ln_b,
                            OutSplit{post->out->hi, post->out->lo}, rows, seq->off, seq->B, nd.dil, nd.pad_left, 1e-6f, RT, rd);
             } else if (post)
-                launch_pdl(this, mlp::mlp_reduce_post_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
+                launch_pdl(this, nslice > 4 ? mlp::mlp_reduce_post_kernel<true> : mlp::mlp_reduce_post_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
                            (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
                            post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr, nslice);
             else
-                launch_pdl(this, mlp::mlp_reduce_kernel, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
+                launch_pdl(this, nslice > 4 ? mlp::mlp_reduce_kernel<true> : mlp::mlp_reduce_kernel<false>, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
                            (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, nslice);
             ++launches;
         }
