@@ -70,6 +70,8 @@ STC_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
+// kF16: single-pass fp16 operands (gemm_tc.cuh): a stage holds 128 K-elements, 8 MMAs instead of 24 per 128 K-elements.
+template <bool kF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -88,7 +90,8 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
-    const int num_kb = (p.K + BK - 1) / BK;
+    constexpr int KSTAGE = kF16 ? 2 * BK : BK;
+    const int num_kb = (p.K + KSTAGE - 1) / KSTAGE;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_pairs = ((p.M + BM - 1) / BM + 1) / 2;
     const int num_ct = m_pairs * n_tiles;
@@ -121,8 +124,20 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     mbar_wait(empty_bar(s), ph ^ 1);                         // the pair's MMAs on this stage have retired
                     if (p.trace && blockIdx.x == 0 && kbc < 48) p.trace[64 + kbc] = clock64();
                     const uint32_t st = smem_base + s * STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
                     const uint32_t fb = mapa_rank(full_bar(s), 0);
+                    if constexpr (kF16) {
+                        const int k0 = kb * KSTAGE;
+                        const bool two = k0 + BK < p.K;
+                        if (rank == 0) mbar_expect_tx(full_bar(s), two ? 2 * STAGE_BYTES : STAGE_BYTES);
+                        tma_load_2d_2sm(st, &map_a_hi, fb, k0, m0);
+                        tma_load_2d_2sm(st + 2 * A_BYTES, &map_w_hi, fb, k0, n0);
+                        if (two) {
+                            tma_load_2d_2sm(st + A_BYTES, &map_a_hi, fb, k0 + BK, m0);
+                            tma_load_2d_2sm(st + 2 * A_BYTES + W_BYTES, &map_w_hi, fb, k0 + BK, n0);
+                        }
+                        continue;
+                    }
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
                     tma_load_2d_2sm(st, &map_a_hi, fb, kb * BK, m0);
                     tma_load_2d_2sm(st + A_BYTES, &map_a_lo, fb, kb * BK, m0);
                     tma_load_2d_2sm(st + 2 * A_BYTES, &map_w_hi, fb, kb * BK, n0);
@@ -133,7 +148,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
         if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+            constexpr uint32_t idesc = kF16 ? make_idesc_f16(2 * BM, BN) : make_idesc_bf16(2 * BM, BN);
             uint32_t kbc = 0, it = 0;
             for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
                 const uint32_t ab = it & 1, aph = (it >> 1) & 1;
@@ -151,12 +166,27 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         const uint32_t st = smem_base + s * STAGE_BYTES;
                         const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_BYTES);
                         const uint64_t w_hi = make_smem_desc(st + 2 * A_BYTES), w_lo = make_smem_desc(st + 2 * A_BYTES + W_BYTES);
+                        if constexpr (kF16) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                umma2_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                            }
+                            if (kb * KSTAGE + BK < p.K) {
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k) {
+                                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                    umma2_bf16(tmem_d, a_lo + adv, w_lo + adv, idesc, 1);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
                             umma2_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
                             umma2_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
                             umma2_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                        }
                         }
                         umma2_commit(empty_bar(s));
                         if (kb == num_kb - 1) umma2_commit(tfull_bar(ab));
@@ -214,7 +244,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                             v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
                         }
                         if (p.ep.mask) { v.x *= mk[i]; v.y *= mk[i]; v.z *= mk[i]; v.w *= mk[i]; }
-                        if (p.split) {
+                        if (p.split && !p.out_lo) {
+                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+                        } else if (p.split) {
                             uint2 hi, lo;
                             split_pair(v.x, v.y, hi.x, lo.x); split_pair(v.z, v.w, hi.y, lo.y);
                             *reinterpret_cast<uint2*>(p.out_hi + o) = hi;

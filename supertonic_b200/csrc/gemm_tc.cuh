@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -153,6 +154,9 @@ STC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {           // a = b = F16 (format 0)
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {          // a = b = TF32 (format 2)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -229,7 +233,10 @@ struct TileIter {
 // kTf32: single-pass TF32 arithmetic for the vocoder (DESIGN.md "precision"): map_a_hi / map_w_hi describe fp32 [rows, K]
 // operands (box 32 elements = one 128-byte swizzled row); a stage still holds 64 K-elements — K sub-block 0 where the bf16
 // hi halves go, sub-block 1 where the lo halves go — and issues 8 MMAs (2 sub-blocks x 4 K-slices of 8) instead of 12.
-template <int BN, bool kRope = false, bool kTf32 = false>
+// kF16: single-pass fp16 arithmetic for the vocoder (the default there, DESIGN.md "precision"): map_a_hi / map_w_hi describe fp16
+// [rows, K] operands; a stage holds 128 K-elements — K sub-block 0 in the slots of the bf16 hi halves, sub-block 1 in the slots of the
+// lo halves — and issues 8 MMAs per 128 K-elements instead of 24 (a sub-block that lies wholly beyond K is neither loaded nor issued).
+template <int BN, bool kRope = false, bool kTf32 = false, bool kF16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -250,7 +257,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cm = p.cm, cn = p.cn, csize = cm * cn;
     const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
-    const int num_kb = (p.K + BK - 1) / BK;
+    constexpr int KSTAGE = kF16 ? 2 * BK : BK;                                  // K-elements per stage
+    const int num_kb = (p.K + KSTAGE - 1) / KSTAGE;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.M + BM - 1) / BM;
     TileIter ti{(n_tiles + cn - 1) / cn, cm, cn, crank / cn, crank % cn};
@@ -291,6 +299,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const uint32_t ph = (kbc / T::STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);                         // freed by every CTA that receives these slices
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
+                    if constexpr (kF16) {
+                        const int k0 = kb * KSTAGE;
+                        const bool two = k0 + BK < p.K;
+                        mbar_expect_tx(full_bar(s), two ? T::STAGE_BYTES : T::STAGE_BYTES / 2);
+                        tma_load_2d(st, &map_a_hi, full_bar(s), k0, m0);
+                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), k0, n0);
+                        if (two) {
+                            tma_load_2d(st + T::A_BYTES, &map_a_hi, full_bar(s), k0 + BK, m0);
+                            tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_hi, full_bar(s), k0 + BK, n0);
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(s), T::STAGE_BYTES);             // own slices + the peers' multicasts
                     if constexpr (kTf32) {
                         tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
@@ -318,7 +338,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = kTf32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = kF16 ? make_idesc_f16(BM, BN) : kTf32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
         const uint16_t free_mask = row_mask | col_mask;
         uint32_t kbc = 0, it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
@@ -335,7 +355,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
                     const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + T::A_BYTES);
                     const uint64_t w_hi = make_smem_desc(st + 2 * T::A_BYTES), w_lo = make_smem_desc(st + 2 * T::A_BYTES + T::W_BYTES);
-                    if constexpr (kTf32) {
+                    if constexpr (kF16) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        }
+                        if (kb * KSTAGE + BK < p.K) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                umma_bf16(tmem_d, a_lo + adv, w_lo + adv, idesc, 1);   // K sub-block 1 (the "lo" slots)
+                            }
+                        }
+                    } else if constexpr (kTf32) {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B = 8 fp32 per K-slice
@@ -428,7 +461,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
                         }
                         if (p.ep.mask) { v.x *= mk[i]; v.y *= mk[i]; v.z *= mk[i]; v.w *= mk[i]; }
-                        if (p.split) {
+                        if (p.split && !p.out_lo) {             // single fp16 operand of the next GEMM
+                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+                        } else if (p.split) {
                             uint2 hi, lo;
                             split_pair(v.x, v.y, hi.x, lo.x); split_pair(v.z, v.w, hi.y, lo.y);
                             *reinterpret_cast<uint2*>(p.out_hi + o) = hi;

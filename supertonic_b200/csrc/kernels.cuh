@@ -83,9 +83,15 @@ template <typename T> struct OutPlain {
         p[i] = v;
     }
 };
+// fp32 x2 -> packed fp16x2 (first argument in the lower half), round to nearest, saturating at +-65504: the single-pass fp16
+// operand form of the vocoder GEMMs (DESIGN.md "precision"; `lo == nullptr` in OutSplit / Act selects it, `hi` then holds fp16 bits)
+STC_DEVINL uint32_t pack_f16x2(float a, float b) {
+    uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
 struct OutSplit {
     __nv_bfloat16* hi; __nv_bfloat16* lo;
     STC_DEVINL void store(size_t i, float v) const {
+        if (!lo) { reinterpret_cast<uint16_t*>(hi)[i] = (uint16_t)(pack_f16x2(v, 0.f) & 0xffffu); return; }
         __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -193,6 +199,16 @@ STC_DEVINL void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
 }
 template <int CPL> STC_DEVINL void store_row_vec(const OutSplit& o, size_t i, const float (&y)[CPL]) {
     uint32_t hi[CPL / 2], lo[CPL / 2];
+    if (!o.lo) {                // single fp16 operand
+#pragma unroll
+        for (int j = 0; j < CPL / 2; ++j) hi[j] = pack_f16x2(y[2 * j], y[2 * j + 1]);
+        if constexpr (CPL == 4) *reinterpret_cast<uint2*>(o.hi + i) = make_uint2(hi[0], hi[1]);
+        else {
+#pragma unroll
+            for (int j = 0; j < CPL / 8; ++j) *reinterpret_cast<uint4*>(o.hi + i + 8 * j) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < CPL / 2; ++j) split2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
     if constexpr (CPL == 4) {

@@ -180,7 +180,8 @@ struct Handle {
     template <typename T> T* ws(size_t n) { return static_cast<T*>(arena.alloc(n * sizeof(T))); }
     bool tc_mode() const { return precision == STC_PREC_BF16X3; }
     Act ws_act_f32(size_t n) { Act a; a.f = ws<float>(n); return a; }       // operand of a kind::tf32 GEMM (or of the CUDA-core path)
-    Act ws_act_for(const Linear& w, size_t n) { return w.w_nk ? ws_act_f32(n) : ws_act(n); }
+    Act ws_act_f16(size_t n) { Act a; a.hi = ws<__nv_bfloat16>(n); return a; }   // single fp16 operand (hi holds fp16 bits, lo stays null)
+    Act ws_act_for(const Linear& w, size_t n) { return w.w_nk ? ws_act_f32(n) : w.f16 ? ws_act_f16(n) : ws_act(n); }
     Act ws_act(size_t n) {
         Act a;
         if (tc_mode()) { a.hi = ws<__nv_bfloat16>(n); a.lo = ws<__nv_bfloat16>(n); } else a.f = ws<float>(n);
@@ -216,6 +217,7 @@ struct Handle {
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
     bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
+    bool voc_f16 = true;              // vocoder GEMMs single-pass fp16 (default; env STC_VOC=bf16x3 keeps the split-bf16 form there too)
     bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
                                       // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
@@ -448,6 +450,19 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
         if (K % 4) throw StcError(STC_ERR_UNSUPPORTED, "tf32 GEMM needs K % 4 == 0, got " + std::to_string(K));
         if (N % 4) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs N % 4 == 0, got " + std::to_string(N));
         l.has_maps = true;
+    } else if (tc == 3) {   // single fp16 operand: [N,K] K-major, round to nearest, saturating
+        std::vector<uint16_t> hf((size_t)N * K);
+        for (int k = 0; k < K; ++k)
+            for (int n = 0; n < N; ++n) {
+                float v = std::min(65504.f, std::max(-65504.f, w_kn[(size_t)k * N + n]));
+                __half hv = __float2half_rn(v);
+                memcpy(&hf[(size_t)n * K + k], &hv, 2);
+            }
+        STC_CUDA(cudaMalloc((void**)&l.w_hi, hf.size() * 2)); owned.push_back(l.w_hi);
+        STC_CUDA(cudaMemcpy(l.w_hi, hf.data(), hf.size() * 2, cudaMemcpyHostToDevice));
+        if (K % 8) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs K % 8 == 0, got " + std::to_string(K));
+        if (N % 4) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs N % 4 == 0, got " + std::to_string(N));
+        l.f16 = true; l.has_maps = true;
     } else if (tc) {
         std::vector<uint16_t> hi((size_t)N * K), lo((size_t)N * K);
         for (int k = 0; k < K; ++k)
@@ -641,7 +656,7 @@ void Handle::load(const std::string& onnx_dir) {
     {
         OnnxFile f = load_onnx(onnx_dir + "/vocoder.onnx");
         voc_arch = arch_of(f, "vocoder.onnx");
-        load_net(f, voc_arch, voc, tc ? (voc_tf32 ? 2 : 1) : 0);
+        load_net(f, voc_arch, voc, tc ? (voc_tf32 ? 2 : voc_f16 ? 3 : 1) : 0);
         voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
         voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
     }
@@ -776,6 +791,8 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
     const bool tf32 = w.w_nk != nullptr;          // vocoder in tf32 mode: fp32 operands (a.f, w.w_nk), single-pass kind::tf32
     if (tf32 && (!a.f || ep.rope_freqs)) throw StcError(STC_ERR_INVALID, "tf32 linear needs an fp32 activation operand");
+    const bool f16 = w.f16;                       // vocoder in f16 mode: single fp16 operands (a.hi, w.w_hi; no lo halves)
+    if (!tf32 && (!a.hi || (a.lo == nullptr) != f16 || (f16 && ep.rope_freqs))) throw StcError(STC_ERR_INVALID, "GEMM operand form does not match the weights");
     if (out_f32) { p.out_f32 = out_f32; p.split = 0; }
     else if (!out_act->hi) { p.out_f32 = out_act->f; p.split = 0; p.round_tf32 = 1; }     // fp32 operand of the next tf32 GEMM
     else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
@@ -784,12 +801,13 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
     p.cm = c.cm; p.cn = c.cn;
     const int csize = c.cm * c.cn;
+    if (f16) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
     if (c.bn == 512 && (tf32 || ep.rope_freqs)) c = GemmCfg{256, 1, 1};       // variants the two-SM kernel does not carry
     if (c.bn == 512) {          // two-SM form (gemm2_tc.cuh): 256 x 256 tiles computed by CTA pairs
         if (w.N % 4) throw StcError(STC_ERR_INVALID, "two-SM GEMM: N % 4 != 0");
         p.cm = 2; p.cn = 1;
-        const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM), mal = tmap(a.lo, M, w.K, tc::BM);
-        const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, tc2::HALF), mwl = tmap(w.w_lo, w.N, w.K, tc2::HALF);
+        const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM), mal = f16 ? mah : tmap(a.lo, M, w.K, tc::BM);
+        const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, tc2::HALF), mwl = f16 ? mwh : tmap(w.w_lo, w.N, w.K, tc2::HALF);
         const int num_ct = cdiv(cdiv(M, tc::BM), 2) * cdiv(w.N, tc2::BN);
         const int clusters = std::max(1, std::min(num_ct, num_sms / 2));
         cudaLaunchConfig_t cfg{};
@@ -800,7 +818,8 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
         if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
         cfg.attrs = attr; cfg.numAttrs = na;
         kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel, mah, mal, mwh, mwl, p);
+        cudaError_t e = f16 ? cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<true>, mah, mal, mwh, mwl, p)
+                            : cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<false>, mah, mal, mwh, mwl, p);
         if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("two-SM tcgen05 GEMM launch: ") + cudaGetErrorString(e));
         ++launches;
         kprof_end();
@@ -808,9 +827,9 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     }
     if (tf32) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
     const CUtensorMap mah = tf32 ? tmap_tf32(a.f, M, w.K, tc::BM) : tmap(a.hi, M, w.K, tc::BM / c.cn);
-    const CUtensorMap mal = tf32 ? mah : tmap(a.lo, M, w.K, tc::BM / c.cn);
+    const CUtensorMap mal = (tf32 || f16) ? mah : tmap(a.lo, M, w.K, tc::BM / c.cn);
     const CUtensorMap mwh = tf32 ? tmap_tf32(w.w_nk, w.N, w.K, c.bn) : tmap(w.w_hi, w.N, w.K, c.bn / c.cm);
-    const CUtensorMap mwl = tf32 ? mwh : tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
+    const CUtensorMap mwl = (tf32 || f16) ? mwh : tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
     const int m_tiles = cdiv(M, tc::BM), n_tiles = cdiv(w.N, c.bn);
     const int cluster_tiles = cdiv(m_tiles, c.cm) * cdiv(n_tiles, c.cn);
     const int clusters = std::max(1, std::min(cluster_tiles, num_sms / csize));
@@ -823,7 +842,10 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     cfg.attrs = attr; cfg.numAttrs = na;
     kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
-    switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : c.bn) {
+    switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : f16 ? 2000 + c.bn : c.bn) {
+        case 2064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, false, true>, mah, mal, mwh, mwl, p); break;
+        case 2128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, false, true>, mah, mal, mwh, mwl, p); break;
+        case 2256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256, false, false, true>, mah, mal, mwh, mwl, p); break;
         case 1064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, true>, mah, mal, mwh, mwl, p); break;
         case 1128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, true>, mah, mal, mwh, mwl, p); break;
         case 1256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256, false, true>, mah, mal, mwh, mwl, p); break;
@@ -863,7 +885,7 @@ Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
 //               than the cluster form (4224 rows: 20.8 vs 23.7) -> the default.
 //   0 unfused : pw1 and pw2 as two GEMMs (other widths: vocoder C=512/H=2048, tiny config).
 int Handle::mlp_form(const ConvNeXt& c, int rows) const {
-    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi)) return 0;
+    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi && !c.pw1.f16 && !c.pw2.f16)) return 0;
     if (mlp_mode == 1) return 1;
     if (mlp_mode == 2) return 0;
     if (mlp_mode == 3) return 2;
@@ -1524,7 +1546,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : std::string(e) == "thin64" ? 6 : 0; }
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; }
+        { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; hd->voc_f16 = !e || std::string(e) == "f16"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_MLP_INREDUCE"); hd->mlp_inreduce = e && e[0] == '1'; }
@@ -1560,7 +1582,11 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
@@ -2137,6 +2163,11 @@ __global__ void debug_join_kernel(const __nv_bfloat16* __restrict__ hi, const __
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
+__global__ void debug_unhalf_kernel(const __half* __restrict__ h, float* __restrict__ out, size_t n) {
+    pdl_trigger(); pdl_wait();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __half2float(h[i]);
+}
 
 int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, int epilogue, int iters, float* ms_per_iter,
                    float* max_abs_err) {
@@ -2152,13 +2183,14 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         for (auto& v : wk) v = rnd() / std::sqrt((float)K) * 1.7f;
         for (auto& v : bias) v = rnd() * 0.1f;
         const bool tf32 = getenv("STC_DEBUG_TF32") != nullptr;          // time / check the kind::tf32 instantiation instead
-        Linear lin = h->make_linear_host(wk, bias, K, N, tf32 ? 2 : 1);
+        const bool f16 = !tf32 && getenv("STC_DEBUG_F16") != nullptr;   // ... or the single-pass fp16 one
+        Linear lin = h->make_linear_host(wk, bias, K, N, tf32 ? 2 : f16 ? 3 : 1);
         auto body = [&]() {
             h->arena.reset(); h->h_stage_off = 0;
             float* A = h->ws<float>((size_t)M * K); float* X = h->ws<float>((size_t)M * N); float* Xr = h->ws<float>((size_t)M * N);
             float* gamma = h->ws<float>(N); float* mask = h->ws<float>(M);
             float* out = h->ws<float>((size_t)M * N); float* ref = h->ws<float>((size_t)M * N); float* err = h->ws<float>(1);
-            Act a = tf32 ? h->ws_act_f32((size_t)M * K) : h->ws_act((size_t)M * K), o = tf32 ? h->ws_act_f32((size_t)M * N) : h->ws_act((size_t)M * N);
+            Act a = h->ws_act_for(lin, (size_t)M * K), o = h->ws_act_for(lin, (size_t)M * N);
             if (h->dry) { h->ws<long long>(128); return; }
             debug_fill_kernel<<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, (size_t)M * K, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(X, (size_t)M * N, 2, 1.0f);
@@ -2201,6 +2233,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             }
             one(true);
             if (epilogue == 1 && tf32) STC_CUDA(cudaMemcpyAsync(out, o.f, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
+            else if (epilogue == 1 && f16) debug_unhalf_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(reinterpret_cast<const __half*>(o.hi), out, (size_t)M * N);
             else if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
             debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(out, refp, (size_t)M * N, err);
             // timed: `iters` launches replayed from a CUDA graph (as in production), so the host is not in the loop

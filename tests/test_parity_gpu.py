@@ -7,8 +7,13 @@ Tolerances (written here, per north_star):
     the float32 durations themselves are compared bit-exact too (both sides evaluate DP in fp64 and round once);
   * normalised latents: max-abs <= 1e-3 (north-star bound); we additionally assert the 2e-4 we actually expect
     from split-bf16 (bf16x3) products with fp32 accumulation;
-  * waveform SNR >= 40 dB (north-star bound); expected >= 80 dB.
+  * waveform SNR >= 40 dB (north-star bound). The vocoder's GEMMs run single-pass fp16 (fp32 accumulation) by default —
+    >= 60 dB asserted (~70 dB measured); STC_VOC=bf16x3 keeps the split-bf16 form there too: >= 80 dB asserted (> 100 dB measured).
+    The Euler loop (latents) is split-bf16 in both modes.
 """
+import contextlib
+import os
+
 import numpy as np
 import pytest
 
@@ -17,7 +22,28 @@ from tests import _util as U
 pytestmark = pytest.mark.gpu
 
 LAT_TOL_NORTH_STAR, LAT_TOL_EXPECTED = 1e-3, 2e-4
-SNR_NORTH_STAR, SNR_EXPECTED = 40.0, 80.0
+SNR_NORTH_STAR, SNR_EXPECTED, SNR_EXACT = 40.0, 60.0, 80.0
+# an utterance alone vs inside a batch: latents agree to 1e-5, not bit for bit (the fused MLP picks its form by row count), so a
+# single-pass fp16 vocoder rounds a few operands the other way — same level as its distance to the oracle; the split-bf16 vocoder
+# keeps 90 dB
+SNR_INVARIANCE = {"default": 60.0, "bf16x3": 90.0}
+
+
+@contextlib.contextmanager
+def _engine(rig, voc):
+    """The module's default engine, or a second one created under STC_VOC=<voc>."""
+    if voc == "default":
+        yield rig["eng"]
+        return
+    os.environ["STC_VOC"] = voc
+    try:
+        eng = rig["capi"].Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_VOC"]
+    try:
+        yield eng
+    finally:
+        eng.close()
 
 
 @pytest.fixture(scope="module", params=["tiny", "full"])
@@ -100,6 +126,9 @@ def test_vocoder_parity(rig):
         got = rig["eng"].vocode(lat)
         assert got.shape == (n, L * 3072)
         assert U.snr_db(got, want) >= SNR_EXPECTED, U.snr_db(got, want)
+        with _engine(rig, "bf16x3") as exact:
+            snr_exact = U.snr_db(exact.vocode(lat), want)
+        assert snr_exact >= SNR_EXACT and snr_exact > U.snr_db(got, want), (snr_exact, U.snr_db(got, want))
 
 
 @pytest.mark.parametrize("steps", [2, 5])
@@ -155,23 +184,15 @@ def test_unchunked_text_longer_than_the_tensor_core_attention_limit(rig):
 
 def test_tf32_vocoder_mode_stays_inside_the_waveform_bound(rig):
     """STC_VOC=tf32 (opt-in): the vocoder's GEMMs run single-pass kind::tf32 on operands rounded to nearest. The waveform must stay
-    inside the north-star bound (>= 40 dB) with margin (>= 60 dB asserted; ~70 dB measured); the default mode keeps >= 80 dB."""
-    import os
-    os.environ["STC_VOC"] = "tf32"
-    try:
-        eng = rig["capi"].Engine(rig["root"] + "/onnx")
-    finally:
-        del os.environ["STC_VOC"]
-    try:
-        rng = np.random.default_rng(5)
-        lat = rng.standard_normal((2, 144, 70)).astype(np.float32)
-        want = rig["ora"].voc(dict(latent=lat))
-        got, exact = eng.vocode(lat), rig["eng"].vocode(lat)
-        snr_tf32, snr_exact = U.snr_db(got.reshape(-1), want.reshape(-1)), U.snr_db(exact.reshape(-1), want.reshape(-1))
-        assert snr_tf32 >= 60.0, snr_tf32
-        assert snr_exact >= SNR_EXPECTED and snr_exact > snr_tf32, (snr_exact, snr_tf32)
-    finally:
-        eng.close()
+    inside the north-star bound (>= 40 dB) with margin (>= 60 dB asserted; ~70 dB measured); the split-bf16 mode keeps >= 80 dB."""
+    rng = np.random.default_rng(5)
+    lat = rng.standard_normal((2, 144, 70)).astype(np.float32)
+    want = rig["ora"].voc(dict(latent=lat))
+    with _engine(rig, "tf32") as eng, _engine(rig, "bf16x3") as ex:
+        got, exact = eng.vocode(lat), ex.vocode(lat)
+    snr_tf32, snr_exact = U.snr_db(got.reshape(-1), want.reshape(-1)), U.snr_db(exact.reshape(-1), want.reshape(-1))
+    assert snr_tf32 >= 60.0, snr_tf32
+    assert snr_exact >= SNR_EXACT and snr_exact > snr_tf32, (snr_exact, snr_tf32)
 
 
 def test_noise_stride_and_capacity_retry(rig):
@@ -186,24 +207,30 @@ def test_noise_stride_and_capacity_retry(rig):
     assert out["L"] == L and U.snr_db(out["wav"].reshape(-1), wav_ref) >= SNR_EXPECTED
 
 
-def test_batch_composition_invariance(rig):
+@pytest.mark.parametrize("voc", ["default", "bf16x3"])
+def test_batch_composition_invariance(rig, voc):
     """An utterance synthesised alone equals the same utterance inside a ragged batch on its valid region
     (what makes length-bucketing parity-neutral)."""
+    with _engine(rig, voc) as eng:
+        _batch_composition_invariance(rig, eng, SNR_INVARIANCE[voc])
+
+
+def _batch_composition_invariance(rig, eng, snr_min):
     ids, mask, ttl, dp = _inputs(rig, 50, 4, 20, 110)
     rng = np.random.default_rng(9)
-    full = rig["eng"].synthesize(ids, mask, ttl, dp, 3, 1.05, noise=rng.standard_normal((4, 144, 400)).astype(np.float32),
+    full = eng.synthesize(ids, mask, ttl, dp, 3, 1.05, noise=rng.standard_normal((4, 144, 400)).astype(np.float32),
                                  want_latent=True)
     rng = np.random.default_rng(9)
     nz = rng.standard_normal((4, 144, 400)).astype(np.float32)
     for b in range(4):
         t = int(mask[b].sum())
-        one = rig["eng"].synthesize(ids[b:b + 1, :t], mask[b:b + 1, :, :t], ttl[b:b + 1], dp[b:b + 1], 3, 1.05,
-                                    noise=nz[b:b + 1], want_latent=True)
+        one = eng.synthesize(ids[b:b + 1, :t], mask[b:b + 1, :, :t], ttl[b:b + 1], dp[b:b + 1], 3, 1.05,
+                             noise=nz[b:b + 1], want_latent=True)
         np.testing.assert_array_equal(one["duration"], full["duration"][b:b + 1])
         n = int(one["wav_lengths"][0])
         Lb = one["L"]
         assert np.abs(one["latent"][0] - full["latent"][b, :, :Lb]).max() <= 1e-5
-        assert U.snr_db(one["wav"][0, :n], full["wav"][b, :n]) >= 90.0
+        assert U.snr_db(one["wav"][0, :n], full["wav"][b, :n]) >= snr_min
 
 
 def test_packed_synthesis_matches_oracle_per_utterance(rig):
@@ -350,14 +377,19 @@ def test_twenty_euler_steps_stay_inside_the_north_star_bound(rig):
     assert U.snr_db(out["wav"].reshape(-1), wav_ref) >= SNR_EXPECTED
 
 
-def test_speed_and_long_form_chunks(rig):
+@pytest.mark.parametrize("voc", ["default", "bf16x3"])
+def test_speed_and_long_form_chunks(rig, voc):
+    with _engine(rig, voc) as eng:
+        _speed_and_long_form_chunks(rig, eng, SNR_INVARIANCE[voc])
+
+
+def _speed_and_long_form_chunks(rig, eng, snr_min):
     """configs[3]: long-form text through chunkText at speed 1.05 — every chunk synthesised in ONE packed batch equals the same
     chunk synthesised alone (the reference runs them sequentially at batch 1, cpp/helper.cpp:703-716)."""
     from supertonic_b200 import tts as T
     text = " ".join(U.make_text(np.random.default_rng(i), 140) + "." for i in range(5))
     chunks = T.chunk_text(text, 300)
     assert len(chunks) >= 2
-    eng = rig["eng"]
     ids, mask = eng.text_to_ids(chunks, ["en"] * len(chunks))
     ttl, dp = U.styles(rig["root"], ["M1"] * len(chunks))
     nz = np.random.default_rng(3).standard_normal((len(chunks), 144, 400)).astype(np.float32)
@@ -368,7 +400,7 @@ def test_speed_and_long_form_chunks(rig):
         np.testing.assert_array_equal(one["duration"], packed["duration"][k:k + 1])
         n = int(one["wav_lengths"][0])
         assert len(packed["wavs"][k]) == n
-        assert U.snr_db(packed["wavs"][k], one["wav"][0, :n]) >= 90.0
+        assert U.snr_db(packed["wavs"][k], one["wav"][0, :n]) >= snr_min
 
 
 def test_chunked_vocoder_with_overlapped_copies_is_bit_identical(rig):
