@@ -66,8 +66,16 @@ STC_DEVINL void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
 STC_DEVINL void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// Hands a drained TMEM accumulator back to the leader's MMA warp. Relaxed: the tcgen05.ld reads it orders are complete
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync); the .release.cluster form compiles to MEMBAR.ALL.GPU and makes the warp
+// wait for every global store of its tile to be acknowledged before the MMAs of the tile after next may start (measured on the
+// fp16 pw1: the MMA warp idled ~8k of 11k cycles per tile on this barrier).
+STC_DEVINL void st_global_256(void* p, const uint32_t* v) {       // one full 32-byte sector per lane (sm_100: STG.256)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 STC_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
 // kF16: single-pass fp16 operands (gemm_tc.cuh): a stage holds 128 K-elements, 8 MMAs instead of 24 per 128 K-elements.
@@ -202,6 +210,8 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         float* stg = reinterpret_cast<float*>(smem_gen + EPI_OFF + (warp - 2) * STG_BYTES);
         const int sub = lane >> 2, cq = lane & 3;               // phase 2: 8 rows x 4 float4 per warp instruction
         const float* resid = static_cast<const float*>(p.ep.resid);
+        // fp16 operand out, bias + GELU only: the direct form below
+        const bool direct = kF16 && p.split && !p.out_lo && p.ep.gelu && p.ep.bias && !p.ep.scale && !p.ep.mask && !resid && p.N % 64 == 0 && p.ldo % 16 == 0;
         uint32_t it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
             const int m0 = ((ct / n_tiles) * 2 + rank) * BM + q * 32, n0 = (ct % n_tiles) * BN + part * COLS_PER_WARP;
@@ -212,11 +222,68 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 const int row = m0 + i * 8 + sub;
                 mk[i] = (p.ep.mask && row < p.M) ? __ldg(p.ep.mask + row) : 1.f;
             }
+            if (kF16 && direct) {
+                // this warp's 64 bias values -> its staging slot while the tile's MMAs still run (with 226 KB of shared memory in use
+                // there is no L1: a __ldg inside the loop is an L2 round trip on the epilogue's critical path)
+                __syncwarp();
+                stg[lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + lane) : 0.f;
+                stg[32 + lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + 32 + lane) : 0.f;
+                __syncwarp();
+            }
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
+            if (kF16 && direct) {
+                // bias -> GELU -> fp16 straight out of TMEM: lane = row, 32 consecutive columns = 64 contiguous bytes per lane and
+                // chunk (no shared-memory transpose: 31 -> ~20 issued instructions per element; this epilogue, not the MMAs,
+                // bounds the K = 512 tiles of the vocoder's pw1)
+                const int row = m0 + lane;
+                __nv_bfloat16* orow = p.out_hi + (size_t)row * p.ldo + n0;
+#pragma unroll 1
+                for (int c = 0; c < COLS_PER_WARP; c += 32) {
+                    uint32_t r[32], o[16];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + part * COLS_PER_WARP + c), r);
+                    if (c + 32 >= COLS_PER_WARP) {             // the accumulator is in registers: hand the buffer back before the math
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(ab), 0));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(stg + c + j);                     // broadcast read
+                        const float v0 = gelu_erf_mufu(__uint_as_float(r[j]) + b.x), v1 = gelu_erf_mufu(__uint_as_float(r[j + 1]) + b.y);
+                        const float v2 = gelu_erf_mufu(__uint_as_float(r[j + 2]) + b.z), v3 = gelu_erf_mufu(__uint_as_float(r[j + 3]) + b.w);
+                        o[j / 2] = pack_f16x2(v0, v1); o[j / 2 + 1] = pack_f16x2(v2, v3);
+                    }
+                    if (row < p.M && n0 + c < p.N) {
+                        st_global_256(orow + c, o);
+                        st_global_256(orow + c + 16, o + 8);
+                    }
+                }
+                continue;
+            }
+            // bias / layer-scale of chunk c + 1 and the residual rows of chunk c are requested before the TMEM load of chunk c: there is
+            // no L1 beside 226 KB of shared memory, every __ldg is an L2 round trip
+            float4 bias_n = make_float4(0.f, 0.f, 0.f, 0.f), scale_n = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (n0 + cq * 4 < p.N) {
+                if (p.ep.bias) bias_n = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n0 + cq * 4));
+                if (p.ep.scale) scale_n = __ldg(reinterpret_cast<const float4*>(p.ep.scale + n0 + cq * 4));
+            }
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP; c += EPI_CHUNK) {
                 uint32_t r[16];
+                const float4 bias = bias_n, scale = scale_n;
+                if (c + EPI_CHUNK < COLS_PER_WARP && n0 + c + EPI_CHUNK + cq * 4 < p.N) {
+                    if (p.ep.bias) bias_n = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n0 + c + EPI_CHUNK + cq * 4));
+                    if (p.ep.scale) scale_n = __ldg(reinterpret_cast<const float4*>(p.ep.scale + n0 + c + EPI_CHUNK + cq * 4));
+                }
+                float4 rs[4];
+                if (resid && n0 + c + cq * 4 < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = m0 + i * 8 + sub;
+                        if (row < p.M) rs[i] = *reinterpret_cast<const float4*>(resid + (size_t)row * p.ldo + n0 + c + cq * 4);
+                    }
+                }
                 __syncwarp();
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + part * COLS_PER_WARP + c), r);
                 // lane = row: its four 16-byte chunks go to slots j ^ ((row >> 1) & 3) — conflict-free for the row-wise writes
@@ -227,9 +294,6 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 __syncwarp();
                 const int col = n0 + c + cq * 4;
                 if (col < p.N) {
-                    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), scale = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (p.ep.bias) bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
-                    if (p.ep.scale) scale = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col));
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rl = i * 8 + sub, row = m0 + rl;
@@ -239,10 +303,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         if (p.ep.gelu) { v.x = gelu_erf_mufu(v.x); v.y = gelu_erf_mufu(v.y); v.z = gelu_erf_mufu(v.z); v.w = gelu_erf_mufu(v.w); }
                         if (p.ep.scale) { v.x *= scale.x; v.y *= scale.y; v.z *= scale.z; v.w *= scale.w; }
                         const size_t o = (size_t)row * p.ldo + col;
-                        if (resid) {
-                            const float4 s = *reinterpret_cast<const float4*>(resid + o);
-                            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-                        }
+                        if (resid) { v.x += rs[i].x; v.y += rs[i].y; v.z += rs[i].z; v.w += rs[i].w; }
                         if (p.ep.mask) { v.x *= mk[i]; v.y *= mk[i]; v.z *= mk[i]; v.w *= mk[i]; }
                         if (p.split && !p.out_lo) {
                             *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));

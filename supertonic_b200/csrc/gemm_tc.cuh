@@ -45,6 +45,8 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_CHUNK = 16;                  // accumulator columns moved TMEM -> smem -> global per step
 constexpr int EPI_PITCH = EPI_CHUNK + 4;       // floats per staged row: 16-byte aligned, conflict-free for v4 accesses
 constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+constexpr int EPI_BS = 256;                    // floats per warp: bias [0,128) and layer-scale [128,256) of the warp's columns
+constexpr int EPI_BS_BYTES = EPI_WARPS * EPI_BS * 4;
 
 template <int BN> struct Tile {
     static constexpr int A_BYTES = BM * BK * 2;
@@ -53,7 +55,9 @@ template <int BN> struct Tile {
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 6 ? 6 : (196608 / STAGE_BYTES);
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                       // mbarriers + TMEM slot
     static constexpr int EPI_OFF = BAR_OFF + 256;                              // epilogue staging
-    static constexpr int SMEM_BYTES = EPI_OFF + EPI_BYTES + 1024 /*align slack*/;
+    static constexpr int BS_OFF = EPI_OFF + EPI_BYTES;                          // per-warp bias / layer-scale slices
+    static constexpr int SMEM_BYTES = BS_OFF + EPI_BS_BYTES + 1024 /*align slack*/;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int TMEM_COLS = 2 * BN;        // two accumulator buffers (BN in {64,128,256} -> power of two)
 };
 
@@ -174,19 +178,20 @@ struct Params {
     long long* trace;               // debug (stc_debug_gemm, STC_GEMM_TRACE=1): clock64() stamps of block 0's producer / MMA warps
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with MUFU reciprocal / exp2: ~14 instructions against ~40 for
-// erff() + IEEE division. The GELU is then (x * (erf(x/sqrt2) + 1)) * 0.5 as in the graphs.
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with MUFU reciprocal / exp2 against ~40 instructions for erff() + IEEE
+// division. With z = |x|/sqrt2 and E = erf(z) in [0, 1], the graphs' (x * (erf(x/sqrt2) + 1)) * 0.5 is h + |h| * E, h = x/2 (erf is
+// odd): 14 instructions — the constants carry the 1/sqrt2 and log2(e) factors, the sign needs no copysign.
 STC_DEVINL float gelu_erf_mufu(float x) {
-    const float z = fabsf(x) * 0.70710678f;
-    float t; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float t; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678f, fabsf(x), 1.0f)));
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
-    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));
     const float erf_abs = fmaf(-poly, e, 1.0f);
-    return (x * (copysignf(erf_abs, x) + 1.0f)) * 0.5f;
+    const float h = 0.5f * x;
+    return fmaf(fabsf(h), erf_abs, h);
 }
 
 // v (fp32 x2) -> packed bf16x2 hi and lo with v ~= hi + lo
@@ -400,6 +405,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr int COLS_PER_WARP = BN / 2;
         float* stg = reinterpret_cast<float*>(smem_gen + T::EPI_OFF) + (warp - 2) * 32 * EPI_PITCH;
+        float* bs = reinterpret_cast<float*>(smem_gen + T::BS_OFF) + (warp - 2) * EPI_BS;
         const int sub = lane >> 2, cq = (lane & 3) * 4;         // phase 2: 8 rows x 4 float4 per warp instruction
         const float* resid = static_cast<const float*>(p.ep.resid);
         uint32_t it = 0;
@@ -421,11 +427,29 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     }
                 }
             }
+            // bias / layer-scale of this warp's columns -> shared memory while the tile's MMAs still run: with the operand ring in
+            // place the SM has no L1, and a __ldg inside the chunk loop is an L2 round trip on the epilogue's critical path
+            __syncwarp();
+#pragma unroll
+            for (int c = lane; c < COLS_PER_WARP; c += 32) {
+                const int col = n0 + c;
+                bs[c] = (p.ep.bias && col < p.N) ? __ldg(p.ep.bias + col) : 0.f;
+                bs[128 + c] = (p.ep.scale && col < p.N) ? __ldg(p.ep.scale + col) : 1.f;
+            }
+            __syncwarp();
             mbar_wait(tfull_bar(ab), aph);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP; c += EPI_CHUNK) {
                 uint32_t r[16];
+                float4 rs[4];                                   // residual rows of this chunk: in flight under the TMEM load + staging
+                if (resid && n0 + c + cq < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = m0 + i * 8 + sub;
+                        if (row < p.M) rs[i] = *reinterpret_cast<const float4*>(resid + (size_t)row * p.ldo + n0 + c + cq);
+                    }
+                }
                 __syncwarp();                                   // tcgen05.ld is .sync.aligned; staging of the previous chunk is consumed
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + half * COLS_PER_WARP + c), r);
 #pragma unroll
@@ -434,9 +458,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 __syncwarp();
                 const int col = n0 + c + cq;
                 if (col < p.N) {                                // N % 4 == 0 is checked on the host
-                    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), scale = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (p.ep.bias) bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
-                    if (p.ep.scale) scale = __ldg(reinterpret_cast<const float4*>(p.ep.scale + col));
+                    const float4 bias = *reinterpret_cast<const float4*>(bs + c + cq), scale = *reinterpret_cast<const float4*>(bs + 128 + c + cq);
                     float f0 = 0.f, f1 = 0.f;
                     if (kRope && p.ep.rope_freqs) {             // this float4 = rotary pairs i, i+1 of its head
                         const int i2 = (col % p.ep.rope_dh) >> 1;
@@ -456,10 +478,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         if (p.ep.gelu) { v.x = gelu_erf_mufu(v.x); v.y = gelu_erf_mufu(v.y); v.z = gelu_erf_mufu(v.z); v.w = gelu_erf_mufu(v.w); }
                         if (p.ep.scale) { v.x *= scale.x; v.y *= scale.y; v.z *= scale.z; v.w *= scale.w; }
                         const size_t o = (size_t)row * p.ldo + col;
-                        if (resid) {
-                            const float4 s = *reinterpret_cast<const float4*>(resid + o);
-                            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-                        }
+                        if (resid) { v.x += rs[i].x; v.y += rs[i].y; v.z += rs[i].z; v.w += rs[i].w; }
                         if (p.ep.mask) { v.x *= mk[i]; v.y *= mk[i]; v.z *= mk[i]; v.w *= mk[i]; }
                         if (p.split && !p.out_lo) {             // single fp16 operand of the next GEMM
                             *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));

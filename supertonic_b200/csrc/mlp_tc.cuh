@@ -30,7 +30,9 @@ constexpr int X_BYTES = 2 * (C / BK) * KBLK;      // 128 KB: a-tile (hi k-blocks
 constexpr int UNIT = 2 * KBLK;                    // 32 KB: 128 weight rows x 64 K, hi + lo
 constexpr int SLOTS = 3;
 constexpr int OFF_X = 0, OFF_RING = X_BYTES, OFF_BAR = OFF_RING + SLOTS * UNIT;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int OFF_B1 = OFF_BAR + 256;             // 1 KB: this CTA's slice of the pw1 bias (read by the GELU epilogue)
+constexpr int SMEM_BYTES = OFF_B1 + 1024 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int UNITS_PER_PHASE = (C / BK) * (HC / 128);     // 8
 constexpr int RECV_BYTES = BM * 64 * 4;           // 32 KB: one sender's partial for my 64 columns
 static_assert(3 * RECV_BYTES <= SLOTS * UNIT, "receive slots alias the weight ring");
@@ -249,6 +251,14 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
             if (lane == 0) mbar_arrive(bar_a);
         }
         // ===== epilogue 1: P = split(GELU(S + b1)) =====
+        // b1 slice -> shared memory while S is still being accumulated: with 226 KB of shared memory in use the SM has no L1, so a
+        // __ldg inside the loop below would be an L2 round trip (~0.5 us under load) on the CTA's serial chain, once per K block
+        float* b1s = reinterpret_cast<float*>(smem_gen + OFF_B1);
+        {
+            const int t = (int)threadIdx.x - 64;
+            if (t < HCt) b1s[t] = __ldg(p.b1 + crank * HCt + t);
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight epilogue warps only
+        }
         const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t prow_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
@@ -259,16 +269,18 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
             uint32_t v[32];
             __syncwarp();
             tmem_ld32(trow + j * BK + half * 32, v);
-            const float* b1 = p.b1 + crank * HCt + j * BK + half * 32;
+            const float* b1 = b1s + j * BK + half * 32;
             uint8_t* p_hi = smem_gen + OFF_X + j * KBLK + prow_off;
             uint8_t* p_lo = p_hi + (C / BK) * KBLK;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 uint32_t hi[4], lo[4];
+                const float4 ba = *reinterpret_cast<const float4*>(b1 + c8 * 8), bb = *reinterpret_cast<const float4*>(b1 + c8 * 8 + 4);   // broadcast
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const float e0 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t]) + __ldg(b1 + c8 * 8 + 2 * t));
-                    const float e1 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t + 1]) + __ldg(b1 + c8 * 8 + 2 * t + 1));
+                    const float e0 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t]) + bv[2 * t]);
+                    const float e1 = gelu_erf_mufu(__uint_as_float(v[c8 * 8 + 2 * t + 1]) + bv[2 * t + 1]);
                     split_pair(e0, e1, hi[t], lo[t]);
                 }
                 const int chunk = (half * 4 + c8) ^ (r & 7);

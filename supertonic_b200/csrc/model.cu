@@ -801,7 +801,11 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
     p.cm = c.cm; p.cn = c.cn;
     const int csize = c.cm * c.cn;
-    if (f16) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
+    if (f16) {
+        c.cm = c.cn = 1; p.cm = p.cn = 1;
+        // single-pass operands: the two-SM form wins at every K (tools/gemm_f16.py: conv_in, K = 168, 32 -> 22 us)
+        if (!force_cfg.bn && gemm2 && w.N % 256 == 0 && w.K >= 128 && (int)cdiv(M, 2 * tc::BM) * (w.N / 256) >= num_sms) c = GemmCfg{512, 2, 1};
+    }
     if (c.bn == 512 && (tf32 || ep.rope_freqs)) c = GemmCfg{256, 1, 1};       // variants the two-SM kernel does not carry
     if (c.bn == 512) {          // two-SM form (gemm2_tc.cuh): 256 x 256 tiles computed by CTA pairs
         if (w.N % 4) throw StcError(STC_ERR_INVALID, "two-SM GEMM: N % 4 != 0");
