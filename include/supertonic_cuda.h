@@ -188,7 +188,8 @@ void* stc_stream(stc_handle* h);
  * {dp, te, ve_total, vocoder, whole}. Requires stc_set_profile(h, >=1) (adds event records). */
 int stc_set_profile(stc_handle* h, int level);   /* 0 off, 1 stage events, 2 + per-kernel events (bench roofline leg) */
 /* Per-kernel-class totals of the most recent stc_synthesize* call at profile level 2.
- * cls: 0 = tcgen05 GEMM, 1 = depthwise-conv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (with its reduce kernel).
+ * cls: 0 = tcgen05 GEMM (split-bf16 operands), 1 = depthwise-conv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (with its
+ * reduce kernel), 4 = tcgen05 GEMM with single-pass fp16 operands (the vocoder projections).
  * out = {milliseconds (CUDA events around each launch), algorithmic FLOPs, algorithmic bytes, launches}. */
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]);
 int stc_last_stage_ms(const stc_handle* h, float out[5]);

@@ -40,6 +40,19 @@ constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
 constexpr int TMEM_COLS = 512;                         // S: 5 x 64 columns, O: 64 columns at 320
 constexpr int O_COL = MAX_BLOCKS * KB;
 static_assert(4 * P_BYTES <= K_REGION, "P double buffer must fit in the K region");
+// Layout per maximum key-block count. MAXB = 1 (<= 64 keys: the 50-key style attentions) needs 80 KB of shared memory and 128
+// TMEM columns, so TWO CTAs share an SM and the ~200 (sequence, head, query tile) CTAs of a batch run in one wave instead of two.
+template <int MAXB> struct Lay {
+    static constexpr int K_REGION = MAXB == 1 ? 2 * P_BYTES : (2 * MAXB * KBLK_BYTES > 4 * P_BYTES ? 2 * MAXB * KBLK_BYTES : 4 * P_BYTES);
+    static constexpr int V_REGION = 2 * MAXB * KBLK_BYTES;
+    static constexpr int OFF_V = OFF_K + K_REGION;
+    static constexpr int OFF_BAR = OFF_V + V_REGION;
+    static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+    static constexpr int TMEM_COLS = MAXB == 1 ? 128 : 512;
+    static constexpr int O_COL = MAXB * KB;
+    static constexpr int CTAS_PER_SM = MAXB == 1 ? 2 : 1;
+};
+static_assert(Lay<MAX_BLOCKS>::SMEM_BYTES == SMEM_BYTES && Lay<MAX_BLOCKS>::O_COL == O_COL, "the 320-key layout is unchanged");
 
 struct Params {
     const int* qoff; const int* koff; const int* kcnt;       // packed row offsets [B+1]; valid key count or null
@@ -49,13 +62,16 @@ struct Params {
     int split;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MAXB>
+__global__ void __launch_bounds__(NUM_THREADS, Lay<MAXB>::CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
                     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
                     const Params p) {
     pdl_trigger(); pdl_wait();
     using namespace tc;
+    using L = Lay<MAXB>;
+    constexpr int OFF_V = L::OFF_V, OFF_BAR = L::OFF_BAR, TMEM_COLS = L::TMEM_COLS, O_COL = L::O_COL, MAX_BLOCKS = MAXB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));

@@ -74,6 +74,8 @@ STC_DEVINL void st_global_256(void* p, const uint32_t* v) {       // one full 32
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+// (The same lane = row form for the fp32 + residual epilogue of pw2 — 256-bit loads of the residual row, 256-bit stores — was
+// measured slower than the staged one: vocoder 1.82 -> 1.91 ms; a warp-wide 32-byte access to 32 different rows costs 32 L2 requests.)
 STC_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }

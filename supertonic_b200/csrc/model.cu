@@ -129,7 +129,8 @@ struct Handle {
     bool force_simt_attn = false;     // env STC_ATTN=simt: keep the CUDA-core attention core (cross-check)
     int profile = 0;          // 0 off, 1 stage events, 2 + per-kernel events for the GEMM / dwconv+LN classes
     struct KProf { double ms = 0, flops = 0, bytes = 0; uint64_t n = 0; };
-    KProf kprof[4];           // 0 = tcgen05 GEMM, 1 = dwconv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (+ its reduce)
+    KProf kprof[5];           // 0 = tcgen05 GEMM (split-bf16), 1 = dwconv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (+ its reduce),
+                              // 4 = tcgen05 GEMM, single-pass fp16 operands (vocoder)
     struct Pending { int cls; cudaEvent_t a, b; double flops, bytes; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
@@ -217,6 +218,7 @@ struct Handle {
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
     bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
+    bool attn_small = true;           // env STC_ATTN_SMALL=0: the 50-key style attentions use the 320-key layout too (one CTA per SM)
     bool voc_f16 = true;              // vocoder GEMMs single-pass fp16 (default; env STC_VOC=bf16x3 keeps the split-bf16 form there too)
     bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
                                       // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
@@ -821,7 +823,7 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
         int na = 0;
         if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
         cfg.attrs = attr; cfg.numAttrs = na;
-        kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
+        kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
         cudaError_t e = f16 ? cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<true>, mah, mal, mwh, mwl, p)
                             : cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<false>, mah, mal, mwh, mwl, p);
         if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("two-SM tcgen05 GEMM launch: ") + cudaGetErrorString(e));
@@ -844,7 +846,7 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
     if (csize > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = csize; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
     cfg.attrs = attr; cfg.numAttrs = na;
-    kprof_begin(0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
+    kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
     switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : f16 ? 2000 + c.bn : c.bn) {
         case 2064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, false, true>, mah, mal, mwh, mwl, p); break;
@@ -1124,7 +1126,10 @@ void Handle::attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const 
         const CUtensorMap mkh = tmap(kv.k_hi, k.rows, a.C, attn::KB), mkl = tmap(kv.k_lo, k.rows, a.C, attn::KB);
         const CUtensorMap mvh = tmap(kv.vt_hi, vrows, kv.ldk, attn::DH), mvl = tmap(kv.vt_lo, vrows, kv.ldk, attn::DH);
         dim3 grid(cdiv(q.maxlen, attn::BQ), a.heads, q.B);
-        launch_pdl(this, attn::attention_tc_kernel, grid, dim3(attn::NUM_THREADS), (size_t)attn::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
+        if (k.maxlen <= attn::KB && attn_small)       // <= 64 keys (style attention): the two-CTAs-per-SM layout
+            launch_pdl(this, attn::attention_tc_kernel<1>, grid, dim3(attn::NUM_THREADS), (size_t)attn::Lay<1>::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
+        else
+            launch_pdl(this, attn::attention_tc_kernel<attn::MAX_BLOCKS>, grid, dim3(attn::NUM_THREADS), (size_t)attn::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
         ++launches;
     }
     kprof_end();
@@ -1550,6 +1555,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : std::string(e) == "thin64" ? 6 : 0; }
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
+        { const char* e = getenv("STC_ATTN_SMALL"); hd->attn_small = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; hd->voc_f16 = !e || std::string(e) == "f16"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
@@ -1594,7 +1600,8 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<attn::MAX_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Lay<1>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
@@ -1639,7 +1646,7 @@ int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID;
 void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
 int stc_set_profile(stc_handle* h, int level) { if (!h) return STC_ERR_INVALID; h->impl->profile = level; return STC_OK; }
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]) {
-    if (!h || !out || cls < 0 || cls > 3) return STC_ERR_INVALID;
+    if (!h || !out || cls < 0 || cls > 4) return STC_ERR_INVALID;
     const auto& k = h->impl->kprof[cls];
     out[0] = k.ms; out[1] = k.flops; out[2] = k.bytes; out[3] = (double)k.n;
     return STC_OK;
