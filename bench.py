@@ -346,6 +346,9 @@ def main():
                         "`frac_executed_mma` is the tensor-pipe load")
         roof[other] = tensor_line(other)
         roof["gemm_f16"] = tensor_line("gemm_f16", passes=1)
+        tpf = os.path.join(ROOT, "profiles", "gemm_f16_traffic.json")
+        roof["gemm_f16"]["traffic"] = json.load(open(tpf)).get("dram_bytes_per_launch") if os.path.exists(tpf) else None
+        roof["gemm_f16"]["traffic_source"] = "profiles/gemm_f16_traffic.json (pw1, one launch under ncu --set full)"
         roof["dwconv_ln"] = {"bound": "hbm", "achieved_gbs": prof["dwconv_ln"]["bytes"] / max(prof["dwconv_ln"]["ms"], 1e-9) / 1e6,
                              "peak_gbs": pk["hbm"], "launches": prof["dwconv_ln"]["launches"],
                              "share_of_step": prof["dwconv_ln"]["ms"] / max(stage["whole"], 1e-9)}
