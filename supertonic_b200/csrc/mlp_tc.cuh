@@ -74,7 +74,12 @@ STC_DEVINL void st_cluster_v4(uint32_t addr, float a, float b, float c, float d)
 // HCt: hidden units per CTA. 256 (CS = 4 CTAs per row tile) everywhere the SMs are full; 128 (the "thin" form, eight CTAs per row
 // tile, !kCluster only) when 8 x row tiles still fit one wave: a CTA's serial chain a-tile -> S -> GELU -> O halves (18 -> ~12 us
 // for a single row tile — the batch-1 latency path runs 172 of these per utterance).
-template <bool kCluster, int HCt = HC>
+// kWide (HCt = 256 only): the MMAs are N = 256 wide. A weight unit is then 256 rows x 64 K of ONE half — unit (kb, 0) the hi halves,
+// unit (kb, 1) the lo halves, same 32 KB and the same ring — and the hi unit feeds a_lo.w_hi and a_hi.w_hi, the lo unit a_hi.w_lo.
+// Why: an N = 128 MMA reads 8 KB of operands (4 KB of `a`, 4 KB of W) per 64 tensor cycles = 128 B/clk, all the shared-memory port
+// has, while TMA is filling the ring through the same port (traces: 1150-1500 cycles per unit against 768 of pure MMA time); an
+// N = 256 MMA reads 12 KB per 128 cycles = 96 B/clk.
+template <bool kCluster, int HCt = HC, bool kWide = false>
 STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo, const CUtensorMap& map_w1_hi,
                                   const CUtensorMap& map_w1_lo, const CUtensorMap& map_w2_hi, const CUtensorMap& map_w2_lo,
                                   const Params& p) {
@@ -95,6 +100,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 104);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(HCt == HC || ((HCt == HC_THIN || HCt == HC_THIN64) && !kCluster), "hidden slice per CTA");
+    static_assert(!kWide || (HCt == HC && !kCluster), "wide MMAs: the 256-unit split form");
     constexpr int CSt = H / HCt;
     constexpr int WR1 = HCt < 128 ? HCt : 128;                                    // weight rows of a phase-1 unit (= its MMA N)
     constexpr int U1 = (C / BK) * (HCt / WR1), U2 = (HCt / BK) * (C / 128);       // weight units of phase 1 / phase 2
@@ -133,7 +139,10 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                 mbar_expect_tx(full_bar(s), second ? UNIT : 2 * WR1 * BK * 2);
                 const int v = second ? u - U1 : u;
                 const int kb = (second || HCt == HC) ? v >> 1 : v, nh = (second || HCt == HC) ? v & 1 : 0;
-                if (!second) {                      // W1[hidden rows, C]: rows crank*HCt + nh*128, K block kb of C
+                if constexpr (kWide) {              // one half (nh: 0 = hi, 1 = lo) of 256 weight rows (map boxes of 256 rows)
+                    if (!second) tma_load_2d(dst, nh ? &map_w1_lo : &map_w1_hi, full_bar(s), kb * BK, crank * HCt);
+                    else tma_load_2d(dst, nh ? &map_w2_lo : &map_w2_hi, full_bar(s), crank * HCt + kb * BK, 0);
+                } else if (!second) {               // W1[hidden rows, C]: rows crank*HCt + nh*128, K block kb of C
                     tma_load_2d(dst, &map_w1_hi, full_bar(s), kb * BK, crank * HCt + nh * 128);
                     tma_load_2d(dst + KBLK, &map_w1_lo, full_bar(s), kb * BK, crank * HCt + nh * 128);
                 } else {                            // W2[C rows, hidden]: rows nh*128, K block kb of this CTA's hidden slice
@@ -161,6 +170,18 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                 const uint32_t xk = smem_base + OFF_X + kb * KBLK, st = smem_base + OFF_RING + s * UNIT;
                 const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
                 const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
+                if constexpr (kWide) {
+                    constexpr uint32_t idw = make_idesc_bf16(BM, 256);
+                    const uint32_t dw = tmem_base + (second ? 256 : 0);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        if (nh == 0) {              // w_hi unit
+                            umma_bf16(dw, a_lo + adv, w_hi + adv, idw, (kb | k) != 0);
+                            umma_bf16(dw, a_hi + adv, w_hi + adv, idw, 1);
+                        } else umma_bf16(dw, a_hi + adv, w_hi + adv, idw, 1);       // the unit holds the lo halves
+                    }
+                } else {
                 const uint32_t d = tmem_base + (second ? 256 : 0) + nh * 128;
                 const uint32_t idesc = second ? idesc2 : idesc1;
 #pragma unroll
@@ -169,6 +190,7 @@ STC_DEVINL void convnext_mlp_body(const CUtensorMap& map_a_hi, const CUtensorMap
                     umma_bf16(d, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
                     umma_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
                     umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
+                }
                 }
                 umma_commit(empty_bar(s));
                 if (u == U1 - 1) umma_commit(bar_s1);                   // S complete; the a-tile is dead
@@ -521,6 +543,15 @@ convnext_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __
                           const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                           const Params p) {
     convnext_mlp_body<false>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
+}
+
+// map_w1_* / map_w2_*: boxes of 256 weight rows
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_split_wide_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                               const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                               const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                               const Params p) {
+    convnext_mlp_body<false, HC, true>(map_a_hi, map_a_lo, map_w1_hi, map_w1_lo, map_w2_hi, map_w2_lo, p);
 }
 
 // ===== "TS" form of the split kernel: P = GELU(S) never touches shared memory =================================================

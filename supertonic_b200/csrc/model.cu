@@ -218,6 +218,7 @@ struct Handle {
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
     bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
+    bool mlp_wide = true;             // env STC_MLP_WIDE=0: the 256-unit split form issues N = 128 MMAs (hi + lo units) as before
     bool attn_small = true;           // env STC_ATTN_SMALL=0: the 50-key style attentions use the 320-key layout too (one CTA per SM)
     bool voc_f16 = true;              // vocoder GEMMs single-pass fp16 (default; env STC_VOC=bf16x3 keeps the split-bf16 form there too)
     bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
@@ -970,7 +971,12 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
             } else {
                 if (inred) launch_coop(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                                        mah, mal, w1h, w1l, w2h, w2l, p);
-                else launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                else if (mlp_wide && a) {
+                    const CUtensorMap x1h = tmap(c.pw1.w_hi, c.H, c.C, 256), x1l = tmap(c.pw1.w_lo, c.H, c.C, 256);
+                    const CUtensorMap x2h = tmap(c.pw2.w_hi, c.C, c.H, 256), x2l = tmap(c.pw2.w_lo, c.C, c.H, 256);
+                    launch_pdl(this, mlp::convnext_mlp_split_wide_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
+                               mah, mal, x1h, x1l, x2h, x2l, p);
+                } else launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
                                 mah, mal, w1h, w1l, w2h, w2l, p);
             }
             if (inred) {
@@ -1556,6 +1562,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : std::string(e) == "thin64" ? 6 : 0; }
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_ATTN_SMALL"); hd->attn_small = !(e && e[0] == '0'); }
+        { const char* e = getenv("STC_MLP_WIDE"); hd->mlp_wide = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; hd->voc_f16 = !e || std::string(e) == "f16"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
@@ -1604,6 +1611,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Lay<1>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
