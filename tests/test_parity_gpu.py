@@ -182,6 +182,19 @@ def test_unchunked_text_longer_than_the_tensor_core_attention_limit(rig):
     assert lens[0] > 320
 
 
+def test_fp16_vocoder_operands_saturate_instead_of_overflowing(rig):
+    """The single-pass fp16 vocoder converts its GEMM operands with cvt.rn.satfinite: latents at 3e4 times the normal scale push the
+    im2col operand past fp16's 65504 on the full graphs; the waveform must stay finite and the split-bf16 mode must still agree with
+    the oracle on the same input (fp32 range)."""
+    rng = np.random.default_rng(8)
+    lat = (rng.standard_normal((1, 144, 12)) * 3e4).astype(np.float32)
+    got = rig["eng"].vocode(lat)
+    assert np.isfinite(got).all()
+    want = rig["ora"].voc(dict(latent=lat))
+    with _engine(rig, "bf16x3") as exact:
+        assert U.snr_db(exact.vocode(lat), want) >= SNR_EXACT
+
+
 def test_tf32_vocoder_mode_stays_inside_the_waveform_bound(rig):
     """STC_VOC=tf32 (opt-in): the vocoder's GEMMs run single-pass kind::tf32 on operands rounded to nearest. The waveform must stay
     inside the north-star bound (>= 40 dB) with margin (>= 60 dB asserted; ~70 dB measured); the split-bf16 mode keeps >= 80 dB."""
