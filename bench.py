@@ -309,7 +309,7 @@ def main():
     stage = None
     if rank == 0:
         eng.set_profile(2)
-        prof = {k: dict(ms=0, flops=0, bytes=0, launches=0) for k in ("gemm_tc", "dwconv_ln", "attention", "fused_mlp", "gemm_f16")}
+        prof = {k: dict(ms=0, flops=0, bytes=0, launches=0) for k in ("gemm_tc", "dwconv_ln", "attention", "fused_mlp", "gemm_f16", "dwconv_ln_hbm")}
         stage = dict(dp=0.0, te=0.0, ve=0.0, vocoder=0.0, whole=0.0)
         for b in buckets:
             eng.synthesize_packed_device(b["ids"].data_ptr(), b["mask"].data_ptr(), b["ttl"].data_ptr(), b["dp"].data_ptr(), b["B"], b["T"],
@@ -352,6 +352,11 @@ def main():
         roof["dwconv_ln"] = {"bound": "hbm", "achieved_gbs": prof["dwconv_ln"]["bytes"] / max(prof["dwconv_ln"]["ms"], 1e-9) / 1e6,
                              "peak_gbs": pk["hbm"], "launches": prof["dwconv_ln"]["launches"],
                              "share_of_step": prof["dwconv_ln"]["ms"] / max(stage["whole"], 1e-9)}
+        dh = prof["dwconv_ln_hbm"]
+        roof["dwconv_ln_hbm"] = {"kernel": "stc::dwconv_ln_slide_kernel<4, 7, ring> (vocoder: 27.7k x 512 rows, fp32 in, fp16 operand out)", "bound": "hbm",
+                                 "achieved": dh["bytes"] / max(dh["ms"], 1e-9) / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                                 "frac": dh["bytes"] / max(dh["ms"], 1e-9) / 1e6 / pk["hbm"], "launches": dh["launches"],
+                                 "avg_launch_us": 1000 * dh["ms"] / max(dh["launches"], 1), "share_of_step": dh["ms"] / max(stage["whole"], 1e-9)}
         roof["attention"] = {"achieved_tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9,
                              "launches": prof["attention"]["launches"],
                              "share_of_step": prof["attention"]["ms"] / max(stage["whole"], 1e-9)}

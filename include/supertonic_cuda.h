@@ -189,7 +189,8 @@ void* stc_stream(stc_handle* h);
 int stc_set_profile(stc_handle* h, int level);   /* 0 off, 1 stage events, 2 + per-kernel events (bench roofline leg) */
 /* Per-kernel-class totals of the most recent stc_synthesize* call at profile level 2.
  * cls: 0 = tcgen05 GEMM (split-bf16 operands), 1 = depthwise-conv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (with its
- * reduce kernel), 4 = tcgen05 GEMM with single-pass fp16 operands (the vocoder projections).
+ * reduce kernel), 4 = tcgen05 GEMM with single-pass fp16 operands (the vocoder projections), 5 = depthwise-conv+LayerNorm launches
+ * of >= 32 MB (the vocoder's, HBM-resident; class 1 then holds the L2-resident ones).
  * out = {milliseconds (CUDA events around each launch), algorithmic FLOPs, algorithmic bytes, launches}. */
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]);
 int stc_last_stage_ms(const stc_handle* h, float out[5]);

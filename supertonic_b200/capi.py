@@ -368,7 +368,7 @@ class Engine:
     def kernel_profile(self):
         """Per-kernel-class totals of the last synthesize call (profile level 2)."""
         res = {}
-        for cls, name in enumerate(("gemm_tc", "dwconv_ln", "attention", "fused_mlp", "gemm_f16")):
+        for cls, name in enumerate(("gemm_tc", "dwconv_ln", "attention", "fused_mlp", "gemm_f16", "dwconv_ln_hbm")):
             out = np.zeros(4, np.float64)
             lib.stc_kernel_profile(self._h, cls, _ptr(out))
             res[name] = dict(ms=out[0], flops=out[1], bytes=out[2], launches=int(out[3]))

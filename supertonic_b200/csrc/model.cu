@@ -129,8 +129,9 @@ struct Handle {
     bool force_simt_attn = false;     // env STC_ATTN=simt: keep the CUDA-core attention core (cross-check)
     int profile = 0;          // 0 off, 1 stage events, 2 + per-kernel events for the GEMM / dwconv+LN classes
     struct KProf { double ms = 0, flops = 0, bytes = 0; uint64_t n = 0; };
-    KProf kprof[5];           // 0 = tcgen05 GEMM (split-bf16), 1 = dwconv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (+ its reduce),
-                              // 4 = tcgen05 GEMM, single-pass fp16 operands (vocoder)
+    KProf kprof[6];           // 0 = tcgen05 GEMM (split-bf16), 1 = dwconv+LayerNorm, 2 = attention core, 3 = fused ConvNeXt MLP (+ its reduce),
+                              // 4 = tcgen05 GEMM, single-pass fp16 operands (vocoder), 5 = dwconv+LayerNorm launches of >= 32 MB (the vocoder's:
+                              // HBM-resident; class 1 keeps the L2-resident ones)
     struct Pending { int cls; cudaEvent_t a, b; double flops, bytes; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
@@ -753,13 +754,13 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
     int K = cn ? cn->K : 0, dil = cn ? cn->dil : 1, pad = cn ? cn->pad_left : 0, rows = seq.rows;
     if constexpr (std::is_same<T, float>::value) {
         if (out_act && out_act->hi) {
-            kprof_begin(1, (2.0 * K + 8.0) * rows * C, 8.0 * rows * C + 4.0 * C * (K + 3));
+            kprof_begin(8.0 * rows * C >= 32e6 ? 5 : 1, (2.0 * K + 8.0) * rows * C, (out_act->lo || !out_act->hi ? 8.0 : 6.0) * rows * C + 4.0 * C * (K + 3));
             launch_dwln<T, OutSplit>(this, C, x, w, wb, g, b, OutSplit{out_act->hi, out_act->lo}, rows, seq.off, seq.B, K, dil, pad, eps);
             kprof_end();
             return;
         }
         if (out_act) {          // fp32 operand: of the CUDA-core GEMMs (fp32_simt mode), or of a kind::tf32 GEMM (rounded here)
-            kprof_begin(1, (2.0 * K + 8.0) * rows * C, 8.0 * rows * C + 4.0 * C * (K + 3));
+            kprof_begin(8.0 * rows * C >= 32e6 ? 5 : 1, (2.0 * K + 8.0) * rows * C, (out_act->lo || !out_act->hi ? 8.0 : 6.0) * rows * C + 4.0 * C * (K + 3));
             launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_act->f, tc_mode() ? 1 : 0}, rows, seq.off, seq.B, K, dil, pad, eps);
             kprof_end();
             return;
@@ -1654,7 +1655,7 @@ int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID;
 void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
 int stc_set_profile(stc_handle* h, int level) { if (!h) return STC_ERR_INVALID; h->impl->profile = level; return STC_OK; }
 int stc_kernel_profile(const stc_handle* h, int cls, double out[4]) {
-    if (!h || !out || cls < 0 || cls > 4) return STC_ERR_INVALID;
+    if (!h || !out || cls < 0 || cls > 5) return STC_ERR_INVALID;
     const auto& k = h->impl->kprof[cls];
     out[0] = k.ms; out[1] = k.flops; out[2] = k.bytes; out[3] = (double)k.n;
     return STC_OK;
