@@ -66,18 +66,19 @@ STC_DEVINL void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
 STC_DEVINL void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// Hands a drained TMEM accumulator back to the leader's MMA warp. Relaxed: the tcgen05.ld reads it orders are complete
-// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync); the .release.cluster form compiles to MEMBAR.ALL.GPU and makes the warp
-// wait for every global store of its tile to be acknowledged before the MMAs of the tile after next may start (measured on the
-// fp16 pw1: the MMA warp idled ~8k of 11k cycles per tile on this barrier).
 STC_DEVINL void st_global_256(void* p, const uint32_t* v) {       // one full 32-byte sector per lane (sm_100: STG.256)
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 // (The same lane = row form for the fp32 + residual epilogue of pw2 — 256-bit loads of the residual row, 256-bit stores — was
 // measured slower than the staged one: vocoder 1.82 -> 1.91 ms; a warp-wide 32-byte access to 32 different rows costs 32 L2 requests.)
+
+// Hands a drained TMEM accumulator back to the leader's MMA warp: the remote arrive in its default form (what CUTLASS's
+// ClusterBarrier::arrive(cta_id) issues; SASS: a bare SYNCS.ARRIVE). The tcgen05.ld reads it orders are complete (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync). The explicit .release.cluster form used before compiles to MEMBAR.ALL.GPU + the arrive and made
+// the warp wait for every global store of its tile to be acknowledged first (9 % of the warp samples of the fp16 pw1 were stall_membar).
 STC_DEVINL void mbar_arrive_cluster(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
 // kF16: single-pass fp16 operands (gemm_tc.cuh): a stage holds 128 K-elements, 8 MMAs instead of 24 per 128 K-elements.
