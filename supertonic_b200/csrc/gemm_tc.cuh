@@ -7,7 +7,8 @@
 // and the product is formed as A_hi·W_hi + A_lo·W_hi + A_hi·W_lo with three kind::f16 MMAs per K-slice
 // (bf16 x bf16 products are exact in fp32; the dropped lo·lo term is 2^-16 relative). Measured effect on the
 // full surrogate at 20 Euler steps: max-abs latent error 1e-5 vs 9e-4 for single-pass TF32 and 7e-3 for plain
-// bf16 (DESIGN.md "precision"); the north-star bound is 1e-3.
+// bf16 (DESIGN.md "precision"); the north-star bound is 1e-3. The vocoder's GEMMs (bound: waveform SNR >= 40 dB) instead run the kF16
+// instantiation: one fp16 value per operand element, one MMA per K-slice, half the operand bytes (~68 dB against the oracle).
 //
 // Structure (persistent over 128 x BN output tiles, 320 threads, one CTA per SM):
 //   warp 0   : TMA producer   — cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles, STAGES-deep mbarrier ring

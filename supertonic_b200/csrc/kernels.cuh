@@ -67,7 +67,8 @@ STC_DEVINL int find_seq(const int* __restrict__ off, int B, int row) {
 
 // ---- GEMM operand stores ---------------------------------------------------------------------
 // Operands of the tensor-core GEMMs are kept as split bf16 pairs: v ~= hi + lo, hi = bf16(v),
-// lo = bf16(v - hi) (16 mantissa bits). Plain mode keeps T.
+// lo = bf16(v - hi) (16 mantissa bits). Plain mode keeps T. A null `lo` selects the single fp16 form
+// (vocoder GEMMs): `hi` then holds fp16 bits, converted with saturation.
 struct SplitPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
 
 // round-to-nearest to TF32 (10 mantissa bits): the tensor core reads the upper 19 bits of an fp32 operand, so operands rounded
