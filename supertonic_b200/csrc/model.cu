@@ -219,6 +219,7 @@ struct Handle {
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
     bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
+    bool simt_bm32 = true;            // env STC_SIMT_BM32=0: the fp64 duration-predictor GEMMs keep 16-row tiles
     bool mlp_wide = true;             // env STC_MLP_WIDE=0: the 256-unit split form issues N = 128 MMAs (hi + lo units) as before
     bool attn_small = true;           // env STC_ATTN_SMALL=0: the 50-key style attentions use the 320-key layout too (one CTA per SM)
     bool voc_f16 = true;              // vocoder GEMMs single-pass fp16 (default; env STC_VOC=bf16x3 keeps the split-bf16 form there too)
@@ -772,6 +773,18 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
 template <typename T>
 void Handle::gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo) {
     // small row tiles when 64-row tiles would not give every SM a block (the fp64 duration predictor: 150 blocks before)
+    // (per-element accumulation order over k is the same for every tile height: the variants are bit-identical)
+    // tallest tile that still gives every SM a block: 64 rows (TM = 4: 8 shared-memory loads per 16 FMAs), else 32, else 16
+    if (simt_bm32 && cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 64) >= (unsigned)num_sms) {
+        dim3 grid(cdiv(w.N, 64), cdiv(M, 64));
+        STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
+        return;
+    }
+    if (simt_bm32 && cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 32) >= (unsigned)num_sms && M > 32) {
+        dim3 grid(cdiv(w.N, 64), cdiv(M, 32));
+        STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>, 32>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
+        return;
+    }
     if (cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && M > 16) {
         dim3 grid(cdiv(w.N, 64), cdiv(M, 16));
         STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>, 16>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
@@ -1564,6 +1577,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_ATTN_SMALL"); hd->attn_small = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_MLP_WIDE"); hd->mlp_wide = !(e && e[0] == '0'); }
+        { const char* e = getenv("STC_SIMT_BM32"); hd->simt_bm32 = !(e && e[0] == '0'); }
         { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; hd->voc_f16 = !e || std::string(e) == "f16"; }
         { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
         { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
