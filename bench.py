@@ -117,6 +117,32 @@ def oracle_run(texts, langs, voices, total_step, reps):
     return audio, times, cores
 
 
+def parity_check(eng, root, ids, mask, style, total_step, which):
+    """Outside the timed region: the timed batch once more through stc_synthesize_packed with INJECTED noise (same kernels, same
+    row-tile count), and the utterances `which` of it against the oracle (oracle/: the CPU restatement of the reference's `_infer`)
+    run on each of them alone with the same noise rows."""
+    from oracle.pipeline import OraclePipeline
+    ora = OraclePipeline(root)
+    B = ids.shape[0]
+    nz = np.random.default_rng(4321).standard_normal((B, eng.cfg.latent_channels, 420)).astype(np.float32)
+    out = eng.synthesize_packed(ids, mask, style.ttl, style.dp, total_step, 1.05, noise=nz, want_latent=True)
+    worst_err, worst_snr, exact = 0.0, 1e9, True
+    for b in which:
+        t = int(mask[b].sum())
+        tr = {}
+        wav_ref, dur_ref = ora.infer_ids(ids[b:b + 1, :t], mask[b:b + 1, :, :t], style.ttl[b:b + 1], style.dp[b:b + 1], total_step,
+                                         np.float32(1.05), lambda B_, D_, L_, b=b: nz[b:b + 1, :, :L_], tr)
+        n = int(tr["wav_lengths"][0])
+        exact = exact and bool(out["duration"][b] == dur_ref[0]) and int(out["wav_lengths"][b]) == n and int(out["frames"][b]) == tr["latent_len"]
+        worst_err = max(worst_err, float(np.abs(out["latent"][b].T - tr["xs"][-1][0]).max()))
+        ref = wav_ref[:n].astype(np.float64)
+        err = ((out["wavs"][b].astype(np.float64) - ref) ** 2).sum()
+        worst_snr = min(worst_snr, 200.0 if err == 0 else float(10 * np.log10((ref ** 2).sum() / err)))
+    return {"utterances": [int(b) for b in which], "durations_and_frame_counts_bit_exact": exact, "latent_max_abs": worst_err,
+            "snr_db": worst_snr, "against": "oracle/ (CPU restatement of the reference _infer), same injected noise",
+            "tolerance": {"latent_max_abs": 2e-4, "snr_db": 60.0}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,6 +153,7 @@ def main():
     ap.add_argument("--total-step", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--vary-batches", action="store_true", help="N > 1: every rank draws its own 32 utterances (seed 1234 + 1000 rank)")
     ap.add_argument("--workload", default="batch", choices=["batch", "sweep1024"],
                     help="batch: configs[1], every GPU its own --batch utterances (weak scaling, the default and the headline). "
@@ -370,6 +397,14 @@ def main():
                              "launches": prof["attention"]["launches"],
                              "share_of_step": prof["attention"]["ms"] / max(stage["whole"], 1e-9)}
 
+    pcheck = None
+    if rank == 0 and not a.no_parity_check:
+        # the shortest and the longest utterance of the timed batch, checked against the oracle outside the timed region
+        pcheck = parity_check(eng, root, ids[:group] if n_utt > group else ids, mask[:group] if n_utt > group else mask,
+                              T.Style(style.ttl[:group], style.dp[:group]) if n_utt > group else style, a.total_step,
+                              [int(np.argmin(lens[:group])), int(np.argmax(lens[:group]))])
+        if not (pcheck["durations_and_frame_counts_bit_exact"] and pcheck["latent_max_abs"] <= 2e-4 and pcheck["snr_db"] >= 60.0):
+            print("bench.py: PARITY CHECK FAILED " + json.dumps(pcheck), file=sys.stderr)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -392,7 +427,7 @@ def main():
                                      "ms_per_step": 1000 * float(temax[0].item()) / a.steps,
                                      "windows_ms_per_step": [1000 * w / a.steps for w in wins],
                                      "window": "median of three windows of exactly `steps` steps each (max over ranks per window)"},
-           "gpu_launches": int(launches), "per_rank": per_rank, "latency": lat, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
+           "gpu_launches": int(launches), "parity_check": pcheck, "per_rank": per_rank, "latency": lat, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
            "p50_step_ms": float(np.median(step_ms))}
     print(json.dumps(out))
     if world > 1:

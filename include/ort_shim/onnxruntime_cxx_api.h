@@ -157,11 +157,26 @@ public:
         const stc_config& c = shared_->cfg;
         std::vector<Value> out;
         int rc = STC_OK;
+        // the C ABI takes bare pointers: every borrowed input is checked against the shapes the graph expects, as ONNX Runtime
+        // does before running ("Got invalid dimensions for input")
+        auto want_shape = [&](const char* name, const Value& v, std::vector<int64_t> want) {
+            const auto s = v.GetTensorTypeAndShapeInfo();
+            bool ok = s.shape.size() == want.size();
+            size_t n = 1;
+            for (size_t i = 0; ok && i < want.size(); ++i) { ok = s.shape[i] == want[i]; n *= (size_t)want[i]; }
+            if (!ok || s.count != n) throw Exception(std::string("Got invalid dimensions for input: ") + name, STC_ERR_INVALID);
+        };
+        auto style_ok = [&](int B, const Value* ttl, const Value* dp) {
+            if (ttl) want_shape("style_ttl", *ttl, {B, c.style_ttl_tokens, c.style_ttl_dim});
+            if (dp) want_shape("style_dp", *dp, {B, c.style_dp_tokens, c.style_dp_dim});
+        };
         switch (kind_) {
             case DP: {
                 want_out("duration");
                 const Value& ids = find("text_ids", 8);
                 int B = (int)dim(ids, 0), T = (int)dim(ids, 1);
+                style_ok(B, nullptr, &find("style_dp", 4));
+                want_shape("text_mask", find("text_mask", 4), {B, 1, T});
                 out.push_back(Value::Owned({B}));
                 rc = stc_duration(h, ids.GetTensorData<int64_t>(), fptr(find("style_dp", 4)), fptr(find("text_mask", 4)), B, T,
                                   out[0].GetTensorMutableData<float>());
@@ -171,6 +186,8 @@ public:
                 want_out("text_emb");
                 const Value& ids = find("text_ids", 8);
                 int B = (int)dim(ids, 0), T = (int)dim(ids, 1);
+                style_ok(B, &find("style_ttl", 4), nullptr);
+                want_shape("text_mask", find("text_mask", 4), {B, 1, T});
                 out.push_back(Value::Owned({B, c.text_emb_channels, T}));
                 rc = stc_text_encode(h, ids.GetTensorData<int64_t>(), fptr(find("style_ttl", 4)), fptr(find("text_mask", 4)), B, T,
                                      out[0].GetTensorMutableData<float>(), nullptr);
@@ -182,6 +199,12 @@ public:
                 const Value& te = find("text_emb", 4);
                 int B = (int)dim(x, 0), L = (int)dim(x, 2), T = (int)dim(te, 2);
                 if (dim(x, 1) != c.latent_channels) throw Exception("shim: noisy_latent channel count != tts.json", STC_ERR_INVALID);
+                style_ok(B, &find("style_ttl", 4), nullptr);
+                want_shape("text_emb", te, {B, c.text_emb_channels, T});
+                want_shape("text_mask", find("text_mask", 4), {B, 1, T});
+                want_shape("latent_mask", find("latent_mask", 4), {B, 1, L});
+                want_shape("total_step", find("total_step", 4), {B});
+                want_shape("current_step", find("current_step", 4), {B});
                 out.push_back(Value::Owned({B, c.latent_channels, L}));
                 rc = stc_vector_step(h, fptr(x), fptr(te), fptr(find("style_ttl", 4)), fptr(find("text_mask", 4)),
                                      fptr(find("latent_mask", 4)), fptr(find("total_step", 4)), fptr(find("current_step", 4)), B, L, T,
@@ -192,6 +215,7 @@ public:
                 want_out("wav_tts");
                 const Value& z = find("latent", 4);
                 int B = (int)dim(z, 0), L = (int)dim(z, 2);
+                want_shape("latent", z, {B, c.latent_channels, L});
                 out.push_back(Value::Owned({B, (int64_t)L * c.chunk_size}));
                 rc = stc_vocode(h, fptr(z), B, L, out[0].GetTensorMutableData<float>());
                 break;

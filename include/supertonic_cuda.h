@@ -70,6 +70,13 @@ void stc_destroy(stc_handle* h);
 const char* stc_last_error(const stc_handle* h);
 int stc_get_config(const stc_handle* h, stc_config* out);
 
+/* Shape check of the style tensors a caller is about to pass for a batch of B utterances: style_ttl must be [B, S, Cs] and
+ * style_dp [B, e1, e2] with the dims of stc_config (ONNX Runtime raises "Got invalid dimensions for input" at the same
+ * boundary, cpp/helper.cpp:519, 552, 643). The entry points below take bare pointers and trust the caller, so every
+ * wrapper that builds these tensors from client-selectable voice-style files (cpp/helper.cpp:829-897) must call this first.
+ * Either shape pointer may be NULL (not checked). Returns STC_ERR_INVALID with a message naming the offending dims. */
+int stc_validate_style(const stc_handle* h, int B, const int64_t style_ttl_shape[3], const int64_t style_dp_shape[3]);
+
 /* ---- parity layer: 1:1 with the four Session::Run calls, host pointers in/out ---------------- */
 
 /* duration_predictor.onnx — cpp/helper.cpp:512-526. text_ids[B,T] int64, style_dp[B,e1,e2],
@@ -180,6 +187,11 @@ int stc_chunk_text(const char* text, int max_len, char* out_buf, size_t out_cap,
 
 /* Kernels launched by this handle since creation (bench `gpu_launches`). */
 uint64_t stc_launch_count(const stc_handle* h);
+/* Which variant each size-dependent kernel dispatcher chose, as "name=count\n" lines (launches issued or captured since the handle
+ * was created): gemm_bn64 / gemm_bn128 / gemm_bn256 / gemm2_bf16x3 / gemm2_f16 / gemm_f16_bn*, mlp_*, dwconv_ln_slide[_ring] / _tile /
+ * _vec / _generic, attention_tc[_small] / attention_simt. Lets a parity test assert that the kernels a benchmark-size input reaches
+ * are the ones it compared with the oracle. *need = bytes required (incl. NUL); STC_ERR_CAPACITY if cap is smaller. */
+int stc_kernel_variants(const stc_handle* h, char* buf, size_t cap, size_t* need);
 /* Use CUDA graphs for the fast layer (default 1). */
 int stc_set_graphs(stc_handle* h, int enabled);
 /* cudaStream_t the handle launches on (as void*), for callers that time with CUDA events. */

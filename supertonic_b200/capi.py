@@ -38,6 +38,7 @@ _SIGS = {
     "stc_destroy": (None, [_vp]),
     "stc_last_error": (C.c_char_p, [_vp]),
     "stc_get_config": (_i, [_vp, C.POINTER(StcConfig)]),
+    "stc_validate_style": (_i, [_vp, _i, _vp, _vp]),
     "stc_duration": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "stc_text_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "stc_vector_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -56,6 +57,7 @@ _SIGS = {
     "stc_frontend_text_to_ids": (_i, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _vp, _vp, _i64, _vp]),
     "stc_chunk_text": (_i, [C.c_char_p, _i, _vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(_i)]),
     "stc_launch_count": (C.c_uint64, [_vp]),
+    "stc_kernel_variants": (_i, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "stc_set_graphs": (_i, [_vp, _i]),
     "stc_stream": (_vp, [_vp]),
     "stc_set_profile": (_i, [_vp, _i]),
@@ -201,10 +203,24 @@ class Engine:
         if rc != STC_OK:
             raise StcError(rc, lib.stc_last_error(self._h).decode())
 
+    def _check(self, B, T=None, ttl=None, dp=None, mask=None, ids=None):
+        """Shapes against the engine's geometry before bare pointers cross the C ABI (ORT raises at the same boundary)."""
+        def shp(a):
+            return None if a is None else (C.c_int64 * 3)(*(tuple(a.shape) + (-1, -1, -1))[:3])
+        if (ttl is not None and ttl.ndim != 3) or (dp is not None and dp.ndim != 3):
+            raise StcError(-1, "Got invalid dimensions for input: style tensors must have rank 3")
+        if ttl is not None or dp is not None:
+            self._chk(lib.stc_validate_style(self._h, B, shp(ttl), shp(dp)))
+        if ids is not None and ids.shape != (B, T):
+            raise StcError(-1, f"Got invalid dimensions for input: text_ids {ids.shape}, expected {(B, T)}")
+        if mask is not None and mask.size != B * T:
+            raise StcError(-1, f"Got invalid dimensions for input: text_mask {mask.shape}, expected {(B, 1, T)}")
+
     # ---- parity layer (1:1 with the reference's four Session::Run calls)
     def duration(self, text_ids, style_dp, text_mask) -> np.ndarray:
         ids, sty, m = _cf(text_ids, np.int64), _cf(style_dp, np.float32), _cf(text_mask, np.float32)
         B, T = ids.shape
+        self._check(B, T, dp=sty, mask=m)
         out = np.empty((B,), np.float32)
         self._chk(lib.stc_duration(self._h, _ptr(ids), _ptr(sty), _ptr(m), B, T, _ptr(out)))
         return out
@@ -212,6 +228,7 @@ class Engine:
     def text_encode(self, text_ids, style_ttl, text_mask) -> np.ndarray:
         ids, sty, m = _cf(text_ids, np.int64), _cf(style_ttl, np.float32), _cf(text_mask, np.float32)
         B, T = ids.shape
+        self._check(B, T, ttl=sty, mask=m)
         out = np.empty((B, self.cfg.text_emb_channels, T), np.float32)
         shp = np.zeros(3, np.int64)
         self._chk(lib.stc_text_encode(self._h, _ptr(ids), _ptr(sty), _ptr(m), B, T, _ptr(out), _ptr(shp)))
@@ -224,6 +241,10 @@ class Engine:
         tot, cur = _cf(total_step, np.float32), _cf(current_step, np.float32)
         B, D, L = x.shape
         T = te.shape[2]
+        self._check(B, T, ttl=sty, mask=tm)
+        if D != self.cfg.latent_channels or te.shape[:2] != (B, self.cfg.text_emb_channels) or lm.size != B * L or tot.size != B or cur.size != B:
+            raise StcError(-1, f"Got invalid dimensions for input: noisy_latent {x.shape}, text_emb {te.shape}, latent_mask {lm.shape}, "
+                               f"total_step {tot.shape}, current_step {cur.shape}")
         out = np.empty_like(x)
         self._chk(lib.stc_vector_step(self._h, _ptr(x), _ptr(te), _ptr(sty), _ptr(tm), _ptr(lm), _ptr(tot), _ptr(cur),
                                       B, L, T, _ptr(out)))
@@ -232,6 +253,8 @@ class Engine:
     def vocode(self, latent) -> np.ndarray:
         x = _cf(latent, np.float32)
         B, D, L = x.shape
+        if D != self.cfg.latent_channels:
+            raise StcError(-1, f"Got invalid dimensions for input: latent {x.shape}, expected [B,{self.cfg.latent_channels},L]")
         out = np.empty((B, L * self.cfg.chunk_size), np.float32)
         self._chk(lib.stc_vocode(self._h, _ptr(x), B, L, _ptr(out)))
         return out
@@ -243,10 +266,13 @@ class Engine:
         ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
         sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
         B, T = ids.shape
+        self._check(B, T, ttl=sttl, dp=sdp, mask=m)
         cs = self.cfg.chunk_size
         nz, nld = None, 0
         if noise is not None:
             nz = _cf(noise, np.float32)
+            if nz.ndim != 3 or nz.shape[:2] != (B, self.cfg.latent_channels):
+                raise StcError(-1, f"Got invalid dimensions for input: noise {nz.shape}, expected [{B},{self.cfg.latent_channels},>=L]")
             nld = nz.shape[2]
         # duration is data dependent; start from a per-token guess and retry once with the exact size on overflow
         cap = wav_cap or max(int(T * 0.12 * self.cfg.sample_rate / cs) + 8, 16) * cs
@@ -282,10 +308,14 @@ class Engine:
         ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
         sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
         B, T = ids.shape
+        self._check(B, T, ttl=sttl, dp=sdp, mask=m)
         cs, D = self.cfg.chunk_size, self.cfg.latent_channels
         nz, nld = None, 0
         if noise is not None:
-            nz = _cf(noise, np.float32); nld = nz.shape[2]
+            nz = _cf(noise, np.float32)
+            if nz.ndim != 3 or nz.shape[:2] != (B, D):
+                raise StcError(-1, f"Got invalid dimensions for input: noise {nz.shape}, expected [{B},{D},>=frames]")
+            nld = nz.shape[2]
         cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs
         dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
         use_async = (not wait) and bool(pinned) and noise is None and not want_latent
@@ -358,6 +388,14 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(lib.stc_launch_count(self._h))
+
+    def kernel_variants(self) -> dict:
+        """{variant name: launches issued or captured since creation} of the size-dependent kernel dispatchers."""
+        need = C.c_size_t(0)
+        lib.stc_kernel_variants(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value + 64)
+        self._chk(lib.stc_kernel_variants(self._h, buf, need.value + 64, C.byref(need)))
+        return {k: int(v) for k, v in (ln.split("=") for ln in buf.value.decode().splitlines() if ln)}
 
     def set_graphs(self, on: bool):
         lib.stc_set_graphs(self._h, int(on))

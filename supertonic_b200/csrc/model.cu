@@ -3,6 +3,7 @@
 // What it replaces in the reference: the four Ort::Session objects (cpp/helper.cpp:784-795) and their
 // Run calls inside TextToSpeech::_infer (:512-523 DP, :545-556 TE, :620-647 VE step, :662-672 vocoder),
 // plus the host-side latent bookkeeping between them (:424-467, :590-659).
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -55,9 +56,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct GraphKey {
     int stage, mode, B, T, rows, maxlen, steps; int64_t noise_ld; uintptr_t p0, p1;
     int trows = 0, tmaxlen = 0;         // packed text side: launched rows / longest-sequence bound (0: rectangle)
+    // device-resident entry points: the graph bakes the caller's four input pointers (ids, mask, style_ttl, style_dp) — all of
+    // them are part of the key, unhashed (a folded key let two distinct pointer sets replay each other's graph)
+    std::array<uintptr_t, 4> in{};
     bool operator<(const GraphKey& o) const {
-        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1, trows, tmaxlen) <
-               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1, o.trows, o.tmaxlen);
+        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1, trows, tmaxlen, in) <
+               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1, o.trows, o.tmaxlen, o.in);
     }
 };
 
@@ -123,6 +127,10 @@ struct Handle {
     void run_graphed(const GraphKey& key, const std::function<void()>& body, cudaEvent_t after_uploads = nullptr);
     uint64_t graph_replays = 0, graph_captures = 0;
     uint64_t launches = 0;
+    // which kernel variant each size-dependent dispatcher chose (issued or captured launches since creation): lets a test assert
+    // that the variants running at benchmark scale are the ones it compared with the oracle (stc_kernel_variants)
+    std::map<std::string, uint64_t> variant_count;
+    void note(const char* name) { if (!dry) ++variant_count[name]; }
     EncodeTiledFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int>, CUtensorMap> map_cache;
     bool use_graphs = true;
@@ -638,6 +646,13 @@ void Handle::load(const std::string& onnx_dir) {
         cfg.vocab_size = dp_arch.at("vocab");
         dp.vec["embed"] = W(f, "dp.embed.weight", (size_t)cfg.vocab_size * dp.C);
         int si = dp_arch.at("style_in");
+        {   // style_dp[B, e1, e2]: the split comes from the graph's input signature (the reference reads it from the voice-style
+            // JSON, cpp/helper.cpp:856-861, and ORT checks it against the graph)
+            const OnnxValueInfo* v = f.input("style_dp");
+            if (!v || v->dims.size() != 3 || v->dims[1] <= 0 || v->dims[2] <= 0 || v->dims[1] * v->dims[2] != si)
+                throw StcError(STC_ERR_UNSUPPORTED, "duration_predictor.onnx: input style_dp must be [B, e1, e2] with e1*e2 = " + std::to_string(si));
+            cfg.style_dp_tokens = (int)v->dims[1]; cfg.style_dp_dim = (int)v->dims[2];
+        }
         dp.lin.push_back(make_linear(f, "dp.style", si, dp.C, false));
         dp.vec["head.ln_g"] = W(f, "dp.head.ln.weight", dp.C);
         dp.vec["head.ln_b"] = W(f, "dp.head.ln.bias", dp.C);
@@ -651,6 +666,9 @@ void Handle::load(const std::string& onnx_dir) {
         te.vec["embed"] = W(f, "te.embed.weight", (size_t)cfg.vocab_size * te.C);
         cfg.text_emb_channels = te.C;
         cfg.style_ttl_tokens = te_arch.at("n_style"); cfg.style_ttl_dim = te_arch.at("style_dim");
+        const OnnxValueInfo* v = f.input("style_ttl");
+        if (v && v->dims.size() == 3 && v->dims[1] > 0 && v->dims[2] > 0 && (v->dims[1] != cfg.style_ttl_tokens || v->dims[2] != cfg.style_ttl_dim))
+            throw StcError(STC_ERR_UNSUPPORTED, "text_encoder.onnx: input style_ttl dims do not match the layer plan");
     }
     {
         OnnxFile f = load_onnx(onnx_dir + "/vector_estimator.onnx");
@@ -665,9 +683,6 @@ void Handle::load(const std::string& onnx_dir) {
         voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
         voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
     }
-    // style_dp dims: e1*e2 = style_in; keep the reference's [B,e1,e2] split from the surrogate (8 x 16) when it matches
-    int si = dp_arch.at("style_in");
-    cfg.style_dp_tokens = 8; cfg.style_dp_dim = si / 8;
 }
 
 // ------------------------------------------------------------------------------------------ kernels (host side)
@@ -701,6 +716,7 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             dim3 sg(cdiv(chains, 512 / C));
 #define STC_SLIDE(NW, KK)                                                                                                                     \
     do {                                                                                                                                      \
+        h->note(ring ? "dwconv_ln_slide_ring" : "dwconv_ln_slide");                                                                          \
         if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{}); \
         else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{});     \
         return;                                                                                                                               \
@@ -723,6 +739,7 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             const size_t smem = (size_t)(std::max(R, 8) + span) * C * sizeof(float);
             if (R >= 8 && smem <= 200 * 1024) {
                 dim3 tg(cdiv(rows, R));
+                h->note("dwconv_ln_tile");
                 switch (C / 32) {
                     case 4: STC_LAUNCH(h, (dwconv_ln_tile_kernel<4, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
                     case 8: STC_LAUNCH(h, (dwconv_ln_tile_kernel<8, Out>), tg, block, smem, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps, R); return;
@@ -730,6 +747,7 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
                 }
             }
         }
+        if (C == 128 || C == 256 || C == 512) h->note("dwconv_ln_vec");
         switch (C / 32) {
             case 4: STC_LAUNCH(h, (dwconv_ln_vec_kernel<4, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
             case 8: STC_LAUNCH(h, (dwconv_ln_vec_kernel<8, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); return;
@@ -737,6 +755,7 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             default: break;
         }
     }
+    h->note("dwconv_ln_generic");
     switch (C / 32) {
         case 1: STC_LAUNCH(h, (dwconv_ln_kernel<T, 1, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
         case 2: STC_LAUNCH(h, (dwconv_ln_kernel<T, 2, Out>), grid, block, 0, x, w, wb, g, b, out, rows, off, B, K, dil, pad, eps); break;
@@ -799,6 +818,7 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     if (!ep.bias) ep.bias = w.bias;
     if (!tc_mode()) {
         float* o = out_f32 ? out_f32 : out_act->f;
+        note("gemm_simt_f32");
         gemm_simt<float>(a.f, w.K, M, w, ep, o, ldo);
         return;
     }
@@ -839,6 +859,7 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
         if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
         cfg.attrs = attr; cfg.numAttrs = na;
         kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
+        note(f16 ? "gemm2_f16" : "gemm2_bf16x3");
         cudaError_t e = f16 ? cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<true>, mah, mal, mwh, mwl, p)
                             : cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<false>, mah, mal, mwh, mwl, p);
         if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("two-SM tcgen05 GEMM launch: ") + cudaGetErrorString(e));
@@ -863,6 +884,9 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     cfg.attrs = attr; cfg.numAttrs = na;
     kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
     cudaError_t e;
+    note(ep.rope_freqs ? "gemm_bn64_rope" : c.bn == 64 ? (tf32 ? "gemm_tf32_bn64" : f16 ? "gemm_f16_bn64" : "gemm_bn64")
+                       : c.bn == 128 ? (tf32 ? "gemm_tf32_bn128" : f16 ? "gemm_f16_bn128" : "gemm_bn128")
+                                     : (tf32 ? "gemm_tf32_bn256" : f16 ? "gemm_f16_bn256" : "gemm_bn256"));
     switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : f16 ? 2000 + c.bn : c.bn) {
         case 2064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, false, true>, mah, mal, mwh, mwl, p); break;
         case 2128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, false, true>, mah, mal, mwh, mwl, p); break;
@@ -954,6 +978,7 @@ void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, cons
         }
     }
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
+    note(form == 1 ? "mlp_cluster" : form == 3 ? "mlp_ts" : form == 5 ? "mlp_thin64" : form == 4 ? "mlp_thin" : (mlp_wide && a && !inred) ? "mlp_split_wide" : "mlp_split");
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
         const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
@@ -1077,6 +1102,7 @@ void Handle::attn_core(const float* Q, const float* K, const float* V, const Act
     float scale = 1.0f / std::sqrt((float)dh);
     const float* kmask = key_masked ? k.mask : nullptr;
     kprof_begin(2, 4.0 * (double)q.rows * k.maxlen * heads * dh, 4.0 * heads * dh * (2.0 * q.rows + 2.0 * k.rows));
+    note("attention_simt");
     if (out.hi) {
         OutSplit o{out.hi, out.lo};
         if (dh == 64) STC_LAUNCH(this, (attention_kernel<64, OutSplit>), grid, 128, 0, Q, K, V, kmask, o, q.off, k.off, kmask ? k.cnt : nullptr, heads, scale);
@@ -1146,6 +1172,7 @@ void Handle::attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const 
         const CUtensorMap mkh = tmap(kv.k_hi, k.rows, a.C, attn::KB), mkl = tmap(kv.k_lo, k.rows, a.C, attn::KB);
         const CUtensorMap mvh = tmap(kv.vt_hi, vrows, kv.ldk, attn::DH), mvl = tmap(kv.vt_lo, vrows, kv.ldk, attn::DH);
         dim3 grid(cdiv(q.maxlen, attn::BQ), a.heads, q.B);
+        note(k.maxlen <= attn::KB && attn_small ? "attention_tc_small" : "attention_tc");
         if (k.maxlen <= attn::KB && attn_small)       // <= 64 keys (style attention): the two-CTAs-per-SM layout
             launch_pdl(this, attn::attention_tc_kernel<1>, grid, dim3(attn::NUM_THREADS), (size_t)attn::Lay<1>::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
         else
@@ -1664,7 +1691,29 @@ int stc_get_config(const stc_handle* h, stc_config* out) {
     return STC_OK;
 }
 
+int stc_validate_style(const stc_handle* h, int B, const int64_t ttl[3], const int64_t dp[3]) {
+    if (!h || !h->impl) return fail(nullptr, STC_ERR_INVALID, "stc_validate_style: null handle");
+    const stc_config& c = h->impl->cfg;
+    auto bad = [&](const char* name, const int64_t* got, int d1, int d2) {
+        return fail(const_cast<stc_handle*>(h), STC_ERR_INVALID,
+                    std::string("Got invalid dimensions for input: ") + name + " — got [" + std::to_string(got[0]) + "," + std::to_string(got[1]) + "," +
+                        std::to_string(got[2]) + "], expected [" + std::to_string(B) + "," + std::to_string(d1) + "," + std::to_string(d2) + "]");
+    };
+    if (ttl && (ttl[0] != B || ttl[1] != c.style_ttl_tokens || ttl[2] != c.style_ttl_dim)) return bad("style_ttl", ttl, c.style_ttl_tokens, c.style_ttl_dim);
+    if (dp && (dp[0] != B || dp[1] != c.style_dp_tokens || dp[2] != c.style_dp_dim)) return bad("style_dp", dp, c.style_dp_tokens, c.style_dp_dim);
+    return STC_OK;
+}
+
 uint64_t stc_launch_count(const stc_handle* h) { return h ? h->impl->launches : 0; }
+int stc_kernel_variants(const stc_handle* h, char* buf, size_t cap, size_t* need) {
+    if (!h || !h->impl || !need) return STC_ERR_INVALID;
+    std::string s;
+    for (const auto& kv : h->impl->variant_count) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+    *need = s.size() + 1;
+    if (!buf || cap < s.size() + 1) return STC_ERR_CAPACITY;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return STC_OK;
+}
 int stc_set_graphs(stc_handle* h, int enabled) { if (!h) return STC_ERR_INVALID; h->impl->use_graphs = enabled != 0; return STC_OK; }
 void* stc_stream(stc_handle* h) { return h ? (void*)h->impl->stream : nullptr; }
 int stc_set_profile(stc_handle* h, int level) { if (!h) return STC_ERR_INVALID; h->impl->profile = level; return STC_OK; }
@@ -1945,7 +1994,10 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         //      for the durations while the text encoder is still running.
         const int64_t* d_ids = nullptr; const float *d_tmask = nullptr, *d_sttl = nullptr, *d_sdp = nullptr;
         float *d_dur = nullptr, *d_temb = nullptr; int64_t* d_wavlen = nullptr;
-        const uintptr_t pin = host_io ? 0 : (uintptr_t)text_ids ^ ((uintptr_t)text_mask << 1) ^ ((uintptr_t)style_ttl << 2) ^ ((uintptr_t)style_dp << 3);
+        const uintptr_t pin = 0;
+        std::array<uintptr_t, 4> pins{};
+        if (!host_io) pins = {(uintptr_t)text_ids, (uintptr_t)text_mask, (uintptr_t)style_ttl, (uintptr_t)style_dp};
+        auto keyed = [&](GraphKey k) { k.in = pins; return k; };
         const size_t stage_base = h->h_stage_off;
         auto stage1a = [&]() {
             h->arena.reset(); h->persist.reset(); h->h_stage_off = stage_base;
@@ -1972,20 +2024,20 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         // workspace: the two are independent (cpp/helper.cpp:512-556 runs them back to back) and DP alone leaves the GPU idle
         if (ovl) {
             std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f);
-            try { h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in); }
+            try { h->run_graphed(keyed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}), stage1a, h->ev_in); }
             catch (...) { std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f); throw; }
             cudaEventRecord(h->ev[6], h->stream);
             std::swap(h->stream, h->stream_f); h->arena.swap(h->arena_f);
             STC_CUDA(cudaStreamWaitEvent(st, h->ev[6], 0));           // stage 2 reads the durations / wav lengths on the device
         } else {
-            h->run_graphed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}, stage1a, h->ev_in);
+            h->run_graphed(keyed(GraphKey{1, mode, B, T, 0, 0, 0, (int64_t)speed_bits, pin, 0, trows, tmaxlen}), stage1a, h->ev_in);
             if (h->profile) cudaEventRecord(h->ev[1], st);
             cudaEventRecord(h->ev[6], st);
         }
         {
             STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
-            try { h->run_graphed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0, trows, tmaxlen}, stage1b); }
+            try { h->run_graphed(keyed(GraphKey{2, mode, B, T, 0, 0, 0, 0, pin, 0, trows, tmaxlen}), stage1b); }
             catch (...) { std::swap(h->stream, h->stream2); h->arena.swap(h->arena2); throw; }
             cudaEventRecord(h->ev_te, h->stream);
             std::swap(h->stream, h->stream2); h->arena.swap(h->arena2);
@@ -2065,8 +2117,8 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             }
             h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav, !chunked);
         };
-        h->run_graphed(GraphKey{3, mode | (latent_out ? 4 : 0) | (chunked ? 8 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
-                                pin, async_copy ? (uintptr_t)h->outbuf[slot] : host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}, stage2);
+        h->run_graphed(keyed(GraphKey{3, mode | (latent_out ? 4 : 0) | (chunked ? 8 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
+                                      pin, async_copy ? (uintptr_t)h->outbuf[slot] : host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}), stage2);
         if (getenv("STC_TIMING")) {
             const auto t_host2 = std::chrono::steady_clock::now();
             fprintf(stderr, "[stc timing] wait for durations %.1f us, host work until stage-2 launch returned %.1f us\n",

@@ -1,4 +1,4 @@
-// Minimal ONNX (protobuf wire format) reader: initializers + metadata_props + graph I/O names.
+// Minimal ONNX (protobuf wire format) reader: nodes, initializers, metadata_props, graph I/O signatures.
 // No protobuf / onnx dependency (neither is in the image). Field numbers from the public onnx.proto
 // (SURVEY.md Appendix C). Replaces what Ort::Session(env, path, opts) does with the file at
 // reference cpp/helper.cpp:781 — for this library: "load the ONNX initializers into device buffers".
@@ -21,11 +21,32 @@ struct OnnxTensor {
     const float* f32() const { return reinterpret_cast<const float*>(raw.data()); }
 };
 
+struct OnnxAttr {                     // AttributeProto: the scalar / list kinds the four graphs use
+    int64_t i = 0; float f = 0.f; std::string s;
+    std::vector<int64_t> ints;
+};
+struct OnnxNode {                     // NodeProto
+    std::string op, name;
+    std::vector<std::string> in, out;
+    std::map<std::string, OnnxAttr> attr;
+    int64_t attr_i(const std::string& k, int64_t dflt) const { auto it = attr.find(k); return it == attr.end() ? dflt : it->second.i; }
+};
+struct OnnxValueInfo {                // ValueInfoProto of a graph input / output: dims < 0 are symbolic (dim_param)
+    std::string name; int elem_type = 0;
+    std::vector<int64_t> dims;
+};
+
 struct OnnxFile {
     std::map<std::string, OnnxTensor> initializers;
     std::map<std::string, std::string> metadata;
     std::vector<std::string> inputs, outputs;
+    std::vector<OnnxValueInfo> input_info, output_info;
+    std::vector<OnnxNode> nodes;      // in file order (ONNX requires a topological order)
     size_t n_nodes = 0;
+    const OnnxValueInfo* input(const std::string& name) const {
+        for (const auto& v : input_info) if (v.name == name) return &v;
+        return nullptr;
+    }
 };
 
 namespace pb {
@@ -60,8 +81,8 @@ inline void parse_tensor(pb::Reader r, std::string& name, OnnxTensor& t) {
         int f = r.next(wt, v, s);
         if (f == 1) { if (wt == 2) { while (s.ok()) t.dims.push_back((int64_t)s.varint()); } else t.dims.push_back((int64_t)v); }
         else if (f == 2) t.dtype = (int)v;
-        else if (f == 8) name = s.str();
-        else if (f == 9) { t.raw.assign(s.p, s.end); has_raw = true; }
+        else if (f == 8) { if (wt != 2) throw std::runtime_error("onnx: tensor name with wire type " + std::to_string(wt)); name = s.str(); }
+        else if (f == 9) { if (wt != 2) throw std::runtime_error("onnx: raw_data with wire type " + std::to_string(wt)); t.raw.assign(s.p, s.end); has_raw = true; }
         else if (f == 4) { if (wt == 2) { size_t n = (s.end - s.p) / 4; size_t o = floats.size(); floats.resize(o + n); memcpy(floats.data() + o, s.p, n * 4); }
                            else { float x; uint32_t u = (uint32_t)v; memcpy(&x, &u, 4); floats.push_back(x); } }
         else if (f == 7) { if (wt == 2) { while (s.ok()) i64.push_back((int64_t)s.varint()); } else i64.push_back((int64_t)v); }
@@ -71,17 +92,79 @@ inline void parse_tensor(pb::Reader r, std::string& name, OnnxTensor& t) {
         if (!floats.empty()) { t.raw.resize(floats.size() * 4); memcpy(t.raw.data(), floats.data(), t.raw.size()); }
         else if (!i64.empty()) { t.raw.resize(i64.size() * 8); memcpy(t.raw.data(), i64.data(), t.raw.size()); }
     }
+    // the payload must hold exactly numel elements of the declared type (a truncated file would otherwise be read past its end)
+    const size_t esz = t.dtype == 1 ? 4 : t.dtype == 7 ? 8 : t.dtype == 11 ? 8 : t.dtype == 6 ? 4 : t.dtype == 10 || t.dtype == 16 ? 2 : t.dtype == 2 || t.dtype == 3 || t.dtype == 9 ? 1 : 0;
+    for (auto d : t.dims) if (d < 0) throw std::runtime_error("onnx: initializer " + name + " has a negative dimension");
+    if (esz && t.raw.size() != t.numel() * esz)
+        throw std::runtime_error("onnx: initializer " + name + " holds " + std::to_string(t.raw.size()) + " bytes, its dims need " +
+                                 std::to_string(t.numel() * esz));
 }
 
-inline std::string parse_value_info_name(pb::Reader r) {
-    while (r.ok()) { int wt; uint64_t v; pb::Reader s{nullptr, nullptr}; if (r.next(wt, v, s) == 1) return s.str(); }
-    return "";
+// ValueInfoProto: name = 1, type = 2 -> TypeProto.tensor_type = 1 -> {elem_type = 1, shape = 2 -> dim = 1 -> {dim_value = 1, dim_param = 2}}
+inline OnnxValueInfo parse_value_info(pb::Reader r) {
+    OnnxValueInfo out;
+    while (r.ok()) {
+        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        const int f = r.next(wt, v, s);
+        if (f == 1 && wt == 2) out.name = s.str();
+        else if (f == 2 && wt == 2) {
+            pb::Reader ty = s;
+            while (ty.ok()) {
+                pb::Reader tt{nullptr, nullptr};
+                if (ty.next(wt, v, tt) != 1 || wt != 2) continue;
+                while (tt.ok()) {
+                    pb::Reader sh{nullptr, nullptr};
+                    const int f3 = tt.next(wt, v, sh);
+                    if (f3 == 1 && wt == 0) out.elem_type = (int)v;
+                    else if (f3 == 2 && wt == 2) {
+                        while (sh.ok()) {
+                            pb::Reader dm{nullptr, nullptr};
+                            if (sh.next(wt, v, dm) != 1 || wt != 2) continue;
+                            int64_t dv = -1;
+                            while (dm.ok()) { pb::Reader q{nullptr, nullptr}; uint64_t vv; int w2; if (dm.next(w2, vv, q) == 1 && w2 == 0) dv = (int64_t)vv; }
+                            out.dims.push_back(dv);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return out;
+}
+
+inline void parse_attr(pb::Reader r, std::string& name, OnnxAttr& a) {
+    while (r.ok()) {
+        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        const int f = r.next(wt, v, s);
+        if (f == 1 && wt == 2) name = s.str();
+        else if (f == 2 && wt == 5) { uint32_t u = (uint32_t)v; memcpy(&a.f, &u, 4); }
+        else if (f == 3 && wt == 0) a.i = (int64_t)v;
+        else if (f == 4 && wt == 2) a.s = s.str();
+        else if (f == 8) { if (wt == 2) { while (s.ok()) a.ints.push_back((int64_t)s.varint()); } else a.ints.push_back((int64_t)v); }
+    }
+}
+
+inline OnnxNode parse_node(pb::Reader r) {
+    OnnxNode n;
+    while (r.ok()) {
+        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        const int f = r.next(wt, v, s);
+        if (wt != 2) continue;
+        if (f == 1) n.in.push_back(s.str());
+        else if (f == 2) n.out.push_back(s.str());
+        else if (f == 3) n.name = s.str();
+        else if (f == 4) n.op = s.str();
+        else if (f == 5) { std::string k; OnnxAttr a; parse_attr(s, k, a); n.attr.emplace(std::move(k), std::move(a)); }
+    }
+    return n;
 }
 
 inline OnnxFile load_onnx(const std::string& path) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f.is_open()) throw std::runtime_error("Failed to open file: " + path);
-    std::vector<uint8_t> buf((size_t)f.tellg());
+    const std::streamoff fsize = f.tellg();
+    if (fsize < 0) throw std::runtime_error("Failed to size file: " + path);
+    std::vector<uint8_t> buf((size_t)fsize);
     f.seekg(0); f.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size());
     OnnxFile out;
     pb::Reader r{buf.data(), buf.data() + buf.size()};
@@ -93,14 +176,16 @@ inline OnnxFile load_onnx(const std::string& path) {
             while (g.ok()) {
                 pb::Reader s2{nullptr, nullptr};
                 int f2 = g.next(wt, v, s2);
-                if (f2 == 1) out.n_nodes++;
+                if (f2 != 1 && f2 != 5 && f2 != 11 && f2 != 12) continue;
+                if (wt != 2) throw std::runtime_error("onnx: graph field " + std::to_string(f2) + " with wire type " + std::to_string(wt));
+                if (f2 == 1) { out.n_nodes++; out.nodes.push_back(parse_node(s2)); }
                 else if (f2 == 5) { std::string name; OnnxTensor t; parse_tensor(s2, name, t); out.initializers.emplace(std::move(name), std::move(t)); }
-                else if (f2 == 11) out.inputs.push_back(parse_value_info_name(s2));
-                else if (f2 == 12) out.outputs.push_back(parse_value_info_name(s2));
+                else if (f2 == 11) { out.input_info.push_back(parse_value_info(s2)); out.inputs.push_back(out.input_info.back().name); }
+                else if (f2 == 12) { out.output_info.push_back(parse_value_info(s2)); out.outputs.push_back(out.output_info.back().name); }
             }
         } else if (fno == 14 && wt == 2) {               // metadata_props
             std::string k, val; pb::Reader m = s;
-            while (m.ok()) { pb::Reader s2{nullptr, nullptr}; int f2 = m.next(wt, v, s2); if (f2 == 1) k = s2.str(); else if (f2 == 2) val = s2.str(); }
+            while (m.ok()) { pb::Reader s2{nullptr, nullptr}; int f2 = m.next(wt, v, s2); if (wt != 2) continue; if (f2 == 1) k = s2.str(); else if (f2 == 2) val = s2.str(); }
             out.metadata[k] = val;
         }
     }

@@ -94,6 +94,16 @@ TextToSpeech::TextToSpeech(const Config& cfgs, stc_handle* engine) : cfgs_(cfgs)
 }
 TextToSpeech::~TextToSpeech() { stc_destroy(engine_); }
 
+// The C ABI takes bare pointers: a voice-style file with other dims than the graphs' (or a style batch that does not match
+// the texts) must be rejected here, where ONNX Runtime would raise a shape error (cpp/helper.cpp:519, 552, 643)
+void TextToSpeech::checkStyle(const Style& style, int bsz) const {
+    const auto& t = style.getTtlShape(); const auto& d = style.getDpShape();
+    if (t.size() != 3 || d.size() != 3) throw std::runtime_error("Got invalid dimensions for input: style tensors must have rank 3");
+    if ((int64_t)style.getTtlData().size() != t[0] * t[1] * t[2] || (int64_t)style.getDpData().size() != d[0] * d[1] * d[2])
+        throw std::runtime_error("Got invalid dimensions for input: style data does not match its dims");
+    if (stc_validate_style(engine_, bsz, t.data(), d.data()) != STC_OK) raise(engine_, "voice style");
+}
+
 void TextToSpeech::textToIds(const std::vector<std::string>& texts, const std::vector<std::string>& langs, std::vector<int64_t>& ids,
                              std::vector<float>& mask, int64_t& T) const {
     if (texts.size() != langs.size()) throw std::runtime_error("Number of texts must match number of languages");
@@ -108,6 +118,7 @@ TextToSpeech::SynthesisResult TextToSpeech::_infer(const std::vector<std::string
                                                    const Style& style, int total_step, float speed) {
     int bsz = (int)text_list.size();
     if (bsz != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
+    checkStyle(style, bsz);
     std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;
     textToIds(text_list, lang_list, ids, mask, T);
     const int cs = geo_.chunk_size;
@@ -163,6 +174,7 @@ std::vector<TextToSpeech::Utterance> TextToSpeech::many(const std::vector<std::s
                                                         const Style& style, int total_step, float speed, int max_batch) {
     const int n = (int)text_list.size();
     if (n != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
+    checkStyle(style, n);
     std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;
     textToIds(text_list, lang_list, ids, mask, T);
     std::vector<int> tok(n), order(n);

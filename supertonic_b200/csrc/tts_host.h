@@ -85,6 +85,7 @@ private:
                            int total_step, float speed);
     void textToIds(const std::vector<std::string>& texts, const std::vector<std::string>& langs, std::vector<int64_t>& ids,
                    std::vector<float>& mask, int64_t& T) const;
+    void checkStyle(const Style& style, int bsz) const;
     Config cfgs_;
     stc_handle* engine_;
     stc_config geo_{};
