@@ -147,6 +147,30 @@ int stc_synthesize_packed_async(stc_handle* h, const int64_t* text_ids, const fl
                                 const float* style_dp, int B, int T, int total_step, float speed, uint64_t seed,
                                 float* wav_out_pinned, int64_t wav_cap, int64_t* wav_offsets_out, float* duration_out,
                                 int64_t* wav_lengths_out);
+/* Output options of the packed entry point below (long-form pipeline):
+ *   pcm16       1: samples are int16, quantised on the device exactly like writeWavFile — (int16_t)(max(-1, min(1, x)) * 32767),
+ *               the cast truncating toward zero (cpp/helper.cpp:985-988) — which halves the device->host traffic; 0: float32.
+ *   gap_samples zeros written after every utterance but the last: TextToSpeech::call joins the chunks of a long text with
+ *               (int)(silence_duration * sample_rate) zeros between the UNTRIMMED chunk waveforms (cpp/helper.cpp:706-714); with the
+ *               chunks of one text as the batch, `out` is that joined waveform.
+ *   noise_index optional HOST int64[B] (NULL: b): utterance b draws the device noise stream (seed, noise_index[b]) instead of (seed, b),
+ *               so a request batch split over several calls or GPUs gets, utterance by utterance, the noise one call would give it. */
+typedef struct stc_out_opts {
+    int32_t pcm16;
+    int64_t gap_samples;
+    const int64_t* noise_index;
+} stc_out_opts;
+
+/* stc_synthesize_packed with output options. `out` holds out_cap ELEMENTS (float or int16_t per opts->pcm16; opts == NULL: plain
+ * float32). Utterance b's frames_b * cs samples start at wav_offsets_out[b]; wav_offsets_out[B] is the total element count (gaps
+ * included, none after the last utterance). async_copy != 0: as stc_synthesize_packed_async (`out` page-locked, valid after
+ * stc_wait, no injected noise). */
+int stc_synthesize_packed_ex(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
+                             const float* style_dp, int B, int T, int total_step, float speed,
+                             const float* noise, int64_t noise_ld, uint64_t seed, const stc_out_opts* opts,
+                             void* out, int64_t out_cap, int64_t* wav_offsets_out, float* duration_out,
+                             int64_t* wav_lengths_out, int async_copy);
+
 /* Waits for every outstanding asynchronous call of the handle; reports their errors. */
 int stc_wait(stc_handle* h);
 
@@ -224,6 +248,10 @@ int stc_debug_mlp(stc_handle* h, int M, int iters, float* ms_fused, float* ms_un
  * kernel: mean device time of each writing split-bf16 operands, and the max-abs difference of their fp32 outputs. */
 int stc_debug_dwconv(stc_handle* h, int rows, int C, int K, int dil, int causal, int B, int rt, int iters, float* ms_slide,
                      float* ms_tile, float* max_abs_diff);
+
+/* The device PCM16 quantiser of stc_out_opts.pcm16 on n caller-provided float samples (known-answer tests against the reference's
+ * writeWavFile, cpp/helper.cpp:985-988). */
+int stc_debug_pcm16(stc_handle* h, const float* samples, int64_t n, int16_t* out);
 
 #ifdef __cplusplus
 }

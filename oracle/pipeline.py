@@ -56,3 +56,50 @@ class OraclePipeline(host_ref.ReferenceTTS):
 
     def style(self, names):
         return load_style([os.path.join(self.asset_root, "voice_styles", n + ".json") for n in names])
+
+
+def ort_version():
+    """onnxruntime's version if it can be imported here, else None. (It never could in this environment: no wheel, no network —
+    DESIGN.md §2. The probe exists so that the day it can, the TRUE reference runtime becomes the oracle and the CPU baseline.)"""
+    try:
+        import onnxruntime as ort           # noqa: F401
+        return ort.__version__
+    except Exception:                       # noqa: BLE001
+        return None
+
+
+class OrtPipeline(host_ref.ReferenceTTS):
+    """The reference's own runtime: the four graphs through ONNX Runtime's CPU execution provider, orchestrated by the restated host
+    arithmetic (the same call sites as py/helper.py:190-214 / cpp/helper.cpp:519, 552, 643, 668). Used as the primary oracle and CPU
+    baseline whenever `import onnxruntime` succeeds (SURVEY.md §8c "closing the gap")."""
+
+    def __init__(self, asset_root: str, threads: Optional[int] = None):
+        import onnxruntime as ort
+        onnx_dir = os.path.join(asset_root, "onnx")
+        cfg = json.load(open(os.path.join(onnx_dir, "tts.json")))
+        indexer = json.load(open(os.path.join(onnx_dir, "unicode_indexer.json")))
+        so = ort.SessionOptions()
+        if threads:
+            so.intra_op_num_threads = int(threads)
+        self.sessions = {k: ort.InferenceSession(os.path.join(onnx_dir, f + ".onnx"), so, providers=["CPUExecutionProvider"])
+                         for k, f in (("dp", "duration_predictor"), ("te", "text_encoder"), ("ve", "vector_estimator"), ("voc", "vocoder"))}
+
+        def runner(key):
+            sess = self.sessions[key]
+            names = {i.name for i in sess.get_inputs()}
+            return lambda feeds: np.asarray(sess.run(None, {k: v for k, v in feeds.items() if k in names})[0], np.float32)
+        super().__init__(cfg, indexer, runner("dp"), runner("te"), runner("ve"), runner("voc"))
+        self.asset_root = asset_root
+
+    def style(self, names):
+        return load_style([os.path.join(self.asset_root, "voice_styles", n + ".json") for n in names])
+
+
+def best_oracle(asset_root: str):
+    """(pipeline, kind): ONNX Runtime when it is importable ("ort"), else the torch-CPU interpreter ("port")."""
+    if ort_version():
+        try:
+            return OrtPipeline(asset_root), "ort"
+        except Exception:                   # noqa: BLE001  (e.g. an ORT build that rejects the surrogate graphs' opset)
+            pass
+    return OraclePipeline(asset_root), "port"

@@ -24,6 +24,10 @@ PREC_DEFAULT, PREC_BF16X3, PREC_FP32_SIMT = 0, 1, 2
 ERR_CAPACITY = -5
 
 
+class StcOutOpts(C.Structure):
+    _fields_ = [("pcm16", C.c_int32), ("gap_samples", C.c_int64), ("noise_index", C.c_void_p)]
+
+
 class StcConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "sample_rate", "base_chunk_size", "chunk_compress_factor", "latent_dim", "latent_channels", "chunk_size",
@@ -47,6 +51,8 @@ _SIGS = {
     "stc_synthesize_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_synthesize_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stc_synthesize_packed_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp, _vp]),
+    "stc_synthesize_packed_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
+    "stc_debug_pcm16": (_i, [_vp, _vp, _i64, _vp]),
     "stc_wait": (_i, [_vp]),
     "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_pinned_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
@@ -347,6 +353,57 @@ class Engine:
             fo = np.concatenate([[0], np.cumsum(frames)])
             res["latent"] = [lat[fo[b]:fo[b + 1]] for b in range(B)]
         return res
+
+    def synthesize_joined(self, text_ids, text_mask, style_ttl, style_dp, total_step: int, speed: float = 1.05,
+                          noise: Optional[np.ndarray] = None, seed: int = 0, pcm16: bool = False, gap_samples: int = 0,
+                          pinned=False, wait: bool = True, noise_index=None):
+        """stc_synthesize_packed_ex: the batch as ONE output array — utterance b's untrimmed frames_b*cs samples at offsets[b], with
+        `gap_samples` zeros after every utterance but the last (TextToSpeech::call's silence join, cpp/helper.cpp:706-714), as
+        float32 or, with pcm16=True, int16 quantised on the device like writeWavFile (cpp/helper.cpp:985-988).
+        noise_index (int64[B], optional): utterance b draws the device noise stream (seed, noise_index[b]) instead of (seed, b) — a
+        request split over several calls / GPUs then gets the noise one call would give it.
+        Returns dict(out=array[total], offsets[B+1], duration[B], wav_lengths[B], frames[B])."""
+        ids, m = _cf(text_ids, np.int64), _cf(text_mask, np.float32)
+        sttl, sdp = _cf(style_ttl, np.float32), _cf(style_dp, np.float32)
+        B, T = ids.shape
+        self._check(B, T, ttl=sttl, dp=sdp, mask=m)
+        cs = self.cfg.chunk_size
+        nz, nld = None, 0
+        if noise is not None:
+            nz = _cf(noise, np.float32)
+            if nz.ndim != 3 or nz.shape[:2] != (B, self.cfg.latent_channels):
+                raise StcError(-1, f"Got invalid dimensions for input: noise {nz.shape}")
+            nld = nz.shape[2]
+        dt = np.int16 if pcm16 else np.float32
+        ni = None if noise_index is None else _cf(noise_index, np.int64)
+        if ni is not None and ni.shape != (B,):
+            raise StcError(-1, f"noise_index must have shape ({B},)")
+        opts = StcOutOpts(int(bool(pcm16)), int(gap_samples), None if ni is None else ni.ctypes.data)
+        cap = int(m.sum() * 0.12 * self.cfg.sample_rate) + (B + 8) * cs + (B - 1) * int(gap_samples)
+        dur = np.empty((B,), np.float32); wl = np.empty((B,), np.int64); off = np.zeros((B + 1,), np.int64)
+        use_async = (not wait) and bool(pinned) and noise is None
+        pname = pinned if isinstance(pinned, str) else "wav_joined"
+        for _ in range(2):
+            out = self.pinned(pname, cap, dt) if pinned else np.empty((cap,), dt)
+            rc = lib.stc_synthesize_packed_ex(self._h, _ptr(ids), _ptr(m), _ptr(sttl), _ptr(sdp), B, T, int(total_step), float(speed),
+                                              _ptr(nz), nld, seed, C.byref(opts), _ptr(out), cap, _ptr(off), _ptr(dur), _ptr(wl),
+                                              int(use_async))
+            if rc == ERR_CAPACITY and off[B] > cap:
+                cap = int(off[B])
+                continue
+            self._chk(rc)
+            if use_async:
+                self._pending = getattr(self, "_pending", set()) | {pname}
+            break
+        gaps = np.concatenate([np.full(B - 1, int(gap_samples), np.int64), [0]])
+        frames = ((off[1:] - off[:-1] - gaps) // cs).astype(np.int64)
+        return dict(out=out[:int(off[B])], offsets=off, duration=dur, wav_lengths=wl, frames=frames)
+
+    def debug_pcm16(self, samples) -> np.ndarray:
+        x = _cf(samples, np.float32).reshape(-1)
+        out = np.empty(x.shape, np.int16)
+        self._chk(lib.stc_debug_pcm16(self._h, _ptr(x), x.size, _ptr(out)))
+        return out
 
     def wait(self):
         """Deliver every outstanding wait=False call (their waveform views hold data afterwards)."""

@@ -1,0 +1,173 @@
+// Depthwise conv1d (+bias) -> LayerNorm for LONG chains (the vocoder: 27.7k rows x 512 channels per launch, HBM-resident):
+// the bandwidth kernel of the path (replaces ORT's Conv(group=C) -> Transpose -> LayerNormalization of every vocoder ConvNeXt
+// block, vocoder.onnx run at reference cpp/helper.cpp:668).
+//
+// Same decomposition as dwconv_ln_slide_kernel (kernels.cuh): a thread owns four channels and walks a chain of rows
+// r, r + dil, r + 2 dil, ... keeping the K - 1 previous rows of the chain in registers, so every input row is read from global memory
+// once per chain, coalesced; rows arrive through a per-thread cp.async ring (RD iterations in flight per thread, no barrier: a thread
+// reads back only what it copied). What changed, because that kernel was issue bound at 40 % of the HBM rate (586 warp instructions
+// per 512-channel row, two shuffle + barrier LayerNorm passes per four rows, IPC 0.47):
+//   * U = K - 1 rows per iteration: the register window turns over completely, so no window shifting (24 MOVs per iteration before),
+//     and one barrier serves 6 rows (K = 7) instead of two barriers per 4;
+//   * ONE LayerNorm pass: sum and sum of squares of all U rows go through a single reduce-scatter butterfly (16 shuffles for the 2 U
+//     values) and one barrier on a double-buffered scratch; variance = E[y^2] - mean^2 in fp32 (y is a convolution output with
+//     |mean| ~ std: relative error ~1e-6, far below the 2e-5 the cross-check against the two-pass tile kernel allows);
+//   * normalisation folded into one FMA per element (scale = inv * g, shift = beta - mean * scale), rsqrt + one Newton step;
+//   * sequence bookkeeping once per iteration when the whole iteration lies inside one sequence (the common case).
+#pragma once
+#include "kernels.cuh"
+
+namespace stc {
+
+constexpr int CHAIN_RD = 3;        // ring depth in iterations
+
+template <int K> struct ChainSmem {
+    static constexpr int U = K - 1;
+    static constexpr size_t RING = (size_t)(CHAIN_RD + 1) * U * 128 * 16;
+    static constexpr size_t BYTES = RING + 2 * 4 * 16 * 4 * sizeof(float);      // + red[2][groups <= 4][16][NW <= 4]
+};
+
+template <int NW, int K, typename Out>
+__global__ void __launch_bounds__(128)
+dwconv_ln_chain_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
+                       const float* __restrict__ g, const float* __restrict__ beta, Out out,
+                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
+    pdl_trigger(); pdl_wait();
+    constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = K - 1;
+    static_assert(2 * U <= 16, "two statistics per row through a 16-value butterfly");
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    float4* ring = reinterpret_cast<float4*>(chain_smem);                               // [slot][u][thread]
+    float* red = reinterpret_cast<float*>(chain_smem + ChainSmem<K>::RING);             // [2][GPB][16][NW]
+    const int grp = threadIdx.x / GT, t = threadIdx.x % GT, wig = t >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * GPB + grp;
+    const int r_first = (chain / dil) * (RT * dil) + chain % dil;
+    if (r_first >= rows) return;                       // the whole group leaves (barriers are per group)
+    const float* xc = x + 4 * t;
+    float2 w[K][2];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wT + (size_t)k * C) + t);
+        w[k][0] = make_float2(v.x, v.y); w[k][1] = make_float2(v.z, v.w);
+    }
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(wb) + t);
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + t), bv = __ldg(reinterpret_cast<const float4*>(beta) + t);
+    const int rw0 = r_first - pad_left;                // window slot j of output i holds row rw0 + (i + j) * dil
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 16u;
+    auto fetch = [&](int it) {                         // rows of iteration `it` -> ring slot it % (RD + 1); always one commit group
+        if (it * U < RT) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = rw0 + (U + it * U + u) * dil;
+                const bool ok = r >= 0 && r < rows;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + (uint32_t)((it % (CHAIN_RD + 1)) * U + u) * 2048u),
+                             "l"(ok ? xc + (size_t)r * C : xc), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int it = 0; it < CHAIN_RD; ++it) fetch(it);
+    float4 win[U], cur[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const int r = rw0 + j * dil;
+        win[j] = (r >= 0 && r < rows) ? *reinterpret_cast<const float4*>(xc + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
+    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+    const float inv_c = 1.0f / (float)C;
+
+    for (int it = 0; it * U < RT; ++it) {
+        const int i0 = it * U;
+        if (r_first + i0 * dil >= rows) break;         // uniform in the group
+        asm volatile("cp.async.wait_group %0;" ::"n"(CHAIN_RD - 1) : "memory");
+        {
+            const int slot = it % (CHAIN_RD + 1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = ring[(slot * U + u) * 128 + threadIdx.x];
+        }
+        fetch(it + CHAIN_RD);                          // into the slot consumed one iteration ago
+        // rows of this iteration: r_u = r_first + (i0 + u) * dil; taps of r_u are window slots u .. u + K - 1 (win, then cur)
+        float2 y[U][2];
+        bool pad[U];
+        const int r_lastrow = r_first + (i0 + U - 1) * dil;
+        const bool interior = b >= 0 && (r_first + i0 * dil) - pad_left >= lo && r_lastrow - pad_left + (K - 1) * dil < hi && r_lastrow < hi;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            y[u][0] = make_float2(bias.x, bias.y); y[u][1] = make_float2(bias.z, bias.w);
+            pad[u] = false;
+            auto slot = [&](int j) -> const float4& { return j < U ? win[j] : cur[j - U]; };
+            if (interior) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4& s = slot(u + k);
+                    y[u][0] = __ffma2_rn(w[k][0], make_float2(s.x, s.y), y[u][0]);
+                    y[u][1] = __ffma2_rn(w[k][1], make_float2(s.z, s.w), y[u][1]);
+                }
+            } else {
+                const int r = r_first + (i0 + u) * dil;
+                if (b >= 0 && r >= hi) {               // next sequence (empty ones are skipped); past the last one: padding
+                    do ++b; while (b < B && r >= __ldg(off + b + 1));
+                    if (b >= B) b = -1; else { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+                }
+                pad[u] = b < 0;
+                if (b < 0) y[u][0] = y[u][1] = make_float2(0.f, 0.f);            // bucket padding row: keep it finite
+                else {
+                    const int first = r - pad_left;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int rk = first + k * dil;
+                        if (rk >= lo && rk < hi) {     // taps outside [lo, hi) are the zero padding of the sequence
+                            const float4& s = slot(u + k);
+                            y[u][0] = __ffma2_rn(w[k][0], make_float2(s.x, s.y), y[u][0]);
+                            y[u][1] = __ffma2_rn(w[k][1], make_float2(s.z, s.w), y[u][1]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) win[j] = cur[j];   // (renamed away by the unrolled loop body: cur is reloaded next iteration)
+        // ---- LayerNorm statistics: v[2u] = sum, v[2u+1] = sum of squares of this thread's four channels of row u
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float2 s2 = __fadd2_rn(y[u][0], y[u][1]);
+            const float2 q2 = __ffma2_rn(y[u][0], y[u][0], __fmul2_rn(y[u][1], y[u][1]));
+            v[2 * u] = s2.x + s2.y; v[2 * u + 1] = q2.x + q2.y;
+        }
+#pragma unroll
+        for (int i = 2 * U; i < 16; ++i) v[i] = 0.f;
+        // reduce-scatter butterfly over the warp: lane l ends with the warp total of value l >> 1
+        float a8[8], a4[4], a2[2], a1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a8[i] = (h16 ? v[8 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[8 + i], 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a4[i] = (h8 ? a8[4 + i] : a8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a8[i] : a8[4 + i], 8);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a2[i] = (h4 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? a4[i] : a4[2 + i], 4);
+        a1 = (h2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? a2[0] : a2[1], 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        float* rbuf = red + ((it & 1) * GPB + grp) * 16 * NW;
+        if ((lane & 1) == 0 && (lane >> 1) < 2 * U) rbuf[(lane >> 1) * NW + wig] = a1;
+        group_barrier<NW>(grp);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = r_first + (i0 + u) * dil;
+            if (r >= rows) continue;
+            const float mean = group_total<NW>(rbuf + (2 * u) * NW) * inv_c;
+            const float var = fmaxf(group_total<NW>(rbuf + (2 * u + 1) * NW) * inv_c - mean * mean, 0.f) + eps;
+            float inv = rsqrtf(var);
+            inv = inv * (1.5f - 0.5f * var * inv * inv);                          // one Newton step: full fp32 accuracy
+            const float2 s0 = make_float2(gv.x * inv, gv.y * inv), s1 = make_float2(gv.z * inv, gv.w * inv);
+            const float2 nm = make_float2(-mean, -mean);
+            const float2 o0 = __ffma2_rn(__fadd2_rn(y[u][0], nm), s0, make_float2(bv.x, bv.y));
+            const float2 o1 = __ffma2_rn(__fadd2_rn(y[u][1], nm), s1, make_float2(bv.z, bv.w));
+            const float o[4] = {pad[u] ? 0.f : o0.x, pad[u] ? 0.f : o0.y, pad[u] ? 0.f : o1.x, pad[u] ? 0.f : o1.y};
+            store_row_vec<4>(out, (size_t)r * C + 4 * t, o);
+        }
+    }
+}
+
+}  // namespace stc

@@ -15,10 +15,11 @@ namespace stc {
 
 #define STC_DEVINL __device__ __forceinline__
 
-// Programmatic dependent launch: every kernel is launched with programmatic stream serialization, lets its successor start
-// (launch latency, prologue) right away, and waits for its predecessor's writes itself before touching global memory.
-STC_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-STC_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Where a kernel would release its dependents / wait for its predecessor under programmatic dependent launch. PDL was built and
+// measured twice on B200 (slower for the throughput path both times: model.cu launch_k) and removed; the markers stay as no-ops so
+// that the kernels document where those points are.
+STC_DEVINL void pdl_trigger() {}
+STC_DEVINL void pdl_wait() {}
 
 template <typename T> STC_DEVINL T t_erf(T x);
 template <> STC_DEVINL float t_erf<float>(float x) { return erff(x); }
@@ -428,23 +429,11 @@ template <int NW> STC_DEVINL float group_total(const float* p) {     // sum of t
 // keeps in flight — the long vocoder chains are bound by bytes in flight, the short VE / TE chains (one or two iterations)
 // by latency and keep the register prefetch.
 constexpr int RING_D = 4;
-// RED: the kernel also FINISHES the previous ConvNeXt block (what mlp_reduce_kernel / mlp_reduce_post_kernel do): the row it
-// "loads" is  x_new = ((sum_s partial_s + b2) * gamma + x) * mask  [then (x_new + add_vec) * mask], computed from the fused MLP's
-// hidden-slice partials in the same order and with the same expressions as those kernels (bit-identical); halo rows are
-// recomputed by the neighbouring chains, the chain that owns a row writes it to x_out — a buffer OTHER than x, because the
-// neighbours still read the old x of their halo rows. One launch instead of two per ConvNeXt -> ConvNeXt transition.
-struct SlideRed {
-    const float* partial = nullptr; size_t slice = 0; int nslice = 0;
-    const float* b2 = nullptr; const float* gamma = nullptr; const float* mask = nullptr; const float* add_vec = nullptr;
-    float* x_out = nullptr;
-    int jc = 0;                 // window slot of an output row's own input row: pad_left / dil
-};
-template <int NW, int K, bool RING, typename Out, bool RED = false>
+template <int NW, int K, bool RING, typename Out>
 __global__ void __launch_bounds__(128)
 dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                        const float* __restrict__ g, const float* __restrict__ beta, Out out,
-                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT, const SlideRed rd) {
-    static_assert(!(RED && RING), "the reducing form uses the register prefetch");
+                       int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
     pdl_trigger(); pdl_wait();
     constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = 4;
     __shared__ __align__(16) float red[2][GPB][U][NW];
@@ -461,31 +450,9 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
     }
     const float4 bias = __ldg(reinterpret_cast<const float4*>(wb) + t);
     const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + t), bv = __ldg(reinterpret_cast<const float4*>(beta) + t);
-    float4 rb2, rgm, rav;
-    if constexpr (RED) {
-        rb2 = __ldg(reinterpret_cast<const float4*>(rd.b2) + t); rgm = __ldg(reinterpret_cast<const float4*>(rd.gamma) + t);
-        rav = rd.add_vec ? __ldg(reinterpret_cast<const float4*>(rd.add_vec) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     auto load_row = [&](int r) -> float4 {
         if (!(r >= 0 && r < rows)) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (!RED) return *reinterpret_cast<const float4*>(xc + (size_t)r * C);
-        else {
-            const size_t i = (size_t)r * C + 4 * t;
-            float4 acc = *reinterpret_cast<const float4*>(rd.partial + i);
-#pragma unroll 4
-            for (int sl = 1; sl < rd.nslice; ++sl) {
-                const float4 v = *reinterpret_cast<const float4*>(rd.partial + sl * rd.slice + i);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            const float4 res = *reinterpret_cast<const float4*>(x + i);
-            const float mk = rd.mask ? __ldg(rd.mask + r) : 1.f;
-            acc.x = ((acc.x + rb2.x) * rgm.x + res.x) * mk; acc.y = ((acc.y + rb2.y) * rgm.y + res.y) * mk;
-            acc.z = ((acc.z + rb2.z) * rgm.z + res.z) * mk; acc.w = ((acc.w + rb2.w) * rgm.w + res.w) * mk;
-            if (rd.add_vec) {
-                acc.x = (acc.x + rav.x) * mk; acc.y = (acc.y + rav.y) * mk; acc.z = (acc.z + rav.z) * mk; acc.w = (acc.w + rav.w) * mk;
-            }
-            return acc;
-        }
+        return *reinterpret_cast<const float4*>(xc + (size_t)r * C);
     };
     const int rw0 = r_first - pad_left;                // window slot j of output i holds row rw0 + (i + j) * dil
     float4 win[K - 1 + U], nxt[RING ? 1 : U];
@@ -541,10 +508,6 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
                 if (b >= B) b = -1; else { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
             }
             pad[u] = b < 0;
-            if constexpr (RED) {                       // this chain owns row r of the residual stream
-                // same-padded (jc = (K-1)/2) or causal (jc = K-1) convolutions only: static register indices
-                if (r < rows) *reinterpret_cast<float4*>(rd.x_out + (size_t)r * C + 4 * t) = rd.jc == K - 1 ? win[u + K - 1] : win[u + (K - 1) / 2];
-            }
             y[u][0] = make_float2(bias.x, bias.y); y[u][1] = make_float2(bias.z, bias.w);
             const int first = r - pad_left;
             if (b < 0) {                               // bucket padding row: keep it finite
@@ -830,7 +793,7 @@ STC_DEVINL uint32_t mix32(uint64_t z) {
 }
 __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, const uint64_t* __restrict__ seed_p,
                                    const float* __restrict__ mask, float* __restrict__ x, int rows,
-                                   const int* __restrict__ off, int B, int D) {
+                                   const int* __restrict__ off, int B, int D, const int* __restrict__ noise_index) {
     pdl_trigger(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * D) return;
@@ -842,7 +805,9 @@ __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, 
     float v;
     if (noise) v = noise[((size_t)b * D + d) * ld + l];
     else {
-        uint64_t key = __ldg(seed_p) * 0x9E3779B97F4A7C15ull + ((uint64_t)b << 40) + ((uint64_t)d << 24) + (uint64_t)l;
+        // utterance b draws stream noise_index[b] (default b): a request split over several calls / GPUs gets the noise of one call
+        const uint64_t ub = noise_index ? (uint64_t)(uint32_t)__ldg(noise_index + b) : (uint64_t)b;
+        uint64_t key = __ldg(seed_p) * 0x9E3779B97F4A7C15ull + (ub << 40) + ((uint64_t)d << 24) + (uint64_t)l;
         float u1 = (mix32(key) + 1.0f) * (1.0f / 4294967808.0f);          // (0,1]
         float u2 = mix32(key ^ 0xD1B54A32D192ED03ull) * (1.0f / 4294967296.0f);
         v = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
@@ -935,6 +900,48 @@ __global__ void dur_post_kernel(float* __restrict__ dur, int64_t* __restrict__ w
     float d = __fdiv_rn(dur[b], speed);
     dur[b] = d;
     wav_len[b] = (int64_t)__fmul_rn(d, (float)sr);
+}
+
+// ---- waveform output packing: silence insert + PCM16 quantise on the device ----------------------------------------------
+// The vocoder leaves utterance b's samples at src[off[b]*cs ...) (packed frames). This writes them to dst with `gap` zeros after every
+// utterance but the last — what TextToSpeech::call does on the host when it joins the chunks of a long text (cpp/helper.cpp:706-714) —
+// and, for PCM16, quantised exactly like writeWavFile (cpp/helper.cpp:985-988): (int16_t)(max(-1, min(1, x)) * 32767), the cast
+// truncating toward zero. One block per latent frame (cs samples, 8 per thread step).
+STC_DEVINL int16_t pcm16_of(float v) {
+    const float c = fmaxf(-1.0f, fminf(1.0f, v));            // std::max(-1.0f, std::min(1.0f, sample)); NaN -> -1 on both sides
+    return (int16_t)__float2int_rz(__fmul_rn(c, 32767.0f));
+}
+template <typename TO> STC_DEVINL TO wav_out_of(float v);
+template <> STC_DEVINL float wav_out_of<float>(float v) { return v; }
+template <> STC_DEVINL int16_t wav_out_of<int16_t>(float v) { return pcm16_of(v); }
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+wav_pack_kernel(const float* __restrict__ src, TO* __restrict__ dst, const int* __restrict__ off, int B, int cs, long long gap) {
+    pdl_trigger(); pdl_wait();
+    const int r = blockIdx.x;
+    const int b = find_seq(off, B, r);
+    if (b < 0) return;                                         // bucket padding frame
+    const float* s = src + (size_t)r * cs;
+    TO* d = dst + (size_t)r * cs + (size_t)b * gap;
+    const bool vec = (reinterpret_cast<uintptr_t>(d) & 15) == 0 && cs % 8 == 0;
+    if (vec) {
+        for (int i = threadIdx.x * 8; i < cs; i += blockDim.x * 8) {
+            const float4 v0 = *reinterpret_cast<const float4*>(s + i), v1 = *reinterpret_cast<const float4*>(s + i + 4);
+            if constexpr (sizeof(TO) == 2) {
+                const int16_t q[8] = {pcm16_of(v0.x), pcm16_of(v0.y), pcm16_of(v0.z), pcm16_of(v0.w), pcm16_of(v1.x), pcm16_of(v1.y), pcm16_of(v1.z), pcm16_of(v1.w)};
+                *reinterpret_cast<uint4*>(d + i) = *reinterpret_cast<const uint4*>(q);
+            } else {
+                *reinterpret_cast<float4*>(d + i) = v0; *reinterpret_cast<float4*>(d + i + 4) = v1;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < cs; i += blockDim.x) d[i] = wav_out_of<TO>(s[i]);
+    }
+    if (gap > 0 && b + 1 < B && r + 1 == __ldg(off + b + 1)) {  // the utterance's last frame also writes the silence behind it
+        TO* z = d + cs;
+        for (long long i = threadIdx.x; i < gap; i += blockDim.x) z[i] = (TO)0;
+    }
 }
 
 // sinusoidal time embedding: t = cur/tot; out[b] = [sin(t*f), cos(t*f)]

@@ -42,6 +42,20 @@ struct StreamParams {
     long long* trace;       // debug (stc_debug_mlp with STC_MLP_TRACE=1): clock64() stamps of CTA 0
 };
 
+// mbarrier wait with a bound: a protocol error in this kernel must surface as a launch failure, not as a hung GPU
+// (try_wait suspends the thread for a hardware-defined time slice per attempt, so the bound is seconds, never reached otherwise)
+STC_DEVINL void mbar_wait_b(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spins > (1u << 24)) __trap();
+    }
+}
+
 // hidden range of slice c out of s: 64-unit blocks [c*16/s, (c+1)*16/s)
 STC_DEVINL void stream_range(int c, int s, int& u0, int& u1) { u0 = (c * 16) / s; u1 = ((c + 1) * 16) / s; }
 
@@ -121,9 +135,9 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
             load_a(0);
             stream_units(nchunks, nblk64, [&](int kind, int c, int a, int b) {
                 const int s = u % SLOTS;
-                mbar_wait(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
+                mbar_wait_b(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
                 const uint32_t dst = smem_base + OFF_RING + s * UNIT, fb = full_bar(s);
-                if (p.trace && blockIdx.x == 0 && u < 24) p.trace[40 + u] = clock64();
+                if (p.trace && blockIdx.x == 0 && u < 16) p.trace[40 + u] = clock64();
                 if (kind == 0) {            // W1[hidden rows of chunk c, K block a of C]
                     const int w = chunk_w(c), row = h0 + c * 128;
                     mbar_expect_tx(fb, 2 * w * BK * 2);
@@ -145,15 +159,15 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
         stream_units(nchunks, nblk64, [&](int kind, int c, int a, int b) {
             const int s = u % SLOTS, buf = c & 1;
             const uint32_t par = (uint32_t)((c >> 1) & 1);
-            if (kind == 0 && c == 0) mbar_wait(bar_ak(a), 0);                       // a-tile K block a has landed
+            if (kind == 0 && c == 0) mbar_wait_b(bar_ak(a), 0);                       // a-tile K block a has landed
             if (kind == 1 && (c + 1 < nchunks ? b == 0 : true)) {
                 // P sub-block a of chunk c is in TMEM (non-last chunks reach it first with b == 0; the last chunk's half-major
                 // order reaches every sub-block once per half — a second wait on a completed phase returns at once)
-                mbar_wait(bar_p(buf, a), par);
+                mbar_wait_b(bar_p(buf, a), par);
             }
-            mbar_wait(full_bar(s), (u / SLOTS) & 1);
+            mbar_wait_b(full_bar(s), (u / SLOTS) & 1);
             tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && lane == 0 && u < 24) p.trace[8 + u] = clock64();
+            if (p.trace && blockIdx.x == 0 && lane == 0 && u < 16) p.trace[8 + u] = clock64();
             if (elect_one()) {
                 const uint32_t st = smem_base + OFF_RING + s * UNIT;
                 const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
@@ -205,7 +219,7 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
             // __ldg inside the loop below would be an L2 round trip on the CTA's serial chain). Slot buf was last read two chunks ago.
             if (et < w) b1s[buf * 128 + et] = __ldg(p.b1 + h0 + c * 128 + et);
             asm volatile("bar.sync 1, 256;" ::: "memory");                       // the eight epilogue warps only
-            mbar_wait(bar_s(buf), (uint32_t)((c >> 1) & 1));
+            mbar_wait_b(bar_s(buf), (uint32_t)((c >> 1) & 1));
             tc_fence_after();
             if (warp == 2) STC_STRACE(24 + (c < 4 ? c : 3));
 #pragma unroll 1
@@ -245,7 +259,7 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
         int it = 0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            mbar_wait(bar_o(half), 0);         // every MMA up to the last one of this half has retired (so has every read of the a-tile)
+            mbar_wait_b(bar_o(half), 0);         // every MMA up to the last one of this half has retired (so has every read of the a-tile)
             tc_fence_after();
             if (warp == 2) STC_STRACE(32 + half);
 #pragma unroll 1

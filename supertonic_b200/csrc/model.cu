@@ -17,8 +17,11 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_stream.cuh"
 #include "gemm2_tc.cuh"
 #include "model.cuh"
+#include "dp_fused.cuh"
+#include "dwconv_chain.cuh"
 #include "text_frontend.h"
 
 using json = nlohmann::json;
@@ -59,9 +62,10 @@ struct GraphKey {
     // device-resident entry points: the graph bakes the caller's four input pointers (ids, mask, style_ttl, style_dp) — all of
     // them are part of the key, unhashed (a folded key let two distinct pointer sets replay each other's graph)
     std::array<uintptr_t, 4> in{};
+    int64_t gap = 0;                    // silence samples between utterances baked into the output-packing kernel
     bool operator<(const GraphKey& o) const {
-        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1, trows, tmaxlen, in) <
-               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1, o.trows, o.tmaxlen, o.in);
+        return std::tie(stage, mode, B, T, rows, maxlen, steps, noise_ld, p0, p1, trows, tmaxlen, in, gap) <
+               std::tie(o.stage, o.mode, o.B, o.T, o.rows, o.maxlen, o.steps, o.noise_ld, o.p0, o.p1, o.trows, o.tmaxlen, o.in, o.gap);
     }
 };
 
@@ -79,10 +83,6 @@ struct PostOps {
     const float* add_vec = nullptr;                      // x <- (x + add_vec) * mask   (time conditioning)
     const float* ln_g = nullptr; const float* ln_b = nullptr;   // with `out`: LayerNorm(x); without ln_g: x itself
     const Act* out = nullptr;                            // split-bf16 operand of the next layer
-    // the next layer is another ConvNeXt block: the reduce kernel also runs ITS depthwise conv + LayerNorm (dwconv_ln_slide_kernel
-    // <.., RED>): `out` receives LayerNorm(dwconv(x_new)), the residual stream continues in x_out (not in place, see SlideRed)
-    const ConvNeXt* next_dw = nullptr;
-    float* x_out = nullptr;
 };
 
 struct VeCtx {
@@ -105,7 +105,7 @@ struct Handle {
     // main stream; the stage-1 buffers (inputs, durations, text_emb) of odd calls live in persist_alt, so that call k's stage 2 and
     // call k+1's stage 1 never share memory. The host's wait for the durations of call k+1 then ends while call k is still running.
     cudaStream_t stream_f = nullptr;
-    bool overlap = true;
+    bool overlap = true;                     // (always on; kept as a member so that a debugger can serialise the stages)
     cudaEvent_t ev_out = nullptr, copy_done[2] = {nullptr, nullptr};
     float* outbuf[2] = {nullptr, nullptr}; size_t outcap[2] = {0, 0};
     int slot = 0; bool async_pending = false;
@@ -181,17 +181,14 @@ struct Handle {
     CUtensorMap encode_map(const void* ptr, int rows, int K, int box_rows);
     const CUtensorMap& tmap(const void* ptr, int rows, int K, int box_rows);
     const CUtensorMap& tmap_f32(const void* ptr, int rows, int cols);
-    const CUtensorMap& tmap_tf32(const void* ptr, int rows, int K, int box_rows);
-    struct GemmCfg { int bn, cm, cn; };
-    GemmCfg pick_gemm(int M, int N, int K) const;
-    GemmCfg force_cfg{0, 0, 0};      // debug / sweep override (bn == 0: heuristic)
+    int pick_gemm(int M, int N, int K, bool f16) const;      // tile width 64 / 128 / 256, or 512 = the two-SM 256 x 256 form
+    int force_bn = 0;                // debug / sweep override (0: heuristic)
 
     // ---- workspace helpers
     template <typename T> T* ws(size_t n) { return static_cast<T*>(arena.alloc(n * sizeof(T))); }
     bool tc_mode() const { return precision == STC_PREC_BF16X3; }
-    Act ws_act_f32(size_t n) { Act a; a.f = ws<float>(n); return a; }       // operand of a kind::tf32 GEMM (or of the CUDA-core path)
     Act ws_act_f16(size_t n) { Act a; a.hi = ws<__nv_bfloat16>(n); return a; }   // single fp16 operand (hi holds fp16 bits, lo stays null)
-    Act ws_act_for(const Linear& w, size_t n) { return w.w_nk ? ws_act_f32(n) : w.f16 ? ws_act_f16(n) : ws_act(n); }
+    Act ws_act_for(const Linear& w, size_t n) { return w.f16 ? ws_act_f16(n) : ws_act(n); }
     Act ws_act(size_t n) {
         Act a;
         if (tc_mode()) { a.hi = ws<__nv_bfloat16>(n); a.lo = ws<__nv_bfloat16>(n); } else a.f = ws<float>(n);
@@ -207,42 +204,17 @@ struct Handle {
                                          const Seq& seq, float eps, T* out_plain, const Act* out_act);
     void gemm(const Act& a, int M, const Linear& w, const Epilogue& ep, float* out_f32, const Act* out_act, int ldo);
     template <typename T> void gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilogue& ep, T* out, int ldo);
-    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr, const Act* a_pre = nullptr);
+    template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr);
     void apply_post(const PostOps& post, float* x, const Seq& seq, int C);      // the same post-ops as separate launches
-    int mlp_form(const ConvNeXt& c, int rows) const;
-    bool can_chain_dw(const ConvNeXt& c, const ConvNeXt& n, int rows) const;
-    // env STC_DW_CHAIN=1: fold the next ConvNeXt block's depthwise conv + LayerNorm into the reduce kernel of the block before it
-    // (dwconv_ln_slide_kernel<.., RED>). Bit-identical, 120 launches fewer per step, and measured SLOWER on B200 (11.02 vs 10.46
-    // ms/step, batch-1 latency 6.46 vs 5.58 ms): a chain reduces its K-1 halo rows again (8 x 5..9 loads per thread against one row's
-    // 5 in the plain reduce kernel's 300k threads), which costs more than the launch it saves. OFF by default.
-    bool dw_chain = false;
-    void fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
-                   const PostOps* post = nullptr);
-    // env STC_MLP_PRODUCER=1: compute LayerNorm(dwconv(x)) inside the fused MLP kernel instead of a separate launch. Measured
-    // SLOWER (15.3 vs 11.5 ms/step): with 226 KB of shared memory in use the SM has no L1 left, so every tap row and every
-    // per-channel weight is re-fetched from L2 (~1.6 MB per CTA on top of the 0.5 MB of GEMM weights). OFF by default.
-    bool mlp_producer = false;
-    int voc_groups = 1;               // env STC_VOC_GROUPS (see synth_impl)
-    int mlp_mode = 0;                 // env STC_MLP: 0 auto, 1 "fused" (cluster form), 2 "unfused", 3 "split" always (cross-checks), 4 "ts", 5 "thin" always
+    bool mlp_fused(const ConvNeXt& c) const;
+    int mlp_slices(int tiles, int rows) const;
+    void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, const PostOps* post = nullptr);
+    bool mlp_unfused = false;         // env STC_MLP=unfused: the C = 256 / H = 1024 blocks as two tcgen05 GEMMs (cross-check)
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
-    bool gemm2 = true;                // env STC_GEMM2=0: keep the one-SM tiles everywhere (cross-check / comparison)
-    bool simt_bm32 = true;            // env STC_SIMT_BM32=0: the fp64 duration-predictor GEMMs keep 16-row tiles
-    bool mlp_wide = true;             // env STC_MLP_WIDE=0: the 256-unit split form issues N = 128 MMAs (hi + lo units) as before
-    bool attn_small = true;           // env STC_ATTN_SMALL=0: the 50-key style attentions use the 320-key layout too (one CTA per SM)
+    bool dp_fused = true;             // env STC_DP=unfused: the duration predictor's ConvNeXt blocks as separate fp64 conv / GEMM launches (cross-check)
     bool voc_f16 = true;              // vocoder GEMMs single-pass fp16 (default; env STC_VOC=bf16x3 keeps the split-bf16 form there too)
-    bool voc_tf32 = false;            // env STC_VOC=tf32: single-pass kind::tf32 vocoder GEMMs (waveform SNR ~70 dB instead of > 100 dB;
-                                      // measured 3.51 vs 3.78 ms per configs[1] batch — shared-memory bandwidth, not the MMA count, bounds
-                                      // these GEMMs, so the 1/3 fewer MMAs buy 7 %). Default: split-bf16 like everything else.
-    int mlp_epi = 8;                  // env STC_MLP_EPI: epilogue warps of the TS form (8 or 16)
-    // env STC_MLP_INREDUCE=1: finish a split-form block inside the MLP kernel (cooperative launch; a CTA waits for its row tile's
-    // sibling CTAs and reduces BM / CS rows itself) instead of launching the reduce kernel. Bit-identical and measured SLOWER on
-    // B200: 23.9 vs 20.0 us per block at 37 row tiles, 16.0 vs 14.3 us at one tile, 10.86 vs 10.40 ms per configs[1] step — the wait
-    // for the slowest sibling plus a 256-thread reduce sit on every CTA's critical path, where the separate kernel spreads the
-    // same 24 MB over 300k threads in 4 us. OFF by default.
-    bool mlp_inreduce = false;
-    int* mlp_cnt = nullptr;           // [64 row tiles][2] arrival / departure counters of the in-kernel reduce (zeroed once, self-resetting)
-    bool mlp_thin = true;             // env STC_MLP_THIN=0: never use the thin split form (eight 128-unit hidden slices per row tile)
+    bool dw_chain_kernel = true;      // env STC_DW=slide: long chains keep the two-pass sliding-window kernel with the ring (cross-check)
     bool dw_slide = true;             // env STC_DW=tile: shared-memory tiled depthwise conv + LayerNorm instead of the register sliding window
     int dw_rt = 0;                    // env STC_DW_RT: rows per chain of the sliding-window kernel (0: heuristic)
     int dw_ring = -1;                 // env STC_DW_RING: 1 / 0 force the shared-memory ring prefetch on / off (-1: by chain length)
@@ -272,49 +244,28 @@ struct Handle {
     void check_launch(const char* what);
     void ensure_ws(const std::function<void()>& fn);
     void synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                    uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, bool with_vocoder);
-    cudaEvent_t ev_voc[4] = {};       // vocoder group g finished (its waveform may be copied out while group g+1 runs)
+                    uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, const int* d_noise_index = nullptr);
     std::map<std::pair<uint32_t, uint32_t>, float*> tvec_cache;
     int* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging for offset arrays
 };
 
-// Optional (env STC_PDL=1) programmatic dependent launch: every kernel goes out with programmatic stream serialization, may
-// start while its predecessor drains, and waits for the predecessor's memory itself (pdl_wait() at the top of every kernel;
-// a no-op without the attribute). Measured on B200 (profiles/r1g_bench.json vs r1f): 15.2 ms/step with PDL against 14.3
-// without — the ~860 programmatic graph edges cost more than the overlapped prologues save — so it is OFF by default.
-static bool g_use_pdl = [] { const char* e = getenv("STC_PDL"); return e && e[0] == '1'; }();
+// Every kernel of the library goes out through this (plain stream-ordered launches; inside a stream capture they become graph nodes).
+// Programmatic dependent launch was measured twice on B200 (r1g: 15.2 vs 14.3 ms/step; r2b: 8.61 vs 8.50 ms/step, batch-1 latency
+// 4.76 vs 4.91 ms) — the ~770 programmatic graph edges cost the throughput path more than the overlapped prologues save — and removed.
 template <typename... KArgs, typename... Args>
-static inline void launch_pdl(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
+static inline void launch_k(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cfg.attrs = nullptr; cfg.numAttrs = 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
-}
-
-// Cooperative launch (every CTA of the grid resident at once; the launch fails instead of deadlocking if that is impossible): the
-// fused MLP's in-kernel reduce waits on sibling CTAs.
-template <typename... KArgs, typename... Args>
-static inline void launch_coop(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                               Args&&... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-    if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("cooperative kernel launch: ") + cudaGetErrorString(e));
 }
 
 #define STC_LAUNCH(h, kernel, grid, block, smem, ...)                                       \
     do {                                                                                    \
         if (!(h)->dry) {                                                                    \
-            launch_pdl((h), kernel, dim3(grid), dim3(block), (size_t)(smem), (h)->stream, __VA_ARGS__); \
+            launch_k((h), kernel, dim3(grid), dim3(block), (size_t)(smem), (h)->stream, __VA_ARGS__); \
             ++(h)->launches;                                                                \
         }                                                                                   \
     } while (0)
@@ -339,7 +290,6 @@ Handle::~Handle() {
     if (stream_copy) cudaStreamDestroy(stream_copy);
     if (stream_f) cudaStreamDestroy(stream_f);
     if (ev_te) cudaEventDestroy(ev_te);
-    for (auto& e : ev_voc) if (e) cudaEventDestroy(e);
 }
 
 void Handle::wait_async() {
@@ -413,23 +363,6 @@ const CUtensorMap& Handle::tmap_f32(const void* ptr, int rows, int cols) {
     return map_cache.emplace(key, m).first->second;
 }
 
-// fp32 [rows, K] K-major GEMM operand for kind::tf32: box = 32 elements (one 128-byte swizzled row) x box_rows
-const CUtensorMap& Handle::tmap_tf32(const void* ptr, int rows, int K, int box_rows) {
-    auto key = std::make_tuple(ptr, rows, K, 100000 + box_rows);
-    auto it = map_cache.find(key);
-    if (it != map_cache.end()) return it->second;
-    if (map_cache.size() > 16384) map_cache.clear();
-    CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK / 2, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw StcError(STC_ERR_CUDA, "cuTensorMapEncodeTiled (tf32 operand) failed: " + std::to_string((int)r));
-    return map_cache.emplace(key, m).first->second;
-}
 
 const CUtensorMap& Handle::tmap(const void* ptr, int rows, int K, int box_rows) {
     auto key = std::make_tuple(ptr, rows, K, box_rows);
@@ -451,19 +384,7 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
     Linear l; l.K = K; l.N = N;
     l.w_kn = upload_f32(w_kn.data(), w_kn.size());
     l.bias = upload_f32(bias.data(), bias.size());
-    if (tc == 2) {          // kind::tf32 operand: [N,K] K-major fp32, rounded to nearest TF32
-        std::vector<float> nk((size_t)N * K);
-        for (int k = 0; k < K; ++k)
-            for (int n = 0; n < N; ++n) {
-                uint32_t u; memcpy(&u, &w_kn[(size_t)k * N + n], 4);
-                if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
-                memcpy(&nk[(size_t)n * K + k], &u, 4);
-            }
-        l.w_nk = upload_f32(nk.data(), nk.size());
-        if (K % 4) throw StcError(STC_ERR_UNSUPPORTED, "tf32 GEMM needs K % 4 == 0, got " + std::to_string(K));
-        if (N % 4) throw StcError(STC_ERR_UNSUPPORTED, "tensor-core GEMM needs N % 4 == 0, got " + std::to_string(N));
-        l.has_maps = true;
-    } else if (tc == 3) {   // single fp16 operand: [N,K] K-major, round to nearest, saturating
+    if (tc == 3) {   // single fp16 operand: [N,K] K-major, round to nearest, saturating
         std::vector<uint16_t> hf((size_t)N * K);
         for (int k = 0; k < K; ++k)
             for (int n = 0; n < N; ++n) {
@@ -679,7 +600,7 @@ void Handle::load(const std::string& onnx_dir) {
     {
         OnnxFile f = load_onnx(onnx_dir + "/vocoder.onnx");
         voc_arch = arch_of(f, "vocoder.onnx");
-        load_net(f, voc_arch, voc, tc ? (voc_tf32 ? 2 : voc_f16 ? 3 : 1) : 0);
+        load_net(f, voc_arch, voc, tc ? (voc_f16 ? 3 : 1) : 0);
         voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
         voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
     }
@@ -712,13 +633,29 @@ static void launch_dwln(Handle* h, int C, const T* x, const float* w, const floa
             }
             RT = std::max(4, RT / 4 * 4);
             const bool ring = h->dw_ring < 0 ? RT >= 16 : h->dw_ring > 0;
+            // long chains: the one-pass kernel of dwconv_chain.cuh (K - 1 rows per iteration; chain length a multiple of that)
+            if (ring && h->dw_chain_kernel && h->dw_rt <= 0) RT = (int)cdiv(RT, 4 * (K - 1)) * 4 * (K - 1);
+            const bool chain_k = ring && h->dw_chain_kernel && RT % (K - 1) == 0;
             const unsigned chains = cdiv(rows, RT * dil) * dil;
             dim3 sg(cdiv(chains, 512 / C));
+            if (chain_k) {
+                h->note("dwconv_ln_chain");
+#define STC_CHAIN(NW, KK) STC_LAUNCH(h, (dwconv_ln_chain_kernel<NW, KK, Out>), sg, 128, ChainSmem<KK>::BYTES, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT); return
+                switch (C / 128 * 10 + K) {
+                    case 15: STC_CHAIN(1, 5);
+                    case 17: STC_CHAIN(1, 7);
+                    case 25: STC_CHAIN(2, 5);
+                    case 27: STC_CHAIN(2, 7);
+                    case 45: STC_CHAIN(4, 5);
+                    case 47: STC_CHAIN(4, 7);
+                }
+#undef STC_CHAIN
+            }
 #define STC_SLIDE(NW, KK)                                                                                                                     \
     do {                                                                                                                                      \
         h->note(ring ? "dwconv_ln_slide_ring" : "dwconv_ln_slide");                                                                          \
-        if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{}); \
-        else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT, SlideRed{});     \
+        if (ring) STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, true, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT); \
+        else STC_LAUNCH(h, (dwconv_ln_slide_kernel<NW, KK, false, Out>), sg, 128, 0, x, w, wb, g, b, out, rows, off, B, dil, pad, eps, RT);     \
         return;                                                                                                                               \
     } while (0)
             switch (C / 128 * 10 + K) {
@@ -779,9 +716,9 @@ void Handle::dwconv_ln(const T* x, const ConvNeXt* cn, const float* g, const flo
             kprof_end();
             return;
         }
-        if (out_act) {          // fp32 operand: of the CUDA-core GEMMs (fp32_simt mode), or of a kind::tf32 GEMM (rounded here)
+        if (out_act) {          // fp32 operand of the CUDA-core GEMMs (fp32_simt mode)
             kprof_begin(8.0 * rows * C >= 32e6 ? 5 : 1, (2.0 * K + 8.0) * rows * C, (out_act->lo || !out_act->hi ? 8.0 : 6.0) * rows * C + 4.0 * C * (K + 3));
-            launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_act->f, tc_mode() ? 1 : 0}, rows, seq.off, seq.B, K, dil, pad, eps);
+            launch_dwln<T, OutPlain<T>>(this, C, x, w, wb, g, b, OutPlain<T>{out_act->f}, rows, seq.off, seq.B, K, dil, pad, eps);
             kprof_end();
             return;
         }
@@ -794,12 +731,12 @@ void Handle::gemm_simt(const T* a, int lda, int M, const Linear& w, const Epilog
     // small row tiles when 64-row tiles would not give every SM a block (the fp64 duration predictor: 150 blocks before)
     // (per-element accumulation order over k is the same for every tile height: the variants are bit-identical)
     // tallest tile that still gives every SM a block: 64 rows (TM = 4: 8 shared-memory loads per 16 FMAs), else 32, else 16
-    if (simt_bm32 && cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 64) >= (unsigned)num_sms) {
+    if (cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 64) >= (unsigned)num_sms) {
         dim3 grid(cdiv(w.N, 64), cdiv(M, 64));
         STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
         return;
     }
-    if (simt_bm32 && cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 32) >= (unsigned)num_sms && M > 32) {
+    if (cdiv(w.N, 64) * cdiv(M, 64) < 4u * num_sms && cdiv(w.N, 64) * cdiv(M, 32) >= (unsigned)num_sms && M > 32) {
         dim3 grid(cdiv(w.N, 64), cdiv(M, 32));
         STC_LAUNCH(this, (gemm_simt_kernel<T, OutPlain<T>, 32>), grid, 256, 0, a, lda, w.w_kn, OutPlain<T>{out}, ldo, M, w.N, w.K, ep);
         return;
@@ -826,220 +763,113 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     tc::Params p{};
     p.trace = gemm_trace;
     p.M = M; p.N = w.N; p.K = w.K; p.ep = ep; p.ldo = ldo;
-    const bool tf32 = w.w_nk != nullptr;          // vocoder in tf32 mode: fp32 operands (a.f, w.w_nk), single-pass kind::tf32
-    if (tf32 && (!a.f || ep.rope_freqs)) throw StcError(STC_ERR_INVALID, "tf32 linear needs an fp32 activation operand");
-    const bool f16 = w.f16;                       // vocoder in f16 mode: single fp16 operands (a.hi, w.w_hi; no lo halves)
-    if (!tf32 && (!a.hi || (a.lo == nullptr) != f16 || (f16 && ep.rope_freqs))) throw StcError(STC_ERR_INVALID, "GEMM operand form does not match the weights");
+    const bool f16 = w.f16;                       // vocoder: single fp16 operands (a.hi, w.w_hi; no lo halves)
+    if (!a.hi || (a.lo == nullptr) != f16 || (f16 && ep.rope_freqs)) throw StcError(STC_ERR_INVALID, "GEMM operand form does not match the weights");
     if (out_f32) { p.out_f32 = out_f32; p.split = 0; }
-    else if (!out_act->hi) { p.out_f32 = out_act->f; p.split = 0; p.round_tf32 = 1; }     // fp32 operand of the next tf32 GEMM
     else { p.out_hi = out_act->hi; p.out_lo = out_act->lo; p.split = 1; }
     if (dry) return;
-    GemmCfg c = force_cfg.bn ? force_cfg : pick_gemm(M, w.N, w.K);
-    if (ep.rope_freqs) c = GemmCfg{64, 1, 1};          // the rotary epilogue exists for the 64-wide tile only
-    p.cm = c.cm; p.cn = c.cn;
-    const int csize = c.cm * c.cn;
-    if (f16) {
-        c.cm = c.cn = 1; p.cm = p.cn = 1;
-        // single-pass operands: the two-SM form wins at every K (tools/gemm_f16.py: conv_in, K = 168, 32 -> 22 us)
-        if (!force_cfg.bn && gemm2 && w.N % 256 == 0 && w.K >= 128 && (int)cdiv(M, 2 * tc::BM) * (w.N / 256) >= num_sms) c = GemmCfg{512, 2, 1};
-    }
-    if (c.bn == 512 && (tf32 || ep.rope_freqs)) c = GemmCfg{256, 1, 1};       // variants the two-SM kernel does not carry
-    if (c.bn == 512) {          // two-SM form (gemm2_tc.cuh): 256 x 256 tiles computed by CTA pairs
+    int bn = force_bn ? force_bn : pick_gemm(M, w.N, w.K, f16);
+    if (ep.rope_freqs) bn = 64;                   // the rotary epilogue exists for the 64-wide tile only
+    p.cm = p.cn = 1;
+    kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
+    if (bn == 512) {          // two-SM form (gemm2_tc.cuh): 256 x 256 tiles computed by CTA pairs
         if (w.N % 4) throw StcError(STC_ERR_INVALID, "two-SM GEMM: N % 4 != 0");
         p.cm = 2; p.cn = 1;
         const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM), mal = f16 ? mah : tmap(a.lo, M, w.K, tc::BM);
         const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, tc2::HALF), mwl = f16 ? mwh : tmap(w.w_lo, w.N, w.K, tc2::HALF);
         const int num_ct = cdiv(cdiv(M, tc::BM), 2) * cdiv(w.N, tc2::BN);
         const int clusters = std::max(1, std::min(num_ct, num_sms / 2));
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(tc2::THREADS); cfg.stream = stream;
-        cfg.dynamicSmemBytes = tc2::SMEM_BYTES;
-        cudaLaunchAttribute attr[1];
-        int na = 0;
-        if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
-        cfg.attrs = attr; cfg.numAttrs = na;
-        kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
         note(f16 ? "gemm2_f16" : "gemm2_bf16x3");
-        cudaError_t e = f16 ? cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<true>, mah, mal, mwh, mwl, p)
-                            : cudaLaunchKernelEx(&cfg, tc2::gemm2_bf16x3_kernel<false>, mah, mal, mwh, mwl, p);
-        if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("two-SM tcgen05 GEMM launch: ") + cudaGetErrorString(e));
+        if (f16) launch_k(this, tc2::gemm2_bf16x3_kernel<true>, dim3(clusters * 2), dim3(tc2::THREADS), (size_t)tc2::SMEM_BYTES, stream, mah, mal, mwh, mwl, p);
+        else launch_k(this, tc2::gemm2_bf16x3_kernel<false>, dim3(clusters * 2), dim3(tc2::THREADS), (size_t)tc2::SMEM_BYTES, stream, mah, mal, mwh, mwl, p);
         ++launches;
         kprof_end();
         return;
     }
-    if (tf32) { c.cm = c.cn = 1; p.cm = p.cn = 1; }
-    const CUtensorMap mah = tf32 ? tmap_tf32(a.f, M, w.K, tc::BM) : tmap(a.hi, M, w.K, tc::BM / c.cn);
-    const CUtensorMap mal = (tf32 || f16) ? mah : tmap(a.lo, M, w.K, tc::BM / c.cn);
-    const CUtensorMap mwh = tf32 ? tmap_tf32(w.w_nk, w.N, w.K, c.bn) : tmap(w.w_hi, w.N, w.K, c.bn / c.cm);
-    const CUtensorMap mwl = (tf32 || f16) ? mwh : tmap(w.w_lo, w.N, w.K, c.bn / c.cm);
-    const int m_tiles = cdiv(M, tc::BM), n_tiles = cdiv(w.N, c.bn);
-    const int cluster_tiles = cdiv(m_tiles, c.cm) * cdiv(n_tiles, c.cn);
-    const int clusters = std::max(1, std::min(cluster_tiles, num_sms / csize));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * csize); cfg.blockDim = dim3(tc::NUM_THREADS); cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
-    if (csize > 1) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = csize; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
-    cfg.attrs = attr; cfg.numAttrs = na;
-    kprof_begin(f16 ? 4 : 0, 2.0 * M * (double)w.N * w.K, 4.0 * ((double)M * w.K + (double)w.N * w.K + (double)M * w.N * (ep.resid ? 2 : 1)));
-    cudaError_t e;
-    note(ep.rope_freqs ? "gemm_bn64_rope" : c.bn == 64 ? (tf32 ? "gemm_tf32_bn64" : f16 ? "gemm_f16_bn64" : "gemm_bn64")
-                       : c.bn == 128 ? (tf32 ? "gemm_tf32_bn128" : f16 ? "gemm_f16_bn128" : "gemm_bn128")
-                                     : (tf32 ? "gemm_tf32_bn256" : f16 ? "gemm_f16_bn256" : "gemm_bn256"));
-    switch (ep.rope_freqs ? 1 : tf32 ? 1000 + c.bn : f16 ? 2000 + c.bn : c.bn) {
-        case 2064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, false, true>, mah, mal, mwh, mwl, p); break;
-        case 2128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, false, true>, mah, mal, mwh, mwl, p); break;
-        case 2256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256, false, false, true>, mah, mal, mwh, mwl, p); break;
-        case 1064: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, false, true>, mah, mal, mwh, mwl, p); break;
-        case 1128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128, false, true>, mah, mal, mwh, mwl, p); break;
-        case 1256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256, false, true>, mah, mal, mwh, mwl, p); break;
-        case 1: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64, true>, mah, mal, mwh, mwl, p); break;
-        case 64: cfg.dynamicSmemBytes = tc::Tile<64>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<64>, mah, mal, mwh, mwl, p); break;
-        case 128: cfg.dynamicSmemBytes = tc::Tile<128>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<128>, mah, mal, mwh, mwl, p); break;
-        case 256: cfg.dynamicSmemBytes = tc::Tile<256>::SMEM_BYTES; e = cudaLaunchKernelEx(&cfg, tc::gemm_bf16x3_kernel<256>, mah, mal, mwh, mwl, p); break;
+    const CUtensorMap mah = tmap(a.hi, M, w.K, tc::BM), mal = f16 ? mah : tmap(a.lo, M, w.K, tc::BM);
+    const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, bn), mwl = f16 ? mwh : tmap(w.w_lo, w.N, w.K, bn);
+    const int tiles = cdiv(M, tc::BM) * cdiv(w.N, bn);
+    const dim3 grid(std::max(1, std::min(tiles, num_sms))), block(tc::NUM_THREADS);          // persistent over tiles
+    note(ep.rope_freqs ? "gemm_bn64_rope" : bn == 64 ? (f16 ? "gemm_f16_bn64" : "gemm_bn64") : bn == 128 ? (f16 ? "gemm_f16_bn128" : "gemm_bn128")
+                                                                                              : (f16 ? "gemm_f16_bn256" : "gemm_bn256"));
+    switch (ep.rope_freqs ? 1 : f16 ? 2000 + bn : bn) {
+        case 2064: launch_k(this, tc::gemm_bf16x3_kernel<64, false, false, true>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 2128: launch_k(this, tc::gemm_bf16x3_kernel<128, false, false, true>, grid, block, (size_t)tc::Tile<128>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 2256: launch_k(this, tc::gemm_bf16x3_kernel<256, false, false, true>, grid, block, (size_t)tc::Tile<256>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 1: launch_k(this, tc::gemm_bf16x3_kernel<64, true>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 64: launch_k(this, tc::gemm_bf16x3_kernel<64>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 128: launch_k(this, tc::gemm_bf16x3_kernel<128>, grid, block, (size_t)tc::Tile<128>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 256: launch_k(this, tc::gemm_bf16x3_kernel<256>, grid, block, (size_t)tc::Tile<256>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
         default: throw StcError(STC_ERR_INVALID, "bad GEMM tile width");
     }
-    if (e != cudaSuccess) throw StcError(STC_ERR_CUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(e));
     ++launches;
     kprof_end();
 }
 
-// Tile width and cluster shape per problem (tuned with stc_debug_gemm sweeps on B200, profiles/): the kernel is bound by
-// L2 -> smem operand bytes, so prefer the shape that minimises (A bytes / cn + W bytes / cm) per tile while still giving
-// every SM a tile.
-Handle::GemmCfg Handle::pick_gemm(int M, int N, int K) const {
-    // Measured (tools/gemm_sweep.py, profiles/r1c_gemm_sweep.txt): TMA multicast inside a cluster does not shorten any of
-    // the hot shapes — the limit is bytes delivered INTO each SM, which multicast does not reduce — so clusters stay off.
-    // Wide tiles win once every SM has many tiles (fewer operand bytes per flop); narrow ones when tiles are scarce.
-    // Two-SM 256 x 256 tiles (gemm2_tc.cuh) once there are at least two waves of them: the vocoder projections. Measured
-    // (tools/gemm_epi.py, profiles/r1z_gemm_epi.txt): pw1 158.8 -> 142.3 us, pw2 145.3 -> 127.6 us.
-    if (gemm2 && N % 256 == 0 && K >= 512 && cdiv(M, 2 * tc::BM) * (N / 256) >= num_sms) return GemmCfg{512, 2, 1};
+// Tile width per problem (tuned with stc_debug_gemm sweeps on B200, profiles/r1c_gemm_sweep.txt, r1z_gemm_epi.txt): the one-SM
+// kernel is bound by L2 -> shared-memory operand bytes, so wide tiles win once every SM has many tiles (fewer operand bytes per
+// flop), narrow ones when tiles are scarce; two-SM 256 x 256 tiles (gemm2_tc.cuh, returned as 512) once they fill the SMs: the
+// vocoder projections (pw1 158.8 -> 142.3 us split-bf16; single-pass fp16 operands: the two-SM form wins at every K, conv_in 32 -> 22 us).
+// TMA multicast inside clusters was implemented and measured as well (2x1 / 1x2 / 2x2: 5-100 % slower on every hot shape — the
+// limit is bytes delivered INTO each SM, which multicast does not reduce) and is no longer reachable from the host.
+int Handle::pick_gemm(int M, int N, int K, bool f16) const {
+    if (N % 256 == 0 && K >= (f16 ? 128 : 512) && (int)(cdiv(M, 2 * tc::BM) * (N / 256)) >= num_sms) return 512;
     const int tiles128 = cdiv(M, tc::BM) * cdiv(N, 128);
-    int bn = 64;
-    if (tiles128 >= 16 * num_sms && N % 256 == 0) bn = 256;
-    else if (tiles128 >= num_sms && K >= 512 && N > 64) bn = 128;
-    return GemmCfg{bn, 1, 1};
+    if (tiles128 >= 16 * num_sms && N % 256 == 0) return 256;
+    if (tiles128 >= num_sms && K >= 512 && N > 64) return 128;
+    return 64;
 }
 
-// Fused forms of the ConvNeXt MLP (mlp_tc.cuh) and where each pays (tools/mlp_sweep.py, profiles/r1o_mlp_sweep.txt):
-//   1 cluster : 4-CTA clusters + DSMEM reduction. All clusters must be resident in ONE wave and a B200 places only 33 of them
-//               (GPCs of 16/18/20 SMs strand 16 SMs): 34+ row tiles double its time.
-//   2 split   : four independent CTAs per row tile write partial outputs, a small kernel reduces them. Measured faster than the
-//               two GEMMs at every row count tried (128 rows 18.0 vs 20.3 us, 4736 rows 20.9 vs 30.1, 9600 rows 53.3 vs 56.0) and
-//               than the cluster form (4224 rows: 20.8 vs 23.7) -> the default.
-//   0 unfused : pw1 and pw2 as two GEMMs (other widths: vocoder C=512/H=2048, tiny config).
-int Handle::mlp_form(const ConvNeXt& c, int rows) const {
-    if (!(tc_mode() && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi && !c.pw1.f16 && !c.pw2.f16)) return 0;
-    if (mlp_mode == 1) return 1;
-    if (mlp_mode == 2) return 0;
-    if (mlp_mode == 3) return 2;
-    if (mlp_mode == 4) return 3;
-    if (mlp_mode == 5) return 4;
-    if (mlp_mode == 6) return 5;
-    // "thin" split form (eight hidden slices of 128 per row tile) while its CTAs still fit one wave: small batches / batch-1 latency
-    if (mlp_thin && (int)cdiv(rows, mlp::BM) * mlp::CS_THIN64 <= num_sms) return 5;       // sixteen slices of 64 (<= 9 row tiles)
-    if (mlp_thin && (int)cdiv(rows, mlp::BM) * mlp::CS_THIN <= num_sms) return 4;
-    return 2;
+// The C = 256 / H = 1024 ConvNeXt blocks (vector estimator, text encoder) run the fused MLP of mlp_stream.cuh; other widths
+// (vocoder C = 512 / H = 2048, tiny config) and STC_MLP=unfused run pw1 and pw2 as two GEMMs.
+bool Handle::mlp_fused(const ConvNeXt& c) const {
+    return tc_mode() && !mlp_unfused && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi && !c.pw1.f16 && !c.pw2.f16;
 }
 
-// The reduce kernel of block `c` can also run the depthwise conv + LayerNorm of the following block `n` (PostOps::next_dw)
-bool Handle::can_chain_dw(const ConvNeXt& c, const ConvNeXt& n, int rows) const {
-    if (!dw_chain || !dw_slide || mlp_producer || mlp_form(c, rows) < 2 || mlp_form(n, rows) < 2) return false;
-    if (n.C != 256 || n.K != 5 || n.dil < 1 || n.pad_left % n.dil) return false;
-    const int jc = n.pad_left / n.dil;
-    if (jc != n.K - 1 && jc != (n.K - 1) / 2) return false;
-    return rows <= num_sms * 8 * 12;                 // chains of 4 rows (register prefetch), as launch_dwln would choose
-}
-
-// a == nullptr: producer mode — the kernel computes LayerNorm(dwconv(x)) itself (needs seq, c.K <= mlp::KMAX).
-void Handle::fused_mlp(const Act* a, int rows, const ConvNeXt& c, float* x, const Seq* seq, const float* mask, int form,
-                       const PostOps* post) {
-    mlp::Params p{};
-    p.trace = mlp_trace;
-    p.M = rows; p.b1 = c.pw1.bias; p.b2 = c.pw2.bias; p.gamma = c.gamma; p.mask = mask; p.x = x;
-    if (!a) {
-        p.dw_wT = c.dw_wt; p.dw_b = c.dw_b; p.ln_g = c.ln_g; p.ln_b = c.ln_b; p.off = seq->off; p.B = seq->B;
-        p.K = c.K; p.dil = c.dil; p.pad_left = c.pad_left; p.eps = 1e-6f;
+// Hidden slices per 128-row tile of the stream form (mlp_stream.cuh): the count that minimises a cost model fitted to
+// tools/mlp_sweep.py on B200 (profiles/r2c_mlp_sweep.txt) —
+//   waves(tiles * s CTAs on the SMs) x (fixed part of a CTA + its 64-unit hidden blocks) + the reduce kernel's s partial reads.
+// 37 tiles -> 4 slices (148 CTAs, one wave); 38..49 -> 3; 50..74 -> 2; 75 tiles -> 3 slices in two waves (one slice per tile would
+// leave half of the SMs idle); >= ~100 tiles -> 1; <= 9 tiles -> 16 slices of 64 units (the batch-1 latency path).
+int Handle::mlp_slices(int tiles, int rows) const {
+    const double fixed_us = 5.2, blk64_us = 2.2, red0_us = 3.0, red_slice_us = 0.4 * std::max(rows, 1) / 4736.0;
+    int best = 1; double best_t = 1e30;
+    for (int s = 1; s <= 16; ++s) {
+        const int waves = (tiles * s + num_sms - 1) / num_sms, blk = (16 + s - 1) / s;
+        const double t = waves * (fixed_us + blk64_us * blk) + red0_us + red_slice_us * s;
+        if (t < best_t - 1e-9) { best_t = t; best = s; }
     }
+    return best;
+}
+
+// pw1 -> GELU -> pw2 of one C = 256 / H = 1024 ConvNeXt block on `rows` rows: the stream kernel writes `nslice` partial outputs per
+// row tile, the reduce kernel adds them in slice order and applies b2 / layer-scale / residual / mask (+ the post-ops).
+void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, const PostOps* post) {
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
-    const int nslice = form == 5 ? mlp::CS_THIN64 : form == 4 ? mlp::CS_THIN : mlp::CS;
-    if (form >= 2) p.partial = ws<float>(slice * nslice);
-    // in-kernel reduce: split forms whose grid fits the SMs (cooperative launch), nothing chained behind the reduce
-    const bool inred = mlp_inreduce && mlp_cnt && (form == 2 || form == 4 || form == 5) && a && tiles * nslice <= num_sms && tiles <= 64 &&
-                       !g_use_pdl && !(post && post->next_dw);
-    if (inred) {
-        p.cnt = mlp_cnt;
-        if (post) {
-            p.add_vec = post->add_vec; p.post_ln_g = post->ln_g; p.post_ln_b = post->ln_b;
-            p.out_hi = post->out ? post->out->hi : nullptr; p.out_lo = post->out ? post->out->lo : nullptr;
-        }
-    }
+    const int nslice = mlp_slices(tiles, rows);
+    float* partial = ws<float>(slice * nslice);
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
-    note(form == 1 ? "mlp_cluster" : form == 3 ? "mlp_ts" : form == 5 ? "mlp_thin64" : form == 4 ? "mlp_thin" : (mlp_wide && a && !inred) ? "mlp_split_wide" : "mlp_split");
+    note(nslice == 1 ? "mlp_stream_x1" : nslice == 2 ? "mlp_stream_x2" : nslice == 3 ? "mlp_stream_x3" : nslice == 4 ? "mlp_stream_x4" : nslice <= 8 ? "mlp_stream_x5to8" : "mlp_stream_x9to16");
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
+        const CUtensorMap w1h64 = tmap(c.pw1.w_hi, c.H, c.C, 64), w1l64 = tmap(c.pw1.w_lo, c.H, c.C, 64);
         const CUtensorMap w2h = tmap(c.pw2.w_hi, c.C, c.H, 128), w2l = tmap(c.pw2.w_lo, c.C, c.H, 128);
-        const CUtensorMap mah = a ? tmap(a->hi, rows, c.C, mlp::BM) : w1h, mal = a ? tmap(a->lo, rows, c.C, mlp::BM) : w1l;   // unused in producer mode
-        if (form == 1)
-            launch_pdl(this, mlp::convnext_mlp_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                       mah, mal, w1h, w1l, w2h, w2l, p);
-        else {
-            if (form == 3) {
-                const CUtensorMap mpart = tmap_f32(p.partial, tiles * mlp::BM * mlp::CS, mlp::C);
-                if (mlp_epi == 16)
-                    launch_pdl(this, mlp::convnext_mlp_ts_kernel<16>, dim3(tiles * mlp::CS), dim3(64 + 32 * 16), (size_t)mlp::SMEM_BYTES, stream,
-                               mah, mal, w1h, w1l, w2h, w2l, mpart, p);
-                else
-                    launch_pdl(this, mlp::convnext_mlp_ts_kernel<8>, dim3(tiles * mlp::CS), dim3(64 + 32 * 8), (size_t)mlp::SMEM_BYTES, stream,
-                               mah, mal, w1h, w1l, w2h, w2l, mpart, p);
-            }
-            else if (form == 5) {
-                const CUtensorMap w1h64 = tmap(c.pw1.w_hi, c.H, c.C, 64), w1l64 = tmap(c.pw1.w_lo, c.H, c.C, 64);
-                if (inred) launch_coop(this, mlp::convnext_mlp_thin64_kernel, dim3(tiles * mlp::CS_THIN64), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                       mah, mal, w1h64, w1l64, w2h, w2l, p);
-                else launch_pdl(this, mlp::convnext_mlp_thin64_kernel, dim3(tiles * mlp::CS_THIN64), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                mah, mal, w1h64, w1l64, w2h, w2l, p);
-            } else if (form == 4) {
-                if (inred) launch_coop(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                       mah, mal, w1h, w1l, w2h, w2l, p);
-                else launch_pdl(this, mlp::convnext_mlp_thin_kernel, dim3(tiles * mlp::CS_THIN), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                mah, mal, w1h, w1l, w2h, w2l, p);
-            } else {
-                if (inred) launch_coop(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                       mah, mal, w1h, w1l, w2h, w2l, p);
-                else if (mlp_wide && a) {
-                    const CUtensorMap x1h = tmap(c.pw1.w_hi, c.H, c.C, 256), x1l = tmap(c.pw1.w_lo, c.H, c.C, 256);
-                    const CUtensorMap x2h = tmap(c.pw2.w_hi, c.C, c.H, 256), x2l = tmap(c.pw2.w_lo, c.C, c.H, 256);
-                    launch_pdl(this, mlp::convnext_mlp_split_wide_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                               mah, mal, x1h, x1l, x2h, x2l, p);
-                } else launch_pdl(this, mlp::convnext_mlp_split_kernel, dim3(tiles * mlp::CS), dim3(mlp::NUM_THREADS), (size_t)mlp::SMEM_BYTES, stream,
-                                mah, mal, w1h, w1l, w2h, w2l, p);
-            }
-            if (inred) {
-                --launches;                 // no reduce launch follows (the common `++launches` below counts one)
-            } else if (post && post->next_dw) {
-                // reduce + the next block's depthwise conv + LayerNorm in one launch (eligibility: Handle::can_chain_dw)
-                const ConvNeXt& nd = *post->next_dw;
-                SlideRed rd; rd.partial = p.partial; rd.slice = slice; rd.nslice = nslice; rd.b2 = p.b2; rd.gamma = p.gamma; rd.mask = p.mask;
-                rd.add_vec = post->add_vec; rd.x_out = post->x_out; rd.jc = nd.pad_left / nd.dil;
-                const int RT = 4;
-                const unsigned chains = cdiv(rows, RT * nd.dil) * nd.dil;
-                launch_pdl(this, (dwconv_ln_slide_kernel<2, 5, false, OutSplit, true>), dim3(cdiv(chains, 2)), dim3(128), (size_t)0, stream,
-                           (const float*)p.x, (const float*)nd.dw_wt, (const float*)nd.dw_b, (const float*)nd.ln_g, (const float*)nd.ln_b,
-                           OutSplit{post->out->hi, post->out->lo}, rows, seq->off, seq->B, nd.dil, nd.pad_left, 1e-6f, RT, rd);
-            } else if (post)
-                launch_pdl(this, nslice > 4 ? mlp::mlp_reduce_post_kernel<true> : mlp::mlp_reduce_post_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
-                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
-                           post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr, nslice);
-            else
-                launch_pdl(this, nslice > 4 ? mlp::mlp_reduce_kernel<true> : mlp::mlp_reduce_kernel<false>, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
-                           (const float*)p.partial, slice, p.b2, p.gamma, p.mask, p.x, rows, nslice);
-            ++launches;
-        }
-        ++launches;
+        const CUtensorMap mah = tmap(a.hi, rows, c.C, mlp::BM), mal = tmap(a.lo, rows, c.C, mlp::BM);
+        const CUtensorMap mpart = tmap_f32(partial, tiles * mlp::BM * nslice, mlp::C);
+        mlp::StreamParams sp{};
+        sp.M = rows; sp.nslice = nslice; sp.b1 = c.pw1.bias; sp.trace = mlp_trace;
+        launch_k(this, mlp::convnext_mlp_stream_kernel, dim3(tiles * nslice), dim3(mlp::NUM_THREADS), (size_t)mlp::ST_SMEM_BYTES, stream,
+                 mah, mal, w1h, w1l, w1h64, w1l64, w2h, w2l, mpart, sp);
+        if (post)
+            launch_k(this, nslice > 4 ? mlp::mlp_reduce_post_kernel<true> : mlp::mlp_reduce_post_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
+                     (const float*)partial, slice, c.pw2.bias, c.gamma, mask, x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
+                     post->out ? post->out->hi : (__nv_bfloat16*)nullptr, post->out ? post->out->lo : (__nv_bfloat16*)nullptr, nslice);
+        else
+            launch_k(this, nslice > 4 ? mlp::mlp_reduce_kernel<true> : mlp::mlp_reduce_kernel<false>, dim3(cdiv((size_t)rows * mlp::C / 4, 256)), dim3(256), (size_t)0, stream,
+                     (const float*)partial, slice, c.pw2.bias, c.gamma, mask, x, rows, nslice);
+        launches += 2;
     }
     kprof_end();
     release(mk);
@@ -1056,31 +886,22 @@ void Handle::apply_post(const PostOps& post, float* x, const Seq& seq, int C) {
 }
 
 template <typename T>
-void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post, const Act* a_pre) {
+void Handle::convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post) {
     size_t mk = mark();
     int rows = seq.rows;
     Epilogue e1; e1.gelu = 1;
     Epilogue e2; e2.scale = c.gamma; e2.resid = x; e2.mask = c.masked ? seq.mask : nullptr;
     if constexpr (std::is_same<T, float>::value) {
-        const int form = mlp_form(c, rows);
-        const bool post_fused = post && form >= 2;          // the split forms' reduce kernel carries the post-ops
-        if (form && mlp_producer && c.K <= mlp::KMAX) {
-            fused_mlp(nullptr, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
-        } else {
-            Act a;
-            if (a_pre) a = *a_pre;                 // LayerNorm(dwconv(x)) came out of the previous block's reduce kernel
-            else {
-                a = ws_act_for(c.pw1, (size_t)rows * c.C);
-                dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
-            }
-            if (form) fused_mlp(&a, rows, c, x, &seq, c.masked ? seq.mask : nullptr, form, post);
-            else {
-                Act hid = ws_act_for(c.pw2, (size_t)rows * c.H);
-                gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
-                gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
-            }
+        const bool fused = mlp_fused(c);                 // the fused form's reduce kernel carries the post-ops
+        Act a = ws_act_for(c.pw1, (size_t)rows * c.C);
+        dwconv_ln<float>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, nullptr, &a);
+        if (fused) fused_mlp(a, rows, c, x, c.masked ? seq.mask : nullptr, post);
+        else {
+            Act hid = ws_act_for(c.pw2, (size_t)rows * c.H);
+            gemm(a, rows, c.pw1, e1, nullptr, &hid, c.H);
+            gemm(hid, rows, c.pw2, e2, x, nullptr, c.C);
         }
-        if (post && !post_fused) apply_post(*post, x, seq, c.C);
+        if (post && !fused) apply_post(*post, x, seq, c.C);
     } else {
         T* a = ws<T>((size_t)rows * c.C); T* hid = ws<T>((size_t)rows * c.H);
         dwconv_ln<T>(x, &c, c.ln_g, c.ln_b, c.C, seq, 1e-6f, a, nullptr);
@@ -1172,11 +993,11 @@ void Handle::attn_core_tc(const Act& Q, const Attention& a, const KV& kv, const 
         const CUtensorMap mkh = tmap(kv.k_hi, k.rows, a.C, attn::KB), mkl = tmap(kv.k_lo, k.rows, a.C, attn::KB);
         const CUtensorMap mvh = tmap(kv.vt_hi, vrows, kv.ldk, attn::DH), mvl = tmap(kv.vt_lo, vrows, kv.ldk, attn::DH);
         dim3 grid(cdiv(q.maxlen, attn::BQ), a.heads, q.B);
-        note(k.maxlen <= attn::KB && attn_small ? "attention_tc_small" : "attention_tc");
-        if (k.maxlen <= attn::KB && attn_small)       // <= 64 keys (style attention): the two-CTAs-per-SM layout
-            launch_pdl(this, attn::attention_tc_kernel<1>, grid, dim3(attn::NUM_THREADS), (size_t)attn::Lay<1>::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
+        note(k.maxlen <= attn::KB ? "attention_tc_small" : "attention_tc");
+        if (k.maxlen <= attn::KB)       // <= 64 keys (style attention): the two-CTAs-per-SM layout
+            launch_k(this, attn::attention_tc_kernel<1>, grid, dim3(attn::NUM_THREADS), (size_t)attn::Lay<1>::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
         else
-            launch_pdl(this, attn::attention_tc_kernel<attn::MAX_BLOCKS>, grid, dim3(attn::NUM_THREADS), (size_t)attn::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
+            launch_k(this, attn::attention_tc_kernel<attn::MAX_BLOCKS>, grid, dim3(attn::NUM_THREADS), (size_t)attn::SMEM_BYTES, stream, mqh, mql, mkh, mkl, mvh, mvl, p);
         ++launches;
     }
     kprof_end();
@@ -1281,8 +1102,24 @@ void Handle::run_dp(const int64_t* ids, const float* style_dp, const Seq& seq, i
     Epilogue es; es.bias = ls.bias;
     gemm_simt<double>(sd, si, B, ls, es, s, C);
     STC_LAUNCH(this, add_rowvec_mask_kernel<double>, cdiv((size_t)rows * C, 256), 256, 0, x, s, mask, rows, C, C, seq.off, B);
-    for (const Layer& l : dp.layers)
-        if (l.type == L_CONVNEXT) convnext<double>(dp.cn[l.idx], x, seq);
+    double* x2 = ws<double>((size_t)rows * C);
+    for (const Layer& l : dp.layers) {
+        if (l.type != L_CONVNEXT) continue;
+        const ConvNeXt& c = dp.cn[l.idx];
+        // (a block of 32 rows is one CTA's serial chain: below ~1 000 rows — the batch-1 latency path — the separate launches, whose
+        //  GEMMs spread over 16-row tiles, finish sooner: p50 of call() 4.50 vs 4.80 ms)
+        const bool fused = dp_fused && rows >= 1024 && c.dil == 1 && c.K <= 7 && ((c.C == 64 && c.H == 256) || (c.C == 32 && c.H == 64));
+        if (!fused) { note("dp_convnext_unfused"); convnext<double>(c, x, seq); continue; }
+        // one launch per ConvNeXt block (dp_fused.cuh): conv + LayerNorm + both projections of 32 token rows in shared memory
+        DpBlockParams bp{};
+        bp.x = x; bp.out = x2; bp.dw_w = c.dw_w; bp.dw_b = c.dw_b; bp.ln_g = c.ln_g; bp.ln_b = c.ln_b;
+        bp.w1 = c.pw1.w_kn; bp.b1 = c.pw1.bias; bp.w2 = c.pw2.w_kn; bp.b2 = c.pw2.bias; bp.gamma = c.gamma;
+        bp.mask = c.masked ? mask : nullptr; bp.off = seq.off; bp.B = B; bp.rows = rows; bp.K = c.K; bp.pad_left = c.pad_left; bp.eps = 1e-6f;
+        note("dp_convnext_fused");
+        if (c.C == 64) STC_LAUNCH(this, (dp_convnext_kernel<64, 256>), cdiv(rows, 32), 256, (DpTile<64, 256>::SMEM), bp);
+        else STC_LAUNCH(this, (dp_convnext_kernel<32, 64>), cdiv(rows, 32), 256, (DpTile<32, 64>::SMEM), bp);
+        std::swap(x, x2);
+    }
     float clip = dp_arch.at("clip"), spt = dp_arch.at("sec_per_token");
     if (C == 64) STC_LAUNCH(this, dp_head_kernel<2>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, seq.off, 1e-6f, clip, spt);
     else if (C == 32) STC_LAUNCH(this, dp_head_kernel<1>, B, 256, 0, x, dp.vec["head.ln_g"], dp.vec["head.ln_b"], dp.vec["head.w"], dp.vec["head.b"], mask, dur, seq.off, 1e-6f, clip, spt);
@@ -1299,9 +1136,8 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq,
     STC_LAUNCH(this, embed_kernel<float>, cdiv(rows, 8), dim3(32, 8), 0, ids, te.vec["embed"], tseq.mask, x, rows, C, cfg.vocab_size, tseq.off, B, T);
     Act sty = ws_act((size_t)B * S * Cs);
     to_act(style_ttl, (size_t)B * S * Cs, sty);
-    Act nxt = ws_act((size_t)rows * C);
-    float* x_alt = ws<float>((size_t)rows * C);   // see run_ve_step
-    bool nxt_ready = false, a_ready = false;
+    Act nxt = ws_act((size_t)rows * C);           // operand a ConvNeXt block's reduce kernel prepares for the layer after it
+    bool nxt_ready = false;
     for (size_t li = 0; li < te.layers.size(); ++li) {
         const Layer& l = te.layers[li];
         if (l.type == L_CONVNEXT) {
@@ -1311,14 +1147,8 @@ void Handle::run_te(const int64_t* ids, const float* style_ttl, const Seq& tseq,
                 post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = nxt_ready = true;
             } else if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_PROJ_OUT) {
                 post.out = &nxt; any = nxt_ready = true;
-            } else if (li + 1 < te.layers.size() && te.layers[li + 1].type == L_CONVNEXT &&
-                       can_chain_dw(te.cn[l.idx], te.cn[te.layers[li + 1].idx], rows)) {
-                post.next_dw = &te.cn[te.layers[li + 1].idx]; post.out = &nxt; post.x_out = x_alt; any = true;
             }
-            const bool had_a = a_ready;
-            convnext<float>(te.cn[l.idx], x, tseq, any ? &post : nullptr, had_a ? &nxt : nullptr);
-            a_ready = post.next_dw != nullptr;
-            if (a_ready) std::swap(x, x_alt);
+            convnext<float>(te.cn[l.idx], x, tseq, any ? &post : nullptr);
         } else if (l.type == L_ATTN) {
             const Attention& a = te.at[l.idx];
             const Act* pre_ln = nxt_ready ? &nxt : nullptr;
@@ -1396,9 +1226,8 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
     const Seq& ls = vc.lat;
     int rows = ls.rows, C = ve.C, D = cfg.latent_channels, itc = 0;
     float* x = ws<float>((size_t)rows * C);
-    float* x_alt = ws<float>((size_t)rows * C);   // the residual stream alternates between x and x_alt across chained ConvNeXt blocks
     Act nxt = ws_act((size_t)rows * C);           // operand a ConvNeXt block's reduce kernel prepares for the layer after it
-    bool nxt_ready = false, a_ready = false;      // a_ready: nxt holds LayerNorm(dwconv(x)) of the ConvNeXt block that comes next
+    bool nxt_ready = false;
     for (size_t li = 0; li < ve.layers.size(); ++li) {
         const Layer& l = ve.layers[li];
         switch (l.type) {
@@ -1424,13 +1253,8 @@ void Handle::run_ve_step(const VeCtx& vc, float* x_lat, const float* tvec, const
                     post.ln_g = a.ln_g; post.ln_b = a.ln_b; post.out = &nxt; any = true; nxt_ready = true;
                 } else if (nx < ve.layers.size() && ve.layers[nx].type == L_PROJ_OUT) {
                     post.out = &nxt; any = true; nxt_ready = true;
-                } else if (nx < ve.layers.size() && ve.layers[nx].type == L_CONVNEXT && can_chain_dw(ve.cn[l.idx], ve.cn[ve.layers[nx].idx], rows)) {
-                    post.next_dw = &ve.cn[ve.layers[nx].idx]; post.out = &nxt; post.x_out = x_alt; any = true;
                 }
-                const bool had_a = a_ready;
-                convnext<float>(ve.cn[l.idx], x, ls, any ? &post : nullptr, had_a ? &nxt : nullptr);
-                a_ready = post.next_dw != nullptr;
-                if (a_ready) std::swap(x, x_alt);
+                convnext<float>(ve.cn[l.idx], x, ls, any ? &post : nullptr);
                 break;
             }
             case L_TIME_COND:
@@ -1598,39 +1422,20 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             throw StcError(STC_ERR_UNSUPPORTED, "the tcgen05 path needs an sm_100 device, found sm_" + std::to_string(prop.major * 10 + prop.minor));
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
-        { const char* e = getenv("STC_MLP_PRODUCER"); hd->mlp_producer = e && e[0] == '1'; }
-        { const char* e = getenv("STC_VOC_GROUPS"); hd->voc_groups = e ? std::max(1, std::min(4, atoi(e))) : 1; }
-        { const char* e = getenv("STC_MLP"); hd->mlp_mode = !e ? 0 : std::string(e) == "fused" ? 1 : std::string(e) == "unfused" ? 2 : std::string(e) == "split" ? 3 : std::string(e) == "ts" ? 4 : std::string(e) == "thin" ? 5 : std::string(e) == "thin64" ? 6 : 0; }
-        { const char* e = getenv("STC_GEMM2"); hd->gemm2 = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_ATTN_SMALL"); hd->attn_small = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_MLP_WIDE"); hd->mlp_wide = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_SIMT_BM32"); hd->simt_bm32 = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_VOC"); hd->voc_tf32 = e && std::string(e) == "tf32"; hd->voc_f16 = !e || std::string(e) == "f16"; }
-        { const char* e = getenv("STC_MLP_EPI"); hd->mlp_epi = e && atoi(e) == 16 ? 16 : 8; }
-        { const char* e = getenv("STC_MLP_THIN"); hd->mlp_thin = !(e && e[0] == '0'); }
-        { const char* e = getenv("STC_MLP_INREDUCE"); hd->mlp_inreduce = e && e[0] == '1'; }
-        { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); }
+        { const char* e = getenv("STC_MLP"); hd->mlp_unfused = e && !strcmp(e, "unfused"); }
+        { const char* e = getenv("STC_DP"); hd->dp_fused = !(e && !strcmp(e, "unfused")); }
+        { const char* e = getenv("STC_VOC"); hd->voc_f16 = !e || !strcmp(e, "f16"); }
+        { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); hd->dw_chain_kernel = !(e && !strcmp(e, "slide")); }
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
-        { const char* e = getenv("STC_DW_CHAIN"); hd->dw_chain = e && e[0] == '1'; }
         { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
-        {
-            // env STC_PRIO=1: the main stream (Euler loop + vocoder) gets the highest priority, the stage-1 streams the lowest, so that
-            // in a request stream the next call's duration predictor / text encoder only fill what the current call leaves free
-            int lo = 0, hi = 0;
-            STC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            const char* e = getenv("STC_PRIO");
-            const bool prio = e && e[0] == '1';
-            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream, cudaStreamNonBlocking, prio ? hi : 0));
-            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream2, cudaStreamNonBlocking, prio ? lo : 0));
-            STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
-            STC_CUDA(cudaStreamCreateWithPriority(&hd->stream_f, cudaStreamNonBlocking, prio ? lo : 0));
-        }
-        { const char* e = getenv("STC_OVERLAP"); hd->overlap = !(e && e[0] == '0'); }
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_copy, cudaStreamNonBlocking));
+        STC_CUDA(cudaStreamCreateWithFlags(&hd->stream_f, cudaStreamNonBlocking));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_out, cudaEventDisableTiming));
         for (auto& e : hd->copy_done) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_in, cudaEventDisableTiming));
         STC_CUDA(cudaEventCreateWithFlags(&hd->ev_te, cudaEventDisableTiming));
-        for (auto& e : hd->ev_voc) STC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& ev : hd->ev) STC_CUDA(cudaEventCreate(&ev));
         if (precision == STC_PREC_BF16X3) {
             void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
@@ -1646,21 +1451,19 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<attn::MAX_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Lay<1>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_split_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_thin64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-            STC_CUDA(cudaMalloc((void**)&hd->mlp_cnt, 128 * sizeof(int))); hd->owned.push_back(hd->mlp_cnt);
-            STC_CUDA(cudaMemset(hd->mlp_cnt, 0, 128 * sizeof(int)));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::ST_SMEM_BYTES));
         }
+#define STC_CHAIN_ATTR(NW, KK)                                                                                                                 \
+    STC_CUDA(cudaFuncSetAttribute((dwconv_ln_chain_kernel<NW, KK, OutSplit>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainSmem<KK>::BYTES)); \
+    STC_CUDA(cudaFuncSetAttribute((dwconv_ln_chain_kernel<NW, KK, OutPlain<float>>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainSmem<KK>::BYTES)); \
+    STC_CUDA(cudaFuncSetAttribute((dwconv_ln_chain_kernel<NW, KK, OutSplit>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    STC_CUDA(cudaFuncSetAttribute((dwconv_ln_chain_kernel<NW, KK, OutPlain<float>>), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+        STC_CHAIN_ATTR(1, 5); STC_CHAIN_ATTR(1, 7); STC_CHAIN_ATTR(2, 5); STC_CHAIN_ATTR(2, 7); STC_CHAIN_ATTR(4, 5); STC_CHAIN_ATTR(4, 7);
+#undef STC_CHAIN_ATTR
+        STC_CUDA(cudaFuncSetAttribute((dp_convnext_kernel<64, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DpTile<64, 256>::SMEM));
+        STC_CUDA(cudaFuncSetAttribute((dp_convnext_kernel<32, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DpTile<32, 64>::SMEM));
         {
             const int big = 200 * 1024;
             STC_CUDA(cudaFuncSetAttribute(dwconv_ln_tile_kernel<4, OutSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1893,23 +1696,20 @@ static int latent_len_f32(const float* dur, int B, int sr, int cs) {
 }
 
 void Handle::synth_tail(const float* d_text_emb, const Seq& text, const float* d_style_ttl, const float* d_noise, int64_t noise_ld,
-                        uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, bool with_vocoder) {
+                        uint64_t seed, const Seq& lat, int steps, float* d_xlat, float* d_wav, const int* d_noise_index) {
     int D = cfg.latent_channels;
     std::vector<const float*> tv(steps);
     for (int s = 0; s < steps; ++s) tv[s] = time_vectors((float)s, (float)steps);
     std::vector<int> sbits = {(int)(uint32_t)(seed & 0xffffffffu), (int)(uint32_t)(seed >> 32)};
     const uint64_t* d_seed = reinterpret_cast<const uint64_t*>(stage_ints(sbits));     // per call, outside the graph's baked arguments
-    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)lat.rows * D, 256), 256, 0, d_noise, noise_ld, d_seed, lat.mask, d_xlat, lat.rows, lat.off, lat.B, D);
+    STC_LAUNCH(this, init_latent_kernel, cdiv((size_t)lat.rows * D, 256), 256, 0, d_noise, noise_ld, d_seed, lat.mask, d_xlat, lat.rows, lat.off, lat.B, D, d_noise_index);
     VeCtx vc; vc.lat = lat; vc.text = text; vc.style = rect_seq(text.B, cfg.style_ttl_tokens, nullptr, false);
     prepare_ve(vc, d_text_emb, d_style_ttl);
     float* d_dt = ws<float>(D);
     STC_LAUNCH(this, fill_kernel, cdiv(D, 128), 128, 0, d_dt, 1.0f / (float)steps, (size_t)D);
     for (int s = 0; s < steps; ++s) run_ve_step(vc, d_xlat, tv[s], d_dt);
     if (profile && !dry) cudaEventRecord(ev[3], stream);
-    if (with_vocoder) run_vocoder(d_xlat, lat, d_wav);
-    else if (dry && !restage) {         // measuring pass: reserve the workspace the (later, eager) vocoder passes will need
-        size_t m = mark(); run_vocoder(d_xlat, lat, d_wav); release(m);
-    }
+    run_vocoder(d_xlat, lat, d_wav);
 }
 
 }  // namespace stc
@@ -1920,10 +1720,22 @@ extern "C" {
 static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const float* text_mask, const float* style_ttl,
                       const float* style_dp, int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld,
                       uint64_t seed, float* wav_out, int64_t wav_cap, float* duration_out, int64_t* wav_lengths_out, int64_t* L_out,
-                      float* latent_out, int64_t* wav_offsets_out, const int32_t* text_lens, bool async_copy = false) {
+                      float* latent_out, int64_t* wav_offsets_out, const int32_t* text_lens, bool async_copy = false,
+                      const stc_out_opts* oo = nullptr) {
     STC_TRY(sh, {
         const bool host_io = mode & 1, packed = mode & 2;
         Scope sc(sh, async_copy); Handle* h = sc.h;
+        // output packing (packed host-I/O entry points only): PCM16 quantisation and / or silence between utterances on the device
+        const bool pcm = oo && oo->pcm16;
+        const int64_t gap = oo ? oo->gap_samples : 0;
+        const bool pack = pcm || gap > 0;
+        if (pack && !(host_io && packed)) throw StcError(STC_ERR_INVALID, "output options need the packed host entry points");
+        if (gap < 0) throw StcError(STC_ERR_INVALID, "gap_samples < 0");
+        const size_t esz = pcm ? sizeof(int16_t) : sizeof(float);
+        if (pack) mode |= 256 | (pcm ? 512 : 0);               // graphs of the packing forms carry one more kernel
+        const int64_t* nidx = oo ? oo->noise_index : nullptr;
+        if (nidx && !(host_io && packed)) throw StcError(STC_ERR_INVALID, "noise_index needs the packed host entry points");
+        if (nidx) mode |= 1024;
         if (async_copy && !(host_io && packed && !latent_out && !h->profile && h->use_graphs)) async_copy = false;
         int slot = 0;
         if (async_copy) {                              // this call's half of the pinned offset staging + its device result buffer
@@ -1997,7 +1809,7 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
         const uintptr_t pin = 0;
         std::array<uintptr_t, 4> pins{};
         if (!host_io) pins = {(uintptr_t)text_ids, (uintptr_t)text_mask, (uintptr_t)style_ttl, (uintptr_t)style_dp};
-        auto keyed = [&](GraphKey k) { k.in = pins; return k; };
+        auto keyed = [&](GraphKey k) { k.in = pins; k.gap = gap; return k; };
         const size_t stage_base = h->h_stage_off;
         auto stage1a = [&]() {
             h->arena.reset(); h->persist.reset(); h->h_stage_off = stage_base;
@@ -2059,38 +1871,27 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             lens[b] = (int)((h->h_wavlen[b] + c.chunk_size - 1) / c.chunk_size);
             R += lens[b]; maxlen = std::max(maxlen, lens[b]);
         }
-        if (wav_offsets_out) { wav_offsets_out[0] = 0; for (int b = 0; b < B; ++b) wav_offsets_out[b + 1] = wav_offsets_out[b] + (int64_t)lens[b] * c.chunk_size; }
+        // utterance b's samples start at wav_offsets_out[b]; with a gap the silence follows them, so [B] (the total) excludes a trailing gap
+        if (wav_offsets_out) {
+            wav_offsets_out[0] = 0;
+            for (int b = 0; b < B; ++b) wav_offsets_out[b + 1] = wav_offsets_out[b] + (int64_t)lens[b] * c.chunk_size + (b + 1 < B ? gap : 0);
+        }
         // graph buckets: packed rows are rounded up to a multiple of 128 (extra rows belong to no sequence), the
         // longest-utterance bound (attention grid) to a multiple of 16
         const int64_t rows = packed ? (h->use_graphs && !h->profile ? (R + 127) / 128 * 128 : R) : (int64_t)B * L;
         const int maxlen_launch = packed ? (maxlen + 15) / 16 * 16 : L;
-        const int64_t wav_need = packed ? rows * c.chunk_size : (int64_t)L * c.chunk_size;   // total floats (packed) / per row (rectangle)
+        const int64_t wav_need = packed ? rows * c.chunk_size + (int64_t)(B - 1) * gap : (int64_t)L * c.chunk_size;   // total elements (packed) / per row (rectangle)
+        const int64_t wav_real = R * c.chunk_size + (int64_t)(B - 1) * gap;                 // elements the caller receives (packed)
         if (wav_cap < wav_need) {
             if (wav_offsets_out) wav_offsets_out[B] = std::max<int64_t>(wav_offsets_out[B], wav_need);
             throw StcError(STC_ERR_CAPACITY, "wav_out too small: need " + std::to_string(wav_need));
         }
         if (noise && noise_ld < (packed ? maxlen : L)) throw StcError(STC_ERR_CAPACITY, "noise_ld smaller than the latent length");
         // ---- stage 2: everything that depends on L
-        // Optional (env STC_VOC_GROUPS=2..4) for the host-I/O throughput path: the vocoder runs in utterance groups (eager launches
-        // behind the VE graph) and every group's waveform is copied out on the second stream while the next group is decoded.
-        // Measured on configs[1] (57 MB of waveform per step): e2e 15.8 ms/step with 4 groups against 14.7 ms with one pass —
-        // the four smaller passes lose more tensor-pipe efficiency than the hidden copy (1.1 ms) gains — so it is OFF by default.
-        std::vector<int> grp_end;      // utterance index where each vocoder group ends
-        if (h->voc_groups > 1 && !async_copy && host_io && packed && !h->profile && h->use_graphs && B >= 2 &&
-            R * c.chunk_size * (int64_t)sizeof(float) >= (int64_t(8) << 20)) {
-            const int G = std::min(h->voc_groups, B);
-            int64_t acc = 0; int g = 1;
-            for (int b = 0; b < B; ++b) {
-                acc += lens[b];
-                if (acc * G >= R * g && (int)grp_end.size() < G - 1 && b + 1 < B) { grp_end.push_back(b + 1); while (acc * G >= R * g) ++g; }
-            }
-            grp_end.push_back(B);
-            if (grp_end.size() < 2) grp_end.clear();
-        }
-        const bool chunked = !grp_end.empty();
         float *d_noise = nullptr, *d_lmask = nullptr, *d_xlat = nullptr, *d_wav = nullptr, *d_lat_ncl = nullptr;
+        void* d_out = nullptr;                 // what is copied to the caller: d_wav itself, or the packed / quantised copy of it
         if (async_copy) {
-            const size_t need = (size_t)rows * c.chunk_size;
+            const size_t need = (size_t)wav_need;          // (elements; sized as floats, so a PCM16 result uses half of it)
             if (h->outcap[slot] < need) {
                 std::lock_guard<std::recursive_mutex> lk(g_capture_mu);
                 STC_CUDA(cudaEventSynchronize(h->copy_done[slot]));                  // the copy that last read this buffer
@@ -2106,7 +1907,9 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             d_noise = nullptr;
             if (noise) d_noise = up(h, noise, (size_t)B * D * noise_ld);
             d_xlat = h->ws<float>((size_t)rows * D);
-            d_wav = async_copy ? h->outbuf[slot] : host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
+            d_wav = (async_copy && !pack) ? h->outbuf[slot] : host_io ? h->ws<float>((size_t)rows * c.chunk_size) : wav_out;
+            d_out = d_wav;
+            if (pack) d_out = async_copy ? (void*)h->outbuf[slot] : (void*)h->ws<unsigned char>((size_t)wav_need * esz);
             Seq text = text_seq(d_tmask, true), lat;
             if (packed) lat = h->packed_seq(lens, (int)rows, maxlen_launch);
             else {
@@ -2115,9 +1918,19 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
                 lat = h->rect_seq(B, L, d_lmask, true);
                 if (latent_out) d_lat_ncl = h->ws<float>((size_t)B * L * D);
             }
-            h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav, !chunked);
+            const int* d_nidx = nullptr;
+            if (nidx) {
+                std::vector<int> ni(B);
+                for (int b = 0; b < B; ++b) ni[b] = (int)(nidx[b] & 0x7fffffff);
+                d_nidx = h->stage_ints(ni);
+            }
+            h->synth_tail(d_temb, text, d_sttl, d_noise, noise_ld, seed, lat, total_step, d_xlat, d_wav, d_nidx);
+            if (pack) {
+                if (pcm) STC_LAUNCH(h, wav_pack_kernel<int16_t>, (unsigned)rows, 256, 0, (const float*)d_wav, (int16_t*)d_out, lat.off, B, c.chunk_size, (long long)gap);
+                else STC_LAUNCH(h, wav_pack_kernel<float>, (unsigned)rows, 256, 0, (const float*)d_wav, (float*)d_out, lat.off, B, c.chunk_size, (long long)gap);
+            }
         };
-        h->run_graphed(keyed(GraphKey{3, mode | (latent_out ? 4 : 0) | (chunked ? 8 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
+        h->run_graphed(keyed(GraphKey{3, mode | (latent_out ? 4 : 0), B, T, (int)rows, maxlen_launch, total_step, noise ? noise_ld : -1,
                                       pin, async_copy ? (uintptr_t)h->outbuf[slot] : host_io ? 0 : (uintptr_t)wav_out, trows, tmaxlen}), stage2);
         if (getenv("STC_TIMING")) {
             const auto t_host2 = std::chrono::steady_clock::now();
@@ -2130,34 +1943,14 @@ static int synth_impl(stc_handle* sh, int mode, const int64_t* text_ids, const f
             // the copy rides its own stream; this call returns as soon as it is enqueued (stc_wait delivers it)
             STC_CUDA(cudaEventRecord(h->ev_out, st));
             STC_CUDA(cudaStreamWaitEvent(h->stream_copy, h->ev_out, 0));
-            STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)R * c.chunk_size * sizeof(float), cudaMemcpyDeviceToHost, h->stream_copy));
+            STC_CUDA(cudaMemcpyAsync(wav_out, d_out, (size_t)wav_real * esz, cudaMemcpyDeviceToHost, h->stream_copy));
             STC_CUDA(cudaEventRecord(h->copy_done[slot], h->stream_copy));
             h->async_pending = true;
             return STC_OK;
         }
-        if (chunked) {
-            int b0 = 0; int64_t r0 = 0;
-            for (size_t g = 0; g < grp_end.size(); ++g) {
-                const int b1 = grp_end[g];
-                std::vector<int> gl(lens.begin() + b0, lens.begin() + b1);
-                int64_t rg = 0; int mg = 0;
-                for (int v : gl) { rg += v; mg = std::max(mg, v); }
-                const size_t m = h->mark();
-                Seq lg = h->packed_seq(gl, (int)rg, (mg + 15) / 16 * 16);
-                h->run_vocoder(d_xlat + r0 * D, lg, d_wav + r0 * c.chunk_size);
-                h->release(m);
-                STC_CUDA(cudaEventRecord(h->ev_voc[g], st));
-                STC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_voc[g], 0));
-                STC_CUDA(cudaMemcpyAsync(wav_out + r0 * c.chunk_size, d_wav + r0 * c.chunk_size, (size_t)rg * c.chunk_size * sizeof(float),
-                                         cudaMemcpyDeviceToHost, h->stream2));
-                b0 = b1; r0 += rg;
-            }
-            STC_CUDA(cudaEventRecord(h->ev_te, h->stream2));
-            STC_CUDA(cudaStreamWaitEvent(st, h->ev_te, 0));
-            if (latent_out) STC_CUDA(cudaMemcpyAsync(latent_out, d_xlat, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-        } else if (host_io) {
+        if (host_io) {
             if (packed) {
-                STC_CUDA(cudaMemcpyAsync(wav_out, d_wav, (size_t)R * c.chunk_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+                STC_CUDA(cudaMemcpyAsync(wav_out, d_out, (size_t)wav_real * esz, cudaMemcpyDeviceToHost, st));
                 if (latent_out) STC_CUDA(cudaMemcpyAsync(latent_out, d_xlat, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToHost, st));
             } else {
                 int64_t wav_row = (int64_t)L * c.chunk_size;
@@ -2214,6 +2007,15 @@ int stc_synthesize_packed_async(stc_handle* h, const int64_t* text_ids, const fl
                       duration_out, wav_lengths_out, nullptr, nullptr, wav_offsets_out, nullptr, true);
 }
 
+int stc_synthesize_packed_ex(stc_handle* h, const int64_t* text_ids, const float* text_mask, const float* style_ttl, const float* style_dp,
+                             int B, int T, int total_step, float speed, const float* noise, int64_t noise_ld, uint64_t seed,
+                             const stc_out_opts* opts, void* out, int64_t out_cap, int64_t* wav_offsets_out, float* duration_out,
+                             int64_t* wav_lengths_out, int async_copy) {
+    if (async_copy && noise) return fail(h, STC_ERR_INVALID, "stc_synthesize_packed_ex: the asynchronous form takes no injected noise");
+    return synth_impl(h, 3, text_ids, text_mask, style_ttl, style_dp, B, T, total_step, speed, noise, noise_ld, seed, static_cast<float*>(out), out_cap,
+                      duration_out, wav_lengths_out, nullptr, nullptr, wav_offsets_out, nullptr, async_copy != 0, opts);
+}
+
 int stc_wait(stc_handle* sh) {
     STC_TRY(sh, {
         if (!sh || !sh->impl) throw StcError(STC_ERR_INVALID, "null handle");
@@ -2262,15 +2064,14 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
         if (!h->tc_mode()) throw StcError(STC_ERR_UNSUPPORTED, "stc_debug_gemm needs the tcgen05 precision mode");
         if (M <= 0 || N <= 0 || K <= 0 || iters <= 0 || epilogue < 0 || epilogue > 2) throw StcError(STC_ERR_INVALID, "stc_debug_gemm: bad argument");
         if (bn && (bn != 64 && bn != 128 && bn != 256 && bn != 512)) throw StcError(STC_ERR_INVALID, "bn must be 0, 64, 128, 256 or 512 (two-SM 256 x 256)");
-        if (bn && bn != 512 && (cm < 1 || cn < 1 || cm * cn > 8 || (tc::BM / cn) % 8 || (bn / cm) % 8)) throw StcError(STC_ERR_INVALID, "bad cluster shape");
+        if (cm != 1 || cn != 1) throw StcError(STC_ERR_UNSUPPORTED, "cluster shapes other than 1 x 1 were measured slower and removed (DESIGN.md)");
         std::vector<float> wk((size_t)K * N), bias(N);
         uint64_t z = 12345;
         auto rnd = [&]() { z = z * 6364136223846793005ull + 1442695040888963407ull; return (float)((int64_t)(z >> 11) % 2000001 - 1000000) * 1e-6f; };
         for (auto& v : wk) v = rnd() / std::sqrt((float)K) * 1.7f;
         for (auto& v : bias) v = rnd() * 0.1f;
-        const bool tf32 = getenv("STC_DEBUG_TF32") != nullptr;          // time / check the kind::tf32 instantiation instead
-        const bool f16 = !tf32 && getenv("STC_DEBUG_F16") != nullptr;   // ... or the single-pass fp16 one
-        Linear lin = h->make_linear_host(wk, bias, K, N, tf32 ? 2 : f16 ? 3 : 1);
+        const bool f16 = getenv("STC_DEBUG_F16") != nullptr;            // time / check the single-pass fp16 instantiation instead
+        Linear lin = h->make_linear_host(wk, bias, K, N, f16 ? 3 : 1);
         auto body = [&]() {
             h->arena.reset(); h->h_stage_off = 0;
             float* A = h->ws<float>((size_t)M * K); float* X = h->ws<float>((size_t)M * N); float* Xr = h->ws<float>((size_t)M * N);
@@ -2284,8 +2085,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 2, 0.0f, (size_t)std::min(M - M / 2, 3));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
-            if (tf32) convert_kernel<OutPlain<float>><<<cdiv((size_t)M * K, 256), 256, 0, h->stream>>>(A, OutPlain<float>{a.f, 1}, (size_t)M * K);
-            else h->to_act(A, (size_t)M * K, a);
+            h->to_act(A, (size_t)M * K, a);
             Epilogue ep;
             if (epilogue == 1) ep.gelu = 1;
             if (epilogue == 2) { ep.scale = gamma; ep.mask = mask; }
@@ -2295,7 +2095,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             if (epilogue == 2) er.resid = Xr;
             h->gemm_simt<float>(A, K, M, lin, er, epilogue == 2 ? Xr : ref, N);
             const float* refp = epilogue == 2 ? Xr : ref;
-            h->force_cfg = Handle::GemmCfg{bn, cm, cn};
+            h->force_bn = bn;
             cudaEvent_t e0 = h->pool_event(), e1 = h->pool_event();
             auto one = [&](bool checked) {
                 if (epilogue == 2) {
@@ -2318,8 +2118,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
                 fprintf(stderr, "\n");
             }
             one(true);
-            if (epilogue == 1 && tf32) STC_CUDA(cudaMemcpyAsync(out, o.f, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, h->stream));
-            else if (epilogue == 1 && f16) debug_unhalf_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(reinterpret_cast<const __half*>(o.hi), out, (size_t)M * N);
+            if (epilogue == 1 && f16) debug_unhalf_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(reinterpret_cast<const __half*>(o.hi), out, (size_t)M * N);
             else if (epilogue == 1) debug_join_kernel<<<cdiv((size_t)M * N, 256), 256, 0, h->stream>>>(o.hi, o.lo, out, (size_t)M * N);
             debug_maxdiff_kernel<<<592, 256, 0, h->stream>>>(out, refp, (size_t)M * N, err);
             // timed: `iters` launches replayed from a CUDA graph (as in production), so the host is not in the loop
@@ -2332,7 +2131,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             cudaEventRecord(e0, h->stream);
             STC_CUDA(cudaGraphLaunch(exec, h->stream));
             cudaEventRecord(e1, h->stream);
-            h->force_cfg = Handle::GemmCfg{0, 0, 0};
+            h->force_bn = 0;
             STC_CUDA(cudaStreamSynchronize(h->stream));
             h->check_launch("stc_debug_gemm");
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -2341,7 +2140,7 @@ int stc_debug_gemm(stc_handle* sh, int M, int N, int K, int bn, int cm, int cn, 
             if (max_abs_err) STC_CUDA(cudaMemcpy(max_abs_err, err, 4, cudaMemcpyDeviceToHost));
             h->ev_next = 0;
         };
-        h->force_cfg = Handle::GemmCfg{0, 0, 0};
+        h->force_bn = 0;
         h->ensure_ws(body);
         body();
         // the temporary weights stay owned by the handle until it is destroyed (debug entry point: acceptable)
@@ -2370,15 +2169,14 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
             float* Xa = h->ws<float>((size_t)M * C); float* Xb = h->ws<float>((size_t)M * C);
             float* mask = h->ws<float>(M); float* err = h->ws<float>(1);
             Act a = h->ws_act((size_t)M * C), hid = h->ws_act((size_t)M * H);
-            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * mlp::CS_THIN64); h->ws<long long>(64); return; }     // split form's scratch
+            if (h->dry) { h->ws<float>((size_t)cdiv(M, mlp::BM) * mlp::BM * mlp::C * 16); h->ws<long long>(64); return; }     // partial outputs (<= 16 slices)
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(A, (size_t)M * C, 1, 1.0f);
             debug_fill_kernel<<<cdiv((size_t)M * C, 256), 256, 0, h->stream>>>(X0, (size_t)M * C, 2, 1.0f);
             fill_kernel<<<cdiv(M, 256), 256, 0, h->stream>>>(mask, 1.0f, (size_t)M);
             fill_kernel<<<1, 32, 0, h->stream>>>(mask + M / 3, 0.0f, (size_t)std::min(M - M / 3, 2));
             fill_kernel<<<1, 32, 0, h->stream>>>(err, 0.0f, (size_t)1);
             h->to_act(A, (size_t)M * C, a);
-            const int form = h->mlp_mode == 6 ? 5 : h->mlp_mode == 5 ? 4 : h->mlp_mode == 4 ? 3 : h->mlp_mode == 3 ? 2 : 1;
-            auto fused = [&](float* x) { h->fused_mlp(&a, M, cn, x, nullptr, mask, form); };
+            auto fused = [&](float* x) { h->fused_mlp(a, M, cn, x, mask); };
             auto unfused = [&](float* x) {
                 Epilogue e1; e1.gelu = 1;
                 Epilogue e2; e2.scale = cn.gamma; e2.resid = x; e2.mask = mask;
@@ -2395,7 +2193,7 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
                 long long ht[64];
                 STC_CUDA(cudaMemcpyAsync(ht, tr, 64 * 8, cudaMemcpyDeviceToHost, h->stream));
                 STC_CUDA(cudaStreamSynchronize(h->stream));
-                fprintf(stderr, "mlp trace M=%d (cycles since prologue end):", M);
+                fprintf(stderr, "mlp trace M=%d (cycles since prologue end; [8..23] MMA warp per weight unit, [24..27] S chunk ready, [28..31] P chunk written, [32,33] output half final, [34] end, [40..55] producer per unit):", M);
                 for (int i = 0; i < 64; ++i) fprintf(stderr, "%s%lld", i % 8 == 0 ? "\n  " : " ", ht[i] ? ht[i] - ht[0] : -99999);
                 fprintf(stderr, "\n");
                 STC_CUDA(cudaMemcpyAsync(Xa, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -2494,6 +2292,26 @@ int stc_debug_dwconv(stc_handle* sh, int rows, int C, int K, int dil, int causal
         };
         h->ensure_ws(body);
         body();
+    })
+}
+
+// The device quantiser on caller-provided samples (known-answer tests against the reference's writeWavFile goldens)
+int stc_debug_pcm16(stc_handle* sh, const float* samples, int64_t n, int16_t* out) {
+    STC_TRY(sh, {
+        Scope sc(sh); Handle* h = sc.h;
+        if (n <= 0 || !samples || !out) throw StcError(STC_ERR_INVALID, "stc_debug_pcm16: bad argument");
+        auto body = [&]() {
+            h->arena.reset(); h->h_stage_off = 0;
+            float* d_in = up(h, samples, (size_t)n);
+            int16_t* d_out = h->ws<int16_t>((size_t)n);
+            const int* off = h->stage_ints(std::vector<int>{0, 1});
+            STC_LAUNCH(h, wav_pack_kernel<int16_t>, 1, 256, 0, (const float*)d_in, d_out, off, 1, (int)n, (long long)0);
+            if (!h->dry) STC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+        };
+        h->ensure_ws(body);
+        body();
+        STC_CUDA(cudaStreamSynchronize(h->stream));
+        h->check_launch("stc_debug_pcm16");
     })
 }
 

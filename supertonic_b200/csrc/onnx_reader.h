@@ -77,7 +77,7 @@ struct Reader {
 inline void parse_tensor(pb::Reader r, std::string& name, OnnxTensor& t) {
     std::vector<float> floats; std::vector<int64_t> i64; bool has_raw = false;
     while (r.ok()) {
-        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        int wt; uint64_t v = 0; pb::Reader s{nullptr, nullptr};
         int f = r.next(wt, v, s);
         if (f == 1) { if (wt == 2) { while (s.ok()) t.dims.push_back((int64_t)s.varint()); } else t.dims.push_back((int64_t)v); }
         else if (f == 2) t.dtype = (int)v;
@@ -104,7 +104,7 @@ inline void parse_tensor(pb::Reader r, std::string& name, OnnxTensor& t) {
 inline OnnxValueInfo parse_value_info(pb::Reader r) {
     OnnxValueInfo out;
     while (r.ok()) {
-        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        int wt; uint64_t v = 0; pb::Reader s{nullptr, nullptr};
         const int f = r.next(wt, v, s);
         if (f == 1 && wt == 2) out.name = s.str();
         else if (f == 2 && wt == 2) {
@@ -134,7 +134,7 @@ inline OnnxValueInfo parse_value_info(pb::Reader r) {
 
 inline void parse_attr(pb::Reader r, std::string& name, OnnxAttr& a) {
     while (r.ok()) {
-        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        int wt; uint64_t v = 0; pb::Reader s{nullptr, nullptr};
         const int f = r.next(wt, v, s);
         if (f == 1 && wt == 2) name = s.str();
         else if (f == 2 && wt == 5) { uint32_t u = (uint32_t)v; memcpy(&a.f, &u, 4); }
@@ -147,7 +147,7 @@ inline void parse_attr(pb::Reader r, std::string& name, OnnxAttr& a) {
 inline OnnxNode parse_node(pb::Reader r) {
     OnnxNode n;
     while (r.ok()) {
-        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        int wt; uint64_t v = 0; pb::Reader s{nullptr, nullptr};
         const int f = r.next(wt, v, s);
         if (wt != 2) continue;
         if (f == 1) n.in.push_back(s.str());
@@ -169,7 +169,7 @@ inline OnnxFile load_onnx(const std::string& path) {
     OnnxFile out;
     pb::Reader r{buf.data(), buf.data() + buf.size()};
     while (r.ok()) {
-        int wt; uint64_t v; pb::Reader s{nullptr, nullptr};
+        int wt; uint64_t v = 0; pb::Reader s{nullptr, nullptr};
         int fno = r.next(wt, v, s);
         if (fno == 7 && wt == 2) {                       // GraphProto
             pb::Reader g = s;

@@ -4,11 +4,13 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <nlohmann/json.hpp>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 
 using json = nlohmann::json;
 
@@ -170,48 +172,57 @@ TextToSpeech::SynthesisResult TextToSpeech::batch(const std::vector<std::string>
     return _infer(text_list, lang_list, style, total_step, speed);
 }
 
-std::vector<TextToSpeech::Utterance> TextToSpeech::many(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list,
-                                                        const Style& style, int total_step, float speed, int max_batch) {
+// many() = plan (front-end once, groups of similar token counts) + run (packed launches of the groups on ONE engine).
+// MultiGpuTextToSpeech runs the same plan with the groups dealt out over several engines.
+TextToSpeech::ManyPlan TextToSpeech::planMany(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list,
+                                              int max_batch) const {
+    ManyPlan p;
     const int n = (int)text_list.size();
-    if (n != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
-    checkStyle(style, n);
-    std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;
-    textToIds(text_list, lang_list, ids, mask, T);
-    std::vector<int> tok(n), order(n);
-    for (int i = 0; i < n; ++i) tok[i] = (int)std::accumulate(mask.begin() + (size_t)i * T, mask.begin() + (size_t)(i + 1) * T, 0.f);
+    textToIds(text_list, lang_list, p.ids, p.mask, p.T);
+    p.tok.resize(n);
+    for (int i = 0; i < n; ++i) p.tok[i] = (int)std::accumulate(p.mask.begin() + (size_t)i * p.T, p.mask.begin() + (size_t)(i + 1) * p.T, 0.f);
+    std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tok[a] < tok[b]; });     // similar token counts share a group
-    std::vector<Utterance> out(n);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.tok[a] < p.tok[b]; });     // similar token counts share a group
+    for (int g0 = 0; g0 < n; g0 += max_batch) p.groups.emplace_back(order.begin() + g0, order.begin() + std::min(n, g0 + max_batch));
+    return p;
+}
+
+void TextToSpeech::runGroups(const ManyPlan& plan, const std::vector<int>& group_ids, const Style& style, int total_step, float speed,
+                             uint64_t seed, std::vector<Utterance>& out) {
     const int cs = geo_.chunk_size;
-    ++calls_;
-    // Groups go out as an asynchronous request stream (stc_synthesize_packed_async): the device->host copy of group g runs
+    const int64_t T = plan.T;
+    // Groups go out as an asynchronous request stream (stc_synthesize_packed_ex, async): the device->host copy of group g runs
     // while group g+1 is computed. Each group gets its own page-locked result buffer; everything lands at stc_wait.
-    struct Pending { std::vector<int> grp; float* wav = nullptr; std::vector<int64_t> off, wl; std::vector<float> dur; };
+    struct Pending { const std::vector<int>* grp; float* wav = nullptr; std::vector<int64_t> off, wl, nidx; std::vector<float> dur; };
     std::vector<Pending> pend;
     auto free_all = [&]() { for (auto& p : pend) stc_pinned_free(p.wav); };
     try {
-        for (int g0 = 0; g0 < n; g0 += max_batch) {
+        for (int gi : group_ids) {
             Pending p;
-            p.grp.assign(order.begin() + g0, order.begin() + std::min(n, g0 + max_batch));
-            const int B = (int)p.grp.size(), Tg = tok[p.grp.back()];
-            std::vector<int64_t> gi((size_t)B * Tg); std::vector<float> gm((size_t)B * Tg);
+            p.grp = &plan.groups[gi];
+            const std::vector<int>& grp = *p.grp;
+            const int B = (int)grp.size(), Tg = plan.tok[grp.back()];
+            std::vector<int64_t> gids((size_t)B * Tg); std::vector<float> gm((size_t)B * Tg);
             int64_t toks = 0;
             for (int k = 0; k < B; ++k) {
-                std::copy_n(ids.begin() + (size_t)p.grp[k] * T, Tg, gi.begin() + (size_t)k * Tg);
-                std::copy_n(mask.begin() + (size_t)p.grp[k] * T, Tg, gm.begin() + (size_t)k * Tg);
-                toks += tok[p.grp[k]];
+                std::copy_n(plan.ids.begin() + (size_t)grp[k] * T, Tg, gids.begin() + (size_t)k * Tg);
+                std::copy_n(plan.mask.begin() + (size_t)grp[k] * T, Tg, gm.begin() + (size_t)k * Tg);
+                toks += plan.tok[grp[k]];
             }
-            Style st = style.slice(p.grp);
+            Style st = style.slice(grp);
             int64_t cap = (int64_t)((double)toks * 0.12 * sample_rate_) + (int64_t)(B + 8) * cs;
             p.off.assign(B + 1, 0); p.wl.assign(B, 0); p.dur.assign(B, 0.f);
+            p.nidx.assign(grp.begin(), grp.end());          // noise stream = index in the REQUEST: the result does not depend on grouping / sharding
+            stc_out_opts oo{}; oo.noise_index = p.nidx.data();
             for (int attempt = 0;; ++attempt) {
                 void* mem = nullptr;
                 if (stc_pinned_alloc((size_t)cap * sizeof(float), &mem) != STC_OK) raise(nullptr, "stc_pinned_alloc");
                 p.wav = static_cast<float*>(mem);
-                int rc = stc_synthesize_packed_async(engine_, gi.data(), gm.data(), st.getTtlData().data(), st.getDpData().data(), B, Tg,
-                                                     total_step, speed, seed_ + calls_, p.wav, cap, p.off.data(), p.dur.data(), p.wl.data());
+                int rc = stc_synthesize_packed_ex(engine_, gids.data(), gm.data(), st.getTtlData().data(), st.getDpData().data(), B, Tg, total_step,
+                                                  speed, nullptr, 0, seed, &oo, p.wav, cap, p.off.data(), p.dur.data(), p.wl.data(), 1);
                 if (rc == STC_ERR_CAPACITY && attempt == 0 && p.off[B] > cap) { stc_pinned_free(p.wav); p.wav = nullptr; cap = p.off[B]; continue; }
-                if (rc != STC_OK) { stc_pinned_free(p.wav); p.wav = nullptr; raise(engine_, "stc_synthesize_packed_async"); }
+                if (rc != STC_OK) { stc_pinned_free(p.wav); p.wav = nullptr; raise(engine_, "stc_synthesize_packed_ex"); }
                 break;
             }
             pend.push_back(std::move(p));          // (the library keeps at most two calls in flight)
@@ -219,29 +230,103 @@ std::vector<TextToSpeech::Utterance> TextToSpeech::many(const std::vector<std::s
         if (stc_wait(engine_) != STC_OK) raise(engine_, "stc_wait");
     } catch (...) { stc_wait(engine_); free_all(); throw; }
     for (auto& p : pend)
-        for (size_t k = 0; k < p.grp.size(); ++k) {
-            Utterance& u = out[p.grp[k]];
+        for (size_t k = 0; k < p.grp->size(); ++k) {
+            Utterance& u = out[(*p.grp)[k]];
             u.duration = p.dur[k];
             u.wav.assign(p.wav + p.off[k], p.wav + p.off[k] + p.wl[k]);
         }
     free_all();
+}
+
+std::vector<TextToSpeech::Utterance> TextToSpeech::many(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list,
+                                                        const Style& style, int total_step, float speed, int max_batch) {
+    const int n = (int)text_list.size();
+    if (n != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
+    checkStyle(style, n);
+    ManyPlan plan = planMany(text_list, lang_list, max_batch);
+    std::vector<int> all(plan.groups.size());
+    std::iota(all.begin(), all.end(), 0);
+    std::vector<Utterance> out(n);
+    ++calls_;
+    runGroups(plan, all, style, total_step, speed, seed_ + calls_, out);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------- several GPUs of one box
+// north_star: "a request batch is length-bucketed and partitioned across the 8 B200s of one box. Each GPU holds a full weight replica
+// and no collective runs on the hot path". The reference entry point that fans out is TextToSpeech::batch (cpp/helper.cpp:725-734).
+MultiGpuTextToSpeech::MultiGpuTextToSpeech(const std::string& onnx_dir, const std::vector<int>& devices) {
+    if (devices.empty()) throw std::runtime_error("MultiGpuTextToSpeech: no devices given");
+    for (int d : devices) engines_.push_back(loadTextToSpeech(onnx_dir, true, d));
+}
+
+std::vector<TextToSpeech::Utterance> MultiGpuTextToSpeech::many(const std::vector<std::string>& text_list,
+                                                                const std::vector<std::string>& lang_list, const Style& style,
+                                                                int total_step, float speed, int max_batch) {
+    const int n = (int)text_list.size(), nd = (int)engines_.size();
+    if (n != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
+    engines_[0]->checkStyle(style, n);
+    TextToSpeech::ManyPlan plan = engines_[0]->planMany(text_list, lang_list, max_batch);
+    // longest-processing-time-first over the groups; cost ~ tokens (frames are proportional) x (Euler steps + vocoder share)
+    std::vector<double> cost(plan.groups.size(), 0.0);
+    for (size_t g = 0; g < plan.groups.size(); ++g)
+        for (int i : plan.groups[g]) cost[g] += (double)plan.tok[i] * (total_step * 1.0 + 6 * 4.0 * 0.35);
+    std::vector<int> order(plan.groups.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<std::vector<int>> shard(nd);
+    std::vector<double> load(nd, 0.0);
+    for (int g : order) {
+        const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[r].push_back(g); load[r] += cost[g];
+    }
+    std::vector<TextToSpeech::Utterance> out(n);
+    ++calls_;
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> err(nd);
+    for (int r = 0; r < nd; ++r)
+        th.emplace_back([&, r]() {
+            try { if (!shard[r].empty()) engines_[r]->runGroups(plan, shard[r], style, total_step, speed, seed_ + calls_, out); }
+            catch (...) { err[r] = std::current_exception(); }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
     return out;
 }
 
 TextToSpeech::SynthesisResult TextToSpeech::callBatched(const std::string& text, const std::string& lang, const Style& style,
                                                         int total_step, float speed, float silence_duration) {
+    // `call()` with the chunks as ONE packed batch: the untrimmed chunk waveforms joined with (int)(silence * sr) zeros exactly as
+    // cpp/helper.cpp:703-716 does on the host — here the library writes the joined waveform on the device (stc_out_opts.gap_samples)
     if (style.getTtlShape()[0] != 1) throw std::runtime_error("Single speaker text to speech only supports single style");
     std::vector<std::string> chunks = chunkText(text, lang == "ko" ? 120 : 300);
-    std::vector<std::string> langs(chunks.size(), lang);
-    Style st = style.slice(std::vector<int>(chunks.size(), 0));
-    std::vector<Utterance> parts = many(chunks, langs, st, total_step, speed, (int)chunks.size());
+    const int n = (int)chunks.size();
+    std::vector<std::string> langs(n, lang);
+    Style st = style.slice(std::vector<int>(n, 0));
+    checkStyle(st, n);
+    std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;
+    textToIds(chunks, langs, ids, mask, T);
+    const int cs = geo_.chunk_size;
+    stc_out_opts oo{};
+    oo.pcm16 = 0; oo.gap_samples = (int64_t)static_cast<int>(silence_duration * sample_rate_);
+    double toks = 0;
+    for (float m : mask) toks += m;
+    int64_t cap = (int64_t)(toks * 0.12 * sample_rate_) + (int64_t)(n + 8) * cs + (int64_t)(n - 1) * oo.gap_samples;
+    std::vector<int64_t> off(n + 1, 0), wl(n, 0);
+    std::vector<float> dur(n, 0.f);
     SynthesisResult out;
-    float total = 0.f;
-    for (size_t i = 0; i < parts.size(); ++i) {
-        if (i) { out.wav.resize(out.wav.size() + (size_t)static_cast<int>(silence_duration * sample_rate_), 0.f); total += silence_duration; }
-        out.wav.insert(out.wav.end(), parts[i].wav.begin(), parts[i].wav.end());
-        total += parts[i].duration;
+    ++calls_;
+    for (int attempt = 0;; ++attempt) {
+        out.wav.resize((size_t)cap);
+        int rc = stc_synthesize_packed_ex(engine_, ids.data(), mask.data(), st.getTtlData().data(), st.getDpData().data(), n, (int)T, total_step,
+                                          speed, nullptr, 0, seed_ + calls_, &oo, out.wav.data(), cap, off.data(), dur.data(), wl.data(), 0);
+        if (rc == STC_ERR_CAPACITY && attempt == 0 && off[n] > cap) { cap = off[n]; continue; }
+        if (rc != STC_OK) raise(engine_, "stc_synthesize_packed_ex");
+        break;
     }
+    out.wav.resize((size_t)off[n]);
+    float total = dur[0];
+    for (int i = 1; i < n; ++i) total += dur[i] + silence_duration;
     out.duration = {total};
     return out;
 }
@@ -319,6 +404,31 @@ long stc_host_wav_bytes(const float* audio, size_t n, int sample_rate, unsigned 
     if (b.size() > cap) return -5;
     std::memcpy(out, b.data(), b.size());
     return (long)b.size();
+}
+// many() on one engine vs MultiGpuTextToSpeech::many() on `nd` devices for the same request and seed: per utterance the duration, the
+// sample count and the sum of |samples| of both (tests/test_multi_gpu.py compares them).
+int stc_host_many_check(const char* onnx_dir, const int* devices, int nd, const char* const* texts, const char* const* langs, int n,
+                        const char* const* style_paths, int total_step, float speed, int max_batch, float* dur, int64_t* nsamp, double* asum) {
+    try {
+        std::vector<std::string> tx(texts, texts + n), lg(langs, langs + n);
+        supertonic::Style st = supertonic::loadVoiceStyle(std::vector<std::string>(style_paths, style_paths + n));
+        auto fill = [&](const std::vector<supertonic::TextToSpeech::Utterance>& u, int k) {
+            for (int i = 0; i < n; ++i) {
+                dur[k * n + i] = u[i].duration; nsamp[k * n + i] = (int64_t)u[i].wav.size();
+                double s = 0; for (float v : u[i].wav) s += std::fabs((double)v);
+                asum[k * n + i] = s;
+            }
+        };
+        {
+            auto one = supertonic::loadTextToSpeech(onnx_dir, true, devices[0]);
+            one->setNoiseSeed(11);
+            fill(one->many(tx, lg, st, total_step, speed, max_batch), 0);
+        }
+        supertonic::MultiGpuTextToSpeech multi(onnx_dir, std::vector<int>(devices, devices + nd));
+        multi.setNoiseSeed(11);
+        fill(multi.many(tx, lg, st, total_step, speed, max_batch), 1);
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "stc_host_many_check: %s\n", e.what()); return -1; }
 }
 int stc_host_load_voice_style(const char* const* paths, int n, int64_t shapes[6], double sums[2], float ttl_head[4]) {
     try {

@@ -66,13 +66,26 @@ public:
                          float speed = 1.05f, float silence_duration = 0.3f);
     SynthesisResult batch(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list, const Style& style,
                           int total_step, float speed = 1.05f);
-    // call() with every chunk of the text synthesised in ONE packed batch; same concatenation rule, chunk wavs trimmed
-    // to their frame count (untrimmed L*cs rows do not exist on packed rows).
+    // call() with every chunk of the text synthesised in ONE packed batch: the same joined waveform (untrimmed chunk rows +
+    // silence), written on the device (stc_out_opts.gap_samples).
     SynthesisResult callBatched(const std::string& text, const std::string& lang, const Style& style, int total_step,
                                 float speed = 1.05f, float silence_duration = 0.3f);
     // Independent utterances (style row i belongs to text i), packed latent rows, at most `max_batch` per launch group.
     std::vector<Utterance> many(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list, const Style& style,
                                 int total_step, float speed = 1.05f, int max_batch = 128);
+
+    // many() in two halves, so that MultiGpuTextToSpeech can deal the groups of one plan out over several engines:
+    struct ManyPlan {
+        std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;      // front-end output for the whole request
+        std::vector<int> tok;                                                   // token count per text
+        std::vector<std::vector<int>> groups;                                   // text indices per launch group (similar token counts)
+    };
+    ManyPlan planMany(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list, int max_batch) const;
+    // Synthesises the groups `group_ids` of `plan` on this engine into out[text index]. Noise streams are keyed by the text's index in
+    // the request (stc_out_opts.noise_index), so the result does not depend on how the request was grouped or sharded.
+    void runGroups(const ManyPlan& plan, const std::vector<int>& group_ids, const Style& style, int total_step, float speed,
+                   uint64_t seed, std::vector<Utterance>& out);
+    void checkStyle(const Style& style, int bsz) const;
 
     int getSampleRate() const { return sample_rate_; }
     // Noise: Philox keyed by (seed + call index); or inject N(0,1) as [B][D][ld] for the NEXT _infer only.
@@ -85,7 +98,6 @@ private:
                            int total_step, float speed);
     void textToIds(const std::vector<std::string>& texts, const std::vector<std::string>& langs, std::vector<int64_t>& ids,
                    std::vector<float>& mask, int64_t& T) const;
-    void checkStyle(const Style& style, int bsz) const;
     Config cfgs_;
     stc_handle* engine_;
     stc_config geo_{};
@@ -93,6 +105,21 @@ private:
     uint64_t seed_ = 0, calls_ = 0;
     std::vector<float> noise_;
     int64_t noise_ld_ = 0;
+};
+
+// One process, several GPUs of one box: a full weight replica (TextToSpeech engine) + a host thread per device; a request is
+// length-bucketed into launch groups once and the groups are dealt out longest-first (no collective, no inter-GPU traffic).
+class MultiGpuTextToSpeech {
+public:
+    MultiGpuTextToSpeech(const std::string& onnx_dir, const std::vector<int>& devices);
+    std::vector<TextToSpeech::Utterance> many(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list,
+                                              const Style& style, int total_step, float speed = 1.05f, int max_batch = 128);
+    int deviceCount() const { return (int)engines_.size(); }
+    TextToSpeech& engine(int i) { return *engines_[i]; }
+    void setNoiseSeed(uint64_t seed) { seed_ = seed; calls_ = 0; }
+private:
+    std::vector<std::unique_ptr<TextToSpeech>> engines_;
+    uint64_t seed_ = 0, calls_ = 0;
 };
 
 Config loadCfgs(const std::string& onnx_dir);

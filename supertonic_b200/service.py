@@ -245,13 +245,17 @@ _app = None
 
 def get_app():
     """The service configured from the environment like the reference's (py/service.py:19-24): TTS_ONNX_DIR, plus
-    TTS_DEVICE, TTS_MAX_BATCH, TTS_MAX_WAIT_MS. TTS_USE_GPU=0 is refused: there is no CPU path here."""
+    TTS_DEVICE (one GPU) or TTS_DEVICES (e.g. "0-7": one engine + host thread per GPU, every coalesced launch group dealt out over
+    them — tts.MultiGpuTextToSpeech), TTS_MAX_BATCH, TTS_MAX_WAIT_MS. TTS_USE_GPU=0 is refused: there is no CPU path here."""
     global _app
     if _app is None:
         from . import tts as T
         if os.getenv("TTS_USE_GPU", "1").strip().lower() in {"0", "false", "no", "n", "off"}:
             raise RuntimeError("supertonic_b200.service is GPU-only (TTS_USE_GPU=0 requested)")
-        tt = T.load_text_to_speech(os.getenv("TTS_ONNX_DIR", "assets/onnx"), True, int(os.getenv("TTS_DEVICE", "0")))
+        onnx_dir = os.getenv("TTS_ONNX_DIR", "assets/onnx")
+        devs = os.getenv("TTS_DEVICES", "").strip()
+        tt = (T.MultiGpuTextToSpeech(onnx_dir, T.parse_devices(devs)) if devs
+              else T.load_text_to_speech(onnx_dir, True, int(os.getenv("TTS_DEVICE", "0"))))
         _app = create_app(tt, max_batch=int(os.getenv("TTS_MAX_BATCH", "32")), max_wait_ms=float(os.getenv("TTS_MAX_WAIT_MS", "2")))
     return _app
 

@@ -82,6 +82,13 @@ def wav_file_bytes(audio: np.ndarray, sample_rate: int) -> bytes:
             struct.pack("<ihhiihh", 16, 1, 1, sample_rate, sample_rate * 2, 2, 16) + b"data" + struct.pack("<i", len(data)) + data)
 
 
+def wav_file_bytes_pcm16(pcm: np.ndarray, sample_rate: int) -> bytes:
+    """The same file from samples already quantised on the device (stc_out_opts.pcm16)."""
+    data = np.ascontiguousarray(pcm, dtype="<i2").tobytes()
+    return (b"RIFF" + struct.pack("<i", 36 + len(data)) + b"WAVEfmt " +
+            struct.pack("<ihhiihh", 16, 1, 1, sample_rate, sample_rate * 2, 2, 16) + b"data" + struct.pack("<i", len(data)) + data)
+
+
 def write_wav_file(filename: str, audio: np.ndarray, sample_rate: int) -> None:
     try:
         with open(filename, "wb") as f:
@@ -144,6 +151,26 @@ class TextToSpeech:
                 dur_cat = np.float32(dur_cat + np.float32(r.duration[0] + np.float32(silence_duration)))
         return SynthesisResult(wav_cat, np.asarray([dur_cat], np.float32))
 
+    def call_batched(self, text, lang: str, style: Style, total_step: int, speed: float = 1.05, silence_duration: float = 0.3,
+                     pcm16: bool = False, seed: Optional[int] = None) -> SynthesisResult:
+        """`call()` with the chunks of the text as ONE packed batch: same result layout — the untrimmed chunk waveforms joined with
+        (int)(silence_duration * sample_rate) zeros (cpp/helper.cpp:703-716) — but the join (and, with pcm16=True, writeWavFile's
+        quantisation, cpp/helper.cpp:985-988) happens on the device and one launch serves the whole text.
+        `wav` is float32, or int16 PCM with pcm16=True (half the device->host bytes)."""
+        if style.ttl.shape[0] != 1:
+            raise RuntimeError("Single speaker text to speech only supports single style")
+        chunks = chunk_text(text, 120 if lang == "ko" else 300)
+        n = len(chunks)
+        ids, mask = self.engine.text_to_ids(chunks, [lang] * n)
+        self._calls += 1
+        gap = int(np.float32(silence_duration) * np.float32(self.sample_rate))
+        r = self.engine.synthesize_joined(ids, mask, np.repeat(style.ttl, n, 0), np.repeat(style.dp, n, 0), total_step, speed,
+                                          seed=self.noise_seed + self._calls if seed is None else seed, pcm16=pcm16, gap_samples=gap)
+        dur = np.float32(r["duration"][0])
+        for d in r["duration"][1:]:
+            dur = np.float32(dur + np.float32(d + np.float32(silence_duration)))
+        return SynthesisResult(r["out"], np.asarray([dur], np.float32))
+
     # -- cpp/helper.cpp:725-734
     def batch(self, text_list, lang_list, style: Style, total_step: int, speed: float = 1.05) -> SynthesisResult:
         return self._infer(text_list, lang_list, style, total_step, speed)
@@ -151,34 +178,121 @@ class TextToSpeech:
     # -- throughput path (north_star: "a request batch is length-bucketed")
     def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05,
                         max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None, copy: bool = False,
-                        wait: bool = True):
+                        wait: bool = True, pcm16: bool = False):
         """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
         rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
         utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
-        (tests: batch-composition invariance). With copy=False the waveforms are views into the engine's page-locked result
-        buffers (one per group, two alternating sets), valid until the call after the next one. Groups are issued
-        asynchronously: the device->host copy of one group overlaps the computation of the next. wait=False returns before the
-        last copies have landed — call `engine.wait()` before reading the waveforms; issuing the next synthesize_many first
-        overlaps its computation with these copies (request streams)."""
-        from .scheduler import length_buckets
-        n = len(texts)
-        ids, mask = self.engine.text_to_ids(texts, langs)
-        lens = mask.reshape(n, -1).sum(1).astype(np.int64)
-        out: List[Optional[Tuple[np.ndarray, float]]] = [None] * n
+        (tests: batch-composition invariance; device noise streams are keyed by the utterance's index in the REQUEST).
+        With copy=False the waveforms are views into the engine's page-locked result buffers (one per group, two alternating
+        sets): they stay valid until the SECOND-next synthesize_many on this object — copy them (copy=True) to keep them longer.
+        Groups are issued asynchronously: the device->host copy of one group overlaps the computation of the next. wait=False
+        returns before the last copies have landed — call `engine.wait()` before reading the waveforms; issuing the next
+        synthesize_many first overlaps its computation with these copies (request streams). pcm16=True: int16 samples quantised
+        on the device (writeWavFile's rule), half the device->host bytes."""
+        plan = plan_many(self.engine, texts, langs, max_batch)
+        out: List[Optional[Tuple[np.ndarray, float]]] = [None] * len(texts)
         self._parity = 1 - getattr(self, "_parity", 1)
-        for gi, grp in enumerate(length_buckets(lens, max_batch, 1e9)):
-            g = np.asarray(grp)
-            T = int(lens[g].max())
-            r = self.engine.synthesize_packed(ids[g, :T], mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed,
-                                              seed=seed, noise=None if noise is None else noise[g],
-                                              pinned=f"wav_packed{gi}_{self._parity}", wait=False)
-            for k, i in enumerate(grp):
-                out[i] = (r["wavs"][k], float(r["duration"][k]))
+        run_groups(self.engine, plan, range(len(plan.groups)), style, total_step, speed, seed, out, tag=f"p{self._parity}", noise=noise, pcm16=pcm16)
         if wait or copy:
             self.engine.wait()
             if copy:
                 out = [(w.copy(), d) for w, d in out]
         return out
+
+
+@dataclass
+class ManyPlan:
+    ids: np.ndarray             # [n, T] token ids of the whole request (text front-end run once)
+    mask: np.ndarray            # [n, 1, T]
+    lens: np.ndarray            # [n] token counts
+    groups: List[List[int]]     # text indices per launch group (similar token counts)
+
+
+def plan_many(engine: capi.Engine, texts, langs, max_batch: int) -> ManyPlan:
+    from .scheduler import length_buckets
+    ids, mask = engine.text_to_ids(texts, langs)
+    lens = mask.reshape(len(texts), -1).sum(1).astype(np.int64)
+    return ManyPlan(ids, mask, lens, length_buckets(lens, max_batch, 1e9))
+
+
+def run_groups(engine: capi.Engine, plan: ManyPlan, group_ids, style: Style, total_step: int, speed: float, seed: int, out: list,
+               tag: str = "", noise: Optional[np.ndarray] = None, pcm16: bool = False) -> None:
+    """The launch groups `group_ids` of `plan` on ONE engine, as an asynchronous request stream; fills out[text index] with
+    (trimmed waveform view, duration). The caller waits (`engine.wait()`) before reading the waveforms."""
+    for gi in group_ids:
+        g = np.asarray(plan.groups[gi])
+        T = int(plan.lens[g].max())
+        r = engine.synthesize_joined(plan.ids[g, :T], plan.mask[g, :, :T], style.ttl[g], style.dp[g], total_step, speed, seed=seed,
+                                     noise=None if noise is None else noise[g], noise_index=g, pcm16=pcm16,
+                                     pinned=f"many{gi}_{tag}", wait=noise is not None)
+        for k, i in enumerate(g):
+            o = int(r["offsets"][k])
+            out[int(i)] = (r["out"][o:o + int(r["wav_lengths"][k])], float(r["duration"][k]))
+
+
+class MultiGpuTextToSpeech:
+    """One process, several GPUs of one box (north_star: "a request batch is length-bucketed and partitioned across the 8 B200s of
+    one box; each GPU holds a full weight replica and no collective runs on the hot path"): one engine (handle, streams, CUDA-graph
+    cache, page-locked result buffers) and one host thread per device. The reference entry point that fans out is
+    TextToSpeech::batch (cpp/helper.cpp:725-734). A request is bucketed into launch groups ONCE (front-end on the host), the groups
+    are dealt out longest-processing-time-first by predicted cost, and results come back in input order. Noise streams are keyed by
+    the utterance's index in the request, so the audio does not depend on the number of devices."""
+
+    def __init__(self, onnx_dir: Optional[str], devices: Sequence[int], precision: int = capi.PREC_DEFAULT, engines=None):
+        if not len(devices):
+            raise RuntimeError("MultiGpuTextToSpeech: no devices given")
+        self.devices = [int(d) for d in devices]
+        # (`engines`: already-built capi.Engine objects, one per entry of `devices` — used by tests)
+        self.engines = list(engines) if engines is not None else [capi.Engine(onnx_dir, d, precision) for d in self.devices]
+        self.engine = self.engines[0]
+        self.cfg = self.engine.cfg
+        self.sample_rate = self.cfg.sample_rate
+        self._parity = 1
+        self._first = TextToSpeech(self.engine)        # single-utterance entry points (latency path) run on the first device
+
+    def get_sample_rate(self) -> int:
+        return self.sample_rate
+
+    def call(self, *a, **k):
+        return self._first.call(*a, **k)
+
+    def call_batched(self, *a, **k):
+        return self._first.call_batched(*a, **k)
+
+    def batch(self, *a, **k):
+        return self._first.batch(*a, **k)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05, max_batch: int = 128, seed: int = 0,
+                        copy: bool = False, pcm16: bool = False):
+        import threading
+        from .scheduler import shard_lpt, synth_cost
+        if len(texts) != style.ttl.shape[0]:
+            raise RuntimeError("Number of texts must match number of style vectors")
+        plan = plan_many(self.engine, texts, langs, max_batch)
+        costs = [sum(synth_cost(int(plan.lens[i]), total_step) for i in g) for g in plan.groups]
+        shards = shard_lpt(costs, len(self.engines))
+        out: List[Optional[Tuple[np.ndarray, float]]] = [None] * len(texts)
+        self._parity = 1 - self._parity
+        errs: List[BaseException] = []
+
+        def work(r):
+            try:
+                run_groups(self.engines[r], plan, shards[r], style, total_step, speed, seed, out, tag=f"p{self._parity}", pcm16=pcm16)
+                self.engines[r].wait()
+            except BaseException as e:      # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(r,)) for r in range(len(self.engines)) if shards[r]]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return [(w.copy(), d) for w, d in out] if copy else out
 
 
 def load_text_to_speech(onnx_dir: str, use_gpu: bool = True, device: int = 0, precision: int = capi.PREC_DEFAULT) -> TextToSpeech:
@@ -187,3 +301,20 @@ def load_text_to_speech(onnx_dir: str, use_gpu: bool = True, device: int = 0, pr
     if not use_gpu:
         raise RuntimeError("CPU mode is not supported by supertonic_b200 (use the reference's ONNX Runtime path)")
     return TextToSpeech(capi.Engine(onnx_dir, device, precision))
+
+
+def parse_devices(spec: str) -> List[int]:
+    """'0-3' / '0,2,5' / '0-1,4' -> [device indices] (service env TTS_DEVICES, CLI --devices)."""
+    out: List[int] = []
+    for part in str(spec).split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-", 1)
+            out += list(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    if not out:
+        raise ValueError(f"no devices in {spec!r}")
+    return out
