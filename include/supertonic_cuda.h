@@ -249,6 +249,12 @@ int stc_debug_mlp(stc_handle* h, int M, int iters, float* ms_fused, float* ms_un
 int stc_debug_dwconv(stc_handle* h, int rows, int C, int K, int dil, int causal, int B, int rt, int iters, float* ms_slide,
                      float* ms_tile, float* max_abs_diff);
 
+/* The layer plan derived from the NODES of one graph file (kind: "duration_predictor" | "text_encoder" | "vector_estimator" |
+ * "vocoder") as a JSON string — what stc_create uses for graphs that carry no `stc_arch` metadata (a released export; the reference
+ * loads whatever is on disk, cpp/helper.cpp:776-795). Host only. STC_ERR_UNSUPPORTED with the list of unexplained nodes when a
+ * pattern is not recognised; STC_ERR_CAPACITY (and *need) when buf is too small. */
+int stc_derive_arch(const char* onnx_path, const char* kind, char* buf, size_t cap, size_t* need);
+
 /* The device PCM16 quantiser of stc_out_opts.pcm16 on n caller-provided float samples (known-answer tests against the reference's
  * writeWavFile, cpp/helper.cpp:985-988). */
 int stc_debug_pcm16(stc_handle* h, const float* samples, int64_t n, int16_t* out);

@@ -53,6 +53,7 @@ _SIGS = {
     "stc_synthesize_packed_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp, _vp]),
     "stc_synthesize_packed_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i64, C.c_uint64, _vp, _vp, _i64, _vp, _vp, _vp, _i]),
     "stc_debug_pcm16": (_i, [_vp, _vp, _i64, _vp]),
+    "stc_derive_arch": (_i, [C.c_char_p, C.c_char_p, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "stc_wait": (_i, [_vp]),
     "stc_synthesize_packed_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, C.c_uint64, _vp, _i64, _vp, _vp]),
     "stc_pinned_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
@@ -136,6 +137,20 @@ def chunk_text(text, max_len: int) -> List[bytes]:
         if rc != ERR_CAPACITY:
             raise StcError(rc, lib.stc_last_error(None).decode())
         cap = need.value + 16
+
+
+def derive_arch(onnx_path: str, kind: str) -> dict:
+    """The layer plan the library derives from a graph's NODES (csrc/graph_plan.h) — host only, no GPU."""
+    import json
+    need = C.c_size_t(0)
+    lib.stc_derive_arch(_b(onnx_path), _b(kind), None, 0, C.byref(need))
+    if not need.value:
+        raise StcError(-4, lib.stc_last_error(None).decode())
+    buf = C.create_string_buffer(need.value + 16)
+    rc = lib.stc_derive_arch(_b(onnx_path), _b(kind), buf, need.value + 16, C.byref(need))
+    if rc != STC_OK:
+        raise StcError(rc, lib.stc_last_error(None).decode())
+    return json.loads(buf.value.decode())
 
 
 class Frontend:

@@ -20,6 +20,7 @@
 #include "mlp_stream.cuh"
 #include "gemm2_tc.cuh"
 #include "model.cuh"
+#include "graph_plan.h"
 #include "dp_fused.cuh"
 #include "dwconv_chain.cuh"
 #include "text_frontend.h"
@@ -173,7 +174,7 @@ struct Handle {
     void load(const std::string& onnx_dir);
     float* upload_f32(const float* p, size_t n);
     float* W(const OnnxFile& f, const std::string& name, size_t numel);
-    Linear make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, int tc);
+    Linear make_linear(const OnnxFile& f, const std::string& wname, const std::string& bname, int K, int N, int tc);
     Linear make_linear_host(const std::vector<float>& w_kn, const std::vector<float>& bias, int K, int N, int tc);
     void load_net(const OnnxFile& f, const json& arch, Net& net, int tc);
     ConvNeXt load_convnext(const OnnxFile& f, const json& l, int tc);
@@ -417,9 +418,17 @@ Linear Handle::make_linear_host(const std::vector<float>& w_kn, const std::vecto
     return l;
 }
 
-Linear Handle::make_linear(const OnnxFile& f, const std::string& prefix, int K, int N, int tc) {
-    const OnnxTensor& w = get_tensor(f, prefix + ".weight", (size_t)K * N);
-    const OnnxTensor& b = get_tensor(f, prefix + ".bias", (size_t)N);
+// Initializer name of role `key` of a layer (or of the graph): the name the node-pattern matcher found in that position
+// (graph_plan.h, entry "t"), else the surrogate generator's naming scheme.
+static std::string tn(const json& l, const char* key, const std::string& dflt) {
+    auto it = l.find("t");
+    if (it != l.end() && it->contains(key)) return it->at(key).get<std::string>();
+    return dflt;
+}
+
+Linear Handle::make_linear(const OnnxFile& f, const std::string& wname, const std::string& bname, int K, int N, int tc) {
+    const OnnxTensor& w = get_tensor(f, wname, (size_t)K * N);
+    const OnnxTensor& b = get_tensor(f, bname, (size_t)N);
     return make_linear_host(std::vector<float>(w.f32(), w.f32() + w.numel()), std::vector<float>(b.f32(), b.f32() + b.numel()), K, N, tc);
 }
 
@@ -431,19 +440,19 @@ ConvNeXt Handle::load_convnext(const OnnxFile& f, const json& l, int tc) {
     c.masked = l.at("masked");
     int span = c.dil * (c.K - 1);
     c.pad_left = causal ? span : span / 2;
-    c.dw_w = W(f, p + ".dw.weight", (size_t)c.C * c.K);
+    c.dw_w = W(f, tn(l, "dw_w", p + ".dw.weight"), (size_t)c.C * c.K);
     {   // tap-major copy for the vectorised kernel
-        const float* w = get_tensor(f, p + ".dw.weight", (size_t)c.C * c.K).f32();
+        const float* w = get_tensor(f, tn(l, "dw_w", p + ".dw.weight"), (size_t)c.C * c.K).f32();
         std::vector<float> wt((size_t)c.C * c.K);
         for (int ch = 0; ch < c.C; ++ch) for (int k = 0; k < c.K; ++k) wt[(size_t)k * c.C + ch] = w[(size_t)ch * c.K + k];
         c.dw_wt = upload_f32(wt.data(), wt.size());
     }
-    c.dw_b = W(f, p + ".dw.bias", c.C);
-    c.ln_g = W(f, p + ".ln.weight", c.C);
-    c.ln_b = W(f, p + ".ln.bias", c.C);
-    c.gamma = W(f, p + ".gamma", c.C);
-    c.pw1 = make_linear(f, p + ".pw1", c.C, c.H, tc);
-    c.pw2 = make_linear(f, p + ".pw2", c.H, c.C, tc);
+    c.dw_b = W(f, tn(l, "dw_b", p + ".dw.bias"), c.C);
+    c.ln_g = W(f, tn(l, "ln_g", p + ".ln.weight"), c.C);
+    c.ln_b = W(f, tn(l, "ln_b", p + ".ln.bias"), c.C);
+    c.gamma = W(f, tn(l, "gamma", p + ".gamma"), c.C);
+    c.pw1 = make_linear(f, tn(l, "w1", p + ".pw1.weight"), tn(l, "b1", p + ".pw1.bias"), c.C, c.H, tc);
+    c.pw2 = make_linear(f, tn(l, "w2", p + ".pw2.weight"), tn(l, "b2", p + ".pw2.bias"), c.H, c.C, tc);
     return c;
 }
 
@@ -458,15 +467,15 @@ Attention Handle::load_attention(const OnnxFile& f, const json& l, int tc) {
     a.masked = l.at("masked"); a.key_masked = l.at("key_masked");
     int dh = a.C / a.heads;
     if (dh != 32 && dh != 64) throw StcError(STC_ERR_UNSUPPORTED, "attention head dim must be 32 or 64");
-    a.ln_g = W(f, p + ".ln.weight", a.C);
-    a.ln_b = W(f, p + ".ln.bias", a.C);
-    a.freqs = a.rope != ROPE_NONE ? W(f, p + ".rope_freqs", dh / 2) : nullptr;
+    a.ln_g = W(f, tn(l, "ln_g", p + ".ln.weight"), a.C);
+    a.ln_b = W(f, tn(l, "ln_b", p + ".ln.bias"), a.C);
+    a.freqs = a.rope != ROPE_NONE ? W(f, tn(l, "rope_freqs", p + ".rope_freqs"), dh / 2) : nullptr;
     if (a.rope != ROPE_NONE) {
         // rotary pairs (d, d + dh/2) of every head move to adjacent output columns (2i, 2i+1) of the Q and K projections
         // (kernels.cuh rope_kernel): Q.K^T does not change, and the GEMM epilogue can rotate inside one float4
-        auto permuted = [&](const std::string& name, int K) {
-            const float* w = get_tensor(f, name + ".weight", (size_t)K * a.C).f32();
-            const float* b = get_tensor(f, name + ".bias", (size_t)a.C).f32();
+        auto permuted = [&](const std::string& wname, const std::string& bname, int K) {
+            const float* w = get_tensor(f, wname, (size_t)K * a.C).f32();
+            const float* b = get_tensor(f, bname, (size_t)a.C).f32();
             std::vector<float> wp((size_t)K * a.C), bp(a.C);
             for (int n = 0; n < a.C; ++n) {
                 const int h = n / dh, j = n % dh, src = h * dh + ((j & 1) ? dh / 2 + j / 2 : j / 2);
@@ -475,14 +484,14 @@ Attention Handle::load_attention(const OnnxFile& f, const json& l, int tc) {
             }
             return make_linear_host(wp, bp, K, a.C, tc);
         };
-        a.q = permuted(p + ".q", a.C);
-        a.k = permuted(p + ".k", a.ctx_dim);
+        a.q = permuted(tn(l, "wq", p + ".q.weight"), tn(l, "bq", p + ".q.bias"), a.C);
+        a.k = permuted(tn(l, "wk", p + ".k.weight"), tn(l, "bk", p + ".k.bias"), a.ctx_dim);
     } else {
-        a.q = make_linear(f, p + ".q", a.C, a.C, tc);
-        a.k = make_linear(f, p + ".k", a.ctx_dim, a.C, tc);
+        a.q = make_linear(f, tn(l, "wq", p + ".q.weight"), tn(l, "bq", p + ".q.bias"), a.C, a.C, tc);
+        a.k = make_linear(f, tn(l, "wk", p + ".k.weight"), tn(l, "bk", p + ".k.bias"), a.ctx_dim, a.C, tc);
     }
-    a.v = make_linear(f, p + ".v", a.ctx_dim, a.C, tc);
-    a.o = make_linear(f, p + ".o", a.C, a.C, tc);
+    a.v = make_linear(f, tn(l, "wv", p + ".v.weight"), tn(l, "bv", p + ".v.bias"), a.ctx_dim, a.C, tc);
+    a.o = make_linear(f, tn(l, "wo", p + ".o.weight"), tn(l, "bo", p + ".o.bias"), a.C, a.C, tc);
     return a;
 }
 
@@ -498,28 +507,29 @@ void Handle::load_net(const OnnxFile& f, const json& arch, Net& net, int tc) {
             net.at.push_back(a); net.layers.push_back({L_ATTN, (int)net.at.size() - 1});
         } else if (type == "time_cond") {
             std::string p = l.at("name"); int C = l.at("C");
-            net.lin.push_back(make_linear(f, p, C, C, false)); net.layers.push_back({L_TIME_COND, (int)net.lin.size() - 1});
+            net.lin.push_back(make_linear(f, tn(l, "w", p + ".weight"), tn(l, "b", p + ".bias"), C, C, false));
+            net.layers.push_back({L_TIME_COND, (int)net.lin.size() - 1});
         } else if (type == "proj_in" || type == "proj_out") {
             std::string p = l.at("name"); int ci = l.at("cin"), co = l.at("cout");
-            net.lin.push_back(make_linear(f, p, ci, co, tc));
+            net.lin.push_back(make_linear(f, tn(l, "w", p + ".weight"), tn(l, "b", p + ".bias"), ci, co, tc));
             net.layers.push_back({type == "proj_in" ? L_PROJ_IN : L_PROJ_OUT, (int)net.lin.size() - 1});
         } else if (type == "time_mlp") {
             std::string p = l.at("name"); int td = l.at("time_dim"), C = l.at("C");
-            net.vec["time.freqs"] = W(f, p + ".freqs", td / 2);
-            net.lin.push_back(make_linear(f, p + ".fc1", td, C, false));
-            net.lin.push_back(make_linear(f, p + ".fc2", C, C, false));
+            net.vec["time.freqs"] = W(f, tn(l, "freqs", p + ".freqs"), td / 2);
+            net.lin.push_back(make_linear(f, tn(l, "w1", p + ".fc1.weight"), tn(l, "b1", p + ".fc1.bias"), td, C, false));
+            net.lin.push_back(make_linear(f, tn(l, "w2", p + ".fc2.weight"), tn(l, "b2", p + ".fc2.bias"), C, C, false));
             net.layers.push_back({L_TIME_MLP, (int)net.lin.size() - 2});
         } else if (type == "conv_in") {
             // Conv1d(ld -> C, K, causal) followed by eval-mode BatchNorm: fold BN into the conv (in double) and
             // express it as a [K*ld, C] linear over the im2col rows the front-end kernel writes.
             std::string p = l.at("name"), bn = l.at("bn");
             int ci = l.at("cin"), co = l.at("cout"), K = l.at("K");
-            const float* w = get_tensor(f, p + ".weight", (size_t)co * ci * K).f32();
-            const float* b = get_tensor(f, p + ".bias", co).f32();
-            const float* g = get_tensor(f, bn + ".weight", co).f32();
-            const float* be = get_tensor(f, bn + ".bias", co).f32();
-            const float* mu = get_tensor(f, bn + ".running_mean", co).f32();
-            const float* var = get_tensor(f, bn + ".running_var", co).f32();
+            const float* w = get_tensor(f, tn(l, "w", p + ".weight"), (size_t)co * ci * K).f32();
+            const float* b = get_tensor(f, tn(l, "b", p + ".bias"), co).f32();
+            const float* g = get_tensor(f, tn(l, "bn_w", bn + ".weight"), co).f32();
+            const float* be = get_tensor(f, tn(l, "bn_b", bn + ".bias"), co).f32();
+            const float* mu = get_tensor(f, tn(l, "bn_mean", bn + ".running_mean"), co).f32();
+            const float* var = get_tensor(f, tn(l, "bn_var", bn + ".running_var"), co).f32();
             std::vector<float> wk((size_t)K * ci * co), bb(co);
             for (int o = 0; o < co; ++o) {
                 double s = (double)g[o] / std::sqrt((double)var[o] + 1e-5);
@@ -531,20 +541,22 @@ void Handle::load_net(const OnnxFile& f, const json& arch, Net& net, int tc) {
             net.layers.push_back({L_CONV_IN, (int)net.lin.size() - 1});
         } else if (type == "head") {
             std::string p = l.at("name"); int ci = l.at("cin"), co = l.at("cout");
-            net.vec["head.ln_g"] = W(f, p + ".ln.weight", ci);
-            net.vec["head.ln_b"] = W(f, p + ".ln.bias", ci);
-            net.lin.push_back(make_linear(f, p + ".proj", ci, co, tc));
+            net.vec["head.ln_g"] = W(f, tn(l, "ln_g", p + ".ln.weight"), ci);
+            net.vec["head.ln_b"] = W(f, tn(l, "ln_b", p + ".ln.bias"), ci);
+            net.lin.push_back(make_linear(f, tn(l, "w", p + ".proj.weight"), tn(l, "b", p + ".proj.bias"), ci, co, tc));
             net.layers.push_back({L_HEAD, (int)net.lin.size() - 1});
         } else throw StcError(STC_ERR_UNSUPPORTED, "layer type " + type);
     }
 }
 
-static json arch_of(const OnnxFile& f, const std::string& path) {
+// Layer plan of a graph: the `stc_arch` metadata the surrogate generator writes (fast path), else derived from the NODES
+// (graph_plan.h) — what a released export carries. STC_IGNORE_ARCH=1 forces the derivation (tests).
+static json arch_of(const OnnxFile& f, const std::string& file, const std::string& kind) {
     auto it = f.metadata.find("stc_arch");
-    if (it == f.metadata.end())
-        throw StcError(STC_ERR_UNSUPPORTED, path + ": no 'stc_arch' metadata — only graphs whose layer plan is described are "
-                                                   "supported (topology matching of the released graphs is not implemented)");
-    return json::parse(it->second);
+    const char* ig = getenv("STC_IGNORE_ARCH");
+    if (it != f.metadata.end() && !(ig && ig[0] == '1')) return json::parse(it->second);
+    try { return derive_arch(f, kind); }
+    catch (const PlanError& e) { throw StcError(STC_ERR_UNSUPPORTED, file + ": " + e.what()); }
 }
 
 void Handle::load(const std::string& onnx_dir) {
@@ -562,10 +574,10 @@ void Handle::load(const std::string& onnx_dir) {
     bool tc = tc_mode();
     {
         OnnxFile f = load_onnx(onnx_dir + "/duration_predictor.onnx");
-        dp_arch = arch_of(f, "duration_predictor.onnx");
+        dp_arch = arch_of(f, "duration_predictor.onnx", "duration_predictor");
         load_net(f, dp_arch, dp, false);
         cfg.vocab_size = dp_arch.at("vocab");
-        dp.vec["embed"] = W(f, "dp.embed.weight", (size_t)cfg.vocab_size * dp.C);
+        dp.vec["embed"] = W(f, tn(dp_arch, "embed", "dp.embed.weight"), (size_t)cfg.vocab_size * dp.C);
         int si = dp_arch.at("style_in");
         {   // style_dp[B, e1, e2]: the split comes from the graph's input signature (the reference reads it from the voice-style
             // JSON, cpp/helper.cpp:856-861, and ORT checks it against the graph)
@@ -574,17 +586,17 @@ void Handle::load(const std::string& onnx_dir) {
                 throw StcError(STC_ERR_UNSUPPORTED, "duration_predictor.onnx: input style_dp must be [B, e1, e2] with e1*e2 = " + std::to_string(si));
             cfg.style_dp_tokens = (int)v->dims[1]; cfg.style_dp_dim = (int)v->dims[2];
         }
-        dp.lin.push_back(make_linear(f, "dp.style", si, dp.C, false));
-        dp.vec["head.ln_g"] = W(f, "dp.head.ln.weight", dp.C);
-        dp.vec["head.ln_b"] = W(f, "dp.head.ln.bias", dp.C);
-        dp.vec["head.w"] = W(f, "dp.head.proj.weight", dp.C);
-        dp.vec["head.b"] = W(f, "dp.head.proj.bias", 1);
+        dp.lin.push_back(make_linear(f, tn(dp_arch, "style_w", "dp.style.weight"), tn(dp_arch, "style_b", "dp.style.bias"), si, dp.C, false));
+        dp.vec["head.ln_g"] = W(f, tn(dp_arch, "head_ln_g", "dp.head.ln.weight"), dp.C);
+        dp.vec["head.ln_b"] = W(f, tn(dp_arch, "head_ln_b", "dp.head.ln.bias"), dp.C);
+        dp.vec["head.w"] = W(f, tn(dp_arch, "head_w", "dp.head.proj.weight"), dp.C);
+        dp.vec["head.b"] = W(f, tn(dp_arch, "head_b", "dp.head.proj.bias"), 1);
     }
     {
         OnnxFile f = load_onnx(onnx_dir + "/text_encoder.onnx");
-        te_arch = arch_of(f, "text_encoder.onnx");
+        te_arch = arch_of(f, "text_encoder.onnx", "text_encoder");
         load_net(f, te_arch, te, tc);
-        te.vec["embed"] = W(f, "te.embed.weight", (size_t)cfg.vocab_size * te.C);
+        te.vec["embed"] = W(f, tn(te_arch, "embed", "te.embed.weight"), (size_t)cfg.vocab_size * te.C);
         cfg.text_emb_channels = te.C;
         cfg.style_ttl_tokens = te_arch.at("n_style"); cfg.style_ttl_dim = te_arch.at("style_dim");
         const OnnxValueInfo* v = f.input("style_ttl");
@@ -593,16 +605,16 @@ void Handle::load(const std::string& onnx_dir) {
     }
     {
         OnnxFile f = load_onnx(onnx_dir + "/vector_estimator.onnx");
-        ve_arch = arch_of(f, "vector_estimator.onnx");
+        ve_arch = arch_of(f, "vector_estimator.onnx", "vector_estimator");
         load_net(f, ve_arch, ve, tc);
         if ((int)ve_arch.at("latent_ch") != cfg.latent_channels) throw StcError(STC_ERR_IO, "vector_estimator latent_ch != tts.json");
     }
     {
         OnnxFile f = load_onnx(onnx_dir + "/vocoder.onnx");
-        voc_arch = arch_of(f, "vocoder.onnx");
+        voc_arch = arch_of(f, "vocoder.onnx", "vocoder");
         load_net(f, voc_arch, voc, tc ? (voc_f16 ? 3 : 1) : 0);
-        voc.vec["std"] = W(f, "voc.latent_std", cfg.latent_channels);
-        voc.vec["mean"] = W(f, "voc.latent_mean", cfg.latent_channels);
+        voc.vec["std"] = W(f, tn(voc_arch, "latent_std", "voc.latent_std"), cfg.latent_channels);
+        voc.vec["mean"] = W(f, tn(voc_arch, "latent_mean", "voc.latent_mean"), cfg.latent_channels);
     }
 }
 
@@ -2312,6 +2324,20 @@ int stc_debug_pcm16(stc_handle* sh, const float* samples, int64_t n, int16_t* ou
         body();
         STC_CUDA(cudaStreamSynchronize(h->stream));
         h->check_launch("stc_debug_pcm16");
+    })
+}
+
+// The layer plan the node-pattern matcher (graph_plan.h) derives from one .onnx file, as JSON — host only, no GPU needed.
+int stc_derive_arch(const char* onnx_path, const char* kind, char* buf, size_t cap, size_t* need) {
+    STC_TRY(nullptr, {
+        if (!onnx_path || !kind || !need) throw StcError(STC_ERR_INVALID, "stc_derive_arch: bad argument");
+        std::string out;
+        try { out = derive_arch(load_onnx(onnx_path), kind).dump(); }
+        catch (const PlanError& e) { throw StcError(STC_ERR_UNSUPPORTED, e.what()); }
+        catch (const std::runtime_error& e) { throw StcError(STC_ERR_IO, e.what()); }
+        *need = out.size() + 1;
+        if (!buf || cap < out.size() + 1) throw StcError(STC_ERR_CAPACITY, "stc_derive_arch: buffer too small");
+        memcpy(buf, out.c_str(), out.size() + 1);
     })
 }
 

@@ -1,0 +1,121 @@
+"""The node-pattern matcher (supertonic_b200/csrc/graph_plan.h): the layer plan the library derives from a graph's ONNX nodes — what it
+uses for graphs without `stc_arch` metadata, i.e. any export the reference's loader would accept (loadOnnx, cpp/helper.cpp:776-795).
+
+CPU part (stc_derive_arch, no GPU): for every surrogate graph the derived plan equals the plan the generator wrote down when it built
+the graph; initializer names come from the node inputs (a renamed export loads); a graph with an unknown sub-graph is rejected with
+the list of unexplained nodes. GPU part: an engine built from node-derived plans computes bit-identical results."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+KINDS = ("duration_predictor", "text_encoder", "vector_estimator", "vocoder")
+FIELDS = ("type", "C", "H", "K", "dilation", "causal", "masked", "heads", "ctx", "ctx_dim", "rope", "key_masked", "cin", "cout", "time_dim")
+
+
+def _assets(size):
+    from supertonic_b200 import surrogate
+    return surrogate.ensure_assets(size)
+
+
+@pytest.mark.parametrize("size", ["tiny", "full"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_derived_plan_equals_the_generators_plan(size, kind):
+    from supertonic_b200 import capi, onnx_lite as ol
+    path = os.path.join(_assets(size), "onnx", kind + ".onnx")
+    got = capi.derive_arch(path, kind)
+    model = ol.load_model(path)
+    want = json.loads(model.metadata["stc_arch"])
+    assert got["derived_from"] == "nodes"
+    assert len(got["layers"]) == len(want["layers"])
+    for a, b in zip(got["layers"], want["layers"]):
+        for k in FIELDS:
+            if k in b:
+                assert a.get(k) == b[k], (b.get("name"), k, a.get(k), b[k])
+        for role, name in a["t"].items():                      # every recorded tensor is an initializer of the file
+            assert name in model.graph.initializers, (role, name)
+    for k, v in want.items():
+        if k in ("layers", "surrogate_version", "kind"):
+            continue
+        if isinstance(v, float):
+            assert np.float32(got[k]) == np.float32(v), k
+        else:
+            assert got[k] == v, k
+
+
+def test_renamed_initializers_and_stripped_metadata_still_load(tmp_path):
+    """A released export names its initializers arbitrarily (onnx::MatMul_123 ...) and carries no private metadata: rename every
+    initializer, drop the metadata, and the derived plan must point at the renamed tensors in the right roles."""
+    from supertonic_b200 import capi, onnx_lite as ol
+    src = os.path.join(_assets("tiny"), "onnx", "vector_estimator.onnx")
+    ref = capi.derive_arch(src, "vector_estimator")
+    m = ol.load_model(src)
+    ren = {name: f"onnx::T_{i}" for i, name in enumerate(m.graph.initializers)}
+    m.graph.initializers = {ren[k]: v for k, v in m.graph.initializers.items()}
+    for n in m.graph.nodes:
+        n.inputs = [ren.get(x, x) for x in n.inputs]
+    m.metadata = {}
+    out = str(tmp_path / "ve_renamed.onnx")
+    ol.save_model(m, out)
+    got = capi.derive_arch(out, "vector_estimator")
+    assert [l["type"] for l in got["layers"]] == [l["type"] for l in ref["layers"]]
+    for a, b in zip(got["layers"], ref["layers"]):
+        assert {k: ren[v] for k, v in b["t"].items()} == a["t"]
+
+
+def test_unknown_subgraph_is_rejected_with_the_unexplained_nodes(tmp_path):
+    from supertonic_b200 import capi, onnx_lite as ol
+    src = os.path.join(_assets("tiny"), "onnx", "text_encoder.onnx")
+    # (1) a GELU that is not the exact-erf form
+    m = ol.load_model(src)
+    erf = next(n for n in m.graph.nodes if n.op_type == "Erf")
+    erf.op_type = "Tanh"
+    p1 = str(tmp_path / "te_tanh.onnx"); ol.save_model(m, p1)
+    with pytest.raises(capi.StcError) as e:
+        capi.derive_arch(p1, "text_encoder")
+    assert e.value.code == -4 and "GELU" in str(e.value)
+    # (2) an extra operator on the main path that belongs to no layer
+    m = ol.load_model(src)
+    last = next(n for n in m.graph.nodes if n.outputs == ["text_emb"])             # Identity -> text_emb
+    extra = copy.deepcopy(last)
+    extra.op_type, extra.name = "Relu", "mystery_relu"
+    extra.inputs, extra.outputs = [last.inputs[0]], ["/mystery"]
+    last.inputs = ["/mystery"]
+    m.graph.nodes.insert(m.graph.nodes.index(last), extra)
+    p2 = str(tmp_path / "te_relu.onnx"); ol.save_model(m, p2)
+    with pytest.raises(capi.StcError) as e:
+        capi.derive_arch(p2, "text_encoder")
+    assert e.value.code == -4 and "mystery_relu" in str(e.value)
+    # (3) wrong graph for the requested kind
+    with pytest.raises(capi.StcError):
+        capi.derive_arch(src, "vocoder")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", ["tiny", "full"])
+def test_engine_from_node_derived_plans_is_bit_identical(size):
+    from supertonic_b200 import capi
+    root = _assets(size)
+    texts, langs = U.make_batch(5, 4, 20, 200)
+    a = capi.Engine(root + "/onnx")
+    os.environ["STC_IGNORE_ARCH"] = "1"
+    try:
+        b = capi.Engine(root + "/onnx")
+    finally:
+        del os.environ["STC_IGNORE_ARCH"]
+    try:
+        ids, mask = a.text_to_ids(texts, langs)
+        ttl, dp = U.styles(root, ["M1", "F1", "M2", "F2"])
+        np.testing.assert_array_equal(a.duration(ids, dp, mask), b.duration(ids, dp, mask))
+        np.testing.assert_array_equal(a.text_encode(ids, ttl, mask), b.text_encode(ids, ttl, mask))
+        ra = a.synthesize_packed(ids, mask, ttl, dp, 3, 1.05, seed=3, want_latent=True)
+        rb = b.synthesize_packed(ids, mask, ttl, dp, 3, 1.05, seed=3, want_latent=True)
+        for k in range(4):
+            np.testing.assert_array_equal(ra["latent"][k], rb["latent"][k])
+            np.testing.assert_array_equal(ra["wavs"][k], rb["wavs"][k])
+    finally:
+        a.close(); b.close()
