@@ -253,9 +253,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(stg + c + j);                     // broadcast read
-                        const float v0 = gelu_erf_mufu(__uint_as_float(r[j]) + b.x), v1 = gelu_erf_mufu(__uint_as_float(r[j + 1]) + b.y);
-                        const float v2 = gelu_erf_mufu(__uint_as_float(r[j + 2]) + b.z), v3 = gelu_erf_mufu(__uint_as_float(r[j + 3]) + b.w);
-                        o[j / 2] = pack_f16x2(v0, v1); o[j / 2 + 1] = pack_f16x2(v2, v3);
+                        const float2 g0 = tc::gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), make_float2(b.x, b.y)));
+                        const float2 g1 = tc::gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b.z, b.w)));
+                        o[j / 2] = pack_f16x2(g0.x, g0.y); o[j / 2 + 1] = pack_f16x2(g1.x, g1.y);
                     }
                     if (row < p.M && n0 + c < p.N) {
                         st_global_256(orow + c, o);

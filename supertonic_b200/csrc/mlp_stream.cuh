@@ -234,12 +234,10 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
 #pragma unroll
                     for (int t = 0; t < 8; t += 2) {
                         const float4 bv = *reinterpret_cast<const float4*>(b1 + 2 * t);                  // broadcast
-                        const float e0 = gelu_erf_mufu(__uint_as_float(v[2 * t]) + bv.x);
-                        const float e1 = gelu_erf_mufu(__uint_as_float(v[2 * t + 1]) + bv.y);
-                        const float e2 = gelu_erf_mufu(__uint_as_float(v[2 * t + 2]) + bv.z);
-                        const float e3 = gelu_erf_mufu(__uint_as_float(v[2 * t + 3]) + bv.w);
-                        split_pair(e0, e1, o[t], o[8 + t]);
-                        split_pair(e2, e3, o[t + 1], o[8 + t + 1]);
+                        const float2 g0 = gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1])), make_float2(bv.x, bv.y)));
+                        const float2 g1 = gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(v[2 * t + 2]), __uint_as_float(v[2 * t + 3])), make_float2(bv.z, bv.w)));
+                        split_pair(g0.x, g0.y, o[t], o[8 + t]);
+                        split_pair(g1.x, g1.y, o[t + 1], o[8 + t + 1]);
                     }
                     tmem_st16(trow + buf * 128 + col, o);
                 }
