@@ -13,7 +13,12 @@
  * Behaviour kept from ONNX Runtime:
  *   - inputs are matched by NAME, not position (other ports pass them in other orders, go/helper.go:884);
  *   - input tensors are borrowed for the duration of Run; each output Value owns its buffer;
+ *   - input shapes are checked against the graph's geometry before Run ("Got invalid dimensions for input: ..."): the C ABI behind
+ *     it takes bare pointers;
  *   - failures surface as Ort::Exception (derived from std::exception, what() carries the library message).
+ * Graph files: the library takes its layer plan from `stc_arch` metadata or derives it from the graph's nodes; a
+ * graph built from other patterns is rejected at Session construction with the unexplained nodes listed. So far it has only ever run
+ * the labelled SURROGATE graphs — the released assets were never available to this project.
  * The four Sessions of one onnx directory share one GPU handle (the reference loads all four from the same
  * directory, cpp/helper.cpp:784-795); the handle dies with the last of them. Device: env STC_DEVICE (default 0).
  */

@@ -9,6 +9,12 @@
  * reference builds at cpp/helper.cpp:495-509, 574-580, 604-618); outputs are written into
  * caller-provided host buffers. All tensors are dense row-major with the reference's layouts.
  *
+ * Model files: stc_create reads the four .onnx graphs of an asset directory. It takes the layer plan from the `stc_arch` metadata the
+ * surrogate generator writes, or derives it from the graph's NODES (ConvNeXt / attention / time-conditioning patterns, see
+ * stc_derive_arch) — so a released export loads if it is built from those patterns and is rejected with the list of unexplained
+ * nodes otherwise. The released Supertonic assets were never available to this project: everything measured and tested so far ran on
+ * labelled SURROGATE graphs of the hypothesised architecture.
+ *
  * Errors: every function returns STC_OK (0) or a negative status; the message is available via
  * stc_last_error(). There is NO CPU fallback: without a CUDA device stc_create fails.
  *

@@ -2267,7 +2267,8 @@ int stc_debug_dwconv(stc_handle* sh, int rows, int C, int K, int dil, int causal
             float* X = h->ws<float>((size_t)rows * C);
             float* Ya = h->ws<float>((size_t)rows * C); float* Yb = h->ws<float>((size_t)rows * C);
             float* err = h->ws<float>(1);
-            Act oa = h->ws_act((size_t)rows * C);
+            // timed form: split-bf16 operands (8 B per element), or with STC_DEBUG_F16 the single fp16 operand the vocoder uses (6 B)
+            Act oa = getenv("STC_DEBUG_F16") ? h->ws_act_f16((size_t)rows * C) : h->ws_act((size_t)rows * C);
             Seq seq = h->packed_seq(lens, rows, 0);
             if (h->dry) return;
             debug_fill_kernel<<<cdiv((size_t)rows * C, 256), 256, 0, h->stream>>>(X, (size_t)rows * C, 3, 1.0f);
