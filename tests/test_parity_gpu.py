@@ -360,7 +360,10 @@ def test_sliding_window_dwconv_layernorm_equals_the_tiled_kernel(rig):
     eng = rig["eng"]
     for rows, C, K, dil, causal, B, rt in [(4736, 256, 5, 1, False, 32, 0), (4736, 256, 5, 8, False, 32, 8), (4736, 256, 5, 4, True, 7, 16),
                                            (1000, 512, 7, 1, False, 3, 4), (5555, 512, 7, 4, False, 32, 32), (5555, 512, 7, 2, True, 5, 64),
-                                           (333, 128, 5, 2, False, 4, 4), (130, 128, 7, 1, False, 1, 8), (27726, 512, 7, 2, False, 32, 0)]:
+                                           (333, 128, 5, 2, False, 4, 4), (130, 128, 7, 1, False, 1, 8), (27726, 512, 7, 2, False, 32, 0),
+                                           # long chains at the library's own chain length: the 8-channels-per-thread kernel (K = 7) and the chain kernel (K = 5)
+                                           (27726, 512, 7, 1, True, 32, 0), (20000, 512, 7, 4, True, 9, 0), (30011, 256, 7, 1, False, 32, 0),
+                                           (30011, 256, 7, 2, True, 3, 0), (40000, 256, 5, 1, False, 32, 0), (25000, 512, 5, 2, True, 7, 0)]:
         _, _, diff = eng.debug_dwconv(rows, C, K, dil, causal, B, rt, 2)
         assert diff <= 2e-5, (rows, C, K, dil, causal, B, rt, diff)
 
