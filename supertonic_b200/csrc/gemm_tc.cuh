@@ -20,12 +20,11 @@
 //                               fp32 or split-bf16 stores. Two TMEM accumulator buffers: the epilogue of tile i
 //                               overlaps the MMAs of tile i+1.
 //
-// Operand traffic: the kernel is bound by L2 -> shared-memory operand bytes, not by the tensor pipe (measured:
-// profiles/r1b_*): a 128 x BN tile re-reads its A rows for every N tile and its W rows for every M tile. CTAs are
-// therefore launched as thread-block clusters of CM x CN tiles: the A tile of a cluster row is loaded once and
-// TMA-multicast to the CN CTAs that share it (each issues 1/CN of the rows), the W tile of a cluster column once for
-// its CM CTAs. A stage is released to the producers of every CTA that multicasts into it by a multicast
-// tcgen05.commit.
+// Operand traffic: the kernel is bound by L2 -> shared-memory operand bytes, not by the tensor pipe (measured: profiles/r1b_*,
+// r1c_gemm_sweep.txt): a 128 x BN tile re-reads its A rows for every N tile and its W rows for every M tile. Thread-block clusters
+// with TMA multicast of the shared A / W slices were built and measured in round 1 (2x1 / 1x2 / 2x2: 5-100 % slower on every hot
+// shape — multicast halves L2 reads but every SM still ingests its full tiles, and the cluster runs in lock-step) and removed in
+// round 2; the two-SM form that does help the big shapes is gemm2_tc.cuh.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -117,15 +116,6 @@ STC_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// kind::tf32: fp32 operands straight from shared memory (the tensor core reads the upper 19 bits), K = 8 per instruction
-// (32 bytes of a 128-byte swizzled row, like K = 16 of bf16), half the bf16 rate per element.
-STC_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 STC_DEVINL void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -162,9 +152,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {           // a = b = F16 (format 0)
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {          // a = b = TF32 (format 2)
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct Params {
     int M, N, K;
@@ -174,8 +161,7 @@ struct Params {
     __nv_bfloat16* out_lo;
     int ldo;
     int split;
-    int round_tf32;                 // fp32 output is the tf32 operand of the next GEMM: round it to nearest here
-    int cm, cn;                     // cluster shape in tiles (cm * cn CTAs per cluster)
+    int cm, cn;                     // (two-SM form: cm = 2; unused by the one-SM kernel)
     long long* trace;               // debug (stc_debug_gemm, STC_GEMM_TRACE=1): clock64() stamps of block 0's producer / MMA warps
 };
 
@@ -227,15 +213,6 @@ STC_DEVINL void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
-STC_DEVINL void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
-}
-STC_DEVINL void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
 STC_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 STC_DEVINL uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 STC_DEVINL uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -253,21 +230,12 @@ STC_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Tile coordinates of this CTA for cluster-tile `ct` (n fastest, so that concurrently running clusters share A rows in L2).
-struct TileIter {
-    int ctn, cm, cn, im, in;
-    STC_DEVINL void coords(int ct, int& mt, int& nt) const { mt = (ct / ctn) * cm + im; nt = (ct % ctn) * cn + in; }
-};
-
 // kRope: the rotary-embedding epilogue (Q / K projections) lives in its own instantiation — its sincosf slow path costs
 // registers, a stack frame and unrolling in every epilogue it is compiled into (the vocoder GEMMs lost 10 % to it).
-// kTf32: single-pass TF32 arithmetic for the vocoder (DESIGN.md "precision"): map_a_hi / map_w_hi describe fp32 [rows, K]
-// operands (box 32 elements = one 128-byte swizzled row); a stage still holds 64 K-elements — K sub-block 0 where the bf16
-// hi halves go, sub-block 1 where the lo halves go — and issues 8 MMAs (2 sub-blocks x 4 K-slices of 8) instead of 12.
 // kF16: single-pass fp16 arithmetic for the vocoder (the default there, DESIGN.md "precision"): map_a_hi / map_w_hi describe fp16
 // [rows, K] operands; a stage holds 128 K-elements — K sub-block 0 in the slots of the bf16 hi halves, sub-block 1 in the slots of the
 // lo halves — and issues 8 MMAs per 128 K-elements instead of 24 (a sub-block that lies wholly beyond K is neither loaded nor issued).
-template <int BN, bool kRope = false, bool kTf32 = false, bool kF16 = false>
+template <int BN, bool kRope = false, bool kF16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -286,32 +254,23 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + T::BAR_OFF + 8 * (2 * T::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cm = p.cm, cn = p.cn, csize = cm * cn;
-    const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
     constexpr int KSTAGE = kF16 ? 2 * BK : BK;                                  // K-elements per stage
     const int num_kb = (p.K + KSTAGE - 1) / KSTAGE;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.M + BM - 1) / BM;
-    TileIter ti{(n_tiles + cn - 1) / cn, cm, cn, crank / cn, crank % cn};
-    const int num_ct = ((m_tiles + cm - 1) / cm) * ti.ctn;
-    const int ct0 = csize > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
-    const int ct_step = csize > 1 ? (int)cluster_count_x() : (int)gridDim.x;
-    // CTAs this one exchanges operand slices with: its cluster row (same A tile) and column (same W tile)
-    uint16_t row_mask = 0, col_mask = 0;
-    for (int j = 0; j < cn; ++j) row_mask |= (uint16_t)(1u << (ti.im * cn + j));
-    for (int j = 0; j < cm; ++j) col_mask |= (uint16_t)(1u << (j * cn + ti.in));
+    const int num_ct = m_tiles * n_tiles;          // tile ct: m tile ct / n_tiles, n tile ct % n_tiles (n fastest: concurrent CTAs share A rows in L2)
+    const int ct0 = (int)blockIdx.x, ct_step = (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
-        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)(cm + cn - 1)); }
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, T::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
-    if (csize > 1) cluster_sync_all();          // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     pdl_wait();                                 // prologue above overlapped the predecessor; its writes are visible from here
@@ -319,16 +278,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            const int a_rows = BM / cn, w_rows = BN / cm;                    // rows of the slice this CTA fetches
-            const uint32_t a_off = (uint32_t)(ti.in * a_rows * BK * 2), w_off = (uint32_t)(ti.im * w_rows * BK * 2);
             uint32_t kbc = 0;
             for (int ct = ct0; ct < num_ct; ct += ct_step) {
-                int mt, nt; ti.coords(ct, mt, nt);
-                const int m0 = mt * BM + ti.in * a_rows, n0 = nt * BN + ti.im * w_rows;
+                const int m0 = (ct / n_tiles) * BM, n0 = (ct % n_tiles) * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
                     const int s = kbc % T::STAGES;
                     const uint32_t ph = (kbc / T::STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);                         // freed by every CTA that receives these slices
+                    mbar_wait(empty_bar(s), ph ^ 1);
                     const uint32_t st = smem_base + s * T::STAGE_BYTES;
                     if constexpr (kF16) {
                         const int k0 = kb * KSTAGE;
@@ -342,35 +298,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         }
                         continue;
                     }
-                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);             // own slices + the peers' multicasts
-                    if constexpr (kTf32) {
-                        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-                        tma_load_2d(st + T::A_BYTES, &map_a_hi, full_bar(s), kb * BK + BK / 2, m0);
-                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
-                        tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_hi, full_bar(s), kb * BK + BK / 2, n0);
-                        continue;
-                    }
-                    if (cn > 1) {
-                        tma_load_2d_mc(st + a_off, &map_a_hi, full_bar(s), kb * BK, m0, row_mask);
-                        tma_load_2d_mc(st + T::A_BYTES + a_off, &map_a_lo, full_bar(s), kb * BK, m0, row_mask);
-                    } else {
-                        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-                        tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
-                    }
-                    if (cm > 1) {
-                        tma_load_2d_mc(st + 2 * T::A_BYTES + w_off, &map_w_hi, full_bar(s), kb * BK, n0, col_mask);
-                        tma_load_2d_mc(st + 2 * T::A_BYTES + T::W_BYTES + w_off, &map_w_lo, full_bar(s), kb * BK, n0, col_mask);
-                    } else {
-                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
-                        tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
-                    }
+                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
+                    tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = kF16 ? make_idesc_f16(BM, BN) : kTf32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
-        const uint16_t free_mask = row_mask | col_mask;
+        constexpr uint32_t idesc = kF16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
         uint32_t kbc = 0, it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
             const uint32_t ab = it & 1, aph = (it >> 1) & 1;
@@ -399,17 +337,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                                 umma_bf16(tmem_d, a_lo + adv, w_lo + adv, idesc, 1);   // K sub-block 1 (the "lo" slots)
                             }
                         }
-                    } else if constexpr (kTf32) {
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B = 8 fp32 per K-slice
-                            umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-                        }
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            umma_tf32(tmem_d, a_lo + adv, w_lo + adv, idesc, 1);       // K sub-block 1 (the "lo" slots)
-                        }
                     } else {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -419,8 +346,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
                     }
                     }
-                    if (csize > 1) umma_commit_mc(empty_bar(s), free_mask);          // frees the stage in every sender
-                    else umma_commit(empty_bar(s));
+                    umma_commit(empty_bar(s));
                     if (kb == num_kb - 1) umma_commit(tfull_bar(ab));   // accumulator complete
                 }
                 __syncwarp();
@@ -436,8 +362,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const float* resid = static_cast<const float*>(p.ep.resid);
         uint32_t it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
-            int mt, nt; ti.coords(ct, mt, nt);
-            const int m0 = mt * BM + q * 32, n0 = nt * BN + half * COLS_PER_WARP;
+            const int m0 = (ct / n_tiles) * BM + q * 32, n0 = (ct % n_tiles) * BN + half * COLS_PER_WARP;
             const uint32_t ab = it & 1, aph = (it >> 1) & 1;
             float mk[4], pos[4];
 #pragma unroll
@@ -514,7 +439,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             *reinterpret_cast<uint2*>(p.out_hi + o) = hi;
                             *reinterpret_cast<uint2*>(p.out_lo + o) = lo;
                         } else {
-                            if (p.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                             *reinterpret_cast<float4*>(p.out_f32 + o) = v;
                         }
                     }
@@ -527,7 +451,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (csize > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into it / signal its barriers
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, T::TMEM_COLS);
 }

@@ -72,18 +72,9 @@ STC_DEVINL int find_seq(const int* __restrict__ off, int B, int row) {
 // (vocoder GEMMs): `hi` then holds fp16 bits, converted with saturation.
 struct SplitPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
 
-// round-to-nearest to TF32 (10 mantissa bits): the tensor core reads the upper 19 bits of an fp32 operand, so operands rounded
-// here are truncated without bias there (kind::tf32 GEMMs of the vocoder)
-STC_DEVINL float round_tf32(float v) {
-    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r);
-}
 template <typename T> struct OutPlain {
     T* p;
-    int rnd = 0;        // float only: the values are TF32 GEMM operands
-    STC_DEVINL void store(size_t i, T v) const {
-        if constexpr (std::is_same<T, float>::value) { if (rnd) v = round_tf32(v); }
-        p[i] = v;
-    }
+    STC_DEVINL void store(size_t i, T v) const { p[i] = v; }
 };
 // fp32 x2 -> packed fp16x2 (first argument in the lower half), round to nearest, saturating at +-65504: the single-pass fp16
 // operand form of the vocoder GEMMs (DESIGN.md "precision"; `lo == nullptr` in OutSplit / Act selects it, `hi` then holds fp16 bits)
@@ -225,12 +216,6 @@ template <int CPL> STC_DEVINL void store_row_vec(const OutSplit& o, size_t i, co
     }
 }
 template <int CPL> STC_DEVINL void store_row_vec(const OutPlain<float>& o, size_t i, const float (&y)[CPL]) {
-    if (o.rnd) {
-#pragma unroll
-        for (int j = 0; j < CPL; j += 4)
-            *reinterpret_cast<float4*>(o.p + i + j) = make_float4(round_tf32(y[j]), round_tf32(y[j + 1]), round_tf32(y[j + 2]), round_tf32(y[j + 3]));
-        return;
-    }
 #pragma unroll
     for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(o.p + i + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
 }

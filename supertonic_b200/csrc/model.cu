@@ -805,9 +805,9 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
     note(ep.rope_freqs ? "gemm_bn64_rope" : bn == 64 ? (f16 ? "gemm_f16_bn64" : "gemm_bn64") : bn == 128 ? (f16 ? "gemm_f16_bn128" : "gemm_bn128")
                                                                                               : (f16 ? "gemm_f16_bn256" : "gemm_bn256"));
     switch (ep.rope_freqs ? 1 : f16 ? 2000 + bn : bn) {
-        case 2064: launch_k(this, tc::gemm_bf16x3_kernel<64, false, false, true>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
-        case 2128: launch_k(this, tc::gemm_bf16x3_kernel<128, false, false, true>, grid, block, (size_t)tc::Tile<128>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
-        case 2256: launch_k(this, tc::gemm_bf16x3_kernel<256, false, false, true>, grid, block, (size_t)tc::Tile<256>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 2064: launch_k(this, tc::gemm_bf16x3_kernel<64, false, true>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 2128: launch_k(this, tc::gemm_bf16x3_kernel<128, false, true>, grid, block, (size_t)tc::Tile<128>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
+        case 2256: launch_k(this, tc::gemm_bf16x3_kernel<256, false, true>, grid, block, (size_t)tc::Tile<256>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
         case 1: launch_k(this, tc::gemm_bf16x3_kernel<64, true>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
         case 64: launch_k(this, tc::gemm_bf16x3_kernel<64>, grid, block, (size_t)tc::Tile<64>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
         case 128: launch_k(this, tc::gemm_bf16x3_kernel<128>, grid, block, (size_t)tc::Tile<128>::SMEM_BYTES, stream, mah, mal, mwh, mwl, p); break;
@@ -1310,7 +1310,7 @@ void Handle::run_vocoder(const float* lat_cl, const Seq& lat, float* wav) {
             Act a = ws_act_for(w, (size_t)rows * w.K);
             size_t n = (size_t)rows * w.K;
             if (a.hi) STC_LAUNCH(this, voc_im2col_kernel<OutSplit>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutSplit{a.hi, a.lo}, rows, lat.off, lat.B, f, ld, K, w.K);
-            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f, tc_mode() ? 1 : 0}, rows, lat.off, lat.B, f, ld, K, w.K);
+            else STC_LAUNCH(this, voc_im2col_kernel<OutPlain<float>>, cdiv(n, 256), 256, 0, lat_cl, voc.vec["std"], voc.vec["mean"], OutPlain<float>{a.f}, rows, lat.off, lat.B, f, ld, K, w.K);
             gemm(a, rows, w, Epilogue{}, x, nullptr, C);
             release(m2);
         } else if (l.type == L_CONVNEXT) convnext<float>(voc.cn[l.idx], x, s6);
@@ -1460,9 +1460,9 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
-            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<attn::MAX_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Lay<1>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::ST_SMEM_BYTES));

@@ -45,7 +45,6 @@ struct Linear {
     float* bias = nullptr;            // [N]
     __nv_bfloat16* w_hi = nullptr;    // [N,K] K-major split pair (tensor-core B operand)
     __nv_bfloat16* w_lo = nullptr;
-    float* w_nk = nullptr;            // [N,K] K-major fp32, rounded to TF32 (kind::tf32 B operand; vocoder in STC_VOC=tf32 mode)
     bool f16 = false;                 // w_hi holds single fp16 weights [N,K], w_lo is null (vocoder, default STC_VOC=f16 mode)
     bool has_maps = false;            // w_hi / w_lo (or w_nk) present (tensor maps are cached per box shape in the handle)
 };
