@@ -196,6 +196,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     torch.cuda.set_device(lrank)
+    bound = None
+    if world > 1 and os.environ.get("STC_BIND", "1") != "0":
+        from supertonic_b200 import affinity
+        bound = affinity.bind_to_gpu(lrank)          # before any page-locked buffer exists: they land in the GPU's NUMA node
+    cfg["host_binding"] = f"rank 0 bound to {len(bound)} CPUs local to its GPU" if bound else "none"
     from supertonic_b200 import assets
     if lrank == 0:
         root, asset_kind = assets.asset_root("full")
@@ -315,6 +320,22 @@ def main():
         e2e = {"value": float(te[0].item()) / (e2e_s / steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1000 * e2e_s / steps, "windows_ms_per_step": [1000 * w / steps for w in wins],
                "window": "median of three windows of exactly `steps` steps each (max over ranks per window)"}
+        # the same request stream with 16-bit PCM results (quantised on the device like writeWavFile, cpp/helper.cpp:985-988): what a
+        # server that writes WAV needs, at half the device->host bytes — at N = 8 the float32 waveforms of all ranks (1.7 GB per pass of
+        # configs[4]) are what the end-to-end leg waits for on this box (~50 GB/s aggregate D2H)
+        for w in range(2):
+            tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, pcm16=True)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            res16 = tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, seed=k, wait=False, pcm16=True)
+        eng.wait()
+        torch.cuda.synchronize()
+        t16 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+        e2e["pcm16"] = {"value": float(te[0].item()) / (float(t16[0].item()) / steps), "unit": "audio-s/s", "d2h_bytes_per_step": d2h // 2,
+                        "ms_per_step": 1000 * float(t16[0].item()) / steps, "window": "one window of `steps` steps"}
         return dict(value=audio_all / (ms_per_step / 1000), ms_per_step=ms_per_step, audio=audio, audio_all=audio_all, launches=int(launches),
                     clocks=clk, per_rank=per_rank, e2e=e2e, p50_step_ms=float(np.median(step_ms)), buckets=buckets, style=style,
                     ids=ids, mask=mask, lens=lens)

@@ -266,6 +266,8 @@ std::vector<TextToSpeech::Utterance> MultiGpuTextToSpeech::many(const std::vecto
     const int n = (int)text_list.size(), nd = (int)engines_.size();
     if (n != style.getTtlShape()[0]) throw std::runtime_error("Number of texts must match number of style vectors");
     engines_[0]->checkStyle(style, n);
+    // at least two launch groups per device: the device->host copy of one group then runs under the computation of the next
+    if (nd > 1) max_batch = std::min(max_batch, std::max(16, (n + 2 * nd - 1) / (2 * nd)));
     TextToSpeech::ManyPlan plan = engines_[0]->planMany(text_list, lang_list, max_batch);
     // longest-processing-time-first over the groups; cost ~ tokens (frames are proportional) x (Euler steps + vocoder share)
     std::vector<double> cost(plan.groups.size(), 0.0);

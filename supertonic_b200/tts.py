@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import capi
+from . import affinity, capi
 
 
 @dataclass
@@ -272,6 +272,11 @@ class MultiGpuTextToSpeech:
         from .scheduler import shard_lpt, synth_cost
         if len(texts) != style.ttl.shape[0]:
             raise RuntimeError("Number of texts must match number of style vectors")
+        # at least two launch groups per device, so that the device->host copy of one group runs under the computation of the next
+        # (measured on 8 GPUs, 1 024 utterances: 173 k audio-s/s with one group of 128 per device, 212 k with two of 64)
+        nd = len(self.engines)
+        if nd > 1:
+            max_batch = min(max_batch, max(16, -(-len(texts) // (2 * nd))))
         plan = plan_many(self.engine, texts, langs, max_batch)
         costs = [sum(synth_cost(int(plan.lens[i]), total_step) for i in g) for g in plan.groups]
         shards = shard_lpt(costs, len(self.engines))
@@ -281,6 +286,8 @@ class MultiGpuTextToSpeech:
 
         def work(r):
             try:
+                if len(self.engines) > 1 and os.environ.get("STC_BIND", "1") != "0":
+                    affinity.bind_to_gpu(self.devices[r])      # this thread (and the pinned buffers it allocates) next to its GPU
                 run_groups(self.engines[r], plan, shards[r], style, total_step, speed, seed, out, tag=f"p{self._parity}", pcm16=pcm16)
                 self.engines[r].wait()
             except BaseException as e:      # noqa: BLE001
