@@ -101,7 +101,7 @@ struct Handle {
     // asynchronous result copies (stc_synthesize_packed_async): a third stream carries the device->host copy of the waveform
     // while the main stream already runs the next call; two alternating device result buffers and staging halves
     cudaStream_t stream_copy = nullptr;
-    // Request streams (stc_synthesize_packed_async), env STC_OVERLAP: uploads + duration predictor of call k+1 run on stream_f
+    // Request streams (stc_synthesize_packed_async): uploads + duration predictor of call k+1 run on stream_f
     // with their own workspace (arena_f) and the text encoder on stream2 WHILE the Euler loop / vocoder of call k still occupy the
     // main stream; the stage-1 buffers (inputs, durations, text_emb) of odd calls live in persist_alt, so that call k's stage 2 and
     // call k+1's stage 1 never share memory. The host's wait for the durations of call k+1 then ends while call k is still running.

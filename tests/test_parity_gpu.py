@@ -458,7 +458,7 @@ def test_asynchronous_request_stream_equals_synchronous_calls(rig):
         for a, b in zip(w["wavs"], g["wavs"]):
             np.testing.assert_array_equal(a, b)
     # a longer stream of graph REPLAYS: stage 1 (duration predictor, text encoder) of call k+1 runs under stage 2 of call k on
-    # its own streams and arenas (STC_OVERLAP) — every call must still equal its synchronous result
+    # its own streams and arenas — every call must still equal its synchronous result
     for rep in range(2):
         got = [eng.synthesize_packed(*jobs[k % 3], 2, 1.05, seed=40 + k % 3, pinned=f"s{k}", wait=False) for k in range(9)]
         eng.wait()
