@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[4] strong-scaling sub-object")
     ap.add_argument("--no-vary", action="store_true", help="skip the varied-draw sub-object")
+    ap.add_argument("--lanes", type=int, default=2, help="handles per GPU for the end-to-end request stream (TextToSpeech lanes); 1 = one handle")
     ap.add_argument("--vary-batches", action="store_true", help="N > 1: every rank draws its own 32 utterances (seed 1234 + 1000 rank)")
     ap.add_argument("--workload", default="batch", choices=["batch", "sweep1024"],
                     help="batch: configs[1], every GPU its own --batch utterances (weak scaling, the default and the headline). "
@@ -192,7 +193,7 @@ def main():
     import torch
     import torch.distributed as dist
     from supertonic_b200 import capi, surrogate, tts as T
-    from supertonic_b200.scheduler import length_buckets, shard_for_rank
+    from supertonic_b200.scheduler import shard_for_rank
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     torch.cuda.set_device(lrank)
@@ -208,7 +209,7 @@ def main():
         dist.barrier()
     root, asset_kind = assets.asset_root("full")
     cfg["weights"] = ("released assets at " + root) if asset_kind == "released" else cfg["weights"]
-    tt = T.load_text_to_speech(os.path.join(root, "onnx"), use_gpu=True, device=lrank)
+    tt = T.load_text_to_speech(os.path.join(root, "onnx"), use_gpu=True, device=lrank, lanes=a.lanes)
     eng = tt.engine
     ext = torch.cuda.ExternalStream(eng.stream)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -225,10 +226,13 @@ def main():
         n_utt = len(texts)
         style = T.load_voice_style([os.path.join(root, "voice_styles", v + ".json") for v in voices])
         # ---- device-resident leg ---------------------------------------------------------------------
-        ids, mask = eng.text_to_ids(texts, langs)
-        lens = mask.reshape(n_utt, -1).sum(1).astype(np.int64)
+        # the launch groups are the product's own (tts.plan_many: at most `group` utterances and 140 row tiles of predicted latent
+        # frames per group, equal predicted frames); one untimed request first, so that the plan uses the measured frames per token
+        tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group)
+        plan = T.plan_many(eng, texts, langs, group)
+        ids, mask, lens = plan.ids, plan.mask, plan.lens
         buckets = []
-        for grp in length_buckets(lens, group, 1e9):              # groups by token count; inside a group everything is packed rows
+        for grp in plan.groups:                                   # inside a group everything is packed rows
             g = np.asarray(grp); Tg = int(lens[g].max())
             cap = int(lens[g].sum() * 0.12 * eng.cfg.sample_rate) + (len(g) + 8) * cs
             buckets.append(dict(B=len(g), T=Tg, cap=cap,
@@ -292,8 +296,9 @@ def main():
                      "row_tiles_of_128": int(-(-int(v[2]) // 128))} for i, v in enumerate(allr)]
         ms_per_step = total_ms / steps
         # ---- end-to-end leg: public API, host buffers, front-end + H2D + D2H inside the timed region ---------
-        for w in range(max(2, warmup - 1)):          # two: both alternating pinned result sets exist before the timed region
-            tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group)
+        for w in range(max(2 * a.lanes, warmup - 1)):          # both alternating pinned result sets (and CUDA graphs) of every lane exist before the timed region
+            tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, wait=False)
+        tt.wait()
         # Three windows of exactly K steps each, the MEDIAN window is reported (all three are in `windows_ms_per_step`): this leg is
         # wall-clock on the host (front-end threads, pinned copies) and a single hiccup of a shared box moved a 100 ms window by 20 %.
         wins = []
@@ -303,7 +308,7 @@ def main():
             for k in range(steps):
                 # request stream: step k+1 is issued before step k's waveform copy has landed (two alternating pinned result sets)
                 res = tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, seed=k, wait=False)
-            eng.wait()
+            tt.wait()
             torch.cuda.synchronize()
             wins.append(time.perf_counter() - t0)
         tw = torch.tensor(wins, dtype=torch.float64, device="cuda")
@@ -319,17 +324,21 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.SUM)
         e2e = {"value": float(te[0].item()) / (e2e_s / steps), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1000 * e2e_s / steps, "windows_ms_per_step": [1000 * w / steps for w in wins],
-               "window": "median of three windows of exactly `steps` steps each (max over ranks per window)"}
+               "window": "median of three windows of exactly `steps` steps each (max over ranks per window)",
+               "request_lanes": a.lanes,
+               "how": "TextToSpeech.synthesize_many(wait=False) request stream: host text front-end, H2D, synthesis, D2H into page-locked buffers; "
+                      f"{a.lanes} handle(s) per GPU take the launch groups alternately, so consecutive requests overlap on the device"}
         # the same request stream with 16-bit PCM results (quantised on the device like writeWavFile, cpp/helper.cpp:985-988): what a
         # server that writes WAV needs, at half the device->host bytes — at N = 8 the float32 waveforms of all ranks (1.7 GB per pass of
         # configs[4]) are what the end-to-end leg waits for on this box (~50 GB/s aggregate D2H)
-        for w in range(2):
-            tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, pcm16=True)
+        for w in range(2 * a.lanes):
+            tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, pcm16=True, wait=False)
+        tt.wait()
         barrier()
         t0 = time.perf_counter()
         for k in range(steps):
             res16 = tt.synthesize_many(texts, langs, style, a.total_step, 1.05, max_batch=group, seed=k, wait=False, pcm16=True)
-        eng.wait()
+        tt.wait()
         torch.cuda.synchronize()
         t16 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -346,7 +355,7 @@ def main():
         texts, langs, voices = [texts[i] for i in mine], [langs[i] for i in mine], [voices[i] for i in mine]
         group = 128
         cfg["workload"] = (f"configs[4]: 1024 synthetic utterances (chars uniform 20..300, seed 1234) sharded over {world} GPU(s) by LPT, "
-                           f"groups of {group}, total_step={a.total_step}, speed=1.05")
+                           f"launch groups of <= {group} utterances and equal predicted latent frames (tts.plan_many), total_step={a.total_step}, speed=1.05")
     else:
         texts, langs, voices = workload(a.batch, 1234 + (1000 * rank if a.vary_batches else 0))
         group = a.batch
@@ -365,8 +374,9 @@ def main():
         mine4 = shard_for_rank([len(t) + 9 for t in t4], a.total_step, rank, world)
         m4 = measure([t4[i] for i in mine4], [l4[i] for i in mine4], [v4[i] for i in mine4], 128, max(2, a.steps // 4), 2)
         strong = {"workload": f"configs[4]: 1024 synthetic utterances (seed 1234) sharded over {world} GPU(s) by LPT (scheduler.shard_for_rank), "
-                              f"packed groups of 128, total_step={a.total_step}", "scaling": "strong", "value": m4["value"], "unit": "audio-s/s",
-                  "ms_per_pass": m4["ms_per_step"], "e2e": m4["e2e"], "per_rank": m4["per_rank"], "steps": max(2, a.steps // 4)}
+                              f"packed launch groups of <= 128 utterances and equal predicted latent frames (tts.plan_many), total_step={a.total_step}", "scaling": "strong", "value": m4["value"], "unit": "audio-s/s",
+                  "ms_per_pass": m4["ms_per_step"], "e2e": m4["e2e"], "per_rank": m4["per_rank"], "steps": max(2, a.steps // 4),
+                  "groups": [[b["B"], b["T"], b.get("L", 0)] for b in m4["buckets"]]}
 
     # ---- varied draws (rank 0 only at N = 1; per rank at N > 1): every seed another 32-utterance batch, i.e. another row-tile count ----
     vary = None
@@ -466,7 +476,7 @@ def main():
         traffic = json.load(open(tp)).get("dram_bytes_per_launch") if os.path.exists(tp) else None
         names = {"gemm_tc": "tc::gemm_bf16x3_kernel<64|128|256> (TMA -> tcgen05.mma kind::f16 -> TMEM, 3 MMAs per K-slice)",
                  "gemm_f16": "tc2::gemm2_bf16x3_kernel<true> (vocoder projections: two-SM cta_group::2 tcgen05.mma kind::f16, single-pass fp16 operands)",
-                 "fused_mlp": "mlp::convnext_mlp_stream_kernel + mlp_reduce[_post]_kernel (pw1 -> GELU -> pw2 fused: S in TMEM, P written back into TMEM, "
+                 "fused_mlp": "mlp::convnext_mlp_stream2_kernel (CTA pairs, cta_group::2) / convnext_mlp_stream_kernel + mlp_reduce[_post]_kernel (pw1 -> GELU -> pw2 fused: S in TMEM, P written back into TMEM, "
                               "O accumulated from the TMEM operand; tcgen05, 3 MMAs per K-slice)"}
 
         def tensor_line(key, passes=3):

@@ -25,8 +25,17 @@
 // hi + lo, through a 3-slot ring), 1 = MMA issuer, 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 // The last chunk's O units run output-half-major, so the first 128 output columns are final (and are being stored) while the
 // tensor pipe still accumulates the other 128.
+//
+// PAIR form (convnext_mlp_stream2_kernel, cta_group::2): the kernel above is paced by bytes delivered into each SM (640 KB per CTA at 37
+// tiles x 4 slices: 128 KB of `a` + 512 KB of weights, 95 MB per launch against TMA's ~6 300 B/clk chip-wide). Two row tiles that share
+// a hidden slice run as a CTA pair with ONE instruction stream (M = 256 MMAs issued by the leader): each CTA keeps its own `a` tile, its
+// own S / P / O in its own TMEM, and only HALF of every weight unit (64 of the 128 weight rows) — 384 KB per CTA. The pair's barriers:
+// TMA of both CTAs completes on the leader's full barriers, tcgen05.commit multicasts to both CTAs, the peer's epilogue warps
+// arrive remotely on the leader's P barriers. An odd last row tile runs the one-CTA form inside the same launch (its cluster's two
+// CTAs take two of its hidden slices), so 37 tiles x 4 slices is still 148 CTAs in one wave.
 #pragma once
 #include "mlp_tc.cuh"
+#include "gemm2_tc.cuh"
 
 namespace stc {
 namespace mlp {
@@ -38,6 +47,7 @@ static_assert(ST_SMEM_BYTES <= 232448, "shared memory budget");
 struct StreamParams {
     int M;                  // rows
     int nslice;             // CTAs per 128-row tile (1..16)
+    int npairs;             // pair kernel only: row-tile pairs; a row tile after them (odd count, not padded) runs the one-CTA form
     const float* b1;        // [H]
     long long* trace;       // debug (stc_debug_mlp with STC_MLP_TRACE=1): clock64() stamps of CTA 0
 };
@@ -78,29 +88,43 @@ STC_DEVINL void stream_units(int nchunks, int nblk64, F&& f) {
     }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                           const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
-                           const __grid_constant__ CUtensorMap map_w1_hi64, const __grid_constant__ CUtensorMap map_w1_lo64,
-                           const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
-                           const __grid_constant__ CUtensorMap map_part, const StreamParams p) {
+STC_DEVINL void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+struct StreamMaps {
+    const CUtensorMap *a_hi, *a_lo;          // [rows, C], box 128 rows x 64
+    const CUtensorMap *w1_hi, *w1_lo;        // [H, C], box = this CTA's weight rows of a 128-unit chunk (128; pair: 64) x 64
+    const CUtensorMap *w1_hi_s, *w1_lo_s;    // the same for a final 64-unit chunk (one-CTA form only)
+    const CUtensorMap *w2_hi, *w2_lo;        // [C, H], box = this CTA's output rows of a half (128; pair: 64) x 64
+    const CUtensorMap *part;                 // [nslice * tiles * 128, C] fp32, box 32 x 32
+};
+
+// One CTA's share of a block: row tile `tile`, hidden slice `slice`. PAIR: this CTA is rank `rank` of a CTA pair (cluster of two
+// along x) that owns row tiles (tile - rank, tile - rank + 1); hidden slices are 128-unit aligned there (16 / nslice even).
+template <bool PAIR>
+STC_DEVINL void stream_body(const StreamMaps& mp, const StreamParams& p, const int tile, const int slice, const int rank, uint8_t* smem_raw) {
     using namespace tc;
-    pdl_trigger();
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int NS = PAIR ? 2 * SLOTS : SLOTS;            // ring slots
+    constexpr int UNIT_B = PAIR ? KBLK : UNIT;              // bytes per slot: this CTA's weight rows x 64 K, hi + lo
+    constexpr int HALF_B = UNIT_B / 2;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // same offset in both CTAs of a pair
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar = smem_base + OFF_BAR;
-    auto full_bar = [&](int s) { return bar + 8u * s; };                   // 0..2
-    auto empty_bar = [&](int s) { return bar + 24 + 8u * s; };             // 3..5
-    auto bar_ak = [&](int kb) { return bar + 48 + 8u * kb; };              // a-tile K block kb landed
-    auto bar_s = [&](int buf) { return bar + 80 + 8u * buf; };             // S chunk complete in TMEM buffer buf
-    auto bar_p = [&](int buf, int j) { return bar + 96 + 8u * (2 * buf + j); };   // P sub-block j of buffer buf written
-    auto bar_o = [&](int half) { return bar + 128 + 8u * half; };          // output half final
-    const uint32_t tmem_slot = bar + 144;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 144);
+    const uint32_t bar = smem_base + OFF_BAR, bar2 = bar + 16u * NS;
+    auto full_bar = [&](int s) { return bar + 8u * s; };
+    auto empty_bar = [&](int s) { return bar + 8u * (NS + s); };
+    auto bar_ak = [&](int kb) { return bar2 + 8u * kb; };                  // a-tile K block kb landed (pair: both CTAs')
+    auto bar_s = [&](int buf) { return bar2 + 32 + 8u * buf; };            // S chunk complete in TMEM buffer buf
+    auto bar_p = [&](int buf, int j) { return bar2 + 48 + 8u * (2 * buf + j); };  // P sub-block j of buffer buf written (pair: by both CTAs)
+    auto bar_o = [&](int half) { return bar2 + 80 + 8u * half; };          // output half final
+    const uint32_t tmem_slot = bar2 + 96;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 16 * NS + 96);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slice = (int)(blockIdx.x % p.nslice);
-    const int m0 = (int)(blockIdx.x / p.nslice) * BM;
+    const int m0 = tile * BM;
     int u0, u1;
     stream_range(slice, p.nslice, u0, u1);
     const int nblk64 = u1 - u0, nchunks = (nblk64 + 1) >> 1, h0 = u0 * 64;
@@ -108,45 +132,72 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
 #define STC_STRACE(idx) do { if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[idx] = clock64(); } while (0)
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_w1_hi); tma_prefetch_desc(&map_w1_lo);
-        tma_prefetch_desc(&map_w1_hi64); tma_prefetch_desc(&map_w1_lo64); tma_prefetch_desc(&map_w2_hi); tma_prefetch_desc(&map_w2_lo);
-        tma_prefetch_desc(&map_part);
-        for (int s = 0; s < SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        tma_prefetch_desc(mp.a_hi); tma_prefetch_desc(mp.a_lo); tma_prefetch_desc(mp.w1_hi); tma_prefetch_desc(mp.w1_lo);
+        if (!PAIR) { tma_prefetch_desc(mp.w1_hi_s); tma_prefetch_desc(mp.w1_lo_s); }
+        tma_prefetch_desc(mp.w2_hi); tma_prefetch_desc(mp.w2_lo);
+        tma_prefetch_desc(mp.part);
+        for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int kb = 0; kb < C / BK; ++kb) mbar_init(bar_ak(kb), 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_s(b), 1); mbar_init(bar_p(b, 0), 8); mbar_init(bar_p(b, 1), 8); mbar_init(bar_o(b), 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_s(b), 1); mbar_init(bar_p(b, 0), (PAIR ? 2 : 1) * EPI_WARPS); mbar_init(bar_p(b, 1), (PAIR ? 2 : 1) * EPI_WARPS); mbar_init(bar_o(b), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if constexpr (PAIR) tc2::tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();             // the peer's barriers exist before anything is signalled at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     if (warp == 2) STC_STRACE(0);
     pdl_wait();
 
     if (warp == 0) {
+        // ===== TMA producer (pair: both CTAs — own a-tile, own half of every weight unit; bytes complete on the LEADER's barriers) =====
         if (elect_one()) {
             auto load_a = [&](int kb) {
-                mbar_expect_tx(bar_ak(kb), 2 * KBLK);
-                tma_load_2d(smem_base + OFF_X + kb * KBLK, &map_a_hi, bar_ak(kb), kb * BK, m0);
-                tma_load_2d(smem_base + OFF_X + (C / BK + kb) * KBLK, &map_a_lo, bar_ak(kb), kb * BK, m0);
+                const uint32_t d_hi = smem_base + OFF_X + kb * KBLK, d_lo = smem_base + OFF_X + (C / BK + kb) * KBLK;
+                if constexpr (PAIR) {
+                    if (rank == 0) mbar_expect_tx(bar_ak(kb), 4 * KBLK);
+                    const uint32_t rb = tc2::mapa_rank(bar_ak(kb), 0);
+                    tc2::tma_load_2d_2sm(d_hi, mp.a_hi, rb, kb * BK, m0);
+                    tc2::tma_load_2d_2sm(d_lo, mp.a_lo, rb, kb * BK, m0);
+                } else {
+                    mbar_expect_tx(bar_ak(kb), 2 * KBLK);
+                    tma_load_2d(d_hi, mp.a_hi, bar_ak(kb), kb * BK, m0);
+                    tma_load_2d(d_lo, mp.a_lo, bar_ak(kb), kb * BK, m0);
+                }
             };
             int u = 0;
             load_a(0);
             stream_units(nchunks, nblk64, [&](int kind, int c, int a, int b) {
-                const int s = u % SLOTS;
-                mbar_wait_b(empty_bar(s), ((u / SLOTS) & 1) ^ 1);
-                const uint32_t dst = smem_base + OFF_RING + s * UNIT, fb = full_bar(s);
+                const int s = u % NS;
+                mbar_wait_b(empty_bar(s), ((u / NS) & 1) ^ 1);
+                const uint32_t dst = smem_base + OFF_RING + s * UNIT_B;
                 if (p.trace && blockIdx.x == 0 && u < 16) p.trace[40 + u] = clock64();
-                if (kind == 0) {            // W1[hidden rows of chunk c, K block a of C]
-                    const int w = chunk_w(c), row = h0 + c * 128;
-                    mbar_expect_tx(fb, 2 * w * BK * 2);
-                    tma_load_2d(dst, w == 128 ? &map_w1_hi : &map_w1_hi64, fb, a * BK, row);
-                    tma_load_2d(dst + KBLK, w == 128 ? &map_w1_lo : &map_w1_lo64, fb, a * BK, row);
-                } else {                    // W2[output rows b*128.., hidden K block]
-                    mbar_expect_tx(fb, UNIT);
-                    tma_load_2d(dst, &map_w2_hi, fb, h0 + c * 128 + a * BK, b * 128);
-                    tma_load_2d(dst + KBLK, &map_w2_lo, fb, h0 + c * 128 + a * BK, b * 128);
+                if constexpr (PAIR) {
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2 * UNIT_B);
+                    const uint32_t fb = tc2::mapa_rank(full_bar(s), 0);
+                    if (kind == 0) {        // W1[this CTA's 64 hidden rows of chunk c, K block a of C]
+                        const int row = h0 + c * 128 + rank * 64;
+                        tc2::tma_load_2d_2sm(dst, mp.w1_hi, fb, a * BK, row);
+                        tc2::tma_load_2d_2sm(dst + HALF_B, mp.w1_lo, fb, a * BK, row);
+                    } else {                // W2[this CTA's 64 output rows of half b, hidden K block]
+                        tc2::tma_load_2d_2sm(dst, mp.w2_hi, fb, h0 + c * 128 + a * BK, b * 128 + rank * 64);
+                        tc2::tma_load_2d_2sm(dst + HALF_B, mp.w2_lo, fb, h0 + c * 128 + a * BK, b * 128 + rank * 64);
+                    }
+                } else {
+                    const uint32_t fb = full_bar(s);
+                    if (kind == 0) {        // W1[hidden rows of chunk c, K block a of C]
+                        const int w = chunk_w(c), row = h0 + c * 128;
+                        mbar_expect_tx(fb, 2 * w * BK * 2);
+                        tma_load_2d(dst, w == 128 ? mp.w1_hi : mp.w1_hi_s, fb, a * BK, row);
+                        tma_load_2d(dst + HALF_B, w == 128 ? mp.w1_lo : mp.w1_lo_s, fb, a * BK, row);
+                    } else {                // W2[output rows b*128.., hidden K block]
+                        mbar_expect_tx(fb, UNIT_B);
+                        tma_load_2d(dst, mp.w2_hi, fb, h0 + c * 128 + a * BK, b * 128);
+                        tma_load_2d(dst + HALF_B, mp.w2_lo, fb, h0 + c * 128 + a * BK, b * 128);
+                    }
                 }
                 // the rest of the a-tile queues between the first weight units: the first MMAs need 32 KB of `a` + one unit
                 if (u < C / BK - 1) load_a(u + 1);
@@ -155,78 +206,95 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
         }
         __syncwarp();
     } else if (warp == 1) {
-        int u = 0;
-        stream_units(nchunks, nblk64, [&](int kind, int c, int a, int b) {
-            const int s = u % SLOTS, buf = c & 1;
-            const uint32_t par = (uint32_t)((c >> 1) & 1);
-            if (kind == 0 && c == 0) mbar_wait_b(bar_ak(a), 0);                       // a-tile K block a has landed
-            if (kind == 1 && (c + 1 < nchunks ? b == 0 : true)) {
-                // P sub-block a of chunk c is in TMEM (non-last chunks reach it first with b == 0; the last chunk's half-major
-                // order reaches every sub-block once per half — a second wait on a completed phase returns at once)
-                mbar_wait_b(bar_p(buf, a), par);
-            }
-            mbar_wait_b(full_bar(s), (u / SLOTS) & 1);
-            tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && lane == 0 && u < 16) p.trace[8 + u] = clock64();
-            if (elect_one()) {
-                const uint32_t st = smem_base + OFF_RING + s * UNIT;
-                const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + KBLK);
-                if (kind == 0) {
-                    const uint32_t xk = smem_base + OFF_X + a * KBLK;
-                    const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
-                    const uint32_t d = tmem_base + buf * 128;
-                    const uint32_t idesc = chunk_w(c) == 128 ? make_idesc_bf16(BM, 128) : make_idesc_bf16(BM, 64);
+        // ===== MMA issuer (pair: the leader's warp issues for both CTAs) =====
+        if (!PAIR || rank == 0) {
+            int u = 0;
+            stream_units(nchunks, nblk64, [&](int kind, int c, int a, int b) {
+                const int s = u % NS, buf = c & 1;
+                const uint32_t par = (uint32_t)((c >> 1) & 1);
+                if (kind == 0 && c == 0) mbar_wait_b(bar_ak(a), 0);                       // a-tile K block a has landed
+                if (kind == 1 && (c + 1 < nchunks ? b == 0 : true)) {
+                    // P sub-block a of chunk c is in TMEM (non-last chunks reach it first with b == 0; the last chunk's half-major
+                    // order reaches every sub-block once per half — a second wait on a completed phase returns at once)
+                    mbar_wait_b(bar_p(buf, a), par);
+                }
+                mbar_wait_b(full_bar(s), (u / NS) & 1);
+                tc_fence_after();
+                if (p.trace && blockIdx.x == 0 && lane == 0 && u < 16) p.trace[8 + u] = clock64();
+                if (elect_one()) {
+                    const uint32_t st = smem_base + OFF_RING + s * UNIT_B;
+                    const uint64_t w_hi = make_smem_desc(st), w_lo = make_smem_desc(st + HALF_B);
+                    auto commit = [&](uint32_t b_) { if constexpr (PAIR) tc2::umma2_commit(b_); else umma_commit(b_); };
+                    if (kind == 0) {
+                        const uint32_t xk = smem_base + OFF_X + a * KBLK;
+                        const uint64_t a_hi = make_smem_desc(xk), a_lo = make_smem_desc(xk + (C / BK) * KBLK);
+                        const uint32_t d = tmem_base + buf * 128;
+                        const uint32_t idesc = PAIR ? make_idesc_bf16(2 * BM, 128) : chunk_w(c) == 128 ? make_idesc_bf16(BM, 128) : make_idesc_bf16(BM, 64);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        umma_bf16(d, a_lo + adv, w_hi + adv, idesc, (a | k) != 0);
-                        umma_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
-                    }
-                    umma_commit(empty_bar(s));
-                    if (a == C / BK - 1) umma_commit(bar_s(buf));                    // S chunk c complete
-                } else {
-                    constexpr uint32_t idesc = make_idesc_bf16(BM, 128);
-                    const uint32_t d = tmem_base + 256 + b * 128;
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            if constexpr (PAIR) {
+                                tc2::umma2_bf16(d, a_lo + adv, w_hi + adv, idesc, (a | k) != 0);
+                                tc2::umma2_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
+                                tc2::umma2_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
+                            } else {
+                                umma_bf16(d, a_lo + adv, w_hi + adv, idesc, (a | k) != 0);
+                                umma_bf16(d, a_hi + adv, w_lo + adv, idesc, 1);
+                                umma_bf16(d, a_hi + adv, w_hi + adv, idesc, 1);
+                            }
+                        }
+                        commit(empty_bar(s));
+                        if (a == C / BK - 1) commit(bar_s(buf));                         // S chunk c complete
+                    } else {
+                        constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, 128);
+                        const uint32_t d = tmem_base + 256 + b * 128;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        const uint32_t p_hi = tmem_base + buf * 128 + a * BK + k * UMMA_K, p_lo = p_hi + UMMA_K / 2;
-                        umma_bf16_ts(d, p_lo, w_hi + adv, idesc, (c | a | k) != 0);
-                        umma_bf16_ts(d, p_hi, w_lo + adv, idesc, 1);
-                        umma_bf16_ts(d, p_hi, w_hi + adv, idesc, 1);
-                    }
-                    umma_commit(empty_bar(s));
-                    if (c + 1 == nchunks) {
-                        const int nj = nblk64 - 2 * c >= 2 ? 2 : 1;
-                        if (a == nj - 1) umma_commit(bar_o(b));                      // output half b is final
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            const uint32_t p_hi = tmem_base + buf * 128 + a * BK + k * UMMA_K, p_lo = p_hi + UMMA_K / 2;
+                            if constexpr (PAIR) {
+                                umma2_bf16_ts(d, p_lo, w_hi + adv, idesc, (c | a | k) != 0);
+                                umma2_bf16_ts(d, p_hi, w_lo + adv, idesc, 1);
+                                umma2_bf16_ts(d, p_hi, w_hi + adv, idesc, 1);
+                            } else {
+                                umma_bf16_ts(d, p_lo, w_hi + adv, idesc, (c | a | k) != 0);
+                                umma_bf16_ts(d, p_hi, w_lo + adv, idesc, 1);
+                                umma_bf16_ts(d, p_hi, w_hi + adv, idesc, 1);
+                            }
+                        }
+                        commit(empty_bar(s));
+                        if (c + 1 == nchunks) {
+                            const int nj = nblk64 - 2 * c >= 2 ? 2 : 1;
+                            if (a == nj - 1) commit(bar_o(b));                           // output half b is final
+                        }
                     }
                 }
-            }
-            __syncwarp();
-            ++u;
-        });
+                __syncwarp();
+                ++u;
+            });
+        }
     } else {
         // ===== epilogue 1, per chunk: P = split(GELU(S + b1)), in place in TMEM =====
+        constexpr int PARTS = EPI_WARPS / 4;                                      // column parts per TMEM lane quarter
         const int q = warp & 3, part = (warp - 2) >> 2;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         float* b1s = reinterpret_cast<float*>(smem_gen + ST_OFF_B1);
-        const int et = (int)threadIdx.x - 64;                                    // 0..255
+        const int et = (int)threadIdx.x - 64;                                    // 0 .. 32 * EPI_WARPS - 1
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             const int buf = c & 1, w = chunk_w(c);
             // this chunk's b1 slice -> shared memory while S is still being accumulated (no L1 next to 226 KB of shared memory: a
             // __ldg inside the loop below would be an L2 round trip on the CTA's serial chain). Slot buf was last read two chunks ago.
             if (et < w) b1s[buf * 128 + et] = __ldg(p.b1 + h0 + c * 128 + et);
-            asm volatile("bar.sync 1, 256;" ::: "memory");                       // the eight epilogue warps only
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");       // the epilogue warps only
             mbar_wait_b(bar_s(buf), (uint32_t)((c >> 1) & 1));
             tc_fence_after();
             if (warp == 2) STC_STRACE(24 + (c < 4 ? c : 3));
 #pragma unroll 1
             for (int j = 0; j < w / BK; ++j) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int col = j * BK + part * 32 + g * 16;
+                for (int g = 0; g < BK / (16 * PARTS); ++g) {
+                    const int col = j * BK + (part * (BK / (16 * PARTS)) + g) * 16;
                     uint32_t v[16], o[16];
                     __syncwarp();
                     tmem_ld16(trow + buf * 128 + col, v);
@@ -244,7 +312,10 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_p(buf, j));
+                if (lane == 0) {
+                    if constexpr (PAIR) tc2::mbar_arrive_cluster(tc2::mapa_rank(bar_p(buf, j), 0));      // the leader's MMA warp waits for both CTAs
+                    else mbar_arrive(bar_p(buf, j));
+                }
             }
             if (warp == 2) STC_STRACE(28 + (c < 4 ? c : 3));
         }
@@ -254,6 +325,7 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
         const uint32_t stg = smem_base + OFF_X + (uint32_t)(warp - 2) * 8192u;
         const int mpad = ((p.M + BM - 1) / BM) * BM;
         const int grow = slice * mpad + m0 + q * 32;
+        const bool phantom = m0 >= mpad;         // pair form, odd tile count padded to a whole pair: the second CTA computes on zero rows and stores nothing
         int it = 0;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -261,8 +333,8 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
             tc_fence_after();
             if (warp == 2) STC_STRACE(32 + half);
 #pragma unroll 1
-            for (int cc = 0; cc < 64; cc += 32, ++it) {
-                const int col = half * 128 + part * 64 + cc;
+            for (int cc = 0; cc < 128 / PARTS; cc += 32, ++it) {
+                const int col = half * 128 + part * (128 / PARTS) + cc;
                 const uint32_t buf = stg + (uint32_t)(it & 1) * 4096u;
                 if (it >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }        // the store that last read this buffer has drained
                 uint32_t v[32];
@@ -273,18 +345,57 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
                                  "r"(v[4 * ch]), "r"(v[4 * ch + 1]), "r"(v[4 * ch + 2]), "r"(v[4 * ch + 3]) : "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) { tma_store_2d(&map_part, buf, col, grow); bulk_commit(); }
+                if (lane == 0 && !phantom) { tma_store_2d(mp.part, buf, col, grow); bulk_commit(); }
             }
         }
+        if (warp == 2) STC_STRACE(35);
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
+        if (warp == 2) STC_STRACE(36);
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 2) STC_STRACE(37);
+    if constexpr (PAIR) cluster_sync_all();             // neither CTA leaves (or frees TMEM) while the pair still computes / signals
     tc_fence_after();
     if (warp == 2) STC_STRACE(34);
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) { if constexpr (PAIR) tc2::tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 #undef STC_STRACE
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                           const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                           const __grid_constant__ CUtensorMap map_w1_hi64, const __grid_constant__ CUtensorMap map_w1_lo64,
+                           const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                           const __grid_constant__ CUtensorMap map_part, const StreamParams p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const StreamMaps mp{&map_a_hi, &map_a_lo, &map_w1_hi, &map_w1_lo, &map_w1_hi64, &map_w1_lo64, &map_w2_hi, &map_w2_lo, &map_part};
+    stream_body<false>(mp, p, (int)(blockIdx.x / p.nslice), (int)(blockIdx.x % p.nslice), 0, smem_raw);
+}
+
+// Pair form: clusters [0, npairs * nslice) are CTA pairs (row tiles 2 i, 2 i + 1; hidden slice = cluster % nslice); the clusters after
+// them are the odd last tile in the one-CTA form, two hidden slices per cluster. nslice must be 1, 2, 4 or 8 (128-unit aligned slices).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+convnext_mlp_stream2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                            const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                            const __grid_constant__ CUtensorMap map_w1_hi64, const __grid_constant__ CUtensorMap map_w1_lo64,
+                            const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                            const __grid_constant__ CUtensorMap map_w2_hi64, const __grid_constant__ CUtensorMap map_w2_lo64,
+                            const __grid_constant__ CUtensorMap map_part, const StreamParams p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const int cl = (int)tc::cluster_id_x(), rank = (int)tc::cluster_ctarank(), npc = p.npairs * p.nslice;
+    if (cl < npc) {
+        const StreamMaps mp{&map_a_hi, &map_a_lo, &map_w1_hi64, &map_w1_lo64, nullptr, nullptr, &map_w2_hi64, &map_w2_lo64, &map_part};
+        stream_body<true>(mp, p, 2 * (cl / p.nslice) + rank, cl % p.nslice, rank, smem_raw);
+    } else {
+        const int e = (cl - npc) * 2 + rank;
+        if (e >= p.nslice) return;
+        const StreamMaps mp{&map_a_hi, &map_a_lo, &map_w1_hi, &map_w1_lo, &map_w1_hi64, &map_w1_lo64, &map_w2_hi, &map_w2_lo, &map_part};
+        stream_body<false>(mp, p, 2 * p.npairs, e, 0, smem_raw);
+    }
 }
 
 }  // namespace mlp

@@ -14,7 +14,9 @@ namespace mlp {
 
 constexpr int C = 256, H = 1024;                  // channels, hidden units
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;                      // 16 warps were measured: the GELU of a 128-unit chunk takes 2 800 cycles either way (MUFU + issue bound:
+                                                  // 2 MUFU and ~22 issue slots per element), profiles/r2t_mlp_sweep_epi16.txt
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int KBLK = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16, one half (hi or lo)
 constexpr int X_BYTES = 2 * (C / BK) * KBLK;      // 128 KB: a-tile (hi k-blocks 0..3, lo k-blocks 0..3); later the store staging
 constexpr int UNIT = 2 * KBLK;                    // 32 KB: 128 weight rows x 64 K, hi + lo

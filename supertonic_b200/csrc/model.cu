@@ -91,6 +91,8 @@ struct VeCtx {
     std::vector<KV> kv;               // per cross-attention layer: step-invariant, hoisted out of the Euler loop
 };
 
+struct MlpPlan { int nslice; int mode; };      // mode 0: single CTAs; 1: CTA pairs + an odd last tile as single CTAs; 2: pairs, odd tile padded
+
 struct Handle {
     int device = 0;
     int num_sms = 148;
@@ -208,8 +210,10 @@ struct Handle {
     template <typename T> void convnext(const ConvNeXt& c, T* x, const Seq& seq, const PostOps* post = nullptr);
     void apply_post(const PostOps& post, float* x, const Seq& seq, int C);      // the same post-ops as separate launches
     bool mlp_fused(const ConvNeXt& c) const;
-    int mlp_slices(int tiles, int rows) const;
+    MlpPlan mlp_plan(int tiles, int rows) const;
     void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, const PostOps* post = nullptr);
+    int mlp_pair = -1;                // env STC_MLP_PAIR: 0 = one-CTA stream kernel only (cross-check), default: CTA pairs where the slices allow
+    int mlp_force_slices = 0;         // env STC_MLP_SLICES (tools/mlp_sweep.py): hidden slices per row tile instead of the cost model
     bool mlp_unfused = false;         // env STC_MLP=unfused: the C = 256 / H = 1024 blocks as two tcgen05 GEMMs (cross-check)
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
@@ -838,18 +842,39 @@ bool Handle::mlp_fused(const ConvNeXt& c) const {
     return tc_mode() && !mlp_unfused && c.C == mlp::C && c.H == mlp::H && c.pw1.w_hi && c.pw2.w_hi && !c.pw1.f16 && !c.pw2.f16;
 }
 
-// Hidden slices per 128-row tile of the stream form (mlp_stream.cuh): the count that minimises a cost model fitted to
-// tools/mlp_sweep.py on B200 (profiles/r2c_mlp_sweep.txt) —
-//   waves(tiles * s CTAs on the SMs) x (fixed part of a CTA + its 64-unit hidden blocks) + the reduce kernel's s partial reads.
-// 37 tiles -> 4 slices (148 CTAs, one wave); 38..49 -> 3; 50..74 -> 2; 75 tiles -> 3 slices in two waves (one slice per tile would
-// leave half of the SMs idle); >= ~100 tiles -> 1; <= 9 tiles -> 16 slices of 64 units (the batch-1 latency path).
-int Handle::mlp_slices(int tiles, int rows) const {
-    const double fixed_us = 5.2, blk64_us = 2.2, red0_us = 3.0, red_slice_us = 0.4 * std::max(rows, 1) / 4736.0;
-    int best = 1; double best_t = 1e30;
+// How a block's 128-row tiles x 1024 hidden units are dealt out to CTAs (mlp_stream.cuh): `nslice` hidden slices per row tile, as
+// single CTAs or — for 128-unit aligned slices (1, 2 or 4 of them) — as CTA pairs of two row tiles (half of the weight bytes per SM;
+// an odd last tile either runs as single CTAs inside the same launch or is padded to a pair, whichever keeps the wave count).
+// The plan minimises a cost model fitted to tools/mlp_sweep.py on B200 (profiles/r2c_mlp_sweep.txt, r2t_mlp_sweep_epi16.txt):
+//   waves x K(chunks of 128 units per CTA) x (1 + load x CTAs / SMs)  +  reduce kernel (3 us + 0.4 us per slice and 4 736 rows)
+// with K = 9.5 / 12.5 / +4.0 us per further chunk for single CTAs (a chunk is 8 weight units of ~980 cycles, shared-memory-port
+// paced) and 9.4 / 10.9 / +3.25 us for pairs (~795 cycles per unit: MMA bound), 7.1 us for a lone 64-unit slice.
+// 37 tiles -> 4 slices, 18 pairs + 1 single tile = 148 CTAs; 38..49 -> 3 slices, single (pairs need 2 or 4); 50..74 -> 2 slices in
+// pairs; >= ~100 tiles -> 1 slice in pairs; <= 9 tiles -> 16 slices of 64 units (the batch-1 latency path).
+MlpPlan Handle::mlp_plan(int tiles, int rows) const {
+    const double red0_us = 3.0, red_slice_us = 0.4 * std::max(rows, 1) / 4736.0;
+    auto kernel_us = [&](int chunks, bool half_chunk, bool pair) {
+        if (half_chunk) return 7.1;
+        if (pair) return chunks == 1 ? 9.4 : 10.9 + 3.25 * (chunks - 2);
+        return chunks == 1 ? 9.5 : 12.5 + 4.0 * (chunks - 2);
+    };
+    MlpPlan best{1, 0}; double best_t = 1e30;
     for (int s = 1; s <= 16; ++s) {
-        const int waves = (tiles * s + num_sms - 1) / num_sms, blk = (16 + s - 1) / s;
-        const double t = waves * (fixed_us + blk64_us * blk) + red0_us + red_slice_us * s;
-        if (t < best_t - 1e-9) { best_t = t; best = s; }
+        if (mlp_force_slices && s != mlp_force_slices) continue;
+        const int blk = (16 + s - 1) / s, chunks = (blk + 1) / 2;
+        const double red = red0_us + red_slice_us * s;
+        for (int mode = 0; mode < 3; ++mode) {
+            if (mode && (mlp_pair == 0 || tiles < 2 || !(s == 1 || s == 2 || s == 4))) continue;
+            if (!mode && mlp_pair == 1 && tiles >= 2 && (s == 1 || s == 2 || s == 4)) continue;      // forced pairs (sweeps)
+            if (mode == 2 && tiles % 2 == 0) continue;
+            const int ctas = mode == 0 ? tiles * s : mode == 1 ? (tiles / 2) * 2 * s + (tiles % 2) * s : (tiles + 1) / 2 * 2 * s;
+            const int waves = (ctas + num_sms - 1) / num_sms;
+            const double load = std::min(1.0, (double)ctas / num_sms);
+            double t = waves * kernel_us(chunks, blk == 1, mode != 0) * (1.0 + (mode ? 0.23 : 0.15) * load);
+            if (mode == 1 && tiles % 2) t = std::max(t, waves * kernel_us(chunks, false, false) * 1.08);   // the single CTAs of the odd tile
+            t += red;
+            if (t < best_t - 1e-9) { best_t = t; best = MlpPlan{s, mode}; }
+        }
     }
     return best;
 }
@@ -860,10 +885,12 @@ void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, cons
     const int tiles = cdiv(rows, mlp::BM);
     const size_t slice = (size_t)tiles * mlp::BM * mlp::C;
     const size_t mk = mark();
-    const int nslice = mlp_slices(tiles, rows);
+    const MlpPlan plan = mlp_plan(tiles, rows);
+    const int nslice = plan.nslice;
     float* partial = ws<float>(slice * nslice);
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
-    note(nslice == 1 ? "mlp_stream_x1" : nslice == 2 ? "mlp_stream_x2" : nslice == 3 ? "mlp_stream_x3" : nslice == 4 ? "mlp_stream_x4" : nslice <= 8 ? "mlp_stream_x5to8" : "mlp_stream_x9to16");
+    if (plan.mode) note(nslice == 1 ? "mlp_stream2_x1" : nslice == 2 ? "mlp_stream2_x2" : "mlp_stream2_x4");
+    else note(nslice == 1 ? "mlp_stream_x1" : nslice == 2 ? "mlp_stream_x2" : nslice == 3 ? "mlp_stream_x3" : nslice == 4 ? "mlp_stream_x4" : nslice <= 8 ? "mlp_stream_x5to8" : "mlp_stream_x9to16");
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);
         const CUtensorMap w1h64 = tmap(c.pw1.w_hi, c.H, c.C, 64), w1l64 = tmap(c.pw1.w_lo, c.H, c.C, 64);
@@ -872,8 +899,15 @@ void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, cons
         const CUtensorMap mpart = tmap_f32(partial, tiles * mlp::BM * nslice, mlp::C);
         mlp::StreamParams sp{};
         sp.M = rows; sp.nslice = nslice; sp.b1 = c.pw1.bias; sp.trace = mlp_trace;
-        launch_k(this, mlp::convnext_mlp_stream_kernel, dim3(tiles * nslice), dim3(mlp::NUM_THREADS), (size_t)mlp::ST_SMEM_BYTES, stream,
-                 mah, mal, w1h, w1l, w1h64, w1l64, w2h, w2l, mpart, sp);
+        if (plan.mode) {
+            const CUtensorMap w2h64 = tmap(c.pw2.w_hi, c.C, c.H, 64), w2l64 = tmap(c.pw2.w_lo, c.C, c.H, 64);
+            sp.npairs = plan.mode == 2 ? (tiles + 1) / 2 : tiles / 2;
+            const int clusters = sp.npairs * nslice + (plan.mode == 1 && tiles % 2 ? (nslice + 1) / 2 : 0);
+            launch_k(this, mlp::convnext_mlp_stream2_kernel, dim3(2 * clusters), dim3(mlp::NUM_THREADS), (size_t)mlp::ST_SMEM_BYTES, stream,
+                     mah, mal, w1h, w1l, w1h64, w1l64, w2h, w2l, w2h64, w2l64, mpart, sp);
+        } else
+            launch_k(this, mlp::convnext_mlp_stream_kernel, dim3(tiles * nslice), dim3(mlp::NUM_THREADS), (size_t)mlp::ST_SMEM_BYTES, stream,
+                     mah, mal, w1h, w1l, w1h64, w1l64, w2h, w2l, mpart, sp);
         if (post)
             launch_k(this, nslice > 4 ? mlp::mlp_reduce_post_kernel<true> : mlp::mlp_reduce_post_kernel<false>, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, stream,
                      (const float*)partial, slice, c.pw2.bias, c.gamma, mask, x, rows, post->add_vec, post->ln_g, post->ln_b, 1e-6f,
@@ -1435,6 +1469,8 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         hd->precision = precision;
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_MLP"); hd->mlp_unfused = e && !strcmp(e, "unfused"); }
+        { const char* e = getenv("STC_MLP_PAIR"); if (e && *e) hd->mlp_pair = atoi(e); }
+        { const char* e = getenv("STC_MLP_SLICES"); if (e && *e) hd->mlp_force_slices = std::max(0, std::min(16, atoi(e))); }
         { const char* e = getenv("STC_DP"); hd->dp_fused = !(e && !strcmp(e, "unfused")); }
         { const char* e = getenv("STC_VOC"); hd->voc_f16 = !e || !strcmp(e, "f16"); }
         { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); hd->dw_chain_kernel = !(e && !strcmp(e, "slide")); }
@@ -1466,6 +1502,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<attn::MAX_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Lay<1>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::ST_SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(mlp::convnext_mlp_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::ST_SMEM_BYTES));
         }
 #define STC_CHAIN_ATTR(NW, KK)                                                                                                                 \
     STC_CUDA(cudaFuncSetAttribute((dwconv_ln_chain_kernel<NW, KK, OutSplit>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainSmem<KK>::BYTES)); \
@@ -2205,7 +2242,7 @@ int stc_debug_mlp(stc_handle* sh, int M, int iters, float* ms_fused, float* ms_u
                 long long ht[64];
                 STC_CUDA(cudaMemcpyAsync(ht, tr, 64 * 8, cudaMemcpyDeviceToHost, h->stream));
                 STC_CUDA(cudaStreamSynchronize(h->stream));
-                fprintf(stderr, "mlp trace M=%d (cycles since prologue end; [8..23] MMA warp per weight unit, [24..27] S chunk ready, [28..31] P chunk written, [32,33] output half final, [34] end, [40..55] producer per unit):", M);
+                fprintf(stderr, "mlp trace M=%d (cycles since prologue end; [8..23] MMA warp per weight unit, [24..27] S chunk ready, [28..31] P chunk written, [32,33] output half final, [35] stores issued, [36] store reads drained, [37] CTA joined, [34] end, [40..55] producer per unit):", M);
                 for (int i = 0; i < 64; ++i) fprintf(stderr, "%s%lld", i % 8 == 0 ? "\n  " : " ", ht[i] ? ht[i] - ht[0] : -99999);
                 fprintf(stderr, "\n");
                 STC_CUDA(cudaMemcpyAsync(Xa, X0, (size_t)M * C * 4, cudaMemcpyDeviceToDevice, h->stream));

@@ -172,8 +172,12 @@ TextToSpeech::SynthesisResult TextToSpeech::batch(const std::vector<std::string>
     return _infer(text_list, lang_list, style, total_step, speed);
 }
 
-// many() = plan (front-end once, groups of similar token counts) + run (packed launches of the groups on ONE engine).
+// many() = plan (front-end once, launch groups) + run (packed launches of the groups on ONE engine).
 // MultiGpuTextToSpeech runs the same plan with the groups dealt out over several engines.
+// Groups: as few as `max_batch` utterances and 140 row tiles of PREDICTED latent frames per group allow, filled to equal predicted
+// frames (longest text first into the emptiest group). Packed rows carry no padding, so a group need not hold similar lengths;
+// what costs is a group whose 128-row tiles do not fill the 148 SMs, or one that spills into a second wave of the fused MLP
+// (model.cu mlp_plan). The frames-per-token ratio is what the last runGroups of this object measured (1.0 until then).
 TextToSpeech::ManyPlan TextToSpeech::planMany(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list,
                                               int max_batch) const {
     ManyPlan p;
@@ -181,10 +185,27 @@ TextToSpeech::ManyPlan TextToSpeech::planMany(const std::vector<std::string>& te
     textToIds(text_list, lang_list, p.ids, p.mask, p.T);
     p.tok.resize(n);
     for (int i = 0; i < n; ++i) p.tok[i] = (int)std::accumulate(p.mask.begin() + (size_t)i * p.T, p.mask.begin() + (size_t)(i + 1) * p.T, 0.f);
+    if (n == 0) return p;
+    max_batch = std::max(1, max_batch);
+    const double fpt = frames_per_token_.load(), max_rows = 140.0 * 128.0;
+    std::vector<double> est(n);
+    double total = 0;
+    for (int i = 0; i < n; ++i) { est[i] = std::max(1.0, p.tok[i] * fpt); total += est[i]; }
+    const int ng = std::min(n, std::max((n + max_batch - 1) / max_batch, (int)std::ceil(total / max_rows)));
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.tok[a] < p.tok[b]; });     // similar token counts share a group
-    for (int g0 = 0; g0 < n; g0 += max_batch) p.groups.emplace_back(order.begin() + g0, order.begin() + std::min(n, g0 + max_batch));
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return est[a] > est[b]; });
+    std::vector<double> load(ng, 0.0);
+    p.groups.assign(ng, {});
+    for (int i : order) {
+        int g = -1;
+        for (int k = 0; k < ng; ++k)
+            if ((int)p.groups[k].size() < max_batch && (g < 0 || load[k] < load[g])) g = k;
+        p.groups[g].push_back(i);
+        load[g] += est[i];
+    }
+    for (auto& g : p.groups) std::sort(g.begin(), g.end());
+    p.groups.erase(std::remove_if(p.groups.begin(), p.groups.end(), [](const std::vector<int>& g) { return g.empty(); }), p.groups.end());
     return p;
 }
 
@@ -202,7 +223,9 @@ void TextToSpeech::runGroups(const ManyPlan& plan, const std::vector<int>& group
             Pending p;
             p.grp = &plan.groups[gi];
             const std::vector<int>& grp = *p.grp;
-            const int B = (int)grp.size(), Tg = plan.tok[grp.back()];
+            const int B = (int)grp.size();
+            int Tg = 1;
+            for (int i : grp) Tg = std::max(Tg, plan.tok[i]);
             std::vector<int64_t> gids((size_t)B * Tg); std::vector<float> gm((size_t)B * Tg);
             int64_t toks = 0;
             for (int k = 0; k < B; ++k) {
@@ -229,12 +252,16 @@ void TextToSpeech::runGroups(const ManyPlan& plan, const std::vector<int>& group
         }
         if (stc_wait(engine_) != STC_OK) raise(engine_, "stc_wait");
     } catch (...) { stc_wait(engine_); free_all(); throw; }
+    int64_t frames = 0, tokens = 0;
     for (auto& p : pend)
         for (size_t k = 0; k < p.grp->size(); ++k) {
             Utterance& u = out[(*p.grp)[k]];
             u.duration = p.dur[k];
             u.wav.assign(p.wav + p.off[k], p.wav + p.off[k] + p.wl[k]);
+            frames += (p.off[k + 1] - p.off[k]) / cs;
+            tokens += plan.tok[(*p.grp)[k]];
         }
+    if (tokens > 0) frames_per_token_.store((double)frames / (double)tokens);       // the next plan's prediction
     free_all();
 }
 

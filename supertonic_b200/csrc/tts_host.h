@@ -12,6 +12,7 @@
 // :442-443), `many()` — independent utterances on packed latent rows — and `callBatched()` — all chunks of one
 // long text in a single packed batch.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <iomanip>
@@ -78,7 +79,7 @@ public:
     struct ManyPlan {
         std::vector<int64_t> ids; std::vector<float> mask; int64_t T = 0;      // front-end output for the whole request
         std::vector<int> tok;                                                   // token count per text
-        std::vector<std::vector<int>> groups;                                   // text indices per launch group (similar token counts)
+        std::vector<std::vector<int>> groups;                                   // text indices per launch group (equal predicted latent frames)
     };
     ManyPlan planMany(const std::vector<std::string>& text_list, const std::vector<std::string>& lang_list, int max_batch) const;
     // Synthesises the groups `group_ids` of `plan` on this engine into out[text index]. Noise streams are keyed by the text's index in
@@ -103,6 +104,7 @@ private:
     stc_config geo_{};
     int sample_rate_;
     uint64_t seed_ = 0, calls_ = 0;
+    std::atomic<double> frames_per_token_{1.0};      // latent frames per text token measured by the last runGroups (planMany's prediction)
     std::vector<float> noise_;
     int64_t noise_ld_ = 0;
 };

@@ -28,6 +28,33 @@ def length_buckets(lengths: Sequence[int], max_batch: int = 64, max_pad: float =
     return groups
 
 
+# One wave of the fused ConvNeXt MLP at one hidden slice per row tile = one 128-row tile per SM (148 on B200); a launch group a few
+# tiles larger takes a second wave (csrc/model.cu mlp_plan), so groups are filled to 140 tiles of PREDICTED latent frames.
+GROUP_ROWS = 140 * 128
+
+
+def frame_balanced_groups(lengths: Sequence[int], max_batch: int = 128, frames_per_token: float = 1.0,
+                          max_rows: int = GROUP_ROWS) -> List[List[int]]:
+    """Launch groups for the packed path (`synthesize_many`): as few groups as `max_batch` utterances and `max_rows` predicted
+    latent frames per group allow, filled to EQUAL predicted frames (longest utterance first into the emptiest group). Packed rows
+    carry no padding, so a group need not hold similar lengths; what costs is a group whose row tiles do not fill the SMs (small
+    groups run at a fraction of the rate: 32 utterances 40 k audio-s/s, 128 utterances 57 k) or spill into a second wave. Sorting
+    by length (length_buckets) made one group of a 1 024-utterance request 29 row tiles and another 223. Indices inside a group
+    are ascending; results do not depend on the grouping (noise streams are keyed by the index in the request)."""
+    n = len(lengths)
+    if n == 0:
+        return []
+    est = np.maximum(np.asarray(lengths, dtype=np.float64) * float(frames_per_token), 1.0)
+    n_groups = min(n, max(-(-n // max(1, int(max_batch))), int(np.ceil(est.sum() / max(1, int(max_rows))))))
+    load = [0.0] * n_groups
+    groups: List[List[int]] = [[] for _ in range(n_groups)]
+    for i in sorted(range(n), key=lambda k: (-est[k], k)):
+        g = min((k for k in range(n_groups) if len(groups[k]) < max_batch), key=lambda k: (load[k], k))
+        groups[g].append(i)
+        load[g] += est[i]
+    return [sorted(g) for g in groups if g]
+
+
 def shard_lpt(costs: Sequence[float], world_size: int) -> List[List[int]]:
     """Longest-processing-time-first assignment of work items to `world_size` replicas (deterministic)."""
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))

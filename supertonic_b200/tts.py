@@ -113,8 +113,14 @@ class SynthesisResult:
 
 
 class TextToSpeech:
-    def __init__(self, engine: capi.Engine):
+    def __init__(self, engine: capi.Engine, lanes: Sequence[capi.Engine] = ()):
+        """`lanes`: further engines (handles) on the SAME GPU — request lanes. Inside one handle the Euler loop / vocoder of
+        consecutive requests run back to back on one stream; a second handle has its own streams, workspaces and CUDA graphs, so
+        the launch groups `synthesize_many` deals out alternately overlap on the device: a stream of 32-utterance requests gains
+        ~10 % with two lanes (tools/concurrent_handles.py), groups of 128 utterances fill the GPU on their own and gain nothing."""
         self.engine = engine
+        self.lanes = [engine, *lanes]
+        self._lane = 0
         self.cfg = engine.cfg
         self.sample_rate = engine.cfg.sample_rate
         self.noise_seed = 0            # advanced per _infer call unless noise is injected
@@ -189,15 +195,30 @@ class TextToSpeech:
         returns before the last copies have landed — call `engine.wait()` before reading the waveforms; issuing the next
         synthesize_many first overlaps its computation with these copies (request streams). pcm16=True: int16 samples quantised
         on the device (writeWavFile's rule), half the device->host bytes."""
+        lanes = getattr(self, "lanes", None) or [self.engine]
         plan = plan_many(self.engine, texts, langs, max_batch)
         out: List[Optional[Tuple[np.ndarray, float]]] = [None] * len(texts)
         self._parity = 1 - getattr(self, "_parity", 1)
-        run_groups(self.engine, plan, range(len(plan.groups)), style, total_step, speed, seed, out, tag=f"p{self._parity}", noise=noise, pcm16=pcm16)
+        if len(lanes) == 1 or noise is not None:
+            run_groups(self.engine, plan, range(len(plan.groups)), style, total_step, speed, seed, out, tag=f"p{self._parity}", noise=noise, pcm16=pcm16)
+        else:
+            # request lanes: consecutive launch groups (of this and of the previous calls) go to alternating handles; the tag keeps
+            # the page-locked result buffers of the last two calls apart per handle
+            for gi in range(len(plan.groups)):
+                eng = lanes[self._lane % len(lanes)]
+                self._lane += 1
+                run_groups(eng, plan, [gi], style, total_step, speed, seed, out, tag=f"p{self._parity}", pcm16=pcm16)
+            self.engine.frames_per_token = lanes[(self._lane - 1) % len(lanes)].frames_per_token
         if wait or copy:
-            self.engine.wait()
+            self.wait()
             if copy:
                 out = [(w.copy(), d) for w, d in out]
         return out
+
+    def wait(self) -> None:
+        """Blocks until every asynchronous result of synthesize_many(wait=False) has landed (all request lanes)."""
+        for e in getattr(self, "lanes", None) or [self.engine]:
+            e.wait()
 
 
 @dataclass
@@ -205,20 +226,23 @@ class ManyPlan:
     ids: np.ndarray             # [n, T] token ids of the whole request (text front-end run once)
     mask: np.ndarray            # [n, 1, T]
     lens: np.ndarray            # [n] token counts
-    groups: List[List[int]]     # text indices per launch group (similar token counts)
+    groups: List[List[int]]     # text indices per launch group (equal predicted latent frames, scheduler.frame_balanced_groups)
 
 
 def plan_many(engine: capi.Engine, texts, langs, max_batch: int) -> ManyPlan:
-    from .scheduler import length_buckets
+    """Front-end once, then launch groups of equal predicted latent frames. The frames-per-token ratio is what this engine's
+    last synthesize_many measured (`engine.frames_per_token`; 1.0 — about one 70 ms latent frame per character — until then)."""
+    from .scheduler import frame_balanced_groups
     ids, mask = engine.text_to_ids(texts, langs)
     lens = mask.reshape(len(texts), -1).sum(1).astype(np.int64)
-    return ManyPlan(ids, mask, lens, length_buckets(lens, max_batch, 1e9))
+    return ManyPlan(ids, mask, lens, frame_balanced_groups(lens, max_batch, getattr(engine, "frames_per_token", 1.0)))
 
 
 def run_groups(engine: capi.Engine, plan: ManyPlan, group_ids, style: Style, total_step: int, speed: float, seed: int, out: list,
                tag: str = "", noise: Optional[np.ndarray] = None, pcm16: bool = False) -> None:
     """The launch groups `group_ids` of `plan` on ONE engine, as an asynchronous request stream; fills out[text index] with
     (trimmed waveform view, duration). The caller waits (`engine.wait()`) before reading the waveforms."""
+    frames = tokens = 0
     for gi in group_ids:
         g = np.asarray(plan.groups[gi])
         T = int(plan.lens[g].max())
@@ -228,6 +252,10 @@ def run_groups(engine: capi.Engine, plan: ManyPlan, group_ids, style: Style, tot
         for k, i in enumerate(g):
             o = int(r["offsets"][k])
             out[int(i)] = (r["out"][o:o + int(r["wav_lengths"][k])], float(r["duration"][k]))
+        frames += int(np.asarray(r["frames"]).sum())
+        tokens += int(plan.lens[g].sum())
+    if tokens:
+        engine.frames_per_token = frames / tokens      # the next plan's prediction (plan_many)
 
 
 class MultiGpuTextToSpeech:
@@ -302,12 +330,13 @@ class MultiGpuTextToSpeech:
         return [(w.copy(), d) for w, d in out] if copy else out
 
 
-def load_text_to_speech(onnx_dir: str, use_gpu: bool = True, device: int = 0, precision: int = capi.PREC_DEFAULT) -> TextToSpeech:
+def load_text_to_speech(onnx_dir: str, use_gpu: bool = True, device: int = 0, precision: int = capi.PREC_DEFAULT, lanes: int = 1) -> TextToSpeech:
     """Mirror of loadTextToSpeech (cpp/helper.cpp:903-937). The reference throws on use_gpu=True; this library is
-    GPU-only, so it throws on use_gpu=False instead — there is no CPU path to fall back to."""
+    GPU-only, so it throws on use_gpu=False instead — there is no CPU path to fall back to. `lanes` > 1: that many handles on
+    the device (TextToSpeech `lanes`)."""
     if not use_gpu:
         raise RuntimeError("CPU mode is not supported by supertonic_b200 (use the reference's ONNX Runtime path)")
-    return TextToSpeech(capi.Engine(onnx_dir, device, precision))
+    return TextToSpeech(capi.Engine(onnx_dir, device, precision), [capi.Engine(onnx_dir, device, precision) for _ in range(max(1, int(lanes)) - 1)])
 
 
 def parse_devices(spec: str) -> List[int]:

@@ -30,7 +30,7 @@ class _FakeEngine:
                           wait=True, gap_samples=0):
         B = ids.shape[0]
         lens = mask.reshape(B, -1).sum(1).astype(np.int64)
-        assert (np.diff(lens) >= 0).all(), "a launch group holds similar token counts in ascending order"
+        assert (np.diff(np.asarray(noise_index)) > 0).all(), "a launch group holds request indices in ascending order"
         self.calls.append((self.name, [int(i) for i in noise_index], pinned))
         frames = (lens + 9) // 10
         off = np.concatenate([[0], np.cumsum(frames * 3072)])

@@ -315,10 +315,40 @@ def test_error_paths(rig):
     assert eng.launches > 0
 
 
-@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_DW", "tile"), ("STC_DW", "slide"), ("STC_DP", "unfused")])
+@pytest.mark.parametrize("pair", ["0", "1", ""])
+def test_fused_mlp_forms_match_two_gemms(rig, pair):
+    """stc_debug_mlp: the fused ConvNeXt MLP (mlp_stream.cuh) against pw1 -> GELU -> pw2 as two tcgen05 GEMMs on the same random block,
+    at row counts on both sides of every boundary of the plan (mlp_plan): one-CTA slices, CTA pairs (cta_group::2) with an even tile
+    count, with an odd last tile as single CTAs in the same launch (37 tiles) and padded to a pair (19, 65, 145 tiles), ragged last tile.
+    STC_MLP_PAIR=0 / 1 force the one-CTA form / pairs wherever the slices allow."""
+    import os
+    if rig["name"] != "full":
+        pytest.skip("kernel-level check, independent of the graphs")
+    capi = rig["capi"]
+    os.environ["STC_MLP_PAIR"] = pair
+    try:
+        eng2 = capi.Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_MLP_PAIR"]
+    try:
+        v0 = eng2.kernel_variants()
+        for rows in (100, 300, 1152, 2432, 4700, 4736, 4864, 6000, 8320, 9472, 12800, 18560):
+            _, _, diff = eng2.debug_mlp(rows, 2)
+            assert diff <= 5e-6, (pair, rows, diff)
+        d = {k: v - v0.get(k, 0) for k, v in eng2.kernel_variants().items() if k.startswith("mlp_stream")}
+        if pair == "0":
+            assert not any(k.startswith("mlp_stream2") for k in d), d
+        else:
+            assert d.get("mlp_stream2_x4", 0) and d.get("mlp_stream2_x2", 0) and d.get("mlp_stream2_x1", 0), d
+    finally:
+        eng2.close()
+
+
+@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP_PAIR", "0"), ("STC_DW", "tile"), ("STC_DW", "slide"), ("STC_DP", "unfused")])
 def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
     """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
-    fp32 core. STC_MLP=unfused: the fused ConvNeXt MLP (mlp_stream.cuh) against pw1 / pw2 as two tcgen05 GEMMs. STC_DW=tile / slide:
+    fp32 core. STC_MLP=unfused: the fused ConvNeXt MLP (mlp_stream.cuh) against pw1 / pw2 as two tcgen05 GEMMs; STC_MLP_PAIR=0: its
+    one-CTA form against CTA pairs. STC_DW=tile / slide:
     the depthwise-conv + LayerNorm kernels against their simpler forms. STC_DP=unfused: the one-kernel-per-block fp64 duration
     predictor against separate conv / GEMM launches. Same weights, text encoder (self + style attention, rotary) and one
     vector-estimator step (length-aware rotary cross-attention with a masked key tail, 50-key style attention, ragged rows incl. a

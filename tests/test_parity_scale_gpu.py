@@ -76,7 +76,7 @@ def _packed_vs_oracle(rig, ids, mask, ttl, dp, steps, noise_seed, check_all=True
 
 def test_configs1_batch_matches_the_oracle(rig):
     """configs[1] exactly as bench.py builds it: 32 utterances, 4 621 latent frames = 37 row tiles, 5 858 text tokens, total_step 5.
-    Reaches the 4-slice fused MLP, the two-SM fp16 vocoder GEMMs, the BN = 128/256 one-SM tiles and the ring depthwise conv."""
+    Reaches the 4-slice fused MLP in its CTA-pair form, the two-SM fp16 vocoder GEMMs, the BN = 128/256 one-SM tiles and the ring depthwise conv."""
     ids, mask, ttl, dp = _bench_batch(rig, 32, 1234)
     v0 = rig["eng"].kernel_variants()
     frames, err, snr = _packed_vs_oracle(rig, ids, mask, ttl, dp, 5, 77)
@@ -84,7 +84,7 @@ def test_configs1_batch_matches_the_oracle(rig):
     d = _delta(v0, rig["eng"].kernel_variants())
     assert d.get("gemm2_f16", 0) > 0, d                       # vocoder pw1 / pw2 / conv_in / head on CTA pairs
     assert d.get("dwconv_ln_chain", 0) >= 10, d               # vocoder depthwise conv + LayerNorm (long chains)
-    assert d.get("mlp_stream_x4", 0) == 160 and d.get("mlp_stream_x3", 0) == 12, d     # 37 latent row tiles / 46 text row tiles
+    assert d.get("mlp_stream2_x4", 0) == 160 and d.get("mlp_stream_x3", 0) == 12, d    # 37 latent row tiles (18 CTA pairs + 1) / 46 text row tiles
     assert d.get("dp_convnext_fused", 0) == 4, d              # fp64 duration predictor, one kernel per block
     print(f"configs[1]: latent max-abs {err:.2e}, worst wav SNR {snr:.1f} dB, variants {d}")
 

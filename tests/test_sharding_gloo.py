@@ -71,4 +71,24 @@ def test_length_buckets_and_lpt_properties():
         loads = [sum(lens[i] for i in s) for s in sh]
         assert max(loads) - min(loads) <= max(lens)
     assert S.shard_lpt([], 4) == [[], [], [], []]
+
+
+def test_frame_balanced_groups_properties():
+    """Launch groups of synthesize_many: every utterance once, at most max_batch per group, as few groups as the utterance and
+    predicted-frame budgets allow, predicted frames equal to within the longest utterance, budget respected when it can be."""
+    rng = np.random.default_rng(1)
+    lens = [int(x) for x in rng.integers(22, 305, size=1024)]
+    for fpt, mb in ((0.8, 128), (1.0, 128), (1.0, 64), (2.5, 128), (0.8, 1000)):
+        groups = S.frame_balanced_groups(lens, mb, fpt)
+        assert sorted(i for g in groups for i in g) == list(range(1024))
+        assert all(g == sorted(g) and 0 < len(g) <= mb for g in groups)
+        total = sum(lens) * fpt
+        assert len(groups) == max(-(-1024 // mb), int(np.ceil(total / S.GROUP_ROWS)))
+        loads = [sum(lens[i] for i in g) * fpt for g in groups]
+        assert max(loads) - min(loads) <= max(lens) * fpt + 1e-9
+        if len(groups) > -(-1024 // mb):          # the frame budget set the group count: it holds up to one utterance
+            assert max(loads) <= S.GROUP_ROWS + max(lens) * fpt
+    assert S.frame_balanced_groups([], 8) == []
+    assert S.frame_balanced_groups([5, 9, 300], 128, 1.0) == [[0, 1, 2]]                      # a small request is one group
+    assert S.frame_balanced_groups([10] * 5, 2, 1.0) == [[0, 3], [1, 4], [2]]                 # the utterance cap alone
     assert S.reduce_throughput(10.0, 500.0, 1) == (20.0, 500.0, 10.0)
