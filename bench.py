@@ -505,7 +505,16 @@ def main():
             fl_total = 4.0 * 256 * 1024 * (n_ve * frames + 12 * tokens)
             ig["fused_mlp"] = {"us_per_block_latent_rows": f_lat, "us_per_block_text_rows": f_txt, "rows": [frames, tokens],
                                "two_gemm_form_us": [u_lat, u_txt], "achieved": fl_total / us_total / 1e6,
+                               "large_group": None,
                                "how": "stc_debug_mlp: 20 launches of (stream kernel + reduce kernel) replayed from one CUDA graph, CUDA events on the library's stream"}
+            # the same kernel pair on a launch group of configs[4] (tts.plan_many fills groups to ~136 row tiles: one CTA pair per two tiles,
+            # the whole hidden layer per pair — the wave-limited 37-tile headline shape is the small end of the kernel's range)
+            g_rows = 136 * 128
+            f_big, u_big, _ = eng.debug_mlp(g_rows, 20)
+            a_big = 4.0 * 256 * 1024 * g_rows / f_big / 1e6
+            ig["fused_mlp"]["large_group"] = {"rows": g_rows, "us_per_block": f_big, "two_gemm_form_us": u_big, "achieved": a_big,
+                                              "frac": a_big / pk["bf16_sustained"], "frac_executed_mma": 3 * a_big / pk["bf16_sustained"],
+                                              "frac_executed_mma_of_burst_peak": 3 * a_big / pk["bf16"]}
             os.environ["STC_DEBUG_F16"] = "1"
             vrows = frames * eng.cfg.chunk_compress_factor
             s_us, t_us, _ = eng.debug_dwconv(vrows, 512, 7, 1, True, len(texts), 0, 20)

@@ -105,7 +105,9 @@ struct StreamMaps {
 };
 
 // One CTA's share of a block: row tile `tile`, hidden slice `slice`. PAIR: this CTA is rank `rank` of a CTA pair (cluster of two
-// along x) that owns row tiles (tile - rank, tile - rank + 1); hidden slices are 128-unit aligned there (16 / nslice even).
+// along x) that owns row tiles (tile - rank, tile - rank + 1); hidden slices are whole 128-unit chunks there (the eight chunks dealt out
+// as evenly as possible: 3 slices = 2 + 3 + 3 chunks). The partition of the hidden layer may differ from tile to tile — the reduce kernel
+// only adds a row's nslice partials — so an odd last tile keeps the one-CTA form's 64-unit granularity.
 template <bool PAIR>
 STC_DEVINL void stream_body(const StreamMaps& mp, const StreamParams& p, const int tile, const int slice, const int rank, uint8_t* smem_raw) {
     using namespace tc;
@@ -126,7 +128,8 @@ STC_DEVINL void stream_body(const StreamMaps& mp, const StreamParams& p, const i
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = tile * BM;
     int u0, u1;
-    stream_range(slice, p.nslice, u0, u1);
+    if constexpr (PAIR) { u0 = 2 * ((slice * 8) / p.nslice); u1 = 2 * (((slice + 1) * 8) / p.nslice); }      // whole 128-unit chunks
+    else stream_range(slice, p.nslice, u0, u1);
     const int nblk64 = u1 - u0, nchunks = (nblk64 + 1) >> 1, h0 = u0 * 64;
     auto chunk_w = [&](int c) { return nblk64 - 2 * c >= 2 ? 128 : 64; };
 #define STC_STRACE(idx) do { if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[idx] = clock64(); } while (0)
@@ -376,7 +379,7 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
 }
 
 // Pair form: clusters [0, npairs * nslice) are CTA pairs (row tiles 2 i, 2 i + 1; hidden slice = cluster % nslice); the clusters after
-// them are the odd last tile in the one-CTA form, two hidden slices per cluster. nslice must be 1, 2, 4 or 8 (128-unit aligned slices).
+// them are the odd last tile in the one-CTA form, two hidden slices per cluster. nslice <= 8 (a pair's slice is at least one 128-unit chunk).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 convnext_mlp_stream2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                             const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,

@@ -843,13 +843,13 @@ bool Handle::mlp_fused(const ConvNeXt& c) const {
 }
 
 // How a block's 128-row tiles x 1024 hidden units are dealt out to CTAs (mlp_stream.cuh): `nslice` hidden slices per row tile, as
-// single CTAs or — for 128-unit aligned slices (1, 2 or 4 of them) — as CTA pairs of two row tiles (half of the weight bytes per SM;
+// single CTAs or — up to 4 slices of whole 128-unit chunks — as CTA pairs of two row tiles (half of the weight bytes per SM;
 // an odd last tile either runs as single CTAs inside the same launch or is padded to a pair, whichever keeps the wave count).
 // The plan minimises a cost model fitted to tools/mlp_sweep.py on B200 (profiles/r2c_mlp_sweep.txt, r2t_mlp_sweep_epi16.txt):
 //   waves x K(chunks of 128 units per CTA) x (1 + load x CTAs / SMs)  +  reduce kernel (3 us + 0.4 us per slice and 4 736 rows)
 // with K = 9.5 / 12.5 / +4.0 us per further chunk for single CTAs (a chunk is 8 weight units of ~980 cycles, shared-memory-port
 // paced) and 9.4 / 10.9 / +3.25 us for pairs (~795 cycles per unit: MMA bound), 7.1 us for a lone 64-unit slice.
-// 37 tiles -> 4 slices, 18 pairs + 1 single tile = 148 CTAs; 38..49 -> 3 slices, single (pairs need 2 or 4); 50..74 -> 2 slices in
+// 37 tiles -> 4 slices, 18 pairs + 1 single tile = 148 CTAs; 38..49 -> 3 slices (2 + 3 + 3 chunks) in pairs; 50..74 -> 2 slices in
 // pairs; >= ~100 tiles -> 1 slice in pairs; <= 9 tiles -> 16 slices of 64 units (the batch-1 latency path).
 MlpPlan Handle::mlp_plan(int tiles, int rows) const {
     const double red0_us = 3.0, red_slice_us = 0.4 * std::max(rows, 1) / 4736.0;
@@ -861,17 +861,19 @@ MlpPlan Handle::mlp_plan(int tiles, int rows) const {
     MlpPlan best{1, 0}; double best_t = 1e30;
     for (int s = 1; s <= 16; ++s) {
         if (mlp_force_slices && s != mlp_force_slices) continue;
-        const int blk = (16 + s - 1) / s, chunks = (blk + 1) / 2;
+        const int blk = (16 + s - 1) / s;
         const double red = red0_us + red_slice_us * s;
         for (int mode = 0; mode < 3; ++mode) {
-            if (mode && (mlp_pair == 0 || tiles < 2 || !(s == 1 || s == 2 || s == 4))) continue;
-            if (!mode && mlp_pair == 1 && tiles >= 2 && (s == 1 || s == 2 || s == 4)) continue;      // forced pairs (sweeps)
+            const bool pair_ok = tiles >= 2 && s <= 4;            // a pair's slice is whole 128-unit chunks: 8 / 4 / 2+3+3 / 2
+            if (mode && (mlp_pair == 0 || !pair_ok)) continue;
+            if (!mode && mlp_pair == 1 && pair_ok) continue;      // forced pairs (sweeps)
+            const int chunks = mode ? (8 + s - 1) / s : (blk + 1) / 2;
             if (mode == 2 && tiles % 2 == 0) continue;
             const int ctas = mode == 0 ? tiles * s : mode == 1 ? (tiles / 2) * 2 * s + (tiles % 2) * s : (tiles + 1) / 2 * 2 * s;
             const int waves = (ctas + num_sms - 1) / num_sms;
             const double load = std::min(1.0, (double)ctas / num_sms);
             double t = waves * kernel_us(chunks, blk == 1, mode != 0) * (1.0 + (mode ? 0.23 : 0.15) * load);
-            if (mode == 1 && tiles % 2) t = std::max(t, waves * kernel_us(chunks, false, false) * 1.08);   // the single CTAs of the odd tile
+            if (mode == 1 && tiles % 2) t = std::max(t, waves * kernel_us((blk + 1) / 2, false, false) * 1.08);   // the single CTAs of the odd tile
             t += red;
             if (t < best_t - 1e-9) { best_t = t; best = MlpPlan{s, mode}; }
         }
@@ -889,7 +891,7 @@ void Handle::fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, cons
     const int nslice = plan.nslice;
     float* partial = ws<float>(slice * nslice);
     kprof_begin(3, 4.0 * rows * (double)c.C * c.H, 4.0 * (3.0 * rows * c.C + 2.0 * c.C * c.H));
-    if (plan.mode) note(nslice == 1 ? "mlp_stream2_x1" : nslice == 2 ? "mlp_stream2_x2" : "mlp_stream2_x4");
+    if (plan.mode) note(nslice == 1 ? "mlp_stream2_x1" : nslice == 2 ? "mlp_stream2_x2" : nslice == 3 ? "mlp_stream2_x3" : "mlp_stream2_x4");
     else note(nslice == 1 ? "mlp_stream_x1" : nslice == 2 ? "mlp_stream_x2" : nslice == 3 ? "mlp_stream_x3" : nslice == 4 ? "mlp_stream_x4" : nslice <= 8 ? "mlp_stream_x5to8" : "mlp_stream_x9to16");
     if (!dry) {
         const CUtensorMap w1h = tmap(c.pw1.w_hi, c.H, c.C, 128), w1l = tmap(c.pw1.w_lo, c.H, c.C, 128);

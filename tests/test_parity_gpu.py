@@ -339,7 +339,7 @@ def test_fused_mlp_forms_match_two_gemms(rig, pair):
         if pair == "0":
             assert not any(k.startswith("mlp_stream2") for k in d), d
         else:
-            assert d.get("mlp_stream2_x4", 0) and d.get("mlp_stream2_x2", 0) and d.get("mlp_stream2_x1", 0), d
+            assert d.get("mlp_stream2_x4", 0) and d.get("mlp_stream2_x3", 0) and d.get("mlp_stream2_x2", 0) and d.get("mlp_stream2_x1", 0), d
     finally:
         eng2.close()
 

@@ -84,7 +84,7 @@ def test_configs1_batch_matches_the_oracle(rig):
     d = _delta(v0, rig["eng"].kernel_variants())
     assert d.get("gemm2_f16", 0) > 0, d                       # vocoder pw1 / pw2 / conv_in / head on CTA pairs
     assert d.get("dwconv_ln_chain", 0) >= 10, d               # vocoder depthwise conv + LayerNorm (long chains)
-    assert d.get("mlp_stream2_x4", 0) == 160 and d.get("mlp_stream_x3", 0) == 12, d    # 37 latent row tiles (18 CTA pairs + 1) / 46 text row tiles
+    assert d.get("mlp_stream2_x4", 0) == 160 and d.get("mlp_stream2_x3", 0) == 12, d   # 37 latent row tiles (18 CTA pairs + 1) / 46 text row tiles (23 pairs)
     assert d.get("dp_convnext_fused", 0) == 4, d              # fp64 duration predictor, one kernel per block
     print(f"configs[1]: latent max-abs {err:.2e}, worst wav SNR {snr:.1f} dB, variants {d}")
 
