@@ -246,7 +246,9 @@ _app = None
 def get_app():
     """The service configured from the environment like the reference's (py/service.py:19-24): TTS_ONNX_DIR, plus
     TTS_DEVICE (one GPU) or TTS_DEVICES (e.g. "0-7": one engine + host thread per GPU, every coalesced launch group dealt out over
-    them — tts.MultiGpuTextToSpeech), TTS_MAX_BATCH, TTS_MAX_WAIT_MS. TTS_USE_GPU=0 is refused: there is no CPU path here."""
+    them — tts.MultiGpuTextToSpeech; a device may be named twice, "0,0" = two handles on GPU 0, whose launch groups then overlap on the
+    device), TTS_LANES (handles on the one GPU of TTS_DEVICE, dealt launch groups alternately), TTS_MAX_BATCH, TTS_MAX_WAIT_MS.
+    TTS_USE_GPU=0 is refused: there is no CPU path here."""
     global _app
     if _app is None:
         from . import tts as T
@@ -255,7 +257,7 @@ def get_app():
         onnx_dir = os.getenv("TTS_ONNX_DIR", "assets/onnx")
         devs = os.getenv("TTS_DEVICES", "").strip()
         tt = (T.MultiGpuTextToSpeech(onnx_dir, T.parse_devices(devs)) if devs
-              else T.load_text_to_speech(onnx_dir, True, int(os.getenv("TTS_DEVICE", "0"))))
+              else T.load_text_to_speech(onnx_dir, True, int(os.getenv("TTS_DEVICE", "0")), lanes=int(os.getenv("TTS_LANES", "1"))))
         _app = create_app(tt, max_batch=int(os.getenv("TTS_MAX_BATCH", "32")), max_wait_ms=float(os.getenv("TTS_MAX_WAIT_MS", "2")))
     return _app
 
