@@ -110,7 +110,7 @@ private:
 };
 
 // One process, several GPUs of one box: a full weight replica (TextToSpeech engine) + a host thread per device; a request is
-// length-bucketed into launch groups once and the groups are dealt out longest-first (no collective, no inter-GPU traffic).
+// cut into launch groups of equal predicted latent frames once and the groups are dealt out longest-first (no collective, no inter-GPU traffic).
 class MultiGpuTextToSpeech {
 public:
     MultiGpuTextToSpeech(const std::string& onnx_dir, const std::vector<int>& devices);

@@ -1,4 +1,5 @@
-"""Utterance scheduling: length bucketing on one GPU and sharding across the GPUs of a box.
+"""Utterance scheduling: launch groups on one GPU (frame_balanced_groups; length_buckets for padded rectangles) and sharding across
+the GPUs of a box.
 
 Utterances are independent (reference `_infer` couples them only through padding to the batch maximum,
 cpp/helper.cpp:376, 430), so there is no collective on the data path: every GPU holds a full weight replica

@@ -185,14 +185,14 @@ class TextToSpeech:
     def synthesize_many(self, texts, langs, style: Style, total_step: int, speed: float = 1.05,
                         max_batch: int = 128, seed: int = 0, noise: Optional[np.ndarray] = None, copy: bool = False,
                         wait: bool = True, pcm16: bool = False):
-        """Independent utterances -> list of (trimmed wav, duration) in input order. The latent side runs on packed
-        rows (no padded frames); the text side is one [B, T_max] rectangle per group of at most `max_batch`
-        utterances, grouped by token count so text padding stays small. Results do not depend on the grouping
+        """Independent utterances -> list of (trimmed wav, duration) in input order. Both sides run on packed rows (no padded
+        frames or tokens are computed); the request is cut into launch groups of at most `max_batch` utterances and 140 row
+        tiles of predicted latent frames, filled to equal predicted frames (plan_many). Results do not depend on the grouping
         (tests: batch-composition invariance; device noise streams are keyed by the utterance's index in the REQUEST).
         With copy=False the waveforms are views into the engine's page-locked result buffers (one per group, two alternating
         sets): they stay valid until the SECOND-next synthesize_many on this object — copy them (copy=True) to keep them longer.
         Groups are issued asynchronously: the device->host copy of one group overlaps the computation of the next. wait=False
-        returns before the last copies have landed — call `engine.wait()` before reading the waveforms; issuing the next
+        returns before the last copies have landed — call `wait()` before reading the waveforms; issuing the next
         synthesize_many first overlaps its computation with these copies (request streams). pcm16=True: int16 samples quantised
         on the device (writeWavFile's rule), half the device->host bytes."""
         lanes = getattr(self, "lanes", None) or [self.engine]

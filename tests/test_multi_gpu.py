@@ -122,6 +122,41 @@ def test_two_engines_equal_one_engine_per_utterance(full_assets):
 
 
 @pytest.mark.gpu
+def test_request_lanes_give_the_single_handle_result(full_assets):
+    """TextToSpeech(lanes=...): launch groups dealt alternately to two handles on one GPU (consecutive requests then overlap on the
+    device). Same weights, same plan, noise keyed by the index in the request: bit-identical audio, also for a request stream
+    issued with wait=False."""
+    from supertonic_b200 import tts as T
+    texts, langs = _request(40, seed=9)
+    voices = [("M1", "F1", "M2", "F2")[i % 4] for i in range(40)]
+    style = T.load_voice_style([os.path.join(full_assets, "voice_styles", v + ".json") for v in voices])
+    one = T.load_text_to_speech(os.path.join(full_assets, "onnx"), True, 0)
+    two = T.load_text_to_speech(os.path.join(full_assets, "onnx"), True, 0, lanes=2)
+    try:
+        assert len(two.lanes) == 2 and two.lanes[0] is two.engine
+        for k in range(3):          # the first request also settles both planners' frames-per-token estimate
+            want = one.synthesize_many(texts, langs, style, 3, 1.05, max_batch=12, seed=30 + k, copy=True)
+            got = two.synthesize_many(texts, langs, style, 3, 1.05, max_batch=12, seed=30 + k, copy=True)
+        for (w1, d1), (w2, d2) in zip(got, want):
+            assert d1 == d2
+            np.testing.assert_array_equal(w1, w2)
+        assert all(e.launches > 0 for e in two.lanes)          # both handles took launch groups
+        # request stream: three requests in flight over the two lanes, results read after wait()
+        outs = [two.synthesize_many(texts[:10], langs[:10], T.Style(style.ttl[:10], style.dp[:10]), 3, 1.05, max_batch=12, seed=50, wait=False)
+                for _ in range(2)]
+        two.wait()
+        ref = one.synthesize_many(texts[:10], langs[:10], T.Style(style.ttl[:10], style.dp[:10]), 3, 1.05, max_batch=12, seed=50, copy=True)
+        for o in outs:
+            for (w1, d1), (w2, d2) in zip(o, ref):
+                assert d1 == d2
+                np.testing.assert_array_equal(w1, w2)
+    finally:
+        one.engine.close()
+        for e in two.lanes:
+            e.close()
+
+
+@pytest.mark.gpu
 def test_cpp_multi_gpu_many_equals_single_engine(full_assets):
     """supertonic::MultiGpuTextToSpeech::many (csrc/tts_host.cc: std::thread per device) against TextToSpeech::many."""
     import torch
