@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128)
 dwconv_ln_chain_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                        const float* __restrict__ g, const float* __restrict__ beta, Out out,
                        int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = K - 1;
     static_assert(2 * U <= 16, "two statistics per row through a 16-value butterfly");
     extern __shared__ __align__(16) unsigned char chain_smem[];

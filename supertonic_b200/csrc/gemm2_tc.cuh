@@ -206,6 +206,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
         }
+        pdl_trigger_late();                  // (the peer's idle MMA warp releases at once: the leader's release is the pair's)
     } else {
         // ===== epilogue warps 2..17 (both CTAs): TMEM lane quarter = warp % 4, column quarter = (warp-2)/4 =====
         const int q = warp & 3, part = (warp - 2) >> 2;

@@ -352,6 +352,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 __syncwarp();
             }
         }
+        pdl_trigger_late();                  // every MMA of this CTA is issued: its last epilogue is what is left
     } else {
         // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp-2)/4 =====
         const int q = warp & 3, half = (warp - 2) >> 2;

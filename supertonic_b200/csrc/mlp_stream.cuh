@@ -276,6 +276,7 @@ STC_DEVINL void stream_body(const StreamMaps& mp, const StreamParams& p, const i
                 ++u;
             });
         }
+        pdl_trigger_late();                  // every MMA of this CTA (pair) is issued: what is left is the drain and the store of the partials
     } else {
         // ===== epilogue 1, per chunk: P = split(GELU(S + b1)), in place in TMEM =====
         constexpr int PARTS = EPI_WARPS / 4;                                      // column parts per TMEM lane quarter

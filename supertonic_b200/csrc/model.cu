@@ -212,6 +212,7 @@ struct Handle {
     bool mlp_fused(const ConvNeXt& c) const;
     MlpPlan mlp_plan(int tiles, int rows) const;
     void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, const PostOps* post = nullptr);
+    int pdl_mode = 2;                 // env STC_PDL (launch_k): 0 = plain stream-ordered launches (cross-check), 1 / 2 / 3 = release point (kernels.cuh)
     int mlp_pair = -1;                // env STC_MLP_PAIR: 0 = one-CTA stream kernel only (cross-check), default: CTA pairs where the slices allow
     int mlp_force_slices = 0;         // env STC_MLP_SLICES (tools/mlp_sweep.py): hidden slices per row tile instead of the cost model
     bool mlp_unfused = false;         // env STC_MLP=unfused: the C = 256 / H = 1024 blocks as two tcgen05 GEMMs (cross-check)
@@ -254,15 +255,19 @@ struct Handle {
     int* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_off = 0;   // pinned staging for offset arrays
 };
 
-// Every kernel of the library goes out through this (plain stream-ordered launches; inside a stream capture they become graph nodes).
-// Programmatic dependent launch was measured twice on B200 (r1g: 15.2 vs 14.3 ms/step; r2b: 8.61 vs 8.50 ms/step, batch-1 latency
-// 4.76 vs 4.91 ms) — the ~770 programmatic graph edges cost the throughput path more than the overlapped prologues save — and removed.
+// Every kernel of the library goes out through this (stream-ordered launches; inside a stream capture they become graph nodes).
+// env STC_PDL = 1 / 2 / 3: programmatic dependent launch (the kernel may start while its predecessor still runs and waits for it
+// itself, kernels.cuh pdl_wait) with the release point per c_pdl_mode. Measured on B200 with every kernel releasing at its top
+// (mode 1): r1g 15.2 vs 14.3 ms/step, r2b 8.61 vs 8.50 ms/step, batch-1 latency 4.76 vs 4.91 ms.
 template <typename... KArgs, typename... Args>
 static inline void launch_k(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cfg.attrs = nullptr; cfg.numAttrs = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl_mode ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     if (e != cudaSuccess) throw ::stc::StcError(STC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
 }
@@ -1116,7 +1121,7 @@ Seq Handle::packed_seq(const std::vector<int>& lens, int rows_launch, int maxlen
 }
 
 __global__ void scale_off_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int f) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] * f;
 }
@@ -1132,7 +1137,7 @@ Seq Handle::scaled_seq(const Seq& s, int f) {
 // ------------------------------------------------------------------------------------------ graph walkers
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (TO)in[i];
 }
@@ -1472,6 +1477,8 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_ATTN"); hd->force_simt_attn = e && std::string(e) == "simt"; }
         { const char* e = getenv("STC_MLP"); hd->mlp_unfused = e && !strcmp(e, "unfused"); }
         { const char* e = getenv("STC_MLP_PAIR"); if (e && *e) hd->mlp_pair = atoi(e); }
+        { const char* e = getenv("STC_PDL"); if (e && *e) hd->pdl_mode = std::max(0, std::min(3, atoi(e))); }
+        STC_CUDA(cudaMemcpyToSymbol(stc::c_pdl_mode, &hd->pdl_mode, sizeof(int)));
         { const char* e = getenv("STC_MLP_SLICES"); if (e && *e) hd->mlp_force_slices = std::max(0, std::min(16, atoi(e))); }
         { const char* e = getenv("STC_DP"); hd->dp_fused = !(e && !strcmp(e, "unfused")); }
         { const char* e = getenv("STC_VOC"); hd->voc_f16 = !e || !strcmp(e, "f16"); }
@@ -2084,26 +2091,26 @@ int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, con
 
 // ---- debug / tuning: one tcgen05 GEMM of a given shape and launch configuration, timed and checked -----------------
 __global__ void debug_fill_kernel(float* __restrict__ p, size_t n, uint64_t seed, float scale) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float u1 = (stc::mix32(seed + 2 * i) + 1.0f) * (1.0f / 4294967808.0f), u2 = stc::mix32(seed + 2 * i + 1) * (1.0f / 4294967296.0f);
     p[i] = scale * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 __global__ void debug_maxdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i] - b[i]));
     m = stc::warp_max(m);
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));     // non-negative floats order like ints
 }
 __global__ void debug_join_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, size_t n) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
 __global__ void debug_unhalf_kernel(const __half* __restrict__ h, float* __restrict__ out, size_t n) {
-    pdl_trigger(); pdl_wait();
+    pdl_trigger_light(); pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __half2float(h[i]);
 }

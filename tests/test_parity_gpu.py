@@ -344,11 +344,12 @@ def test_fused_mlp_forms_match_two_gemms(rig, pair):
         eng2.close()
 
 
-@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP_PAIR", "0"), ("STC_DW", "tile"), ("STC_DW", "slide"), ("STC_DP", "unfused")])
+@pytest.mark.parametrize("env", [("STC_ATTN", "simt"), ("STC_MLP", "unfused"), ("STC_MLP_PAIR", "0"), ("STC_PDL", "0"), ("STC_DW", "tile"), ("STC_DW", "slide"), ("STC_DP", "unfused")])
 def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
     """STC_ATTN=simt: tcgen05 attention core (attn_tc.cuh: split-bf16 QK^T and PV in TMEM, fp32 softmax) against the CUDA-core
     fp32 core. STC_MLP=unfused: the fused ConvNeXt MLP (mlp_stream.cuh) against pw1 / pw2 as two tcgen05 GEMMs; STC_MLP_PAIR=0: its
-    one-CTA form against CTA pairs. STC_DW=tile / slide:
+    one-CTA form against CTA pairs. STC_PDL=0: plain stream-ordered launches against programmatic dependent launch (must be
+    bit-identical: the same kernels, only their start is earlier). STC_DW=tile / slide:
     the depthwise-conv + LayerNorm kernels against their simpler forms. STC_DP=unfused: the one-kernel-per-block fp64 duration
     predictor against separate conv / GEMM launches. Same weights, text encoder (self + style attention, rotary) and one
     vector-estimator step (length-aware rotary cross-attention with a masked key tail, 50-key style attention, ragged rows incl. a
@@ -377,6 +378,8 @@ def test_fused_tensor_core_kernels_match_their_simple_forms(rig, env):
                      total_step=np.full(n, 5, np.float32), current_step=np.full(n, 3, np.float32))
         ya, yb = rig["eng"].vector_step(**feeds), eng2.vector_step(**feeds)
         assert np.abs(ya - yb).max() <= 5e-5, np.abs(ya - yb).max()
+        if env[0] == "STC_PDL":
+            np.testing.assert_array_equal(a, b); np.testing.assert_array_equal(ya, yb)
     finally:
         eng2.close()
 

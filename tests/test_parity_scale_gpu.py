@@ -101,6 +101,31 @@ def test_other_row_tile_counts_match_the_oracle(rig, n, seed, tiles):
     print(f"B={n}: {frames} frames = {-(-frames // 128)} row tiles, latent max-abs {err:.2e}, worst wav SNR {snr:.1f} dB")
 
 
+def test_programmatic_dependent_launch_changes_no_bit(rig):
+    """Every kernel goes out with programmatic stream serialization (launch_k, STC_PDL): a kernel may start while its predecessor
+    still runs and waits for it itself (griddepcontrol.wait before its first global access). A missing or late wait would be a
+    race between consecutive kernels, so: configs[1] three times with PDL and once on a handle without it — all four results
+    bit-identical (latents, waveforms, durations)."""
+    import os
+    ids, mask, ttl, dp = _bench_batch(rig, 32, 1234)
+    nz = np.random.default_rng(5).standard_normal((32, 144, 420)).astype(np.float32)
+    runs = [rig["eng"].synthesize_packed(ids, mask, ttl, dp, 5, 1.05, noise=nz, want_latent=True) for _ in range(3)]
+    os.environ["STC_PDL"] = "0"
+    try:
+        plain = rig["capi"].Engine(rig["root"] + "/onnx")
+    finally:
+        del os.environ["STC_PDL"]
+    try:
+        runs.append(plain.synthesize_packed(ids, mask, ttl, dp, 5, 1.05, noise=nz, want_latent=True))
+    finally:
+        plain.close()
+    for r in runs[1:]:
+        np.testing.assert_array_equal(r["duration"], runs[0]["duration"])
+        for b in range(32):
+            np.testing.assert_array_equal(r["latent"][b], runs[0]["latent"][b])
+            np.testing.assert_array_equal(r["wavs"][b], runs[0]["wavs"][b])
+
+
 def test_vocoder_at_two_sm_gemm_scale(rig):
     """stc_vocode on 16 x 200 latent frames = 19 200 vocoder rows: both pointwise projections of every block take the two-SM
     (cta_group::2) fp16 GEMM and the depthwise conv its shared-memory ring; also in the split-bf16 mode (>= 80 dB)."""
