@@ -68,7 +68,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
                     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
                     const Params p) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     using namespace tc;
     using L = Lay<MAXB>;
     constexpr int OFF_V = L::OFF_V, OFF_BAR = L::OFF_BAR, TMEM_COLS = L::TMEM_COLS, O_COL = L::O_COL, MAX_BLOCKS = MAXB;
@@ -260,7 +260,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 __global__ void __launch_bounds__(256)
 v_prep_kernel(const float* __restrict__ v, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
               const int* __restrict__ koff, int heads, int ldk) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     __shared__ float tile[KB][DH + 1];
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * KB;
     const int kbase = __ldg(koff + b), Nk = __ldg(koff + b + 1) - kbase;

@@ -40,7 +40,7 @@ struct DpTile {
 template <int C, int H>
 __global__ void __launch_bounds__(256)
 dp_convnext_kernel(const DpBlockParams p) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     using TL = DpTile<C, H>;
     constexpr int R = TL::R;
     extern __shared__ __align__(16) unsigned char dp_smem[];

@@ -32,7 +32,6 @@ __global__ void __launch_bounds__(128)
 dwconv_ln_chain_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                        const float* __restrict__ g, const float* __restrict__ beta, Out out,
                        int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
-    pdl_trigger_light(); pdl_wait();
     constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = K - 1;
     static_assert(2 * U <= 16, "two statistics per row through a 16-value butterfly");
     extern __shared__ __align__(16) unsigned char chain_smem[];
@@ -65,6 +64,10 @@ dwconv_ln_chain_kernel(const float* __restrict__ x, const float* __restrict__ wT
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // (weights and the sequence lookup above do not depend on the predecessor kernel: they overlap its tail, kernels.cuh pre-wait rules)
+    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
+    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+    pdl_wait(); pdl_trigger_light();
 #pragma unroll
     for (int it = 0; it < CHAIN_RD; ++it) fetch(it);
     float4 win[U], cur[U];
@@ -73,8 +76,6 @@ dwconv_ln_chain_kernel(const float* __restrict__ x, const float* __restrict__ wT
         const int r = rw0 + j * dil;
         win[j] = (r >= 0 && r < rows) ? *reinterpret_cast<const float4*>(xc + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
-    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
     const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
     const float inv_c = 1.0f / (float)C;
 

@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const Params p) {
-    pdl_trigger();                      // the successor may launch; it waits for this grid's completion itself
     using T = Tile<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024-B alignment

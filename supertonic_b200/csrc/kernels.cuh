@@ -15,14 +15,17 @@ namespace stc {
 
 #define STC_DEVINL __device__ __forceinline__
 
-// Programmatic dependent launch (env STC_PDL, model.cu launch_k): with the launch attribute set a kernel may start while its predecessor
-// still runs; pdl_wait() (first statement that matters in every kernel, before any global access) blocks until the predecessor grid
-// has completed and its writes are visible. Without the attribute both instructions are no-ops.
-// c_pdl_mode: 1 = every kernel releases its dependents at the top (pdl_trigger), 2 = the tensor-core kernels release them late, when a
-// CTA has issued its last MMA (pdl_trigger_late), the light kernels at the top, 3 = nobody releases early (implicit at CTA exit).
+// Programmatic dependent launch (env STC_PDL, model.cu launch_k): with the launch attribute set a kernel may START while its
+// predecessor still runs; pdl_wait() blocks until the predecessor grid has completed and its writes are visible. Without the
+// attribute both instructions are no-ops. The rules every kernel of the library follows:
+//   * nothing a predecessor may still be writing is read, and nothing it may still be reading is written, before pdl_wait();
+//   * a kernel releases its dependents only AFTER its own pdl_wait() — light kernels right after it (pdl_trigger_light), the
+//     tensor-core kernels when a CTA has issued its last MMA (pdl_trigger_late) — so while kernel n runs its pre-wait code, kernel
+//     n-1 has passed its wait, i.e. kernel n-2 and everything before it are complete;
+//   * hence pre-wait code may read what was produced at least TWO kernels earlier (weights, sequence offsets), never activations.
+// c_pdl_mode: 2 = as described (default), 3 = nobody releases early (dependents start when the last CTA exits).
 __constant__ int c_pdl_mode;
-STC_DEVINL void pdl_trigger() { if (c_pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-STC_DEVINL void pdl_trigger_light() { if (c_pdl_mode == 1 || c_pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+STC_DEVINL void pdl_trigger_light() { if (c_pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 STC_DEVINL void pdl_trigger_late() { if (c_pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 STC_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -102,7 +105,7 @@ template <typename T>
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
                              const float* __restrict__ mask, T* __restrict__ out, int rows, int C, int V,
                              const int* __restrict__ off, int B, int Tn) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int row = blockIdx.x * blockDim.y + threadIdx.y;
     if (row >= rows) return;
     const int b = find_seq(off, B, row);
@@ -120,7 +123,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
 template <typename T>
 __global__ void add_rowvec_mask_kernel(T* __restrict__ x, const T* __restrict__ v, const float* __restrict__ mask,
                                        int rows, int C, int vstride, const int* __restrict__ off, int B) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     // vstride = C: one vector per sequence (row -> b through the packed offsets); vstride = 0: one vector for every row
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * C) return;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ wb,
                  const float* __restrict__ g, const float* __restrict__ beta, Out out,
                  int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int C = CPL * 32;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_vec_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                      const float* __restrict__ g, const float* __restrict__ beta, Out out,
                      int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int C = CPL * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                       const float* __restrict__ g, const float* __restrict__ beta, Out out,
                       int rows, const int* __restrict__ off, int B, int K, int dil, int pad_left, float eps, int R) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int C = CPL * 32, V = CPL / 4;
     extern __shared__ float4 tile4[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,7 +427,6 @@ __global__ void __launch_bounds__(128)
 dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ wb,
                        const float* __restrict__ g, const float* __restrict__ beta, Out out,
                        int rows, const int* __restrict__ off, int B, int dil, int pad_left, float eps, int RT) {
-    pdl_trigger_light(); pdl_wait();
     constexpr int C = 128 * NW, GT = 32 * NW, GPB = 4 / NW, U = 4;
     __shared__ __align__(16) float red[2][GPB][U][NW];
     const int grp = threadIdx.x / GT, t = threadIdx.x % GT, wig = t >> 5, lane = threadIdx.x & 31;
@@ -460,6 +462,11 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // tap weights, LayerNorm parameters and the sequence lookup (a binary search: five dependent L2 round trips) do not depend on the
+    // predecessor kernel: under programmatic dependent launch they overlap its tail (kernels.cuh: pre-wait rules)
+    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
+    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
+    pdl_wait(); pdl_trigger_light();
     if constexpr (RING) {
 #pragma unroll
         for (int it = 0; it < RING_D; ++it) fetch(it);
@@ -470,8 +477,6 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
 #pragma unroll
         for (int u = 0; u < U; ++u) nxt[u] = load_row(rw0 + (K - 1 + u) * dil);
     }
-    int b = find_seq(off, B, r_first), lo = 0x7fffffff, hi = 0x7fffffff;
-    if (b >= 0) { lo = __ldg(off + b); hi = __ldg(off + b + 1); }
     for (int i0 = 0; i0 < RT; i0 += U) {
         if (r_first + i0 * dil >= rows) break;         // uniform in the group
         if constexpr (RING) {
@@ -554,7 +559,7 @@ dwconv_ln_slide_kernel(const float* __restrict__ x, const float* __restrict__ wT
 // ---- elementwise copy into operand format (split bf16 or plain) ----------------------------------
 template <typename Out>
 __global__ void convert_kernel(const float* __restrict__ x, Out out, size_t n) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out.store(i, x[i]);
 }
@@ -580,7 +585,7 @@ template <typename T, typename Out, int BM = 64>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, Out out, int ldo,
                  int M, int N, int K, Epilogue ep) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int BN = 64, BK = 16, TM = BM / 16;
     __shared__ T As[BK][BM + 1];
     __shared__ T Ws[BK][BN + 1];
@@ -636,7 +641,7 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const float* __restrict__ W, 
 
 // ---- sequence lengths from masks: len[b] = sum_n mask[b,n] ---------------------------------------
 __global__ void mask_len_kernel(const float* __restrict__ mask, float* __restrict__ len, int* __restrict__ cnt, int N) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     // len[b] = sum of the mask (what the graphs' ReduceSum sees); cnt[b] = 1 + index of the last non-zero entry
     int b = blockIdx.x;
     float s = 0.f; int last = 0;
@@ -654,7 +659,7 @@ __global__ void mask_len_kernel(const float* __restrict__ mask, float* __restric
 // CUDA-core path's form of the same thing. pos = n (abs) or n / len[b] (length-aware RoPE); ang = pos * freqs[i].
 __global__ void rope_kernel(float* __restrict__ x, const float* __restrict__ freqs, const float* __restrict__ len,
                             int rows, const int* __restrict__ off, int B, int heads, int DH, int normalise) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int half = DH / 2;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)rows * heads * half;
@@ -681,7 +686,7 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, const float* __restrict__ Vt,
                  const float* __restrict__ kmask, Out out, const int* __restrict__ qoff, const int* __restrict__ koff,
                  const int* __restrict__ kcnt, int heads, float scale) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int QPW = 4, WARPS = 4, QT = QPW * WARPS, KC = 32, DPL = DH / 32;
     __shared__ float Ks[KC][DH + 1];
     __shared__ float Vs[KC][DH + 1];
@@ -757,7 +762,7 @@ attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kt, cons
 // NCL [B,C,N] -> NLC [B,N,C] (and back), 32x32 shared-memory tile transpose
 template <typename TI, typename TO>
 __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int Cc) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     // in: [batch][R][Cc] -> out: [batch][Cc][R]
     __shared__ float tile[32][33];
     int b = blockIdx.z;
@@ -784,7 +789,7 @@ STC_DEVINL uint32_t mix32(uint64_t z) {
 __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, const uint64_t* __restrict__ seed_p,
                                    const float* __restrict__ mask, float* __restrict__ x, int rows,
                                    const int* __restrict__ off, int B, int D, const int* __restrict__ noise_index) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * D) return;
     int d = (int)(i % D);
@@ -807,7 +812,7 @@ __global__ void init_latent_kernel(const float* __restrict__ noise, int64_t ld, 
 
 // latent mask from wav lengths: mask[b,l] = l < ceil(wav_len[b]/cs)  (getLatentMask, cpp/helper.cpp:759-770)
 __global__ void latent_mask_kernel(const int64_t* __restrict__ wav_len, float* __restrict__ mask, int B, int L, int cs) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     int b = i / L, l = i % L;
@@ -822,7 +827,7 @@ template <typename Out>
 __global__ void voc_im2col_kernel(const float* __restrict__ lat, const float* __restrict__ sd,
                                   const float* __restrict__ mean, Out out, int rows6, const int* __restrict__ off,
                                   int B, int f, int ld, int K, int lda) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     // off = LATENT-frame offsets; output rows run at f x the latent rate: row6 in [f*off[b], f*off[b+1])
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int KW = K * ld;
@@ -852,7 +857,7 @@ template <int CPL>
 __global__ void dp_head_kernel(const double* __restrict__ x, const float* __restrict__ g, const float* __restrict__ beta,
                                const float* __restrict__ w, const float* __restrict__ wb, const float* __restrict__ mask,
                                float* __restrict__ dur, const int* __restrict__ off, float eps, float clip, float spt) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     constexpr int C = CPL * 32;
     __shared__ double part[32];
     int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -884,7 +889,7 @@ __global__ void dp_head_kernel(const double* __restrict__ x, const float* __rest
 
 // duration /= speed; wav_len = (int64)(d*sr)   (cpp/helper.cpp:529-531, 434) — float32 IEEE, no fast-math
 __global__ void dur_post_kernel(float* __restrict__ dur, int64_t* __restrict__ wav_len, int B, float speed, int sr) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float d = __fdiv_rn(dur[b], speed);
@@ -908,7 +913,7 @@ template <> STC_DEVINL int16_t wav_out_of<int16_t>(float v) { return pcm16_of(v)
 template <typename TO>
 __global__ void __launch_bounds__(256)
 wav_pack_kernel(const float* __restrict__ src, TO* __restrict__ dst, const int* __restrict__ off, int B, int cs, long long gap) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     const int r = blockIdx.x;
     const int b = find_seq(off, B, r);
     if (b < 0) return;                                         // bucket padding frame
@@ -937,7 +942,7 @@ wav_pack_kernel(const float* __restrict__ src, TO* __restrict__ dst, const int* 
 // sinusoidal time embedding: t = cur/tot; out[b] = [sin(t*f), cos(t*f)]
 __global__ void time_embed_kernel(const float* __restrict__ cur, const float* __restrict__ tot,
                                   const float* __restrict__ freqs, float* __restrict__ out, int B, int half) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     int b = i / half, j = i % half;
@@ -949,7 +954,7 @@ __global__ void time_embed_kernel(const float* __restrict__ cur, const float* __
 
 // copy rows [B][L*cs] out of a wider device matrix into a strided destination
 __global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }

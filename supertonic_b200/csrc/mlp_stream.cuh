@@ -373,7 +373,6 @@ convnext_mlp_stream_kernel(const __grid_constant__ CUtensorMap map_a_hi, const _
                            const __grid_constant__ CUtensorMap map_w1_hi64, const __grid_constant__ CUtensorMap map_w1_lo64,
                            const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                            const __grid_constant__ CUtensorMap map_part, const StreamParams p) {
-    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const StreamMaps mp{&map_a_hi, &map_a_lo, &map_w1_hi, &map_w1_lo, &map_w1_hi64, &map_w1_lo64, &map_w2_hi, &map_w2_lo, &map_part};
     stream_body<false>(mp, p, (int)(blockIdx.x / p.nslice), (int)(blockIdx.x % p.nslice), 0, smem_raw);
@@ -388,7 +387,6 @@ convnext_mlp_stream2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const 
                             const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                             const __grid_constant__ CUtensorMap map_w2_hi64, const __grid_constant__ CUtensorMap map_w2_lo64,
                             const __grid_constant__ CUtensorMap map_part, const StreamParams p) {
-    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const int cl = (int)tc::cluster_id_x(), rank = (int)tc::cluster_ctarank(), npc = p.npairs * p.nslice;
     if (cl < npc) {

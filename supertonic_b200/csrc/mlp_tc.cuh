@@ -61,7 +61,7 @@ mlp_reduce_post_kernel(const float* __restrict__ partial, size_t slice, const fl
                   const float* __restrict__ mask, float* __restrict__ x, int M, const float* __restrict__ add_vec,
                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int nslice) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= M) return;
@@ -137,7 +137,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(256)
 mlp_reduce_kernel(const float* __restrict__ partial, size_t slice, const float* __restrict__ b2, const float* __restrict__ gamma,
                   const float* __restrict__ mask, float* __restrict__ x, int M, int nslice) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= (size_t)M * C) return;
     const int row = (int)(i / C), col = (int)(i % C);

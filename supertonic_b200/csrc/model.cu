@@ -212,7 +212,7 @@ struct Handle {
     bool mlp_fused(const ConvNeXt& c) const;
     MlpPlan mlp_plan(int tiles, int rows) const;
     void fused_mlp(const Act& a, int rows, const ConvNeXt& c, float* x, const float* mask, const PostOps* post = nullptr);
-    int pdl_mode = 2;                 // env STC_PDL (launch_k): 0 = plain stream-ordered launches (cross-check), 1 / 2 / 3 = release point (kernels.cuh)
+    int pdl_mode = 2;                 // env STC_PDL (launch_k): 0 = plain stream-ordered launches (cross-check), 2 / 3 = release point (kernels.cuh)
     int mlp_pair = -1;                // env STC_MLP_PAIR: 0 = one-CTA stream kernel only (cross-check), default: CTA pairs where the slices allow
     int mlp_force_slices = 0;         // env STC_MLP_SLICES (tools/mlp_sweep.py): hidden slices per row tile instead of the cost model
     bool mlp_unfused = false;         // env STC_MLP=unfused: the C = 256 / H = 1024 blocks as two tcgen05 GEMMs (cross-check)
@@ -256,9 +256,11 @@ struct Handle {
 };
 
 // Every kernel of the library goes out through this (stream-ordered launches; inside a stream capture they become graph nodes).
-// env STC_PDL = 1 / 2 / 3: programmatic dependent launch (the kernel may start while its predecessor still runs and waits for it
-// itself, kernels.cuh pdl_wait) with the release point per c_pdl_mode. Measured on B200 with every kernel releasing at its top
-// (mode 1): r1g 15.2 vs 14.3 ms/step, r2b 8.61 vs 8.50 ms/step, batch-1 latency 4.76 vs 4.91 ms.
+// Programmatic dependent launch (default; env STC_PDL=0 for plain launches, 3 for no early release): the kernel may start while its
+// predecessor still runs and waits for it itself (kernels.cuh: pdl_wait and the pre-wait rules). With every kernel releasing its
+// dependents at its very top this lost twice (r1g 15.2 vs 14.3 ms/step, r2b 8.61 vs 8.50); releasing after the kernel's own wait —
+// late in the tensor-core kernels — wins: end-to-end request stream 40.7 k -> 44.5 k audio-s/s, batch-1 p50 4.64 -> 4.2 ms
+// (profiles/r2y_pdl_modes.txt).
 template <typename... KArgs, typename... Args>
 static inline void launch_k(stc::Handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args&&... args) {
@@ -1121,7 +1123,7 @@ Seq Handle::packed_seq(const std::vector<int>& lens, int rows_launch, int maxlen
 }
 
 __global__ void scale_off_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int f) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] * f;
 }
@@ -1137,7 +1139,7 @@ Seq Handle::scaled_seq(const Seq& s, int f) {
 // ------------------------------------------------------------------------------------------ graph walkers
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (TO)in[i];
 }
@@ -2091,26 +2093,26 @@ int stc_synthesize_packed_device(stc_handle* h, const int64_t* text_ids_dev, con
 
 // ---- debug / tuning: one tcgen05 GEMM of a given shape and launch configuration, timed and checked -----------------
 __global__ void debug_fill_kernel(float* __restrict__ p, size_t n, uint64_t seed, float scale) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float u1 = (stc::mix32(seed + 2 * i) + 1.0f) * (1.0f / 4294967808.0f), u2 = stc::mix32(seed + 2 * i + 1) * (1.0f / 4294967296.0f);
     p[i] = scale * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 __global__ void debug_maxdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i] - b[i]));
     m = stc::warp_max(m);
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));     // non-negative floats order like ints
 }
 __global__ void debug_join_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, size_t n) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
 __global__ void debug_unhalf_kernel(const __half* __restrict__ h, float* __restrict__ out, size_t n) {
-    pdl_trigger_light(); pdl_wait();
+    pdl_wait(); pdl_trigger_light();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __half2float(h[i]);
 }
