@@ -1572,6 +1572,7 @@ int stc_kernel_variants(const stc_handle* h, char* buf, size_t cap, size_t* need
     if (!h || !h->impl || !need) return STC_ERR_INVALID;
     std::string s;
     for (const auto& kv : h->impl->variant_count) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+    s += "graph_captures=" + std::to_string(h->impl->graph_captures) + "\ngraph_replays=" + std::to_string(h->impl->graph_replays) + "\n";
     *need = s.size() + 1;
     if (!buf || cap < s.size() + 1) return STC_ERR_CAPACITY;
     memcpy(buf, s.c_str(), s.size() + 1);

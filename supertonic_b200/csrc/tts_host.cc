@@ -187,22 +187,24 @@ TextToSpeech::ManyPlan TextToSpeech::planMany(const std::vector<std::string>& te
     for (int i = 0; i < n; ++i) p.tok[i] = (int)std::accumulate(p.mask.begin() + (size_t)i * p.T, p.mask.begin() + (size_t)(i + 1) * p.T, 0.f);
     if (n == 0) return p;
     max_batch = std::max(1, max_batch);
-    const double fpt = frames_per_token_.load(), max_rows = 140.0 * 128.0;
-    std::vector<double> est(n);
-    double total = 0;
-    for (int i = 0; i < n; ++i) { est[i] = std::max(1.0, p.tok[i] * fpt); total += est[i]; }
-    const int ng = std::min(n, std::max((n + max_batch - 1) / max_batch, (int)std::ceil(total / max_rows)));
+    // the groups are balanced on the integer token counts (predicted frames are proportional to them), so the same request always gives
+    // the same groups — and hits the same CUDA graphs — however the measured ratio jitters; the ratio, rounded up to a multiple of
+    // 1/16, only decides how many groups there are
+    const double fpt = std::ceil(std::max(frames_per_token_.load(), 1e-3) * 16.0) / 16.0, max_rows = 140.0 * 128.0;
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) total += std::max(1, p.tok[i]);
+    const int ng = std::min(n, std::max((n + max_batch - 1) / max_batch, (int)std::ceil((double)total * fpt / max_rows)));
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return est[a] > est[b]; });
-    std::vector<double> load(ng, 0.0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.tok[a] > p.tok[b]; });
+    std::vector<int64_t> load(ng, 0);
     p.groups.assign(ng, {});
     for (int i : order) {
         int g = -1;
         for (int k = 0; k < ng; ++k)
             if ((int)p.groups[k].size() < max_batch && (g < 0 || load[k] < load[g])) g = k;
         p.groups[g].push_back(i);
-        load[g] += est[i];
+        load[g] += std::max(1, p.tok[i]);
     }
     for (auto& g : p.groups) std::sort(g.begin(), g.end());
     p.groups.erase(std::remove_if(p.groups.begin(), p.groups.end(), [](const std::vector<int>& g) { return g.empty(); }), p.groups.end());

@@ -45,14 +45,18 @@ def frame_balanced_groups(lengths: Sequence[int], max_batch: int = 128, frames_p
     n = len(lengths)
     if n == 0:
         return []
-    est = np.maximum(np.asarray(lengths, dtype=np.float64) * float(frames_per_token), 1.0)
-    n_groups = min(n, max(-(-n // max(1, int(max_batch))), int(np.ceil(est.sum() / max(1, int(max_rows))))))
-    load = [0.0] * n_groups
+    # The groups themselves are balanced on the integer token counts (predicted frames are proportional to them), so the same
+    # request always gives the same groups — and hits the same CUDA graphs — however the measured ratio jitters between calls; the
+    # ratio, rounded up to a multiple of 1/16, only decides how many groups there are.
+    tok = np.maximum(np.asarray(lengths, dtype=np.int64), 1)
+    fpt = np.ceil(max(float(frames_per_token), 1e-3) * 16.0) / 16.0
+    n_groups = min(n, max(-(-n // max(1, int(max_batch))), int(np.ceil(float(tok.sum()) * fpt / max(1, int(max_rows))))))
+    load = [0] * n_groups
     groups: List[List[int]] = [[] for _ in range(n_groups)]
-    for i in sorted(range(n), key=lambda k: (-est[k], k)):
+    for i in sorted(range(n), key=lambda k: (-int(tok[k]), k)):
         g = min((k for k in range(n_groups) if len(groups[k]) < max_batch), key=lambda k: (load[k], k))
         groups[g].append(i)
-        load[g] += est[i]
+        load[g] += int(tok[i])
     return [sorted(g) for g in groups if g]
 
 

@@ -122,6 +122,29 @@ def test_two_engines_equal_one_engine_per_utterance(full_assets):
 
 
 @pytest.mark.gpu
+def test_a_repeated_request_replays_its_cuda_graphs(full_assets):
+    """The launch groups of a request must not depend on the frames-per-token ratio the engines measured on the previous call
+    (each engine of a multi-device object sees other groups, so its ratio jitters): the groups are balanced on integer token
+    counts. A third identical request captures no new CUDA graph on any engine — a re-capture costs ~100 ms and is serialised
+    across the engines of a process (8 devices: 6 k instead of 200 k audio-s/s when the plan was unstable)."""
+    from supertonic_b200 import tts as T
+    texts, langs = _request(96, seed=4)
+    voices = [("M1", "F1", "M2", "F2")[i % 4] for i in range(96)]
+    style = T.load_voice_style([os.path.join(full_assets, "voice_styles", v + ".json") for v in voices])
+    multi = T.MultiGpuTextToSpeech(os.path.join(full_assets, "onnx"), [0, 0, 0])
+    try:
+        for k in range(2):
+            multi.synthesize_many(texts, langs, style, 2, 1.05, max_batch=16, seed=k)
+        caps = [e.kernel_variants()["graph_captures"] for e in multi.engines]
+        plan = T.plan_many(multi.engine, texts, langs, 16)
+        multi.synthesize_many(texts, langs, style, 2, 1.05, max_batch=16, seed=7)
+        assert [e.kernel_variants()["graph_captures"] for e in multi.engines] == caps
+        assert T.plan_many(multi.engine, texts, langs, 16).groups == plan.groups
+    finally:
+        multi.close()
+
+
+@pytest.mark.gpu
 def test_request_lanes_give_the_single_handle_result(full_assets):
     """TextToSpeech(lanes=...): launch groups dealt alternately to two handles on one GPU (consecutive requests then overlap on the
     device). Same weights, same plan, noise keyed by the index in the request: bit-identical audio, also for a request stream
