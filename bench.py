@@ -346,7 +346,7 @@ def main():
         e2e["pcm16"] = {"value": float(te[0].item()) / (float(t16[0].item()) / steps), "unit": "audio-s/s", "d2h_bytes_per_step": d2h // 2,
                         "ms_per_step": 1000 * float(t16[0].item()) / steps, "window": "one window of `steps` steps"}
         return dict(value=audio_all / (ms_per_step / 1000), ms_per_step=ms_per_step, audio=audio, audio_all=audio_all, launches=int(launches),
-                    clocks=clk, per_rank=per_rank, e2e=e2e, p50_step_ms=float(np.median(step_ms)), buckets=buckets, style=style,
+                    clocks=clk, per_rank=per_rank, e2e=e2e, p50_step_ms=float(np.median(step_ms)), step_ms=[float(v) for v in step_ms], buckets=buckets, style=style,
                     ids=ids, mask=mask, lens=lens)
 
     if a.workload == "sweep1024":
@@ -587,7 +587,7 @@ def main():
                                                audio_s_per_step_per_gpu=audio),
            "clocks": clocks, "e2e": main["e2e"],
            "gpu_launches": int(launches), "parity_check": pcheck, "per_rank": per_rank, "latency": lat, "strong": strong, "vary_batches": vary, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
-           "p50_step_ms": main["p50_step_ms"]}
+           "p50_step_ms": main["p50_step_ms"], "step_ms": main["step_ms"]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
