@@ -14,25 +14,27 @@
 //     O[128 x 256] += P_c[128 x w] . W2[:, chunk c]^T               (TMEM columns 256..511; A operand read from TMEM)
 //
 // The MMA warp issues S_{c+1} before O_c, so the GELU of chunk c runs under the MMAs of S_{c+1} and the tensor pipe never waits for
-// the epilogue warps in steady state. The host picks nslice = floor(SMs / row tiles) (clamped to 1..16): 37 tiles -> 4 slices of 256
-// units (148 CTAs), 38..49 tiles -> 3 slices of 320/320/384 in ONE wave (the 256-unit form took two waves there: 20 -> 35 us per
-// block), 50..74 -> 2, >= 75 tiles -> 1 slice = the whole hidden layer per CTA (four times fewer CTAs than before), <= 9 tiles ->
-// 16 slices of 64 (the batch-1 latency path). Every CTA writes its partial O (fp32, by TMA) into slot `slice` of the scratch
-// tensor; mlp_reduce_kernel / mlp_reduce_post_kernel add the slots in slice order (deterministic) and apply b2 / layer-scale /
-// residual / mask (+ what follows the block in the graph).
+// the epilogue warps in steady state. The host picks the plan (model.cu mlp_plan: slices per tile, single CTAs or pairs, from a
+// cost model fitted to tools/mlp_sweep.py): <= 9 tiles -> 16 slices of 64 units (the batch-1 latency path), 19..37 -> 4 slices
+// (148 CTAs at 37 tiles), 38..49 -> 3 slices in ONE wave (the 256-unit form took two waves there: 20 -> 35 us per block),
+// 50..74 -> 2, >= 75 tiles -> 1 slice = the whole hidden layer per CTA (pair). Every CTA writes its partial O (fp32, by TMA) into
+// slot `slice` of the scratch tensor; mlp_reduce_kernel / mlp_reduce_post_kernel add the slots in slice order (deterministic) and
+// apply b2 / layer-scale / residual / mask (+ what follows the block in the graph).
 //
 // Warps: 0 = TMA producer (a-tile K blocks interleaved with the first weight units, then weight units of 128 (64) rows x 64 K,
 // hi + lo, through a 3-slot ring), 1 = MMA issuer, 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 // The last chunk's O units run output-half-major, so the first 128 output columns are final (and are being stored) while the
 // tensor pipe still accumulates the other 128.
 //
-// PAIR form (convnext_mlp_stream2_kernel, cta_group::2): the kernel above is paced by bytes delivered into each SM (640 KB per CTA at 37
-// tiles x 4 slices: 128 KB of `a` + 512 KB of weights, 95 MB per launch against TMA's ~6 300 B/clk chip-wide). Two row tiles that share
-// a hidden slice run as a CTA pair with ONE instruction stream (M = 256 MMAs issued by the leader): each CTA keeps its own `a` tile, its
-// own S / P / O in its own TMEM, and only HALF of every weight unit (64 of the 128 weight rows) — 384 KB per CTA. The pair's barriers:
-// TMA of both CTAs completes on the leader's full barriers, tcgen05.commit multicasts to both CTAs, the peer's epilogue warps
-// arrive remotely on the leader's P barriers. An odd last row tile runs the one-CTA form inside the same launch (its cluster's two
-// CTAs take two of its hidden slices), so 37 tiles x 4 slices is still 148 CTAs in one wave.
+// PAIR form (convnext_mlp_stream2_kernel, cta_group::2): the one-CTA form is paced by the shared-memory port (an S unit of 12 MMAs
+// reads 96 KB of operands while TMA fills 32 KB: 1 000 cycles for 768 cycles of MMAs) and pulls 640 KB into each SM per block at
+// 4 slices. Two row tiles that share a hidden slice run as a CTA pair with ONE instruction stream (M = 256 MMAs issued by the leader):
+// each CTA keeps its own `a` tile, its own S / P / O in its own TMEM, and only HALF of every weight unit (64 of the 128 weight rows,
+// 6-slot ring of 16 KB) — 384 KB per CTA, ~795 cycles per unit. The pair's barriers: TMA of both CTAs completes on the leader's full
+// barriers, tcgen05.commit multicasts to both CTAs, the peer's epilogue warps arrive remotely on the leader's P barriers. An odd last
+// row tile runs the one-CTA form inside the same launch (its cluster's two CTAs take two of its hidden slices), so 37 tiles x 4 slices
+// is still 148 CTAs in one wave; where it does not add a wave it is padded to a pair instead (the phantom CTA computes on zero rows
+// and stores nothing).
 #pragma once
 #include "mlp_tc.cuh"
 #include "gemm2_tc.cuh"
