@@ -68,7 +68,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
                     const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
                     const Params p) {
-    pdl_wait(); pdl_trigger_light();
+    // (pre-wait, kernels.cuh: the sequence offsets, the K and V^T blocks were produced at least two kernels ago — the K / V projections
+    // come before the Q projection, hoisted ones long before — so set-up and the K / V loads overlap the Q projection's tail)
     using namespace tc;
     using L = Lay<MAXB>;
     constexpr int OFF_V = L::OFF_V, OFF_BAR = L::OFF_BAR, TMEM_COLS = L::TMEM_COLS, O_COL = L::O_COL, MAX_BLOCKS = MAXB;
@@ -107,8 +108,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     if (warp == 0) {
         if (elect_one()) {
             mbar_expect_tx(bar_qk, 2 * Q_BYTES + 2 * nblk * KBLK_BYTES);
-            tma_load_2d(smem_base + OFF_Q, &map_q_hi, bar_qk, h * DH, qbase + q0);
-            tma_load_2d(smem_base + OFF_Q + Q_BYTES, &map_q_lo, bar_qk, h * DH, qbase + q0);
             for (int j = 0; j < nblk; ++j) {
                 tma_load_2d(smem_base + OFF_K + j * KBLK_BYTES, &map_k_hi, bar_qk, h * DH, kbase + j * KB);
                 tma_load_2d(smem_base + OFF_K + (MAX_BLOCKS + j) * KBLK_BYTES, &map_k_lo, bar_qk, h * DH, kbase + j * KB);
@@ -119,8 +118,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 tma_load_2d(smem_base + OFF_V + j * KBLK_BYTES, &map_v_hi, bar_v, j * KB, vrow);
                 tma_load_2d(smem_base + OFF_V + (MAX_BLOCKS + j) * KBLK_BYTES, &map_v_lo, bar_v, j * KB, vrow);
             }
+            pdl_wait();                                       // Q is the predecessor's output
+            tma_load_2d(smem_base + OFF_Q, &map_q_hi, bar_qk, h * DH, qbase + q0);
+            tma_load_2d(smem_base + OFF_Q + Q_BYTES, &map_q_lo, bar_qk, h * DH, qbase + q0);
         }
+        __syncwarp();
+        pdl_wait(); pdl_trigger_light();
     } else if (warp == 1) {
+        pdl_wait(); pdl_trigger_light();
         constexpr uint32_t idesc = make_idesc_bf16(BQ, KB);           // M = 128, N = 64 for both products
         mbar_wait(bar_qk, 0);
         tc_fence_after();
@@ -166,6 +171,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
     } else {
         // ===== softmax warps 2..5: query row r = 32 * (warp % 4) + lane =====
+        pdl_wait(); pdl_trigger_light();
         const int quarter = warp & 3, r = quarter * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         mbar_wait(bar_s, 0);
