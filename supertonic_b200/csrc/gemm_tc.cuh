@@ -272,41 +272,57 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    pdl_wait();                                 // prologue above overlapped the predecessor; its writes are visible from here
 
     if (warp == 0) {
         // ===== TMA producer =====
+        // Under programmatic dependent launch (kernels.cuh) the W halves of the first STAGES stages are requested BEFORE the dependency
+        // wait — weights do not depend on the predecessor — so only the A halves are outstanding when it returns.
         if (elect_one()) {
-            uint32_t kbc = 0;
-            for (int ct = ct0; ct < num_ct; ct += ct_step) {
+            auto load = [&](int ct, int kb, uint32_t kbc, bool first_pass, bool w_part, bool a_part) {
                 const int m0 = (ct / n_tiles) * BM, n0 = (ct % n_tiles) * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
-                    const int s = kbc % T::STAGES;
-                    const uint32_t ph = (kbc / T::STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1);
-                    const uint32_t st = smem_base + s * T::STAGE_BYTES;
-                    if constexpr (kF16) {
-                        const int k0 = kb * KSTAGE;
-                        const bool two = k0 + BK < p.K;
+                const int s = kbc % T::STAGES;
+                const uint32_t st = smem_base + s * T::STAGE_BYTES;
+                if (!first_pass) mbar_wait(empty_bar(s), ((kbc / T::STAGES) & 1) ^ 1);
+                if constexpr (kF16) {
+                    const int k0 = kb * KSTAGE;
+                    const bool two = k0 + BK < p.K;
+                    if (w_part) {
                         mbar_expect_tx(full_bar(s), two ? T::STAGE_BYTES : T::STAGE_BYTES / 2);
-                        tma_load_2d(st, &map_a_hi, full_bar(s), k0, m0);
                         tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), k0, n0);
-                        if (two) {
-                            tma_load_2d(st + T::A_BYTES, &map_a_hi, full_bar(s), k0 + BK, m0);
-                            tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_hi, full_bar(s), k0 + BK, n0);
-                        }
-                        continue;
+                        if (two) tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_hi, full_bar(s), k0 + BK, n0);
                     }
-                    mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
-                    tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
-                    tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+                    if (a_part) {
+                        tma_load_2d(st, &map_a_hi, full_bar(s), k0, m0);
+                        if (two) tma_load_2d(st + T::A_BYTES, &map_a_hi, full_bar(s), k0 + BK, m0);
+                    }
+                } else {
+                    if (w_part) {
+                        mbar_expect_tx(full_bar(s), T::STAGE_BYTES);
+                        tma_load_2d(st + 2 * T::A_BYTES, &map_w_hi, full_bar(s), kb * BK, n0);
+                        tma_load_2d(st + 2 * T::A_BYTES + T::W_BYTES, &map_w_lo, full_bar(s), kb * BK, n0);
+                    }
+                    if (a_part) {
+                        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BK, m0);
+                        tma_load_2d(st + T::A_BYTES, &map_a_lo, full_bar(s), kb * BK, m0);
+                    }
                 }
-            }
+            };
+            uint32_t kbc = 0;
+            for (int ct = ct0; ct < num_ct && kbc < (uint32_t)T::STAGES; ct += ct_step)
+                for (int kb = 0; kb < num_kb && kbc < (uint32_t)T::STAGES; ++kb, ++kbc) load(ct, kb, kbc, true, true, false);
+            pdl_wait();
+            kbc = 0;
+            for (int ct = ct0; ct < num_ct; ct += ct_step)
+                for (int kb = 0; kb < num_kb; ++kb, ++kbc) {
+                    const bool first_pass = kbc < (uint32_t)T::STAGES;
+                    load(ct, kb, kbc, first_pass, !first_pass, true);
+                }
         }
+        __syncwarp();
+        pdl_wait();
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        pdl_wait();
         constexpr uint32_t idesc = kF16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
         uint32_t kbc = 0, it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
@@ -354,6 +370,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         pdl_trigger_late();                  // every MMA of this CTA is issued: its last epilogue is what is left
     } else {
         // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp-2)/4 =====
+        pdl_wait();                             // bias / residual / mask reads and every store below come after the predecessor
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr int COLS_PER_WARP = BN / 2;
         float* stg = reinterpret_cast<float*>(smem_gen + T::EPI_OFF) + (warp - 2) * 32 * EPI_PITCH;
