@@ -378,46 +378,73 @@ def main():
                   "ms_per_pass": m4["ms_per_step"], "e2e": m4["e2e"], "per_rank": m4["per_rank"], "steps": max(2, a.steps // 4),
                   "groups": [[b["B"], b["T"], b.get("L", 0)] for b in m4["buckets"]]}
 
+    def device_ms(tv, lv, vv, total_step, reps=3):
+        """Median device time (CUDA events on the library's stream, L2 flushed) of one device-resident synthesis of the given utterances."""
+        sv = T.load_voice_style([os.path.join(root, "voice_styles", v + ".json") for v in vv])
+        iv, mv = eng.text_to_ids(tv, lv)
+        dv = {k: torch.from_numpy(np.ascontiguousarray(x)).cuda() for k, x in dict(ids=iv, mask=mv, ttl=sv.ttl, dp=sv.dp).items()}
+        lv32 = mv.reshape(len(tv), -1).sum(1).astype(np.int32)
+        st = dict(cap=int(lv32.sum() * 0.12 * eng.cfg.sample_rate) + (len(tv) + 8) * cs)
+        st["wav"] = torch.empty(st["cap"], dtype=torch.float32, device="cuda")
+        duv = torch.empty(len(tv), dtype=torch.float32, device="cuda")
+
+        def one(seed):
+            for attempt in range(2):
+                try:
+                    return eng.synthesize_packed_device(dv["ids"].data_ptr(), dv["mask"].data_ptr(), dv["ttl"].data_ptr(), dv["dp"].data_ptr(), len(tv),
+                                                        iv.shape[1], total_step, 1.05, seed, st["wav"].data_ptr(), st["cap"], duv.data_ptr(), text_lens=lv32)
+                except capi.StcError as e:
+                    if e.code != capi.ERR_CAPACITY or attempt:
+                        raise
+                    st["cap"] = int(e.need); st["wav"] = torch.empty(st["cap"], dtype=torch.float32, device="cuda")
+        for w in range(2):
+            off = one(w)
+        ts = []
+        for k in range(reps):
+            flush.fill_(k); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ext):
+                e0.record(); off = one(10 + k); e1.record()
+            e1.synchronize(); ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)), int(off[-1] // cs), float(duv.sum().item())
+
     # ---- varied draws (rank 0 only at N = 1; per rank at N > 1): every seed another 32-utterance batch, i.e. another row-tile count ----
     vary = None
     if a.workload == "batch" and not a.no_vary and rank == 0:
         rows_v = []
         for sd in range(8):
             tv, lv, vv = workload(a.batch, 2234 + 1000 * sd)
-            sv = T.load_voice_style([os.path.join(root, "voice_styles", v + ".json") for v in vv])
-            iv, mv = eng.text_to_ids(tv, lv)
-            dv = {k: torch.from_numpy(np.ascontiguousarray(x)).cuda() for k, x in dict(ids=iv, mask=mv, ttl=sv.ttl, dp=sv.dp).items()}
-            lv32 = mv.reshape(len(tv), -1).sum(1).astype(np.int32)
-            capv = int(lv32.sum() * 0.12 * eng.cfg.sample_rate) + (len(tv) + 8) * cs
-            wv = torch.empty(capv, dtype=torch.float32, device="cuda"); duv = torch.empty(len(tv), dtype=torch.float32, device="cuda")
-
-            def one(seed):
-                nonlocal wv, capv
-                for attempt in range(2):
-                    try:
-                        return eng.synthesize_packed_device(dv["ids"].data_ptr(), dv["mask"].data_ptr(), dv["ttl"].data_ptr(), dv["dp"].data_ptr(), len(tv),
-                                                            iv.shape[1], a.total_step, 1.05, seed, wv.data_ptr(), capv, duv.data_ptr(), text_lens=lv32)
-                    except capi.StcError as e:
-                        if e.code != capi.ERR_CAPACITY or attempt:
-                            raise
-                        capv = int(e.need); wv = torch.empty(capv, dtype=torch.float32, device="cuda")
-            for w in range(2):
-                off = one(w)
-            ts = []
-            for k in range(3):
-                flush.fill_(k); torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                with torch.cuda.stream(ext):
-                    e0.record(); off = one(10 + k); e1.record()
-                e1.synchronize(); ts.append(e0.elapsed_time(e1))
-            fr = int(off[-1] // cs)
-            rows_v.append({"seed": 2234 + 1000 * sd, "latent_frames": fr, "row_tiles_of_128": -(-fr // 128), "ms_per_step": float(np.median(ts)),
-                           "audio_s": float(duv.sum().item())})
+            ms, fr, au = device_ms(tv, lv, vv, a.total_step)
+            rows_v.append({"seed": 2234 + 1000 * sd, "latent_frames": fr, "row_tiles_of_128": -(-fr // 128), "ms_per_step": ms, "audio_s": au})
         msv = [r["ms_per_step"] for r in rows_v]
         vary = {"what": "eight other draws of the 32-utterance batch (seeds 2234 + 1000 k), device-resident leg, median of 3 steps each",
                 "draws": rows_v, "mean_ms_per_step": float(np.mean(msv)), "worst_ms_per_step": float(np.max(msv)),
                 "mean_audio_s_per_s": float(np.mean([r["audio_s"] / (r["ms_per_step"] / 1000) for r in rows_v])),
                 "worst_over_headline": float(np.max(msv) / ms_per_step)}
+
+    # ---- total_step sweep (rank 0): configs[2] (en/ko/es/pt/fr in one batch, one voice style per utterance, total_step 2/5/10/20) and the
+    #      same sweep on the headline batch; the slope over total_step is the device time of ONE Euler step of the vector estimator,
+    #      the intercept what surrounds the loop (duration predictor || text encoder, vocoder) ----
+    sweep = None
+    if a.workload == "batch" and not a.no_vary and rank == 0:
+        def sweep_of(tv, lv, vv):
+            rows_s = []
+            for ts_ in (2, 5, 10, 20):
+                ms, fr, au = device_ms(tv, lv, vv, ts_)
+                rows_s.append({"total_step": ts_, "ms": ms, "audio_s_per_s": au / (ms / 1000)})
+            slope, icpt = np.polyfit([r["total_step"] for r in rows_s], [r["ms"] for r in rows_s], 1)
+            return {"utterances": len(tv), "latent_frames": fr, "row_tiles_of_128": -(-fr // 128), "audio_s": au, "by_total_step": rows_s,
+                    "ms_per_euler_step": float(slope), "ms_outside_the_loop": float(icpt)}
+        base = {"en": "This morning, I took a walk in the park, and the sound of the birds and the breeze was so pleasant.",
+                "ko": "오늘 아침에 공원을 산책했는데, 새소리와 바람 소리가 너무 기분 좋았어요.", "es": "El niño comió piñas en la montaña, ¿verdad? ¡Sí, señor!",
+                "pt": "A ação e o coração não são fáceis de explicar, mas vovô tentou.", "fr": "Où est l'hôtel? Ça coûte très cher, naïve Zoë préfère le café déjà."}
+        tm, lm, vm = [], [], []
+        for i in range(30):                                      # 6 utterances per language, 1..3 repetitions of its sentence (<= 300 characters,
+            lg = ("en", "ko", "es", "pt", "fr")[i % 5]           # the reference's chunk size, cpp/helper.cpp:698), voices cycling
+            tm.append(" ".join([base[lg]] * (1 + (i // 5) % 3))); lm.append(lg); vm.append(("M1", "F1", "M2", "F2")[i % 4])
+        sweep = {"what": "device-resident synthesis at total_step 2/5/10/20 (median of 3, L2 flushed): ms = ms_outside_the_loop + total_step x ms_per_euler_step (least squares)",
+                 "multilingual": dict(sweep_of(tm, lm, vm), workload="configs[2]: 30 utterances en/ko/es/pt/fr (6 each, 1-3 sentences, <= 300 characters), voices M1/F1/M2/F2 per utterance, speed 1.05"),
+                 "headline_batch": dict(sweep_of(texts[:group], langs[:group], voices[:group]), workload="configs[1] batch")}
 
     # ---- latency leg (rank 0): p50 wall time of TextToSpeech.call() on the reference's default sentence (configs[0]) and on a
     #      ~2 000-character text (configs[3]: chunkText -> sequential chunks like the reference, and all chunks as one packed batch) ----
@@ -586,7 +613,7 @@ def main():
            "data": "synthetic", "config": dict(cfg, buckets=[[b["B"], b["T"], b.get("L")] for b in buckets],
                                                audio_s_per_step_per_gpu=audio),
            "clocks": clocks, "e2e": main["e2e"],
-           "gpu_launches": int(launches), "parity_check": pcheck, "per_rank": per_rank, "latency": lat, "strong": strong, "vary_batches": vary, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
+           "gpu_launches": int(launches), "parity_check": pcheck, "per_rank": per_rank, "latency": lat, "strong": strong, "vary_batches": vary, "step_sweep": sweep, "roofline": roof, "cpu_baseline": cpu, "stage_ms": stage,
            "p50_step_ms": main["p50_step_ms"], "step_ms": main["step_ms"]}
     print(json.dumps(out))
     if world > 1:
