@@ -70,6 +70,48 @@ STC_DEVINL void st_global_256(void* p, const uint32_t* v) {       // one full 32
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+// TMEM -> registers without the wait, and the wait as a separate step that carries the destination registers as in/out operands, so
+// that no consumer of them can be scheduled above it: the load of chunk c + 1 is in flight under the math of chunk c.
+STC_DEVINL void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+STC_DEVINL void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+
+// GELU(erf) with ONE special-function instruction per element, for the fp16-output epilogue of the vocoder's pw1 (which is bound by
+// the MUFU pipe with the two-MUFU form of gemm_tc.cuh: ncu xu 51 % of peak, `mio` throttle on every MUFU): erf by Abramowitz-Stegun
+// 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 (|err| <= 3e-7), the 1/sqrt2 powers folded into the coefficients, the 16th power
+// as four packed squarings, the reciprocal on the MUFU. With h = x/2: (x (erf(x/sqrt2) + 1)) / 2 = (h + |h|) - |h| r  (h + |h| is
+// exact: x or 0). Max |error| against the exact function 7e-7 in fp32 (4.7e-7 for the two-MUFU form), far below the fp16 rounding
+// of the output; p^16 overflows to +inf for |x| > ~40 and the reciprocal returns 0 there, which is the right limit.
+STC_DEVINL float2 gelu_erf_rcp2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    constexpr float c1 = 0.0705230784f * 0.70710678f, c2 = 0.0422820123f * 0.5f, c3 = 0.0092705272f * 0.35355339f,
+                    c4 = 0.0001520143f * 0.25f, c5 = 0.0002765672f * 0.17677670f, c6 = 0.0000430638f * 0.125f;
+    float2 q = __ffma2_rn(ax, make_float2(c6, c6), make_float2(c5, c5));
+    q = __ffma2_rn(q, ax, make_float2(c4, c4));
+    q = __ffma2_rn(q, ax, make_float2(c3, c3));
+    q = __ffma2_rn(q, ax, make_float2(c2, c2));
+    q = __ffma2_rn(q, ax, make_float2(c1, c1));
+    q = __ffma2_rn(q, ax, make_float2(1.0f, 1.0f));
+    q = __fmul2_rn(q, q); q = __fmul2_rn(q, q); q = __fmul2_rn(q, q); q = __fmul2_rn(q, q);
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(q.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(q.y));
+    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    const float2 ah = __fmul2_rn(ax, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(make_float2(-ah.x, -ah.y), r, __fadd2_rn(h, ah));
+}
+
 // (The same lane = row form for the fp32 + residual epilogue of pw2 — 256-bit loads of the residual row, 256-bit stores — was
 // measured slower than the staged one: vocoder 1.82 -> 1.91 ms; a warp-wide 32-byte access to 32 different rows costs 32 L2 requests.)
 
@@ -215,6 +257,15 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const float* resid = static_cast<const float*>(p.ep.resid);
         // fp16 operand out, bias + GELU only: the direct form below
         const bool direct = kF16 && p.split && !p.out_lo && p.ep.gelu && p.ep.bias && !p.ep.scale && !p.ep.mask && !resid && p.N % 64 == 0 && p.ldo % 16 == 0;
+        // direct form: the warp's 64 bias values of EVERY column tile go to its staging slot once (2 KB = 8 tiles: N <= 2048)
+        const bool bias_all = kF16 && direct && n_tiles * COLS_PER_WARP * (int)sizeof(float) <= STG_BYTES;
+        if (bias_all) {
+            for (int i = lane; i < n_tiles * COLS_PER_WARP; i += 32) {
+                const int col = (i / COLS_PER_WARP) * BN + part * COLS_PER_WARP + i % COLS_PER_WARP;
+                stg[i] = col < p.N ? __ldg(p.ep.bias + col) : 0.f;
+            }
+            __syncwarp();
+        }
         uint32_t it = 0;
         for (int ct = ct0; ct < num_ct; ct += ct_step, ++it) {
             const int m0 = ((ct / n_tiles) * 2 + rank) * BM + q * 32, n0 = (ct % n_tiles) * BN + part * COLS_PER_WARP;
@@ -226,44 +277,48 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 mk[i] = (p.ep.mask && row < p.M) ? __ldg(p.ep.mask + row) : 1.f;
             }
             if (kF16 && direct) {
-                // this warp's 64 bias values -> its staging slot while the tile's MMAs still run (with 226 KB of shared memory in use
-                // there is no L1: a __ldg inside the loop is an L2 round trip on the epilogue's critical path)
-                __syncwarp();
-                stg[lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + lane) : 0.f;
-                stg[32 + lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + 32 + lane) : 0.f;
-                __syncwarp();
-            }
-            mbar_wait(tfull_bar(ab), aph);
-            tc_fence_after();
-            if (kF16 && direct) {
-                // bias -> GELU -> fp16 straight out of TMEM: lane = row, 32 consecutive columns = 64 contiguous bytes per lane and
-                // chunk (no shared-memory transpose: 31 -> ~20 issued instructions per element; this epilogue, not the MMAs,
-                // bounds the K = 512 tiles of the vocoder's pw1)
+                // bias -> GELU -> fp16 straight out of TMEM: lane = row, 16 consecutive columns = 32 contiguous bytes per lane and chunk
+                // (no shared-memory transpose; this epilogue, not the MMAs, bounds the K = 512 tiles of the vocoder's pw1). The bias
+                // of every column tile sits in the warp's staging slot since the kernel's start (bias_all; otherwise it is fetched
+                // here, an L2 round trip per tile: with 226 KB of shared memory in use there is no L1).
+                const float* bs = stg + (bias_all ? (ct % n_tiles) * COLS_PER_WARP : 0);
+                if (!bias_all) {
+                    __syncwarp();
+                    stg[lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + lane) : 0.f;
+                    stg[32 + lane] = n0 < p.N ? __ldg(p.ep.bias + n0 + 32 + lane) : 0.f;
+                    __syncwarp();
+                }
+                mbar_wait(tfull_bar(ab), aph);
+                tc_fence_after();
                 const int row = m0 + lane;
                 __nv_bfloat16* orow = p.out_hi + (size_t)row * p.ldo + n0;
-#pragma unroll 1
-                for (int c = 0; c < COLS_PER_WARP; c += 32) {
-                    uint32_t r[32], o[16];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + part * COLS_PER_WARP + c), r);
-                    if (c + 32 >= COLS_PER_WARP) {             // the accumulator is in registers: hand the buffer back before the math
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + part * COLS_PER_WARP);
+                uint32_t ra[16], rb[16];
+                tmem_ld16_issue(tcol, ra);
+                auto chunk = [&](uint32_t (&r)[16], uint32_t (&nxt)[16], int c) {
+                    tmem_ld_wait16(r);
+                    if (c + 16 < COLS_PER_WARP) tmem_ld16_issue(tcol + c + 16, nxt);     // in flight under this chunk's math
+                    else {                                     // the whole accumulator slice is in registers: hand the buffer back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(ab), 0));
                     }
+                    uint32_t o[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(stg + c + j);                     // broadcast read
-                        const float2 g0 = tc::gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), make_float2(b.x, b.y)));
-                        const float2 g1 = tc::gelu_erf_mufu2(__fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b.z, b.w)));
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bs + c + j);                      // broadcast read
+                        const float2 g0 = gelu_erf_rcp2(__fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), make_float2(b.x, b.y)));
+                        const float2 g1 = gelu_erf_rcp2(__fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b.z, b.w)));
                         o[j / 2] = pack_f16x2(g0.x, g0.y); o[j / 2 + 1] = pack_f16x2(g1.x, g1.y);
                     }
-                    if (row < p.M && n0 + c < p.N) {
-                        st_global_256(orow + c, o);
-                        st_global_256(orow + c + 16, o + 8);
-                    }
-                }
+                    if (row < p.M && n0 + c < p.N) st_global_256(orow + c, o);
+                };
+                static_assert(COLS_PER_WARP == 64, "four chunks of 16 columns");
+                chunk(ra, rb, 0); chunk(rb, ra, 16); chunk(ra, rb, 32); chunk(rb, ra, 48);
                 continue;
             }
+            mbar_wait(tfull_bar(ab), aph);
+            tc_fence_after();
             // bias / layer-scale of chunk c + 1 and the residual rows of chunk c are requested before the TMEM load of chunk c: there is
             // no L1 beside 226 KB of shared memory, every __ldg is an L2 round trip
             float4 bias_n = make_float4(0.f, 0.f, 0.f, 0.f), scale_n = make_float4(1.f, 1.f, 1.f, 1.f);
