@@ -297,7 +297,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 tmem_ld16_issue(tcol, ra);
                 auto chunk = [&](uint32_t (&r)[16], uint32_t (&nxt)[16], int c) {
                     tmem_ld_wait16(r);
-                    if (c + 16 < COLS_PER_WARP) tmem_ld16_issue(tcol + c + 16, nxt);     // in flight under this chunk's math
+                    if (c + 16 < COLS_PER_WARP) tmem_ld16_issue(tcol + c + 16, nxt);
                     else {                                     // the whole accumulator slice is in registers: hand the buffer back
                         tc_fence_before();
                         __syncwarp();

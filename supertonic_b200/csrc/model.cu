@@ -19,6 +19,7 @@
 #include "mlp_tc.cuh"
 #include "mlp_stream.cuh"
 #include "gemm2_tc.cuh"
+#include "gemm2_astat.cuh"
 #include "model.cuh"
 #include "graph_plan.h"
 #include "dp_fused.cuh"
@@ -215,6 +216,7 @@ struct Handle {
     int pdl_mode = 2;                 // env STC_PDL (launch_k): 0 = plain stream-ordered launches (cross-check), 2 / 3 = release point (kernels.cuh)
     int mlp_pair = -1;                // env STC_MLP_PAIR: 0 = one-CTA stream kernel only (cross-check), default: CTA pairs where the slices allow
     int mlp_force_slices = 0;         // env STC_MLP_SLICES (tools/mlp_sweep.py): hidden slices per row tile instead of the cost model
+    bool gemm_astat = true;           // env STC_ASTAT=0: the vocoder's pw1 keeps the streaming two-SM kernel (cross-check of gemm2_astat.cuh)
     bool mlp_unfused = false;         // env STC_MLP=unfused: the C = 256 / H = 1024 blocks as two tcgen05 GEMMs (cross-check)
     long long* gemm_trace = nullptr;  // stc_debug_gemm with STC_GEMM_TRACE=1
     long long* mlp_trace = nullptr;   // stc_debug_mlp with STC_MLP_TRACE=1
@@ -802,6 +804,16 @@ void Handle::gemm(const Act& a, int M, const Linear& w, const Epilogue& ep_in, f
         const CUtensorMap mwh = tmap(w.w_hi, w.N, w.K, tc2::HALF), mwl = f16 ? mwh : tmap(w.w_lo, w.N, w.K, tc2::HALF);
         const int num_ct = cdiv(cdiv(M, tc::BM), 2) * cdiv(w.N, tc2::BN);
         const int clusters = std::max(1, std::min(num_ct, num_sms / 2));
+        // K <= 512, bias + GELU -> fp16 operand (the vocoder's pw1): A rows stay in shared memory, W tiles stream (gemm2_astat.cuh)
+        if (f16 && gemm_astat && w.K <= tc2a::MAX_KB * tc2a::KBLK && p.split && !p.out_lo && ep.gelu && ep.bias && !ep.scale && !ep.mask && !ep.resid &&
+            w.N % tc2::BN == 0 && ldo % 16 == 0) {
+            const int units = cdiv(cdiv(M, tc::BM), 2) * cdiv(w.N / tc2::BN, tc2a::NG);
+            note("gemm2_f16_astat");
+            launch_k(this, tc2a::gemm2_f16_astat_kernel, dim3(std::max(1, std::min(units, num_sms / 2)) * 2), dim3(tc2a::THREADS), (size_t)tc2a::SMEM_BYTES, stream, mah, mwh, p);
+            ++launches;
+            kprof_end();
+            return;
+        }
         note(f16 ? "gemm2_f16" : "gemm2_bf16x3");
         if (f16) launch_k(this, tc2::gemm2_bf16x3_kernel<true>, dim3(clusters * 2), dim3(tc2::THREADS), (size_t)tc2::SMEM_BYTES, stream, mah, mal, mwh, mwl, p);
         else launch_k(this, tc2::gemm2_bf16x3_kernel<false>, dim3(clusters * 2), dim3(tc2::THREADS), (size_t)tc2::SMEM_BYTES, stream, mah, mal, mwh, mwl, p);
@@ -1486,6 +1498,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
         { const char* e = getenv("STC_VOC"); hd->voc_f16 = !e || !strcmp(e, "f16"); }
         { const char* e = getenv("STC_DW"); hd->dw_slide = !(e && !strcmp(e, "tile")); hd->dw_chain_kernel = !(e && !strcmp(e, "slide")); }
         { const char* e = getenv("STC_DW_RT"); hd->dw_rt = e ? atoi(e) : 0; }
+        { const char* e = getenv("STC_ASTAT"); hd->gemm_astat = !(e && !strcmp(e, "0")); }
         { const char* e = getenv("STC_DW_RING"); hd->dw_ring = e ? atoi(e) : -1; }
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream, cudaStreamNonBlocking));
         STC_CUDA(cudaStreamCreateWithFlags(&hd->stream2, cudaStreamNonBlocking));
@@ -1507,6 +1520,7 @@ int stc_create(const char* onnx_dir, int device, int precision, stc_handle** out
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute(tc2::gemm2_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+            STC_CUDA(cudaFuncSetAttribute(tc2a::gemm2_f16_astat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2a::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<64, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<64>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<128>::SMEM_BYTES));
             STC_CUDA(cudaFuncSetAttribute((tc::gemm_bf16x3_kernel<256, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile<256>::SMEM_BYTES));

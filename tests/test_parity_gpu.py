@@ -315,6 +315,35 @@ def test_error_paths(rig):
     assert eng.launches > 0
 
 
+@pytest.mark.parametrize("astat", ["", "0"])
+def test_two_sm_fp16_gemm_forms_against_cuda_cores(rig, astat):
+    """stc_debug_gemm, fp16 operands, bias + GELU -> fp16 operand (the vocoder's pw1 epilogue) on CTA pairs: the A-stationary kernel
+    (gemm2_astat.cuh: A rows resident, units of four column tiles) and, with STC_ASTAT=0, the streaming kernel (gemm2_tc.cuh) against
+    the fp32 CUDA-core GEMM on the same random operands. Shapes: ragged last row tile, an odd number of row tiles (the pair's second
+    CTA computes on rows beyond M), 1 / 4 / 10 column tiles (units of 4 + 4 + 2), K not a multiple of the 64-element block, K = 512."""
+    import os
+    if rig["name"] != "full":
+        pytest.skip("kernel-level check, independent of the graphs")
+    capi = rig["capi"]
+    os.environ["STC_DEBUG_F16"] = "1"
+    if astat:
+        os.environ["STC_ASTAT"] = astat
+    try:
+        eng2 = capi.Engine(rig["root"] + "/onnx")
+        try:
+            v0 = eng2.kernel_variants()
+            for M, N, K in ((300, 256, 64), (1000, 512, 256), (513, 1024, 384), (3000, 2560, 200), (2700, 2048, 512)):
+                _, err = eng2.debug_gemm(M, N, K, 512, 2, 1, 1, iters=2)
+                assert err <= 6e-3, (astat, M, N, K, err)              # fp16 rounding of operands and of outputs up to ~4 in magnitude
+            d = {k: v - v0.get(k, 0) for k, v in eng2.kernel_variants().items() if k.startswith("gemm2")}
+            assert (d.get("gemm2_f16", 0) > 0 and not d.get("gemm2_f16_astat")) if astat else d.get("gemm2_f16_astat", 0) > 0, d
+        finally:
+            eng2.close()
+    finally:
+        del os.environ["STC_DEBUG_F16"]
+        os.environ.pop("STC_ASTAT", None)
+
+
 @pytest.mark.parametrize("pair", ["0", "1", ""])
 def test_fused_mlp_forms_match_two_gemms(rig, pair):
     """stc_debug_mlp: the fused ConvNeXt MLP (mlp_stream.cuh) against pw1 -> GELU -> pw2 as two tcgen05 GEMMs on the same random block,
