@@ -25,7 +25,7 @@ namespace tc2a {
 
 using namespace tc;
 using tc2::mapa_rank; using tc2::tma_load_2d_2sm; using tc2::umma2_bf16; using tc2::umma2_commit; using tc2::tmem_alloc2; using tc2::tmem_dealloc2;
-using tc2::st_global_256; using tc2::mbar_arrive_cluster; using tc2::tmem_ld16_issue; using tc2::tmem_ld_wait16; using tc2::gelu_erf_rcp2;
+using tc2::st_global_256; using tc2::mbar_arrive_cluster; using tc2::tmem_ld16_issue; using tc2::tmem_ld_wait16;
 
 constexpr int BN = 256, HALF = 128;
 constexpr int KBLK = 64;                               // K elements per block (one 128-byte swizzle row of fp16)

@@ -87,31 +87,6 @@ STC_DEVINL void tmem_ld_wait16(uint32_t (&r)[16]) {
                  :: "memory");
 }
 
-// GELU(erf) with ONE special-function instruction per element, for the fp16-output epilogue of the vocoder's pw1 (which is bound by
-// the MUFU pipe with the two-MUFU form of gemm_tc.cuh: ncu xu 51 % of peak, `mio` throttle on every MUFU): erf by Abramowitz-Stegun
-// 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 (|err| <= 3e-7), the 1/sqrt2 powers folded into the coefficients, the 16th power
-// as four packed squarings, the reciprocal on the MUFU. With h = x/2: (x (erf(x/sqrt2) + 1)) / 2 = (h + |h|) - |h| r  (h + |h| is
-// exact: x or 0). Max |error| against the exact function 7e-7 in fp32 (4.7e-7 for the two-MUFU form), far below the fp16 rounding
-// of the output; p^16 overflows to +inf for |x| > ~40 and the reciprocal returns 0 there, which is the right limit.
-STC_DEVINL float2 gelu_erf_rcp2(float2 x) {
-    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-    constexpr float c1 = 0.0705230784f * 0.70710678f, c2 = 0.0422820123f * 0.5f, c3 = 0.0092705272f * 0.35355339f,
-                    c4 = 0.0001520143f * 0.25f, c5 = 0.0002765672f * 0.17677670f, c6 = 0.0000430638f * 0.125f;
-    float2 q = __ffma2_rn(ax, make_float2(c6, c6), make_float2(c5, c5));
-    q = __ffma2_rn(q, ax, make_float2(c4, c4));
-    q = __ffma2_rn(q, ax, make_float2(c3, c3));
-    q = __ffma2_rn(q, ax, make_float2(c2, c2));
-    q = __ffma2_rn(q, ax, make_float2(c1, c1));
-    q = __ffma2_rn(q, ax, make_float2(1.0f, 1.0f));
-    q = __fmul2_rn(q, q); q = __fmul2_rn(q, q); q = __fmul2_rn(q, q); q = __fmul2_rn(q, q);
-    float2 r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(q.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(q.y));
-    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-    const float2 ah = __fmul2_rn(ax, make_float2(0.5f, 0.5f));
-    return __ffma2_rn(make_float2(-ah.x, -ah.y), r, __fadd2_rn(h, ah));
-}
-
 // (The same lane = row form for the fp32 + residual epilogue of pw2 — 256-bit loads of the residual row, 256-bit stores — was
 // measured slower than the staged one: vocoder 1.82 -> 1.91 ms; a warp-wide 32-byte access to 32 different rows costs 32 L2 requests.)
 
