@@ -502,7 +502,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         traffic = json.load(open(tp)).get("dram_bytes_per_launch") if os.path.exists(tp) else None
         names = {"gemm_tc": "tc::gemm_bf16x3_kernel<64|128|256> (TMA -> tcgen05.mma kind::f16 -> TMEM, 3 MMAs per K-slice)",
-                 "gemm_f16": "tc2::gemm2_bf16x3_kernel<true> (vocoder projections: two-SM cta_group::2 tcgen05.mma kind::f16, single-pass fp16 operands)",
+                 "gemm_f16": "tc2a::gemm2_f16_astat_kernel (pw1: A rows resident) + tc2::gemm2_bf16x3_kernel<true> (pw2, conv_in, head) — vocoder projections: two-SM cta_group::2 tcgen05.mma kind::f16, single-pass fp16 operands",
                  "fused_mlp": "mlp::convnext_mlp_stream2_kernel (CTA pairs, cta_group::2) / convnext_mlp_stream_kernel + mlp_reduce[_post]_kernel (pw1 -> GELU -> pw2 fused: S in TMEM, P written back into TMEM, "
                               "O accumulated from the TMEM operand; tcgen05, 3 MMAs per K-slice)"}
 
