@@ -210,8 +210,8 @@ STC_DEVINL float2 gelu_erf_mufu2(float2 x) {
 // the MUFU pipe with the two-MUFU form of gemm_tc.cuh: ncu xu 51 % of peak, `mio` throttle on every MUFU): erf by Abramowitz-Stegun
 // 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 (|err| <= 3e-7), the 1/sqrt2 powers folded into the coefficients, the 16th power
 // as four packed squarings, the reciprocal on the MUFU. With h = x/2: (x (erf(x/sqrt2) + 1)) / 2 = (h + |h|) - |h| r  (h + |h| is
-// exact: x or 0). Max |error| against the exact function 7e-7 in fp32 (4.7e-7 for the two-MUFU form), far below the fp16 rounding
-// of the output; p^16 overflows to +inf for |x| > ~40 and the reciprocal returns 0 there, which is the right limit.
+// exact: x or 0). Max |error| against the exact function 7e-7 in fp32 (4.7e-7 for the two-MUFU form; tests/test_gelu_forms.py) — below
+// half an fp16 ulp of the output from |y| = 2e-3 up, the same few 1e-7 in absolute terms in the negative tail; p^16 overflows to +inf for |x| > ~40 and the reciprocal returns 0 there, which is the right limit.
 STC_DEVINL float2 gelu_erf_rcp2(float2 x) {
     const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
     constexpr float c1 = 0.0705230784f * 0.70710678f, c2 = 0.0422820123f * 0.5f, c3 = 0.0092705272f * 0.35355339f,
