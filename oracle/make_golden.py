@@ -81,7 +81,34 @@ def cases():
              sample_rate=44100),
         dict(kind="wav", samples=[], sample_rate=22050),
     ]
-    return c
+    return c + random_cases()
+
+
+def random_cases():
+    """Seeded random inputs for the two text functions (the reference's answers on them widen what the oracle restatement and the
+    library's regex-free rewrite are pinned to): sentence / paragraph structure with abbreviations and runs of punctuation for
+    chunkText at the chunk sizes call() uses (300; 120 for Korean) and at tiny limits; mixed-script strings with the symbols the
+    front-end rewrites or drops for UnicodeProcessor::call."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    words = ["the", "river", "Dr.", "Mr.", "Mrs.", "e.g.", "i.e.", "etc.", "U.S.", "3.14", "naïve", "café", "오늘", "아침에", "señor", "ação",
+             "x", "A", "walked", "along", "thunder", "Inc.", "Prof.", "vs.", "No.", "St.", "Jr.", "Ph.D.", "a.m."]
+    seps = [" ", " ", " ", ", ", ". ", "! ", "? ", "... ", ".\n\n", "\n\n", "\n", "?! ", ".  ", "; ", " — ", ".\" ", "。", "! \n \n"]
+    out = []
+    for i in range(36):
+        k = int(rng.integers(1, 60))
+        text = "".join(str(rng.choice(words)) + str(rng.choice(seps)) for _ in range(k))
+        if i % 3 == 0:
+            text = text.strip()
+        out.append(dict(kind="chunk", text=text, max_len=(300, 120, int(rng.integers(1, 40)))[i % 3], cite="seeded random (rng 2024)"))
+    alphabet = list("abc XYZ,.!?;:'\"()[]{}_@&%$#-–—…“”‘’´`0123456789éñçãõàüöß한국어오늘") + ["\n", "\t", "  ", "e.g.,", "i.e.,", "😀", "♥", "→", "|", "/"]
+    for i in range(12):
+        n = int(rng.integers(1, 5))
+        texts = ["".join(rng.choice(alphabet, size=int(rng.integers(1, 80)))) for _ in range(n)]
+        texts = [t if t.strip() else "x" + t for t in texts]
+        out.append(dict(kind="text", texts=texts, langs=[str(rng.choice(["en", "ko", "es", "pt", "fr"])) for _ in range(n)],
+                        cite="seeded random (rng 2024)"))
+    return out
 
 
 def main():
