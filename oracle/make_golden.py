@@ -108,6 +108,17 @@ def random_cases():
         texts = [t if t.strip() else "x" + t for t in texts]
         out.append(dict(kind="text", texts=texts, langs=[str(rng.choice(["en", "ko", "es", "pt", "fr"])) for _ in range(n)],
                         cite="seeded random (rng 2024)"))
+    for i in range(3):              # writeWavFile: clamp, scale by 32767, truncate toward zero (cpp/helper.cpp:985-988)
+        x = rng.standard_normal(400) * (0.4, 0.9, 1.3)[i]
+        x[::37] = (1.0, -1.0, 0.999985, -0.999985, 3.0517578e-05, -3.0517578e-05, 1.5258789e-05, 0.5, -0.5, 2.0, -2.0)[:len(x[::37])]
+        out.append(dict(kind="wav", samples=[float(np.float32(v)) for v in x], sample_rate=(44100, 22050, 16000)[i], cite="seeded random (rng 2024)"))
+    for i in range(4):              # getLatentMask / lengthToMask (cpp/helper.cpp:740-770)
+        out.append(dict(kind="latent_mask", wav_lengths=[int(v) for v in rng.integers(1, 12 * 44100, size=int(rng.integers(1, 7)))],
+                        base_chunk_size=512, chunk_compress_factor=6, cite="seeded random (rng 2024)"))
+        out.append(dict(kind="length_mask", lengths=[int(v) for v in rng.integers(0, 40, size=int(rng.integers(1, 9)))]))
+    for i in range(6):              # sanitizeFilename (cpp/helper.cpp:1070-1111)
+        out.append(dict(kind="sanitize", text="".join(rng.choice(alphabet, size=int(rng.integers(1, 60)))), max_len=int(rng.integers(1, 50)),
+                        cite="seeded random (rng 2024)"))
     return out
 
 
