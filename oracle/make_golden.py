@@ -116,6 +116,17 @@ def random_cases():
         out.append(dict(kind="latent_mask", wav_lengths=[int(v) for v in rng.integers(1, 12 * 44100, size=int(rng.integers(1, 7)))],
                         base_chunk_size=512, chunk_compress_factor=6, cite="seeded random (rng 2024)"))
         out.append(dict(kind="length_mask", lengths=[int(v) for v in rng.integers(0, 40, size=int(rng.integers(1, 9)))]))
+    # sampleNoisyLatent (cpp/helper.cpp:424-467): float32 durations -> latent length and mask; durations around multiples of the
+    # 3072-sample latent frame (where float32 and integer arithmetic could part) and plain random ones
+    cs = 512 * 6
+    for i in range(8):
+        k = rng.integers(1, 90, size=int(rng.integers(1, 6)))
+        d = (k * cs + rng.integers(-2, 3, size=len(k))) / 44100.0
+        out.append(dict(kind="noisy_latent", duration=[float(np.float32(v)) for v in d], cite="seeded random (rng 2024), frame boundaries"))
+    for i in range(8):
+        d = rng.uniform(0.3, 25.0, size=int(rng.integers(1, 7)))
+        out.append(dict(kind="noisy_latent", duration=[float(np.float32(v)) for v in d], cite="seeded random (rng 2024)"))
+    out.append(dict(kind="noisy_latent", duration=[2.0897958278656006], cite="tests/test_host_oracle.py float32-vs-float64 case"))
     for i in range(6):              # sanitizeFilename (cpp/helper.cpp:1070-1111)
         out.append(dict(kind="sanitize", text="".join(rng.choice(alphabet, size=int(rng.integers(1, 60)))), max_len=int(rng.integers(1, 50)),
                         cite="seeded random (rng 2024)"))
@@ -156,6 +167,8 @@ def main():
             print(k, [len(x) for x in r["text_ids"]], [int(sum(m[0])) for m in r["text_mask"]])
         elif k == "chunk":
             print(k, [len(x.encode("utf-8", "surrogateescape")) for x in r["chunks"]])
+        elif k == "noisy_latent":
+            print(k, r["latent_shape"], len(r["mask"][0][0]), r["masked_zero"], r["live_nonzero"])
 
 
 if __name__ == "__main__":

@@ -1,7 +1,27 @@
 // ORACLE BUILD ONLY — drives the unmodified reference host code (cpp/helper.cpp, compiled from
 // /root/reference where it lies) over a JSON list of cases and prints JSON answers. Used by
 // oracle/make_golden.py to produce tests/golden/host_golden.json.
+// (private members of the reference class are reached from THIS driver only: sampleNoisyLatent is private; the class layout and
+//  the reference translation unit are untouched)
+#include <algorithm>
+#include <cstdint>
+#include <fstream>
+#include <iomanip>
+#include <chrono>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <random>
+#include <regex>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <onnxruntime_cxx_api.h>
+#include <nlohmann/json.hpp>
+#define private public
 #include "helper.h"
+#undef private
 #include <fstream>
 #include <nlohmann/json.hpp>
 using json = nlohmann::json;
@@ -41,6 +61,24 @@ int main(int argc, char** argv) {
                 double a = 0, b = 0; for (float v : s.getTtlData()) a += v; for (float v : s.getDpData()) b += v;
                 r["ttl_sum"] = a; r["dp_sum"] = b;
                 r["ttl_head"] = std::vector<float>(s.getTtlData().begin(), s.getTtlData().begin() + 4);
+            } else if (kind == "noisy_latent") {
+                // TextToSpeech::sampleNoisyLatent (cpp/helper.cpp:424-467): latent length / mask from float32 durations; the noise itself
+                // is std::random_device-seeded, so only its geometry and masking are reported
+                Config cfg = loadCfgs(onnx_dir);
+                TextToSpeech tts(cfg, proc.get(), nullptr, nullptr, nullptr, nullptr);
+                std::vector<std::vector<std::vector<float>>> lat, mask;
+                tts.sampleNoisyLatent(c["duration"].get<std::vector<float>>(), lat, mask);
+                r["latent_shape"] = {lat.size(), lat[0].size(), lat[0][0].size()};
+                r["mask"] = mask;
+                bool masked_zero = true, live_nonzero = true;
+                for (size_t b = 0; b < lat.size(); ++b)
+                    for (size_t t = 0; t < lat[b][0].size() && t < mask[b][0].size(); ++t) {
+                        bool any = false;
+                        for (size_t d = 0; d < lat[b].size(); ++d) any = any || lat[b][d][t] != 0.0f;
+                        if (mask[b][0][t] == 0.0f && any) masked_zero = false;
+                        if (mask[b][0][t] != 0.0f && !any) live_nonzero = false;
+                    }
+                r["masked_zero"] = masked_zero; r["live_nonzero"] = live_nonzero;
             } else if (kind == "cfg") {
                 Config cfg = loadCfgs(onnx_dir);
                 r["cfg"] = {cfg.ae.sample_rate, cfg.ae.base_chunk_size, cfg.ttl.chunk_compress_factor, cfg.ttl.latent_dim};

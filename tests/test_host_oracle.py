@@ -80,6 +80,20 @@ def test_cfg_and_style_loading(host_golden, tiny_assets):
     np.testing.assert_array_equal(ttl.reshape(-1)[:4], np.asarray(r["ttl_head"], np.float32))
 
 
+def test_latent_geometry_matches_reference(host_golden):
+    """`latent_geometry` (the restatement of TextToSpeech::sampleNoisyLatent's length arithmetic, cpp/helper.cpp:424-467) against the
+    UNMODIFIED reference run on float32 durations — around multiples of the 3072-sample latent frame, random ones, and the
+    float32-vs-float64 case below: latent length, latent channel count and mask; the reference's noise is zero exactly where the mask is."""
+    rs = _by_kind(host_golden, "noisy_latent")
+    assert len(rs) >= 17
+    for r in rs:
+        d = np.asarray(r["case"]["duration"], np.float32)
+        wl, L, mask = hr.latent_geometry(d, 44100, 512, 6)
+        assert r["latent_shape"] == [len(d), 24 * 6, L], r["case"]
+        np.testing.assert_array_equal(mask, np.asarray(r["mask"], np.float32))
+        assert r["masked_zero"] and r["live_nonzero"]
+
+
 def test_latent_geometry_float32_semantics():
     """cpp/helper.cpp:430-438: float32 formula == integer formula of :767 on every draw (App. G)."""
     rng = np.random.default_rng(0)
