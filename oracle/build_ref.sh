@@ -19,6 +19,11 @@ mkdir -p "$here/_ref"
 g++ -std=c++17 -O2 -I "$here/ref_stub" -I "$ref/cpp" -I "$nl" \
     "$ref/cpp/helper.cpp" "$here/ref_host_driver.cpp" -o "$here/_ref/ref_host"
 echo "built $here/_ref/ref_host"
+# The same reference translation unit against oracle/ref_stub_fake (closed-form stand-ins for the four graphs): the reference's
+# _infer / call / batch orchestration runs end to end on the CPU -> tests/golden/pipeline_golden.json (oracle/make_golden.py).
+g++ -std=c++17 -O2 -DSTC_FAKE_ORT -I "$here/ref_stub_fake" -I "$ref/cpp" -I "$nl" \
+    "$ref/cpp/helper.cpp" "$here/ref_host_driver.cpp" -o "$here/_ref/ref_pipe"
+echo "built $here/_ref/ref_pipe"
 
 # The drop-in proof: the UNMODIFIED reference CLI (cpp/example_onnx.cpp + cpp/helper.cpp, compiled where they lie)
 # against include/ort_shim/onnxruntime_cxx_api.h, linked to libsupertonic_cuda.so instead of libonnxruntime.

@@ -5,7 +5,11 @@ arithmetic around the four Session::Run calls. C++ behaviour is canonical for th
 (SURVEY.md App. E), so strings are handled as UTF-8 *bytes* exactly like cpp/helper.cpp does.
 
 Pinned against tests/golden/host_golden.json, which is produced by running the unmodified
-reference cpp/helper.cpp (oracle/make_golden.py) — see tests/test_host_oracle.py.
+reference cpp/helper.cpp (oracle/make_golden.py) — see tests/test_host_oracle.py — and, for the
+orchestration (ReferenceTTS: _infer / call / batch), against tests/golden/pipeline_golden.json:
+what the unmodified TextToSpeech::call / batch did, Run by Run, over the closed-form stand-ins of
+oracle/ref_stub_fake/onnxruntime_cxx_api.h (tests/test_oracle_pipeline.py). What stays UNPINNED is
+the arithmetic inside the four Session::Run calls (oracle/onnx_interp.py stands in for ONNX Runtime).
 """
 from __future__ import annotations
 

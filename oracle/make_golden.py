@@ -133,6 +133,47 @@ def random_cases():
     return out
 
 
+def pipeline_cases(styles):
+    """TextToSpeech::call / batch (cpp/helper.cpp:685-734 over _infer :469-683) run end to end by oracle/_ref/ref_pipe: the unmodified
+    reference orchestration over the closed-form stand-ins of oracle/ref_stub_fake/onnxruntime_cxx_api.h."""
+    lf = longform_from_reference()
+    m1, f1 = styles("M1"), styles("F1")
+    return [
+        dict(kind="call", text=DEFAULT_EN, lang="en", styles=[m1], total_step=5, speed=1.05, silence_duration=0.3, cite="cpp/example_onnx.cpp:17"),
+        dict(kind="call", text=lf, lang="en", styles=[f1], total_step=2, speed=1.0, silence_duration=0.3, cite="test_all.sh:70 (three chunks)"),
+        dict(kind="call", text=" ".join([BATCH_KO] * 4) + " 정말요? 네!", lang="ko", styles=[m1], total_step=3, speed=1.2, silence_duration=0.25,
+             cite="Korean chunks of 120"),
+        dict(kind="call", text="short", lang="en", styles=[m1], total_step=1, speed=0.8, silence_duration=0.0),
+        dict(kind="batch", texts=[BATCH_EN, BATCH_KO], langs=["en", "ko"], styles=[m1, f1], total_step=5, speed=1.05, cite="test_all.sh:63-64"),
+        dict(kind="batch", texts=["El niño comió piñas, ¿verdad? ¡Sí!", "Ação e coração: não é fácil.", "Où est l'hôtel? Ça coûte très cher.", "x"],
+             langs=["es", "pt", "fr", "en"], styles=[m1, f1, f1, m1], total_step=10, speed=0.9),
+        dict(kind="batch", texts=[DEFAULT_EN], langs=["en"], styles=[m1], total_step=20, speed=2.0),
+        dict(kind="call", text=DEFAULT_EN, lang="en", styles=[m1, f1], total_step=2, speed=1.05, silence_duration=0.3, cite="error: two styles"),
+        dict(kind="batch", texts=[DEFAULT_EN, "two"], langs=["en", "en"], styles=[m1], total_step=2, speed=1.05, cite="error: count mismatch"),
+        dict(kind="batch", texts=["bad"], langs=["de"], styles=[m1], total_step=2, speed=1.05, cite="error: language"),
+    ]
+
+
+def make_pipeline_golden(assets):
+    exe = os.path.join(HERE, "_ref", "ref_pipe")
+    cs = pipeline_cases(lambda n: os.path.join(assets, "voice_styles", n + ".json"))
+    with tempfile.TemporaryDirectory() as td:
+        cj = os.path.join(td, "cases.json")
+        with open(cj, "w", encoding="utf-8") as f:
+            json.dump(cs, f, ensure_ascii=False)
+        raw = subprocess.run([exe, cj, os.path.join(assets, "onnx")], check=True, capture_output=True).stdout
+    res = json.loads(raw.decode("utf-8"))
+    for r in res:
+        r["case"]["styles"] = [os.path.basename(p) for p in r["case"]["styles"]]
+    out = os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")
+    with open(out, "w", encoding="utf-8") as f:
+        json.dump(dict(generator="oracle/make_golden.py", source="unmodified /root/reference/cpp/helper.cpp TextToSpeech::call / batch over "
+                       "oracle/ref_stub_fake/onnxruntime_cxx_api.h (closed-form stand-ins for the four graphs)", results=res), f, ensure_ascii=True)
+    print(f"wrote {out}: {len(res)} cases")
+    for r in res:
+        print(r["case"]["kind"], r.get("error") or (r["wav_len"], r["duration"], len(r["trace"])))
+
+
 def main():
     exe = os.path.join(HERE, "_ref", "ref_host")
     if not os.path.exists(exe):
@@ -159,6 +200,7 @@ def main():
         json.dump(dict(generator="oracle/make_golden.py", source="unmodified /root/reference/cpp/helper.cpp",
                        indexer="supertonic_b200.surrogate.build_indexer()", results=res), f, ensure_ascii=True)
     print(f"wrote {out}: {len(res)} cases")
+    make_pipeline_golden(assets)
     for r in res:
         k = r["case"]["kind"]
         if "error" in r:

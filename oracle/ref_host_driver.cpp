@@ -79,6 +79,39 @@ int main(int argc, char** argv) {
                         if (mask[b][0][t] != 0.0f && !any) live_nonzero = false;
                     }
                 r["masked_zero"] = masked_zero; r["live_nonzero"] = live_nonzero;
+#ifdef STC_FAKE_ORT
+            } else if (kind == "call" || kind == "batch") {
+                // the reference's orchestration end to end over the closed-form stand-ins of oracle/ref_stub_fake (built as ref_pipe)
+                Config cfg = loadCfgs(onnx_dir);
+                fake_ort::g_chunk = cfg.ae.base_chunk_size * cfg.ttl.chunk_compress_factor;
+                Ort::Env env; Ort::SessionOptions opts;
+                Ort::Session dp(env, (onnx_dir + "/duration_predictor.onnx").c_str(), opts), te(env, (onnx_dir + "/text_encoder.onnx").c_str(), opts),
+                    ve(env, (onnx_dir + "/vector_estimator.onnx").c_str(), opts), voc(env, (onnx_dir + "/vocoder.onnx").c_str(), opts);
+                TextToSpeech tts(cfg, proc.get(), &dp, &te, &ve, &voc);
+                Style style = loadVoiceStyle(c["styles"].get<std::vector<std::string>>());
+                auto mem = Ort::MemoryInfo::CreateCpu(OrtArenaAllocator, OrtMemTypeDefault);
+                fake_ort::g_trace.clear(); fake_ort::g_prev_ve.clear();
+                TextToSpeech::SynthesisResult res = kind == "call"
+                    ? tts.call(mem, c["text"].get<std::string>(), c["lang"].get<std::string>(), style, c["total_step"].get<int>(),
+                               c["speed"].get<float>(), c["silence_duration"].get<float>())
+                    : tts.batch(mem, c["texts"].get<std::vector<std::string>>(), c["langs"].get<std::vector<std::string>>(), style,
+                                c["total_step"].get<int>(), c["speed"].get<float>());
+                r["wav_len"] = res.wav.size();
+                double sum = 0; for (float v : res.wav) sum += v;
+                r["wav_sum"] = sum;
+                std::vector<float> samp; for (size_t i = 0; i < res.wav.size(); i += 1009) samp.push_back(res.wav[i]);
+                if (!res.wav.empty()) samp.push_back(res.wav.back());
+                r["wav_samples"] = samp; r["duration"] = res.duration;
+                json tr = json::array();
+                for (auto& k : fake_ort::g_trace) {
+                    json e; e["graph"] = k.graph; e["inputs"] = k.inputs; e["shapes"] = k.shapes;
+                    if (k.graph == "vector_estimator.onnx") {
+                        e["total_step"] = k.total_step; e["current_step"] = k.current_step; e["masked_zero"] = k.masked_zero; e["is_prev_output"] = k.is_prev_output;
+                    }
+                    tr.push_back(e);
+                }
+                r["trace"] = tr;
+#endif
             } else if (kind == "cfg") {
                 Config cfg = loadCfgs(onnx_dir);
                 r["cfg"] = {cfg.ae.sample_rate, cfg.ae.base_chunk_size, cfg.ttl.chunk_compress_factor, cfg.ttl.latent_dim};

@@ -62,3 +62,90 @@ def test_call_concatenates_untrimmed_chunks_with_silence(ora):
         ora.call(text, "en", *ora.style(["M1", "F1"]), 2)
     with pytest.raises(RuntimeError):
         ora.batch(["a", "b"], ["en", "en"], ttl, dp, 2, noise=make_noise(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The restatement of the reference's ORCHESTRATION pinned to the reference itself: tests/golden/pipeline_golden.json holds what the
+# UNMODIFIED TextToSpeech::call / batch (cpp/helper.cpp:469-734, compiled where it lies as oracle/_ref/ref_pipe) did over the
+# closed-form stand-ins of oracle/ref_stub_fake/onnxruntime_cxx_api.h; the same stand-ins in numpy drive host_ref.ReferenceTTS here.
+def _fake_runs(trace, chunk):
+    f = np.float32
+
+    def note(graph, feed, **extra):
+        trace.append(dict(graph=graph, inputs=list(feed), shapes=[list(np.asarray(v).shape) for v in feed.values()], **extra))
+
+    def dp(feed):
+        note("duration_predictor.onnx", feed)
+        ids, mask = feed["text_ids"], feed["text_mask"]
+        return (mask[:, 0, :].sum(1).astype(f) * f(0.0625) + (ids[:, 0] % 5).astype(f) * f(0.03125)).astype(f)
+
+    def te(feed):
+        note("text_encoder.onnx", feed)
+        return (feed["text_mask"] * (np.arange(1, 5, dtype=f) * f(0.03125))[None, :, None]).astype(f)
+
+    def ve(feed):
+        x, lm = feed["noisy_latent"], feed["latent_mask"]
+        prev = trace[-1].get("_out") if trace and trace[-1]["graph"] == "vector_estimator.onnx" else None
+        cur, tot = feed["current_step"], feed["total_step"]
+        D = x.shape[1]
+        out = (lm * (f(0.5) + cur * f(0.0625) + tot * f(0.0078125))[:, None, None]
+               + lm * ((np.arange(D) % 16).astype(f) * f(0.0009765625))[None, :, None]).astype(f)
+        # (0.5 + cur/16 + tot/128) + (d % 16)/1024 is exact in float32 in either association: every term is a multiple of 2^-10 below 4)
+        note("vector_estimator.onnx", feed, total_step=[float(v) for v in tot], current_step=[float(v) for v in cur],
+             masked_zero=bool(np.all(x * (1 - lm) == 0)), is_prev_output=bool(cur[0] == 0 or (prev is not None and np.array_equal(prev, x))), _out=out)
+        return out
+
+    def voc(feed):
+        note("vocoder.onnx", feed)
+        x = feed["latent"]
+        B, D, L = x.shape
+        i = np.arange(L * chunk)
+        return (x[:, i % D, i // chunk] * f(0.5) + ((i % 97) - 48).astype(f) * f(0.0078125)[None]).astype(f)
+    return dp, te, ve, voc
+
+
+def test_orchestration_restatement_matches_the_unmodified_reference(tiny_assets):
+    import json, os
+    from supertonic_b200 import surrogate
+    with open(os.path.join(os.path.dirname(__file__), "golden", "pipeline_golden.json"), encoding="utf-8") as fh:
+        golden = json.load(fh)["results"]
+    cfg = json.load(open(os.path.join(tiny_assets, "onnx", "tts.json")))
+    chunk = int(cfg["ae"]["base_chunk_size"]) * int(cfg["ttl"]["chunk_compress_factor"])
+    rng = np.random.default_rng(0)
+    noise = lambda B, D, L: rng.standard_normal((B, D, L)).astype(np.float32)      # the stand-ins ignore its values, as the golden run did
+    assert len(golden) >= 10
+    ok = errs = 0
+    for r in golden:
+        c = r["case"]
+        ttl, dp_style = [], []
+        for name in c["styles"]:
+            j = json.load(open(os.path.join(tiny_assets, "voice_styles", name)))
+            ttl.append(np.asarray(j["style_ttl"]["data"], np.float32).reshape(j["style_ttl"]["dims"]))
+            dp_style.append(np.asarray(j["style_dp"]["data"], np.float32).reshape(j["style_dp"]["dims"]))
+        ttl, dp_style = np.concatenate(ttl), np.concatenate(dp_style)
+        trace = []
+        tts = host_ref.ReferenceTTS(cfg, surrogate.build_indexer(), *_fake_runs(trace, chunk))
+        try:
+            if c["kind"] == "call":
+                wav, dur = tts.call(c["text"], c["lang"], ttl, dp_style, c["total_step"], c["speed"], c["silence_duration"], noise)
+            else:
+                wav, dur = tts.batch(c["texts"], c["langs"], ttl, dp_style, c["total_step"], c["speed"], noise)
+        except (RuntimeError, ValueError) as e:
+            assert "error" in r and str(e) == r["error"], (c, str(e), r.get("error"))
+            errs += 1
+            continue
+        assert "error" not in r, r.get("error")
+        assert len(wav) == r["wav_len"], c
+        np.testing.assert_array_equal(np.asarray(dur, np.float32), np.asarray(r["duration"], np.float32))
+        samp = np.concatenate([wav[::1009], wav[-1:]])
+        np.testing.assert_array_equal(samp, np.asarray(r["wav_samples"], np.float32))
+        assert float(np.cumsum(wav, dtype=np.float64)[-1]) == r["wav_sum"]            # sequential double sum, as the driver adds
+        # every Session::Run of the reference, in order: graph, input names as passed, shapes, the scalar tensors of the Euler loop
+        assert len(trace) == len(r["trace"]), (len(trace), len(r["trace"]))
+        for got, want in zip(trace, r["trace"]):
+            assert got["graph"] == want["graph"] and got["inputs"] == want["inputs"] and got["shapes"] == want["shapes"], (got["graph"], got["inputs"], want)
+            if want["graph"] == "vector_estimator.onnx":
+                assert got["total_step"] == want["total_step"] and got["current_step"] == want["current_step"]
+                assert want["masked_zero"] and want["is_prev_output"] and got["masked_zero"] and got["is_prev_output"]
+        ok += 1
+    assert ok >= 7 and errs >= 3
