@@ -154,6 +154,55 @@ def pipeline_cases(styles):
     ]
 
 
+def python_reference_answers(res, assets):
+    """The same cases through the UNMODIFIED Python reference (py/helper.py, imported from /root/reference with a fake `onnxruntime`
+    module that computes the same stand-ins, oracle/fake_graphs.py): each record gets a `py` object — what TextToSpeech.__call__ /
+    batch of the Python port returned and the inputs each InferenceSession.run received."""
+    import contextlib
+    import importlib.util
+    import io
+    import numpy as np
+    from oracle import fake_graphs
+    path = "/root/reference/py/helper.py"
+    if not os.path.exists(path):
+        return
+    cfg = json.load(open(os.path.join(assets, "onnx", "tts.json")))
+    chunk = int(cfg["ae"]["base_chunk_size"]) * int(cfg["ttl"]["chunk_compress_factor"])
+    trace = []
+    saved = sys.modules.get("onnxruntime")
+    sys.modules["onnxruntime"] = fake_graphs.fake_onnxruntime_module(trace, chunk)
+    try:
+        spec = importlib.util.spec_from_file_location("supertonic_reference_py_helper", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tts = mod.load_text_to_speech(os.path.join(assets, "onnx"), False)
+        for r in res:
+            c = r["case"]
+            del trace[:]
+            np.random.seed(0)                       # the port draws its noise from np.random.randn; the stand-ins ignore its values
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    style = mod.load_voice_style(c["styles"])
+                    if c["kind"] == "call":
+                        wav, dur = tts(c["text"], c["lang"], style, c["total_step"], c["speed"], c["silence_duration"])
+                    else:
+                        wav, dur = tts.batch(c["texts"], c["langs"], style, c["total_step"], c["speed"])
+            except Exception as e:                  # the port asserts / raises ValueError where the C++ throws
+                r["py"] = dict(error=f"{type(e).__name__}: {e}")
+                continue
+            wav = np.asarray(wav, np.float32).reshape(-1)
+            r["py"] = dict(wav_len=int(wav.size), wav_sum=float(np.cumsum(wav, dtype=np.float64)[-1]),
+                           wav_samples=[float(v) for v in np.concatenate([wav[::1009], wav[-1:]])],
+                           duration=[float(v) for v in np.asarray(dur, np.float32).reshape(-1)],
+                           trace=[{k: v for k, v in t.items() if k != "_out"} for t in trace])
+    finally:
+        if saved is None:
+            sys.modules.pop("onnxruntime", None)
+        else:
+            sys.modules["onnxruntime"] = saved
+
+
 def make_pipeline_golden(assets):
     exe = os.path.join(HERE, "_ref", "ref_pipe")
     cs = pipeline_cases(lambda n: os.path.join(assets, "voice_styles", n + ".json"))
@@ -163,6 +212,7 @@ def make_pipeline_golden(assets):
             json.dump(cs, f, ensure_ascii=False)
         raw = subprocess.run([exe, cj, os.path.join(assets, "onnx")], check=True, capture_output=True).stdout
     res = json.loads(raw.decode("utf-8"))
+    python_reference_answers(res, assets)
     for r in res:
         r["case"]["styles"] = [os.path.basename(p) for p in r["case"]["styles"]]
     out = os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")
@@ -171,7 +221,8 @@ def make_pipeline_golden(assets):
                        "oracle/ref_stub_fake/onnxruntime_cxx_api.h (closed-form stand-ins for the four graphs)", results=res), f, ensure_ascii=True)
     print(f"wrote {out}: {len(res)} cases")
     for r in res:
-        print(r["case"]["kind"], r.get("error") or (r["wav_len"], r["duration"], len(r["trace"])))
+        print(r["case"]["kind"], r.get("error") or (r["wav_len"], r["duration"], len(r["trace"])),
+              "| py:", (r.get("py") or {}).get("error") or ((r.get("py") or {}).get("wav_len"), (r.get("py") or {}).get("duration")))
 
 
 def main():
