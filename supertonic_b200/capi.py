@@ -87,6 +87,12 @@ class StcError(RuntimeError):
         self.code = code
 
 
+def _err(h) -> str:
+    """The library's message for the last failure; bytes taken from a graph file (node / tensor names of a corrupted .onnx) may not be UTF-8."""
+    m = lib.stc_last_error(h)
+    return m.decode("utf-8", "replace") if m else ""
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(_vp)
 
@@ -117,7 +123,7 @@ def _texts_to_ids(fn, handle, texts: Sequence, langs: Sequence[str]) -> Tuple[np
             continue
         break
     if rc != STC_OK:
-        raise StcError(rc, lib.stc_last_error(None).decode())
+        raise StcError(rc, _err(None))
     return np.ascontiguousarray(ids[:, :T.value]), np.ascontiguousarray(mask[:, :, :T.value])
 
 
@@ -135,7 +141,7 @@ def chunk_text(text, max_len: int) -> List[bytes]:
             parts = buf.raw[:need.value].split(b"\0")[:-1]
             return parts[:n.value] if n.value else [b""]
         if rc != ERR_CAPACITY:
-            raise StcError(rc, lib.stc_last_error(None).decode())
+            raise StcError(rc, _err(None))
         cap = need.value + 16
 
 
@@ -145,11 +151,11 @@ def derive_arch(onnx_path: str, kind: str) -> dict:
     need = C.c_size_t(0)
     lib.stc_derive_arch(_b(onnx_path), _b(kind), None, 0, C.byref(need))
     if not need.value:
-        raise StcError(-4, lib.stc_last_error(None).decode())
+        raise StcError(-4, _err(None))
     buf = C.create_string_buffer(need.value + 16)
     rc = lib.stc_derive_arch(_b(onnx_path), _b(kind), buf, need.value + 16, C.byref(need))
     if rc != STC_OK:
-        raise StcError(rc, lib.stc_last_error(None).decode())
+        raise StcError(rc, _err(None))
     return json.loads(buf.value.decode())
 
 
@@ -160,7 +166,7 @@ class Frontend:
         self._h = _vp()
         rc = lib.stc_frontend_open(_b(unicode_indexer_json), C.byref(self._h))
         if rc != STC_OK:
-            raise StcError(rc, lib.stc_last_error(None).decode())
+            raise StcError(rc, _err(None))
 
     def __call__(self, texts, langs):
         return _texts_to_ids(lib.stc_frontend_text_to_ids, self._h, texts, langs)
@@ -183,7 +189,7 @@ class Engine:
         rc = lib.stc_create(_b(onnx_dir), device, precision, C.byref(self._h))
         if rc != STC_OK:
             self._h = None
-            raise StcError(rc, lib.stc_last_error(None).decode())
+            raise StcError(rc, _err(None))
         self.cfg = StcConfig()
         lib.stc_get_config(self._h, C.byref(self.cfg))
         self.onnx_dir = onnx_dir
@@ -214,7 +220,7 @@ class Engine:
             ptr = _vp()
             rc = lib.stc_pinned_alloc(n * dt.itemsize, C.byref(ptr))
             if rc != STC_OK:
-                raise StcError(rc, lib.stc_last_error(None).decode())
+                raise StcError(rc, _err(None))
             buf = (C.c_char * (n * dt.itemsize)).from_address(ptr.value)
             cur = (np.frombuffer(buf, dtype=dt, count=n), ptr)
             self._pinned[name] = cur
@@ -222,7 +228,7 @@ class Engine:
 
     def _chk(self, rc):
         if rc != STC_OK:
-            raise StcError(rc, lib.stc_last_error(self._h).decode())
+            raise StcError(rc, _err(self._h))
 
     def _check(self, B, T=None, ttl=None, dp=None, mask=None, ids=None):
         """Shapes against the engine's geometry before bare pointers cross the C ABI (ORT raises at the same boundary)."""
@@ -435,7 +441,7 @@ class Engine:
         rc = lib.stc_synthesize_packed_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, _ptr(tl), B, T, int(total_step), float(speed),
                                               seed, wav_ptr, wav_cap, _ptr(off), dur_ptr)
         if rc != STC_OK:
-            e = StcError(rc, lib.stc_last_error(self._h).decode())
+            e = StcError(rc, _err(self._h))
             e.need = int(off[B])
             raise e
         return off
@@ -448,7 +454,7 @@ class Engine:
         rc = lib.stc_synthesize_device(self._h, ids_ptr, mask_ptr, sttl_ptr, sdp_ptr, B, T, int(total_step), float(speed),
                                        seed, wav_ptr, wav_ld, dur_ptr, C.byref(L))
         if rc != STC_OK:
-            e = StcError(rc, lib.stc_last_error(self._h).decode())
+            e = StcError(rc, _err(self._h))
             e.L = L.value
             raise e
         return L.value

@@ -102,7 +102,8 @@ private:
         const OnnxTensor& t = init(v);
         if (t.dtype != 7) throw PlanError("expected an int64 constant at '" + v + "'");
         std::vector<int64_t> r(t.numel());
-        memcpy(r.data(), t.raw.data(), r.size() * 8);
+        if (t.raw.size() != r.size() * 8) throw PlanError("int64 constant '" + v + "' has a payload of the wrong size");
+        if (!r.empty()) memcpy(r.data(), t.raw.data(), r.size() * 8);
         return r;
     }
     // every node between `y` and the values in `stops` (exclusive) is explained by the layer that ends in y
@@ -152,9 +153,25 @@ private:
         if ((int)init(l.b).numel() != l.N) fail(std::string(what) + ": bias length", l.b);
         return l;
     }
+    static float attr_f(const OnnxNode& n, const char* k, float dflt) { auto it = n.attr.find(k); return it == n.attr.end() ? dflt : it->second.f; }
+    // the `perm` of a Transpose the kernels' fixed layouts stand for: {0,2,1} (NCL <-> NLC), {0,2,1,3} (head split / merge),
+    // {0,1,3,2} (K^T), {0,2,3,1} (the vocoder's un-compress); anything else computes something else
+    void check_perm(int t, std::initializer_list<int64_t> want, const char* what) const {
+        auto it = N(t).attr.find("perm");
+        if (it == N(t).attr.end() || it->second.ints.size() != want.size() || !std::equal(want.begin(), want.end(), it->second.ints.begin()))
+            fail(std::string(what) + ": unexpected Transpose perm", N(t).out[0]);
+    }
+    // a Transpose consuming v with the given perm (-1 if none) / required
+    int needT(const std::string& v, std::initializer_list<int64_t> want, const char* what) const {
+        int t = need(v, "Transpose", what);
+        check_perm(t, want, what);
+        return t;
+    }
     // exact GELU as exported for opset < 20: Mul(Mul(x, Add(Erf(Div(x, sqrt2)), 1)), 0.5)
     std::string gelu(const std::string& v) const {
-        int d = need(v, "Div", "GELU");
+        int d = consumer(v, "Div", [&](const OnnxNode& n) { return n.in[0] == v; });           // x / sqrt2, not sqrt2 / x
+        if (d < 0) fail("GELU: no Div(x, sqrt2) consumes it", v);
+        if (std::fabs(scalar(N(d).in[1]) - 1.41421356f) > 1e-5f) fail("GELU: divisor is not sqrt(2)", v);
         int e = need(N(d).out[0], "Erf", "GELU");
         int a = need(N(e).out[0], "Add", "GELU");
         int m1 = consumer(v, "Mul", [&](const OnnxNode& n) { return other(n, v) == N(a).out[0]; });
@@ -167,6 +184,9 @@ private:
     struct LN { std::string g, b, out; };
     LN layernorm(const std::string& v, const char* what) const {
         int n = need(v, "LayerNormalization", what);
+        // the kernels normalise over the last (channel) axis with epsilon 1e-6; the ONNX default is 1e-5
+        if (std::fabs(attr_f(N(n), "epsilon", 1e-5f) - 1e-6f) > 1e-9f) fail(std::string(what) + ": LayerNormalization epsilon is not 1e-6", v);
+        if (N(n).attr_i("axis", -1) != -1 && N(n).attr_i("axis", -1) != 2) fail(std::string(what) + ": LayerNormalization axis is not the last one", v);
         LN l; l.g = N(n).in[1]; l.b = N(n).in[2]; l.out = N(n).out[0];
         init(l.g); init(l.b);
         return l;
@@ -201,7 +221,7 @@ private:
         else if (pads[0] == span / 2) causal = false;
         else fail("depthwise Conv padding is neither causal nor centred", x);
         if (c.in.size() < 3) fail("depthwise Conv without bias", x);
-        int t1 = need(c.out[0], "Transpose", "ConvNeXt");
+        int t1 = needT(c.out[0], {0, 2, 1}, "ConvNeXt");
         LN ln = layernorm(N(t1).out[0], "ConvNeXt LayerNorm");
         Lin l1 = linear(ln.out, "ConvNeXt pw1");
         std::string g = gelu(l1.out);
@@ -209,7 +229,7 @@ private:
         int mg = consumer(l2.out, "Mul", [&](const OnnxNode& n) { return is_init(other(n, l2.out)); });
         if (mg < 0) fail("ConvNeXt layer scale", l2.out);
         const std::string gamma = other(N(mg), l2.out);
-        int t2 = need(N(mg).out[0], "Transpose", "ConvNeXt");
+        int t2 = needT(N(mg).out[0], {0, 2, 1}, "ConvNeXt");
         int ad = consumer(N(t2).out[0], "Add", [&](const OnnxNode& n) { return other(n, N(t2).out[0]) == x0; });
         if (ad < 0) fail("ConvNeXt residual Add", N(t2).out[0]);
         std::string y = N(ad).out[0];
@@ -234,19 +254,61 @@ private:
         auto shp = ints(N(r).in[1]);
         if (shp.size() != 4) fail("attention head split shape", v);
         heads = (int)shp[2]; dh = (int)shp[3];
-        return N(need(N(r).out[0], "Transpose", "attention head split")).out[0];
+        return N(needT(N(r).out[0], {0, 2, 1, 3}, "attention head split")).out[0];
     }
     struct Rope { std::string kind = "none", freqs; };
     // forward through an optional rotary chain starting at the split value t; returns the value that enters Q.K^T
-    std::string through_rope(const std::string& t, Rope& rp) const {
+    std::string through_rope(const std::string& t, Rope& rp, int dh) const {
         int s1 = consumer(t, "Slice");
         if (s1 < 0) return t;
-        // r1 = Sub(Mul(t1, cos), Mul(t2, sin)); Concat(r1, r2)
+        // Concat(r1, r2) reached through either half
         int m = need(N(s1).out[0], "Mul", "rotary");
         int nx = consumer(N(m).out[0], "Sub"); if (nx < 0) nx = need(N(m).out[0], "Add", "rotary");
         int cc = need(N(nx).out[0], "Concat", "rotary");
-        // cos / sin <- Mul(pos, freqs)
-        const std::string& trig = other(N(m), N(s1).out[0]);
+        rp = verify_rope(cc, t, dh);
+        return N(cc).out[0];
+    }
+    // The whole rotate-half pattern behind a Concat, operand by operand (other rotary variants — interleaved pairs, a different sign
+    // convention — are refused, not approximated):
+    //   t1 = Slice(t, 0, dh/2, axis 3), t2 = Slice(t, dh/2, dh, axis 3); c = Cos(a), s = Sin(a) of ONE angle a = pos * freqs
+    //   Concat(axis 3)( Sub(Mul(t1, c), Mul(t2, s)),  Add(Mul(t1, s), Mul(t2, c)) )
+    Rope verify_rope(int cc, const std::string& t, int dh) const {
+        const OnnxNode& c = N(cc);
+        const int64_t cax = c.attr_i("axis", 0);
+        if (c.in.size() != 2 || (cax != 3 && cax != -1)) fail("rotary: Concat of two halves along the head dimension expected", c.out[0]);
+        struct Term { std::string slice, trig, angle; int mul; };
+        auto term = [&](const std::string& v) {
+            Term r; r.mul = need_prod(v, "Mul", "rotary");
+            for (int k = 0; k < 2; ++k) {
+                int ps = producer(N(r.mul).in[k]), pt = producer(N(r.mul).in[1 - k]);
+                if (ps >= 0 && N(ps).op == "Slice" && pt >= 0 && (N(pt).op == "Cos" || N(pt).op == "Sin")) {
+                    r.slice = N(r.mul).in[k]; r.trig = N(pt).op; r.angle = N(pt).in[0];
+                    return r;
+                }
+            }
+            fail("rotary: expected Mul(Slice, Cos | Sin)", v);
+        };
+        int sb = need_prod(c.in[0], "Sub", "rotary"), ad = need_prod(c.in[1], "Add", "rotary");
+        Term a0 = term(N(sb).in[0]), a1 = term(N(sb).in[1]), b0 = term(N(ad).in[0]), b1 = term(N(ad).in[1]);
+        if (b0.trig == "Cos") std::swap(b0, b1);                                 // Add commutes: b0 = t1 * sin, b1 = t2 * cos
+        if (a0.trig != "Cos" || a1.trig != "Sin" || b0.trig != "Sin" || b1.trig != "Cos" || a0.slice != b0.slice || a1.slice != b1.slice ||
+            a0.slice == a1.slice || a0.angle != a1.angle || a0.angle != b0.angle || a0.angle != b1.angle)
+            fail("rotary: expected Sub(t1 cos, t2 sin) and Add(t1 sin, t2 cos) of one angle", c.out[0]);
+        auto slice_ok = [&](const std::string& v, int64_t lo, int64_t hi_min) {
+            const OnnxNode& sl = N(producer(v));
+            if (sl.in.size() < 4 || sl.in[0] != t) return false;
+            auto st = ints(sl.in[1]), en = ints(sl.in[2]), ax = ints(sl.in[3]);
+            if (sl.in.size() > 4 && !sl.in[4].empty()) { auto sp = ints(sl.in[4]); if (sp.size() != 1 || sp[0] != 1) return false; }
+            return st.size() == 1 && en.size() == 1 && ax.size() == 1 && st[0] == lo && en[0] >= hi_min && (lo == 0 ? en[0] == hi_min : true) &&
+                   (ax[0] == 3 || ax[0] == -1);
+        };
+        if (dh % 2 || !slice_ok(a0.slice, 0, dh / 2) || !slice_ok(a1.slice, dh / 2, dh)) fail("rotary: halves are not t[..., :dh/2] and t[..., dh/2:]", t);
+        return rope_of(a0.mul, a0.slice);
+    }
+    // the rotary parameters behind Mul(slice, cos|sin): cos / sin <- Mul(pos, freqs), pos <- Unsqueeze(cumsum(mask) - 1 [/ sum(mask)])
+    Rope rope_of(int m, const std::string& slice_value) const {
+        Rope rp;
+        const std::string& trig = other(N(m), slice_value);
         int tg = producer(trig);
         if (tg < 0 || (N(tg).op != "Cos" && N(tg).op != "Sin")) fail("rotary: expected Cos / Sin", trig);
         int ang = need_prod(N(tg).in[0], "Mul", "rotary angle");
@@ -256,23 +318,35 @@ private:
         const std::string& pos = is_init(a0) ? a1 : a0;
         int un = need_prod(pos, "Unsqueeze", "rotary positions");
         int pp = producer(N(un).in[0]);
-        if (pp >= 0 && N(pp).op == "Div") rp.kind = "norm";                    // positions / sequence length (length-aware RoPE)
-        else if (pp >= 0 && N(pp).op == "Sub") rp.kind = "abs";                // cumsum(mask) - 1
+        auto is_cumsum_minus_1 = [&](int sb) {                                  // Sub(CumSum(mask), 1), in this operand order
+            if (sb < 0 || N(sb).op != "Sub" || !is_init(N(sb).in[1]) || std::fabs(scalar(N(sb).in[1]) - 1.0f) > 1e-6f) return false;
+            int cs = producer(N(sb).in[0]);
+            return cs >= 0 && N(cs).op == "CumSum";
+        };
+        if (pp >= 0 && N(pp).op == "Div") {                                     // positions / sequence length (length-aware RoPE)
+            int len = producer(N(pp).in[1]);
+            if (!is_cumsum_minus_1(producer(N(pp).in[0])) || len < 0 || N(len).op != "ReduceSum")
+                fail("rotary positions: expected (cumsum(mask) - 1) / sum(mask)", pos);
+            rp.kind = "norm";
+        } else if (is_cumsum_minus_1(pp)) rp.kind = "abs";                      // cumsum(mask) - 1
         else fail("rotary positions are neither cumsum(mask) - 1 nor that divided by the length", pos);
-        return N(cc).out[0];
+        return rp;
     }
     // backward from the value entering a MatMul to the projection (MatMul + Add) that made it: undo rotary, head split
-    int back_to_projection(std::string v, const char* what) const {
+    int back_to_projection(std::string v, const char* what, int dh, Rope* rope = nullptr) const {
         int p = producer(v);
         if (p >= 0 && N(p).op == "Concat") {                                   // rotary: Concat(Sub(Mul(Slice(t),..),..), ..)
             int sb = need_prod(N(p).in[0], "Sub", what);
             int ml = need_prod(N(sb).in[0], "Mul", what);
             int sl = producer(N(ml).in[0]);
             if (sl < 0 || N(sl).op != "Slice") sl = need_prod(N(ml).in[1], "Slice", what);
+            Rope r = verify_rope(p, N(sl).in[0], dh);
+            if (rope) *rope = r;
             v = N(sl).in[0];
             p = producer(v);
         }
         if (p < 0 || N(p).op != "Transpose") fail(std::string(what) + ": expected the head-split Transpose", v);
+        check_perm(p, {0, 2, 1, 3}, what);
         int r = need_prod(N(p).in[0], "Reshape", what);
         int a = need_prod(N(r).in[0], "Add", what);
         const std::string& mmv = is_init(N(a).in[0]) ? N(a).in[1] : N(a).in[0];
@@ -281,6 +355,7 @@ private:
     json attention(std::string& x) {
         const std::string x0 = x;
         int t0 = consumer(x, "Transpose");
+        check_perm(t0, {0, 2, 1}, "attention input");
         LN ln = layernorm(N(t0).out[0], "attention pre-LayerNorm");
         // q: the projection of LN(x) whose split (and rotated) output is the FIRST operand of a MatMul with a transposed second operand
         int score = -1, heads = 0, dh = 0; Lin q; Rope rq;
@@ -288,14 +363,18 @@ private:
             if (N(m).op != "MatMul" || N(m).in[0] != ln.out || !is_init(N(m).in[1])) continue;
             Lin cand = linear_at(m, "attention projection");
             int h = 0, d = 0; Rope r;
-            std::string qs = through_rope(split_heads(cand.out, h, d), r);
+            const std::string sp = split_heads(cand.out, h, d);
+            std::string qs = through_rope(sp, r, d);
             int mm = consumer(qs, "MatMul", [&](const OnnxNode& n) { int pt = producer(n.in[1]); return n.in[0] == qs && pt >= 0 && N(pt).op == "Transpose"; });
             if (mm >= 0) { score = mm; q = cand; heads = h; dh = d; rq = r; break; }
         }
         if (score < 0) fail("attention: no Q.K^T product found", ln.out);
         const int C = q.N;
         int kt = producer(N(score).in[1]);
-        int mk = back_to_projection(N(kt).in[0], "attention K");
+        check_perm(kt, {0, 1, 3, 2}, "attention K^T");
+        Rope rk;
+        int mk = back_to_projection(N(kt).in[0], "attention K", dh, &rk);
+        if (rk.kind != rq.kind || rk.freqs != rq.freqs) fail("attention: Q and K carry different rotary embeddings", N(kt).in[0]);
         Lin k = linear_at(mk, "attention K");
         const std::string ctx_src = N(mk).in[0];
         // scale, optional key mask, softmax, P.V
@@ -305,16 +384,25 @@ private:
         std::string s = N(sc).out[0];
         bool key_masked = false;
         int mb = consumer(s, "Add");
-        if (mb >= 0) { key_masked = true; s = N(mb).out[0]; }
+        if (mb >= 0) {
+            // the additive key mask: Unsqueeze(Mul(Sub(mask, 1), big)) — masked keys get -big, in this operand order
+            int un = need_prod(other(N(mb), s), "Unsqueeze", "attention key mask");
+            int ml = need_prod(N(un).in[0], "Mul", "attention key mask");
+            const std::string& big = is_init(N(ml).in[0]) ? N(ml).in[0] : N(ml).in[1];
+            int sb = need_prod(other(N(ml), big), "Sub", "attention key mask");
+            if (scalar(big) < 1e4f || !is_input(N(sb).in[0]) || !is_init(N(sb).in[1]) || std::fabs(scalar(N(sb).in[1]) - 1.0f) > 1e-6f)
+                fail("attention key mask is not (mask - 1) * big", N(mb).out[0]);
+            key_masked = true; s = N(mb).out[0];
+        }
         int sm = need(s, "Softmax", "attention");
         int pv = need(N(sm).out[0], "MatMul", "attention P.V");
-        int mv = back_to_projection(N(pv).in[1], "attention V");
+        int mv = back_to_projection(N(pv).in[1], "attention V", dh);
         Lin v = linear_at(mv, "attention V");
         if (N(mv).in[0] != ctx_src) fail("attention K and V read different contexts", N(mv).in[0]);
-        int t1 = need(N(pv).out[0], "Transpose", "attention merge");
+        int t1 = needT(N(pv).out[0], {0, 2, 1, 3}, "attention merge");
         int r1 = need(N(t1).out[0], "Reshape", "attention merge");
         Lin o = linear(N(r1).out[0], "attention output projection");
-        int t2 = need(o.out, "Transpose", "attention");
+        int t2 = needT(o.out, {0, 2, 1}, "attention");
         int ad = consumer(N(t2).out[0], "Add", [&](const OnnxNode& n) { return other(n, N(t2).out[0]) == x0; });
         if (ad < 0) fail("attention residual Add", N(t2).out[0]);
         std::string y = N(ad).out[0];
@@ -326,7 +414,7 @@ private:
         else if (is_input(ctx_src)) { ctx = ctx_src; }
         else {
             int tp = producer(ctx_src);
-            if (tp >= 0 && N(tp).op == "Transpose" && is_input(N(tp).in[0])) ctx = N(tp).in[0];
+            if (tp >= 0 && N(tp).op == "Transpose" && is_input(N(tp).in[0])) { check_perm(tp, {0, 2, 1}, "attention context"); ctx = N(tp).in[0]; }
             else fail("attention context is neither LN(x), a graph input nor its transpose", ctx_src);
         }
         if (ctx != "self" && ctx != "text_emb" && ctx != "style_ttl") fail("attention context input '" + ctx + "' is not text_emb / style_ttl", ctx_src);
@@ -348,7 +436,7 @@ private:
         const OnnxTensor& e = init(emb_name);
         if (e.dims.size() != 2) fail("embedding table rank", emb_name);
         V = (int)e.dims[0]; C = (int)e.dims[1];
-        int t = need(N(g).out[0], "Transpose", "embedding");
+        int t = needT(N(g).out[0], {0, 2, 1}, "embedding");
         std::string x = N(t).out[0];
         if (!masked_tail(x)) fail("embedding is not masked", x);
         mark_cone(x, {});
@@ -409,7 +497,7 @@ private:
         x = y;
         trunk(x, layers);
         // head: Transpose -> LN -> MatMul + Add -> Clip -> Exp -> Mul(sec per token) -> Transpose -> Mul(mask) -> ReduceSum
-        int t = need(x, "Transpose", "duration head");
+        int t = needT(x, {0, 2, 1}, "duration head");
         LN ln = layernorm(N(t).out[0], "duration head");
         Lin pj = linear(ln.out, "duration head projection");
         if (pj.N != 1) fail("duration head projection must map to one value per token", pj.w);
@@ -419,7 +507,7 @@ private:
         int ex = need(N(cl).out[0], "Exp", "duration head");
         int ms = need(N(ex).out[0], "Mul", "duration head");
         const float spt = scalar(other(N(ms), N(ex).out[0]));
-        int t2 = need(N(ms).out[0], "Transpose", "duration head");
+        int t2 = needT(N(ms).out[0], {0, 2, 1}, "duration head");
         std::string d = N(t2).out[0];
         if (!masked_tail(d)) fail("duration head without the mask multiply", d);
         int rsum = need(d, "ReduceSum", "duration head");
@@ -440,9 +528,9 @@ private:
         trunk(x, layers);
         // proj_out: Transpose -> MatMul + Add -> Transpose -> Mul(mask)
         const std::string x0 = x;
-        int t = need(x, "Transpose", "text encoder output projection");
+        int t = needT(x, {0, 2, 1}, "text encoder output projection");
         Lin pj = linear(N(t).out[0], "text encoder output projection");
-        int t2 = need(pj.out, "Transpose", "text encoder output projection");
+        int t2 = needT(pj.out, {0, 2, 1}, "text encoder output projection");
         std::string y = N(t2).out[0];
         if (!masked_tail(y)) fail("text_emb is not masked", y);
         int idn = consumer(y, "Identity"); if (idn >= 0) y = N(idn).out[0];
@@ -482,8 +570,9 @@ private:
         // proj_in: Transpose(noisy_latent) -> MatMul + Add -> Transpose -> Mul(latent_mask)
         int t = consumer("noisy_latent", "Transpose");
         if (t < 0) throw PlanError("vector_estimator: noisy_latent is not transposed into the input projection");
+        check_perm(t, {0, 2, 1}, "input projection");
         Lin pi = linear(N(t).out[0], "input projection");
-        int t2 = need(pi.out, "Transpose", "input projection");
+        int t2 = needT(pi.out, {0, 2, 1}, "input projection");
         std::string x = N(t2).out[0];
         if (!masked_tail(x)) fail("input projection is not masked", x);
         mark_cone(x, {});
@@ -491,9 +580,9 @@ private:
         trunk(x, layers, te);
         // proj_out + in-graph Euler update: y = (noisy_latent + Transpose(linear(Transpose(x))) * (1 / total_step)) * latent_mask
         const std::string x0 = x;
-        int t3 = need(x, "Transpose", "output projection");
+        int t3 = needT(x, {0, 2, 1}, "output projection");
         Lin po = linear(N(t3).out[0], "output projection");
-        int t4 = need(po.out, "Transpose", "output projection");
+        int t4 = needT(po.out, {0, 2, 1}, "output projection");
         int ms = need(N(t4).out[0], "Mul", "Euler update");
         {   // dt = Unsqueeze(Div(1, total_step))
             int ud = need_prod(other(N(ms), N(t4).out[0]), "Unsqueeze", "Euler step size");
@@ -532,7 +621,7 @@ private:
         auto s1 = ints(N(r1).in[1]);
         if (s1.size() != 4) fail("vocoder un-compress shape", N(ad).out[0]);
         const int f = (int)s1[1], ld = (int)s1[2];
-        int tp = need(N(r1).out[0], "Transpose", "vocoder un-compress");
+        int tp = needT(N(r1).out[0], {0, 2, 3, 1}, "vocoder un-compress");
         int r2 = need(N(tp).out[0], "Reshape", "vocoder un-compress");
         // conv_in: Conv(group = 1, causal) -> BatchNormalization
         int cv = need(N(r2).out[0], "Conv", "vocoder input convolution");
@@ -542,14 +631,16 @@ private:
         const int C = (int)w.dims[0], K = (int)w.dims[2];
         auto it = c.attr.find("pads");
         if (it == c.attr.end() || it->second.ints.size() != 2 || it->second.ints[0] != K - 1 || it->second.ints[1] != 0) fail("vocoder input convolution must be causal", c.in[1]);
+        for (const char* k : {"dilations", "strides"}) { auto a = c.attr.find(k); if (a != c.attr.end()) for (int64_t d : a->second.ints) if (d != 1) fail(std::string("vocoder input convolution: ") + k + " != 1", c.in[1]); }
         int bn = need(c.out[0], "BatchNormalization", "vocoder input normalisation");
+        if (std::fabs(attr_f(N(bn), "epsilon", 1e-5f) - 1e-5f) > 1e-9f) fail("vocoder input normalisation: BatchNormalization epsilon is not 1e-5", c.out[0]);
         std::string x = N(bn).out[0];
         mark_cone(x, {});
         layers.push_back(json{{"type", "conv_in"}, {"name", c.in[1]}, {"cin", ld}, {"cout", C}, {"K", K}, {"causal", true}, {"bn", N(bn).in[1]},
                               {"t", {{"w", c.in[1]}, {"b", c.in[2]}, {"bn_w", N(bn).in[1]}, {"bn_b", N(bn).in[2]}, {"bn_mean", N(bn).in[3]}, {"bn_var", N(bn).in[4]}}}});
         trunk(x, layers);
         const std::string x0 = x;
-        int t = need(x, "Transpose", "vocoder head");
+        int t = needT(x, {0, 2, 1}, "vocoder head");
         LN ln = layernorm(N(t).out[0], "vocoder head");
         Lin pj = linear(ln.out, "vocoder head projection");
         int rs = need(pj.out, "Reshape", "vocoder head");

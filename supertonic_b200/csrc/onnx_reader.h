@@ -25,9 +25,23 @@ struct OnnxAttr {                     // AttributeProto: the scalar / list kinds
     int64_t i = 0; float f = 0.f; std::string s;
     std::vector<int64_t> ints;
 };
+// Input / output names of a node with CHECKED indexing: the pattern matcher (graph_plan.h) reads `n.in[1]`, `n.out[0]` of nodes it has
+// identified by op type only — a damaged or unusual file (a MatMul with one input, a node without outputs) must end in an error, not
+// in an out-of-bounds read.
+struct OnnxNames : std::vector<std::string> {
+    using std::vector<std::string>::vector;
+    const std::string& operator[](size_t i) const {
+        if (i >= size()) throw std::runtime_error("ONNX node has no input / output #" + std::to_string(i));
+        return std::vector<std::string>::operator[](i);
+    }
+    std::string& operator[](size_t i) {
+        if (i >= size()) throw std::runtime_error("ONNX node has no input / output #" + std::to_string(i));
+        return std::vector<std::string>::operator[](i);
+    }
+};
 struct OnnxNode {                     // NodeProto
     std::string op, name;
-    std::vector<std::string> in, out;
+    OnnxNames in, out;
     std::map<std::string, OnnxAttr> attr;
     int64_t attr_i(const std::string& k, int64_t dflt) const { auto it = attr.find(k); return it == attr.end() ? dflt : it->second.i; }
 };
@@ -55,7 +69,11 @@ struct Reader {
     bool ok() const { return p < end; }
     uint64_t varint() {
         uint64_t r = 0; int s = 0;
-        while (p < end) { uint8_t b = *p++; r |= uint64_t(b & 0x7F) << s; if (!(b & 0x80)) return r; s += 7; }
+        while (p < end) {
+            uint8_t b = *p++;
+            if (s >= 64) throw std::runtime_error("onnx: varint longer than 10 bytes");
+            r |= uint64_t(b & 0x7F) << s; if (!(b & 0x80)) return r; s += 7;
+        }
         throw std::runtime_error("onnx: truncated varint");
     }
     // returns field number; sets wire type; for wt==2 sets sub-reader

@@ -119,3 +119,118 @@ def test_engine_from_node_derived_plans_is_bit_identical(size):
             np.testing.assert_array_equal(ra["wavs"][k], rb["wavs"][k])
     finally:
         a.close(); b.close()
+
+
+def test_corrupted_graph_files_are_rejected_not_crashed_on(tmp_path):
+    """The ONNX reader and the node-pattern matcher on damaged files (truncated, bytes overwritten anywhere or in the first 4 KB of
+    headers / varints / lengths, spans deleted) of all four graphs: every file either yields a plan (the damage hit a weight payload) or is
+    refused with an StcError whose message survives non-UTF-8 bytes from the file. Runs in a child process: a crash of the native reader
+    would be a failed test, not a dead test session."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import os, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        from supertonic_b200 import capi, surrogate
+        root, td = surrogate.ensure_assets("tiny"), %r
+        rng = np.random.default_rng(7)
+        ok = rejected = 0
+        for kind in ("duration_predictor", "text_encoder", "vector_estimator", "vocoder"):
+            raw = open(os.path.join(root, "onnx", kind + ".onnx"), "rb").read()
+            for i in range(60):
+                b = bytearray(raw)
+                if i %% 4 == 0:
+                    b = b[:int(rng.integers(0, len(b)))]
+                elif i %% 4 == 1:
+                    for _ in range(int(rng.integers(1, 8))):
+                        b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+                elif i %% 4 == 2:
+                    for _ in range(int(rng.integers(1, 6))):
+                        b[int(rng.integers(0, min(len(b), 4096)))] = int(rng.integers(0, 256))
+                else:
+                    p = int(rng.integers(0, len(b)))
+                    del b[p:min(len(b), p + int(rng.integers(1, 64)))]
+                path = os.path.join(td, "g.onnx")
+                open(path, "wb").write(bytes(b))
+                try:
+                    capi.derive_arch(path, kind); ok += 1
+                except capi.StcError as e:
+                    assert str(e); rejected += 1
+        print("ok", ok, "rejected", rejected)
+    ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    _, ok, _, rejected = r.stdout.split()
+    assert int(ok) + int(rejected) == 240 and int(rejected) >= 100, r.stdout
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reversed_operands_of_non_commutative_nodes_are_rejected(tmp_path, kind):
+    """x / sqrt2 is not sqrt2 / x: every Sub, Div and MatMul of every graph with its two operands swapped (GELU's Div, the rotary
+    Sub(t1 cos, t2 sin), cumsum(mask) - 1 and its division by the length on the Q and the K side, the additive key mask (mask - 1) * big,
+    1 / total_step, current_step / total_step, every projection) must make the matcher refuse the graph — it computes something else."""
+    import copy
+    from supertonic_b200 import capi, onnx_lite as ol
+    base = ol.load_model(os.path.join(_assets("tiny"), "onnx", kind + ".onnx"))
+    base.metadata = {}
+    n = 0
+    for k, nd in enumerate(base.graph.nodes):
+        if nd.op_type not in ("Sub", "Div", "MatMul") or len(nd.inputs) != 2:
+            continue
+        m = copy.deepcopy(base)
+        m.graph.nodes[k].inputs = list(reversed(nd.inputs))
+        path = str(tmp_path / "rev.onnx")
+        ol.save_model(m, path)
+        with pytest.raises(capi.StcError):
+            capi.derive_arch(path, kind)
+        n += 1
+    assert n >= 7
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_every_node_matters(tmp_path, kind):
+    """Remove any single node — a rotary Slice, one of the four rotary products, the additive key mask, a Transpose — and the matcher
+    must refuse the graph: no node of a recognised layer is taken on trust. (The one removal that changes nothing is the Identity that
+    gives the graph output its name.)"""
+    import copy
+    from supertonic_b200 import capi, onnx_lite as ol
+    base = ol.load_model(os.path.join(_assets("tiny"), "onnx", kind + ".onnx"))
+    base.metadata = {}
+    accepted = []
+    for k, nd in enumerate(base.graph.nodes):
+        m = copy.deepcopy(base)
+        del m.graph.nodes[k]
+        path = str(tmp_path / "del.onnx")
+        ol.save_model(m, path)
+        try:
+            capi.derive_arch(path, kind)
+            accepted.append(nd.op_type)
+        except capi.StcError:
+            pass
+    assert accepted in ([], ["Identity"]), accepted
+
+
+def test_attribute_values_the_kernels_hard_code_are_checked(tmp_path):
+    """LayerNormalization epsilon (kernels: 1e-6; the ONNX default is 1e-5), BatchNormalization epsilon (1e-5, folded at load), Transpose
+    perms (fixed layouts), dilation of the vocoder's dense input convolution: a graph that differs is refused."""
+    import copy
+    from supertonic_b200 import capi, onnx_lite as ol
+
+    def mutated(kind, pick, change):
+        base = ol.load_model(os.path.join(_assets("tiny"), "onnx", kind + ".onnx"))
+        base.metadata = {}
+        hits = [n for n in base.graph.nodes if pick(n)]
+        assert hits
+        for i in range(len(hits)):
+            m = copy.deepcopy(base)
+            change([n for n in m.graph.nodes if pick(n)][i])
+            path = str(tmp_path / "attr.onnx")
+            ol.save_model(m, path)
+            with pytest.raises(capi.StcError):
+                capi.derive_arch(path, kind)
+    for kind in KINDS:
+        mutated(kind, lambda n: n.op_type == "LayerNormalization", lambda n: n.attrs.update(epsilon=1e-5))
+        mutated(kind, lambda n: n.op_type == "LayerNormalization", lambda n: n.attrs.pop("epsilon"))
+        mutated(kind, lambda n: n.op_type == "Transpose", lambda n: n.attrs.update(perm=list(range(len(n.attrs["perm"])))))
+    mutated("vocoder", lambda n: n.op_type == "BatchNormalization", lambda n: n.attrs.update(epsilon=1e-3))
+    mutated("vocoder", lambda n: n.op_type == "Conv" and n.attrs.get("group", 1) == 1, lambda n: n.attrs.update(dilations=[2]))
