@@ -43,6 +43,8 @@ public:
 
     json derive(const std::string& kind) {
         json arch;
+        // the one mask every masked stage of this graph multiplies by (the engine applies ITS mask wherever the plan says "masked")
+        mask_name_ = kind == "vector_estimator" ? "latent_mask" : "text_mask";
         if (kind == "duration_predictor") arch = duration_predictor();
         else if (kind == "text_encoder") arch = text_encoder();
         else if (kind == "vector_estimator") arch = vector_estimator();
@@ -60,6 +62,7 @@ private:
     std::unordered_map<std::string, int> prod_;
     std::set<std::string> inputs_;
     std::vector<char> used_;
+    std::string mask_name_;
 
     // ---- graph access
     const OnnxNode& N(int i) const { return f_.nodes[i]; }
@@ -195,6 +198,7 @@ private:
     bool masked_tail(std::string& y) const {
         int m = consumer(y, "Mul", [&](const OnnxNode& n) { return is_input(other(n, y)); });
         if (m < 0) return false;
+        if (other(N(m), y) != mask_name_) fail("masked by '" + other(N(m), y) + "', expected " + mask_name_, y);
         y = N(m).out[0];
         return true;
     }
@@ -390,7 +394,7 @@ private:
             int ml = need_prod(N(un).in[0], "Mul", "attention key mask");
             const std::string& big = is_init(N(ml).in[0]) ? N(ml).in[0] : N(ml).in[1];
             int sb = need_prod(other(N(ml), big), "Sub", "attention key mask");
-            if (scalar(big) < 1e4f || !is_input(N(sb).in[0]) || !is_init(N(sb).in[1]) || std::fabs(scalar(N(sb).in[1]) - 1.0f) > 1e-6f)
+            if (scalar(big) < 1e4f || N(sb).in[0] != "text_mask" || !is_init(N(sb).in[1]) || std::fabs(scalar(N(sb).in[1]) - 1.0f) > 1e-6f)
                 fail("attention key mask is not (mask - 1) * big", N(mb).out[0]);
             key_masked = true; s = N(mb).out[0];
         }

@@ -234,3 +234,22 @@ def test_attribute_values_the_kernels_hard_code_are_checked(tmp_path):
         mutated(kind, lambda n: n.op_type == "Transpose", lambda n: n.attrs.update(perm=list(range(len(n.attrs["perm"])))))
     mutated("vocoder", lambda n: n.op_type == "BatchNormalization", lambda n: n.attrs.update(epsilon=1e-3))
     mutated("vocoder", lambda n: n.op_type == "Conv" and n.attrs.get("group", 1) == 1, lambda n: n.attrs.update(dilations=[2]))
+
+
+def test_a_stage_masked_by_the_wrong_mask_is_rejected(tmp_path):
+    """The plan only says "masked"; the engine then multiplies by the latent mask in the vector estimator and by the text mask on the
+    text side. A graph that masks a latent-side stage with text_mask (or the attention keys with latent_mask) is not that graph."""
+    import copy
+    from supertonic_b200 import capi, onnx_lite as ol
+    base = ol.load_model(os.path.join(_assets("tiny"), "onnx", "vector_estimator.onnx"))
+    base.metadata = {}
+    swap = {"latent_mask": "text_mask", "text_mask": "latent_mask"}
+    hits = [k for k, n in enumerate(base.graph.nodes) if n.op_type in ("Mul", "Sub") and any(i in swap for i in n.inputs)]
+    assert len(hits) >= 6
+    for k in hits:
+        m = copy.deepcopy(base)
+        m.graph.nodes[k].inputs = [swap.get(i, i) for i in m.graph.nodes[k].inputs]
+        path = str(tmp_path / "mask.onnx")
+        ol.save_model(m, path)
+        with pytest.raises(capi.StcError):
+            capi.derive_arch(path, "vector_estimator")
