@@ -109,6 +109,17 @@ private:
         if (!r.empty()) memcpy(r.data(), t.raw.data(), r.size() * 8);
         return r;
     }
+    bool ints_are(const std::string& v, std::initializer_list<int64_t> want) const {
+        if (!is_init(v)) return false;
+        auto g = ints(v);
+        return g.size() == want.size() && std::equal(want.begin(), want.end(), g.begin());
+    }
+    // axes of an Unsqueeze / ReduceSum: second input (opset >= 13) or the `axes` attribute
+    bool axes_are(const OnnxNode& n, std::initializer_list<int64_t> want) const {
+        if (n.in.size() >= 2 && !n.in[1].empty()) return ints_are(n.in[1], want);
+        auto it = n.attr.find("axes");
+        return it != n.attr.end() && it->second.ints.size() == want.size() && std::equal(want.begin(), want.end(), it->second.ints.begin());
+    }
     // every node between `y` and the values in `stops` (exclusive) is explained by the layer that ends in y
     void mark_cone(const std::string& y, const std::set<std::string>& stops) {
         std::vector<std::string> st{y};
@@ -321,15 +332,18 @@ private:
         init(rp.freqs);
         const std::string& pos = is_init(a0) ? a1 : a0;
         int un = need_prod(pos, "Unsqueeze", "rotary positions");
+        if (!axes_are(N(un), {3})) fail("rotary positions: Unsqueeze axes != [3]", pos);
         int pp = producer(N(un).in[0]);
         auto is_cumsum_minus_1 = [&](int sb) {                                  // Sub(CumSum(mask), 1), in this operand order
             if (sb < 0 || N(sb).op != "Sub" || !is_init(N(sb).in[1]) || std::fabs(scalar(N(sb).in[1]) - 1.0f) > 1e-6f) return false;
             int cs = producer(N(sb).in[0]);
-            return cs >= 0 && N(cs).op == "CumSum";
+            return cs >= 0 && N(cs).op == "CumSum" && is_input(N(cs).in[0]) && (ints_are(N(cs).in[1], {2}) || ints_are(N(cs).in[1], {-1})) &&
+                   N(cs).attr_i("exclusive", 0) == 0 && N(cs).attr_i("reverse", 0) == 0;                 // along the sequence axis of mask [B,1,N]
         };
         if (pp >= 0 && N(pp).op == "Div") {                                     // positions / sequence length (length-aware RoPE)
             int len = producer(N(pp).in[1]);
-            if (!is_cumsum_minus_1(producer(N(pp).in[0])) || len < 0 || N(len).op != "ReduceSum")
+            if (!is_cumsum_minus_1(producer(N(pp).in[0])) || len < 0 || N(len).op != "ReduceSum" || !is_input(N(len).in[0]) ||
+                !(axes_are(N(len), {2}) || axes_are(N(len), {-1})) || N(len).attr_i("keepdims", 1) != 1)
                 fail("rotary positions: expected (cumsum(mask) - 1) / sum(mask)", pos);
             rp.kind = "norm";
         } else if (is_cumsum_minus_1(pp)) rp.kind = "abs";                      // cumsum(mask) - 1
@@ -337,7 +351,7 @@ private:
         return rp;
     }
     // backward from the value entering a MatMul to the projection (MatMul + Add) that made it: undo rotary, head split
-    int back_to_projection(std::string v, const char* what, int dh, Rope* rope = nullptr) const {
+    int back_to_projection(std::string v, const char* what, int heads, int dh, Rope* rope = nullptr) const {
         int p = producer(v);
         if (p >= 0 && N(p).op == "Concat") {                                   // rotary: Concat(Sub(Mul(Slice(t),..),..), ..)
             int sb = need_prod(N(p).in[0], "Sub", what);
@@ -352,6 +366,7 @@ private:
         if (p < 0 || N(p).op != "Transpose") fail(std::string(what) + ": expected the head-split Transpose", v);
         check_perm(p, {0, 2, 1, 3}, what);
         int r = need_prod(N(p).in[0], "Reshape", what);
+        if (!ints_are(N(r).in[1], {0, -1, heads, dh})) fail(std::string(what) + ": head split is not [0, -1, heads, dh]", v);
         int a = need_prod(N(r).in[0], "Add", what);
         const std::string& mmv = is_init(N(a).in[0]) ? N(a).in[1] : N(a).in[0];
         return need_prod(mmv, "MatMul", what);
@@ -377,7 +392,7 @@ private:
         int kt = producer(N(score).in[1]);
         check_perm(kt, {0, 1, 3, 2}, "attention K^T");
         Rope rk;
-        int mk = back_to_projection(N(kt).in[0], "attention K", dh, &rk);
+        int mk = back_to_projection(N(kt).in[0], "attention K", heads, dh, &rk);
         if (rk.kind != rq.kind || rk.freqs != rq.freqs) fail("attention: Q and K carry different rotary embeddings", N(kt).in[0]);
         Lin k = linear_at(mk, "attention K");
         const std::string ctx_src = N(mk).in[0];
@@ -391,6 +406,7 @@ private:
         if (mb >= 0) {
             // the additive key mask: Unsqueeze(Mul(Sub(mask, 1), big)) — masked keys get -big, in this operand order
             int un = need_prod(other(N(mb), s), "Unsqueeze", "attention key mask");
+            if (!axes_are(N(un), {1})) fail("attention key mask: Unsqueeze axes != [1]", s);
             int ml = need_prod(N(un).in[0], "Mul", "attention key mask");
             const std::string& big = is_init(N(ml).in[0]) ? N(ml).in[0] : N(ml).in[1];
             int sb = need_prod(other(N(ml), big), "Sub", "attention key mask");
@@ -400,11 +416,12 @@ private:
         }
         int sm = need(s, "Softmax", "attention");
         int pv = need(N(sm).out[0], "MatMul", "attention P.V");
-        int mv = back_to_projection(N(pv).in[1], "attention V", dh);
+        int mv = back_to_projection(N(pv).in[1], "attention V", heads, dh);
         Lin v = linear_at(mv, "attention V");
         if (N(mv).in[0] != ctx_src) fail("attention K and V read different contexts", N(mv).in[0]);
         int t1 = needT(N(pv).out[0], {0, 2, 1, 3}, "attention merge");
         int r1 = need(N(t1).out[0], "Reshape", "attention merge");
+        if (!ints_are(N(r1).in[1], {0, -1, (int64_t)heads * dh})) fail("attention merge is not [0, -1, heads * dh]", N(t1).out[0]);
         Lin o = linear(N(r1).out[0], "attention output projection");
         int t2 = needT(o.out, {0, 2, 1}, "attention");
         int ad = consumer(N(t2).out[0], "Add", [&](const OnnxNode& n) { return other(n, N(t2).out[0]) == x0; });
@@ -515,6 +532,7 @@ private:
         std::string d = N(t2).out[0];
         if (!masked_tail(d)) fail("duration head without the mask multiply", d);
         int rsum = need(d, "ReduceSum", "duration head");
+        if (!axes_are(N(rsum), {1, 2})) fail("duration head: ReduceSum over axes other than [1, 2]", d);
         std::string out = N(rsum).out[0];
         int idn = consumer(out, "Identity"); if (idn >= 0) out = N(idn).out[0];
         mark_cone(out, {x});

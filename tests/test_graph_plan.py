@@ -253,3 +253,40 @@ def test_a_stage_masked_by_the_wrong_mask_is_rejected(tmp_path):
         ol.save_model(m, path)
         with pytest.raises(capi.StcError):
             capi.derive_arch(path, "vector_estimator")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_small_constants_are_verified_or_carried_into_the_plan(tmp_path, kind):
+    """Every small constant of a graph (scalars, axes, shapes, slice bounds: <= 8 elements) changed by x 1.5 / + 1: the matcher must either
+    refuse the graph, or return a DIFFERENT plan (the value is carried: clip, seconds per token, heads, ...). What may pass unchanged is
+    only what cannot change the result: the end bound of the upper rotary Slice (clamped to the dimension), the size of the key-mask
+    constant (any large value masks), single-element weights (read by name at load), and broadcasting plumbing (Unsqueeze axes / Reshape
+    shapes whose other values make an invalid graph)."""
+    import copy
+    from supertonic_b200 import capi, onnx_lite as ol
+    base = ol.load_model(os.path.join(_assets("tiny"), "onnx", kind + ".onnx"))
+    base.metadata = {}
+    p0, p1 = str(tmp_path / "c0.onnx"), str(tmp_path / "c1.onnx")
+    ol.save_model(base, p0)
+    ref = capi.derive_arch(p0, kind)
+    used = {i for n in base.graph.nodes for i in n.inputs}
+    checked = 0
+    for name, a in base.graph.initializers.items():
+        if a.size > 8 or name not in used:
+            continue
+        m = copy.deepcopy(base)
+        m.graph.initializers[name] = ((a * 1.5 + (0.25 if np.all(a == 0) else 0)) if np.issubdtype(a.dtype, np.floating) else a + 1).astype(a.dtype)
+        ol.save_model(m, p1)
+        try:
+            same = capi.derive_arch(p1, kind) == ref
+        except capi.StcError:
+            same = False
+        checked += 1
+        if same:
+            ops = {n.op_type for n in base.graph.nodes if name in n.inputs}
+            assert ops <= {"Slice", "Mul", "Add", "Unsqueeze", "Reshape"}, (name, ops)
+            if "Mul" in ops:
+                assert a.size == 1 and float(a.reshape(-1)[0]) >= 1e4, name           # the key-mask constant
+            if "Slice" in ops:
+                assert all(n.inputs.index(name) == 2 for n in base.graph.nodes if name in n.inputs), name   # `ends` only
+    assert checked >= 9
